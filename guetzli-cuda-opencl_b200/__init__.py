@@ -1,0 +1,266 @@
+"""gzb200 -- B200-native (sm_100a CUDA) butteraugli-guided quantisation search for Guetzli.
+
+Thin ctypes binding over the C ABI of ``libgzb200.so`` (include/gzb200.h). The class and method
+names mirror the reference's operator interface for this path -- ``guetzli::Comparator`` /
+``ButteraugliComparator`` (guetzli/comparator.h:29-96, guetzli/butteraugli_comparator.h:33-83) and
+the ``cu*`` free functions (clguetzli/cuguetzli.h) -- so the parity tests read like the reference.
+
+There is NO CPU fallback: importing works without a GPU (so the symbol table can be checked), but
+every compute call fails loudly if the CUDA library or a device is missing. Nothing here imports
+or links anything under ``oracle/``.
+
+The directory name is not a Python identifier; load it with ``__graft_entry__.load_package()``
+(importlib, module name ``gzb200``).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgzb200.so")
+
+COEFF_DATA = np.dtype([("idx", np.int32), ("err", np.float32)])
+
+
+class GzbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Loads libgzb200.so (raises if it has not been built: no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GzbError("libgzb200.so is not built (run __graft_entry__.build()); "
+                           "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.gzb_version.restype = C.c_char_p
+        L.gzb_last_error.restype = C.c_char_p
+        L.gzb_last_error.argtypes = [C.c_void_p]
+        L.gzb_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float,
+                                 C.POINTER(C.c_void_p)]
+        L.gzb_destroy.argtypes = [C.c_void_p]
+        L.gzb_destroy.restype = None
+        L.gzb_score_output_size.restype = C.c_double
+        L.gzb_score_output_size.argtypes = [C.c_void_p, C.c_int]
+        L.gzb_block_error_limit.restype = C.c_float
+        L.gzb_block_error_limit.argtypes = [C.c_void_p]
+        L.gzb_distance_ok.argtypes = [C.c_void_p, C.c_double]
+        L.gzb_last_device_ms.restype = C.c_float
+        L.gzb_last_device_ms.argtypes = [C.c_void_p]
+        L.gzb_launch_count.restype = C.c_ulonglong
+        L.gzb_launch_count.argtypes = [C.c_void_p]
+        L.gzb_compute_block_error_adjustment_weights.argtypes = [
+            C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.gzb_blur.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_double, C.c_double]
+        L.gzb_opsin_dynamics_image.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_size_t, C.c_size_t]
+        L.gzb_diffmap_opsin_dynamics_image.argtypes = [C.c_int] + [C.c_void_p] * 7 + [C.c_size_t] * 3
+        L.gzb_butteraugli_srgb.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p]
+        L.gzb_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t,
+                                      C.POINTER(C.c_size_t)]
+        L.gzb_update_coeffs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        for name in ("gzb_set_jpeg_coeffs", "gzb_set_coeffs", "gzb_get_coeffs"):
+            getattr(L, name).argtypes = [C.c_void_p] * 4
+        for name in ("gzb_copy_from_jpeg", "gzb_apply_global_quantization", "gzb_to_srgb",
+                     "gzb_compare", "gzb_get_distmap", "gzb_compare_blocks"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
+        for name in ("gzb_start_block_comparisons", "gzb_finish_block_comparisons"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.gzb_get_block_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gzb_compute_block_zeroing_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _check(rc, ctx=None):
+    if rc != 0:
+        msg = lib().gzb_last_error(ctx).decode(errors="replace")
+        raise GzbError("gzb200 error %d: %s" % (rc, msg))
+
+
+def device_count():
+    return lib().gzb_device_count()
+
+
+class ButteraugliComparator:
+    """guetzli::ButteraugliComparator on a B200, with the candidate OutputImage held on the device.
+
+    Mirrors guetzli/butteraugli_comparator.h:33-83; the OutputImage methods the search driver
+    needs (CopyFromJpegData, ApplyGlobalQuantization, ToSRGB, SetCoeffBlock) are methods here
+    because the candidate lives in HBM next to the comparator state.
+    """
+
+    def __init__(self, width, height, rgb, target_distance, device=0):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        if rgb.size != width * height * 3:
+            raise ValueError("rgb must hold width*height*3 bytes")
+        self.width, self.height = int(width), int(height)
+        self.block_width, self.block_height = (width + 7) // 8, (height + 7) // 8
+        self.num_blocks = self.block_width * self.block_height
+        self.target_distance = np.float32(target_distance)
+        self._ctx = C.c_void_p()
+        _check(lib().gzb_create(device, width, height, _p(rgb), C.c_float(target_distance),
+                                C.byref(self._ctx)))
+        self.distance = np.float32(0.0)
+
+    def close(self):
+        if self._ctx:
+            lib().gzb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- candidate image ------------------------------------------------------------------
+    def SetJpegCoeffs(self, coeffs):
+        c = np.ascontiguousarray(coeffs, np.int16).reshape(3, self.num_blocks, 64)
+        _check(lib().gzb_set_jpeg_coeffs(self._ctx, _p(c[0]), _p(c[1]), _p(c[2])), self._ctx)
+
+    def CopyFromJpegData(self, quant=None):
+        q = np.ones(192, np.int32) if quant is None else np.ascontiguousarray(quant, np.int32).reshape(192)
+        _check(lib().gzb_copy_from_jpeg(self._ctx, _p(q)), self._ctx)
+
+    def ApplyGlobalQuantization(self, q):
+        q = np.ascontiguousarray(q, np.int32).reshape(192)
+        _check(lib().gzb_apply_global_quantization(self._ctx, _p(q)), self._ctx)
+
+    def SetCoeffs(self, coeffs):
+        c = np.ascontiguousarray(coeffs, np.int16).reshape(3, self.num_blocks, 64)
+        _check(lib().gzb_set_coeffs(self._ctx, _p(c[0]), _p(c[1]), _p(c[2])), self._ctx)
+
+    def GetCoeffs(self):
+        c = np.zeros((3, self.num_blocks, 64), np.int16)
+        _check(lib().gzb_get_coeffs(self._ctx, _p(c[0]), _p(c[1]), _p(c[2])), self._ctx)
+        return c
+
+    def UpdateCoeffs(self, block_ix, idx, val):
+        b = np.ascontiguousarray(block_ix, np.int32)
+        i = np.ascontiguousarray(idx, np.uint8)
+        v = np.ascontiguousarray(val, np.int16)
+        _check(lib().gzb_update_coeffs(self._ctx, _p(b), _p(i), _p(v), len(b)), self._ctx)
+
+    def ToSRGB(self):
+        out = np.zeros((self.height, self.width, 3), np.uint8)
+        _check(lib().gzb_to_srgb(self._ctx, _p(out)), self._ctx)
+        return out
+
+    # ---- Comparator interface -------------------------------------------------------------
+    def Compare(self):
+        d = C.c_float()
+        _check(lib().gzb_compare(self._ctx, C.byref(d)), self._ctx)
+        self.distance = np.float32(d.value)
+        return self.distance
+
+    def distmap(self):
+        out = np.zeros((self.height, self.width), np.float32)
+        _check(lib().gzb_get_distmap(self._ctx, _p(out)), self._ctx)
+        return out
+
+    def distmap_aggregate(self):
+        return self.distance
+
+    def DistanceOK(self, target_mul):
+        return bool(lib().gzb_distance_ok(self._ctx, float(target_mul)))
+
+    def ScoreOutputSize(self, size):
+        return lib().gzb_score_output_size(self._ctx, int(size))
+
+    def BlockErrorLimit(self):
+        return np.float32(lib().gzb_block_error_limit(self._ctx))
+
+    def StartBlockComparisons(self):
+        _check(lib().gzb_start_block_comparisons(self._ctx), self._ctx)
+
+    def FinishBlockComparisons(self):
+        _check(lib().gzb_finish_block_comparisons(self._ctx), self._ctx)
+
+    def BlockLists(self, want_opsin=True):
+        """(imgMaskXyzScaleBlockList [B,3], imgOpsinDynamicsBlockList [B,192])."""
+        ms = np.zeros((self.num_blocks, 3), np.float32)
+        ob = np.zeros((self.num_blocks, 192), np.float32) if want_opsin else None
+        _check(lib().gzb_get_block_lists(self._ctx, _p(ms), _p(ob) if want_opsin else None), self._ctx)
+        return ms, ob
+
+    def CompareBlocks(self):
+        """CompareBlock of every 8x8 block of the resident candidate (factor 1, comp_mask 7)."""
+        out = np.zeros(self.num_blocks, np.float32)
+        _check(lib().gzb_compare_blocks(self._ctx, _p(out)), self._ctx)
+        return out
+
+    def ComputeBlockZeroingOrder(self, comp_mask=7):
+        out = np.zeros((self.num_blocks, 192), COEFF_DATA)
+        _check(lib().gzb_compute_block_zeroing_order(self._ctx, comp_mask, _p(out)), self._ctx)
+        return out
+
+    def ComputeBlockErrorAdjustmentWeights(self, direction, max_block_dist, target_mul, distmap=None):
+        w = np.zeros(self.num_blocks, np.float32)
+        dm = None if distmap is None else np.ascontiguousarray(distmap, np.float32)
+        _check(lib().gzb_compute_block_error_adjustment_weights(
+            self._ctx, direction, max_block_dist, float(target_mul),
+            None if dm is None else _p(dm), _p(w)), self._ctx)
+        return w
+
+    # ---- debugging / measurement ----------------------------------------------------------
+    def debug_fetch(self, name):
+        n = C.c_size_t()
+        _check(lib().gzb_debug_fetch(self._ctx, name.encode(), None, 0, C.byref(n)), self._ctx)
+        out = np.zeros(n.value, np.float32)
+        _check(lib().gzb_debug_fetch(self._ctx, name.encode(), _p(out), out.size, C.byref(n)), self._ctx)
+        return out
+
+    def last_device_ms(self):
+        return float(lib().gzb_last_device_ms(self._ctx))
+
+    def launch_count(self):
+        return int(lib().gzb_launch_count(self._ctx))
+
+
+# ---- stage entry points (roles of the reference's cu* free functions) ----------------------
+def OpsinDynamicsImage(planes, device=0):
+    """cuOpsinDynamicsImage: planes [3,H,W] float32 linear rgb -> XYB (returns a new array)."""
+    a = np.ascontiguousarray(planes, np.float32).copy()
+    _, h, w = a.shape
+    _check(lib().gzb_opsin_dynamics_image(device, _p(a[0]), _p(a[1]), _p(a[2]), w, h))
+    return a
+
+
+def DiffmapOpsinDynamicsImage(xyb0, xyb1, device=0):
+    """cuDiffmapOpsinDynamicsImage: two [3,H,W] XYB images -> diffmap [H,W]."""
+    a = np.ascontiguousarray(xyb0, np.float32)
+    b = np.ascontiguousarray(xyb1, np.float32)
+    _, h, w = a.shape
+    out = np.zeros((h, w), np.float32)
+    _check(lib().gzb_diffmap_opsin_dynamics_image(device, _p(out), _p(a[0]), _p(a[1]), _p(a[2]),
+                                                  _p(b[0]), _p(b[1]), _p(b[2]), w, h, 3))
+    return out
+
+
+def Blur(plane, sigma, border_ratio=0.0, device=0):
+    a = np.ascontiguousarray(plane, np.float32).copy()
+    h, w = a.shape
+    _check(lib().gzb_blur(device, _p(a), w, h, float(sigma), float(border_ratio)))
+    return a
+
+
+def ButteraugliSrgb(rgb0, rgb1, want_diffmap=True, device=0):
+    a = np.ascontiguousarray(rgb0, np.uint8)
+    b = np.ascontiguousarray(rgb1, np.uint8)
+    h, w = a.shape[:2]
+    d = C.c_float()
+    dm = np.zeros((h, w), np.float32) if want_diffmap else None
+    _check(lib().gzb_butteraugli_srgb(device, _p(a), _p(b), w, h, C.byref(d),
+                                      _p(dm) if want_diffmap else None))
+    return np.float32(d.value), dm

@@ -1,0 +1,826 @@
+// gzb200.cu -- context, plans and the C ABI (include/gzb200.h) over the sm_100a kernels.
+// Single translation unit: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gzb200.h"
+#include "gzb_kernels.cuh"
+#include "gzb_zeroing.cuh"
+
+namespace gzb {
+
+// ---------------------------------------------------------------------------------------------
+// Host-side constants: blur kernels (butteraugli.cc:100-112), LUTs.
+// ---------------------------------------------------------------------------------------------
+enum BlurKind { kB11 = 0, kB15, kB0586, kB04, kB14, kB9657, kB14264, kB4533, kB8851, kBUser, kNumBlurKinds };
+static const double kSigmas[kNumBlurKinds] = {1.1, 1.5, 0.586, 0.4, 14.0, 9.65781083553,
+                                              14.2644604355, 4.53358927369, 8.8510880283, 0.0};
+struct HostKernel { int r, step; float taps[kMaxTaps]; };
+
+static bool make_host_kernel(double sigma, HostKernel* k) {
+  const double scaler = -1.0 / (2 * sigma * sigma);
+  k->r = std::max<int>(1, static_cast<int>(2.25 * std::fabs(sigma)));
+  if (2 * k->r + 1 > kMaxTaps) return false;
+  for (int i = -k->r; i <= k->r; ++i) k->taps[i + k->r] = static_cast<float>(std::exp(scaler * i * i));
+  k->step = std::max(1, static_cast<int>(sigma / 3));
+  return true;
+}
+
+// scale = 1 / interpolated in-range tap weight (butteraugli.cc:76-89) at position `pos` of a
+// line of `size` samples.
+static double border_scale(const HostKernel& k, int pos, int size, double border_ratio) {
+  double full = 0.0;
+  for (int j = 0; j <= 2 * k.r; ++j) full += k.taps[j];
+  const int lo = std::max(0, pos - k.r);
+  const int hi = std::min(size, pos + k.r + 1) - 1;
+  double w = 0.0;
+  for (int j = lo; j <= hi; ++j) w += k.taps[j - pos + k.r];
+  w = (1.0 - border_ratio) * w + border_ratio * full;
+  return 1.0 / w;
+}
+
+static HostKernel g_hk[kNumBlurKinds];
+static std::mutex g_init_mu;
+static bool g_dev_ready[64];
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      char buf_[512];                                                                   \
+      snprintf(buf_, sizeof(buf_), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      throw std::string(buf_);                                                          \
+    }                                                                                   \
+  } while (0)
+
+static void init_device_tables(int device) {
+  std::lock_guard<std::mutex> lock(g_init_mu);
+  if (device < 64 && g_dev_ready[device]) return;
+  for (int k = 0; k < kBUser; ++k) make_host_kernel(kSigmas[k], &g_hk[k]);
+  DeviceTables* t = new DeviceTables;
+  // 21-entry ramps built by repeated addition (butteraugli.cc:200-247)
+  const double first[3] = {11.38708334481672, 1.4103373714040413, 5.2511644570349185};
+  const double inc[3] = {14.550189611520716, 0.7084088867024, 5.2511644570349185};
+  for (int l = 0; l < 3; ++l) {
+    t->lut21[l][0] = 0.0;
+    t->lut21[l][1] = first[l];
+    for (int i = 2; i < 21; ++i) t->lut21[l][i] = t->lut21[l][i - 1] + inc[l];
+  }
+  // MakeMask (butteraugli.cc:1242-1254): {extmul, extoff, offset, scaler, mul}
+  static const double MP[6][5] = {
+      {0.975741017749, -4.25328244168, 0.454909521427, 0.0738288224836, 20.8029176447},
+      {0.373995618954, 1.5307267433, 0.911952641929, 1.1731667845, 16.2447033988},
+      {0.61582234137, -4.25376118646, 1.05105070921, 0.47434643535, 31.1444967089},
+      {1.79116943438, -3.86797479189, 0.670960225853, 0.486575865525, 20.4563479139},
+      {0.212223514236, -3.65647120524, 1.73396799447, 0.170392660501, 21.6566724788},
+      {0.349376011816, -0.894711072781, 0.901647926679, 0.380086095024, 18.0373825149}};
+  for (int m = 0; m < 6; ++m)
+    for (int i = 0; i < 512; ++i) {
+      const double c = MP[m][4] / ((0.01 * MP[m][3] * i) + MP[m][2]);
+      double v = 1.0 + MP[m][0] * (c + MP[m][1]);
+      v *= v;
+      t->mask_lut[m][i] = v;
+    }
+  // Srgb8ToLinearTable (guetzli/gamma_correct.cc:23-33), stored as the float the reference casts to
+  for (int i = 0; i < 256; ++i) {
+    const double v = i < 11 ? i / 12.92 : 255.0 * std::pow(((i / 255.0) + 0.055) / 1.055, 2.4);
+    t->srgb_lin[i] = static_cast<float>(v);
+  }
+  CK(cudaMemcpyToSymbol(g_tab, t, sizeof(DeviceTables)));
+  delete t;
+  float taps[12][kMaxTaps];
+  memset(taps, 0, sizeof(taps));
+  for (int k = 0; k < kBUser; ++k) memcpy(taps[k], g_hk[k].taps, sizeof(float) * (2 * g_hk[k].r + 1));
+  CK(cudaMemcpyToSymbol(c_taps, taps, sizeof(taps)));
+  float csf[192], bias[192];
+  for (int i = 0; i < 192; ++i) { csf[i] = kGzbZeroModel[i].csf; bias[i] = kGzbZeroModel[i].bias; }
+  CK(cudaMemcpyToSymbol(c_zero_csf, csf, sizeof(csf)));
+  CK(cudaMemcpyToSymbol(c_zero_bias, bias, sizeof(bias)));
+  double s8[8];
+  for (int x = 0; x < 8; ++x) s8[x] = border_scale(g_hk[kB11], x, 8, 0.0);
+  CK(cudaMemcpyToSymbol(c_scale8, s8, sizeof(s8)));
+  CK(cudaMemcpyToSymbol(c_taps11, g_hk[kB11].taps, 5 * sizeof(float)));
+  if (device < 64) g_dev_ready[device] = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Blur plans
+// ---------------------------------------------------------------------------------------------
+struct BlurPlan {
+  BlurGeom g{};
+  double* d_sx = nullptr;
+  double* d_sy = nullptr;
+  void build(const HostKernel& hk, int kind, int in_w, int in_h, int in_pitch, int x0, int sx, int nx,
+             int y0, int sy, int ny, double border_ratio, int ups) {
+    g.in_w = in_w; g.in_h = in_h; g.in_pitch = in_pitch; g.r = hk.r; g.kind = kind;
+    g.x0 = x0; g.sx = sx; g.nx = nx; g.y0 = y0; g.sy = sy; g.ny = ny;
+    g.tmp_pitch = round_up(std::max(nx, 1), 32); g.ups = ups;
+    g.oxn = std::max(1, std::min(kBhOx, (kBhMaxSpan - 2 * hk.r - 1) / sx + 1));
+    g.oyn = std::max(1, std::min(kBvOy, (kBvMaxRows - 2 * hk.r - 1) / sy + 1));
+    std::vector<double> vx(std::max(nx, 1)), vy(std::max(ny, 1));
+    for (int i = 0; i < nx; ++i) vx[i] = border_scale(hk, x0 + i * sx, in_w, border_ratio);
+    for (int i = 0; i < ny; ++i) vy[i] = border_scale(hk, y0 + i * sy, in_h, border_ratio);
+    CK(cudaMalloc(&d_sx, vx.size() * sizeof(double)));
+    CK(cudaMalloc(&d_sy, vy.size() * sizeof(double)));
+    CK(cudaMemcpy(d_sx, vx.data(), vx.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_sy, vy.data(), vy.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  // The plain decimated blur of the reference: lattice (0, step).
+  void build_decimated(const HostKernel& hk, int kind, int in_w, int in_h, int in_pitch,
+                       double border_ratio, int ups) {
+    build(hk, kind, in_w, in_h, in_pitch, 0, hk.step, (in_w + hk.step - 1) / hk.step, 0, hk.step,
+          (in_h + hk.step - 1) / hk.step, border_ratio, ups);
+  }
+  void release() {
+    if (d_sx) cudaFree(d_sx);
+    if (d_sy) cudaFree(d_sy);
+    d_sx = d_sy = nullptr;
+  }
+  size_t tmp_floats() const { return static_cast<size_t>(g.tmp_pitch) * g.in_h; }
+  size_t out_floats() const { return static_cast<size_t>(g.tmp_pitch) * std::max(g.ny, 1); }
+};
+
+}  // namespace gzb
+
+using namespace gzb;
+
+// ---------------------------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------------------------
+struct gzb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int W = 0, H = 0, P = 0, HP = 0, bw = 0, bh = 0, nblocks = 0, rxs = 0, rys = 0, sqp = 0;
+  size_t ps = 0;       // floats per full-res plane (P * HP)
+  float target = 0.f;
+  float distance = 0.f;
+  float last_ms = 0.f;
+  unsigned long long launches = 0;
+  bool have_orig_coeffs = false, have_coeffs = false, block_cmp = false, have_distmap = false;
+  int sm_count = 148;
+  std::string err;
+
+  uint8_t* d_rgb0 = nullptr;   // original, planar u8 [3][HP][P]
+  uint8_t* d_rgb1 = nullptr;   // candidate
+  uint8_t* d_stage_u8 = nullptr;  // interleaved staging (w*h*3)
+  int16_t* d_orig = nullptr;   // [3][nblocks*64] q=1 coefficients
+  int16_t* d_coef = nullptr;   // [3][nblocks*64] candidate
+  float* d_xyb0 = nullptr;     // [3] planes
+  float* d_xyb1 = nullptr;     // [3]
+  float* d_mh = nullptr;       // [6] planes: MaskHighIntensityChange outputs (img0 x3, img1 x3)
+  float* d_bl = nullptr;       // [6] planes: edge-detector blurs; reused as mask front [3]
+  float* d_tmp = nullptr;      // [6] planes: H-pass scratch
+  float* d_lf = nullptr;       // [6] decimated sigma-14 maps
+  float* d_ms[3] = {nullptr, nullptr, nullptr};  // blurred mask lattices
+  float* d_msb2 = nullptr;     // channel-2 mask lattice for block comparisons
+  float* d_edm = nullptr, *d_dc = nullptr, *d_ac = nullptr;  // res maps x3 floats
+  float* d_sq = nullptr;       // res map, pitch sqp
+  float* d_dsmall = nullptr;   // decimated diffmap blur
+  float* d_diffmap = nullptr;  // [HP][P]
+  float* d_bmax = nullptr, *d_weight = nullptr, *d_mask_scale = nullptr, *d_block_err = nullptr;
+  float* d_pregamma = nullptr;
+  unsigned char* d_flags = nullptr;
+  unsigned int* d_scalars = nullptr;  // [0] distance bits, [1] work counter
+  int* d_q = nullptr;          // 192 ints
+  gzb_coeff_data* d_order = nullptr;
+  float* h_pinned = nullptr;   // small pinned staging
+  size_t lf_stride = 0;
+
+  BlurPlan p_ops, p_ed[3], p_lf, p_mk[3], p_mkb2, p_dm;
+};
+
+static std::string g_create_err;
+
+namespace {
+
+template <typename T>
+void dmalloc(T** p, size_t n) { CK(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T))); }
+
+void run_blur(gzb_ctx* c, const BlurPlan& pl, const float* in, size_t in_stride, int planes,
+              float* out, size_t out_stride, int out_pitch) {
+  const BlurGeom& g = pl.g;
+  if (g.nx <= 0 || g.ny <= 0) return;
+  dim3 blk(32, 8);
+  dim3 gh((g.nx + g.oxn - 1) / g.oxn, (g.in_h + kBhRows - 1) / kBhRows, planes);
+  const size_t tstride = pl.tmp_floats();
+  if (g.ups == 1) k_blur_h<1><<<gh, blk, 0, c->stream>>>(in, in_stride, g, pl.d_sx, c->d_tmp, tstride);
+  else k_blur_h<3><<<gh, blk, 0, c->stream>>>(in, in_stride, g, pl.d_sx, c->d_tmp, tstride);
+  dim3 gv((g.nx + 31) / 32, (g.ny + g.oyn - 1) / g.oyn, planes);
+  k_blur_v<<<gv, blk, 0, c->stream>>>(c->d_tmp, tstride, g, pl.d_sy, out, out_stride, out_pitch);
+  c->launches += 2;
+}
+
+void render_candidate(gzb_ctx* c, int op) {
+  const int grid = (c->nblocks + 31) / 32;
+  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+  const size_t us = static_cast<size_t>(c->P) * c->HP;
+  if (op == kCoeffKeep)
+    k_coeffs_to_rgb8<kCoeffKeep><<<grid, 256, 0, c->stream>>>(c->d_coef, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us);
+  else if (op == kCoeffQuantize)
+    k_coeffs_to_rgb8<kCoeffQuantize><<<grid, 256, 0, c->stream>>>(c->d_coef, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us);
+  else
+    k_coeffs_to_rgb8<kCoeffScale><<<grid, 256, 0, c->stream>>>(c->d_orig, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us);
+  c->launches += 1;
+}
+
+void opsin_from_u8(gzb_ctx* c, const uint8_t* planes, float* xyb) {
+  dim3 blk(32, 8), grd((c->W + 31) / 32, (c->H + 31) / 32);
+  k_opsin_dynamics<<<grd, blk, 0, c->stream>>>(planes, static_cast<size_t>(c->P) * c->HP, c->W, c->H, c->P,
+                                               c->p_ops.d_sx, c->p_ops.d_sy, xyb, c->ps);
+  c->launches += 1;
+}
+
+MaskSample mask_sample(gzb_ctx* c, bool for_blocks) {
+  MaskSample ms;
+  for (int k = 0; k < 3; ++k) {
+    const BlurPlan& pl = (k == 2 && for_blocks) ? c->p_mkb2 : c->p_mk[k];
+    ms.m[k] = (k == 2 && for_blocks) ? c->d_msb2 : c->d_ms[k];
+    ms.pitch[k] = pl.g.tmp_pitch;
+    ms.x0[k] = pl.g.x0; ms.sx[k] = pl.g.sx; ms.y0[k] = pl.g.y0; ms.sy[k] = pl.g.sy;
+  }
+  return ms;
+}
+
+// Mask front + blurs for (a, b) image pair (planes with stride ps); for_blocks selects the
+// channel-2 lattice.
+void run_mask(gzb_ctx* c, const float* a, const float* b, bool for_blocks) {
+  dim3 blk(32, 8), grd((c->W + 31) / 32, (c->H + 31) / 32, 3);
+  k_mask_front<<<grd, blk, 0, c->stream>>>(a, b, c->ps, c->W, c->H, c->P, c->d_bl);
+  c->launches += 1;
+  for (int k = 0; k < 3; ++k) {
+    const BlurPlan& pl = (k == 2 && for_blocks) ? c->p_mkb2 : c->p_mk[k];
+    float* out = (k == 2 && for_blocks) ? c->d_msb2 : c->d_ms[k];
+    run_blur(c, pl, c->d_bl + k * c->ps, 0, 1, out, 0, pl.g.tmp_pitch);
+  }
+}
+
+// DiffmapOpsinDynamicsImage (butteraugli.cc:1046-1079) on d_xyb0 / d_xyb1 -> d_diffmap, distance.
+void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
+  const int W = c->W, H = c->H, P = c->P;
+  dim3 blk(32, 8), gpx((W + 31) / 32, (H + 7) / 8);
+  float* m0 = c->d_mh;
+  float* m1 = c->d_mh + 3 * c->ps;
+  k_mask_high_intensity_change<<<gpx, blk, 0, c->stream>>>(xyb0, xyb1, c->ps, W, H, P, m0, m1);
+  c->launches += 1;
+  // EdgeDetectorMap
+  for (int k = 0; k < 3; ++k)
+    run_blur(c, c->p_ed[k], c->d_mh + k * c->ps, 3 * c->ps, 2, c->d_bl + k * c->ps, 3 * c->ps, P);
+  dim3 gres((c->rxs + 31) / 32, (c->rys + 7) / 8);
+  k_edge_detector_map<<<gres, blk, 0, c->stream>>>(c->d_bl, c->d_bl + 3 * c->ps, c->ps, W, H, P, c->rxs, c->d_edm);
+  // BlockDiffMap
+  const size_t rbytes = static_cast<size_t>(3) * c->rxs * c->rys * sizeof(float);
+  CK(cudaMemsetAsync(c->d_ac, 0, rbytes, c->stream));
+  const int ncx = (W - 4 + 2) / 3, ncy = (H - 4 + 2) / 3;
+  const int cells = ncx * ncy;
+  const int ctas = std::min((cells + kBdmWarps - 1) / kBdmWarps, c->sm_count * 16);
+  k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, c->stream>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac);
+  // EdgeDetectorLowFreq
+  run_blur(c, c->p_lf, c->d_mh, c->ps, 6, c->d_lf, c->lf_stride, c->p_lf.g.tmp_pitch);
+  k_edge_lowfreq<<<gres, blk, 0, c->stream>>>(c->d_lf, c->d_lf + 3 * c->lf_stride, c->lf_stride, c->p_lf.g.tmp_pitch,
+                                             c->p_lf.g.sx, W, H, c->rxs, c->d_ac);
+  c->launches += 3;
+  // Mask + combine
+  run_mask(c, m0, m1, false);
+  k_combine<<<gres, blk, 0, c->stream>>>(mask_sample(c, false), c->d_dc, c->d_ac, c->d_edm, W, H, c->rxs, c->rys, c->sqp, c->d_sq);
+  // CalculateDiffmap
+  run_blur(c, c->p_dm, c->d_sq, 0, 1, c->d_dsmall, 0, c->p_dm.g.tmp_pitch);
+  CK(cudaMemsetAsync(c->d_scalars, 0, sizeof(unsigned int), c->stream));
+  k_diffmap_final<<<gpx, blk, 0, c->stream>>>(c->d_sq, c->sqp, c->d_dsmall, c->p_dm.g.tmp_pitch, c->p_dm.g.sx, W, H, P,
+                                             c->d_diffmap, c->d_scalars);
+  c->launches += 2;
+}
+
+void free_ctx(gzb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  void* ptrs[] = {c->d_rgb0, c->d_rgb1, c->d_stage_u8, c->d_orig, c->d_coef, c->d_xyb0, c->d_xyb1, c->d_mh,
+                  c->d_bl, c->d_tmp, c->d_lf, c->d_ms[0], c->d_ms[1], c->d_ms[2], c->d_msb2, c->d_edm, c->d_dc,
+                  c->d_ac, c->d_sq, c->d_dsmall, c->d_diffmap, c->d_bmax, c->d_weight, c->d_mask_scale,
+                  c->d_block_err, c->d_pregamma, c->d_flags, c->d_scalars, c->d_q, c->d_order};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  c->p_ops.release(); c->p_lf.release(); c->p_mkb2.release(); c->p_dm.release();
+  for (int k = 0; k < 3; ++k) { c->p_ed[k].release(); c->p_mk[k].release(); }
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+// Allocates everything for a W x H image (no original yet).
+gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
+  gzb_ctx* c = new gzb_ctx;
+  try {
+    c->device = device;
+    CK(cudaSetDevice(device));
+    init_device_tables(device);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    c->W = W; c->H = H; c->target = target;
+    c->P = round_up(W, 32);
+    c->bw = (W + 7) / 8; c->bh = (H + 7) / 8; c->nblocks = c->bw * c->bh;
+    c->HP = c->bh * 8;
+    c->ps = static_cast<size_t>(c->P) * c->HP;
+    c->rxs = (W + 2) / 3; c->rys = (H + 2) / 3; c->sqp = round_up(c->rxs, 32);
+    const size_t us = c->ps;
+    dmalloc(&c->d_rgb0, 3 * us); dmalloc(&c->d_rgb1, 3 * us); dmalloc(&c->d_stage_u8, static_cast<size_t>(3) * W * H);
+    CK(cudaMemsetAsync(c->d_rgb0, 0, 3 * us, c->stream));
+    CK(cudaMemsetAsync(c->d_rgb1, 0, 3 * us, c->stream));
+    const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+    dmalloc(&c->d_orig, 3 * cs); dmalloc(&c->d_coef, 3 * cs);
+    dmalloc(&c->d_xyb0, 3 * c->ps); dmalloc(&c->d_xyb1, 3 * c->ps);
+    dmalloc(&c->d_mh, 6 * c->ps); dmalloc(&c->d_bl, 6 * c->ps); dmalloc(&c->d_tmp, 6 * c->ps);
+    // plans
+    c->p_ops.build_decimated(g_hk[kB11], kB11, W, H, c->P, 0.0, 1);
+    const int edk[3] = {kB15, kB0586, kB04};
+    for (int k = 0; k < 3; ++k) c->p_ed[k].build_decimated(g_hk[edk[k]], edk[k], W, H, c->P, 0.0, 1);
+    c->p_lf.build_decimated(g_hk[kB14], kB14, W, H, c->P, 0.0, 1);
+    c->p_mk[0].build_decimated(g_hk[kB9657], kB9657, W, H, c->P, 0.0, 1);
+    c->p_mk[1].build_decimated(g_hk[kB14264], kB14264, W, H, c->P, 0.0, 1);
+    {  // channel 2 (step 1): only the pixels CombineChannels samples, (3rx+3, 3ry+3)
+      const int nx = std::max(0, (W - 5 + 2) / 3), ny = std::max(0, (H - 5 + 2) / 3);
+      c->p_mk[2].build(g_hk[kB4533], kB4533, W, H, c->P, 3, 3, nx, 3, 3, ny, 0.0, 1);
+      c->p_mkb2.build(g_hk[kB4533], kB4533, W, H, c->P, 0, 8, c->bw, 0, 8, c->bh, 0.0, 1);
+    }
+    c->p_dm.build_decimated(g_hk[kB8851], kB8851, W - 5, H - 5, c->sqp, 0.03027655136, 3);
+    c->lf_stride = c->p_lf.out_floats();
+    dmalloc(&c->d_lf, 6 * c->lf_stride);
+    for (int k = 0; k < 3; ++k) dmalloc(&c->d_ms[k], c->p_mk[k].out_floats());
+    dmalloc(&c->d_msb2, c->p_mkb2.out_floats());
+    const size_t rn = static_cast<size_t>(c->rxs) * c->rys;
+    dmalloc(&c->d_edm, 3 * rn); dmalloc(&c->d_dc, 3 * rn); dmalloc(&c->d_ac, 3 * rn);
+    CK(cudaMemsetAsync(c->d_edm, 0, 3 * rn * sizeof(float), c->stream));
+    CK(cudaMemsetAsync(c->d_dc, 0, 3 * rn * sizeof(float), c->stream));
+    dmalloc(&c->d_sq, static_cast<size_t>(c->sqp) * c->rys);
+    dmalloc(&c->d_dsmall, c->p_dm.out_floats());
+    dmalloc(&c->d_diffmap, c->ps);
+    dmalloc(&c->d_bmax, c->nblocks); dmalloc(&c->d_weight, c->nblocks);
+    dmalloc(&c->d_mask_scale, static_cast<size_t>(3) * c->nblocks);
+    dmalloc(&c->d_block_err, c->nblocks);
+    dmalloc(&c->d_pregamma, static_cast<size_t>(192) * c->nblocks);
+    dmalloc(&c->d_flags, c->nblocks);
+    dmalloc(&c->d_scalars, 4);
+    dmalloc(&c->d_q, 192);
+    dmalloc(&c->d_order, static_cast<size_t>(192) * c->nblocks);
+    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_pinned), 4096));
+    // the blur scratch must hold the widest H-pass output of any plan
+    const BlurPlan* all[] = {&c->p_ed[0], &c->p_ed[1], &c->p_ed[2], &c->p_lf, &c->p_mk[0], &c->p_mk[1],
+                             &c->p_mk[2], &c->p_mkb2, &c->p_dm};
+    for (const BlurPlan* pl : all)
+      if (pl->tmp_floats() > c->ps) throw std::string("internal: blur scratch too small");
+    CK(cudaStreamSynchronize(c->stream));
+    return c;
+  } catch (const std::string& e) {
+    g_create_err = e;
+    free_ctx(c);
+    return nullptr;
+  }
+}
+
+void upload_original(gzb_ctx* c, const uint8_t* rgb) {
+  const size_t n = static_cast<size_t>(3) * c->W * c->H;
+  CK(cudaMemcpyAsync(c->d_stage_u8, rgb, n, cudaMemcpyHostToDevice, c->stream));
+  dim3 grd((c->W + 255) / 256, c->H);
+  k_deinterleave_rgb<<<grd, 256, 0, c->stream>>>(c->d_stage_u8, c->W, c->H, c->P, c->d_rgb0, c->ps);
+  opsin_from_u8(c, c->d_rgb0, c->d_xyb0);
+  c->launches += 1;
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+}
+
+int fail(gzb_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_err = msg;
+  return code;
+}
+
+#define GZB_TRY(ctx) \
+  if (!(ctx)) return GZB_ERR_BAD_ARG; \
+  try { CK(cudaSetDevice((ctx)->device));
+#define GZB_END(ctx) \
+  } catch (const std::string& e) { return fail((ctx), GZB_ERR_CUDA, e); } \
+  return GZB_OK;
+
+void sync_check(gzb_ctx* c) {
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* gzb_version(void) { return "gzb200 0.1 (sm_100a)"; }
+const char* gzb_last_error(const gzb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+int gzb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int gzb_create(int device, int width, int height, const uint8_t* rgb, float target_distance, gzb_ctx** out) {
+  if (!out || !rgb) return fail(nullptr, GZB_ERR_BAD_ARG, "gzb_create: null argument");
+  *out = nullptr;
+  if (width < 32 || height < 32) return fail(nullptr, GZB_ERR_TOO_SMALL, "gzb_create: image smaller than 32x32");
+  if (width >= (1 << 16) || height >= (1 << 16)) return fail(nullptr, GZB_ERR_BAD_ARG, "gzb_create: image too large");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0 || device < 0 || device >= n)
+    return fail(nullptr, GZB_ERR_CUDA, std::string("gzb_create: no usable CUDA device (") +
+                                           (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range") + ")");
+  gzb_ctx* c = alloc_ctx(device, width, height, target_distance);
+  if (!c) return GZB_ERR_CUDA;
+  try {
+    upload_original(c, rgb);
+  } catch (const std::string& msg) {
+    g_create_err = msg;
+    free_ctx(c);
+    return GZB_ERR_CUDA;
+  }
+  *out = c;
+  return GZB_OK;
+}
+
+void gzb_destroy(gzb_ctx* ctx) { free_ctx(ctx); }
+
+int gzb_set_jpeg_coeffs(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const int16_t* c2) {
+  GZB_TRY(c)
+  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+  const int16_t* src[3] = {c0, c1, c2};
+  for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(c->d_orig + k * cs, src[k], cs * 2, cudaMemcpyHostToDevice, c->stream));
+  sync_check(c);
+  c->have_orig_coeffs = true;
+  GZB_END(c)
+}
+
+int gzb_copy_from_jpeg(gzb_ctx* c, const int* quant192) {
+  GZB_TRY(c)
+  if (!c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_copy_from_jpeg: gzb_set_jpeg_coeffs not called");
+  CK(cudaMemcpyAsync(c->d_q, quant192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  render_candidate(c, kCoeffScale);
+  sync_check(c);
+  c->have_coeffs = true;
+  GZB_END(c)
+}
+
+int gzb_apply_global_quantization(gzb_ctx* c, const int* q192) {
+  GZB_TRY(c)
+  if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_apply_global_quantization: no candidate coefficients");
+  for (int i = 0; i < 192; ++i) if (q192[i] <= 0) return fail(c, GZB_ERR_BAD_ARG, "quantiser must be positive");
+  CK(cudaMemcpyAsync(c->d_q, q192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  render_candidate(c, kCoeffQuantize);
+  sync_check(c);
+  GZB_END(c)
+}
+
+int gzb_set_coeffs(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const int16_t* c2) {
+  GZB_TRY(c)
+  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+  const int16_t* src[3] = {c0, c1, c2};
+  for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(c->d_coef + k * cs, src[k], cs * 2, cudaMemcpyHostToDevice, c->stream));
+  render_candidate(c, kCoeffKeep);
+  sync_check(c);
+  c->have_coeffs = true;
+  GZB_END(c)
+}
+
+int gzb_get_coeffs(gzb_ctx* c, int16_t* c0, int16_t* c1, int16_t* c2) {
+  GZB_TRY(c)
+  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+  int16_t* dst[3] = {c0, c1, c2};
+  for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(dst[k], c->d_coef + k * cs, cs * 2, cudaMemcpyDeviceToHost, c->stream));
+  sync_check(c);
+  GZB_END(c)
+}
+
+int gzb_update_coeffs(gzb_ctx* c, const int32_t* block_ix, const uint8_t* idx, const int16_t* val, size_t n) {
+  GZB_TRY(c)
+  if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_update_coeffs: no candidate coefficients");
+  // Sparse host-side patch through a pinned-free path: few records per call in practice.
+  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+  for (size_t i = 0; i < n; ++i) {
+    if (block_ix[i] < 0 || block_ix[i] >= c->nblocks || idx[i] >= 192) return fail(c, GZB_ERR_BAD_ARG, "gzb_update_coeffs: index out of range");
+    const size_t off = (idx[i] >> 6) * cs + static_cast<size_t>(block_ix[i]) * 64 + (idx[i] & 63);
+    CK(cudaMemcpyAsync(c->d_coef + off, &val[i], 2, cudaMemcpyHostToDevice, c->stream));
+  }
+  render_candidate(c, kCoeffKeep);
+  sync_check(c);
+  GZB_END(c)
+}
+
+int gzb_to_srgb(gzb_ctx* c, uint8_t* rgb_out) {
+  GZB_TRY(c)
+  if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_to_srgb: no candidate coefficients");
+  std::vector<uint8_t> pl(3 * static_cast<size_t>(c->W) * c->H);
+  const size_t us = c->ps;
+  for (int k = 0; k < 3; ++k)
+    CK(cudaMemcpy2DAsync(pl.data() + static_cast<size_t>(k) * c->W * c->H, c->W, c->d_rgb1 + k * us, c->P, c->W, c->H,
+                         cudaMemcpyDeviceToHost, c->stream));
+  sync_check(c);
+  const size_t n = static_cast<size_t>(c->W) * c->H;
+  for (size_t i = 0; i < n; ++i) {
+    rgb_out[3 * i] = pl[i];
+    rgb_out[3 * i + 1] = pl[n + i];
+    rgb_out[3 * i + 2] = pl[2 * n + i];
+  }
+  GZB_END(c)
+}
+
+int gzb_compare(gzb_ctx* c, float* distance) {
+  GZB_TRY(c)
+  if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compare: no candidate coefficients");
+  CK(cudaEventRecord(c->ev0, c->stream));
+  opsin_from_u8(c, c->d_rgb1, c->d_xyb1);
+  run_diffmap(c, c->d_xyb0, c->d_xyb1);
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+  sync_check(c);
+  CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  memcpy(&c->distance, c->h_pinned, sizeof(float));
+  c->have_distmap = true;
+  if (distance) *distance = c->distance;
+  GZB_END(c)
+}
+
+int gzb_get_distmap(gzb_ctx* c, float* out) {
+  GZB_TRY(c)
+  if (!c->have_distmap) return fail(c, GZB_ERR_STATE, "gzb_get_distmap: no Compare yet");
+  CK(cudaMemcpy2DAsync(out, c->W * sizeof(float), c->d_diffmap, c->P * sizeof(float), c->W * sizeof(float), c->H,
+                       cudaMemcpyDeviceToHost, c->stream));
+  sync_check(c);
+  GZB_END(c)
+}
+
+int gzb_distance_ok(const gzb_ctx* c, double target_mul) {
+  // float distance_ <= double target_mul * float target_distance_ (butteraugli_comparator.h:52-54)
+  return c && static_cast<double>(c->distance) <= target_mul * static_cast<double>(c->target) ? 1 : 0;
+}
+
+double gzb_score_output_size(const gzb_ctx* c, int size) {
+  // ScoreJPEG (guetzli/score.cc:23-41)
+  if (!c) return -1.0;
+  const double diff = static_cast<double>(c->distance) - static_cast<double>(c->target);
+  if (diff <= 0.0) return size;
+  const double e = 50 * diff;
+  if (e > 10) return 1e30 * std::exp(10.0) * diff + size;
+  return std::exp(e) * size;
+}
+
+float gzb_block_error_limit(const gzb_ctx* c) { return c ? c->target : 0.f; }
+
+int gzb_start_block_comparisons(gzb_ctx* c) {
+  GZB_TRY(c)
+  CK(cudaEventRecord(c->ev0, c->stream));
+  run_mask(c, c->d_xyb0, c->d_xyb0, true);
+  k_block_mask_scale<<<(c->nblocks + 255) / 256, 256, 0, c->stream>>>(mask_sample(c, true), c->bw, c->bh, c->d_mask_scale);
+  c->launches += 1;
+  CK(cudaEventRecord(c->ev1, c->stream));
+  sync_check(c);
+  CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  c->block_cmp = true;
+  GZB_END(c)
+}
+
+int gzb_finish_block_comparisons(gzb_ctx* c) {
+  if (!c) return GZB_ERR_BAD_ARG;
+  c->block_cmp = false;
+  return GZB_OK;
+}
+
+static int run_zeroing(gzb_ctx* c, int comp_mask, int mode) {
+  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+  CK(cudaMemsetAsync(c->d_scalars + 1, 0, sizeof(unsigned int), c->stream));
+  if (mode == 0) CK(cudaMemsetAsync(c->d_order, 0, sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(c->nblocks), c->stream));
+  const int ctas = std::min((c->nblocks + kZeroWarps - 1) / kZeroWarps, c->sm_count * 5);
+  CK(cudaEventRecord(c->ev0, c->stream));
+  k_zeroing_order<<<ctas, 32 * kZeroWarps, 0, c->stream>>>(
+      c->d_orig, c->d_coef, cs, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, c->nblocks, c->d_mask_scale, comp_mask,
+      c->target, 3, mode, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1);
+  c->launches += 1;
+  CK(cudaEventRecord(c->ev1, c->stream));
+  return 0;
+}
+
+int gzb_get_block_lists(gzb_ctx* c, float* mask_scale_out, float* opsin_blocks_out) {
+  GZB_TRY(c)
+  if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_get_block_lists: StartBlockComparisons not called");
+  if (opsin_blocks_out) {
+    if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_get_block_lists: no candidate coefficients");
+    run_zeroing(c, 7, 1);
+    CK(cudaMemcpyAsync(opsin_blocks_out, c->d_pregamma, sizeof(float) * 192 * static_cast<size_t>(c->nblocks), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (mask_scale_out)
+    CK(cudaMemcpyAsync(mask_scale_out, c->d_mask_scale, sizeof(float) * 3 * static_cast<size_t>(c->nblocks), cudaMemcpyDeviceToHost, c->stream));
+  sync_check(c);
+  GZB_END(c)
+}
+
+int gzb_compare_blocks(gzb_ctx* c, float* err_out) {
+  GZB_TRY(c)
+  if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_compare_blocks: StartBlockComparisons not called");
+  if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compare_blocks: no candidate coefficients");
+  run_zeroing(c, 7, 1);
+  CK(cudaMemcpyAsync(err_out, c->d_block_err, sizeof(float) * c->nblocks, cudaMemcpyDeviceToHost, c->stream));
+  sync_check(c);
+  CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  GZB_END(c)
+}
+
+int gzb_compute_block_zeroing_order(gzb_ctx* c, int comp_mask, gzb_coeff_data* out) {
+  GZB_TRY(c)
+  if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_compute_block_zeroing_order: StartBlockComparisons not called");
+  if (!c->have_coeffs || !c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compute_block_zeroing_order: coefficients missing");
+  if (comp_mask < 1 || comp_mask > 7) return fail(c, GZB_ERR_BAD_ARG, "comp_mask must be in 1..7");
+  run_zeroing(c, comp_mask, 0);
+  CK(cudaMemcpyAsync(out, c->d_order, sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(c->nblocks), cudaMemcpyDeviceToHost, c->stream));
+  sync_check(c);
+  CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  GZB_END(c)
+}
+
+int gzb_compute_block_error_adjustment_weights(gzb_ctx* c, int direction, int max_block_dist, double target_mul,
+                                               const float* distmap, float* block_weight) {
+  GZB_TRY(c)
+  if (distmap) {
+    CK(cudaMemcpy2DAsync(c->d_diffmap, c->P * sizeof(float), distmap, c->W * sizeof(float), c->W * sizeof(float), c->H,
+                         cudaMemcpyHostToDevice, c->stream));
+    c->have_distmap = false;  // the resident map no longer belongs to the last Compare
+  } else if (!c->have_distmap) {
+    return fail(c, GZB_ERR_STATE, "gzb_compute_block_error_adjustment_weights: no distance map");
+  }
+  const double target = static_cast<double>(c->target) * target_mul;
+  const int g = (c->nblocks + 255) / 256;
+  k_block_max<<<g, 256, 0, c->stream>>>(c->d_diffmap, c->P, c->W, c->H, c->bw, c->bh, c->d_bmax);
+  k_block_flags<<<g, 256, 0, c->stream>>>(c->d_bmax, c->bw, c->bh, direction, max_block_dist, target, c->d_flags);
+  k_block_weights<<<g, 256, 0, c->stream>>>(c->d_flags, c->bw, c->bh, direction, max_block_dist, c->d_weight);
+  c->launches += 3;
+  CK(cudaMemcpyAsync(block_weight, c->d_weight, sizeof(float) * c->nblocks, cudaMemcpyDeviceToHost, c->stream));
+  sync_check(c);
+  GZB_END(c)
+}
+
+int gzb_debug_fetch(gzb_ctx* c, const char* name, float* out, size_t cap, size_t* n_out) {
+  GZB_TRY(c)
+  const std::string s(name ? name : "");
+  const size_t n = static_cast<size_t>(c->W) * c->H, rn = static_cast<size_t>(c->rxs) * c->rys;
+  const float* planes = nullptr; int nplanes = 0;
+  const float* flat = nullptr; size_t flat_n = 0;
+  if (s == "xyb0") { planes = c->d_xyb0; nplanes = 3; }
+  else if (s == "xyb1") { planes = c->d_xyb1; nplanes = 3; }
+  else if (s == "mhic0") { planes = c->d_mh; nplanes = 3; }
+  else if (s == "mhic1") { planes = c->d_mh + 3 * c->ps; nplanes = 3; }
+  else if (s == "mask_front") { planes = c->d_bl; nplanes = 3; }
+  else if (s == "diffmap") { planes = c->d_diffmap; nplanes = 1; }
+  else if (s == "edge_map") { flat = c->d_edm; flat_n = 3 * rn; }
+  else if (s == "block_dc") { flat = c->d_dc; flat_n = 3 * rn; }
+  else if (s == "block_ac") { flat = c->d_ac; flat_n = 3 * rn; }
+  else if (s == "combined_sqrt") { planes = nullptr; }
+  else return fail(c, GZB_ERR_BAD_ARG, "gzb_debug_fetch: unknown name " + s);
+  if (planes) {
+    const size_t total = n * nplanes;
+    if (n_out) *n_out = total;
+    if (cap >= total)
+      for (int k = 0; k < nplanes; ++k)
+        CK(cudaMemcpy2DAsync(out + k * n, c->W * sizeof(float), planes + k * c->ps, c->P * sizeof(float),
+                             c->W * sizeof(float), c->H, cudaMemcpyDeviceToHost, c->stream));
+  } else if (flat) {
+    if (n_out) *n_out = flat_n;
+    if (cap >= flat_n) CK(cudaMemcpyAsync(out, flat, flat_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  } else {  // combined_sqrt: res map with pitch
+    if (n_out) *n_out = rn;
+    if (cap >= rn)
+      CK(cudaMemcpy2DAsync(out, c->rxs * sizeof(float), c->d_sq, c->sqp * sizeof(float), c->rxs * sizeof(float), c->rys,
+                           cudaMemcpyDeviceToHost, c->stream));
+  }
+  sync_check(c);
+  GZB_END(c)
+}
+
+float gzb_last_device_ms(const gzb_ctx* c) { return c ? c->last_ms : 0.f; }
+unsigned long long gzb_launch_count(const gzb_ctx* c) { return c ? c->launches : 0; }
+
+// ---- stage entry points ----------------------------------------------------------------------
+int gzb_blur(int device, float* plane, size_t xsize, size_t ysize, double sigma, double border_ratio) {
+  if (!plane || xsize == 0 || ysize == 0) return fail(nullptr, GZB_ERR_BAD_ARG, "gzb_blur: bad argument");
+  try {
+    CK(cudaSetDevice(device));
+    init_device_tables(device);
+    HostKernel hk;
+    if (!make_host_kernel(sigma, &hk)) return fail(nullptr, GZB_ERR_UNSUPPORTED, "gzb_blur: sigma too large (radius > 32)");
+    if (hk.step > 4) return fail(nullptr, GZB_ERR_UNSUPPORTED, "gzb_blur: decimation > 4");
+    const int W = static_cast<int>(xsize), H = static_cast<int>(ysize), P = round_up(W, 32);
+    float taps[kMaxTaps] = {0};
+    memcpy(taps, hk.taps, sizeof(float) * (2 * hk.r + 1));
+    CK(cudaMemcpyToSymbol(c_taps, taps, sizeof(taps), sizeof(float) * kMaxTaps * kBUser));
+    BlurPlan pl;
+    pl.build_decimated(hk, kBUser, W, H, P, border_ratio, 1);
+    float *d_in = nullptr, *d_tmp = nullptr, *d_out = nullptr;
+    dmalloc(&d_in, static_cast<size_t>(P) * H);
+    dmalloc(&d_tmp, pl.tmp_floats());
+    dmalloc(&d_out, pl.out_floats());
+    CK(cudaMemcpy2D(d_in, P * sizeof(float), plane, W * sizeof(float), W * sizeof(float), H, cudaMemcpyHostToDevice));
+    dim3 blk(32, 8);
+    dim3 gh((pl.g.nx + pl.g.oxn - 1) / pl.g.oxn, (H + kBhRows - 1) / kBhRows, 1);
+    k_blur_h<1><<<gh, blk>>>(d_in, 0, pl.g, pl.d_sx, d_tmp, 0);
+    dim3 gv((pl.g.nx + 31) / 32, (pl.g.ny + pl.g.oyn - 1) / pl.g.oyn, 1);
+    k_blur_v<<<gv, blk>>>(d_tmp, 0, pl.g, pl.d_sy, d_out, 0, pl.g.tmp_pitch);
+    CK(cudaDeviceSynchronize());
+    CK(cudaGetLastError());
+    std::vector<float> small(pl.out_floats());
+    CK(cudaMemcpy(small.data(), d_out, small.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x)
+        plane[static_cast<size_t>(y) * W + x] = small[static_cast<size_t>(y / hk.step) * pl.g.tmp_pitch + x / hk.step];
+    cudaFree(d_in); cudaFree(d_tmp); cudaFree(d_out);
+    pl.release();
+  } catch (const std::string& e) { return fail(nullptr, GZB_ERR_CUDA, e); }
+  return GZB_OK;
+}
+
+int gzb_opsin_dynamics_image(int device, float* r, float* g, float* b, size_t xsize, size_t ysize) {
+  if (!r || !g || !b || xsize == 0 || ysize == 0) return fail(nullptr, GZB_ERR_BAD_ARG, "gzb_opsin_dynamics_image: bad argument");
+  try {
+    CK(cudaSetDevice(device));
+    init_device_tables(device);
+    const int W = static_cast<int>(xsize), H = static_cast<int>(ysize), P = round_up(W, 32);
+    const size_t ps = static_cast<size_t>(P) * H;
+    BlurPlan pl;
+    pl.build_decimated(g_hk[kB11], kB11, W, H, P, 0.0, 1);
+    float *d_in = nullptr, *d_out = nullptr;
+    dmalloc(&d_in, 3 * ps);
+    dmalloc(&d_out, 3 * ps);
+    float* src[3] = {r, g, b};
+    for (int k = 0; k < 3; ++k)
+      CK(cudaMemcpy2D(d_in + k * ps, P * sizeof(float), src[k], W * sizeof(float), W * sizeof(float), H, cudaMemcpyHostToDevice));
+    dim3 blk(32, 8), grd((W + 31) / 32, (H + 31) / 32);
+    k_opsin_dynamics_f32<<<grd, blk>>>(d_in, ps, W, H, P, pl.d_sx, pl.d_sy, d_out, ps);
+    CK(cudaDeviceSynchronize());
+    CK(cudaGetLastError());
+    for (int k = 0; k < 3; ++k)
+      CK(cudaMemcpy2D(src[k], W * sizeof(float), d_out + k * ps, P * sizeof(float), W * sizeof(float), H, cudaMemcpyDeviceToHost));
+    cudaFree(d_in); cudaFree(d_out);
+    pl.release();
+  } catch (const std::string& e) { return fail(nullptr, GZB_ERR_CUDA, e); }
+  return GZB_OK;
+}
+
+int gzb_diffmap_opsin_dynamics_image(int device, float* result, const float* r, const float* g, const float* b,
+                                     const float* r2, const float* g2, const float* b2, size_t xsize, size_t ysize,
+                                     size_t step) {
+  if (step != 3) return fail(nullptr, GZB_ERR_UNSUPPORTED, "gzb_diffmap_opsin_dynamics_image: step must be 3");
+  if (!result || !r || !g || !b || !r2 || !g2 || !b2) return fail(nullptr, GZB_ERR_BAD_ARG, "null plane");
+  if (xsize < 32 || ysize < 32) return fail(nullptr, GZB_ERR_TOO_SMALL, "image smaller than 32x32");
+  gzb_ctx* c = alloc_ctx(device, static_cast<int>(xsize), static_cast<int>(ysize), 1.0f);
+  if (!c) return GZB_ERR_CUDA;
+  int rc = GZB_OK;
+  try {
+    const float* s0[3] = {r, g, b};
+    const float* s1[3] = {r2, g2, b2};
+    for (int k = 0; k < 3; ++k) {
+      CK(cudaMemcpy2DAsync(c->d_xyb0 + k * c->ps, c->P * sizeof(float), s0[k], c->W * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpy2DAsync(c->d_xyb1 + k * c->ps, c->P * sizeof(float), s1[k], c->W * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyHostToDevice, c->stream));
+    }
+    run_diffmap(c, c->d_xyb0, c->d_xyb1);
+    CK(cudaMemcpy2DAsync(result, c->W * sizeof(float), c->d_diffmap, c->P * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyDeviceToHost, c->stream));
+    sync_check(c);
+  } catch (const std::string& e) { rc = fail(nullptr, GZB_ERR_CUDA, e); }
+  free_ctx(c);
+  return rc;
+}
+
+int gzb_butteraugli_srgb(int device, const uint8_t* rgb0, const uint8_t* rgb1, int width, int height, float* distance,
+                         float* diffmap_out) {
+  if (!rgb0 || !rgb1) return fail(nullptr, GZB_ERR_BAD_ARG, "null image");
+  gzb_ctx* c = nullptr;
+  int rc = gzb_create(device, width, height, rgb0, 1.0f, &c);
+  if (rc != GZB_OK) return rc;
+  try {
+    const size_t n = static_cast<size_t>(3) * c->W * c->H;
+    CK(cudaMemcpyAsync(c->d_stage_u8, rgb1, n, cudaMemcpyHostToDevice, c->stream));
+    dim3 grd((c->W + 255) / 256, c->H);
+    k_deinterleave_rgb<<<grd, 256, 0, c->stream>>>(c->d_stage_u8, c->W, c->H, c->P, c->d_rgb1, c->ps);
+    opsin_from_u8(c, c->d_rgb1, c->d_xyb1);
+    run_diffmap(c, c->d_xyb0, c->d_xyb1);
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    if (diffmap_out)
+      CK(cudaMemcpy2DAsync(diffmap_out, c->W * sizeof(float), c->d_diffmap, c->P * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyDeviceToHost, c->stream));
+    sync_check(c);
+    if (distance) memcpy(distance, c->h_pinned, sizeof(float));
+  } catch (const std::string& e) { rc = fail(nullptr, GZB_ERR_CUDA, e); }
+  free_ctx(c);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,404 @@
+// gzb_device_math.cuh -- per-pixel / per-block device arithmetic of the butteraugli metric.
+//
+// Every function follows the MODE_CPU arithmetic of the reference (float storage, double
+// intermediates, identical operand pairing) so that results are bit-identical to the CPU path:
+// the translation unit is compiled with -fmad=false (no FMA contraction), IEEE div/sqrt.
+// Citations: third_party/butteraugli/butteraugli/butteraugli.cc (abbrev. "ba.cc") and guetzli/*.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gzb {
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident constant tables (filled once per process by gzb_tables_init()).
+// ---------------------------------------------------------------------------------------------
+struct DeviceTables {
+  double lut21[3][21];    // HighFreqColorDiffDx, HighFreqColorDiffDy, LowFreqColorDiffDy (ba.cc:200-247)
+  double mask_lut[6][512];  // MaskX,Y,B,DcX,DcY,DcB (ba.cc:1242-1326)
+  float srgb_lin[256];    // float(Srgb8ToLinearTable[i]) (guetzli/gamma_correct.cc:23-33)
+};
+__device__ DeviceTables g_tab;  // global memory (divergent indexing, L1-cached); single-TU build
+
+__constant__ const double kCsf8x8[37] = {  // ba.cc:157-198
+    5.28270670524, 0.0, 0.0, 0.0, 0.3831134973, 0.676303603859, 3.58927792424, 18.6104367002,
+    18.6104367002, 3.09093131948, 1.0, 0.498250875965, 0.36198671102, 0.308982169883,
+    0.1312701920435, 2.37370549629, 3.58927792424, 1.0, 2.37370549629, 0.991205724152,
+    1.05178802919, 0.627264168628, 0.4, 0.1312701920435, 0.676303603859, 0.498250875965,
+    0.991205724152, 0.5, 0.3831134973, 0.349686450518, 0.627264168628, 0.308982169883,
+    0.3831134973, 0.36198671102, 1.05178802919, 0.3831134973, 0.12};
+
+// ---------------------------------------------------------------------------------------------
+// Piecewise-linear table lookups (ba.cc:249-281)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double interp_signed21(const double* __restrict__ lut, double sx) {
+  const double ax = fabs(sx);
+  const int b = static_cast<int>(ax);
+  double r;
+  if (b >= 20) {
+    r = lut[20];
+  } else {
+    const double lo = lut[b], hi = lut[b + 1];
+    r = lo + (ax - b) * (hi - lo);
+  }
+  return sx < 0 ? -r : r;
+}
+
+__device__ __forceinline__ double interp_clamp512(const double* __restrict__ lut, double sx) {
+  if (sx < 0) sx = 0;
+  const int b = static_cast<int>(sx);
+  if (b >= 511) return lut[511];
+  const double lo = lut[b], hi = lut[b + 1];
+  return lo + (sx - b) * (hi - lo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Opsin dynamics (ba.cc:741-764, 868-941, 283-292, 951-973)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void opsin_absorbance(double r, double g, double b, double out[3]) {
+  out[0] = 0.348036746003 * r + 0.577814843137 * g + 0.0544556093735 * b + 0.774145581713;
+  out[1] = 0.26922717275 * r + 0.767247733938 * g + 0.0366922708552 * b + 0.920130265014;
+  out[2] = 0.0882062883536 * r + 0.158581714673 * g + 0.712857943858 * b + 10.6524069248;
+}
+
+// Degree-5/5 Chebyshev rational via Clenshaw; argument and result pass through float.
+__device__ __forceinline__ double gamma_rational(double v) {
+  const float xf = static_cast<float>(v);
+  const double x01 = (static_cast<double>(xf) - 0.770000000000000) /
+                     (274.579999999999984 - 0.770000000000000);
+  const double x = 2.0 * x01 - 1.0;
+  double p1 = 0.0, p2 = 0.0, q1 = 0.0, q2 = 0.0, t, xb;
+#define GZB_CLENSHAW(P, Q)                  \
+  xb = x * p1; t = (xb + xb) - p2 + (P); p2 = p1; p1 = t; \
+  xb = x * q1; t = (xb + xb) - q2 + (Q); q2 = q1; q1 = t;
+  GZB_CLENSHAW(6.683258861509244, 0.035662329617191)
+  GZB_CLENSHAW(85.840860336314364, 0.899112889751053)
+  GZB_CLENSHAW(373.566100223287378, 4.711532733641639)
+  GZB_CLENSHAW(908.662212739659481, 12.161463238367844)
+  GZB_CLENSHAW(1496.058452015812463, 20.557285797683576)
+#undef GZB_CLENSHAW
+  const double yp = x * p1 - p2 + 881.979476556478289;
+  const double yq = x * q1 - q2 + 12.262350348616792;
+  if (yq == 0.0) return 0.0;
+  return static_cast<double>(static_cast<float>(yp / yq));
+}
+
+// One pixel: (blurred linear rgb, sharp linear rgb) -> XYB floats.
+__device__ __forceinline__ void opsin_pixel(float br, float bg, float bb, float r, float g,
+                                            float b, float& X, float& Y, float& B) {
+  double pm[3], cm[3];
+  opsin_absorbance(br, bg, bb, pm);
+  opsin_absorbance(r, g, b, cm);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double sens = gamma_rational(pm[c]) / pm[c];
+    cm[c] *= sens;
+  }
+  X = static_cast<float>(1.01611726948 * cm[0] - 0.982482243696 * cm[1]);
+  Y = static_cast<float>(1.43571362627 * cm[0] + 0.896039849412 * cm[1]);
+  B = static_cast<float>(cm[2]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaskHighIntensityChange, one pixel (ba.cc:798-841). `worst` = max squared Y-average difference
+// to the in-image 4-neighbours (-1 if none).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mhic_pixel(const float c0[3], const float c1[3], double worst,
+                                           float o0[3], float o1[3]) {
+  const double ave1 = (c0[1] + c1[1]) * 0.5;  // float sum, widened by the double multiply
+  const double chroma = 106.95800948271017 / (ave1 + 106.95800948271017);
+  double mix[3];
+  mix[0] = chroma * 275.19165240059317 / (worst + 275.19165240059317);
+  mix[1] = 18599.41286306991 / (worst + 18599.41286306991);
+  mix[2] = chroma * 410.8995306951065 / (worst + 410.8995306951065);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double ave = (c0[c] + c1[c]) * 0.5;
+    o0[c] = static_cast<float>(mix[c] * c0[c] + (1 - mix[c]) * ave);
+    o1[c] = static_cast<float>(mix[c] * c1[c] + (1 - mix[c]) * ave);
+  }
+}
+// Squared difference of the neighbour's Y average to the centre's (ba.cc:817-818).
+__device__ __forceinline__ double mhic_sqdiff(float n0, float n1, float c0, float c1) {
+  const double ave1 = (c0 + c1) * 0.5;
+  double d = 0.5 * (n0 + n1) - ave1;
+  return d * d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Low-frequency colour metric (ba.cc:305-350)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lowfreq_vals(double x, double y, double z, double v[3]) {
+  z += 0.0812519812628 * y;
+  v[2] = z * 7.34905756986;
+  v[0] = x * 6.64482198135;
+  v[1] = interp_signed21(g_tab.lut21[2], y * 0.837846224276);
+}
+// res += factor * (vals(a) - vals(b))^2 ; b == 0 short-circuits like the reference.
+__device__ __forceinline__ void lowfreq_sq_acc(const double a[3], const double b[3],
+                                               double factor, double res[3]) {
+  double va[3];
+  lowfreq_vals(a[0], a[1], a[2], va);
+  if (b[0] == 0.0 && b[1] == 0.0 && b[2] == 0.0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) res[c] += factor * va[c] * va[c];
+    return;
+  }
+  double vb[3];
+  lowfreq_vals(b[0], b[1], b[2], vb);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double d = va[c] - vb[c];
+    res[c] += factor * d * d;
+  }
+}
+__device__ __forceinline__ void lowfreq_sq_acc0(const double a[3], double factor, double res[3]) {
+  double va[3];
+  lowfreq_vals(a[0], a[1], a[2], va);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) res[c] += factor * va[c] * va[c];
+}
+
+// XybToVals, one channel at a time (ba.cc:294-302): the three outputs are independent.
+__device__ __forceinline__ double highfreq_val(int c, double d) {
+  if (c == 0) return interp_signed21(g_tab.lut21[0], d * 0.758304045695);
+  if (c == 1) return interp_signed21(g_tab.lut21[1], d * 2.28148649801);
+  return 1.87816926918 * d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 8-point transforms of the 8x8 power spectrum (ba.cc:371-570), closed form of the split-radix
+// butterflies with the reference's operand pairing.
+// ---------------------------------------------------------------------------------------------
+#define GZB_SQRT_HALF 0.70710678118654752440084436210484903
+
+// Real input x[0..7] -> bins 0..4 (bins 5..7 are conjugates). re[0..4], im[0..4].
+__device__ __forceinline__ void rfft8_half(const double x[8], double re[5], double im[5]) {
+  const double s04 = x[0] + x[4], d04 = x[0] - x[4];
+  const double s26 = x[2] + x[6], d26 = x[2] - x[6];
+  const double s15 = x[1] + x[5], d15 = x[1] - x[5];
+  const double s37 = x[3] + x[7], d37 = x[3] - x[7];
+  const double a = (d15 - d37) * GZB_SQRT_HALF, b = (d15 + d37) * GZB_SQRT_HALF;
+  const double ev = s04 + s26, od = s15 + s37;
+  re[0] = ev + od;   im[0] = 0.0;
+  re[4] = ev - od;   im[4] = 0.0;
+  re[2] = s04 - s26; im[2] = -(s15 - s37);
+  re[1] = a + d04;   im[1] = -(b + d26);
+  re[3] = d04 - a;   im[3] = d26 - b;
+}
+
+// Complex 8-point transform in place (natural output order).
+__device__ __forceinline__ void cfft8(double re[8], double im[8]) {
+  const double sr04 = re[0] + re[4], dr04 = re[0] - re[4];
+  const double si04 = im[0] + im[4], di04 = im[0] - im[4];
+  const double sr26 = re[2] + re[6], dr26 = re[2] - re[6];
+  const double si26 = im[2] + im[6], di26 = im[2] - im[6];
+  const double sr15 = re[1] + re[5], dr15 = re[1] - re[5];
+  const double si15 = im[1] + im[5], di15 = im[1] - im[5];
+  const double sr37 = re[3] + re[7], dr37 = re[3] - re[7];
+  const double si37 = im[3] + im[7], di37 = im[3] - im[7];
+  const double e4r = dr04 - di26, e4i = di04 + dr26;
+  const double e6r = dr04 + di26, e6i = di04 - dr26;
+  const double m1 = dr15 - di37, m3 = dr15 + di37;
+  const double m2 = di15 - dr37, m4 = di15 + dr37;
+  const double P = (m1 - m4) * GZB_SQRT_HALF, Q = (m1 + m4) * GZB_SQRT_HALF;
+  const double U = (m2 - m3) * GZB_SQRT_HALF, V = (m2 + m3) * GZB_SQRT_HALF;
+  const double A = sr04 + sr26, Bv = sr15 + sr37, C = si04 + si26, D = si15 + si37;
+  const double t1 = sr04 - sr26, t3 = sr15 - sr37, t2 = si04 - si26, t4 = si15 - si37;
+  re[0] = A + Bv;   im[0] = C + D;
+  re[4] = A - Bv;   im[4] = C - D;
+  re[6] = t1 - t4;  im[6] = t2 + t3;
+  re[2] = t1 + t4;  im[2] = t2 - t3;
+  re[3] = e4r - P;  im[3] = e4i - Q;
+  re[7] = P + e4r;  im[7] = Q + e4i;
+  re[5] = e6r - V;  im[5] = e6i - U;
+  re[1] = V + e6r;  im[1] = U + e6i;
+}
+
+__device__ __forceinline__ double remove_range_around_zero(double v, double range) {
+  if (v >= -range && v < range) return 0;
+  return v < 0 ? v + range : v - range;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ButteraugliBlockDiff, warp-cooperative (ba.cc:602-684).
+//   fa, fb : the two 8x8x3 blocks as floats in shared memory, [c*64 + 8*y + x]
+//   ws     : per-warp scratch of kBlockDiffScratchDoubles doubles in shared memory
+// Returns dc[3], ac[3], edge[3] in ALL lanes. Sequential sums keep the reference's order.
+// All 32 lanes must call. Ends with __syncwarp(); fa/fb are not modified.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBlockDiffScratchDoubles = 4 * 64 + 4 * 5 * 16;  // planes + row spectra (576)
+
+__device__ __forceinline__ void warp_block_diff(const float* __restrict__ fa,
+                                                const float* __restrict__ fb, double* ws,
+                                                double dc[3], double ac[3], double edge[3]) {
+  const int lane = threadIdx.x & 31;
+  double* pl = ws;            // [4][64]: y_avg, x_halfdiff, y_halfdiff, z_halfdiff
+  double* cs = ws + 4 * 64;   // [4][5][8][2]: row spectra, later reused for terms
+
+  // (1) means and edge means: 15 independent in-order accumulations.
+  double acc = 0.0;
+  if (lane < 3) {
+    const float* a = fa + 64 * lane;
+    const float* b = fb + 64 * lane;
+    for (int i = 0; i < 64; ++i) acc += (static_cast<double>(a[i]) - static_cast<double>(b[i])) / 64;
+  } else if (lane < 15) {
+    const int e = lane - 3, c = e >> 2, side = e & 3;
+    const float* a = fa + 64 * c;
+    const float* b = fb + 64 * c;
+    // side 0: kx==0, 1: ky==0, 2: kx==7, 3: ky==7 (ba.cc:619-626)
+    const int base = side == 0 ? 0 : side == 1 ? 0 : side == 2 ? 7 : 56;
+    const int stride = (side & 1) ? 1 : 8;
+    for (int t = 0; t < 8; ++t) {
+      const int i = base + t * stride;
+      acc += (static_cast<double>(a[i]) - static_cast<double>(b[i])) / 8;
+    }
+  }
+  // (2) average / half-difference planes.
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = lane + 32 * k;
+    const double a0 = fa[i], b0 = fb[i], a1 = fa[64 + i], b1 = fb[64 + i], a2 = fa[128 + i],
+                 b2 = fb[128 + i];
+    pl[i] = (a1 + b1) / 2;
+    pl[64 + i] = (a0 - b0) / 2;
+    pl[128 + i] = (a1 - b1) / 2;
+    pl[192 + i] = (a2 - b2) / 2;
+  }
+  __syncwarp();
+  // gather the 15 sums into lane 0 and evaluate the DC / edge-DC metric there.
+  double m[15];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) m[i] = __shfl_sync(0xffffffffu, acc, i);
+  double dcv[3] = {0.0, 0.0, 0.0}, edv[3] = {0.0, 0.0, 0.0};
+  if (lane == 0) {
+    const double mean[3] = {m[0], m[1], m[2]};
+    lowfreq_sq_acc0(mean, kCsf8x8[0], dcv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const double v[3] = {m[3 + e], m[7 + e], m[11 + e]};
+      lowfreq_sq_acc0(v, kCsf8x8[0], edv);
+    }
+  }
+  // (3) row transforms: lane = plane*8 + row.
+  {
+    const int plane = lane >> 3, row = lane & 7;
+    double x[8], re[5], im[5];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = pl[64 * plane + 8 * row + k];
+    rfft8_half(x, re, im);
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      cs[((plane * 5 + u) * 8 + row) * 2 + 0] = re[u];
+      cs[((plane * 5 + u) * 8 + row) * 2 + 1] = im[u];
+    }
+  }
+  __syncwarp();
+  // (4) column transforms: 20 tasks = plane*5 + u; power into pl[plane*64 + 8u + v].
+  if (lane < 20) {
+    const int plane = lane / 5, u = lane - 5 * plane;
+    const double* src = cs + (plane * 5 + u) * 16;
+    double* dst = pl + 64 * plane + 8 * u;
+    if (u == 0 || u == 4) {
+      double x[8], re[5], im[5];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = src[2 * k];
+      rfft8_half(x, re, im);
+      if (u == 0) {  // needs v = 4..7 : |F4|, |F5|=|F3|, |F6|=|F2|, |F7|=|F1|
+        dst[4] = (re[4] * re[4] + im[4] * im[4]) * 0.000064;
+        dst[5] = (re[3] * re[3] + im[3] * im[3]) * 0.000064;
+        dst[6] = (re[2] * re[2] + im[2] * im[2]) * 0.000064;
+        dst[7] = (re[1] * re[1] + im[1] * im[1]) * 0.000064;
+      } else {  // v = 0..4
+#pragma unroll
+        for (int v = 0; v < 5; ++v) dst[v] = (re[v] * re[v] + im[v] * im[v]) * 0.000064;
+      }
+    } else {
+      double re[8], im[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { re[k] = src[2 * k]; im[k] = src[2 * k + 1]; }
+      cfft8(re, im);
+#pragma unroll
+      for (int v = 0; v < 8; ++v) dst[v] = (re[v] * re[v] + im[v] * im[v]) * 0.000064;
+    }
+  }
+  __syncwarp();
+  // (5) per-frequency terms i = 4..36 (lane L -> i = 4+L; lane 0 also i = 36), then in-order sums.
+  double* term = cs;  // [3][33]
+  for (int i = 4 + lane; i < 37; i += 32) {
+    const double d = kCsf8x8[i];
+    term[i - 4] = d * 64.8 * pl[64 + i];
+    term[66 + i - 4] = d * 2.4 * pl[192 + i];
+    const double ya = sqrt(pl[i]), yh = sqrt(pl[128 + i]);
+    const double y0 = remove_range_around_zero(ya - yh, 0.04);
+    const double y1 = remove_range_around_zero(ya + yh, 0.04);
+    double ty = 0.0;
+    if (y0 != y1) {
+      const double v0 = interp_signed21(g_tab.lut21[1], y0 * 1.51983458269);
+      const double v1 = interp_signed21(g_tab.lut21[1], y1 * 1.51983458269);
+      const double vy = 1.753123908348329 * (v0 - v1);
+      ty = d * vy * vy;
+    }
+    term[33 + i - 4] = ty;
+  }
+  __syncwarp();
+  double s = 0.0;
+  if (lane < 3) {
+    const double* t = term + 33 * lane;
+    for (int i = 0; i < 33; ++i) s += t[i];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    ac[c] = __shfl_sync(0xffffffffu, s, c);
+    dc[c] = __shfl_sync(0xffffffffu, dcv[c], 0);
+    edge[c] = __shfl_sync(0xffffffffu, edv[c], 0);
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Integer 8x8 IDCT (guetzli/idct.cc:29-161) in direct matrix form: exact integer arithmetic, so
+// the result is identical to the reference's factored evaluation.
+// ---------------------------------------------------------------------------------------------
+__constant__ const int kIdctBasis[64] = {
+    8192, 11363, 10703, 9633,   8192,  6437,   4433,   2260,   8192, 9633,   4433,   -2259, -8192,
+    -11362, -10704, -6436,      8192,  6437,   -4433,  -11362, -8192, 2261,  10704,  9633,  8192,
+    2260,  -10703, -6436, 8192, 9633,  -4433,  -11363, 8192,   -2260, -10703, 6436,  8192,  -9633,
+    -4433, 11363,  8192,  -6437, -4433, 11362, -8192,  -2261,  10704, -9633, 8192,   -9633, 4433,
+    2259,  -8192,  11362, -10704, 6436, 8192,  -11363, 10703,  -9633, 8192,  -6437,  4433,  -2260};
+
+// out[x] = sum_u basis[8x+u] * in[u]
+__device__ __forceinline__ void idct_1d(const int in[8], int out[8]) {
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    int acc = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += kIdctBasis[8 * x + u] * in[u];
+    out[x] = acc;
+  }
+}
+__device__ __forceinline__ int idct_col_round(int v) {  // >>11 with rounding, kept as coeff_t
+  return static_cast<int>(static_cast<int16_t>((v + (1 << 10)) >> 11));
+}
+__device__ __forceinline__ int idct_row_round(int v) {  // >>18 with rounding, +128, clamp
+  const int p = (v + (257 << 17)) >> 18;
+  return min(255, max(0, p));
+}
+
+// YCbCr -> RGB, libjpeg 16.16 tables regenerated arithmetically (guetzli/color_transform.h:22-219)
+__device__ __forceinline__ void ycbcr_to_rgb(int y, int cb, int cr, int& r, int& g, int& b) {
+  cb -= 128;
+  cr -= 128;
+  r = min(255, max(0, y + ((91881 * cr + 32768) >> 16)));
+  g = min(255, max(0, y + ((-46802 * cr + (-22554 * cb + 32768)) >> 16)));
+  b = min(255, max(0, y + ((116130 * cb + 32768) >> 16)));
+}
+
+// Quantize (guetzli/quantize.h:24-29)
+__device__ __forceinline__ int quantize_coeff(int raw, int q) {
+  const int r = raw % q;
+  const int delta = 2 * r > q ? q - r : (-2) * r > q ? -q - r : -r;
+  return static_cast<int>(static_cast<int16_t>(raw + delta));
+}
+
+}  // namespace gzb

@@ -1,0 +1,719 @@
+// gzb_kernels.cuh -- sm_100a kernels of the full-image butteraugli Compare pipeline.
+//
+// Data layout in HBM (all resident per context, see gzb_context.cuh):
+//   * full-resolution float planes: row pitch P = round_up(W, 32) floats (128-byte rows)
+//   * candidate / original sRGB8 planes: planar u8, same pitch P, height padded to 8*ceil(H/8)
+//   * coefficients: int16 [3][B8][64], block-major (OutputImageComponent::coeffs layout)
+//   * res-grid maps (step 3): [ceil(H/3)][ceil(W/3)] with 3 interleaved floats where noted
+//   * decimated blur outputs: [ny][pitch round_up(nx,32)]
+// Grids are sized from the image; the heavy warp-per-cell kernels run persistent CTAs in
+// multiples of the SM count.
+#pragma once
+#include "gzb_device_math.cuh"
+
+namespace gzb {
+
+constexpr int kMaxTaps = 65;           // radius <= 32
+__constant__ float c_taps[12][kMaxTaps];  // one row per blur kernel (see BlurKind)
+
+__host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------------
+// K0: interleaved sRGB8 -> planar u8 with pitch (upload helper)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_deinterleave_rgb(const uint8_t* __restrict__ rgb, int W, int H, int P,
+                                   uint8_t* __restrict__ planes, size_t plane_stride) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= W || y >= H) return;
+  const uint8_t* s = rgb + 3 * (static_cast<size_t>(y) * W + x);
+  const size_t o = static_cast<size_t>(y) * P + x;
+  planes[o] = s[0];
+  planes[plane_stride + o] = s[1];
+  planes[2 * plane_stride + o] = s[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: coefficients -> candidate sRGB8 planes (integer IDCT + YCbCr->RGB).
+//   guetzli/output_image.cc:124-146 (SetCoeffBlock), 68-98 (ToPixels), 642-652 (ToSRGB);
+//   in 4:4:4 the stored pixel is idct<<4 and (p+8-(x&1))>>4 returns the idct value.
+// CTA = 256 threads = 32 blocks x 8 threads; thread t owns column t, then row t.
+// Optionally applies a global quantiser first (ApplyGlobalQuantization, output_image.cc:349-360)
+// or the coeff*quant copy (CopyFromJpegComponent, 212-228) and writes the coefficients back.
+// ---------------------------------------------------------------------------------------------
+enum CoeffOp { kCoeffKeep = 0, kCoeffQuantize = 1, kCoeffScale = 2 };
+
+template <int OP>
+__global__ void __launch_bounds__(256)
+k_coeffs_to_rgb8(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t comp_stride,
+                 const int* __restrict__ q192, int bw, int nblocks, int P,
+                 uint8_t* __restrict__ planes, size_t plane_stride) {
+  __shared__ int s_in[32][8][9];
+  __shared__ uint8_t s_px[3][32][8][8];
+  const int lb = threadIdx.x >> 3, t = threadIdx.x & 7;
+  const int b = blockIdx.x * 32 + lb;
+  const bool live = b < nblocks;
+#pragma unroll 1
+  for (int c = 0; c < 3; ++c) {
+    if (live) {
+      const int4 v = reinterpret_cast<const int4*>(src + c * comp_stride)[static_cast<size_t>(b) * 8 + t];
+      int e[8] = {static_cast<int16_t>(v.x & 0xffff), v.x >> 16, static_cast<int16_t>(v.y & 0xffff), v.y >> 16,
+                  static_cast<int16_t>(v.z & 0xffff), v.z >> 16, static_cast<int16_t>(v.w & 0xffff), v.w >> 16};
+      if (OP != kCoeffKeep) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int q = q192[64 * c + 8 * t + k];
+          e[k] = OP == kCoeffQuantize ? quantize_coeff(e[k], q)
+                                      : static_cast<int>(static_cast<int16_t>(e[k] * q));
+        }
+        int4 o;
+        o.x = (e[0] & 0xffff) | (e[1] << 16);
+        o.y = (e[2] & 0xffff) | (e[3] << 16);
+        o.z = (e[4] & 0xffff) | (e[5] << 16);
+        o.w = (e[6] & 0xffff) | (e[7] << 16);
+        reinterpret_cast<int4*>(dst + c * comp_stride)[static_cast<size_t>(b) * 8 + t] = o;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_in[lb][t][k] = e[k];  // row t of the coefficient block
+    }
+    __syncthreads();
+    int col[8], out[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) col[u] = s_in[lb][u][t];  // column t
+    __syncthreads();
+    idct_1d(col, out);
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s_in[lb][y][t] = idct_col_round(out[y]);
+    __syncthreads();
+    int row[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) row[u] = s_in[lb][t][u];
+    idct_1d(row, out);
+#pragma unroll
+    for (int x = 0; x < 8; ++x) s_px[c][lb][t][x] = static_cast<uint8_t>(idct_row_round(out[x]));
+    __syncthreads();
+  }
+  if (!live) return;
+  const int bx = b % bw, by = b / bw;
+  uint32_t pr[2] = {0, 0}, pg[2] = {0, 0}, pb[2] = {0, 0};
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    int r, g, bl;
+    ycbcr_to_rgb(s_px[0][lb][t][x], s_px[1][lb][t][x], s_px[2][lb][t][x], r, g, bl);
+    pr[x >> 2] |= static_cast<uint32_t>(r) << (8 * (x & 3));
+    pg[x >> 2] |= static_cast<uint32_t>(g) << (8 * (x & 3));
+    pb[x >> 2] |= static_cast<uint32_t>(bl) << (8 * (x & 3));
+  }
+  const size_t o = static_cast<size_t>(8 * by + t) * P + 8 * bx;
+  *reinterpret_cast<uint2*>(planes + o) = make_uint2(pr[0], pr[1]);
+  *reinterpret_cast<uint2*>(planes + plane_stride + o) = make_uint2(pg[0], pg[1]);
+  *reinterpret_cast<uint2*>(planes + 2 * plane_stride + o) = make_uint2(pb[0], pb[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: sRGB8 planes -> XYB planes: LUT -> blur sigma 1.1 (5 taps, separable, border-renormalised)
+//     -> opsin dynamics. One 32x32 output tile per CTA, halo 2, all three channels in shared
+//     memory. butteraugli.cc:943-974 with Blur (100-148) inlined; scale tables from the host.
+// ---------------------------------------------------------------------------------------------
+constexpr int kOpsTile = 32;
+__global__ void __launch_bounds__(256)
+k_opsin_dynamics(const uint8_t* __restrict__ planes, size_t plane_stride, int W, int H, int P,
+                 const double* __restrict__ scale_x, const double* __restrict__ scale_y,
+                 float* __restrict__ xyb, size_t xyb_stride) {
+  __shared__ float s_lin[3][kOpsTile + 4][kOpsTile + 4 + 1];
+  __shared__ float s_h[3][kOpsTile + 4][kOpsTile + 1];
+  __shared__ float s_lut[256];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int x0 = blockIdx.x * kOpsTile, y0 = blockIdx.y * kOpsTile;
+  s_lut[tid] = g_tab.srgb_lin[tid];
+  __syncthreads();
+  for (int i = tid; i < 3 * 36 * 36; i += 256) {
+    const int c = i / (36 * 36), rem = i - c * 36 * 36, ly = rem / 36, lx = rem - ly * 36;
+    const int gx = x0 + lx - 2, gy = y0 + ly - 2;
+    float v = 0.0f;
+    if (gx >= 0 && gx < W && gy >= 0 && gy < H)
+      v = s_lut[planes[c * plane_stride + static_cast<size_t>(gy) * P + gx]];
+    s_lin[c][ly][lx] = v;
+  }
+  __syncthreads();
+  const float t0 = c_taps[0][0], t1 = c_taps[0][1], t2 = c_taps[0][2], t3 = c_taps[0][3], t4 = c_taps[0][4];
+  // horizontal pass for 36 rows x 32 columns x 3 channels
+  for (int i = tid; i < 3 * 36 * 32; i += 256) {
+    const int c = i / (36 * 32), rem = i - c * 36 * 32, ly = rem >> 5, lx = rem & 31;
+    const int gx = x0 + lx;
+    float r = 0.0f;
+    if (gx < W) {
+      const float* p = &s_lin[c][ly][lx];
+      double acc = 0.0;
+      acc += static_cast<double>(p[0] * t0);
+      acc += static_cast<double>(p[1] * t1);
+      acc += static_cast<double>(p[2] * t2);
+      acc += static_cast<double>(p[3] * t3);
+      acc += static_cast<double>(p[4] * t4);
+      r = static_cast<float>(acc * scale_x[gx]);
+    }
+    s_h[c][ly][lx] = r;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x, gx = x0 + lx;
+  if (gx >= W) return;
+#pragma unroll 1
+  for (int ly = threadIdx.y; ly < kOpsTile; ly += 8) {
+    const int gy = y0 + ly;
+    if (gy >= H) break;
+    const double sy = scale_y[gy];
+    float bl[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double acc = 0.0;
+      // rows outside the image hold zeros; rows of the H pass outside the image are skipped by
+      // the reference -- they contribute +0.0 here.
+      const bool in0 = gy - 2 >= 0, in1 = gy - 1 >= 0, in3 = gy + 1 < H, in4 = gy + 2 < H;
+      acc += static_cast<double>((in0 ? s_h[c][ly][lx] : 0.0f) * t0);
+      acc += static_cast<double>((in1 ? s_h[c][ly + 1][lx] : 0.0f) * t1);
+      acc += static_cast<double>(s_h[c][ly + 2][lx] * t2);
+      acc += static_cast<double>((in3 ? s_h[c][ly + 3][lx] : 0.0f) * t3);
+      acc += static_cast<double>((in4 ? s_h[c][ly + 4][lx] : 0.0f) * t4);
+      bl[c] = static_cast<float>(acc * sy);
+    }
+    float X, Y, B;
+    opsin_pixel(bl[0], bl[1], bl[2], s_lin[0][ly + 2][lx + 2], s_lin[1][ly + 2][lx + 2],
+                s_lin[2][ly + 2][lx + 2], X, Y, B);
+    const size_t o = static_cast<size_t>(gy) * P + gx;
+    xyb[o] = X;
+    xyb[xyb_stride + o] = Y;
+    xyb[2 * xyb_stride + o] = B;
+  }
+}
+
+// Float-plane variant used by the reference-shaped stage entry point (gzb_opsin_dynamics_image):
+// input linear RGB float planes instead of sRGB8.
+__global__ void __launch_bounds__(256)
+k_opsin_dynamics_f32(const float* __restrict__ lin, size_t lin_stride, int W, int H, int P,
+                     const double* __restrict__ scale_x, const double* __restrict__ scale_y,
+                     float* __restrict__ xyb, size_t xyb_stride) {
+  __shared__ float s_lin[3][kOpsTile + 4][kOpsTile + 4 + 1];
+  __shared__ float s_h[3][kOpsTile + 4][kOpsTile + 1];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int x0 = blockIdx.x * kOpsTile, y0 = blockIdx.y * kOpsTile;
+  for (int i = tid; i < 3 * 36 * 36; i += 256) {
+    const int c = i / (36 * 36), rem = i - c * 36 * 36, ly = rem / 36, lx = rem - ly * 36;
+    const int gx = x0 + lx - 2, gy = y0 + ly - 2;
+    float v = 0.0f;
+    if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = lin[c * lin_stride + static_cast<size_t>(gy) * P + gx];
+    s_lin[c][ly][lx] = v;
+  }
+  __syncthreads();
+  const float t0 = c_taps[0][0], t1 = c_taps[0][1], t2 = c_taps[0][2], t3 = c_taps[0][3], t4 = c_taps[0][4];
+  for (int i = tid; i < 3 * 36 * 32; i += 256) {
+    const int c = i / (36 * 32), rem = i - c * 36 * 32, ly = rem >> 5, lx = rem & 31;
+    const int gx = x0 + lx;
+    float r = 0.0f;
+    if (gx < W) {
+      const float* p = &s_lin[c][ly][lx];
+      double acc = 0.0;
+      acc += static_cast<double>(p[0] * t0);
+      acc += static_cast<double>(p[1] * t1);
+      acc += static_cast<double>(p[2] * t2);
+      acc += static_cast<double>(p[3] * t3);
+      acc += static_cast<double>(p[4] * t4);
+      r = static_cast<float>(acc * scale_x[gx]);
+    }
+    s_h[c][ly][lx] = r;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x, gx = x0 + lx;
+  if (gx >= W) return;
+#pragma unroll 1
+  for (int ly = threadIdx.y; ly < kOpsTile; ly += 8) {
+    const int gy = y0 + ly;
+    if (gy >= H) break;
+    const double sy = scale_y[gy];
+    float bl[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double acc = 0.0;
+      const bool in0 = gy - 2 >= 0, in1 = gy - 1 >= 0, in3 = gy + 1 < H, in4 = gy + 2 < H;
+      acc += static_cast<double>((in0 ? s_h[c][ly][lx] : 0.0f) * t0);
+      acc += static_cast<double>((in1 ? s_h[c][ly + 1][lx] : 0.0f) * t1);
+      acc += static_cast<double>(s_h[c][ly + 2][lx] * t2);
+      acc += static_cast<double>((in3 ? s_h[c][ly + 3][lx] : 0.0f) * t3);
+      acc += static_cast<double>((in4 ? s_h[c][ly + 4][lx] : 0.0f) * t4);
+      bl[c] = static_cast<float>(acc * sy);
+    }
+    float X, Y, B;
+    opsin_pixel(bl[0], bl[1], bl[2], s_lin[0][ly + 2][lx + 2], s_lin[1][ly + 2][lx + 2],
+                s_lin[2][ly + 2][lx + 2], X, Y, B);
+    const size_t o = static_cast<size_t>(gy) * P + gx;
+    xyb[o] = X;
+    xyb[xyb_stride + o] = Y;
+    xyb[2 * xyb_stride + o] = B;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: MaskHighIntensityChange (butteraugli.cc:791-843). One pixel per thread; neighbours via L1.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_mask_high_intensity_change(const float* __restrict__ a, const float* __restrict__ b, size_t stride,
+                             int W, int H, int P, float* __restrict__ oa, float* __restrict__ ob) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const size_t ix = static_cast<size_t>(y) * P + x;
+  const float c0[3] = {a[ix], a[stride + ix], a[2 * stride + ix]};
+  const float c1[3] = {b[ix], b[stride + ix], b[2 * stride + ix]};
+  const float* ya = a + stride;
+  const float* yb = b + stride;
+  double worst = -1;
+  if (x > 0) { const double d = mhic_sqdiff(ya[ix - 1], yb[ix - 1], c0[1], c1[1]); if (worst < d) worst = d; }
+  if (x + 1 < W) { const double d = mhic_sqdiff(ya[ix + 1], yb[ix + 1], c0[1], c1[1]); if (worst < d) worst = d; }
+  if (y > 0) { const double d = mhic_sqdiff(ya[ix - P], yb[ix - P], c0[1], c1[1]); if (worst < d) worst = d; }
+  if (y + 1 < H) { const double d = mhic_sqdiff(ya[ix + P], yb[ix + P], c0[1], c1[1]); if (worst < d) worst = d; }
+  float o0[3], o1[3];
+  mhic_pixel(c0, c1, worst, o0, o1);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    oa[c * stride + ix] = o0[c];
+    ob[c * stride + ix] = o1[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: separable Gaussian on an output lattice (butteraugli.cc:68-148).
+//   H pass: tmp[y][ox]  = float( sum_j double(in[y][j] * tap[j-x+r]) * scale_x[ox] ), x = x0+ox*sx
+//   V pass: out[oy][ox] = float( sum_j double(tmp[j][ox] * tap[j-y+r]) * scale_y[oy] ), y = y0+oy*sy
+// Taps outside the image read 0.0f (adds +0.0: identical to the reference skipping them); the
+// border renormalisation lives in the host-built scale tables. UPS>1 reads a nearest-lower
+// replicated input (in[(y/UPS)][x/UPS]) -- used for the 3x3-upsampled diffmap.
+// Shared-memory tiles with halos; rows are read with coalesced 128-byte lines.
+// ---------------------------------------------------------------------------------------------
+struct BlurGeom {
+  int in_w, in_h;    // logical input size (after UPS replication)
+  int in_pitch;      // physical input pitch (floats)
+  int r, kind;       // radius, row of c_taps
+  int x0, sx, nx;    // output columns
+  int y0, sy, ny;    // output rows
+  int tmp_pitch;     // pitch of tmp and out
+  int ups;
+  int oxn, oyn;      // outputs per CTA along x (H pass) / y (V pass): tile must fit shared memory
+};
+
+constexpr int kBhOx = 32, kBhRows = 16, kBhMaxSpan = kBhOx * 4 + 2 * 32;  // 192
+template <int UPS>
+__global__ void __launch_bounds__(256)
+k_blur_h(const float* __restrict__ in, size_t in_stride, BlurGeom g,
+         const double* __restrict__ scale_x, float* __restrict__ tmp, size_t tmp_stride) {
+  __shared__ float s[kBhRows][kBhMaxSpan + 1];
+  in += blockIdx.z * in_stride;
+  tmp += blockIdx.z * tmp_stride;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int ox0 = blockIdx.x * g.oxn, yb = blockIdx.y * kBhRows;
+  const int xs = g.x0 + ox0 * g.sx - g.r;  // first input column of the tile
+  const int span = (g.oxn - 1) * g.sx + 2 * g.r + 1;
+  for (int i = tid; i < kBhRows * span; i += 256) {
+    const int ly = i / span, k = i - ly * span;
+    const int gx = xs + k, gy = yb + ly;
+    float v = 0.0f;
+    if (gx >= 0 && gx < g.in_w && gy < g.in_h)
+      v = UPS == 1 ? in[static_cast<size_t>(gy) * g.in_pitch + gx]
+                   : in[static_cast<size_t>(gy / UPS) * g.in_pitch + gx / UPS];
+    s[ly][k] = v;
+  }
+  __syncthreads();
+  const int ox = ox0 + threadIdx.x;
+  if (ox >= g.nx || threadIdx.x >= g.oxn) return;
+  const double sc = scale_x[ox];
+  const float* taps = c_taps[g.kind];
+  const int nt = 2 * g.r + 1;
+#pragma unroll
+  for (int rr = 0; rr < kBhRows; rr += 8) {
+    const int ly = threadIdx.y + rr, gy = yb + ly;
+    if (gy >= g.in_h) break;
+    const float* p = &s[ly][threadIdx.x * g.sx];
+    double acc = 0.0;
+    for (int k = 0; k < nt; ++k) acc += static_cast<double>(p[k] * taps[k]);
+    tmp[static_cast<size_t>(gy) * g.tmp_pitch + ox] = static_cast<float>(acc * sc);
+  }
+}
+
+constexpr int kBvOy = 16, kBvMaxRows = (kBvOy - 1) * 4 + 2 * 32 + 1;  // 125
+__global__ void __launch_bounds__(256)
+k_blur_v(const float* __restrict__ tmp, size_t tmp_stride, BlurGeom g,
+         const double* __restrict__ scale_y, float* __restrict__ out, size_t out_stride,
+         int out_pitch) {
+  __shared__ float s[kBvMaxRows][33];
+  tmp += blockIdx.z * tmp_stride;
+  out += blockIdx.z * out_stride;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * g.oyn;
+  const int ys = g.y0 + oy0 * g.sy - g.r;
+  const int rows = (g.oyn - 1) * g.sy + 2 * g.r + 1;
+  for (int i = tid; i < rows * 32; i += 256) {
+    const int ly = i >> 5, lx = i & 31;
+    const int gy = ys + ly, gx = ox0 + lx;
+    float v = 0.0f;
+    if (gy >= 0 && gy < g.in_h && gx < g.nx) v = tmp[static_cast<size_t>(gy) * g.tmp_pitch + gx];
+    s[ly][lx] = v;
+  }
+  __syncthreads();
+  const int ox = ox0 + threadIdx.x;
+  if (ox >= g.nx) return;
+  const float* taps = c_taps[g.kind];
+  const int nt = 2 * g.r + 1;
+#pragma unroll
+  for (int rr = 0; rr < kBvOy; rr += 8) {
+    const int loy = threadIdx.y + rr, oy = oy0 + loy;
+    if (oy >= g.ny || loy >= g.oyn) break;
+    double acc = 0.0;
+    const int base = loy * g.sy;
+    for (int k = 0; k < nt; ++k) acc += static_cast<double>(s[base + k][threadIdx.x] * taps[k]);
+    out[static_cast<size_t>(oy) * out_pitch + ox] = static_cast<float>(acc * scale_y[oy]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: EdgeDetectorMap consumer (butteraugli.cc:689-738, 1135-1148). One res cell per thread,
+// reads the six small-sigma blurred planes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_edge_detector_map(const float* __restrict__ bl0, const float* __restrict__ bl1, size_t stride,
+                    int W, int H, int P, int rxs, float* __restrict__ out) {
+  const int rx = blockIdx.x * 32 + threadIdx.x, ry = blockIdx.y * 8 + threadIdx.y;
+  const int res_x = 3 * rx, res_y = 3 * ry;
+  if (!(res_x + 5 < W && res_y + 5 < H)) return;
+  const int px = min(res_x, W - 8), py = min(res_y, H - 8);
+  const double w = 0.711100840192;
+  double acc[3] = {0.0, 0.0, 0.0};
+  int count = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = px + (k >= 2 ? 7 : 0), y = py + ((k & 1) ? 7 : 0);
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+      size_t i1, i2;
+      if (dir == 0) {
+        if (!(x >= 3 && x + 3 < W)) continue;
+        i1 = static_cast<size_t>(y) * P + (x - 3);
+        i2 = i1 + 6;
+      } else {
+        if (!(y >= 3 && y + 3 < H)) continue;
+        i1 = static_cast<size_t>(y - 3) * P + x;
+        i2 = i1 + 6 * static_cast<size_t>(P);
+      }
+      double d0[3], d1[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        d0[c] = w * (bl0[c * stride + i1] - bl0[c * stride + i2]);  // float difference, widened
+        d1[c] = w * (bl1[c * stride + i1] - bl1[c * stride + i2]);
+      }
+      lowfreq_sq_acc(d0, d1, 1.0, acc);
+      ++count;
+    }
+  }
+  const double mul = 0.01617112696 * 8.0 / count;
+  float* o = out + 3 * (static_cast<size_t>(ry) * rxs + rx);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c] = static_cast<float>(0.0 + mul * acc[c]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: BlockDiffMap (butteraugli.cc:1081-1117): one warp per res cell, persistent CTAs.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBdmWarps = 4;
+__global__ void __launch_bounds__(32 * kBdmWarps)
+k_block_diff_map(const float* __restrict__ a, const float* __restrict__ b, size_t stride, int W,
+                 int H, int P, int rxs, int ncx, int ncy, float* __restrict__ dc_out,
+                 float* __restrict__ ac_out) {
+  __shared__ float s_a[kBdmWarps][192];
+  __shared__ float s_b[kBdmWarps][192];
+  __shared__ double s_ws[kBdmWarps][kBlockDiffScratchDoubles];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = ncx * ncy;
+  for (int cell = blockIdx.x * kBdmWarps + warp; cell < total; cell += gridDim.x * kBdmWarps) {
+    const int ry = cell / ncx, rx = cell - ry * ncx;
+    const int ox = min(3 * rx, W - 8), oy = min(3 * ry, H - 8);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int i = lane + 32 * k, c = i >> 6, y = (i >> 3) & 7, x = i & 7;
+      const size_t g = c * stride + static_cast<size_t>(oy + y) * P + ox + x;
+      s_a[warp][i] = a[g];
+      s_b[warp][i] = b[g];
+    }
+    __syncwarp();
+    double dc[3], ac[3], edge[3];
+    warp_block_diff(s_a[warp], s_b[warp], s_ws[warp], dc, ac, edge);
+    if (lane < 3) {
+      const size_t o = 3 * (static_cast<size_t>(ry) * rxs + rx) + lane;
+      dc_out[o] = static_cast<float>(lane == 0 ? dc[0] : lane == 1 ? dc[1] : dc[2]);
+      ac_out[o] = static_cast<float>(lane == 0 ? ac[0] : lane == 1 ? ac[1] : ac[2]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: EdgeDetectorLowFreq consumer (butteraugli.cc:1164-1204). Reads the decimated sigma-14 maps:
+// blurred[y][x] == small[y/4][x/4]. One lattice point per thread; adds into block_diff_ac.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_edge_lowfreq(const float* __restrict__ s0, const float* __restrict__ s1, size_t stride,
+               int spitch, int step, int W, int H, int rxs, float* __restrict__ ac_io) {
+  const int cx = blockIdx.x * 32 + threadIdx.x, cy = blockIdx.y * 8 + threadIdx.y;
+  const int x = 3 * cx, y = 3 * cy;
+  if (!(x + 8 < W && y + 8 < H)) return;
+  const int ox[4] = {x + 8, x, x + 6, x - 6};
+  const int oy[4] = {y, y + 8, y + 6, y + 6};
+  const size_t i0 = static_cast<size_t>(y / step) * spitch + x / step;
+  double best[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double d[3] = {0.0, 0.0, 0.0};
+    if (!(k == 3 && x < 8)) {
+      const size_t i2 = static_cast<size_t>(oy[k] / step) * spitch + ox[k] / step;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float f = (s1[c * stride + i0] - s0[c * stride + i0]) +
+                        (s0[c * stride + i2] - s1[c * stride + i2]);
+        d[c] = f;
+      }
+    }
+    double sq[3] = {0.0, 0.0, 0.0};
+    lowfreq_sq_acc0(d, 1.0, sq);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) best[c] = best[c] < sq[c] ? sq[c] : best[c];
+  }
+  float* o = ac_io + 3 * (static_cast<size_t>(cy) * rxs + cx + 2);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c] += static_cast<float>(10 * best[c]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8: front of Mask (butteraugli.cc:1440-1493, 1379-1438, 1332-1376) fused per channel:
+//   DiffPrecompute -> Average5x5 (reference float summation order) -> MinSquareVal(4,0).
+// 32x32 output tile per CTA; blockIdx.z = channel (the three channels are independent).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMpT = 32;
+__global__ void __launch_bounds__(256)
+k_mask_front(const float* __restrict__ a, const float* __restrict__ b, size_t stride, int W, int H,
+             int P, float* __restrict__ out) {
+  __shared__ float s_a[kMpT + 7][kMpT + 7 + 1];   // xyb tile, origin (-2,-2), 39 x 39
+  __shared__ float s_b[kMpT + 7][kMpT + 7 + 1];
+  __shared__ float s_p[kMpT + 5][kMpT + 5 + 1];   // precompute, origin (-1,-1)
+  __shared__ float s_v[kMpT + 3][kMpT + 3 + 1];   // averaged, origin (0,0)
+  const int c = blockIdx.z;
+  a += c * stride;
+  b += c * stride;
+  out += c * stride;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int x0 = blockIdx.x * kMpT, y0 = blockIdx.y * kMpT;
+  // xyb tile, origin (-2,-2): the last column/row use their left/upper neighbour instead.
+  for (int i = tid; i < 39 * 39; i += 256) {
+    const int ly = i / 39, lx = i - ly * 39;
+    const int gx = x0 + lx - 2, gy = y0 + ly - 2;
+    float va = 0.0f, vb = 0.0f;
+    if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+      const size_t g = static_cast<size_t>(gy) * P + gx;
+      va = a[g];
+      vb = b[g];
+    }
+    s_a[ly][lx] = va;
+    s_b[ly][lx] = vb;
+  }
+  __syncthreads();
+  for (int i = tid; i < 37 * 37; i += 256) {
+    const int ly = i / 37, lx = i - ly * 37;
+    const int gx = x0 + lx - 1, gy = y0 + ly - 1;
+    float r = 0.0f;
+    if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+      const int tx = lx + 1, ty = ly + 1;  // position in the xyb tile
+      const int hx = gx + 1 < W ? tx + 1 : tx - 1;
+      const int vy = gy + 1 < H ? ty + 1 : ty - 1;
+      const double h0 = highfreq_val(c, s_a[ty][tx] - s_a[ty][hx]);
+      const double h1 = highfreq_val(c, s_b[ty][tx] - s_b[ty][hx]);
+      const double v0 = highfreq_val(c, s_a[ty][tx] - s_a[vy][tx]);
+      const double v1 = highfreq_val(c, s_b[ty][tx] - s_b[vy][tx]);
+      const double sup0 = fabs(h0) + fabs(v0), sup1 = fabs(h1) + fabs(v1);
+      r = static_cast<float>(sup1 < sup0 ? sup1 : sup0);
+    }
+    s_p[ly][lx] = r;
+  }
+  __syncthreads();
+  const float w = 0.679144890667f;
+  const float scale = 1.0f / (5.0f + 4 * w);
+  for (int i = tid; i < 35 * 35; i += 256) {
+    const int ly = i / 35, lx = i - ly * 35;
+    const int gx = x0 + lx, gy = y0 + ly;
+    float r = __int_as_float(0x7f800000);  // +inf outside the image: ignored by the min
+    if (gx < W && gy < H) {
+      const int px = lx + 1, py = ly + 1;
+      // Outside-image neighbours hold 0.0f in s_p; the reference drops them (x + 0 == x).
+      float acc = s_p[py][px];
+      acc += s_p[py - 1][px - 1] * w;
+      acc += s_p[py - 1][px];
+      acc += s_p[py - 1][px + 1] * w;
+      acc += s_p[py][px - 1];
+      acc += s_p[py][px + 1];
+      acc += s_p[py + 1][px - 1] * w;
+      acc += s_p[py + 1][px];
+      acc += s_p[py + 1][px + 1] * w;
+      r = acc * scale;
+    }
+    s_v[ly][lx] = r;
+  }
+  __syncthreads();
+  const int gx = x0 + threadIdx.x;
+  if (gx >= W) return;
+#pragma unroll
+  for (int ly = threadIdx.y; ly < kMpT; ly += 8) {
+    const int gy = y0 + ly;
+    if (gy >= H) break;
+    float m = s_v[ly][threadIdx.x];
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx) m = fminf(m, s_v[ly + dy][threadIdx.x + dx]);
+    out[static_cast<size_t>(gy) * P + gx] = m;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9: mask LUTs at the sampled pixel + CombineChannels + sqrt of CalculateDiffmap
+//     (butteraugli.cc:1538-1566, 1207-1231, 1002-1008). One res cell per thread.
+//     Blurred mask planes are read from their lattices: channel c value at pixel (px,py) is
+//     m[c][(py - my0[c]) / msy[c]][(px - mx0[c]) / msx[c]].
+// ---------------------------------------------------------------------------------------------
+struct MaskSample {
+  const float* m[3];
+  int pitch[3], x0[3], sx[3], y0[3], sy[3];
+};
+__device__ __forceinline__ void mask_at(const MaskSample& ms, int px, int py, double mask[3],
+                                        double mask_dc[3], bool want_dc) {
+  const double wmul[3] = {232.206464018, 22.9455222245, 503.962310606};
+  const float gs = static_cast<float>((1.0 / 14.921561160295326) * (1.0 / 14.921561160295326));
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float s = ms.m[c][static_cast<size_t>((py - ms.y0[c]) / ms.sy[c]) * ms.pitch[c] +
+                            (px - ms.x0[c]) / ms.sx[c]];
+    const double p = wmul[c] * static_cast<double>(s);
+    float m = static_cast<float>(interp_clamp512(g_tab.mask_lut[c], p));
+    m *= gs;
+    mask[c] = m;
+    if (want_dc) {
+      float d = static_cast<float>(interp_clamp512(g_tab.mask_lut[3 + c], p));
+      d *= gs;
+      mask_dc[c] = d;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_combine(MaskSample ms, const float* __restrict__ dc, const float* __restrict__ ac,
+          const float* __restrict__ edm, int W, int H, int rxs, int rys, int sq_pitch,
+          float* __restrict__ sq) {
+  const int rx = blockIdx.x * 32 + threadIdx.x, ry = blockIdx.y * 8 + threadIdx.y;
+  if (rx >= rxs || ry >= rys) return;
+  float r = 0.0f;
+  if (3 * rx + 5 < W && 3 * ry + 5 < H) {
+    double mask[3], mdc[3];
+    mask_at(ms, 3 * rx + 3, 3 * ry + 3, mask, mdc, true);
+    const size_t o = 3 * (static_cast<size_t>(ry) * rxs + rx);
+    const double t0 = dc[o] * mdc[0] + dc[o + 1] * mdc[1] + dc[o + 2] * mdc[2];
+    const double t1 = ac[o] * mask[0] + ac[o + 1] * mask[1] + ac[o + 2] * mask[2];
+    const double t2 = edm[o] * mask[0] + edm[o + 1] * mask[1] + edm[o + 2] * mask[2];
+    const float v = static_cast<float>(t0 + t1 + t2);
+    r = v < (1.0 / (100.0f * 100.0f)) ? 100.0f * v : sqrtf(v);
+  }
+  sq[static_cast<size_t>(ry) * sq_pitch + rx] = r;
+}
+
+// Sampled mask only (StartBlockComparisons: mask_xyz_ at each 8x8 block's top-left pixel;
+// guetzli/butteraugli_comparator.cc:72-79, 148-151). out: [B8][3] floats.
+__global__ void k_block_mask_scale(MaskSample ms, int bw, int bh, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bw * bh) return;
+  double mask[3], unused[3];
+  mask_at(ms, 8 * (b % bw), 8 * (b / bw), mask, unused, false);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[3 * b + c] = static_cast<float>(mask[c]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K10: tail of CalculateDiffmap (butteraugli.cc:1009-1043) + score (1233-1240):
+//   diffmap = (up + 24.82f * blur(up_crop)) * 1/25.82, max-reduced into *dist_bits.
+// `sq` is the res-grid sqrt map, `small` the decimated (step 2) sigma-8.85 blur of the crop.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_diffmap_final(const float* __restrict__ sq, int sq_pitch, const float* __restrict__ small,
+                int small_pitch, int bstep, int W, int H, int out_pitch, float* __restrict__ out,
+                unsigned int* __restrict__ dist_bits) {
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  float v = 0.0f;
+  if (x < W && y < H) {
+    float up = 0.0f;
+    if (x >= 2 && y >= 2) {
+      const int cx = (x - 2) / 3, cy = (y - 2) / 3;
+      if (3 * cx + 5 < W && 3 * cy + 5 < H) up = sq[static_cast<size_t>(cy) * sq_pitch + cx];
+    }
+    v = up;
+    if (x >= 2 && y >= 2 && x - 2 < W - 5 && y - 2 < H - 5) {
+      const float mul1 = static_cast<float>(24.8235314874);
+      v += mul1 * small[static_cast<size_t>((y - 2) / bstep) * small_pitch + (x - 2) / bstep];
+    }
+    v *= static_cast<float>(1.0 / (1.0 + 24.8235314874));
+    out[static_cast<size_t>(y) * out_pitch + x] = v;
+  }
+  // all values are >= 0: unsigned ordering of the bit patterns equals float ordering
+  unsigned int bits = __float_as_uint(v > 0.0f ? v : 0.0f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+  if (threadIdx.x == 0 && bits != 0) atomicMax(dist_bits, bits);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K11: ComputeBlockErrorAdjustmentWeights (guetzli/butteraugli_comparator.cc:169-233), factor 1.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_block_max(const float* __restrict__ dm, int pitch, int W, int H, int bw, int bh,
+                            float* __restrict__ bmax) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bw * bh) return;
+  const int bx = b % bw, by = b / bw;
+  float m = 0.0f;
+  for (int y = 8 * by; y < min(H, 8 * by + 8); ++y)
+    for (int x = 8 * bx; x < min(W, 8 * bx + 8); ++x) m = fmaxf(m, dm[static_cast<size_t>(y) * pitch + x]);
+  bmax[b] = m;
+}
+// flags[b] = 1 if block b passes the per-direction test of the reference.
+__global__ void k_block_flags(const float* __restrict__ bmax, int bw, int bh, int direction, int rad,
+                              double target, unsigned char* __restrict__ flags) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bw * bh) return;
+  const int bx = b % bw, by = b / bw;
+  float local = static_cast<float>(target);
+  for (int y = max(0, by - rad); y < min(bh, by + 1 + rad); ++y)
+    for (int x = max(0, bx - rad); x < min(bw, bx + 1 + rad); ++x) local = fmaxf(local, bmax[y * bw + x]);
+  const double mine = bmax[b];
+  bool f;
+  if (direction > 0) f = mine <= target && static_cast<double>(local) <= 1.1 * target;
+  else f = !(mine <= (1 - 0.5) * target + 0.5 * static_cast<double>(local));
+  flags[b] = f ? 1 : 0;
+}
+__global__ void k_block_weights(const unsigned char* __restrict__ flags, int bw, int bh,
+                                int direction, int rad, float* __restrict__ weight) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bw * bh) return;
+  const int bx = b % bw, by = b / bw;
+  float w = 0.0f;
+  if (direction > 0) {
+    w = flags[b] ? 1.0f : 0.0f;
+  } else {
+    for (int y = max(0, by - rad); y < min(bh, by + 1 + rad); ++y)
+      for (int x = max(0, bx - rad); x < min(bw, bx + 1 + rad); ++x)
+        if (flags[y * bw + x]) {
+          const int d = max(abs(y - by), abs(x - bx));
+          w = fmaxf(w, 1.0f / (d + 1.0f));
+        }
+  }
+  weight[b] = w;
+}
+
+}  // namespace gzb

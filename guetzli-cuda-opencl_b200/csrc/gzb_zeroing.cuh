@@ -1,0 +1,323 @@
+// gzb_zeroing.cuh -- the per-8x8-block greedy coefficient-zeroing search on sm_100a.
+//
+// One warp owns one 8x8 image block for the whole greedy loop of
+// Processor::ComputeBlockZeroingOrder (guetzli/processor.cc:376-487, MODE_CPU semantics: NO early
+// break) and evaluates ButteraugliComparator::CompareBlock (guetzli/butteraugli_comparator.cc:
+// 113-163) for every trial with all block state in shared memory:
+//   candidate coefficients -> integer IDCT (incremental: only the touched column is re-transformed)
+//   -> YCbCr->sRGB->linear -> 8x8 block-local blur + opsin dynamics -> MaskHighIntensityChange
+//   against the original block -> ButteraugliBlockDiff (warp-cooperative FFTs) -> masked error.
+// Blocks are handed out through an atomic counter (work per block varies with its number of
+// non-zero coefficients). 4:4:4 only (factor 1, comp_mask selects components).
+#pragma once
+#include "gzb_device_math.cuh"
+#include "gzb_zeroing_model.h"
+
+namespace gzb {
+
+struct CoeffDataDev { int idx; float block_err; };  // guetzli/processor.h:29-32
+
+__constant__ float c_zero_csf[192];
+__constant__ float c_zero_bias[192];
+__constant__ double c_scale8[8];   // border scales of the sigma-1.1 blur on an 8-sample line
+__constant__ float c_taps11[5];    // sigma-1.1 taps
+
+struct ZeroWarpSmem {
+  double ws[kBlockDiffScratchDoubles];
+  float pg0[192];    // original block, opsin dynamics (SwitchBlock)
+  float cx[192];     // candidate block, opsin dynamics
+  float bufA[192];   // linear rgb -> fa (original after MaskHighIntensityChange)
+  float bufB[192];   // H-pass -> fb (candidate after MaskHighIntensityChange)
+  float key[192];
+  int basis[64];
+  short cf[192];     // processed coefficients
+  short colv[192];   // column-pass values of the processed state
+  short ccol[8];     // candidate's replacement column
+  unsigned char pix[192];   // Y, Cb, Cr pixels of the processed state
+  unsigned char cpx[64];    // candidate pixels of the touched component
+  unsigned char order[192]; // sorted input order
+  unsigned char ent[192];   // unsorted entries
+};
+
+// 8x8 opsin dynamics of linear rgb in `lin` (smem, [c*64+8y+x]) -> `dst`; `hb` is scratch.
+__device__ __forceinline__ void warp_block_opsin(const float* lin, float* hb, float* dst, int lane) {
+  // horizontal pass: 192 outputs, 6 per lane
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int i = lane + 32 * k, x = i & 7;
+    const float* row = lin + (i & ~7);
+    double acc = 0.0;
+#pragma unroll
+    for (int d = -2; d <= 2; ++d) {
+      const int j = x + d;
+      if (j >= 0 && j < 8) acc += static_cast<double>(row[j] * c_taps11[d + 2]);
+    }
+    hb[i] = static_cast<float>(acc * c_scale8[x]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int p = lane + 32 * k, x = p & 7, y = p >> 3;
+    float bl[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double acc = 0.0;
+#pragma unroll
+      for (int d = -2; d <= 2; ++d) {
+        const int j = y + d;
+        if (j >= 0 && j < 8) acc += static_cast<double>(hb[64 * c + 8 * j + x] * c_taps11[d + 2]);
+      }
+      bl[c] = static_cast<float>(acc * c_scale8[y]);
+    }
+    float X, Y, B;
+    opsin_pixel(bl[0], bl[1], bl[2], lin[p], lin[64 + p], lin[128 + p], X, Y, B);
+    dst[p] = X;
+    dst[64 + p] = Y;
+    dst[128 + p] = B;
+  }
+  __syncwarp();
+}
+
+// CompareBlock on the state in `s`: candidate = processed with coefficient `zidx` zeroed
+// (zidx < 0: the processed block itself). Returns the error in all lanes.
+__device__ __forceinline__ float warp_compare_block(ZeroWarpSmem& s, const float* lut, int zidx,
+                                                    int vx, int vy, const float scale[3],
+                                                    int lane) {
+  const int zc = zidx >= 0 ? zidx >> 6 : -1;
+  if (zidx >= 0) {
+    const int k = zidx & 63, kx = k & 7, ky = k >> 3;
+    // replacement column kx of component zc
+    if (lane < 8) {
+      int acc = 0;
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const int cv = v == ky ? 0 : s.cf[64 * zc + 8 * v + kx];
+        acc += s.basis[8 * lane + v] * cv;
+      }
+      s.ccol[lane] = static_cast<short>(idct_col_round(acc));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int p = lane + 32 * h, x = p & 7, y = p >> 3;
+      int acc = 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int cv = u == kx ? s.ccol[y] : s.colv[64 * zc + 8 * y + u];
+        acc += s.basis[8 * x + u] * cv;
+      }
+      s.cpx[p] = static_cast<unsigned char>(idct_row_round(acc));
+    }
+    __syncwarp();
+  }
+  // pixels -> linear rgb (window replication past the image edge, output_image.cc:85-97)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = lane + 32 * h, x = min(p & 7, vx - 1), y = min(p >> 3, vy - 1), sp = 8 * y + x;
+    const int Y = zc == 0 ? s.cpx[sp] : s.pix[sp];
+    const int Cb = zc == 1 ? s.cpx[sp] : s.pix[64 + sp];
+    const int Cr = zc == 2 ? s.cpx[sp] : s.pix[128 + sp];
+    int r, g, b;
+    ycbcr_to_rgb(Y, Cb, Cr, r, g, b);
+    s.bufA[p] = lut[r];
+    s.bufA[64 + p] = lut[g];
+    s.bufA[128 + p] = lut[b];
+  }
+  __syncwarp();
+  warp_block_opsin(s.bufA, s.bufB, s.cx, lane);
+  // MaskHighIntensityChange(8, 8, orig, cand) -> fa (bufA), fb (bufB)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = lane + 32 * h, x = p & 7, y = p >> 3;
+    const float c0[3] = {s.pg0[p], s.pg0[64 + p], s.pg0[128 + p]};
+    const float c1[3] = {s.cx[p], s.cx[64 + p], s.cx[128 + p]};
+    double worst = -1;
+    if (x > 0) { const double d = mhic_sqdiff(s.pg0[64 + p - 1], s.cx[64 + p - 1], c0[1], c1[1]); if (worst < d) worst = d; }
+    if (x < 7) { const double d = mhic_sqdiff(s.pg0[64 + p + 1], s.cx[64 + p + 1], c0[1], c1[1]); if (worst < d) worst = d; }
+    if (y > 0) { const double d = mhic_sqdiff(s.pg0[64 + p - 8], s.cx[64 + p - 8], c0[1], c1[1]); if (worst < d) worst = d; }
+    if (y < 7) { const double d = mhic_sqdiff(s.pg0[64 + p + 8], s.cx[64 + p + 8], c0[1], c1[1]); if (worst < d) worst = d; }
+    float o0[3], o1[3];
+    mhic_pixel(c0, c1, worst, o0, o1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      s.bufA[64 * c + p] = o0[c];
+      s.bufB[64 * c + p] = o1[c];
+    }
+  }
+  __syncwarp();
+  double dc[3], ac[3], edge[3];
+  warp_block_diff(s.bufA, s.bufB, s.ws, dc, ac, edge);
+  double diff = 0.0, diff_edge = 0.0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double sc = scale[c];
+    diff += dc[c] * sc;
+    diff += ac[c] * sc;
+    diff_edge += edge[c] * sc;
+  }
+  return static_cast<float>(sqrt((1 - 0.05) * diff + 0.05 * diff_edge));
+}
+
+// Rebuilds colv / pix of component c from s.cf (full IDCT, warp-cooperative).
+__device__ __forceinline__ void warp_full_idct(ZeroWarpSmem& s, int c, int lane) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = lane + 32 * h, x = p & 7, y = p >> 3;
+    int acc = 0;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) acc += s.basis[8 * y + v] * s.cf[64 * c + 8 * v + x];
+    s.colv[64 * c + p] = static_cast<short>(idct_col_round(acc));
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = lane + 32 * h, x = p & 7, y = p >> 3;
+    int acc = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += s.basis[8 * x + u] * s.colv[64 * c + 8 * y + u];
+    s.pix[64 * c + p] = static_cast<unsigned char>(idct_row_round(acc));
+  }
+  __syncwarp();
+}
+
+constexpr int kZeroWarps = 4;
+
+// mode 0: full zeroing order -> out[block*192 + r]
+// mode 1: single CompareBlock of `cur` with no zeroing -> err_out[block] (stage test entry)
+__global__ void __launch_bounds__(32 * kZeroWarps)
+k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cur,
+                size_t comp_stride, const uint8_t* __restrict__ rgb_planes, size_t plane_stride,
+                int P, int W, int H, int bw, int nblocks, const float* __restrict__ mask_scale,
+                int comp_mask, float limit, int lookahead, int mode,
+                CoeffDataDev* __restrict__ out, float* __restrict__ err_out,
+                float* __restrict__ pregamma_out, unsigned int* __restrict__ counter) {
+  __shared__ ZeroWarpSmem sm[kZeroWarps];
+  __shared__ float s_lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = g_tab.srgb_lin[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ZeroWarpSmem& s = sm[warp];
+  s.basis[lane] = kIdctBasis[lane];
+  s.basis[32 + lane] = kIdctBasis[32 + lane];
+  __syncwarp();
+  for (;;) {
+    unsigned int b = 0;
+    if (lane == 0) b = atomicAdd(counter, 1u);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= static_cast<unsigned int>(nblocks)) break;
+    const int bx = b % bw, by = b / bw;
+    const int vx = min(8, W - 8 * bx), vy = min(8, H - 8 * by);
+    // ---- load block state ----
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int i = lane + 32 * k, c = i >> 6;
+      s.cf[i] = (comp_mask >> c) & 1 ? cur[c * comp_stride + static_cast<size_t>(b) * 64 + (i & 63)] : 0;
+    }
+    // original pixels, coordinates clamped to the image (SwitchBlock, butteraugli_comparator.cc:96-105)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int p = lane + 32 * h;
+      const int x = min(8 * bx + (p & 7), W - 1), y = min(8 * by + (p >> 3), H - 1);
+      const size_t g = static_cast<size_t>(y) * P + x;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s.bufA[64 * c + p] = s_lut[rgb_planes[c * plane_stride + g]];
+    }
+    __syncwarp();
+    warp_block_opsin(s.bufA, s.bufB, s.pg0, lane);
+    if (pregamma_out) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) pregamma_out[static_cast<size_t>(b) * 192 + lane + 32 * k] = s.pg0[lane + 32 * k];
+    }
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) warp_full_idct(s, c, lane);
+    const float scale[3] = {mask_scale[3 * b], mask_scale[3 * b + 1], mask_scale[3 * b + 2]};
+    if (mode == 1) {
+      const float e = warp_compare_block(s, s_lut, -1, vx, vy, scale, lane);
+      if (lane == 0) err_out[b] = e;
+      continue;
+    }
+    // ---- input order: non-zero AC coefficients sorted by |orig|*csf + bias (stable) ----
+    int n = 0;
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k) {
+      const int i = lane + 32 * k, c = i >> 6;
+      const bool take = ((comp_mask >> c) & 1) && (i & 63) != 0 && s.cf[i] != 0;
+      const unsigned int m = __ballot_sync(0xffffffffu, take);
+      if (take) {
+        const int pos = n + __popc(m & ((1u << lane) - 1));
+        const int o = orig[c * comp_stride + static_cast<size_t>(b) * 64 + (i & 63)];
+        s.ent[pos] = static_cast<unsigned char>(i);
+        s.key[pos] = abs(o) * c_zero_csf[i] + c_zero_bias[i];
+      }
+      n += __popc(m);
+    }
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) {
+      const float ke = s.key[e];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const float kj = s.key[j];
+        rank += (kj < ke || (kj == ke && j < e)) ? 1 : 0;
+      }
+      s.order[rank] = s.ent[e];
+    }
+    __syncwarp();
+    // ---- greedy loop ----
+    CoeffDataDev* o = out + static_cast<size_t>(b) * 192;
+    int win[3];
+    int nwin = min(lookahead, n), next = nwin, nout = 0;
+    for (int i = 0; i < 3; ++i) win[i] = i < nwin ? s.order[i] : 0;
+    while (nwin > 0) {
+      float best_err = 1e17f;
+      int best_i = 0;
+      for (int i = 0; i < nwin; ++i) {
+        const float err = warp_compare_block(s, s_lut, win[i], vx, vy, scale, lane);
+        const float max_err = fmaxf(0.0f, err);
+        if (max_err < best_err) { best_err = max_err; best_i = i; }
+      }
+      const int idx = win[best_i];
+      // commit: zero the coefficient, refresh the touched column and the component's pixels
+      {
+        const int c = idx >> 6, k = idx & 63, kx = k & 7;
+        if (lane == 0) s.cf[idx] = 0;
+        __syncwarp();
+        if (lane < 8) {
+          int acc = 0;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) acc += s.basis[8 * lane + v] * s.cf[64 * c + 8 * v + kx];
+          s.colv[64 * c + 8 * lane + kx] = static_cast<short>(idct_col_round(acc));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int p = lane + 32 * h, x = p & 7, y = p >> 3;
+          int acc = 0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc += s.basis[8 * x + u] * s.colv[64 * c + 8 * y + u];
+          s.pix[64 * c + p] = static_cast<unsigned char>(idct_row_round(acc));
+        }
+        __syncwarp();
+      }
+      if (lane == 0) { o[nout].idx = idx; o[nout].block_err = best_err; }
+      ++nout;
+      for (int i = best_i; i + 1 < nwin; ++i) win[i] = win[i + 1];
+      if (next < n) win[nwin - 1] = s.order[next++];
+      else --nwin;
+    }
+    __syncwarp();
+    // ---- monotone from the tail, cut at the limit (processor.cc:467-479) ----
+    if (lane == 0) {
+      float min_err = 1e10f;
+      for (int i = nout - 1; i >= 0; --i) {
+        min_err = fminf(min_err, o[i].block_err);
+        o[i].block_err = min_err;
+      }
+      int keep = 0;
+      while (keep < nout && o[keep].block_err <= limit) ++keep;
+      for (int i = keep; i < nout; ++i) { o[i].idx = 0; o[i].block_err = 0.0f; }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace gzb

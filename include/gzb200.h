@@ -1,0 +1,145 @@
+/* gzb200.h -- C ABI of libgzb200.so, the B200-native (sm_100a CUDA) implementation of Guetzli's
+ * butteraugli-guided quantisation search.
+ *
+ * This is the drop-in boundary: every entry point replaces one piece of the reference's
+ * accelerator interface (yyamamoto79/guetzli-cuda-opencl; paths relative to the reference root).
+ * Plain pointers and sizes only. All pointers are HOST pointers unless stated; each call does its
+ * own host<->device copies on the context's stream and returns when the result is on the host.
+ *
+ * Error convention: every function returns 0 on success or a negative gzb_status; the message is
+ * available from gzb_last_error(). The reference logs CUDA errors and carries on
+ * (clguetzli/ocu.h:14); this library never falls back to a CPU path -- if no CUDA device can be
+ * used, gzb_create fails with GZB_ERR_CUDA.
+ *
+ * Threading: a gzb_ctx is single-owner (one host thread at a time); different contexts (on the
+ * same or different GPUs) may be used concurrently from different threads. No global mutable
+ * state except read-only device tables initialised once per device.
+ *
+ * Numerics: MODE_CPU semantics of the reference (double intermediates, float storage, no early
+ * break in the zeroing loop) -- NOT the float-only semantics of the reference's own kernels.
+ */
+#ifndef GZB200_H_
+#define GZB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gzb_ctx gzb_ctx;
+
+typedef enum {
+  GZB_OK = 0,
+  GZB_ERR_BAD_ARG = -1,
+  GZB_ERR_TOO_SMALL = -2, /* width or height < 32: butteraugli is skipped (guetzli/processor.cc:1171) */
+  GZB_ERR_CUDA = -3,
+  GZB_ERR_STATE = -4,     /* call sequence violated (e.g. zeroing order before StartBlockComparisons) */
+  GZB_ERR_UNSUPPORTED = -5
+} gzb_status;
+
+/* guetzli::CoeffData (guetzli/processor.h:29-32) */
+typedef struct { int idx; float block_err; } gzb_coeff_data;
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* gzb_version(void);
+/* Message of the last failure on this context (or of the last failed gzb_create when ctx==NULL). */
+const char* gzb_last_error(const gzb_ctx* ctx);
+int gzb_device_count(void);
+
+/* ---- comparator life cycle ---------------------------------------------------------------
+ * guetzli::ButteraugliComparator(width, height, &rgb, target_distance, stats)
+ * (guetzli/butteraugli_comparator.cc:48-58) and ButteraugliComparatorEx, which caches the
+ * original's opsin-dynamics image once (clguetzli/clguetzli.cl.cpp:43-69). `rgb` is interleaved
+ * sRGB8, width*height*3 bytes, copied. */
+int gzb_create(int device, int width, int height, const uint8_t* rgb, float target_distance,
+               gzb_ctx** out);
+void gzb_destroy(gzb_ctx* ctx);
+
+/* ---- candidate image (device-resident mirror of guetzli::OutputImage, 4:4:4) --------------
+ * Coefficient planes are int16, block-major, ceil(w/8)*ceil(h/8)*64 values per component
+ * (OutputImageComponent::coeffs(), guetzli/output_image.h). */
+/* Uploads the q=1 JPEG coefficients of the input (jpg.components[c].coeffs). */
+int gzb_set_jpeg_coeffs(gzb_ctx* ctx, const int16_t* c0, const int16_t* c1, const int16_t* c2);
+/* OutputImage::CopyFromJpegData (guetzli/output_image.cc:212-228, 481-492): coeff * quant.
+ * Replaces cuCopyFromJpegComponent (clguetzli/cuguetzli.h:138-148). quant: int[3][64]. */
+int gzb_copy_from_jpeg(gzb_ctx* ctx, const int* quant192);
+/* OutputImage::ApplyGlobalQuantization (guetzli/output_image.cc:349-360, 573-577).
+ * Replaces cuApplyGlobalQuantization (clguetzli/cuguetzli.h:150-156). q: int[3][64]. */
+int gzb_apply_global_quantization(gzb_ctx* ctx, const int* q192);
+/* Replaces the candidate's coefficients wholesale (SetCoeffBlock for every block). */
+int gzb_set_coeffs(gzb_ctx* ctx, const int16_t* c0, const int16_t* c1, const int16_t* c2);
+int gzb_get_coeffs(gzb_ctx* ctx, int16_t* c0, int16_t* c1, int16_t* c2);
+/* Sparse update: n records of {block index, component*64+k, new value} (SetCoeffBlock on the
+ * touched blocks only; used by the back-end loop, guetzli/processor.cc:867-874). */
+int gzb_update_coeffs(gzb_ctx* ctx, const int32_t* block_ix, const uint8_t* idx, const int16_t* val,
+                      size_t n);
+/* OutputImage::ToSRGB() (guetzli/output_image.cc:642-701): interleaved sRGB8, w*h*3 bytes.
+ * Replaces cuComponentsToPixels (clguetzli/cuguetzli.h:157-163). */
+int gzb_to_srgb(gzb_ctx* ctx, uint8_t* rgb_out);
+
+/* ---- Comparator interface (guetzli/comparator.h:29-96) ------------------------------------ */
+/* Compare(img): butteraugli distance of the resident candidate to the original; the distance map
+ * stays on the device. *distance = distmap_aggregate(). Replaces ButteraugliComparatorEx::Compare
+ * (clguetzli/clguetzli.cl.cpp:71-152). */
+int gzb_compare(gzb_ctx* ctx, float* distance);
+/* distmap(): width*height floats. */
+int gzb_get_distmap(gzb_ctx* ctx, float* distmap_out);
+/* DistanceOK(target_mul) / ScoreOutputSize(size) / BlockErrorLimit() for the last Compare. */
+int gzb_distance_ok(const gzb_ctx* ctx, double target_mul);
+double gzb_score_output_size(const gzb_ctx* ctx, int size);
+float gzb_block_error_limit(const gzb_ctx* ctx);
+/* StartBlockComparisons / FinishBlockComparisons (guetzli/butteraugli_comparator.cc:72-83):
+ * builds the per-block mask scale (mask_xyz_ at each block's top-left pixel) on the device. */
+int gzb_start_block_comparisons(gzb_ctx* ctx);
+int gzb_finish_block_comparisons(gzb_ctx* ctx);
+/* The side channel of the reference's GPU modes: ButteraugliComparatorEx::
+ * imgMaskXyzScaleBlockList ([3] per block) and imgOpsinDynamicsBlockList ([R64 G64 B64] per block)
+ * (clguetzli/clguetzli.h:201-217). Either pointer may be NULL. */
+int gzb_get_block_lists(gzb_ctx* ctx, float* mask_scale_out, float* opsin_blocks_out);
+/* CompareBlock for every 8x8 block of the resident candidate at once (factor 1, comp_mask 7):
+ * err_out[block]. (guetzli/butteraugli_comparator.cc:113-163) */
+int gzb_compare_blocks(gzb_ctx* ctx, float* err_out);
+/* cuComputeBlockZeroingOrder (clguetzli/cuguetzli.h:30-40) == the per-block loop of
+ * Processor::SelectFrequencyMasking over ComputeBlockZeroingOrder (guetzli/processor.cc:376-487,
+ * 638-672), MODE_CPU semantics. out: nblocks*192 records, zero-filled, packed from slot 0 in
+ * zeroing order, entries with err <= BlockErrorLimit only. Needs gzb_set_jpeg_coeffs (the original
+ * coefficients) and gzb_start_block_comparisons. */
+int gzb_compute_block_zeroing_order(gzb_ctx* ctx, int comp_mask, gzb_coeff_data* out);
+/* ComputeBlockErrorAdjustmentWeights (guetzli/butteraugli_comparator.cc:169-233), factor 1.
+ * distmap == NULL uses the device-resident map of the last Compare. block_weight: nblocks floats,
+ * overwritten (the reference passes a zero vector, guetzli/processor.cc:776-783). */
+int gzb_compute_block_error_adjustment_weights(gzb_ctx* ctx, int direction, int max_block_dist,
+                                               double target_mul, const float* distmap,
+                                               float* block_weight);
+
+/* ---- stage entry points (the reference's cu* free functions; host planes in, host planes out) */
+/* cuOpsinDynamicsImage (clguetzli/cuguetzli.h:19-21): linear rgb planes in place -> XYB. */
+int gzb_opsin_dynamics_image(int device, float* r, float* g, float* b, size_t xsize, size_t ysize);
+/* cuDiffmapOpsinDynamicsImage (clguetzli/cuguetzli.h:23-28). step must be 3. */
+int gzb_diffmap_opsin_dynamics_image(int device, float* result, const float* r, const float* g,
+                                     const float* b, const float* r2, const float* g2,
+                                     const float* b2, size_t xsize, size_t ysize, size_t step);
+/* butteraugli::Blur (butteraugli.cc:100-148) / cuBlurEx (clguetzli/cuguetzli.h:73-75). */
+int gzb_blur(int device, float* plane, size_t xsize, size_t ysize, double sigma,
+             double border_ratio);
+/* Standalone butteraugli of two sRGB8 images (interleaved): distance and optional diffmap. */
+int gzb_butteraugli_srgb(int device, const uint8_t* rgb0, const uint8_t* rgb1, int width,
+                         int height, float* distance, float* diffmap_out);
+
+/* ---- parity/debug: device intermediates of the last gzb_compare --------------------------- */
+/* name in {"xyb0","xyb1","mhic0","mhic1","edge_map","block_dc","block_ac","combined_sqrt",
+ * "diffmap","mask_front"}; copies min(cap, size) floats; *n_out = size in floats. */
+int gzb_debug_fetch(gzb_ctx* ctx, const char* name, float* out, size_t cap, size_t* n_out);
+
+/* ---- timing of the last call on this context (CUDA events on the context's stream) -------- */
+/* Device milliseconds spent by the kernels of the last gzb_compare / zeroing call. */
+float gzb_last_device_ms(const gzb_ctx* ctx);
+/* Number of kernels launched by this context since creation (bench `gpu_launches`). */
+unsigned long long gzb_launch_count(const gzb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GZB200_H_ */

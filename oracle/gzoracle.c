@@ -1101,3 +1101,86 @@ GZO_API void gzo_dct_double(double* block, int inverse) {
   for (int x = 0; x < 8; ++x) (inverse ? dct1d_inv : dct1d_fwd)(block + x, 8, tmp + x);
   for (int y = 0; y < 8; ++y) (inverse ? dct1d_inv : dct1d_fwd)(tmp + 8 * y, 1, block + 8 * y);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Front end: RGB -> YCbCr (16.16 fixed point) -> integer forward DCT (output
+ * scaled by 16) -> q=1 quantisation.  guetzli/jpeg_data_encoder.cc:28-117, guetzli/fdct.cc:28-240
+ * The transform's shifts truncate, so the operation order below is the reference's.
+ * ---------------------------------------------------------------------------------------- */
+static int mul16(int a, int b) { return (a * b) >> 16; }
+
+static void fdct_column(int16_t* v /* stride 8 */) {
+  const int i0 = v[0], i1 = v[8], i2 = v[16], i3 = v[24], i4 = v[32], i5 = v[40], i6 = v[48], i7 = v[56];
+  int d07 = i0 - i7, s07 = i0 + i7, d25 = i2 - i5, s25 = i2 + i5;
+  int d34 = i3 - i4, s34 = i3 + i4, d16 = i1 - i6, s16 = i1 + i6;
+  int e0 = s07 - s34, e1 = s07 + s34;   /* even part */
+  int e2 = s16 - s25, e3 = s16 + s25;
+  e1 <<= 3; e3 <<= 3;
+  v[0] = (int16_t)(e1 + e3);
+  v[32] = (int16_t)(e1 - e3);
+  e0 <<= 3; e2 <<= 3; d34 <<= 3; d07 <<= 3;
+  v[16] = (int16_t)(mul16(27146, e2) + e0);
+  v[48] = (int16_t)(mul16(27146, e0) - e2);
+  d25 <<= 4; d16 <<= 4;
+  int r = mul16(d16 + d25, 23170), s = mul16(d16 - d25, 23170);
+  int p3 = d34 - s, p1 = d34 + s;      /* BUTTERFLY(m3, m1) */
+  int p0 = d07 - r, p2 = d07 + r;      /* BUTTERFLY(m0, m2) */
+  int q3 = mul16(p3, -21746) + p3 + 1;
+  int q1 = mul16(p1, 13036) + p2 + 1;
+  int q4 = mul16(-21746, p0) + p0;
+  int q5 = mul16(13036, p2);
+  v[8] = (int16_t)q1;
+  v[24] = (int16_t)(p0 - q3);
+  v[40] = (int16_t)(p3 + q4);
+  v[56] = (int16_t)(q5 - p1);
+}
+
+static void fdct_row(int16_t* in, const int16_t* t) {
+  const int a0 = in[0] + in[7], b0 = in[0] - in[7], a1 = in[1] + in[6], b1 = in[1] - in[6];
+  const int a2 = in[2] + in[5], b2 = in[2] - in[5], a3 = in[3] + in[4], b3 = in[3] - in[4];
+  const int C1 = t[0], C2 = t[1], C3 = t[2], C4 = t[3], C5 = t[4], C6 = t[5], C7 = t[6];
+  const int c0 = a0 + a3, c1 = a0 - a3, c2 = a1 + a2, c3 = a1 - a2;
+  in[0] = (int16_t)((C4 * (c0 + c2)) >> 16);
+  in[4] = (int16_t)((C4 * (c0 - c2)) >> 16);
+  in[2] = (int16_t)((C2 * c1 + C6 * c3) >> 16);
+  in[6] = (int16_t)((C6 * c1 - C2 * c3) >> 16);
+  in[1] = (int16_t)((C1 * b0 + C3 * b1 + C5 * b2 + C7 * b3) >> 16);
+  in[3] = (int16_t)((C3 * b0 - C7 * b1 - C1 * b2 - C5 * b3) >> 16);
+  in[5] = (int16_t)((C5 * b0 - C1 * b1 + C7 * b2 + C3 * b3) >> 16);
+  in[7] = (int16_t)((C7 * b0 - C5 * b1 + C3 * b2 - C1 * b3) >> 16);
+}
+
+GZO_API void gzo_fdct(int16_t* block) {
+  static const int16_t T04[7] = {22725, 21407, 19266, 16384, 12873, 8867, 4520};
+  static const int16_t T17[7] = {31521, 29692, 26722, 22725, 17855, 12299, 6270};
+  static const int16_t T26[7] = {29692, 27969, 25172, 21407, 16819, 11585, 5906};
+  static const int16_t T35[7] = {26722, 25172, 22654, 19266, 15137, 10426, 5315};
+  const int16_t* rows[8] = {T04, T17, T26, T35, T04, T35, T26, T17};
+  for (int x = 0; x < 8; ++x) fdct_column(block + x);
+  for (int y = 0; y < 8; ++y) fdct_row(block + 8 * y, rows[y]);
+}
+
+/* EncodeRGBToJpeg with the all-ones quantiser: block-major int16 coefficient planes. */
+GZO_API void gzo_rgb_to_jpeg_coeffs(const uint8_t* rgb, int xs, int ys, int16_t* c0, int16_t* c1,
+                                    int16_t* c2) {
+  const int bw = (xs + 7) / 8, bh = (ys + 7) / 8;
+  int16_t* out[3] = {c0, c1, c2};
+  for (int by = 0; by < bh; ++by)
+    for (int bx = 0; bx < bw; ++bx) {
+      int16_t blk[192];
+      for (int iy = 0; iy < 8; ++iy)
+        for (int ix = 0; ix < 8; ++ix) {
+          const int y = imin(ys - 1, 8 * by + iy), x = imin(xs - 1, 8 * bx + ix);
+          const uint8_t* p = rgb + 3 * ((size_t)y * xs + x);
+          const int r = p[0], g = p[1], b = p[2], k = 8 * iy + ix;
+          blk[k] = (int16_t)((19595 * r + 38469 * g + 7471 * b - (128 << 16) + 32768) >> 16);
+          blk[64 + k] = (int16_t)((-11059 * r - 21709 * g + 32768 * b + 32768 - 1) >> 16);
+          blk[128 + k] = (int16_t)((32768 * r - 27439 * g - 5329 * b + 32768 - 1) >> 16);
+        }
+      for (int c = 0; c < 3; ++c) {
+        gzo_fdct(blk + 64 * c);
+        int16_t* o = out[c] + ((size_t)by * bw + bx) * 64;
+        for (int k = 0; k < 64; ++k) o[k] = (int16_t)((blk[64 * c + k] * 65537 + (0x80 << 12)) >> 20);
+      }
+    }
+}

@@ -210,3 +210,29 @@ def test_block_comparisons_and_zeroing_order(w, h):
     assert (zo_ref["err"] > 0).sum() > s.nblocks  # non-trivial
     s.finish_block_comparisons()
     s.close()
+
+
+def test_front_end_fdct_and_rgb_to_coeffs():
+    rng = np.random.default_rng(9)
+    for t in range(300):
+        blk = rng.integers(-128, 128, 64).astype(np.int16)
+        if t % 3 == 0:
+            blk = (rng.normal(0, 20, 64) + rng.integers(-100, 100)).clip(-128, 127).astype(np.int16)
+        a = blk.copy(); b = blk.copy()
+        oracle().gzo_fdct(p(a)); ref().ref_fdct(p(b))
+        assert np.array_equal(a, b)
+    for (w, h) in [(64, 48), (70, 45), (33, 39)]:
+        img = synth_image(w, h)
+        s = RefSession(img, 1.0)
+        nb = s.nblocks
+        c = np.zeros((3, nb, 64), np.int16)
+        oracle().gzo_rgb_to_jpeg_coeffs(p(img), w, h, p(c[0]), p(c[1]), p(c[2]))
+        assert np.array_equal(c, s.jpg_coeffs())
+        s.close()
+    img = bees()
+    h, w = img.shape[:2]
+    s = RefSession(img, 1.0)
+    c = np.zeros((3, s.nblocks, 64), np.int16)
+    oracle().gzo_rgb_to_jpeg_coeffs(p(img), w, h, p(c[0]), p(c[1]), p(c[2]))
+    assert np.array_equal(c, s.jpg_coeffs())
+    s.close()
