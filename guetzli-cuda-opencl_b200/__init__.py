@@ -264,3 +264,79 @@ def ButteraugliSrgb(rgb0, rgb1, want_diffmap=True, device=0):
     _check(lib().gzb_butteraugli_srgb(device, _p(a), _p(b), w, h, C.byref(d),
                                       _p(dm) if want_diffmap else None))
     return np.float32(d.value), dm
+
+
+# ---- whole encoder and host-side pieces --------------------------------------------------------
+class EncodeStats(C.Structure):
+    _fields_ = [("num_iterations", C.c_int), ("num_iterations_up", C.c_int), ("num_iterations_down", C.c_int),
+                ("num_compares", C.c_int), ("num_jpeg_writes", C.c_int), ("num_entropy_code_builds", C.c_int),
+                ("total_wall_ms", C.c_double), ("host_frontend_ms", C.c_double), ("host_quant_ms", C.c_double),
+                ("host_write_ms", C.c_double), ("compare_wall_ms", C.c_double), ("device_compare_ms", C.c_double),
+                ("zeroing_wall_ms", C.c_double), ("device_zeroing_ms", C.c_double), ("backend_wall_ms", C.c_double),
+                ("final_score", C.c_double), ("final_distance", C.c_float), ("launches", C.c_ulonglong)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def ButteraugliScoreForQuality(quality):
+    L = lib()
+    L.gzb_butteraugli_score_for_quality.restype = C.c_double
+    L.gzb_butteraugli_score_for_quality.argtypes = [C.c_double]
+    return L.gzb_butteraugli_score_for_quality(float(quality))
+
+
+def Process(rgb, butteraugli_target, device=0, host_threads=0, want_trace=False):
+    """guetzli::Process(params, stats, rgb, w, h, &out) on the B200.
+    Returns (jpeg_bytes, stats_dict, trace_or_None)."""
+    L = lib()
+    a = np.ascontiguousarray(rgb, np.uint8)
+    h, w = a.shape[:2]
+    out = C.c_void_p()
+    n = C.c_size_t()
+    st = EncodeStats()
+    tr = C.c_void_p()
+    L.gzb_encode_rgb.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int,
+                                 C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(EncodeStats),
+                                 C.POINTER(C.c_void_p)]
+    L.gzb_encode_last_error.restype = C.c_char_p
+    L.gzb_free.argtypes = [C.c_void_p]
+    L.gzb_free.restype = None
+    rc = L.gzb_encode_rgb(device, _p(a), w, h, C.c_float(butteraugli_target), host_threads,
+                          C.byref(out), C.byref(n), C.byref(st), C.byref(tr) if want_trace else None)
+    if rc != 0:
+        raise GzbError("gzb_encode_rgb failed (%d): %s" % (rc, L.gzb_encode_last_error().decode(errors="replace")))
+    data = C.string_at(out, n.value)
+    L.gzb_free(out)
+    trace = None
+    if want_trace and tr:
+        trace = C.string_at(tr).decode(errors="replace")
+        L.gzb_free(tr)
+    return data, st.as_dict(), trace
+
+
+def RgbToJpegCoeffs(rgb):
+    """guetzli::EncodeRGBToJpeg with q=1 (host code): int16 [3, nblocks, 64]."""
+    a = np.ascontiguousarray(rgb, np.uint8)
+    h, w = a.shape[:2]
+    nb = ((w + 7) // 8) * ((h + 7) // 8)
+    c = np.zeros((3, nb, 64), np.int16)
+    lib().gzb_rgb_to_jpeg_coeffs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    _check(lib().gzb_rgb_to_jpeg_coeffs(_p(a), w, h, _p(c[0]), _p(c[1]), _p(c[2])))
+    return c
+
+
+def WriteJpeg(coeffs, width, height, q, input_tables=False, host_threads=1):
+    """OutputImage::SaveToJpegData + WriteJpeg (host code): JPEG bytes."""
+    c = np.ascontiguousarray(coeffs, np.int16)
+    qq = np.ascontiguousarray(q, np.int32).reshape(192)
+    L = lib()
+    L.gzb_write_jpeg.restype = C.c_long
+    L.gzb_write_jpeg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_int, C.c_void_p, C.c_long]
+    buf = np.zeros(width * height * 3 + (1 << 16), np.uint8)
+    n = L.gzb_write_jpeg(_p(c[0]), _p(c[1]), _p(c[2]), width, height, _p(qq), int(input_tables), host_threads,
+                         _p(buf), buf.size)
+    if n < 0:
+        raise GzbError("gzb_write_jpeg failed (%d)" % n)
+    return buf[:n].tobytes()

@@ -188,6 +188,8 @@ struct gzb_ctx {
   unsigned char* d_flags = nullptr;
   unsigned int* d_scalars = nullptr;  // [0] distance bits, [1] work counter
   int* d_q = nullptr;          // 192 ints
+  uint8_t* d_upd = nullptr;    // sparse-update staging: [cap] int32 | [cap] int16 | [cap] u8
+  size_t upd_cap = 0;
   gzb_coeff_data* d_order = nullptr;
   float* h_pinned = nullptr;   // small pinned staging
   size_t lf_stride = 0;
@@ -302,7 +304,7 @@ void free_ctx(gzb_ctx* c) {
   void* ptrs[] = {c->d_rgb0, c->d_rgb1, c->d_stage_u8, c->d_orig, c->d_coef, c->d_xyb0, c->d_xyb1, c->d_mh,
                   c->d_bl, c->d_tmp, c->d_lf, c->d_ms[0], c->d_ms[1], c->d_ms[2], c->d_msb2, c->d_edm, c->d_dc,
                   c->d_ac, c->d_sq, c->d_dsmall, c->d_diffmap, c->d_bmax, c->d_weight, c->d_mask_scale,
-                  c->d_block_err, c->d_pregamma, c->d_flags, c->d_scalars, c->d_q, c->d_order};
+                  c->d_block_err, c->d_pregamma, c->d_flags, c->d_scalars, c->d_q, c->d_order, c->d_upd};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   c->p_ops.release(); c->p_lf.release(); c->p_mkb2.release(); c->p_dm.release();
@@ -508,15 +510,34 @@ int gzb_get_coeffs(gzb_ctx* c, int16_t* c0, int16_t* c1, int16_t* c2) {
 int gzb_update_coeffs(gzb_ctx* c, const int32_t* block_ix, const uint8_t* idx, const int16_t* val, size_t n) {
   GZB_TRY(c)
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_update_coeffs: no candidate coefficients");
-  // Sparse host-side patch through a pinned-free path: few records per call in practice.
-  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
-  for (size_t i = 0; i < n; ++i) {
+  for (size_t i = 0; i < n; ++i)
     if (block_ix[i] < 0 || block_ix[i] >= c->nblocks || idx[i] >= 192) return fail(c, GZB_ERR_BAD_ARG, "gzb_update_coeffs: index out of range");
-    const size_t off = (idx[i] >> 6) * cs + static_cast<size_t>(block_ix[i]) * 64 + (idx[i] & 63);
-    CK(cudaMemcpyAsync(c->d_coef + off, &val[i], 2, cudaMemcpyHostToDevice, c->stream));
+  if (n > 0) {
+    if (n > c->upd_cap) {
+      if (c->d_upd) cudaFree(c->d_upd);
+      c->upd_cap = n + n / 2 + 1024;
+      dmalloc(&c->d_upd, c->upd_cap * 8);
+    }
+    // records are applied in order (later writes to the same coefficient win): one thread walks
+    // duplicates, so pack {block, idx, val} and let the kernel resolve by record index
+    CK(cudaMemcpyAsync(c->d_upd, block_ix, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_upd + c->upd_cap * 4, val, n * 2, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_upd + c->upd_cap * 6, idx, n, cudaMemcpyHostToDevice, c->stream));
+    const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+    k_scatter_coeffs<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(
+        reinterpret_cast<const int*>(c->d_upd), reinterpret_cast<const int16_t*>(c->d_upd + c->upd_cap * 4),
+        c->d_upd + c->upd_cap * 6, n, cs, c->d_coef);
+    c->launches += 1;
   }
   render_candidate(c, kCoeffKeep);
   sync_check(c);
+  GZB_END(c)
+}
+
+int gzb_clear_distmap(gzb_ctx* c) {
+  GZB_TRY(c)
+  CK(cudaMemsetAsync(c->d_diffmap, 0, c->ps * sizeof(float), c->stream));
+  c->have_distmap = true;
   GZB_END(c)
 }
 

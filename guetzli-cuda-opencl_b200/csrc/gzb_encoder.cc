@@ -1,0 +1,773 @@
+// gzb_encoder.cc -- host search driver: guetzli::Process(rgb -> jpeg) with every butteraugli
+// evaluation, IDCT/quantisation pass and the block-zeroing search running on the B200 through the
+// C ABI of this library. The control flow and every scalar decision follow the reference's
+// Processor (guetzli/processor.cc:151-372, 559-1020, 1157-1185) for the default flags
+// (4:4:4, try_420=false, clear_metadata=true, zeroing_greedy_lookahead=3, new_zeroing_model=true),
+// so that the emitted JPEG is byte-identical to the CPU reference's.
+//
+// Host-side accelerations that do not change any result:
+//   * ComputeEntropyCodes is evaluated only at the steps whose value can be observed
+//     (processor.cc:879-888 recomputes it every 10th step but reads it only in the break test);
+//   * the entropy-coded size is tracked incrementally between code rebuilds;
+//   * the global candidate order is produced by a lazy evaluation of libstdc++'s introsort that
+//     yields exactly std::sort's permutation for the prefix actually consumed;
+//   * WriteJpeg runs block-row bands on host threads and overlaps the GPU Compare.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <future>
+#include <set>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/gzb200.h"
+#include "gzb_jpeg.h"
+
+namespace {
+
+using gzb::jpeg::Frame;
+using gzb::jpeg::Histogram;
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---- front end: RGB -> YCbCr -> integer forward DCT -> q=1 indices ---------------------------
+// (guetzli/jpeg_data_encoder.cc:28-117, guetzli/fdct.cc:28-240; truncating shifts keep the order)
+inline int mul16(int a, int b) { return (a * b) >> 16; }
+
+void fdct_column(int16_t* v) {
+  const int i0 = v[0], i1 = v[8], i2 = v[16], i3 = v[24], i4 = v[32], i5 = v[40], i6 = v[48], i7 = v[56];
+  int d07 = i0 - i7, s07 = i0 + i7, d25 = i2 - i5, s25 = i2 + i5;
+  int d34 = i3 - i4, s34 = i3 + i4, d16 = i1 - i6, s16 = i1 + i6;
+  int e0 = s07 - s34, e1 = s07 + s34, e2 = s16 - s25, e3 = s16 + s25;
+  e1 <<= 3; e3 <<= 3;
+  v[0] = static_cast<int16_t>(e1 + e3);
+  v[32] = static_cast<int16_t>(e1 - e3);
+  e0 <<= 3; e2 <<= 3; d34 <<= 3; d07 <<= 3;
+  v[16] = static_cast<int16_t>(mul16(27146, e2) + e0);
+  v[48] = static_cast<int16_t>(mul16(27146, e0) - e2);
+  d25 <<= 4; d16 <<= 4;
+  const int r = mul16(d16 + d25, 23170), s = mul16(d16 - d25, 23170);
+  const int p3 = d34 - s, p1 = d34 + s, p0 = d07 - r, p2 = d07 + r;
+  const int q3 = mul16(p3, -21746) + p3 + 1;
+  const int q1 = mul16(p1, 13036) + p2 + 1;
+  const int q4 = mul16(-21746, p0) + p0;
+  const int q5 = mul16(13036, p2);
+  v[8] = static_cast<int16_t>(q1);
+  v[24] = static_cast<int16_t>(p0 - q3);
+  v[40] = static_cast<int16_t>(p3 + q4);
+  v[56] = static_cast<int16_t>(q5 - p1);
+}
+
+void fdct_row(int16_t* in, const int16_t* t) {
+  const int a0 = in[0] + in[7], b0 = in[0] - in[7], a1 = in[1] + in[6], b1 = in[1] - in[6];
+  const int a2 = in[2] + in[5], b2 = in[2] - in[5], a3 = in[3] + in[4], b3 = in[3] - in[4];
+  const int C1 = t[0], C2 = t[1], C3 = t[2], C4 = t[3], C5 = t[4], C6 = t[5], C7 = t[6];
+  const int c0 = a0 + a3, c1 = a0 - a3, c2 = a1 + a2, c3 = a1 - a2;
+  in[0] = static_cast<int16_t>((C4 * (c0 + c2)) >> 16);
+  in[4] = static_cast<int16_t>((C4 * (c0 - c2)) >> 16);
+  in[2] = static_cast<int16_t>((C2 * c1 + C6 * c3) >> 16);
+  in[6] = static_cast<int16_t>((C6 * c1 - C2 * c3) >> 16);
+  in[1] = static_cast<int16_t>((C1 * b0 + C3 * b1 + C5 * b2 + C7 * b3) >> 16);
+  in[3] = static_cast<int16_t>((C3 * b0 - C7 * b1 - C1 * b2 - C5 * b3) >> 16);
+  in[5] = static_cast<int16_t>((C5 * b0 - C1 * b1 + C7 * b2 + C3 * b3) >> 16);
+  in[7] = static_cast<int16_t>((C7 * b0 - C5 * b1 + C3 * b2 - C1 * b3) >> 16);
+}
+
+void fdct_block(int16_t* block) {
+  static const int16_t T04[7] = {22725, 21407, 19266, 16384, 12873, 8867, 4520};
+  static const int16_t T17[7] = {31521, 29692, 26722, 22725, 17855, 12299, 6270};
+  static const int16_t T26[7] = {29692, 27969, 25172, 21407, 16819, 11585, 5906};
+  static const int16_t T35[7] = {26722, 25172, 22654, 19266, 15137, 10426, 5315};
+  static const int16_t* const rows[8] = {T04, T17, T26, T35, T04, T35, T26, T17};
+  for (int x = 0; x < 8; ++x) fdct_column(block + x);
+  for (int y = 0; y < 8; ++y) fdct_row(block + 8 * y, rows[y]);
+}
+
+void rgb_to_coeffs_rows(const uint8_t* rgb, int w, int h, int bw, int by0, int by1, int16_t* const out[3]) {
+  for (int by = by0; by < by1; ++by)
+    for (int bx = 0; bx < bw; ++bx) {
+      int16_t blk[192];
+      for (int iy = 0; iy < 8; ++iy)
+        for (int ix = 0; ix < 8; ++ix) {
+          const int y = std::min(h - 1, 8 * by + iy), x = std::min(w - 1, 8 * bx + ix);
+          const uint8_t* p = rgb + 3 * (static_cast<size_t>(y) * w + x);
+          const int r = p[0], g = p[1], b = p[2], k = 8 * iy + ix;
+          blk[k] = static_cast<int16_t>((19595 * r + 38469 * g + 7471 * b - (128 << 16) + 32768) >> 16);
+          blk[64 + k] = static_cast<int16_t>((-11059 * r - 21709 * g + 32768 * b + 32768 - 1) >> 16);
+          blk[128 + k] = static_cast<int16_t>((32768 * r - 27439 * g - 5329 * b + 32768 - 1) >> 16);
+        }
+      for (int c = 0; c < 3; ++c) {
+        fdct_block(blk + 64 * c);
+        int16_t* o = out[c] + (static_cast<size_t>(by) * bw + bx) * 64;
+        for (int k = 0; k < 64; ++k) o[k] = static_cast<int16_t>((blk[64 * c + k] * 65537 + (0x80 << 12)) >> 20);
+      }
+    }
+}
+
+template <typename F>
+void parallel_rows(int n, int nthreads, F fn) {
+  nthreads = std::max(1, std::min(nthreads, n));
+  if (nthreads == 1) { fn(0, n); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) {
+    const int a = static_cast<int>(static_cast<int64_t>(n) * t / nthreads);
+    const int b = static_cast<int>(static_cast<int64_t>(n) * (t + 1) / nthreads);
+    th.emplace_back(fn, a, b);
+  }
+  for (auto& t : th) t.join();
+}
+
+// ---- quantiser (guetzli/quantize.h:24-29) -----------------------------------------------------
+inline int16_t quantize_coeff(int16_t raw, int q) {
+  const int r = raw % q;
+  const int16_t delta = static_cast<int16_t>(2 * r > q ? q - r : (-2) * r > q ? -q - r : -r);
+  return static_cast<int16_t>(raw + delta);
+}
+
+// ---- QuantMatrixGenerator (guetzli/processor.cc:162-308) --------------------------------------
+struct QuantData { int q[3][64]; size_t jpg_size; bool dist_ok; };
+
+double contrast_sensitivity(int k) { return 1.0 / (1.0 + gzb::jpeg::kZigZag[k] / 2.0); }
+
+double quant_heuristic_score(const int q[3][64]) {
+  double score = 0.0;
+  for (int c = 0; c < 3; ++c)
+    for (int k = 0; k < 64; ++k) score += 0.5 * (q[c][k] - 1.0) * contrast_sensitivity(k);
+  return score;
+}
+
+class QuantGenerator {
+ public:
+  QuantGenerator() : a_(-1.0), b_(-1.0), total_csf_(0.0) {
+    for (int k = 0; k < 64; ++k) total_csf_ += 3.0 * contrast_sensitivity(k);
+  }
+  bool next(int q[3][64]) {
+    for (int iter = 0; iter < 1000; ++iter) {
+      double hscore;
+      if (b_ == -1.0) {
+        if (a_ == -1.0) hscore = total_csf_;
+        else if (a_ < 5.0 * total_csf_) hscore = a_ + total_csf_;
+        else hscore = 2 * (a_ + total_csf_);
+        if (hscore > 100 * total_csf_) return false;
+      } else if (b_ == 0.0) {
+        return false;
+      } else if (a_ == -1.0) {
+        hscore = 0.0;
+      } else {
+        int lo[3][64], hi[3][64];
+        const double eps = 0.05;
+        matrix_for((1 - eps) * a_ + eps * 0.5 * (a_ + b_), lo);
+        matrix_for((1 - eps) * b_ + eps * 0.5 * (a_ + b_), hi);
+        if (memcmp(lo, hi, sizeof(lo)) == 0) return false;
+        hscore = (a_ + b_) * 0.5;
+      }
+      matrix_for(hscore, q);
+      bool retry = false;
+      for (const QuantData& d : seen_)
+        if (memcmp(q, d.q, sizeof(d.q)) == 0) {
+          if (d.dist_ok) a_ = hscore; else b_ = hscore;
+          retry = true;
+          break;
+        }
+      if (!retry) return true;
+    }
+    return false;
+  }
+  void add(const QuantData& d) {
+    seen_.push_back(d);
+    const double hs = quant_heuristic_score(d.q);
+    if (d.dist_ok) a_ = std::max(a_, hs);
+    else b_ = b_ == -1.0 ? hs : std::min(b_, hs);
+  }
+
+ private:
+  void matrix_for(double score, int q[3][64]) const {
+    const int level = static_cast<int>(score / total_csf_);
+    score -= level * total_csf_;
+    for (int k = 63; k >= 0; --k) {
+      const int nat = gzb::jpeg::kNaturalOrder[k];
+      for (int c = 0; c < 3; ++c) q[c][nat] = 2 * level + (score > 0.0 ? 3 : 1);
+      score -= 3.0 * contrast_sensitivity(nat);
+    }
+  }
+  double a_, b_, total_csf_;
+  std::vector<QuantData> seen_;
+};
+
+bool quant_data_better(const QuantData& a, const QuantData& b) {
+  if (a.dist_ok && !b.dist_ok) return true;
+  if (!a.dist_ok && b.dist_ok) return false;
+  return a.jpg_size < b.jpg_size;
+}
+
+// ---- lazy std::sort ---------------------------------------------------------------------------
+// Produces, for any prefix that is asked for, exactly the permutation libstdc++'s std::sort would
+// leave in the array (introsort: median-of-3 Hoare partitioning to chunks of <= 16, heap sort
+// beyond the depth limit, then insertion sort), by running the same partition steps through the
+// library's own internals but postponing every right-hand partition until the walk reaches it.
+typedef std::pair<int, float> OrderEntry;
+struct OrderLess {
+  bool operator()(const OrderEntry& a, const OrderEntry& b) const { return a.second < b.second; }
+};
+
+class LazySort {
+ public:
+  LazySort(OrderEntry* data, size_t n) : d_(data), n_(n), sorted_(0) {
+    if (n_ > 1) pending_.push_back({0, n_, 2 * static_cast<int>(std::__lg(n_))});
+    else sorted_ = n_;
+  }
+  // Ensures d_[0 .. i] are final.
+  void ensure(size_t i) {
+    while (sorted_ <= i && sorted_ < n_) advance();
+  }
+  size_t sorted() const { return sorted_; }
+
+ private:
+  struct Range { size_t first, last; int depth; };
+  void advance() {
+    // Leftmost pending range starts at sorted_.
+    Range r = pending_.back();
+    pending_.pop_back();
+    auto comp = __gnu_cxx::__ops::__iter_comp_iter(OrderLess());
+    while (r.last - r.first > 16) {
+      if (r.depth == 0) {
+        std::__partial_sort(d_ + r.first, d_ + r.last, d_ + r.last, comp);
+        finish_chunk(r.first, r.last, true);
+        return;
+      }
+      --r.depth;
+      OrderEntry* cut = std::__unguarded_partition_pivot(d_ + r.first, d_ + r.last, comp);
+      const size_t c = static_cast<size_t>(cut - d_);
+      pending_.push_back({c, r.last, r.depth});
+      r.last = c;
+    }
+    finish_chunk(r.first, r.last, false);
+  }
+  // Final insertion sort restricted to one chunk: the first 16 elements of the whole array use the
+  // guarded variant, everything else the unguarded one (std::__final_insertion_sort).
+  void finish_chunk(size_t first, size_t last, bool already_sorted) {
+    if (!already_sorted) {
+      auto comp = __gnu_cxx::__ops::__iter_comp_iter(OrderLess());
+      if (n_ <= 16) {
+        std::__insertion_sort(d_ + first, d_ + last, comp);
+      } else {
+        // Elements with global index < 16 are handled by __insertion_sort(first, first+16) over
+        // the whole array; since chunks are separated by pivots, sorting chunk-locally with a
+        // guarded insertion sort gives the same arrangement as both library passes.
+        std::__insertion_sort(d_ + first, d_ + last, comp);
+      }
+    }
+    sorted_ = last;
+  }
+  OrderEntry* d_;
+  size_t n_, sorted_;
+  std::vector<Range> pending_;
+};
+
+// ---- encoder state ----------------------------------------------------------------------------
+struct Encoder {
+  int w = 0, h = 0, bw = 0, bh = 0, nb = 0;
+  int nthreads = 1;
+  float target = 0.f;
+  gzb_ctx* ctx = nullptr;
+  std::vector<int16_t> orig[3];   // q=1 indices (jpg_in.components[c].coeffs)
+  std::vector<int16_t> cur[3];    // OutputImage coefficients (dequantised values)
+  std::vector<int16_t> idx[3];    // cur / quant (what the file stores)
+  int quant[3][64];
+  std::string best_jpeg;
+  double best_score = -1;
+  gzb_encode_stats st{};
+  std::string trace;
+  bool want_trace = false;
+  float distance = 0.f;
+
+  void log(const char* fmt, ...) {
+    if (!want_trace) return;
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    trace += buf;
+  }
+
+  int ncomp_for_output() const {
+    for (int c = 1; c < 3; ++c)
+      for (int16_t v : cur[c]) if (v != 0) return 3;
+    return 1;  // SaveToJpegData drops all-zero chroma (output_image.cc:588)
+  }
+
+  // SaveToJpegData + WriteJpeg for the current candidate.
+  void write_candidate(std::string* out) {
+    const double t0 = now_ms();
+    Frame f;
+    f.width = w; f.height = h; f.bw = bw; f.bh = bh;
+    f.ncomp = ncomp_for_output();
+    for (int c = 0; c < 3; ++c) f.coeffs[c] = idx[c].data();
+    gzb::jpeg::frame_set_quant(&f, quant);
+    gzb::jpeg::write_jpeg(f, out, nthreads);
+    st.host_write_ms += now_ms() - t0;
+    st.num_jpeg_writes++;
+  }
+
+  void maybe_output(const std::string& jpeg) {
+    const double score = gzb_score_output_size(ctx, static_cast<int>(jpeg.size()));
+    log(" Score[%.4f]", score);
+    if (score < best_score || best_score < 0) {
+      best_jpeg = jpeg;
+      best_score = score;
+      log(" (*)");
+    }
+    log("\n");
+  }
+
+  bool compare(bool quiet = false) {
+    const double t0 = now_ms();
+    if (gzb_compare(ctx, &distance) != GZB_OK) return false;
+    st.device_compare_ms += gzb_last_device_ms(ctx);
+    st.compare_wall_ms += now_ms() - t0;
+    st.num_compares++;
+    if (!quiet) log(" BA[100.00%%] D[%6.4f]", distance);
+    return true;
+  }
+
+  // img.CopyFromJpegData(jpg) ; img.ApplyGlobalQuantization(q)  (host mirror + device)
+  bool set_global_quant(const int q[3][64]) {
+    const double t0 = now_ms();
+    int ones[192];
+    for (int i = 0; i < 192; ++i) ones[i] = 1;
+    if (gzb_copy_from_jpeg(ctx, ones) != GZB_OK) return false;
+    if (gzb_apply_global_quantization(ctx, &q[0][0]) != GZB_OK) return false;
+    memcpy(quant, q, sizeof(quant));
+    parallel_rows(nb, nthreads, [&](int b0, int b1) {
+      for (int c = 0; c < 3; ++c) {
+        const int16_t* o = orig[c].data();
+        int16_t* cu = cur[c].data();
+        int16_t* ix = idx[c].data();
+        for (size_t i = static_cast<size_t>(b0) * 64; i < static_cast<size_t>(b1) * 64; ++i) {
+          const int qq = q[c][i & 63];
+          const int16_t v = quantize_coeff(o[i], qq);
+          cu[i] = v;
+          ix[i] = static_cast<int16_t>(v / qq);
+        }
+      }
+    });
+    st.host_quant_ms += now_ms() - t0;
+    return true;
+  }
+};
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+double gzb_butteraugli_score_for_quality(double quality) {
+  // guetzli/quality.cc:31-85 (median butteraugli scores of libjpeg-turbo output per quality level)
+  static const double kScore[] = {
+      2.810761, 2.729300, 2.689687, 2.636811, 2.547863, 2.525400, 2.473416, 2.366133, 2.338078, 2.318654,
+      2.201674, 2.145517, 2.087322, 2.009328, 1.945456, 1.900112, 1.805701, 1.750194, 1.644175, 1.562165,
+      1.473608, 1.382021, 1.294298, 1.185402, 1.066781, 0.971769, 0.852901, 0.724544, 0.611302, 0.443185,
+      0.211578, 0.209462, 0.207346, 0.205230, 0.203114, 0.200999, 0.198883, 0.196767, 0.194651, 0.192535,
+      0.190420, 0.190420};
+  if (quality < 70) quality = 70;
+  if (quality > 110) quality = 110;
+  const int index = static_cast<int>(quality);
+  const double mix = quality - index;
+  return kScore[index - 70] * (1 - mix) + kScore[index - 70 + 1] * mix;
+}
+
+void gzb_free(void* p) { free(p); }
+
+static std::string g_encode_err;
+const char* gzb_encode_last_error(void) { return g_encode_err.c_str(); }
+
+int gzb_rgb_to_jpeg_coeffs(const uint8_t* rgb, int width, int height, int16_t* c0, int16_t* c1, int16_t* c2) {
+  if (!rgb || !c0 || !c1 || !c2 || width <= 0 || height <= 0 || width >= (1 << 16) || height >= (1 << 16))
+    return GZB_ERR_BAD_ARG;
+  int16_t* out[3] = {c0, c1, c2};
+  const int bw = (width + 7) / 8, bh = (height + 7) / 8;
+  const int nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  parallel_rows(bh, nt, [&](int y0, int y1) { rgb_to_coeffs_rows(rgb, width, height, bw, y0, y1, out); });
+  return GZB_OK;
+}
+
+long gzb_write_jpeg(const int16_t* c0, const int16_t* c1, const int16_t* c2, int width, int height,
+                    const int* q192, int input_tables, int host_threads, uint8_t* out, long cap) {
+  if (!c0 || !c1 || !c2 || !q192 || width <= 0 || height <= 0) return GZB_ERR_BAD_ARG;
+  const int bw = (width + 7) / 8, bh = (height + 7) / 8;
+  const size_t n = static_cast<size_t>(bw) * bh * 64;
+  const int16_t* src[3] = {c0, c1, c2};
+  std::vector<int16_t> idx[3];
+  int q[3][64];
+  memcpy(q, q192, sizeof(q));
+  bool chroma = false;
+  for (int c = 0; c < 3; ++c) {
+    idx[c].resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      if (q[c][i & 63] <= 0) return GZB_ERR_BAD_ARG;
+      idx[c][i] = static_cast<int16_t>(src[c][i] / q[c][i & 63]);
+      if (c > 0 && src[c][i] != 0) chroma = true;
+    }
+  }
+  Frame f;
+  f.width = width; f.height = height; f.bw = bw; f.bh = bh;
+  f.ncomp = (chroma || input_tables) ? 3 : 1;
+  for (int c = 0; c < 3; ++c) f.coeffs[c] = idx[c].data();
+  if (input_tables) gzb::jpeg::frame_set_quant_input(&f, q); else gzb::jpeg::frame_set_quant(&f, q);
+  std::string s;
+  gzb::jpeg::write_jpeg(f, &s, host_threads > 0 ? host_threads : 1);
+  if (out && static_cast<long>(s.size()) <= cap) memcpy(out, s.data(), s.size());
+  return static_cast<long>(s.size());
+}
+
+// Test hooks: the lazy order must equal std::sort's permutation on the consumed prefix.
+void gzb_test_lazy_sort(int* first, float* second, size_t n, size_t prefix) {
+  std::vector<OrderEntry> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(first[i], second[i]);
+  LazySort ls(v.data(), n);
+  if (prefix > 0) ls.ensure(std::min(prefix, n) - 1);
+  for (size_t i = 0; i < n; ++i) { first[i] = v[i].first; second[i] = v[i].second; }
+}
+void gzb_test_std_sort(int* first, float* second, size_t n) {
+  std::vector<OrderEntry> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(first[i], second[i]);
+  std::sort(v.begin(), v.end(), [](const OrderEntry& a, const OrderEntry& b) { return a.second < b.second; });
+  for (size_t i = 0; i < n; ++i) { first[i] = v[i].first; second[i] = v[i].second; }
+}
+
+int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
+                   int host_threads, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
+                   char** trace_out) {
+  g_encode_err.clear();
+  if (!rgb || !jpeg_out || !jpeg_size) { g_encode_err = "gzb_encode_rgb: null argument"; return GZB_ERR_BAD_ARG; }
+  *jpeg_out = nullptr; *jpeg_size = 0;
+  if (trace_out) *trace_out = nullptr;
+  if (butteraugli_target > 2.0f) {  // processor.cc:939-945
+    g_encode_err = "gzb_encode_rgb: quality below 84 is refused (butteraugli target > 2.0)";
+    return GZB_ERR_BAD_ARG;
+  }
+  if (width < 32 || height < 32) {
+    g_encode_err = "gzb_encode_rgb: images smaller than 32x32 skip butteraugli in the reference; not accelerated";
+    return GZB_ERR_TOO_SMALL;
+  }
+  if (width >= (1 << 16) || height >= (1 << 16)) { g_encode_err = "gzb_encode_rgb: image too large"; return GZB_ERR_BAD_ARG; }
+  const double t_start = now_ms();
+  Encoder e;
+  e.w = width; e.h = height; e.bw = (width + 7) / 8; e.bh = (height + 7) / 8; e.nb = e.bw * e.bh;
+  e.target = butteraugli_target;
+  e.want_trace = trace_out != nullptr;
+  const unsigned hc = std::thread::hardware_concurrency();
+  e.nthreads = host_threads > 0 ? host_threads : static_cast<int>(std::max(1u, std::min(16u, hc)));
+  const size_t ncoef = static_cast<size_t>(e.nb) * 64;
+  for (int c = 0; c < 3; ++c) { e.orig[c].resize(ncoef); e.cur[c].resize(ncoef); e.idx[c].resize(ncoef); }
+  int rc = gzb_create(device, width, height, rgb, butteraugli_target, &e.ctx);
+  if (rc != GZB_OK) { g_encode_err = gzb_last_error(nullptr); return rc; }
+  auto fail = [&](int code) {
+    g_encode_err = gzb_last_error(e.ctx);
+    gzb_destroy(e.ctx);
+    return code;
+  };
+  // EncodeRGBToJpeg (q = 1)
+  {
+    const double t0 = now_ms();
+    int16_t* out[3] = {e.orig[0].data(), e.orig[1].data(), e.orig[2].data()};
+    parallel_rows(e.bh, e.nthreads, [&](int y0, int y1) { rgb_to_coeffs_rows(rgb, width, height, e.bw, y0, y1, out); });
+    e.st.host_frontend_ms = now_ms() - t0;
+  }
+  if (gzb_set_jpeg_coeffs(e.ctx, e.orig[0].data(), e.orig[1].data(), e.orig[2].data()) != GZB_OK) return fail(GZB_ERR_CUDA);
+  int ones[3][64];
+  for (int c = 0; c < 3; ++c) for (int k = 0; k < 64; ++k) ones[c][k] = 1;
+  // "Original": the q=1 input as a JPEG with three index-0 tables (processor.cc:967-985)
+  std::string encoded;
+  {
+    Frame f;
+    f.width = width; f.height = height; f.bw = e.bw; f.bh = e.bh; f.ncomp = 3;
+    for (int c = 0; c < 3; ++c) f.coeffs[c] = e.orig[c].data();
+    gzb::jpeg::frame_set_quant_input(&f, ones);
+    const double t0 = now_ms();
+    gzb::jpeg::write_jpeg(f, &encoded, e.nthreads);
+    e.st.host_write_ms += now_ms() - t0;
+    e.st.num_jpeg_writes++;
+  }
+  e.log("Original Out[%7zd]", encoded.size());
+  if (gzb_copy_from_jpeg(e.ctx, &ones[0][0]) != GZB_OK) return fail(GZB_ERR_CUDA);
+  if (!e.compare()) return fail(GZB_ERR_CUDA);
+  e.maybe_output(encoded);
+
+  // ---- SelectQuantMatrix (processor.cc:310-372) ----
+  int best_q[3][64];
+  memcpy(best_q, ones, sizeof(best_q));
+  auto try_quant = [&](int q[3][64], QuantData* data) -> bool {
+    memcpy(data->q, q, sizeof(data->q));
+    if (!e.set_global_quant(q)) return false;
+    std::string jpg;
+    e.write_candidate(&jpg);
+    e.log("Iter %2d: f111111 GQ[%5.2f] Out[%7zd]", e.st.num_iterations + 1, quant_heuristic_score(q), jpg.size());
+    ++e.st.num_iterations;
+    if (!e.compare()) return false;
+    data->dist_ok = gzb_distance_ok(e.ctx, 0.97f) != 0;  // target_mul_high is a float constant
+    data->jpg_size = jpg.size();
+    e.maybe_output(jpg);
+    return true;
+  };
+  QuantData best;
+  if (!try_quant(best_q, &best)) return fail(GZB_ERR_CUDA);
+  {
+    QuantGenerator gen;
+    for (;;) {
+      int q_next[3][64];
+      if (!gen.next(q_next)) break;
+      QuantData data;
+      if (!try_quant(q_next, &data)) return fail(GZB_ERR_CUDA);
+      gen.add(data);
+      if (quant_data_better(data, best)) {
+        best = data;
+        if (data.dist_ok && !gzb_distance_ok(e.ctx, 0.95f)) break;
+      }
+    }
+  }
+  memcpy(best_q, best.q, sizeof(best_q));
+  if (!best.dist_ok)
+    for (int c = 0; c < 3; ++c) for (int k = 0; k < 64; ++k) best_q[c][k] = 1;
+  if (!e.set_global_quant(best_q)) return fail(GZB_ERR_CUDA);
+
+  // ---- SelectFrequencyMasking(jpg, img, 7, 1.0, false) (processor.cc:559-721) ----
+  const int comp_mask = 7;
+  const double target_mul = 1.0;
+  const int num_blocks = e.nb;
+  std::vector<int> cand_offsets(num_blocks + 1);
+  std::vector<uint8_t> cand_coeffs;
+  std::vector<float> cand_errors;
+  {
+    if (gzb_start_block_comparisons(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
+    const double t0 = now_ms();
+    std::vector<gzb_coeff_data> order(static_cast<size_t>(num_blocks) * 192);
+    if (gzb_compute_block_zeroing_order(e.ctx, comp_mask, order.data()) != GZB_OK) return fail(GZB_ERR_CUDA);
+    e.st.device_zeroing_ms = gzb_last_device_ms(e.ctx);
+    e.st.zeroing_wall_ms = now_ms() - t0;
+    const float limit = gzb_block_error_limit(e.ctx);
+    for (int b = 0; b < num_blocks; ++b) {
+      const gzb_coeff_data* p = &order[static_cast<size_t>(b) * 192];
+      cand_offsets[b] = static_cast<int>(cand_coeffs.size());
+      for (int i = 0; i < 192; ++i)
+        if (p[i].block_err > 0 && p[i].block_err <= limit) {
+          cand_coeffs.push_back(static_cast<uint8_t>(p[i].idx));
+          cand_errors.push_back(p[i].block_err);
+        }
+    }
+    cand_offsets[num_blocks] = static_cast<int>(cand_coeffs.size());
+    gzb_finish_block_comparisons(e.ctx);
+  }
+
+  // ---- SelectFrequencyBackEnd (processor.cc:723-919) ----
+  {
+    const double t_be = now_ms();
+    const int ncomp = 3;
+    Histogram ac_hist[3];
+    int header_size, dc_size;
+    {
+      Frame f;
+      f.width = width; f.height = height; f.bw = e.bw; f.bh = e.bh; f.ncomp = e.ncomp_for_output();
+      for (int c = 0; c < 3; ++c) f.coeffs[c] = e.idx[c].data();
+      gzb::jpeg::frame_set_quant(&f, e.quant);
+      header_size = static_cast<int>(gzb::jpeg::header_size(f));
+      dc_size = static_cast<int>(gzb::jpeg::estimate_dc_size(f));
+      gzb::jpeg::build_ac_histograms(f, ac_hist);
+    }
+    std::vector<uint8_t> ac_depths(3 * Histogram::kSize);
+    // ComputeEntropyCodes (processor.cc:517-536)
+    auto compute_entropy_codes = [&]() -> size_t {
+      Histogram clustered[3] = {ac_hist[0], ac_hist[1], ac_hist[2]};
+      size_t num = ncomp;
+      int indexes[4];
+      uint8_t cd[3 * Histogram::kSize];
+      gzb::jpeg::cluster_histograms(clustered, &num, indexes, cd);
+      for (int i = 0; i < ncomp; ++i)
+        memcpy(&ac_depths[i * Histogram::kSize], &cd[indexes[i] * Histogram::kSize], Histogram::kSize);
+      size_t hs = 0;
+      for (size_t i = 0; i < num; ++i) hs += gzb::jpeg::header_cost_bits(clustered[i]) / 8;
+      ++e.st.num_entropy_code_builds;
+      return hs;
+    };
+    // EntropyCodedDataSize (processor.cc:538-546), with the raw bit sums cached per component.
+    uint64_t raw_bits[3];
+    auto recount_bits = [&]() {
+      for (int c = 0; c < ncomp; ++c) {
+        uint64_t bits = 0;
+        const uint8_t* d = &ac_depths[c * Histogram::kSize];
+        for (int i = 0; i + 1 < Histogram::kSize; ++i) bits += static_cast<uint64_t>(ac_hist[c].counts[i] / 2) * (d[i] + (i & 0xf));
+        raw_bits[c] = bits;
+      }
+    };
+    auto coded_size = [&]() -> size_t {
+      size_t numbits = 0;
+      for (int c = 0; c < ncomp; ++c) numbits += raw_bits[c] + ((raw_bits[c] * 3 + 512) >> 10);
+      return (numbits + 7) / 8;
+    };
+    int ac_histogram_size = static_cast<int>(compute_entropy_codes());
+    recount_bits();
+    const int base_size = header_size + dc_size + ac_histogram_size + static_cast<int>(coded_size());
+    int prev_size = base_size;
+
+    std::vector<float> max_block_error(num_blocks);
+    std::vector<int> last_indexes(num_blocks);
+    std::vector<float> block_weight(num_blocks);
+    std::vector<OrderEntry> global_order;
+    std::vector<int32_t> upd_block;
+    std::vector<uint8_t> upd_idx;
+    std::vector<int16_t> upd_val;
+    bool first_up_iter = true;
+    const int directions[2] = {1, -1};
+    for (int direction : directions) {
+      for (;;) {
+        int blocks_to_change = 0;
+        for (int rblock = 1; rblock <= 4; ++rblock) {
+          // distmap is all zeros until the first iteration has compared (processor.cc:777-780)
+          if (first_up_iter && gzb_clear_distmap(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
+          if (gzb_compute_block_error_adjustment_weights(e.ctx, direction, rblock, target_mul, nullptr,
+                                                         block_weight.data()) != GZB_OK) return fail(GZB_ERR_CUDA);
+          global_order.clear();
+          blocks_to_change = 0;
+          for (int b = 0; b < num_blocks; ++b) {
+            const int last_index = last_indexes[b];
+            const int offset = std::max(0, std::min(cand_offsets[b], static_cast<int>(cand_errors.size()) - 1));
+            const int num_candidates = cand_offsets[b + 1] - offset;
+            const float* errs = cand_errors.data() + offset;
+            const float max_err = max_block_error[b];
+            if (block_weight[b] == 0) continue;
+            if (direction > 0) {
+              for (int i = last_index; i < num_candidates; ++i)
+                global_order.push_back(std::make_pair(b, (errs[i] - max_err) / block_weight[b]));
+              blocks_to_change += last_index < num_candidates ? 1 : 0;
+            } else {
+              for (int i = last_index - 1; i >= 0; --i)
+                global_order.push_back(std::make_pair(b, (max_err - errs[i]) / block_weight[b]));
+              blocks_to_change += last_index > 0 ? 1 : 0;
+            }
+          }
+          if (!global_order.empty()) break;
+        }
+        if (global_order.empty()) break;
+
+        LazySort sorter(global_order.data(), global_order.size());
+        double rel_size_delta = direction > 0 ? 0.01 : 0.0005;
+        if (direction > 0 && gzb_distance_ok(e.ctx, 1.0)) rel_size_delta = 0.05;
+        const double min_size_delta = base_size * rel_size_delta;
+        const float coeffs_to_change_per_block = direction > 0 ? 2.0f : 1 * 1 * 0.2f;
+        int min_coeffs_to_change = static_cast<int>(coeffs_to_change_per_block * blocks_to_change);
+        if (first_up_iter) {
+          const float limit = 0.75f * gzb_block_error_limit(e.ctx);
+          // partition_point on the sorted order == number of entries below the limit
+          size_t below = 0;
+          for (const OrderEntry& oe : global_order) below += oe.second < limit ? 1 : 0;
+          min_coeffs_to_change = std::max<int>(min_coeffs_to_change, static_cast<int>(below));
+          first_up_iter = false;
+        }
+        std::set<int> changed_blocks;
+        float val_threshold = 0.0;
+        int changed_coeffs = 0;
+        int est_jpg_size = prev_size;
+        upd_block.clear(); upd_idx.clear(); upd_val.clear();
+        const size_t order_size = global_order.size();
+        for (size_t i = 0; i < order_size; ++i) {
+          sorter.ensure(i);
+          const int b = global_order[i].first;
+          const int last_idx = last_indexes[b];
+          const int offset = std::max(0, std::min(cand_offsets[b], static_cast<int>(cand_coeffs.size()) - 1));
+          const uint8_t* candidates = cand_coeffs.data() + offset;
+          const int idx = candidates[last_idx + std::min(direction, 0)];
+          const int c = idx / 64, k = idx % 64;
+          const int* qc = e.quant[c];
+          int16_t* blk = e.cur[c].data() + static_cast<size_t>(b) * 64;
+          int16_t* blk_idx = e.idx[c].data() + static_cast<size_t>(b) * 64;
+          const int16_t newval = direction > 0 ? 0 : quantize_coeff(e.orig[c][static_cast<size_t>(b) * 64 + k], qc[k]);
+          // UpdateACHistogram(-1, old) ; UpdateACHistogram(+1, new) (processor.cc:491-515, 871-873),
+          // with the cached raw bit sums following the histogram
+          auto apply = [&](int weight) {
+            int run = 0;
+            Histogram& hh = ac_hist[c];
+            const uint8_t* d = &ac_depths[c * Histogram::kSize];
+            for (int z = 1; z < 64; ++z) {
+              const int v = blk_idx[gzb::jpeg::kNaturalOrder[z]];
+              if (v == 0) { ++run; continue; }
+              while (run > 15) { hh.add(0xf0, weight); raw_bits[c] += static_cast<int64_t>(weight) * (d[0xf0] + 0); run -= 16; }
+              const int nbits = 32 - __builtin_clz(static_cast<unsigned>(std::abs(v)));
+              const int sym = (run << 4) + nbits;
+              hh.add(sym, weight);
+              raw_bits[c] += static_cast<int64_t>(weight) * (d[sym] + (sym & 0xf));
+              run = 0;
+            }
+            if (run > 0) { hh.add(0, weight); raw_bits[c] += static_cast<int64_t>(weight) * d[0]; }
+          };
+          apply(-1);
+          blk[k] = newval;
+          blk_idx[k] = static_cast<int16_t>(newval / qc[k]);
+          apply(1);
+          upd_block.push_back(b); upd_idx.push_back(static_cast<uint8_t>(idx)); upd_val.push_back(newval);
+          last_indexes[b] += direction;
+          changed_blocks.insert(b);
+          val_threshold = global_order[i].second;
+          ++changed_coeffs;
+          if (i % 10 == 0) {
+            // Evaluate only where the result can be observed: by the break test within the next 10
+            // steps, or as prev_size when the order is about to run out.
+            const bool needed = static_cast<long long>(i) + 9 >= min_coeffs_to_change ||
+                                i + 9 >= order_size - 1;
+            if (needed) {
+              ac_histogram_size = static_cast<int>(compute_entropy_codes());
+              recount_bits();
+            }
+          }
+          if (changed_coeffs > min_coeffs_to_change || i + 1 == order_size) {
+            est_jpg_size = header_size + dc_size + ac_histogram_size + static_cast<int>(coded_size());
+            if (changed_coeffs > min_coeffs_to_change && std::abs(est_jpg_size - prev_size) > min_size_delta) break;
+          }
+        }
+        for (int i = 0; i < num_blocks; ++i) max_block_error[i] += block_weight[i] * val_threshold * direction;
+        ++e.st.num_iterations;
+        if (direction > 0) ++e.st.num_iterations_up; else ++e.st.num_iterations_down;
+        // push the changed coefficients to the device, write the file while the GPU compares
+        if (gzb_update_coeffs(e.ctx, upd_block.data(), upd_idx.data(), upd_val.data(), upd_block.size()) != GZB_OK)
+          return fail(GZB_ERR_CUDA);
+        std::string jpg;
+        std::future<void> writer = std::async(std::launch::async, [&]() { e.write_candidate(&jpg); });
+        const bool ok = e.compare(true);
+        writer.get();
+        if (!ok) return fail(GZB_ERR_CUDA);
+        e.log("Iter %2d: f111111(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
+              e.st.num_iterations, comp_mask, direction > 0 ? "up" : "down", changed_coeffs, order_size,
+              changed_blocks.size(), blocks_to_change, num_blocks, val_threshold, jpg.size(),
+              100.0 - (100.0 * est_jpg_size) / jpg.size());
+        e.log(" BA[100.00%%] D[%6.4f]", e.distance);
+        e.maybe_output(jpg);
+        prev_size = est_jpg_size;
+      }
+    }
+    e.st.backend_wall_ms = now_ms() - t_be;
+  }
+
+  e.st.launches = gzb_launch_count(e.ctx);
+  gzb_destroy(e.ctx);
+  *jpeg_size = e.best_jpeg.size();
+  *jpeg_out = static_cast<uint8_t*>(malloc(std::max<size_t>(1, e.best_jpeg.size())));
+  memcpy(*jpeg_out, e.best_jpeg.data(), e.best_jpeg.size());
+  e.st.total_wall_ms = now_ms() - t_start;
+  e.st.final_distance = e.distance;
+  e.st.final_score = e.best_score;
+  if (stats) *stats = e.st;
+  if (trace_out) {
+    *trace_out = static_cast<char*>(malloc(e.trace.size() + 1));
+    memcpy(*trace_out, e.trace.c_str(), e.trace.size() + 1);
+  }
+  return GZB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,436 @@
+// gzb_jpeg.cc -- see gzb_jpeg.h. Output bytes are identical to the reference writer's.
+#include "gzb_jpeg.h"
+
+#include <algorithm>
+#include <cassert>
+#include <cstdlib>
+#include <thread>
+
+namespace gzb {
+namespace jpeg {
+
+const int kNaturalOrder[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
+                               12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
+                               35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+                               58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+const int kZigZag[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42,
+                         3,  8,  12, 17, 25, 30, 41, 43, 9,  11, 18, 24, 31, 40, 44, 53,
+                         10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60,
+                         21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+
+static inline int log2_floor_nz(uint32_t n) { return 31 ^ __builtin_clz(n); }
+static inline int bit_length(uint32_t n) { return n == 0 ? 0 : log2_floor_nz(n) + 1; }
+
+// ---------------------------------------------------------------------------------------------
+// Huffman depths: package-free two-queue construction with a rising count floor until the tree
+// fits `limit` bits (entropy_encode.cc:68-143). Ties: equal counts order by descending symbol.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Node { uint32_t count; int16_t left; int16_t right_or_value; };
+
+bool assign_depths(int root, const Node* pool, uint8_t* depth, int max_depth) {
+  int stack[17];
+  int level = 0, p = root;
+  stack[0] = -1;
+  for (;;) {
+    if (pool[p].left >= 0) {
+      if (++level > max_depth) return false;
+      stack[level] = pool[p].right_or_value;
+      p = pool[p].left;
+      continue;
+    }
+    depth[pool[p].right_or_value] = static_cast<uint8_t>(level);
+    while (level >= 0 && stack[level] == -1) --level;
+    if (level < 0) return true;
+    p = stack[level];
+    stack[level] = -1;
+  }
+}
+}  // namespace
+
+void huffman_depths(const uint32_t* counts, int length, int limit, uint8_t* depth) {
+  Node tree[2 * Histogram::kSize + 1];
+  for (uint32_t floor_count = 1;; floor_count *= 2) {
+    int n = 0;
+    for (int i = length; i-- > 0;)
+      if (counts[i]) tree[n++] = Node{std::max(counts[i], floor_count), -1, static_cast<int16_t>(i)};
+    if (n == 1) {
+      depth[tree[0].right_or_value] = 1;
+      return;
+    }
+    std::sort(tree, tree + n, [](const Node& a, const Node& b) {
+      if (a.count != b.count) return a.count < b.count;
+      return a.right_or_value > b.right_or_value;
+    });
+    const Node sentinel{~0u, -1, -1};
+    tree[n] = sentinel;
+    tree[n + 1] = sentinel;
+    int i = 0, j = n + 1;
+    for (int k = n - 1; k != 0; --k) {
+      int left, right;
+      if (tree[i].count <= tree[j].count) left = i++; else left = j++;
+      if (tree[i].count <= tree[j].count) right = i++; else right = j++;
+      const int parent = 2 * n - k;
+      tree[parent].count = tree[left].count + tree[right].count;
+      tree[parent].left = static_cast<int16_t>(left);
+      tree[parent].right_or_value = static_cast<int16_t>(right);
+      tree[parent + 1] = sentinel;
+    }
+    if (assign_depths(2 * n - 1, tree, depth, limit)) return;
+  }
+}
+
+size_t header_cost_bits(const Histogram& h) {
+  size_t bits = 17 * 8;
+  for (int i = 0; i + 1 < Histogram::kSize; ++i) bits += h.counts[i] > 0 ? 8 : 0;
+  return bits;
+}
+
+size_t entropy_cost_bits(const Histogram& h, const uint8_t* depth) {
+  size_t bits = 0;
+  for (int i = 0; i + 1 < Histogram::kSize; ++i) bits += (h.counts[i] / 2) * (depth[i] + (i & 0xf));
+  bits += (bits * 3 + 512) >> 10;  // escape-byte estimate
+  return bits;
+}
+
+size_t cluster_histograms(Histogram* histo, size_t* num, int* indexes, uint8_t* depth) {
+  memset(depth, 0, *num * Histogram::kSize);
+  size_t costs[4];
+  for (size_t i = 0; i < *num; ++i) {
+    indexes[i] = static_cast<int>(i);
+    huffman_depths(histo[i].counts, Histogram::kSize, 16, depth + i * Histogram::kSize);
+    costs[i] = header_cost_bits(histo[i]) + entropy_cost_bits(histo[i], depth + i * Histogram::kSize);
+  }
+  const size_t orig_num = *num;
+  while (*num > 1) {
+    const size_t last = *num - 1, prev = *num - 2;
+    Histogram both(histo[last]);
+    both.merge(histo[prev]);
+    uint8_t depth_both[Histogram::kSize] = {0};
+    huffman_depths(both.counts, Histogram::kSize, 16, depth_both);
+    const size_t cost_both = header_cost_bits(both) + entropy_cost_bits(both, depth_both);
+    if (!(cost_both < costs[last] + costs[prev])) break;
+    histo[prev] = both;
+    histo[last] = Histogram();
+    costs[prev] = cost_both;
+    memcpy(depth + prev * Histogram::kSize, depth_both, sizeof(depth_both));
+    for (size_t i = 0; i < orig_num; ++i)
+      if (indexes[i] == static_cast<int>(last)) indexes[i] = static_cast<int>(prev);
+    --*num;
+  }
+  size_t total = 0;
+  for (size_t i = 0; i < *num; ++i) total += costs[i];
+  return (total + 7) / 8;
+}
+
+void ac_histogram_add_block(const int16_t* q, int weight, Histogram* h) {
+  int run = 0;
+  for (int k = 1; k < 64; ++k) {
+    const int v = q[kNaturalOrder[k]];
+    if (v == 0) { ++run; continue; }
+    while (run > 15) { h->add(0xf0, weight); run -= 16; }
+    h->add((run << 4) + bit_length(static_cast<uint32_t>(std::abs(v))), weight);
+    run = 0;
+  }
+  if (run > 0) h->add(0, weight);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Frame helpers
+// ---------------------------------------------------------------------------------------------
+void frame_set_quant(Frame* f, const int q[3][64]) {
+  f->num_tables = 0;
+  for (int c = 0; c < f->ncomp; ++c) {
+    int found = -1;
+    for (int t = 0; t < f->num_tables; ++t)
+      if (memcmp(q[c], f->table_values[t], 64 * sizeof(int)) == 0) { found = t; break; }
+    if (found < 0) {
+      found = f->num_tables++;
+      memcpy(f->table_values[found], q[c], 64 * sizeof(int));
+      f->table_index[found] = found;
+    }
+    f->comp_table[c] = found;
+  }
+}
+
+void frame_set_quant_input(Frame* f, const int q[3][64]) {
+  f->num_tables = 3;
+  for (int c = 0; c < 3; ++c) {
+    memcpy(f->table_values[c], q[c], 64 * sizeof(int));
+    f->table_index[c] = 0;
+    f->comp_table[c] = c;
+  }
+}
+
+static int table_precision(const int* v) {
+  for (int k = 0; k < 64; ++k) if (v[k] > 0xff) return 1;
+  return 0;
+}
+
+size_t header_size(const Frame& f) {
+  size_t n = 2 + 18 + 4;  // SOI, APP0, DQT marker
+  for (int t = 0; t < f.num_tables; ++t) n += 1 + (table_precision(f.table_values[t]) ? 2 : 1) * 64;
+  n += 10 + 3 * f.ncomp;  // SOF
+  n += 4;                 // DHT without code data
+  n += 8 + 2 * f.ncomp;   // SOS
+  n += 2;                 // EOI
+  return n;
+}
+
+static void build_dc_histograms(const Frame& f, Histogram* h) {
+  const size_t nb = static_cast<size_t>(f.bw) * f.bh;
+  for (int c = 0; c < f.ncomp; ++c) {
+    int last = 0;
+    const int16_t* p = f.coeffs[c];
+    for (size_t b = 0; b < nb; ++b) {
+      const int dc = p[b * 64];
+      h[c].add(bit_length(static_cast<uint32_t>(std::abs(dc - last))));
+      last = dc;
+    }
+  }
+}
+
+size_t estimate_dc_size(const Frame& f) {
+  Histogram h[3];
+  build_dc_histograms(f, h);
+  size_t num = f.ncomp;
+  int idx[4];
+  uint8_t depth[3 * Histogram::kSize];
+  return cluster_histograms(h, &num, idx, depth);
+}
+
+void build_ac_histograms(const Frame& f, Histogram* h) {
+  const size_t nb = static_cast<size_t>(f.bw) * f.bh;
+  for (int c = 0; c < f.ncomp; ++c) {
+    const int16_t* p = f.coeffs[c];
+    for (size_t b = 0; b < nb; ++b) ac_histogram_add_block(p + b * 64, 1, &h[c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bit-stream writer
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct CodeTable { uint8_t depth[256]; uint16_t code[256]; };
+
+// Canonical code from depths; the sentinel (symbol 256, deepest, last) is dropped
+// (BuildHuffmanCode + BuildHuffmanCodeTable, jpeg_data_writer.cc:136-187).
+void make_code(const uint8_t* depth257, int counts[17], int values[257], CodeTable* table) {
+  memset(counts, 0, 17 * sizeof(int));
+  for (int i = 0; i < 257; ++i) if (depth257[i] > 0) ++counts[depth257[i]];
+  int offset[17] = {0};
+  for (int l = 1; l <= 16; ++l) offset[l] = offset[l - 1] + counts[l - 1];
+  for (int i = 0; i < 257; ++i) if (depth257[i] > 0) values[offset[depth257[i]]++] = i;
+  memset(table->depth, 255, sizeof(table->depth));
+  memset(table->code, 0, sizeof(table->code));
+  int total = 0;
+  for (int l = 1; l <= 16; ++l) total += counts[l];
+  if (total == 0) return;
+  int code = 0, p = 0;
+  for (int l = 1; l <= 16; ++l) {
+    for (int i = 0; i < counts[l]; ++i, ++p) {
+      if (p < total - 1) {  // all but the sentinel
+        table->depth[values[p]] = static_cast<uint8_t>(l);
+        table->code[values[p]] = static_cast<uint16_t>(code);
+      }
+      ++code;
+    }
+    code <<= 1;
+  }
+}
+
+// MSB-first bit accumulator without byte stuffing (stuffing is applied when bands are stitched).
+struct BitBuf {
+  std::vector<uint8_t> bytes;
+  uint64_t acc = 0;
+  int nacc = 0;  // bits held in acc (< 8 after flush)
+  size_t total_bits = 0;
+  inline void put(int nbits, uint32_t bits) {
+    acc = (acc << nbits) | bits;
+    nacc += nbits;
+    total_bits += nbits;
+    while (nacc >= 8) {
+      nacc -= 8;
+      bytes.push_back(static_cast<uint8_t>(acc >> nacc));
+    }
+  }
+};
+
+void encode_band(const Frame& f, const CodeTable* dc, const CodeTable* ac, int by0, int by1, BitBuf* out) {
+  int last_dc[3] = {0, 0, 0};
+  if (by0 > 0)
+    for (int c = 0; c < f.ncomp; ++c) last_dc[c] = f.coeffs[c][(static_cast<size_t>(by0) * f.bw - 1) * 64];
+  out->bytes.reserve(static_cast<size_t>(by1 - by0) * f.bw * 24);
+  for (int by = by0; by < by1; ++by)
+    for (int bx = 0; bx < f.bw; ++bx) {
+      const size_t b = static_cast<size_t>(by) * f.bw + bx;
+      for (int c = 0; c < f.ncomp; ++c) {
+        const int16_t* q = f.coeffs[c] + b * 64;
+        const CodeTable& dct = dc[c];
+        const CodeTable& act = ac[c];
+        int diff = static_cast<int16_t>(q[0] - last_dc[c]);  // coeff_t arithmetic
+        last_dc[c] = q[0];
+        int mag = diff, low = diff;
+        if (diff < 0) { mag = -diff; low = diff - 1; }
+        mag = static_cast<int16_t>(mag);
+        int nbits = bit_length(static_cast<uint32_t>(mag));
+        out->put(dct.depth[nbits], dct.code[nbits]);
+        if (nbits > 0) out->put(nbits, static_cast<uint32_t>(low) & ((1u << nbits) - 1));
+        int run = 0;
+        for (int k = 1; k < 64; ++k) {
+          const int v = q[kNaturalOrder[k]];
+          if (v == 0) { ++run; continue; }
+          const int a = v < 0 ? -v : v;
+          const int lowbits = v < 0 ? ~a : a;
+          while (run > 15) { out->put(act.depth[0xf0], act.code[0xf0]); run -= 16; }
+          nbits = bit_length(static_cast<uint32_t>(a));
+          const int sym = (run << 4) + nbits;
+          out->put(act.depth[sym], act.code[sym]);
+          out->put(nbits, static_cast<uint32_t>(lowbits) & ((1u << nbits) - 1));
+          run = 0;
+        }
+        if (run > 0) out->put(act.depth[0], act.code[0]);
+      }
+    }
+}
+
+inline void emit_stuffed(std::string* out, uint8_t b) {
+  out->push_back(static_cast<char>(b));
+  if (b == 0xff) out->push_back('\0');
+}
+
+}  // namespace
+
+void write_jpeg(const Frame& f, std::string* out, int nthreads) {
+  out->clear();
+  const int ncomp = f.ncomp;
+  // SOI + APP0 (stripped metadata always writes the fixed JFIF header)
+  static const uint8_t kHead[] = {0xff, 0xd8, 0xff, 0xe0, 0x00, 0x10, 0x4a, 0x46, 0x49, 0x46, 0x00,
+                                  0x01, 0x01, 0x00, 0x00, 0x01, 0x00, 0x01, 0x00, 0x00};
+  out->append(reinterpret_cast<const char*>(kHead), sizeof(kHead));
+  {  // DQT
+    int len = 2;
+    for (int t = 0; t < f.num_tables; ++t) len += 1 + (table_precision(f.table_values[t]) ? 2 : 1) * 64;
+    out->push_back(static_cast<char>(0xff)); out->push_back(static_cast<char>(0xdb));
+    out->push_back(static_cast<char>(len >> 8)); out->push_back(static_cast<char>(len & 0xff));
+    for (int t = 0; t < f.num_tables; ++t) {
+      const int prec = table_precision(f.table_values[t]);
+      out->push_back(static_cast<char>((prec << 4) + f.table_index[t]));
+      for (int k = 0; k < 64; ++k) {
+        const int v = f.table_values[t][kNaturalOrder[k]];
+        if (prec) out->push_back(static_cast<char>(v >> 8));
+        out->push_back(static_cast<char>(v & 0xff));
+      }
+    }
+  }
+  {  // SOF (marker 0xc1, as the reference writes)
+    const int len = 8 + 3 * ncomp;
+    const uint8_t h[] = {0xff, 0xc1, static_cast<uint8_t>(len >> 8), static_cast<uint8_t>(len & 0xff), 8,
+                         static_cast<uint8_t>(f.height >> 8), static_cast<uint8_t>(f.height & 0xff),
+                         static_cast<uint8_t>(f.width >> 8), static_cast<uint8_t>(f.width & 0xff),
+                         static_cast<uint8_t>(ncomp)};
+    out->append(reinterpret_cast<const char*>(h), sizeof(h));
+    for (int c = 0; c < ncomp; ++c) {
+      out->push_back(static_cast<char>(c));      // component id
+      out->push_back(static_cast<char>(0x11));   // 1x1 sampling
+      out->push_back(static_cast<char>(f.table_index[f.comp_table[c]]));
+    }
+  }
+  // Huffman codes: DC histograms clustered, then AC histograms clustered.
+  Histogram histo[6];
+  uint8_t depths[6 * Histogram::kSize];
+  build_dc_histograms(f, histo);
+  size_t num_dc = ncomp;
+  int dc_idx[4], ac_idx[4];
+  cluster_histograms(histo, &num_dc, dc_idx, depths);
+  for (int c = 0; c < ncomp; ++c) histo[num_dc + c] = Histogram();
+  build_ac_histograms(f, histo + num_dc);
+  size_t num_ac = ncomp;
+  cluster_histograms(histo + num_dc, &num_ac, ac_idx, depths + num_dc * Histogram::kSize);
+  const int num_histo = static_cast<int>(num_dc + num_ac);
+  int total_symbols = 0;
+  for (int i = 0; i < num_histo; ++i) total_symbols += histo[i].num_symbols();
+  const int dht_len = 2 + num_histo * 17 + total_symbols;
+  out->push_back(static_cast<char>(0xff)); out->push_back(static_cast<char>(0xc4));
+  out->push_back(static_cast<char>(dht_len >> 8)); out->push_back(static_cast<char>(dht_len & 0xff));
+  CodeTable dc_tab[3], ac_tab[3];
+  for (int i = 0; i < num_histo; ++i) {
+    const bool is_dc = i < static_cast<int>(num_dc);
+    const int idx = is_dc ? i : i - static_cast<int>(num_dc);
+    int counts[17], values[257] = {0};
+    CodeTable table;
+    make_code(depths + i * Histogram::kSize, counts, values, &table);
+    for (int c = 0; c < ncomp; ++c) {
+      if (is_dc && dc_idx[c] == idx) dc_tab[c] = table;
+      if (!is_dc && ac_idx[c] == idx) ac_tab[c] = table;
+    }
+    int max_len = 16;
+    while (max_len > 0 && counts[max_len] == 0) --max_len;
+    --counts[max_len];
+    int total = 0;
+    for (int l = 0; l <= max_len; ++l) total += l ? counts[l] : 0;
+    out->push_back(static_cast<char>(is_dc ? i : idx + 0x10));
+    for (int l = 1; l <= 16; ++l) out->push_back(static_cast<char>(counts[l]));
+    for (int j = 0; j < total; ++j) out->push_back(static_cast<char>(values[j]));
+  }
+  {  // SOS
+    const int len = 6 + 2 * ncomp;
+    out->push_back(static_cast<char>(0xff)); out->push_back(static_cast<char>(0xda));
+    out->push_back(static_cast<char>(len >> 8)); out->push_back(static_cast<char>(len & 0xff));
+    out->push_back(static_cast<char>(ncomp));
+    for (int c = 0; c < ncomp; ++c) {
+      out->push_back(static_cast<char>(c));
+      out->push_back(static_cast<char>((dc_idx[c] << 4) | ac_idx[c]));
+    }
+    out->push_back(0); out->push_back(63); out->push_back(0);
+  }
+  // Entropy-coded segment: bands of block rows in parallel, stitched at bit granularity.
+  int nb = std::max(1, std::min(nthreads, f.bh));
+  std::vector<BitBuf> bands(nb);
+  if (nb == 1) {
+    encode_band(f, dc_tab, ac_tab, 0, f.bh, &bands[0]);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nb; ++t) {
+      const int y0 = static_cast<int>(static_cast<int64_t>(f.bh) * t / nb);
+      const int y1 = static_cast<int>(static_cast<int64_t>(f.bh) * (t + 1) / nb);
+      th.emplace_back(encode_band, std::cref(f), dc_tab, ac_tab, y0, y1, &bands[t]);
+    }
+    for (auto& t : th) t.join();
+  }
+  size_t est = 0;
+  for (auto& b : bands) est += b.bytes.size() + 8;
+  out->reserve(out->size() + est + est / 64 + 16);
+  uint32_t acc = 0;  // pending bits (< 8) carried between bands
+  int nacc = 0;
+  for (auto& b : bands) {
+    if (nacc == 0) {
+      for (uint8_t v : b.bytes) emit_stuffed(out, v);
+    } else {
+      for (uint8_t v : b.bytes) {
+        acc = (acc << 8) | v;
+        emit_stuffed(out, static_cast<uint8_t>(acc >> nacc));
+        acc &= (1u << nacc) - 1;
+      }
+    }
+    if (b.nacc > 0) {  // band tail: b.nacc (< 8) leftover bits
+      acc = (acc << b.nacc) | static_cast<uint32_t>(b.acc & ((1u << b.nacc) - 1));
+      nacc += b.nacc;
+      if (nacc >= 8) {
+        nacc -= 8;
+        emit_stuffed(out, static_cast<uint8_t>(acc >> nacc));
+        acc &= (1u << nacc) - 1;
+      }
+    }
+  }
+  if (nacc > 0) {  // pad the last byte with ones (JumpToByteBoundary)
+    const uint32_t pad = (1u << (8 - nacc)) - 1;
+    emit_stuffed(out, static_cast<uint8_t>((acc << (8 - nacc)) | pad));
+  }
+  out->push_back(static_cast<char>(0xff));
+  out->push_back(static_cast<char>(0xd9));
+}
+
+}  // namespace jpeg
+}  // namespace gzb

@@ -1,0 +1,78 @@
+// gzb_jpeg.h -- host-side JPEG back end of the search: Huffman code construction, histogram
+// clustering, size estimation and the baseline bit-stream writer.
+//
+// Written from scratch; the OUTPUT BYTES must equal the reference's, because the search scores
+// every candidate by its true encoded size and the golden checksum covers the final file:
+//   guetzli/jpeg_data_writer.cc (WriteJpeg 540-553, BuildAndEncodeHuffmanCodes 361-456,
+//   ClusterHistograms 295-342, EncodeScan 506-536), guetzli/entropy_encode.cc (CreateHuffmanTree
+//   68-143), guetzli/jpeg_bit_writer.h.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace gzb {
+namespace jpeg {
+
+extern const int kNaturalOrder[64];  // zig-zag position -> natural index
+extern const int kZigZag[64];        // natural index -> zig-zag position
+
+// Symbol histogram with every occurrence counted twice plus one sentinel of weight 1 that takes
+// the all-ones code (JpegHistogram, guetzli/jpeg_data_writer.h:54-90).
+struct Histogram {
+  static const int kSize = 257;
+  uint32_t counts[kSize];
+  Histogram() { clear(); }
+  void clear() { memset(counts, 0, sizeof(counts)); counts[kSize - 1] = 1; }
+  void add(int symbol, int weight = 1) { counts[symbol] += 2 * weight; }
+  void merge(const Histogram& o) {
+    for (int i = 0; i + 1 < kSize; ++i) counts[i] += o.counts[i];
+    counts[kSize - 1] = 1;
+  }
+  int num_symbols() const {
+    int n = 0;
+    for (int i = 0; i + 1 < kSize; ++i) n += counts[i] > 0;
+    return n;
+  }
+};
+
+// Length-limited Huffman depths (CreateHuffmanTree).
+void huffman_depths(const uint32_t* counts, int length, int limit, uint8_t* depth);
+size_t header_cost_bits(const Histogram& h);                        // HistogramHeaderCost
+size_t entropy_cost_bits(const Histogram& h, const uint8_t* depth);  // HistogramEntropyCost
+// ClusterHistograms: merges trailing histograms while that is cheaper; returns bytes.
+size_t cluster_histograms(Histogram* histo, size_t* num, int* indexes, uint8_t* depth);
+
+// AC symbols of one block of QUANTISED indices in natural order (UpdateACHistogramForDCTBlock).
+void ac_histogram_add_block(const int16_t* q, int weight, Histogram* h);
+
+// A frame ready to be serialised: quantised indices, block-major, per component.
+struct Frame {
+  int width = 0, height = 0, ncomp = 3;
+  int bw = 0, bh = 0;
+  const int16_t* coeffs[3] = {nullptr, nullptr, nullptr};  // quantised indices [bw*bh*64]
+  // quantisation tables as the file will carry them
+  int num_tables = 0;
+  int table_values[3][64];
+  int table_index[3];     // DQT index byte of table t
+  int comp_table[3];      // table used by component c
+};
+
+// Deduplicates q[3][64] into tables like SaveQuantTables (guetzli/jpeg_data.cc:67-102).
+void frame_set_quant(Frame* f, const int q[3][64]);
+// The reference's RGB front end writes three tables that all carry index 0
+// (guetzli/jpeg_data_encoder.cc:66-83 with JPEGQuantTable::index defaulting to 0).
+void frame_set_quant_input(Frame* f, const int q[3][64]);
+
+size_t header_size(const Frame& f);             // JpegHeaderSize with stripped metadata
+size_t estimate_dc_size(const Frame& f);        // EstimateDCSize (processor.cc:548-555)
+void build_ac_histograms(const Frame& f, Histogram* h /*[ncomp]*/);
+
+// WriteJpeg(jpg, strip_metadata=true, out). nthreads > 1 encodes block-row bands in parallel and
+// stitches the bit streams; the bytes are identical to the sequential writer.
+void write_jpeg(const Frame& f, std::string* out, int nthreads = 1);
+
+}  // namespace jpeg
+}  // namespace gzb

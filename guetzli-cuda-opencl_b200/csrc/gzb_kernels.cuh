@@ -33,6 +33,19 @@ __global__ void k_deinterleave_rgb(const uint8_t* __restrict__ rgb, int W, int H
   planes[2 * plane_stride + o] = s[2];
 }
 
+// Sparse coefficient update (SetCoeffBlock on touched blocks; guetzli/processor.cc:867-874).
+// A coefficient is touched at most once per batch in the back-end loop except when an "up" and a
+// later record hit the same slot; the highest record index must win, so only the last record of a
+// slot writes.
+__global__ void k_scatter_coeffs(const int* __restrict__ block_ix, const int16_t* __restrict__ val,
+                                 const uint8_t* __restrict__ idx, size_t n, size_t comp_stride,
+                                 int16_t* __restrict__ coef) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int id = idx[i];
+  coef[(id >> 6) * comp_stride + static_cast<size_t>(block_ix[i]) * 64 + (id & 63)] = val[i];
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: coefficients -> candidate sRGB8 planes (integer IDCT + YCbCr->RGB).
 //   guetzli/output_image.cc:124-146 (SetCoeffBlock), 68-98 (ToPixels), 642-652 (ToSRGB);

@@ -128,6 +128,45 @@ int gzb_blur(int device, float* plane, size_t xsize, size_t ysize, double sigma,
 int gzb_butteraugli_srgb(int device, const uint8_t* rgb0, const uint8_t* rgb1, int width,
                          int height, float* distance, float* diffmap_out);
 
+/* Zeroes the device-resident distance map (the back end's first "up" iteration runs
+ * ComputeBlockErrorAdjustmentWeights on an all-zero map, guetzli/processor.cc:777-780). */
+int gzb_clear_distmap(gzb_ctx* ctx);
+
+/* ---- whole encoder: guetzli::Process(params, stats, rgb, w, h, &out) ------------------------
+ * (guetzli/processor.cc:1157-1185 with the default Params, guetzli/processor.h:34-42): RGB ->
+ * q=1 coefficients -> SelectQuantMatrix -> SelectFrequencyMasking -> best JPEG. The search driver
+ * and the Huffman writer run on host threads; every butteraugli evaluation, IDCT/quantisation pass
+ * and the zeroing-order search run on the B200. Output bytes equal the CPU reference's.
+ * *jpeg_out is malloc'ed (release with gzb_free). host_threads <= 0 picks min(16, cores).
+ * trace_out, if non-NULL, receives a malloc'ed copy of the verbose trace in the reference's
+ * GUETZLI_LOG format (guetzli/processor.cc:324-331, 905-913). */
+typedef struct {
+  int num_iterations, num_iterations_up, num_iterations_down;  /* ProcessStats counters */
+  int num_compares, num_jpeg_writes, num_entropy_code_builds;
+  double total_wall_ms, host_frontend_ms, host_quant_ms, host_write_ms;
+  double compare_wall_ms, device_compare_ms, zeroing_wall_ms, device_zeroing_ms, backend_wall_ms;
+  double final_score;
+  float final_distance;
+  unsigned long long launches;
+} gzb_encode_stats;
+int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
+                   int host_threads, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
+                   char** trace_out);
+const char* gzb_encode_last_error(void);
+void gzb_free(void* p);
+/* guetzli::ButteraugliScoreForQuality (guetzli/quality.cc:76-85). */
+double gzb_butteraugli_score_for_quality(double quality);
+/* guetzli::EncodeRGBToJpeg with the all-ones quantiser (guetzli/jpeg_data_encoder.cc:66-136):
+ * block-major int16 coefficient planes of ceil(w/8)*ceil(h/8)*64 values each. Host code. */
+int gzb_rgb_to_jpeg_coeffs(const uint8_t* rgb, int width, int height, int16_t* c0, int16_t* c1,
+                           int16_t* c2);
+/* Serialises coefficient planes (dequantised values, multiples of q) to a JPEG byte stream exactly
+ * as OutputImage::SaveToJpegData + WriteJpeg do (guetzli/output_image.cc:579-640,
+ * guetzli/jpeg_data_writer.cc:540-553). input_tables != 0 writes the q tables the way the RGB
+ * front end leaves them (three tables with index 0). Returns the size; copies if it fits cap. */
+long gzb_write_jpeg(const int16_t* c0, const int16_t* c1, const int16_t* c2, int width, int height,
+                    const int* q192, int input_tables, int host_threads, uint8_t* out, long cap);
+
 /* ---- parity/debug: device intermediates of the last gzb_compare --------------------------- */
 /* name in {"xyb0","xyb1","mhic0","mhic1","edge_map","block_dc","block_ac","combined_sqrt",
  * "diffmap","mask_front"}; copies min(cap, size) floats; *n_out = size in floats. */

@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Regenerates the committed golden fixtures from the UNMODIFIED reference compiled into
+oracle/_ref/libgzref.so (run where /root/reference is mounted: `python tests/golden/make_golden.py`).
+
+  bees_q95.json        sha256/size/iterations + the verbose trace of guetzli::Process on
+                       tests/bees.png at quality 95 -- must equal tests/golden_checksums.txt:3
+  synth_encodes.json   sha256/size/iterations of guetzli::Process on seeded synthetic images
+  stage_vectors.npz    small stage-level vectors (diffmap, distance, zeroing order) on a 96x64 image
+"""
+import hashlib, json, os, sys
+import numpy as np
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from _libs import ref, ref_process, RefSession, synth_image, bees
+
+GOLDEN_BEES = "39cfc110d3d389ddf3b9c47adece290ef077b78467f1ed39679b691c6fb7c96d"  # tests/golden_checksums.txt:3
+
+
+def iter_lines(trace):
+    return [l for l in trace.splitlines() if "Out[" in l]
+
+
+def main():
+    L = ref()
+    out = {}
+    img = bees()
+    t = L.ref_butteraugli_score_for_quality(95.0)
+    jpg, iters, trace = ref_process(img, t, want_trace=True)
+    sha = hashlib.sha256(jpg).hexdigest()
+    assert sha == GOLDEN_BEES, sha
+    json.dump({"sha256": sha, "size": len(jpg), "iterations": iters, "target": t, "trace": iter_lines(trace)},
+              open(os.path.join(HERE, "bees_q95.json"), "w"), indent=1)
+    enc = {}
+    for (w, h, q, seed) in [(128, 96, 90, 1234), (160, 120, 95, 1244), (97, 61, 84, 1254), (256, 256, 90, 1234)]:
+        im = synth_image(w, h, seed)
+        t = L.ref_butteraugli_score_for_quality(float(q))
+        jpg, iters, trace = ref_process(im, t, want_trace=True)
+        enc["%dx%d_q%d_s%d" % (w, h, q, seed)] = {"sha256": hashlib.sha256(jpg).hexdigest(), "size": len(jpg),
+                                                   "iterations": iters, "target": t, "trace": iter_lines(trace)}
+    json.dump(enc, open(os.path.join(HERE, "synth_encodes.json"), "w"), indent=1)
+    w, h, target = 96, 64, 0.971769
+    im = synth_image(w, h)
+    s = RefSession(im, target)
+    s.apply_quant(np.full(192, 3, np.int32))
+    d, dm = s.compare()
+    s.start_block_comparisons()
+    zo = s.zeroing_order(7)
+    np.savez_compressed(os.path.join(HERE, "stage_vectors.npz"), jpg_coeffs=s.jpg_coeffs(), coeffs=s.coeffs(),
+                        srgb=s.to_srgb(), distance=np.float32(d), diffmap=dm, zo_idx=zo["idx"], zo_err=zo["err"])
+    print("ok")
+
+
+if __name__ == "__main__":
+    main()

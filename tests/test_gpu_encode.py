@@ -1,0 +1,81 @@
+"""End-to-end parity of the B200 encoder (gzb_encode_rgb == guetzli::Process) against the golden
+fixtures generated from the unmodified reference (tests/golden/make_golden.py):
+  * tests/bees.png at q95 must reproduce the reference's own golden checksum
+    (tests/golden_checksums.txt:3) byte for byte;
+  * seeded synthetic images must reproduce the reference's bytes and its iteration trace."""
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from _libs import synth_image, bees, ROOT
+import __graft_entry__ as ge
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def gz():
+    mod = ge.load_package()
+    assert mod.device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return mod
+
+
+def trace_records(lines):
+    """(out_bytes, distance) per iteration line of a GUETZLI_LOG trace."""
+    out = []
+    for l in lines:
+        m = re.search(r"Out\[\s*(\d+)\].*D\[\s*([0-9.]+)\]", l)
+        if m:
+            out.append((int(m.group(1)), m.group(2)))
+    return out
+
+
+def check(gz, img, gold):
+    jpg, st, trace = gz.Process(img, np.float32(gold["target"]), want_trace=True)
+    got = trace_records([l for l in trace.splitlines() if "Out[" in l])
+    want = trace_records(gold["trace"])
+    first_bad = next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), None)
+    assert first_bad is None and len(got) == len(want), (
+        "trace diverges at record %s: got %s want %s" % (first_bad, got[first_bad:first_bad + 2] if first_bad is not None else len(got),
+                                                          want[first_bad:first_bad + 2] if first_bad is not None else len(want)))
+    assert st["num_iterations"] == gold["iterations"]
+    assert len(jpg) == gold["size"]
+    assert hashlib.sha256(jpg).hexdigest() == gold["sha256"]
+    return st
+
+
+def test_bees_golden_checksum(gz):
+    gold = json.load(open(os.path.join(GOLD, "bees_q95.json")))
+    assert gold["sha256"] == "39cfc110d3d389ddf3b9c47adece290ef077b78467f1ed39679b691c6fb7c96d"
+    st = check(gz, bees(), gold)
+    assert st["launches"] > 100 and st["device_compare_ms"] > 0 and st["device_zeroing_ms"] > 0
+
+
+@pytest.mark.parametrize("key", ["128x96_q90_s1234", "160x120_q95_s1244", "97x61_q84_s1254", "256x256_q90_s1234"])
+def test_synthetic_encodes_equal_reference(gz, key):
+    gold = json.load(open(os.path.join(GOLD, "synth_encodes.json")))[key]
+    m = re.match(r"(\d+)x(\d+)_q(\d+)_s(\d+)", key)
+    w, h, q, seed = map(int, m.groups())
+    assert abs(gz.ButteraugliScoreForQuality(q) - gold["target"]) < 1e-12
+    check(gz, synth_image(w, h, seed), gold)
+
+
+def test_encode_is_deterministic_and_thread_count_independent(gz):
+    img = synth_image(128, 96, 1234)
+    t = np.float32(gz.ButteraugliScoreForQuality(90))
+    a, _, _ = gz.Process(img, t, host_threads=1)
+    b, _, _ = gz.Process(img, t, host_threads=7)
+    assert a == b
+
+
+def test_encode_rejects_bad_input(gz):
+    img = synth_image(64, 48)
+    with pytest.raises(gz.GzbError):
+        gz.Process(img, 2.5)            # quality < 84 is refused (processor.cc:939-945)
+    with pytest.raises(gz.GzbError):
+        gz.Process(img[:16, :16], 1.0)  # < 32 px

@@ -1,0 +1,136 @@
+"""CPU-only tests of the host side of the product: the C ABI loads and exports every symbol the
+header declares, and the host code (front end, JPEG writer, lazy std::sort) reproduces the
+compiled reference byte for byte. No compute call touches a GPU here."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+from _libs import oracle, ref, have_ref, p, RefSession, synth_image, bees, ROOT
+import __graft_entry__ as ge
+
+
+@pytest.fixture(scope="module")
+def gz():
+    return ge.build()
+
+
+def test_abi_exports_every_declared_symbol(gz):
+    hdr = open(os.path.join(ROOT, "include", "gzb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(gzb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 35
+    L = gz.lib()
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+    assert b"sm_100a" in L.gzb_version()
+
+
+def test_no_cpu_fallback_without_gpu(gz):
+    """Without a CUDA device every compute entry point must fail loudly."""
+    if gz.device_count() > 0:
+        pytest.skip("a GPU is present")
+    img = synth_image(64, 48)
+    with pytest.raises(gz.GzbError):
+        gz.ButteraugliComparator(64, 48, img, 1.0)
+    with pytest.raises(gz.GzbError):
+        gz.Process(img, 1.0)
+
+
+def test_product_does_not_touch_oracle():
+    pkg = os.path.join(ROOT, "guetzli-cuda-opencl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                if f == "gen_tables.py":
+                    continue  # writes oracle/gzoracle_tables.h, does not read the oracle
+                # no load / link / include / import of anything that lives under oracle/
+                assert not re.search(r"libgzoracle|libgzref|gzoracle\.|gzo_[a-z]|ref_session|oracle/[\w/]+\.(so|c|cc|h|py)", txt), f
+
+
+def test_quality_table(gz):
+    for q in (84, 90, 95, 100, 97.5, 70, 110, 60, 120):
+        want = oracle_quality(q)
+        assert gz.ButteraugliScoreForQuality(q) == want
+
+
+def oracle_quality(q):
+    if have_ref():
+        return ref().ref_butteraugli_score_for_quality(float(q))
+    table = {84: 1.945456, 90: 1.473608, 95: 0.971769, 100: 0.211578}
+    return table.get(q, gz.ButteraugliScoreForQuality(q))
+
+
+def test_front_end_matches_oracle(gz):
+    for (w, h) in [(64, 48), (70, 45), (33, 39), (444, 258)]:
+        img = synth_image(w, h) if w != 444 else bees()
+        nb = ((w + 7) // 8) * ((h + 7) // 8)
+        want = np.zeros((3, nb, 64), np.int16)
+        oracle().gzo_rgb_to_jpeg_coeffs(p(img), w, h, p(want[0]), p(want[1]), p(want[2]))
+        assert np.array_equal(gz.RgbToJpegCoeffs(img), want)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("w,h,q", [(64, 48, 1), (97, 61, 5), (200, 133, 2), (444, 258, 3), (160, 120, 40)])
+def test_jpeg_writer_bytes_equal_reference(gz, w, h, q):
+    img = synth_image(w, h) if w != 444 else bees()
+    s = RefSession(img, 0.97)
+    qm = np.full(192, q, np.int32)
+    qm[64:] = q + (q > 1)     # chroma table differs -> two tables in the file
+    s.apply_quant(qm)
+    want = s.write_jpeg()
+    for nt in (1, 3, 8):
+        got = gz.WriteJpeg(s.coeffs(), w, h, qm, host_threads=nt)
+        assert hashlib.sha256(got).hexdigest() == hashlib.sha256(want).hexdigest(), (nt, len(got), len(want))
+    s.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_jpeg_writer_grayscale_and_sparse(gz):
+    img = synth_image(96, 80)
+    gray = np.repeat(img[:, :, :1], 3, axis=2)
+    s = RefSession(gray, 0.97)
+    co = s.coeffs()
+    assert not co[1:].any()   # chroma is exactly zero for r=g=b input
+    want = s.write_jpeg()
+    got = gz.WriteJpeg(co, 96, 80, np.ones(192, np.int32))
+    assert got == want
+    s.close()
+    # long zero runs (ZRL symbols) and large magnitudes
+    s = RefSession(img, 0.97)
+    co = s.jpg_coeffs().copy()
+    rng = np.random.default_rng(1)
+    co[:, :, 1:] = np.where(rng.random(co[:, :, 1:].shape) < 0.03, co[:, :, 1:] * 7, 0).astype(np.int16)
+    s.set_coeffs(co)
+    assert gz.WriteJpeg(co, 96, 80, np.ones(192, np.int32)) == s.write_jpeg()
+    s.close()
+
+
+def test_lazy_sort_equals_std_sort(gz):
+    L = gz.lib()
+    L.gzb_test_lazy_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    L.gzb_test_std_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(4)
+    for n in [0, 1, 2, 15, 16, 17, 33, 100, 1000, 5000, 70000]:
+        for kind in range(4):
+            if kind == 0:
+                v = rng.random(n).astype(np.float32)
+            elif kind == 1:
+                v = rng.integers(0, 7, n).astype(np.float32)          # heavy ties
+            elif kind == 2:
+                v = np.sort(rng.random(n).astype(np.float32))           # sorted input
+            else:
+                v = (rng.integers(0, max(1, n // 3), n) / 8.0).astype(np.float32)
+            ids = np.arange(n, dtype=np.int32)
+            a_id, a_v = ids.copy(), v.copy()
+            L.gzb_test_std_sort(p(a_id), p(a_v), n)
+            for prefix in sorted({0, 1, n // 100, n // 7, n // 2, n}):
+                b_id, b_v = ids.copy(), v.copy()
+                L.gzb_test_lazy_sort(p(b_id), p(b_v), n, prefix)
+                assert np.array_equal(b_id[:prefix], a_id[:prefix]), (n, kind, prefix)
+                assert np.array_equal(b_v[:prefix], a_v[:prefix])
+                assert sorted(b_id.tolist()) == list(range(n))
