@@ -273,6 +273,9 @@ class EncodeStats(C.Structure):
                 ("total_wall_ms", C.c_double), ("host_frontend_ms", C.c_double), ("host_quant_ms", C.c_double),
                 ("host_write_ms", C.c_double), ("compare_wall_ms", C.c_double), ("device_compare_ms", C.c_double),
                 ("zeroing_wall_ms", C.c_double), ("device_zeroing_ms", C.c_double), ("backend_wall_ms", C.c_double),
+                ("write_hist_ms", C.c_double), ("write_code_ms", C.c_double), ("write_encode_ms", C.c_double),
+                ("write_stitch_ms", C.c_double), ("be_weights_ms", C.c_double), ("be_order_ms", C.c_double),
+                ("be_walk_ms", C.c_double), ("be_update_ms", C.c_double), ("create_ms", C.c_double),
                 ("final_score", C.c_double), ("final_distance", C.c_float), ("launches", C.c_ulonglong)]
 
     def as_dict(self):

@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <future>
+#include <memory>
 #include <set>
 #include <string>
 #include <thread>
@@ -112,16 +113,12 @@ void rgb_to_coeffs_rows(const uint8_t* rgb, int w, int h, int bw, int by0, int b
 }
 
 template <typename F>
-void parallel_rows(int n, int nthreads, F fn) {
-  nthreads = std::max(1, std::min(nthreads, n));
-  if (nthreads == 1) { fn(0, n); return; }
-  std::vector<std::thread> th;
-  for (int t = 0; t < nthreads; ++t) {
-    const int a = static_cast<int>(static_cast<int64_t>(n) * t / nthreads);
-    const int b = static_cast<int>(static_cast<int64_t>(n) * (t + 1) / nthreads);
-    th.emplace_back(fn, a, b);
-  }
-  for (auto& t : th) t.join();
+void parallel_rows(int n, gzb::WorkerPool* pool, F fn) {
+  const int T = std::max(1, std::min(pool ? pool->size() : 1, n));
+  if (T == 1) { fn(0, n); return; }
+  pool->run(T, [&](int t) {
+    fn(static_cast<int>(static_cast<int64_t>(n) * t / T), static_cast<int>(static_cast<int64_t>(n) * (t + 1) / T));
+  });
 }
 
 // ---- quantiser (guetzli/quantize.h:24-29) -----------------------------------------------------
@@ -275,6 +272,8 @@ class LazySort {
 struct Encoder {
   int w = 0, h = 0, bw = 0, bh = 0, nb = 0;
   int nthreads = 1;
+  std::unique_ptr<gzb::WorkerPool> pool;
+  gzb::jpeg::WriteTimers wt;
   float target = 0.f;
   gzb_ctx* ctx = nullptr;
   std::vector<int16_t> orig[3];   // q=1 indices (jpg_in.components[c].coeffs)
@@ -305,14 +304,14 @@ struct Encoder {
   }
 
   // SaveToJpegData + WriteJpeg for the current candidate.
-  void write_candidate(std::string* out) {
+  void write_candidate(std::string* out, const Histogram* dc_hist = nullptr, const Histogram* ac_hist = nullptr) {
     const double t0 = now_ms();
     Frame f;
     f.width = w; f.height = h; f.bw = bw; f.bh = bh;
     f.ncomp = ncomp_for_output();
     for (int c = 0; c < 3; ++c) f.coeffs[c] = idx[c].data();
     gzb::jpeg::frame_set_quant(&f, quant);
-    gzb::jpeg::write_jpeg(f, out, nthreads);
+    gzb::jpeg::write_jpeg(f, out, pool.get(), dc_hist, ac_hist, &wt);
     st.host_write_ms += now_ms() - t0;
     st.num_jpeg_writes++;
   }
@@ -346,7 +345,7 @@ struct Encoder {
     if (gzb_copy_from_jpeg(ctx, ones) != GZB_OK) return false;
     if (gzb_apply_global_quantization(ctx, &q[0][0]) != GZB_OK) return false;
     memcpy(quant, q, sizeof(quant));
-    parallel_rows(nb, nthreads, [&](int b0, int b1) {
+    parallel_rows(nb, pool.get(), [&](int b0, int b1) {
       for (int c = 0; c < 3; ++c) {
         const int16_t* o = orig[c].data();
         int16_t* cu = cur[c].data();
@@ -394,8 +393,8 @@ int gzb_rgb_to_jpeg_coeffs(const uint8_t* rgb, int width, int height, int16_t* c
     return GZB_ERR_BAD_ARG;
   int16_t* out[3] = {c0, c1, c2};
   const int bw = (width + 7) / 8, bh = (height + 7) / 8;
-  const int nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-  parallel_rows(bh, nt, [&](int y0, int y1) { rgb_to_coeffs_rows(rgb, width, height, bw, y0, y1, out); });
+  gzb::WorkerPool pool(static_cast<int>(std::max(1u, std::min(16u, std::thread::hardware_concurrency()))));
+  parallel_rows(bh, &pool, [&](int y0, int y1) { rgb_to_coeffs_rows(rgb, width, height, bw, y0, y1, out); });
   return GZB_OK;
 }
 
@@ -423,7 +422,8 @@ long gzb_write_jpeg(const int16_t* c0, const int16_t* c1, const int16_t* c2, int
   for (int c = 0; c < 3; ++c) f.coeffs[c] = idx[c].data();
   if (input_tables) gzb::jpeg::frame_set_quant_input(&f, q); else gzb::jpeg::frame_set_quant(&f, q);
   std::string s;
-  gzb::jpeg::write_jpeg(f, &s, host_threads > 0 ? host_threads : 1);
+  gzb::WorkerPool pool(host_threads > 0 ? host_threads : 1);
+  gzb::jpeg::write_jpeg(f, &s, &pool);
   if (out && static_cast<long>(s.size()) <= cap) memcpy(out, s.data(), s.size());
   return static_cast<long>(s.size());
 }
@@ -466,10 +466,13 @@ int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float 
   e.want_trace = trace_out != nullptr;
   const unsigned hc = std::thread::hardware_concurrency();
   e.nthreads = host_threads > 0 ? host_threads : static_cast<int>(std::max(1u, std::min(16u, hc)));
+  e.pool.reset(new gzb::WorkerPool(e.nthreads));
   const size_t ncoef = static_cast<size_t>(e.nb) * 64;
   for (int c = 0; c < 3; ++c) { e.orig[c].resize(ncoef); e.cur[c].resize(ncoef); e.idx[c].resize(ncoef); }
+  const double t_create = now_ms();
   int rc = gzb_create(device, width, height, rgb, butteraugli_target, &e.ctx);
   if (rc != GZB_OK) { g_encode_err = gzb_last_error(nullptr); return rc; }
+  e.st.create_ms = now_ms() - t_create;
   auto fail = [&](int code) {
     g_encode_err = gzb_last_error(e.ctx);
     gzb_destroy(e.ctx);
@@ -479,7 +482,7 @@ int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float 
   {
     const double t0 = now_ms();
     int16_t* out[3] = {e.orig[0].data(), e.orig[1].data(), e.orig[2].data()};
-    parallel_rows(e.bh, e.nthreads, [&](int y0, int y1) { rgb_to_coeffs_rows(rgb, width, height, e.bw, y0, y1, out); });
+    parallel_rows(e.bh, e.pool.get(), [&](int y0, int y1) { rgb_to_coeffs_rows(rgb, width, height, e.bw, y0, y1, out); });
     e.st.host_frontend_ms = now_ms() - t0;
   }
   if (gzb_set_jpeg_coeffs(e.ctx, e.orig[0].data(), e.orig[1].data(), e.orig[2].data()) != GZB_OK) return fail(GZB_ERR_CUDA);
@@ -493,7 +496,7 @@ int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float 
     for (int c = 0; c < 3; ++c) f.coeffs[c] = e.orig[c].data();
     gzb::jpeg::frame_set_quant_input(&f, ones);
     const double t0 = now_ms();
-    gzb::jpeg::write_jpeg(f, &encoded, e.nthreads);
+    gzb::jpeg::write_jpeg(f, &encoded, e.pool.get(), nullptr, nullptr, &e.wt);
     e.st.host_write_ms += now_ms() - t0;
     e.st.num_jpeg_writes++;
   }
@@ -571,7 +574,7 @@ int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float 
   {
     const double t_be = now_ms();
     const int ncomp = 3;
-    Histogram ac_hist[3];
+    Histogram ac_hist[3], dc_hist[3];
     int header_size, dc_size;
     {
       Frame f;
@@ -579,8 +582,14 @@ int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float 
       for (int c = 0; c < 3; ++c) f.coeffs[c] = e.idx[c].data();
       gzb::jpeg::frame_set_quant(&f, e.quant);
       header_size = static_cast<int>(gzb::jpeg::header_size(f));
-      dc_size = static_cast<int>(gzb::jpeg::estimate_dc_size(f));
-      gzb::jpeg::build_ac_histograms(f, ac_hist);
+      gzb::jpeg::build_histograms(f, dc_hist, ac_hist, e.pool.get());
+      {  // EstimateDCSize (processor.cc:548-555)
+        Histogram tmp[3] = {dc_hist[0], dc_hist[1], dc_hist[2]};
+        size_t num = f.ncomp;
+        int ix[4];
+        uint8_t dd[3 * Histogram::kSize];
+        dc_size = static_cast<int>(gzb::jpeg::cluster_histograms(tmp, &num, ix, dd));
+      }
     }
     std::vector<uint8_t> ac_depths(3 * Histogram::kSize);
     // ComputeEntropyCodes (processor.cc:517-536)
@@ -629,11 +638,13 @@ int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float 
     for (int direction : directions) {
       for (;;) {
         int blocks_to_change = 0;
+        double tt = now_ms();
         for (int rblock = 1; rblock <= 4; ++rblock) {
           // distmap is all zeros until the first iteration has compared (processor.cc:777-780)
           if (first_up_iter && gzb_clear_distmap(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
           if (gzb_compute_block_error_adjustment_weights(e.ctx, direction, rblock, target_mul, nullptr,
                                                          block_weight.data()) != GZB_OK) return fail(GZB_ERR_CUDA);
+          { const double t1 = now_ms(); e.st.be_weights_ms += t1 - tt; tt = t1; }
           global_order.clear();
           blocks_to_change = 0;
           for (int b = 0; b < num_blocks; ++b) {
@@ -653,6 +664,7 @@ int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float 
               blocks_to_change += last_index > 0 ? 1 : 0;
             }
           }
+          { const double t1 = now_ms(); e.st.be_order_ms += t1 - tt; tt = t1; }
           if (!global_order.empty()) break;
         }
         if (global_order.empty()) break;
@@ -732,15 +744,16 @@ int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float 
           }
         }
         for (int i = 0; i < num_blocks; ++i) max_block_error[i] += block_weight[i] * val_threshold * direction;
+        { const double t1 = now_ms(); e.st.be_walk_ms += t1 - tt; tt = t1; }
         ++e.st.num_iterations;
         if (direction > 0) ++e.st.num_iterations_up; else ++e.st.num_iterations_down;
         // push the changed coefficients to the device, write the file while the GPU compares
         if (gzb_update_coeffs(e.ctx, upd_block.data(), upd_idx.data(), upd_val.data(), upd_block.size()) != GZB_OK)
           return fail(GZB_ERR_CUDA);
+        { const double t1 = now_ms(); e.st.be_update_ms += t1 - tt; tt = t1; }
         std::string jpg;
-        std::future<void> writer = std::async(std::launch::async, [&]() { e.write_candidate(&jpg); });
         const bool ok = e.compare(true);
-        writer.get();
+        e.write_candidate(&jpg, dc_hist, ac_hist);
         if (!ok) return fail(GZB_ERR_CUDA);
         e.log("Iter %2d: f111111(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
               e.st.num_iterations, comp_mask, direction > 0 ? "up" : "down", changed_coeffs, order_size,
@@ -755,6 +768,8 @@ int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float 
   }
 
   e.st.launches = gzb_launch_count(e.ctx);
+  e.st.write_hist_ms = e.wt.hist_ms; e.st.write_code_ms = e.wt.code_ms;
+  e.st.write_encode_ms = e.wt.encode_ms; e.st.write_stitch_ms = e.wt.stitch_ms;
   gzb_destroy(e.ctx);
   *jpeg_size = e.best_jpeg.size();
   *jpeg_out = static_cast<uint8_t*>(malloc(std::max<size_t>(1, e.best_jpeg.size())));

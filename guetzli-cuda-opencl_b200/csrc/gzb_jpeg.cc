@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cassert>
+#include <chrono>
 #include <cstdlib>
 #include <thread>
 
@@ -302,7 +303,45 @@ inline void emit_stuffed(std::string* out, uint8_t b) {
 
 }  // namespace
 
-void write_jpeg(const Frame& f, std::string* out, int nthreads) {
+static double now_ms_() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+void build_histograms(const Frame& f, Histogram* dc, Histogram* ac, WorkerPool* pool) {
+  const int T = pool ? std::max(1, std::min(pool->size(), f.bh)) : 1;
+  if (T == 1) {
+    for (int c = 0; c < f.ncomp; ++c) { dc[c] = Histogram(); ac[c] = Histogram(); }
+    build_dc_histograms(f, dc);
+    build_ac_histograms(f, ac);
+    return;
+  }
+  std::vector<Histogram> part(static_cast<size_t>(T) * 6);
+  pool->run(T, [&](int t) {
+    const int y0 = static_cast<int>(static_cast<int64_t>(f.bh) * t / T);
+    const int y1 = static_cast<int>(static_cast<int64_t>(f.bh) * (t + 1) / T);
+    for (int c = 0; c < f.ncomp; ++c) {
+      Histogram& hd = part[t * 6 + c];
+      Histogram& ha = part[t * 6 + 3 + c];
+      const int16_t* p = f.coeffs[c];
+      const size_t b0 = static_cast<size_t>(y0) * f.bw, b1 = static_cast<size_t>(y1) * f.bw;
+      int last = b0 > 0 ? p[(b0 - 1) * 64] : 0;
+      for (size_t b = b0; b < b1; ++b) {
+        const int v = p[b * 64];
+        hd.add(bit_length(static_cast<uint32_t>(std::abs(v - last))));
+        last = v;
+        ac_histogram_add_block(p + b * 64, 1, &ha);
+      }
+    }
+  });
+  for (int c = 0; c < f.ncomp; ++c) {
+    dc[c] = Histogram(); ac[c] = Histogram();
+    for (int t = 0; t < T; ++t) { dc[c].merge(part[t * 6 + c]); ac[c].merge(part[t * 6 + 3 + c]); }
+  }
+}
+
+void write_jpeg(const Frame& f, std::string* out, WorkerPool* pool, const Histogram* dc_hist,
+                const Histogram* ac_hist, WriteTimers* tm) {
+  double t0 = now_ms_();
   out->clear();
   const int ncomp = f.ncomp;
   // SOI + APP0 (stripped metadata always writes the fixed JFIF header)
@@ -338,14 +377,15 @@ void write_jpeg(const Frame& f, std::string* out, int nthreads) {
     }
   }
   // Huffman codes: DC histograms clustered, then AC histograms clustered.
-  Histogram histo[6];
+  Histogram histo[6], hdc[3], hac[3];
   uint8_t depths[6 * Histogram::kSize];
-  build_dc_histograms(f, histo);
+  if (!dc_hist || !ac_hist) build_histograms(f, hdc, hac, pool);
+  for (int c = 0; c < ncomp; ++c) histo[c] = dc_hist ? dc_hist[c] : hdc[c];
+  if (tm) { const double t1 = now_ms_(); tm->hist_ms += t1 - t0; t0 = t1; }
   size_t num_dc = ncomp;
   int dc_idx[4], ac_idx[4];
   cluster_histograms(histo, &num_dc, dc_idx, depths);
-  for (int c = 0; c < ncomp; ++c) histo[num_dc + c] = Histogram();
-  build_ac_histograms(f, histo + num_dc);
+  for (int c = 0; c < ncomp; ++c) histo[num_dc + c] = ac_hist ? ac_hist[c] : hac[c];
   size_t num_ac = ncomp;
   cluster_histograms(histo + num_dc, &num_ac, ac_idx, depths + num_dc * Histogram::kSize);
   const int num_histo = static_cast<int>(num_dc + num_ac);
@@ -369,7 +409,7 @@ void write_jpeg(const Frame& f, std::string* out, int nthreads) {
     while (max_len > 0 && counts[max_len] == 0) --max_len;
     --counts[max_len];
     int total = 0;
-    for (int l = 0; l <= max_len; ++l) total += l ? counts[l] : 0;
+    for (int l = 1; l <= max_len; ++l) total += counts[l];
     out->push_back(static_cast<char>(is_dc ? i : idx + 0x10));
     for (int l = 1; l <= 16; ++l) out->push_back(static_cast<char>(counts[l]));
     for (int j = 0; j < total; ++j) out->push_back(static_cast<char>(values[j]));
@@ -385,52 +425,164 @@ void write_jpeg(const Frame& f, std::string* out, int nthreads) {
     }
     out->push_back(0); out->push_back(63); out->push_back(0);
   }
-  // Entropy-coded segment: bands of block rows in parallel, stitched at bit granularity.
-  int nb = std::max(1, std::min(nthreads, f.bh));
-  std::vector<BitBuf> bands(nb);
-  if (nb == 1) {
+  if (tm) { const double t1 = now_ms_(); tm->code_ms += t1 - t0; t0 = t1; }
+  // Entropy-coded segment: bands of block rows coded in parallel.
+  const int T = pool ? std::max(1, std::min(pool->size(), f.bh)) : 1;
+  std::vector<BitBuf> bands(T);
+  auto band_rows = [&](int t, int* y0, int* y1) {
+    *y0 = static_cast<int>(static_cast<int64_t>(f.bh) * t / T);
+    *y1 = static_cast<int>(static_cast<int64_t>(f.bh) * (t + 1) / T);
+  };
+  if (T == 1) {
     encode_band(f, dc_tab, ac_tab, 0, f.bh, &bands[0]);
   } else {
-    std::vector<std::thread> th;
-    for (int t = 0; t < nb; ++t) {
-      const int y0 = static_cast<int>(static_cast<int64_t>(f.bh) * t / nb);
-      const int y1 = static_cast<int>(static_cast<int64_t>(f.bh) * (t + 1) / nb);
-      th.emplace_back(encode_band, std::cref(f), dc_tab, ac_tab, y0, y1, &bands[t]);
-    }
-    for (auto& t : th) t.join();
+    pool->run(T, [&](int t) {
+      int y0, y1;
+      band_rows(t, &y0, &y1);
+      encode_band(f, dc_tab, ac_tab, y0, y1, &bands[t]);
+    });
   }
-  size_t est = 0;
-  for (auto& b : bands) est += b.bytes.size() + 8;
-  out->reserve(out->size() + est + est / 64 + 16);
-  uint32_t acc = 0;  // pending bits (< 8) carried between bands
-  int nacc = 0;
-  for (auto& b : bands) {
-    if (nacc == 0) {
-      for (uint8_t v : b.bytes) emit_stuffed(out, v);
-    } else {
-      for (uint8_t v : b.bytes) {
-        acc = (acc << 8) | v;
-        emit_stuffed(out, static_cast<uint8_t>(acc >> nacc));
-        acc &= (1u << nacc) - 1;
+  if (tm) { const double t1 = now_ms_(); tm->encode_ms += t1 - t0; t0 = t1; }
+  bool parallel_stitch = T > 1;
+  for (auto& b : bands) if (b.total_bits < 64) parallel_stitch = false;
+  if (!parallel_stitch) {
+    size_t est = 0;
+    for (auto& b : bands) est += b.bytes.size() + 8;
+    out->reserve(out->size() + est + est / 64 + 16);
+    uint32_t acc = 0;  // pending bits (< 8) carried between bands
+    int nacc = 0;
+    for (auto& b : bands) {
+      if (nacc == 0) {
+        for (uint8_t v : b.bytes) emit_stuffed(out, v);
+      } else {
+        for (uint8_t v : b.bytes) {
+          acc = (acc << 8) | v;
+          emit_stuffed(out, static_cast<uint8_t>(acc >> nacc));
+          acc &= (1u << nacc) - 1;
+        }
+      }
+      if (b.nacc > 0) {  // band tail: b.nacc (< 8) leftover bits
+        acc = (acc << b.nacc) | static_cast<uint32_t>(b.acc & ((1u << b.nacc) - 1));
+        nacc += b.nacc;
+        if (nacc >= 8) {
+          nacc -= 8;
+          emit_stuffed(out, static_cast<uint8_t>(acc >> nacc));
+          acc &= (1u << nacc) - 1;
+        }
       }
     }
-    if (b.nacc > 0) {  // band tail: b.nacc (< 8) leftover bits
-      acc = (acc << b.nacc) | static_cast<uint32_t>(b.acc & ((1u << b.nacc) - 1));
-      nacc += b.nacc;
-      if (nacc >= 8) {
-        nacc -= 8;
-        emit_stuffed(out, static_cast<uint8_t>(acc >> nacc));
-        acc &= (1u << nacc) - 1;
-      }
+    if (nacc > 0) {  // pad the last byte with ones (JumpToByteBoundary)
+      const uint32_t pad = (1u << (8 - nacc)) - 1;
+      emit_stuffed(out, static_cast<uint8_t>((acc << (8 - nacc)) | pad));
     }
-  }
-  if (nacc > 0) {  // pad the last byte with ones (JumpToByteBoundary)
-    const uint32_t pad = (1u << (8 - nacc)) - 1;
-    emit_stuffed(out, static_cast<uint8_t>((acc << (8 - nacc)) | pad));
+  } else {
+    // Parallel stitch. Band t contributes merged bits [off[t], off[t+1]); it owns the merged bytes
+    // whose first bit falls in that range and borrows up to 7 head bits of the next band (ones
+    // after the last band) for its final byte.
+    std::vector<uint64_t> off(T + 1, 0);
+    for (int t = 0; t < T; ++t) off[t + 1] = off[t] + bands[t].total_bits;
+    std::vector<uint16_t> head16(T + 1, 0xffff);
+    for (int t = 0; t < T; ++t) head16[t] = static_cast<uint16_t>((bands[t].bytes[0] << 8) | bands[t].bytes[1]);
+    std::vector<std::vector<uint8_t>> stuffed(T);
+    pool->run(T, [&](int t) {
+      BitBuf& b = bands[t];
+      const size_t B = b.bytes.size();
+      const uint32_t tailbits = b.nacc ? static_cast<uint32_t>(b.acc & ((1u << b.nacc) - 1)) : 0;
+      const uint32_t V = ((tailbits << (16 - b.nacc)) | (static_cast<uint32_t>(head16[t + 1]) >> b.nacc)) & 0xffff;
+      b.bytes.push_back(static_cast<uint8_t>(V >> 8));
+      b.bytes.push_back(static_cast<uint8_t>(V & 0xff));
+      const uint64_t j0 = (off[t] + 7) / 8, j1 = (off[t + 1] + 7) / 8;
+      const int s0 = static_cast<int>(8 * j0 - off[t]);
+      const size_t count = static_cast<size_t>(j1 - j0);
+      (void)B;
+      std::vector<uint8_t>& o = stuffed[t];
+      o.reserve(count + count / 32 + 16);
+      const uint8_t* L = b.bytes.data();
+      if (s0 == 0) {
+        for (size_t m = 0; m < count; ++m) { const uint8_t v = L[m]; o.push_back(v); if (v == 0xff) o.push_back(0); }
+      } else {
+        for (size_t m = 0; m < count; ++m) {
+          const uint8_t v = static_cast<uint8_t>(((L[m] << 8) | L[m + 1]) >> (8 - s0));
+          o.push_back(v);
+          if (v == 0xff) o.push_back(0);
+        }
+      }
+    });
+    std::vector<size_t> pos(T + 1, out->size());
+    for (int t = 0; t < T; ++t) pos[t + 1] = pos[t] + stuffed[t].size();
+    out->resize(pos[T]);
+    char* base = &(*out)[0];
+    pool->run(T, [&](int t) { if (!stuffed[t].empty()) memcpy(base + pos[t], stuffed[t].data(), stuffed[t].size()); });
   }
   out->push_back(static_cast<char>(0xff));
   out->push_back(static_cast<char>(0xd9));
+  if (tm) { const double t1 = now_ms_(); tm->stitch_ms += t1 - t0; }
 }
 
 }  // namespace jpeg
+
+// ---------------------------------------------------------------------------------------------
+// WorkerPool
+// ---------------------------------------------------------------------------------------------
+WorkerPool::WorkerPool(int nthreads) : nthreads_(std::max(1, nthreads)) {
+  for (int i = 1; i < nthreads_; ++i) threads_.emplace_back(&WorkerPool::worker, this);
+}
+WorkerPool::~WorkerPool() {
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    stop_ = true;
+  }
+  cv_start_.notify_all();
+  for (auto& t : threads_) t.join();
+}
+void WorkerPool::worker() {
+  unsigned long long seen = 0;
+  for (;;) {
+    const std::function<void(int)>* fn;
+    {
+      std::unique_lock<std::mutex> l(mu_);
+      cv_start_.wait(l, [&] { return stop_ || epoch_ != seen; });
+      if (stop_) return;
+      seen = epoch_;
+      fn = fn_;
+    }
+    for (;;) {
+      int i;
+      {
+        std::lock_guard<std::mutex> l(mu_);
+        if (epoch_ != seen || next_ >= n_) break;
+        i = next_++;
+      }
+      (*fn)(i);
+      {
+        std::lock_guard<std::mutex> l(mu_);
+        if (--pending_ == 0) cv_done_.notify_all();
+      }
+    }
+  }
+}
+void WorkerPool::run(int n, const std::function<void(int)>& fn) {
+  if (n <= 0) return;
+  if (nthreads_ == 1 || n == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    fn_ = &fn; n_ = n; next_ = 0; pending_ = n; ++epoch_;
+  }
+  cv_start_.notify_all();
+  for (;;) {  // the caller works too
+    int i;
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      if (next_ >= n_) break;
+      i = next_++;
+    }
+    fn(i);
+    std::lock_guard<std::mutex> l(mu_);
+    if (--pending_ == 0) cv_done_.notify_all();
+  }
+  std::unique_lock<std::mutex> l(mu_);
+  cv_done_.wait(l, [&] { return pending_ == 0; });
+  n_ = 0;
+}
+
 }  // namespace gzb

@@ -7,13 +7,39 @@
 //   ClusterHistograms 295-342, EncodeScan 506-536), guetzli/entropy_encode.cc (CreateHuffmanTree
 //   68-143), guetzli/jpeg_bit_writer.h.
 #pragma once
+#include <condition_variable>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace gzb {
+
+// Minimal persistent worker pool: run(n, fn) calls fn(i) for i in [0, n) on the workers plus the
+// calling thread and returns when all are done. One pool per encoder (not shared across threads).
+class WorkerPool {
+ public:
+  explicit WorkerPool(int nthreads);
+  ~WorkerPool();
+  int size() const { return nthreads_; }
+  void run(int n, const std::function<void(int)>& fn);
+
+ private:
+  void worker();
+  int nthreads_;
+  std::vector<std::thread> threads_;
+  std::mutex mu_;
+  std::condition_variable cv_start_, cv_done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int n_ = 0, next_ = 0, pending_ = 0;
+  unsigned long long epoch_ = 0;
+  bool stop_ = false;
+};
+
 namespace jpeg {
 
 extern const int kNaturalOrder[64];  // zig-zag position -> natural index
@@ -70,9 +96,18 @@ size_t header_size(const Frame& f);             // JpegHeaderSize with stripped 
 size_t estimate_dc_size(const Frame& f);        // EstimateDCSize (processor.cc:548-555)
 void build_ac_histograms(const Frame& f, Histogram* h /*[ncomp]*/);
 
-// WriteJpeg(jpg, strip_metadata=true, out). nthreads > 1 encodes block-row bands in parallel and
-// stitches the bit streams; the bytes are identical to the sequential writer.
-void write_jpeg(const Frame& f, std::string* out, int nthreads = 1);
+// Per-component DC / AC histograms of a frame (unclustered), band-parallel.
+void build_histograms(const Frame& f, Histogram* dc /*[ncomp]*/, Histogram* ac /*[ncomp]*/, WorkerPool* pool);
+
+struct WriteTimers { double hist_ms = 0, code_ms = 0, encode_ms = 0, stitch_ms = 0; };
+
+// WriteJpeg(jpg, strip_metadata=true, out). With a pool, block-row bands are Huffman-coded in
+// parallel and stitched at bit granularity (also in parallel); the bytes are identical to the
+// sequential writer. dc_hist / ac_hist, when given, are the frame's per-component histograms
+// (the back end maintains the AC ones incrementally) and save the two coefficient scans.
+void write_jpeg(const Frame& f, std::string* out, WorkerPool* pool = nullptr,
+                const Histogram* dc_hist = nullptr, const Histogram* ac_hist = nullptr,
+                WriteTimers* tm = nullptr);
 
 }  // namespace jpeg
 }  // namespace gzb

@@ -145,6 +145,8 @@ typedef struct {
   int num_compares, num_jpeg_writes, num_entropy_code_builds;
   double total_wall_ms, host_frontend_ms, host_quant_ms, host_write_ms;
   double compare_wall_ms, device_compare_ms, zeroing_wall_ms, device_zeroing_ms, backend_wall_ms;
+  double write_hist_ms, write_code_ms, write_encode_ms, write_stitch_ms;   /* parts of host_write_ms */
+  double be_weights_ms, be_order_ms, be_walk_ms, be_update_ms, create_ms;  /* parts of the back end */
   double final_score;
   float final_distance;
   unsigned long long launches;

@@ -1,0 +1,17 @@
+"""Ad-hoc e2e probe (not a test): python tests/perf_encode.py W H QUALITY [threads]"""
+import sys, time, os, json
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from _libs import synth_image
+import __graft_entry__ as ge
+gz = ge.load_package()
+w, h, q = int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3])
+nt = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+img = synth_image(w, h)
+t = np.float32(gz.ButteraugliScoreForQuality(q))
+for rep in range(2):
+    t0 = time.time(); jpg, st, _ = gz.Process(img, t, host_threads=nt); dt = time.time() - t0
+    print("encode %dx%d q%g: %.3f s -> %.3f MPix/s, %d bytes, iters %d" % (w, h, q, dt, w * h / 1e6 / dt, len(jpg), st["num_iterations"]))
+    print(json.dumps({k: (round(v, 2) if isinstance(v, float) else v) for k, v in st.items()}))
+os.system("nproc; grep -m1 'model name' /proc/cpuinfo")
