@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 Guetzli hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size WxH] [--quality Q]
+
+A "step" is one full guetzli::Process of one synthetic image per GPU (RGB -> q=1 coefficients ->
+SelectQuantMatrix -> block-zeroing search -> back-end iterations -> best JPEG). Defaults: N=1,
+1024x1024 at quality 90 (BASELINE.json configs[1]). With N>1 (launched by torchrun, one rank per
+GPU) every rank encodes its own image of the batch: weak scaling, no data-path collective.
+
+  value  : MPix/s of gzb_encoder_run with the image, its XYB and its q=1 coefficients already
+           resident in HBM (gzb_encoder_create is outside the timed region)
+  e2e    : MPix/s of gzb_encode_rgb from a host RGB buffer to host JPEG bytes (context creation,
+           H2D of the image, every per-iteration copy and the D2H results inside the timed region)
+  roofline : dominant kernel (k_zeroing_order), algorithmic bytes U2 = 3084 B per 8x8 block
+            / its CUDA-event duration on the launching stream, vs MEASURED_PEAKS.json
+  cpu_baseline : the unmodified reference (oracle/_ref) on one host core on a bounded sample
+
+--impl reference runs the reference's own CPU encoder on all host cores (one image per core, the
+reference's own batching method, tests/golden_test.sh:25) and prints the same JSON shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ALGO_BYTES_PER_BLOCK = 3084      # U2: 2x384 coeffs + 768 original XYB + 12 mask scale + 1536 out
+ALGO_BYTES_COMPARE_PER_PX = 22   # U1: 6 coeffs + 12 cached XYB + 4 diffmap
+FALLBACK_HBM_GBS = 6650.0
+
+
+def peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference CPU encoder on all host cores
+# ------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    w, h, seed, target = args
+    import _libs
+    img = _libs.synth_image(w, h, seed)
+    t0 = time.perf_counter()
+    jpg, iters, _ = _libs.ref_process(img, target)
+    return time.perf_counter() - t0, len(jpg), iters
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import _libs
+    if not _libs.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgzref.so not built"}))
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample of the workload: one 256x256 crop-sized synthetic image per core per step
+    sw, sh = 256, 256
+    target = float(np.float32(_libs.ref().ref_butteraugli_score_for_quality(float(a.quality))))
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for step in range(a.warmup + a.steps):
+            jobs = [(sw, sh, 1234 + 10 * (step * cores + k), target) for k in range(cores)]
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, jobs)
+            dt = time.perf_counter() - t0
+            if step >= a.warmup:
+                times.append(dt)
+    mpix_step = cores * sw * sh / 1e6
+    total = sum(times)
+    value = mpix_step * len(times) / total
+    line = {
+        "impl": "reference", "metric": "end-to-end encode MPix/s", "value": value, "unit": "MPix/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "reference CPU guetzli::Process, quality %g, %d images of %dx%d per step (one per host core)"
+                               % (a.quality, cores, sw, sh)},
+        "cpu_baseline": {"value": value, "unit": "MPix/s", "cores": cores, "kind": "reference",
+                         "sample": "%d synthetic %dx%d images per step, one per core, quality %g" % (cores, sw, sh, a.quality)},
+        "e2e": {"value": value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline_single_core(quality):
+    """The unmodified reference on ONE core on a bounded sample (384x384, same generator)."""
+    import _libs
+    if not _libs.have_ref():
+        return None
+    sw, sh = 384, 384
+    img = _libs.synth_image(sw, sh, 1234)
+    target = float(np.float32(_libs.ref().ref_butteraugli_score_for_quality(float(quality))))
+    t0 = time.perf_counter()
+    jpg, iters, _ = _libs.ref_process(img, target)
+    dt = time.perf_counter() - t0
+    return {"value": sw * sh / 1e6 / dt, "unit": "MPix/s", "cores": 1, "kind": "reference",
+            "sample": "one synthetic %dx%d image, quality %g, guetzli::Process single-threaded: %.1f s, %d iterations"
+                      % (sw, sh, quality, dt, iters)}
+
+
+def run_ours(a, rank, world, local):
+    import torch
+    import __graft_entry__ as ge
+    import _libs
+    gz = ge.load_package()
+    if not torch.cuda.is_available() or gz.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w, h = a.size
+    target = np.float32(gz.ButteraugliScoreForQuality(a.quality))
+    host_threads = max(1, (os.cpu_count() or 1) // max(1, world))
+    host_threads = min(16, host_threads)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_image(step):
+        return _libs.synth_image(w, h, 1234 + 10 * (step * world + rank))
+
+    images = [one_image(s) for s in range(a.warmup + a.steps)]
+    sampler = ClockSampler(local)
+    run_ms, e2e_ms, launches, h2d, d2h = [], [], 0, 0, 0
+    kt = {}
+    n_cmp = 0
+    for step in range(a.warmup + a.steps):
+        timed = step >= a.warmup
+        if timed and step == a.warmup:
+            sampler.start()
+        img = images[step]
+        # ---- device-resident arm: create outside, run inside the timed region
+        enc = gz.Encoder(img, target, device=local, host_threads=host_threads, profile=timed)
+        flush.fill_(step & 0xff)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        jpg, st, _ = enc.run()
+        e1.record()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        if timed:
+            run_ms.append(max(dt, e0.elapsed_time(e1)))
+            launches += st["launches"]
+            n_cmp += st["num_compares"]
+            for k, (ms, n) in enc.kernel_times().items():
+                a_ms, a_n = kt.get(k, (0.0, 0))
+                kt[k] = (a_ms + ms, a_n + n)
+        enc.close()
+        # ---- end-to-end arm: host RGB buffer -> host JPEG bytes
+        flush.fill_((step + 1) & 0xff)
+        barrier()
+        t0 = time.perf_counter()
+        jpg2, st2, _ = gz.Process(img, target, device=local, host_threads=host_threads)
+        dt2 = (time.perf_counter() - t0) * 1e3
+        assert jpg2 == jpg
+        if timed:
+            e2e_ms.append(dt2)
+            h2d += st2["h2d_bytes"]; d2h += st2["d2h_bytes"] + len(jpg2) * 0
+    clocks = sampler.stop()
+
+    def reduce_max(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    total_run = reduce_max(sum(run_ms))
+    total_e2e = reduce_max(sum(e2e_ms))
+    launches_all = int(reduce_sum(launches))
+    mpix = w * h / 1e6
+    value = world * mpix * a.steps / (total_run / 1e3)
+    e2e_value = world * mpix * a.steps / (total_e2e / 1e3)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    nblocks = ((w + 7) // 8) * ((h + 7) // 8)
+    z_ms, z_n = kt.get("k_zeroing_order", (0.0, 0))
+    gpu_ms_total = sum(v[0] for v in kt.values())
+    roof = None
+    if z_n:
+        achieved = ALGO_BYTES_PER_BLOCK * nblocks / (z_ms / z_n / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_zeroing_order", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": z_ms / z_n, "share_of_gpu_time": z_ms / gpu_ms_total if gpu_ms_total else None,
+                "note": "FP64-compute/latency-bound search kernel (SURVEY 8d): HBM fraction is not its limiter"}
+    cmp_ms = sum(ms for k, (ms, n) in kt.items() if k not in ("k_zeroing_order", "k_block_mask_scale", "k_block_weights", "misc", "k_coeffs_to_rgb8"))
+    kernels = {k: {"ms_per_step": ms / a.steps, "launches_per_step": n / a.steps} for k, (ms, n) in sorted(kt.items(), key=lambda kv: -kv[1][0])}
+    line = {
+        "metric": "end-to-end encode MPix/s", "value": value, "unit": "MPix/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": total_run / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic %dx%d sRGB (SURVEY 8d generator, seed 1234+10k), quality %g, one image per GPU per step, "
+                               "guetzli::Process" % (w, h, a.quality),
+                   "l2": "256 MiB buffer written between timed steps (L2 flush)", "host_threads_per_gpu": host_threads,
+                   "compares_per_step": n_cmp / a.steps},
+        "e2e": {"value": e2e_value, "unit": "MPix/s", "ms_per_step": total_e2e / a.steps,
+                "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps},
+        "gpu_launches": launches_all,
+        "clocks": clocks,
+        "roofline": roof,
+        "butteraugli": {"compare_device_ms_per_call": cmp_ms / max(1, n_cmp), "mpix_per_s": mpix / (cmp_ms / max(1, n_cmp) / 1e3) if cmp_ms else None,
+                        "hbm_frac_U1": (ALGO_BYTES_COMPARE_PER_PX * w * h / (cmp_ms / max(1, n_cmp) / 1e3) / 1e9 / peak) if cmp_ms else None},
+        "kernels": kernels,
+        "cpu_baseline": cpu_baseline_single_core(a.quality) if world == 1 and not a.no_cpu_baseline else None,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", default="1024x1024", type=lambda s: tuple(int(v) for v in s.lower().split("x")))
+    ap.add_argument("--quality", type=float, default=90.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank, world, local = dist_env()
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+    else:
+        run_ours(a, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

@@ -224,6 +224,12 @@ class ButteraugliComparator:
     def last_device_ms(self):
         return float(lib().gzb_last_device_ms(self._ctx))
 
+    def profile(self, on=True):
+        profile_enable(self._ctx, on)
+
+    def kernel_times(self):
+        return profile_get(self._ctx)
+
     def launch_count(self):
         return int(lib().gzb_launch_count(self._ctx))
 
@@ -276,6 +282,7 @@ class EncodeStats(C.Structure):
                 ("write_hist_ms", C.c_double), ("write_code_ms", C.c_double), ("write_encode_ms", C.c_double),
                 ("write_stitch_ms", C.c_double), ("be_weights_ms", C.c_double), ("be_order_ms", C.c_double),
                 ("be_walk_ms", C.c_double), ("be_update_ms", C.c_double), ("create_ms", C.c_double),
+                ("prepare_ms", C.c_double), ("run_ms", C.c_double), ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong),
                 ("final_score", C.c_double), ("final_distance", C.c_float), ("launches", C.c_ulonglong)]
 
     def as_dict(self):
@@ -343,3 +350,80 @@ def WriteJpeg(coeffs, width, height, q, input_tables=False, host_threads=1):
     if n < 0:
         raise GzbError("gzb_write_jpeg failed (%d)" % n)
     return buf[:n].tobytes()
+
+
+class Encoder:
+    """Two-step encoder (gzb_encoder_create / gzb_encoder_run): create() leaves the image, its
+    opsin-dynamics image and the q=1 coefficients resident in HBM; run() performs the search."""
+
+    def __init__(self, rgb, butteraugli_target, device=0, host_threads=0, profile=False):
+        L = lib()
+        a = np.ascontiguousarray(rgb, np.uint8)
+        self.h, self.w = a.shape[:2]
+        L.gzb_encoder_create.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int,
+                                         C.POINTER(C.c_void_p)]
+        L.gzb_encoder_run.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                      C.POINTER(EncodeStats), C.POINTER(C.c_void_p)]
+        L.gzb_encoder_context.restype = C.c_void_p
+        L.gzb_encoder_context.argtypes = [C.c_void_p]
+        L.gzb_encoder_destroy.argtypes = [C.c_void_p]
+        L.gzb_encoder_destroy.restype = None
+        L.gzb_encode_last_error.restype = C.c_char_p
+        L.gzb_free.argtypes = [C.c_void_p]
+        L.gzb_free.restype = None
+        self._enc = C.c_void_p()
+        rc = L.gzb_encoder_create(device, _p(a), self.w, self.h, C.c_float(butteraugli_target), host_threads,
+                                  C.byref(self._enc))
+        if rc != 0:
+            raise GzbError("gzb_encoder_create failed (%d): %s" % (rc, L.gzb_encode_last_error().decode(errors="replace")))
+        self._ctx = C.c_void_p(L.gzb_encoder_context(self._enc))
+        if profile:
+            profile_enable(self._ctx, True)
+
+    def run(self, want_trace=False):
+        L = lib()
+        out = C.c_void_p(); n = C.c_size_t(); st = EncodeStats(); tr = C.c_void_p()
+        rc = L.gzb_encoder_run(self._enc, C.byref(out), C.byref(n), C.byref(st), C.byref(tr) if want_trace else None)
+        if rc != 0:
+            raise GzbError("gzb_encoder_run failed (%d): %s" % (rc, L.gzb_encode_last_error().decode(errors="replace")))
+        data = C.string_at(out, n.value)
+        L.gzb_free(out)
+        trace = None
+        if want_trace and tr:
+            trace = C.string_at(tr).decode(errors="replace")
+            L.gzb_free(tr)
+        return data, st.as_dict(), trace
+
+    def kernel_times(self):
+        return profile_get(self._ctx)
+
+    def close(self):
+        if self._enc:
+            lib().gzb_encoder_destroy(self._enc)
+            self._enc = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def profile_enable(ctx, on=True):
+    L = lib()
+    L.gzb_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    _check(L.gzb_profile_enable(ctx, 1 if on else 0), ctx)
+
+
+def profile_get(ctx):
+    """{kernel name: (accumulated device ms, launches)} from CUDA events on the context's stream."""
+    L = lib()
+    L.gzb_profile_name.restype = C.c_char_p
+    L.gzb_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
+    out = {}
+    for i in range(L.gzb_profile_count()):
+        ms = C.c_double(); n = C.c_ulonglong()
+        _check(L.gzb_profile_get(ctx, i, C.byref(ms), C.byref(n)), ctx)
+        if n.value:
+            out[L.gzb_profile_name(i).decode()] = (ms.value, n.value)
+    return out

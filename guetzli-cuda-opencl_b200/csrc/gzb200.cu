@@ -115,6 +115,8 @@ struct BlurPlan {
   BlurGeom g{};
   double* d_sx = nullptr;
   double* d_sy = nullptr;
+  bool own = false;            // tables allocated with their own cudaMalloc (stage entry points)
+  std::vector<double> hx, hy;  // host copies of the scale tables
   void build(const HostKernel& hk, int kind, int in_w, int in_h, int in_pitch, int x0, int sx, int nx,
              int y0, int sy, int ny, double border_ratio, int ups) {
     g.in_w = in_w; g.in_h = in_h; g.in_pitch = in_pitch; g.r = hk.r; g.kind = kind;
@@ -122,13 +124,10 @@ struct BlurPlan {
     g.tmp_pitch = round_up(std::max(nx, 1), 32); g.ups = ups;
     g.oxn = std::max(1, std::min(kBhOx, (kBhMaxSpan - 2 * hk.r - 1) / sx + 1));
     g.oyn = std::max(1, std::min(kBvOy, (kBvMaxRows - 2 * hk.r - 1) / sy + 1));
-    std::vector<double> vx(std::max(nx, 1)), vy(std::max(ny, 1));
-    for (int i = 0; i < nx; ++i) vx[i] = border_scale(hk, x0 + i * sx, in_w, border_ratio);
-    for (int i = 0; i < ny; ++i) vy[i] = border_scale(hk, y0 + i * sy, in_h, border_ratio);
-    CK(cudaMalloc(&d_sx, vx.size() * sizeof(double)));
-    CK(cudaMalloc(&d_sy, vy.size() * sizeof(double)));
-    CK(cudaMemcpy(d_sx, vx.data(), vx.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_sy, vy.data(), vy.size() * sizeof(double), cudaMemcpyHostToDevice));
+    hx.assign(std::max(nx, 1), 0.0);
+    hy.assign(std::max(ny, 1), 0.0);
+    for (int i = 0; i < nx; ++i) hx[i] = border_scale(hk, x0 + i * sx, in_w, border_ratio);
+    for (int i = 0; i < ny; ++i) hy[i] = border_scale(hk, y0 + i * sy, in_h, border_ratio);
   }
   // The plain decimated blur of the reference: lattice (0, step).
   void build_decimated(const HostKernel& hk, int kind, int in_w, int in_h, int in_pitch,
@@ -136,18 +135,93 @@ struct BlurPlan {
     build(hk, kind, in_w, in_h, in_pitch, 0, hk.step, (in_w + hk.step - 1) / hk.step, 0, hk.step,
           (in_h + hk.step - 1) / hk.step, border_ratio, ups);
   }
+  void upload(cudaStream_t st) {  // d_sx / d_sy already point into the context slab
+    CK(cudaMemcpyAsync(d_sx, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_sy, hy.data(), hy.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  void upload_own() {
+    own = true;
+    CK(cudaMalloc(&d_sx, hx.size() * sizeof(double)));
+    CK(cudaMalloc(&d_sy, hy.size() * sizeof(double)));
+    CK(cudaMemcpy(d_sx, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_sy, hy.data(), hy.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   void release() {
-    if (d_sx) cudaFree(d_sx);
-    if (d_sy) cudaFree(d_sy);
+    if (own) {
+      if (d_sx) cudaFree(d_sx);
+      if (d_sy) cudaFree(d_sy);
+    }
     d_sx = d_sy = nullptr;
   }
   size_t tmp_floats() const { return static_cast<size_t>(g.tmp_pitch) * g.in_h; }
   size_t out_floats() const { return static_cast<size_t>(g.tmp_pitch) * std::max(g.ny, 1); }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Device slabs: one cudaMalloc per context, sub-allocated; released slabs are cached per device so
+// that back-to-back encodes do not pay the driver's map/unmap cost (the reference's cumem_pool
+// plays this role, clguetzli/cumem_pool.cpp:28-112).
+// ---------------------------------------------------------------------------------------------
+struct Slab { void* base = nullptr; size_t cap = 0; void* pinned = nullptr; };
+static std::mutex g_slab_mu;
+static std::vector<Slab> g_slab_cache[64];
+
+static Slab slab_acquire(int device, size_t bytes) {
+  {
+    std::lock_guard<std::mutex> lock(g_slab_mu);
+    std::vector<Slab>& v = g_slab_cache[device & 63];
+    int best = -1;
+    for (size_t i = 0; i < v.size(); ++i)
+      if (v[i].cap >= bytes && (best < 0 || v[i].cap < v[best].cap)) best = static_cast<int>(i);
+    if (best >= 0 && v[best].cap <= bytes + bytes / 2 + (64u << 20)) {
+      Slab s = v[best];
+      v.erase(v.begin() + best);
+      return s;
+    }
+    for (Slab& s : v) { cudaFree(s.base); cudaFreeHost(s.pinned); }  // wrong sizes: drop them
+    v.clear();
+  }
+  Slab s;
+  s.cap = bytes;
+  CK(cudaMalloc(&s.base, bytes));
+  CK(cudaMallocHost(&s.pinned, 4096));
+  return s;
+}
+static void slab_release(int device, Slab s) {
+  if (!s.base) return;
+  std::lock_guard<std::mutex> lock(g_slab_mu);
+  std::vector<Slab>& v = g_slab_cache[device & 63];
+  if (v.size() >= 2) { cudaFree(s.base); cudaFreeHost(s.pinned); return; }
+  v.push_back(s);
+}
+
 }  // namespace gzb
 
 using namespace gzb;
+
+// ---------------------------------------------------------------------------------------------
+// Per-kernel event profiling (off by default)
+// ---------------------------------------------------------------------------------------------
+enum KClass { KC_IDCT = 0, KC_OPSIN, KC_MHIC, KC_BLUR_H, KC_BLUR_V, KC_EDGE_MAP, KC_BLOCK_DIFF, KC_LOWFREQ,
+              KC_MASK_FRONT, KC_COMBINE, KC_DIFFMAP_FINAL, KC_ZEROING, KC_BLOCK_MASK, KC_WEIGHTS, KC_MISC, KC_COUNT };
+static const char* const kClassNames[KC_COUNT] = {
+    "k_coeffs_to_rgb8", "k_opsin_dynamics", "k_mask_high_intensity_change", "k_blur_h", "k_blur_v",
+    "k_edge_detector_map", "k_block_diff_map", "k_edge_lowfreq", "k_mask_front", "k_combine",
+    "k_diffmap_final", "k_zeroing_order", "k_block_mask_scale", "k_block_weights", "misc"};
+struct Prof {
+  bool on = false;
+  struct Pend { int k; cudaEvent_t a, b; };
+  std::vector<cudaEvent_t> free_ev;
+  std::vector<Pend> pend;
+  double ms[KC_COUNT] = {0};
+  unsigned long long n[KC_COUNT] = {0};
+  cudaEvent_t get() {
+    if (!free_ev.empty()) { cudaEvent_t e = free_ev.back(); free_ev.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Context
@@ -161,7 +235,12 @@ struct gzb_ctx {
   float target = 0.f;
   float distance = 0.f;
   float last_ms = 0.f;
-  unsigned long long launches = 0;
+  unsigned long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+  Slab slab;
+  struct Req { void** pp; size_t bytes; };
+  std::vector<Req> reqs;
+  bool upd_own = false;
+  Prof prof;
   bool have_orig_coeffs = false, have_coeffs = false, block_cmp = false, have_distmap = false;
   int sm_count = 148;
   std::string err;
@@ -201,6 +280,27 @@ static std::string g_create_err;
 
 namespace {
 
+// Launch wrapper: counts the launch and, when profiling, brackets it with an event pair.
+#define KLAUNCH(c, kclass, ...)                                        \
+  do {                                                                 \
+    cudaEvent_t ea_ = nullptr;                                         \
+    if ((c)->prof.on) { ea_ = (c)->prof.get(); cudaEventRecord(ea_, (c)->stream); } \
+    __VA_ARGS__;                                                       \
+    if ((c)->prof.on) { cudaEvent_t eb_ = (c)->prof.get(); cudaEventRecord(eb_, (c)->stream); \
+                        (c)->prof.pend.push_back({kclass, ea_, eb_}); } \
+    (c)->launches += 1;                                                \
+  } while (0)
+
+void prof_resolve(gzb_ctx* c) {
+  for (auto& p : c->prof.pend) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { c->prof.ms[p.k] += ms; c->prof.n[p.k] += 1; }
+    c->prof.free_ev.push_back(p.a);
+    c->prof.free_ev.push_back(p.b);
+  }
+  c->prof.pend.clear();
+}
+
 template <typename T>
 void dmalloc(T** p, size_t n) { CK(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T))); }
 
@@ -211,11 +311,10 @@ void run_blur(gzb_ctx* c, const BlurPlan& pl, const float* in, size_t in_stride,
   dim3 blk(32, 8);
   dim3 gh((g.nx + g.oxn - 1) / g.oxn, (g.in_h + kBhRows - 1) / kBhRows, planes);
   const size_t tstride = pl.tmp_floats();
-  if (g.ups == 1) k_blur_h<1><<<gh, blk, 0, c->stream>>>(in, in_stride, g, pl.d_sx, c->d_tmp, tstride);
-  else k_blur_h<3><<<gh, blk, 0, c->stream>>>(in, in_stride, g, pl.d_sx, c->d_tmp, tstride);
+  if (g.ups == 1) KLAUNCH(c, KC_BLUR_H, k_blur_h<1><<<gh, blk, 0, c->stream>>>(in, in_stride, g, pl.d_sx, c->d_tmp, tstride));
+  else KLAUNCH(c, KC_BLUR_H, k_blur_h<3><<<gh, blk, 0, c->stream>>>(in, in_stride, g, pl.d_sx, c->d_tmp, tstride));
   dim3 gv((g.nx + 31) / 32, (g.ny + g.oyn - 1) / g.oyn, planes);
-  k_blur_v<<<gv, blk, 0, c->stream>>>(c->d_tmp, tstride, g, pl.d_sy, out, out_stride, out_pitch);
-  c->launches += 2;
+  KLAUNCH(c, KC_BLUR_V, k_blur_v<<<gv, blk, 0, c->stream>>>(c->d_tmp, tstride, g, pl.d_sy, out, out_stride, out_pitch));
 }
 
 void render_candidate(gzb_ctx* c, int op) {
@@ -223,19 +322,17 @@ void render_candidate(gzb_ctx* c, int op) {
   const size_t cs = static_cast<size_t>(c->nblocks) * 64;
   const size_t us = static_cast<size_t>(c->P) * c->HP;
   if (op == kCoeffKeep)
-    k_coeffs_to_rgb8<kCoeffKeep><<<grid, 256, 0, c->stream>>>(c->d_coef, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us);
+    KLAUNCH(c, KC_IDCT, k_coeffs_to_rgb8<kCoeffKeep><<<grid, 256, 0, c->stream>>>(c->d_coef, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us));
   else if (op == kCoeffQuantize)
-    k_coeffs_to_rgb8<kCoeffQuantize><<<grid, 256, 0, c->stream>>>(c->d_coef, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us);
+    KLAUNCH(c, KC_IDCT, k_coeffs_to_rgb8<kCoeffQuantize><<<grid, 256, 0, c->stream>>>(c->d_coef, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us));
   else
-    k_coeffs_to_rgb8<kCoeffScale><<<grid, 256, 0, c->stream>>>(c->d_orig, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us);
-  c->launches += 1;
+    KLAUNCH(c, KC_IDCT, k_coeffs_to_rgb8<kCoeffScale><<<grid, 256, 0, c->stream>>>(c->d_orig, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us));
 }
 
 void opsin_from_u8(gzb_ctx* c, const uint8_t* planes, float* xyb) {
   dim3 blk(32, 8), grd((c->W + 31) / 32, (c->H + 31) / 32);
-  k_opsin_dynamics<<<grd, blk, 0, c->stream>>>(planes, static_cast<size_t>(c->P) * c->HP, c->W, c->H, c->P,
-                                               c->p_ops.d_sx, c->p_ops.d_sy, xyb, c->ps);
-  c->launches += 1;
+  KLAUNCH(c, KC_OPSIN, k_opsin_dynamics<<<grd, blk, 0, c->stream>>>(planes, static_cast<size_t>(c->P) * c->HP, c->W, c->H, c->P,
+                                               c->p_ops.d_sx, c->p_ops.d_sy, xyb, c->ps));
 }
 
 MaskSample mask_sample(gzb_ctx* c, bool for_blocks) {
@@ -253,8 +350,7 @@ MaskSample mask_sample(gzb_ctx* c, bool for_blocks) {
 // channel-2 lattice.
 void run_mask(gzb_ctx* c, const float* a, const float* b, bool for_blocks) {
   dim3 blk(32, 8), grd((c->W + 31) / 32, (c->H + 31) / 32, 3);
-  k_mask_front<<<grd, blk, 0, c->stream>>>(a, b, c->ps, c->W, c->H, c->P, c->d_bl);
-  c->launches += 1;
+  KLAUNCH(c, KC_MASK_FRONT, k_mask_front<<<grd, blk, 0, c->stream>>>(a, b, c->ps, c->W, c->H, c->P, c->d_bl));
   for (int k = 0; k < 3; ++k) {
     const BlurPlan& pl = (k == 2 && for_blocks) ? c->p_mkb2 : c->p_mk[k];
     float* out = (k == 2 && for_blocks) ? c->d_msb2 : c->d_ms[k];
@@ -268,51 +364,58 @@ void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
   dim3 blk(32, 8), gpx((W + 31) / 32, (H + 7) / 8);
   float* m0 = c->d_mh;
   float* m1 = c->d_mh + 3 * c->ps;
-  k_mask_high_intensity_change<<<gpx, blk, 0, c->stream>>>(xyb0, xyb1, c->ps, W, H, P, m0, m1);
-  c->launches += 1;
+  KLAUNCH(c, KC_MHIC, k_mask_high_intensity_change<<<gpx, blk, 0, c->stream>>>(xyb0, xyb1, c->ps, W, H, P, m0, m1));
   // EdgeDetectorMap
   for (int k = 0; k < 3; ++k)
     run_blur(c, c->p_ed[k], c->d_mh + k * c->ps, 3 * c->ps, 2, c->d_bl + k * c->ps, 3 * c->ps, P);
   dim3 gres((c->rxs + 31) / 32, (c->rys + 7) / 8);
-  k_edge_detector_map<<<gres, blk, 0, c->stream>>>(c->d_bl, c->d_bl + 3 * c->ps, c->ps, W, H, P, c->rxs, c->d_edm);
+  KLAUNCH(c, KC_EDGE_MAP, k_edge_detector_map<<<gres, blk, 0, c->stream>>>(c->d_bl, c->d_bl + 3 * c->ps, c->ps, W, H, P, c->rxs, c->d_edm));
   // BlockDiffMap
   const size_t rbytes = static_cast<size_t>(3) * c->rxs * c->rys * sizeof(float);
   CK(cudaMemsetAsync(c->d_ac, 0, rbytes, c->stream));
   const int ncx = (W - 4 + 2) / 3, ncy = (H - 4 + 2) / 3;
   const int cells = ncx * ncy;
   const int ctas = std::min((cells + kBdmWarps - 1) / kBdmWarps, c->sm_count * 16);
-  k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, c->stream>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac);
+  KLAUNCH(c, KC_BLOCK_DIFF, k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, c->stream>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac));
   // EdgeDetectorLowFreq
   run_blur(c, c->p_lf, c->d_mh, c->ps, 6, c->d_lf, c->lf_stride, c->p_lf.g.tmp_pitch);
-  k_edge_lowfreq<<<gres, blk, 0, c->stream>>>(c->d_lf, c->d_lf + 3 * c->lf_stride, c->lf_stride, c->p_lf.g.tmp_pitch,
-                                             c->p_lf.g.sx, W, H, c->rxs, c->d_ac);
-  c->launches += 3;
+  KLAUNCH(c, KC_LOWFREQ, k_edge_lowfreq<<<gres, blk, 0, c->stream>>>(c->d_lf, c->d_lf + 3 * c->lf_stride, c->lf_stride, c->p_lf.g.tmp_pitch,
+                                             c->p_lf.g.sx, W, H, c->rxs, c->d_ac));
   // Mask + combine
   run_mask(c, m0, m1, false);
-  k_combine<<<gres, blk, 0, c->stream>>>(mask_sample(c, false), c->d_dc, c->d_ac, c->d_edm, W, H, c->rxs, c->rys, c->sqp, c->d_sq);
+  KLAUNCH(c, KC_COMBINE, k_combine<<<gres, blk, 0, c->stream>>>(mask_sample(c, false), c->d_dc, c->d_ac, c->d_edm, W, H, c->rxs, c->rys, c->sqp, c->d_sq));
   // CalculateDiffmap
   run_blur(c, c->p_dm, c->d_sq, 0, 1, c->d_dsmall, 0, c->p_dm.g.tmp_pitch);
   CK(cudaMemsetAsync(c->d_scalars, 0, sizeof(unsigned int), c->stream));
-  k_diffmap_final<<<gpx, blk, 0, c->stream>>>(c->d_sq, c->sqp, c->d_dsmall, c->p_dm.g.tmp_pitch, c->p_dm.g.sx, W, H, P,
-                                             c->d_diffmap, c->d_scalars);
-  c->launches += 2;
+  KLAUNCH(c, KC_DIFFMAP_FINAL, k_diffmap_final<<<gpx, blk, 0, c->stream>>>(c->d_sq, c->sqp, c->d_dsmall, c->p_dm.g.tmp_pitch, c->p_dm.g.sx, W, H, P,
+                                             c->d_diffmap, c->d_scalars));
 }
 
 void free_ctx(gzb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  void* ptrs[] = {c->d_rgb0, c->d_rgb1, c->d_stage_u8, c->d_orig, c->d_coef, c->d_xyb0, c->d_xyb1, c->d_mh,
-                  c->d_bl, c->d_tmp, c->d_lf, c->d_ms[0], c->d_ms[1], c->d_ms[2], c->d_msb2, c->d_edm, c->d_dc,
-                  c->d_ac, c->d_sq, c->d_dsmall, c->d_diffmap, c->d_bmax, c->d_weight, c->d_mask_scale,
-                  c->d_block_err, c->d_pregamma, c->d_flags, c->d_scalars, c->d_q, c->d_order, c->d_upd};
-  for (void* p : ptrs) if (p) cudaFree(p);
-  if (c->h_pinned) cudaFreeHost(c->h_pinned);
-  c->p_ops.release(); c->p_lf.release(); c->p_mkb2.release(); c->p_dm.release();
-  for (int k = 0; k < 3; ++k) { c->p_ed[k].release(); c->p_mk[k].release(); }
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->upd_own && c->d_upd) cudaFree(c->d_upd);
+  slab_release(c->device, c->slab);
+  for (auto& pnd : c->prof.pend) { cudaEventDestroy(pnd.a); cudaEventDestroy(pnd.b); }
+  for (cudaEvent_t ev : c->prof.free_ev) cudaEventDestroy(ev);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
+}
+
+template <typename T>
+void need(gzb_ctx* c, T** pp, size_t n) {
+  c->reqs.push_back({reinterpret_cast<void**>(pp), (std::max<size_t>(n, 1) * sizeof(T) + 255) / 256 * 256});
+}
+void commit_slab(gzb_ctx* c) {
+  size_t total = 0;
+  for (auto& r : c->reqs) total += r.bytes;
+  c->slab = slab_acquire(c->device, total);
+  char* p = static_cast<char*>(c->slab.base);
+  for (auto& r : c->reqs) { *r.pp = p; p += r.bytes; }
+  c->reqs.clear();
 }
 
 // Allocates everything for a W x H image (no original yet).
@@ -322,9 +425,7 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     c->device = device;
     CK(cudaSetDevice(device));
     init_device_tables(device);
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    c->sm_count = prop.multiProcessorCount;
+    CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
@@ -335,13 +436,11 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     c->ps = static_cast<size_t>(c->P) * c->HP;
     c->rxs = (W + 2) / 3; c->rys = (H + 2) / 3; c->sqp = round_up(c->rxs, 32);
     const size_t us = c->ps;
-    dmalloc(&c->d_rgb0, 3 * us); dmalloc(&c->d_rgb1, 3 * us); dmalloc(&c->d_stage_u8, static_cast<size_t>(3) * W * H);
-    CK(cudaMemsetAsync(c->d_rgb0, 0, 3 * us, c->stream));
-    CK(cudaMemsetAsync(c->d_rgb1, 0, 3 * us, c->stream));
+    need(c, &c->d_rgb0, 3 * us); need(c, &c->d_rgb1, 3 * us); need(c, &c->d_stage_u8, static_cast<size_t>(3) * W * H);
     const size_t cs = static_cast<size_t>(c->nblocks) * 64;
-    dmalloc(&c->d_orig, 3 * cs); dmalloc(&c->d_coef, 3 * cs);
-    dmalloc(&c->d_xyb0, 3 * c->ps); dmalloc(&c->d_xyb1, 3 * c->ps);
-    dmalloc(&c->d_mh, 6 * c->ps); dmalloc(&c->d_bl, 6 * c->ps); dmalloc(&c->d_tmp, 6 * c->ps);
+    need(c, &c->d_orig, 3 * cs); need(c, &c->d_coef, 3 * cs);
+    need(c, &c->d_xyb0, 3 * c->ps); need(c, &c->d_xyb1, 3 * c->ps);
+    need(c, &c->d_mh, 6 * c->ps); need(c, &c->d_bl, 6 * c->ps); need(c, &c->d_tmp, 6 * c->ps);
     // plans
     c->p_ops.build_decimated(g_hk[kB11], kB11, W, H, c->P, 0.0, 1);
     const int edk[3] = {kB15, kB0586, kB04};
@@ -356,25 +455,34 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     }
     c->p_dm.build_decimated(g_hk[kB8851], kB8851, W - 5, H - 5, c->sqp, 0.03027655136, 3);
     c->lf_stride = c->p_lf.out_floats();
-    dmalloc(&c->d_lf, 6 * c->lf_stride);
-    for (int k = 0; k < 3; ++k) dmalloc(&c->d_ms[k], c->p_mk[k].out_floats());
-    dmalloc(&c->d_msb2, c->p_mkb2.out_floats());
+    need(c, &c->d_lf, 6 * c->lf_stride);
+    for (int k = 0; k < 3; ++k) need(c, &c->d_ms[k], c->p_mk[k].out_floats());
+    need(c, &c->d_msb2, c->p_mkb2.out_floats());
     const size_t rn = static_cast<size_t>(c->rxs) * c->rys;
-    dmalloc(&c->d_edm, 3 * rn); dmalloc(&c->d_dc, 3 * rn); dmalloc(&c->d_ac, 3 * rn);
+    need(c, &c->d_edm, 3 * rn); need(c, &c->d_dc, 3 * rn); need(c, &c->d_ac, 3 * rn);
+    need(c, &c->d_sq, static_cast<size_t>(c->sqp) * c->rys);
+    need(c, &c->d_dsmall, c->p_dm.out_floats());
+    need(c, &c->d_diffmap, c->ps);
+    need(c, &c->d_bmax, c->nblocks); need(c, &c->d_weight, c->nblocks);
+    need(c, &c->d_mask_scale, static_cast<size_t>(3) * c->nblocks);
+    need(c, &c->d_block_err, c->nblocks);
+    need(c, &c->d_pregamma, static_cast<size_t>(192) * c->nblocks);
+    need(c, &c->d_flags, c->nblocks);
+    need(c, &c->d_scalars, 4);
+    need(c, &c->d_q, 192);
+    need(c, &c->d_order, static_cast<size_t>(192) * c->nblocks);
+    need(c, &c->d_upd, static_cast<size_t>(c->nblocks) * 8 * 8);
+    c->upd_cap = static_cast<size_t>(c->nblocks) * 8;
+    BlurPlan* plans[] = {&c->p_ops, &c->p_ed[0], &c->p_ed[1], &c->p_ed[2], &c->p_lf, &c->p_mk[0], &c->p_mk[1],
+                         &c->p_mk[2], &c->p_mkb2, &c->p_dm};
+    for (BlurPlan* pl : plans) { need(c, &pl->d_sx, pl->hx.size()); need(c, &pl->d_sy, pl->hy.size()); }
+    commit_slab(c);
+    for (BlurPlan* pl : plans) pl->upload(c->stream);
+    c->h_pinned = static_cast<float*>(c->slab.pinned);
+    CK(cudaMemsetAsync(c->d_rgb0, 0, 3 * us, c->stream));
+    CK(cudaMemsetAsync(c->d_rgb1, 0, 3 * us, c->stream));
     CK(cudaMemsetAsync(c->d_edm, 0, 3 * rn * sizeof(float), c->stream));
     CK(cudaMemsetAsync(c->d_dc, 0, 3 * rn * sizeof(float), c->stream));
-    dmalloc(&c->d_sq, static_cast<size_t>(c->sqp) * c->rys);
-    dmalloc(&c->d_dsmall, c->p_dm.out_floats());
-    dmalloc(&c->d_diffmap, c->ps);
-    dmalloc(&c->d_bmax, c->nblocks); dmalloc(&c->d_weight, c->nblocks);
-    dmalloc(&c->d_mask_scale, static_cast<size_t>(3) * c->nblocks);
-    dmalloc(&c->d_block_err, c->nblocks);
-    dmalloc(&c->d_pregamma, static_cast<size_t>(192) * c->nblocks);
-    dmalloc(&c->d_flags, c->nblocks);
-    dmalloc(&c->d_scalars, 4);
-    dmalloc(&c->d_q, 192);
-    dmalloc(&c->d_order, static_cast<size_t>(192) * c->nblocks);
-    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_pinned), 4096));
     // the blur scratch must hold the widest H-pass output of any plan
     const BlurPlan* all[] = {&c->p_ed[0], &c->p_ed[1], &c->p_ed[2], &c->p_lf, &c->p_mk[0], &c->p_mk[1],
                              &c->p_mk[2], &c->p_mkb2, &c->p_dm};
@@ -391,11 +499,10 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
 
 void upload_original(gzb_ctx* c, const uint8_t* rgb) {
   const size_t n = static_cast<size_t>(3) * c->W * c->H;
-  CK(cudaMemcpyAsync(c->d_stage_u8, rgb, n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_stage_u8, rgb, n, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n);
   dim3 grd((c->W + 255) / 256, c->H);
-  k_deinterleave_rgb<<<grd, 256, 0, c->stream>>>(c->d_stage_u8, c->W, c->H, c->P, c->d_rgb0, c->ps);
+  KLAUNCH(c, KC_MISC, k_deinterleave_rgb<<<grd, 256, 0, c->stream>>>(c->d_stage_u8, c->W, c->H, c->P, c->d_rgb0, c->ps));
   opsin_from_u8(c, c->d_rgb0, c->d_xyb0);
-  c->launches += 1;
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaGetLastError());
 }
@@ -415,6 +522,7 @@ int fail(gzb_ctx* c, int code, const std::string& msg) {
 void sync_check(gzb_ctx* c) {
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaGetLastError());
+  if (!c->prof.pend.empty()) prof_resolve(c);
 }
 
 }  // namespace
@@ -461,7 +569,7 @@ int gzb_set_jpeg_coeffs(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const 
   GZB_TRY(c)
   const size_t cs = static_cast<size_t>(c->nblocks) * 64;
   const int16_t* src[3] = {c0, c1, c2};
-  for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(c->d_orig + k * cs, src[k], cs * 2, cudaMemcpyHostToDevice, c->stream));
+  for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(c->d_orig + k * cs, src[k], cs * 2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (cs * 2);
   sync_check(c);
   c->have_orig_coeffs = true;
   GZB_END(c)
@@ -470,7 +578,7 @@ int gzb_set_jpeg_coeffs(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const 
 int gzb_copy_from_jpeg(gzb_ctx* c, const int* quant192) {
   GZB_TRY(c)
   if (!c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_copy_from_jpeg: gzb_set_jpeg_coeffs not called");
-  CK(cudaMemcpyAsync(c->d_q, quant192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_q, quant192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (192 * sizeof(int));
   render_candidate(c, kCoeffScale);
   sync_check(c);
   c->have_coeffs = true;
@@ -481,7 +589,7 @@ int gzb_apply_global_quantization(gzb_ctx* c, const int* q192) {
   GZB_TRY(c)
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_apply_global_quantization: no candidate coefficients");
   for (int i = 0; i < 192; ++i) if (q192[i] <= 0) return fail(c, GZB_ERR_BAD_ARG, "quantiser must be positive");
-  CK(cudaMemcpyAsync(c->d_q, q192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_q, q192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (192 * sizeof(int));
   render_candidate(c, kCoeffQuantize);
   sync_check(c);
   GZB_END(c)
@@ -491,7 +599,7 @@ int gzb_set_coeffs(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const int16
   GZB_TRY(c)
   const size_t cs = static_cast<size_t>(c->nblocks) * 64;
   const int16_t* src[3] = {c0, c1, c2};
-  for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(c->d_coef + k * cs, src[k], cs * 2, cudaMemcpyHostToDevice, c->stream));
+  for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(c->d_coef + k * cs, src[k], cs * 2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (cs * 2);
   render_candidate(c, kCoeffKeep);
   sync_check(c);
   c->have_coeffs = true;
@@ -502,7 +610,7 @@ int gzb_get_coeffs(gzb_ctx* c, int16_t* c0, int16_t* c1, int16_t* c2) {
   GZB_TRY(c)
   const size_t cs = static_cast<size_t>(c->nblocks) * 64;
   int16_t* dst[3] = {c0, c1, c2};
-  for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(dst[k], c->d_coef + k * cs, cs * 2, cudaMemcpyDeviceToHost, c->stream));
+  for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(dst[k], c->d_coef + k * cs, cs * 2, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (cs * 2);
   sync_check(c);
   GZB_END(c)
 }
@@ -514,20 +622,20 @@ int gzb_update_coeffs(gzb_ctx* c, const int32_t* block_ix, const uint8_t* idx, c
     if (block_ix[i] < 0 || block_ix[i] >= c->nblocks || idx[i] >= 192) return fail(c, GZB_ERR_BAD_ARG, "gzb_update_coeffs: index out of range");
   if (n > 0) {
     if (n > c->upd_cap) {
-      if (c->d_upd) cudaFree(c->d_upd);
+      if (c->upd_own && c->d_upd) cudaFree(c->d_upd);
       c->upd_cap = n + n / 2 + 1024;
       dmalloc(&c->d_upd, c->upd_cap * 8);
+      c->upd_own = true;
     }
     // records are applied in order (later writes to the same coefficient win): one thread walks
     // duplicates, so pack {block, idx, val} and let the kernel resolve by record index
-    CK(cudaMemcpyAsync(c->d_upd, block_ix, n * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_upd + c->upd_cap * 4, val, n * 2, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_upd + c->upd_cap * 6, idx, n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_upd, block_ix, n * 4, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n * 4);
+    CK(cudaMemcpyAsync(c->d_upd + c->upd_cap * 4, val, n * 2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n * 2);
+    CK(cudaMemcpyAsync(c->d_upd + c->upd_cap * 6, idx, n, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n);
     const size_t cs = static_cast<size_t>(c->nblocks) * 64;
-    k_scatter_coeffs<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(
+    KLAUNCH(c, KC_MISC, k_scatter_coeffs<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(
         reinterpret_cast<const int*>(c->d_upd), reinterpret_cast<const int16_t*>(c->d_upd + c->upd_cap * 4),
-        c->d_upd + c->upd_cap * 6, n, cs, c->d_coef);
-    c->launches += 1;
+        c->d_upd + c->upd_cap * 6, n, cs, c->d_coef));
   }
   render_candidate(c, kCoeffKeep);
   sync_check(c);
@@ -548,7 +656,7 @@ int gzb_to_srgb(gzb_ctx* c, uint8_t* rgb_out) {
   const size_t us = c->ps;
   for (int k = 0; k < 3; ++k)
     CK(cudaMemcpy2DAsync(pl.data() + static_cast<size_t>(k) * c->W * c->H, c->W, c->d_rgb1 + k * us, c->P, c->W, c->H,
-                         cudaMemcpyDeviceToHost, c->stream));
+                         cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (static_cast<unsigned long long>(c->W) * (c->H));
   sync_check(c);
   const size_t n = static_cast<size_t>(c->W) * c->H;
   for (size_t i = 0; i < n; ++i) {
@@ -566,7 +674,7 @@ int gzb_compare(gzb_ctx* c, float* distance) {
   opsin_from_u8(c, c->d_rgb1, c->d_xyb1);
   run_diffmap(c, c->d_xyb0, c->d_xyb1);
   CK(cudaEventRecord(c->ev1, c->stream));
-  CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(unsigned int));
   sync_check(c);
   CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   memcpy(&c->distance, c->h_pinned, sizeof(float));
@@ -579,7 +687,7 @@ int gzb_get_distmap(gzb_ctx* c, float* out) {
   GZB_TRY(c)
   if (!c->have_distmap) return fail(c, GZB_ERR_STATE, "gzb_get_distmap: no Compare yet");
   CK(cudaMemcpy2DAsync(out, c->W * sizeof(float), c->d_diffmap, c->P * sizeof(float), c->W * sizeof(float), c->H,
-                       cudaMemcpyDeviceToHost, c->stream));
+                       cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (static_cast<unsigned long long>(c->W * sizeof(float)) * (c->H));
   sync_check(c);
   GZB_END(c)
 }
@@ -605,8 +713,7 @@ int gzb_start_block_comparisons(gzb_ctx* c) {
   GZB_TRY(c)
   CK(cudaEventRecord(c->ev0, c->stream));
   run_mask(c, c->d_xyb0, c->d_xyb0, true);
-  k_block_mask_scale<<<(c->nblocks + 255) / 256, 256, 0, c->stream>>>(mask_sample(c, true), c->bw, c->bh, c->d_mask_scale);
-  c->launches += 1;
+  KLAUNCH(c, KC_BLOCK_MASK, k_block_mask_scale<<<(c->nblocks + 255) / 256, 256, 0, c->stream>>>(mask_sample(c, true), c->bw, c->bh, c->d_mask_scale));
   CK(cudaEventRecord(c->ev1, c->stream));
   sync_check(c);
   CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
@@ -626,10 +733,9 @@ static int run_zeroing(gzb_ctx* c, int comp_mask, int mode) {
   if (mode == 0) CK(cudaMemsetAsync(c->d_order, 0, sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(c->nblocks), c->stream));
   const int ctas = std::min((c->nblocks + kZeroWarps - 1) / kZeroWarps, c->sm_count * 5);
   CK(cudaEventRecord(c->ev0, c->stream));
-  k_zeroing_order<<<ctas, 32 * kZeroWarps, 0, c->stream>>>(
+  KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<ctas, 32 * kZeroWarps, 0, c->stream>>>(
       c->d_orig, c->d_coef, cs, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, c->nblocks, c->d_mask_scale, comp_mask,
-      c->target, 3, mode, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1);
-  c->launches += 1;
+      c->target, 3, mode, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1));
   CK(cudaEventRecord(c->ev1, c->stream));
   return 0;
 }
@@ -640,10 +746,10 @@ int gzb_get_block_lists(gzb_ctx* c, float* mask_scale_out, float* opsin_blocks_o
   if (opsin_blocks_out) {
     if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_get_block_lists: no candidate coefficients");
     run_zeroing(c, 7, 1);
-    CK(cudaMemcpyAsync(opsin_blocks_out, c->d_pregamma, sizeof(float) * 192 * static_cast<size_t>(c->nblocks), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(opsin_blocks_out, c->d_pregamma, sizeof(float) * 192 * static_cast<size_t>(c->nblocks), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(float) * 192 * static_cast<size_t>(c->nblocks));
   }
   if (mask_scale_out)
-    CK(cudaMemcpyAsync(mask_scale_out, c->d_mask_scale, sizeof(float) * 3 * static_cast<size_t>(c->nblocks), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(mask_scale_out, c->d_mask_scale, sizeof(float) * 3 * static_cast<size_t>(c->nblocks), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(float) * 3 * static_cast<size_t>(c->nblocks));
   sync_check(c);
   GZB_END(c)
 }
@@ -653,7 +759,7 @@ int gzb_compare_blocks(gzb_ctx* c, float* err_out) {
   if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_compare_blocks: StartBlockComparisons not called");
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compare_blocks: no candidate coefficients");
   run_zeroing(c, 7, 1);
-  CK(cudaMemcpyAsync(err_out, c->d_block_err, sizeof(float) * c->nblocks, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(err_out, c->d_block_err, sizeof(float) * c->nblocks, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(float) * c->nblocks);
   sync_check(c);
   CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   GZB_END(c)
@@ -665,7 +771,7 @@ int gzb_compute_block_zeroing_order(gzb_ctx* c, int comp_mask, gzb_coeff_data* o
   if (!c->have_coeffs || !c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compute_block_zeroing_order: coefficients missing");
   if (comp_mask < 1 || comp_mask > 7) return fail(c, GZB_ERR_BAD_ARG, "comp_mask must be in 1..7");
   run_zeroing(c, comp_mask, 0);
-  CK(cudaMemcpyAsync(out, c->d_order, sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(c->nblocks), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(out, c->d_order, sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(c->nblocks), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(c->nblocks));
   sync_check(c);
   CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   GZB_END(c)
@@ -676,18 +782,17 @@ int gzb_compute_block_error_adjustment_weights(gzb_ctx* c, int direction, int ma
   GZB_TRY(c)
   if (distmap) {
     CK(cudaMemcpy2DAsync(c->d_diffmap, c->P * sizeof(float), distmap, c->W * sizeof(float), c->W * sizeof(float), c->H,
-                         cudaMemcpyHostToDevice, c->stream));
+                         cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (static_cast<unsigned long long>(c->W * sizeof(float)) * (c->H));
     c->have_distmap = false;  // the resident map no longer belongs to the last Compare
   } else if (!c->have_distmap) {
     return fail(c, GZB_ERR_STATE, "gzb_compute_block_error_adjustment_weights: no distance map");
   }
   const double target = static_cast<double>(c->target) * target_mul;
   const int g = (c->nblocks + 255) / 256;
-  k_block_max<<<g, 256, 0, c->stream>>>(c->d_diffmap, c->P, c->W, c->H, c->bw, c->bh, c->d_bmax);
-  k_block_flags<<<g, 256, 0, c->stream>>>(c->d_bmax, c->bw, c->bh, direction, max_block_dist, target, c->d_flags);
-  k_block_weights<<<g, 256, 0, c->stream>>>(c->d_flags, c->bw, c->bh, direction, max_block_dist, c->d_weight);
-  c->launches += 3;
-  CK(cudaMemcpyAsync(block_weight, c->d_weight, sizeof(float) * c->nblocks, cudaMemcpyDeviceToHost, c->stream));
+  KLAUNCH(c, KC_WEIGHTS, k_block_max<<<g, 256, 0, c->stream>>>(c->d_diffmap, c->P, c->W, c->H, c->bw, c->bh, c->d_bmax));
+  KLAUNCH(c, KC_WEIGHTS, k_block_flags<<<g, 256, 0, c->stream>>>(c->d_bmax, c->bw, c->bh, direction, max_block_dist, target, c->d_flags));
+  KLAUNCH(c, KC_WEIGHTS, k_block_weights<<<g, 256, 0, c->stream>>>(c->d_flags, c->bw, c->bh, direction, max_block_dist, c->d_weight));
+  CK(cudaMemcpyAsync(block_weight, c->d_weight, sizeof(float) * c->nblocks, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(float) * c->nblocks);
   sync_check(c);
   GZB_END(c)
 }
@@ -715,20 +820,44 @@ int gzb_debug_fetch(gzb_ctx* c, const char* name, float* out, size_t cap, size_t
     if (cap >= total)
       for (int k = 0; k < nplanes; ++k)
         CK(cudaMemcpy2DAsync(out + k * n, c->W * sizeof(float), planes + k * c->ps, c->P * sizeof(float),
-                             c->W * sizeof(float), c->H, cudaMemcpyDeviceToHost, c->stream));
+                             c->W * sizeof(float), c->H, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (static_cast<unsigned long long>(c->W * sizeof(float)) * (c->H));
   } else if (flat) {
     if (n_out) *n_out = flat_n;
-    if (cap >= flat_n) CK(cudaMemcpyAsync(out, flat, flat_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (cap >= flat_n) CK(cudaMemcpyAsync(out, flat, flat_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (flat_n * sizeof(float));
   } else {  // combined_sqrt: res map with pitch
     if (n_out) *n_out = rn;
     if (cap >= rn)
       CK(cudaMemcpy2DAsync(out, c->rxs * sizeof(float), c->d_sq, c->sqp * sizeof(float), c->rxs * sizeof(float), c->rys,
-                           cudaMemcpyDeviceToHost, c->stream));
+                           cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (static_cast<unsigned long long>(c->rxs * sizeof(float)) * (c->rys));
   }
   sync_check(c);
   GZB_END(c)
 }
 
+int gzb_profile_enable(gzb_ctx* c, int on) {
+  if (!c) return GZB_ERR_BAD_ARG;
+  c->prof.on = on != 0;
+  return GZB_OK;
+}
+int gzb_profile_count(void) { return KC_COUNT; }
+const char* gzb_profile_name(int i) { return i >= 0 && i < KC_COUNT ? kClassNames[i] : ""; }
+int gzb_profile_get(gzb_ctx* c, int i, double* ms, unsigned long long* launches) {
+  if (!c || i < 0 || i >= KC_COUNT) return GZB_ERR_BAD_ARG;
+  if (ms) *ms = c->prof.ms[i];
+  if (launches) *launches = c->prof.n[i];
+  return GZB_OK;
+}
+int gzb_profile_reset(gzb_ctx* c) {
+  if (!c) return GZB_ERR_BAD_ARG;
+  for (int i = 0; i < KC_COUNT; ++i) { c->prof.ms[i] = 0; c->prof.n[i] = 0; }
+  return GZB_OK;
+}
+int gzb_get_transfer_bytes(const gzb_ctx* c, unsigned long long* h2d, unsigned long long* d2h) {
+  if (!c) return GZB_ERR_BAD_ARG;
+  if (h2d) *h2d = c->h2d_bytes;
+  if (d2h) *d2h = c->d2h_bytes;
+  return GZB_OK;
+}
 float gzb_last_device_ms(const gzb_ctx* c) { return c ? c->last_ms : 0.f; }
 unsigned long long gzb_launch_count(const gzb_ctx* c) { return c ? c->launches : 0; }
 
@@ -747,6 +876,7 @@ int gzb_blur(int device, float* plane, size_t xsize, size_t ysize, double sigma,
     CK(cudaMemcpyToSymbol(c_taps, taps, sizeof(taps), sizeof(float) * kMaxTaps * kBUser));
     BlurPlan pl;
     pl.build_decimated(hk, kBUser, W, H, P, border_ratio, 1);
+    pl.upload_own();
     float *d_in = nullptr, *d_tmp = nullptr, *d_out = nullptr;
     dmalloc(&d_in, static_cast<size_t>(P) * H);
     dmalloc(&d_tmp, pl.tmp_floats());
@@ -779,6 +909,7 @@ int gzb_opsin_dynamics_image(int device, float* r, float* g, float* b, size_t xs
     const size_t ps = static_cast<size_t>(P) * H;
     BlurPlan pl;
     pl.build_decimated(g_hk[kB11], kB11, W, H, P, 0.0, 1);
+    pl.upload_own();
     float *d_in = nullptr, *d_out = nullptr;
     dmalloc(&d_in, 3 * ps);
     dmalloc(&d_out, 3 * ps);
@@ -810,11 +941,11 @@ int gzb_diffmap_opsin_dynamics_image(int device, float* result, const float* r, 
     const float* s0[3] = {r, g, b};
     const float* s1[3] = {r2, g2, b2};
     for (int k = 0; k < 3; ++k) {
-      CK(cudaMemcpy2DAsync(c->d_xyb0 + k * c->ps, c->P * sizeof(float), s0[k], c->W * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyHostToDevice, c->stream));
-      CK(cudaMemcpy2DAsync(c->d_xyb1 + k * c->ps, c->P * sizeof(float), s1[k], c->W * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpy2DAsync(c->d_xyb0 + k * c->ps, c->P * sizeof(float), s0[k], c->W * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (static_cast<unsigned long long>(c->W * sizeof(float)) * (c->H));
+      CK(cudaMemcpy2DAsync(c->d_xyb1 + k * c->ps, c->P * sizeof(float), s1[k], c->W * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (static_cast<unsigned long long>(c->W * sizeof(float)) * (c->H));
     }
     run_diffmap(c, c->d_xyb0, c->d_xyb1);
-    CK(cudaMemcpy2DAsync(result, c->W * sizeof(float), c->d_diffmap, c->P * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpy2DAsync(result, c->W * sizeof(float), c->d_diffmap, c->P * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (static_cast<unsigned long long>(c->W * sizeof(float)) * (c->H));
     sync_check(c);
   } catch (const std::string& e) { rc = fail(nullptr, GZB_ERR_CUDA, e); }
   free_ctx(c);
@@ -829,14 +960,14 @@ int gzb_butteraugli_srgb(int device, const uint8_t* rgb0, const uint8_t* rgb1, i
   if (rc != GZB_OK) return rc;
   try {
     const size_t n = static_cast<size_t>(3) * c->W * c->H;
-    CK(cudaMemcpyAsync(c->d_stage_u8, rgb1, n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_stage_u8, rgb1, n, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n);
     dim3 grd((c->W + 255) / 256, c->H);
-    k_deinterleave_rgb<<<grd, 256, 0, c->stream>>>(c->d_stage_u8, c->W, c->H, c->P, c->d_rgb1, c->ps);
+    KLAUNCH(c, KC_MISC, k_deinterleave_rgb<<<grd, 256, 0, c->stream>>>(c->d_stage_u8, c->W, c->H, c->P, c->d_rgb1, c->ps));
     opsin_from_u8(c, c->d_rgb1, c->d_xyb1);
     run_diffmap(c, c->d_xyb0, c->d_xyb1);
-    CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(unsigned int));
     if (diffmap_out)
-      CK(cudaMemcpy2DAsync(diffmap_out, c->W * sizeof(float), c->d_diffmap, c->P * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpy2DAsync(diffmap_out, c->W * sizeof(float), c->d_diffmap, c->P * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (static_cast<unsigned long long>(c->W * sizeof(float)) * (c->H));
     sync_check(c);
     if (distance) memcpy(distance, c->h_pinned, sizeof(float));
   } catch (const std::string& e) { rc = fail(nullptr, GZB_ERR_CUDA, e); }

@@ -284,7 +284,7 @@ struct Encoder {
   double best_score = -1;
   gzb_encode_stats st{};
   std::string trace;
-  bool want_trace = false;
+  bool want_trace = false, ran = false;
   float distance = 0.f;
 
   void log(const char* fmt, ...) {
@@ -443,27 +443,27 @@ void gzb_test_std_sort(int* first, float* second, size_t n) {
   for (size_t i = 0; i < n; ++i) { first[i] = v[i].first; second[i] = v[i].second; }
 }
 
-int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
-                   int host_threads, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
-                   char** trace_out) {
+struct gzb_encoder { Encoder e; double t_start = 0; };
+
+int gzb_encoder_create(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
+                       int host_threads, gzb_encoder** out) {
   g_encode_err.clear();
-  if (!rgb || !jpeg_out || !jpeg_size) { g_encode_err = "gzb_encode_rgb: null argument"; return GZB_ERR_BAD_ARG; }
-  *jpeg_out = nullptr; *jpeg_size = 0;
-  if (trace_out) *trace_out = nullptr;
+  if (!rgb || !out) { g_encode_err = "gzb_encoder_create: null argument"; return GZB_ERR_BAD_ARG; }
+  *out = nullptr;
   if (butteraugli_target > 2.0f) {  // processor.cc:939-945
-    g_encode_err = "gzb_encode_rgb: quality below 84 is refused (butteraugli target > 2.0)";
+    g_encode_err = "gzb_encoder_create: quality below 84 is refused (butteraugli target > 2.0)";
     return GZB_ERR_BAD_ARG;
   }
   if (width < 32 || height < 32) {
-    g_encode_err = "gzb_encode_rgb: images smaller than 32x32 skip butteraugli in the reference; not accelerated";
+    g_encode_err = "gzb_encoder_create: images smaller than 32x32 skip butteraugli in the reference; not accelerated";
     return GZB_ERR_TOO_SMALL;
   }
-  if (width >= (1 << 16) || height >= (1 << 16)) { g_encode_err = "gzb_encode_rgb: image too large"; return GZB_ERR_BAD_ARG; }
-  const double t_start = now_ms();
-  Encoder e;
+  if (width >= (1 << 16) || height >= (1 << 16)) { g_encode_err = "gzb_encoder_create: image too large"; return GZB_ERR_BAD_ARG; }
+  gzb_encoder* enc = new gzb_encoder;
+  enc->t_start = now_ms();
+  Encoder& e = enc->e;
   e.w = width; e.h = height; e.bw = (width + 7) / 8; e.bh = (height + 7) / 8; e.nb = e.bw * e.bh;
   e.target = butteraugli_target;
-  e.want_trace = trace_out != nullptr;
   const unsigned hc = std::thread::hardware_concurrency();
   e.nthreads = host_threads > 0 ? host_threads : static_cast<int>(std::max(1u, std::min(16u, hc)));
   e.pool.reset(new gzb::WorkerPool(e.nthreads));
@@ -471,21 +471,49 @@ int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float 
   for (int c = 0; c < 3; ++c) { e.orig[c].resize(ncoef); e.cur[c].resize(ncoef); e.idx[c].resize(ncoef); }
   const double t_create = now_ms();
   int rc = gzb_create(device, width, height, rgb, butteraugli_target, &e.ctx);
-  if (rc != GZB_OK) { g_encode_err = gzb_last_error(nullptr); return rc; }
+  if (rc != GZB_OK) { g_encode_err = gzb_last_error(nullptr); delete enc; return rc; }
   e.st.create_ms = now_ms() - t_create;
-  auto fail = [&](int code) {
-    g_encode_err = gzb_last_error(e.ctx);
-    gzb_destroy(e.ctx);
-    return code;
-  };
   // EncodeRGBToJpeg (q = 1)
   {
     const double t0 = now_ms();
-    int16_t* out[3] = {e.orig[0].data(), e.orig[1].data(), e.orig[2].data()};
-    parallel_rows(e.bh, e.pool.get(), [&](int y0, int y1) { rgb_to_coeffs_rows(rgb, width, height, e.bw, y0, y1, out); });
+    int16_t* o3[3] = {e.orig[0].data(), e.orig[1].data(), e.orig[2].data()};
+    parallel_rows(e.bh, e.pool.get(), [&](int y0, int y1) { rgb_to_coeffs_rows(rgb, width, height, e.bw, y0, y1, o3); });
     e.st.host_frontend_ms = now_ms() - t0;
   }
-  if (gzb_set_jpeg_coeffs(e.ctx, e.orig[0].data(), e.orig[1].data(), e.orig[2].data()) != GZB_OK) return fail(GZB_ERR_CUDA);
+  if (gzb_set_jpeg_coeffs(e.ctx, e.orig[0].data(), e.orig[1].data(), e.orig[2].data()) != GZB_OK) {
+    g_encode_err = gzb_last_error(e.ctx);
+    gzb_destroy(e.ctx);
+    delete enc;
+    return GZB_ERR_CUDA;
+  }
+  e.st.prepare_ms = now_ms() - enc->t_start;
+  *out = enc;
+  return GZB_OK;
+}
+
+void gzb_encoder_destroy(gzb_encoder* enc) {
+  if (!enc) return;
+  if (enc->e.ctx) gzb_destroy(enc->e.ctx);
+  delete enc;
+}
+
+gzb_ctx* gzb_encoder_context(gzb_encoder* enc) { return enc ? enc->e.ctx : nullptr; }
+
+int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
+                    char** trace_out) {
+  if (!enc || !jpeg_out || !jpeg_size) { g_encode_err = "gzb_encoder_run: null argument"; return GZB_ERR_BAD_ARG; }
+  *jpeg_out = nullptr; *jpeg_size = 0;
+  if (trace_out) *trace_out = nullptr;
+  Encoder& e = enc->e;
+  if (e.ran) { g_encode_err = "gzb_encoder_run: an encoder runs once"; return GZB_ERR_STATE; }
+  e.ran = true;
+  const double t_start = now_ms();
+  const int width = e.w, height = e.h;
+  e.want_trace = trace_out != nullptr;
+  auto fail = [&](int code) {
+    g_encode_err = gzb_last_error(e.ctx);
+    return code;
+  };
   int ones[3][64];
   for (int c = 0; c < 3; ++c) for (int k = 0; k < 64; ++k) ones[c][k] = 1;
   // "Original": the q=1 input as a JPEG with three index-0 tables (processor.cc:967-985)
@@ -770,11 +798,12 @@ int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float 
   e.st.launches = gzb_launch_count(e.ctx);
   e.st.write_hist_ms = e.wt.hist_ms; e.st.write_code_ms = e.wt.code_ms;
   e.st.write_encode_ms = e.wt.encode_ms; e.st.write_stitch_ms = e.wt.stitch_ms;
-  gzb_destroy(e.ctx);
+  gzb_get_transfer_bytes(e.ctx, &e.st.h2d_bytes, &e.st.d2h_bytes);
   *jpeg_size = e.best_jpeg.size();
   *jpeg_out = static_cast<uint8_t*>(malloc(std::max<size_t>(1, e.best_jpeg.size())));
   memcpy(*jpeg_out, e.best_jpeg.data(), e.best_jpeg.size());
-  e.st.total_wall_ms = now_ms() - t_start;
+  e.st.run_ms = now_ms() - t_start;
+  e.st.total_wall_ms = e.st.prepare_ms + e.st.run_ms;
   e.st.final_distance = e.distance;
   e.st.final_score = e.best_score;
   if (stats) *stats = e.st;
@@ -783,6 +812,20 @@ int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float 
     memcpy(*trace_out, e.trace.c_str(), e.trace.size() + 1);
   }
   return GZB_OK;
+}
+
+int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
+                   int host_threads, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
+                   char** trace_out) {
+  if (jpeg_out) *jpeg_out = nullptr;
+  if (jpeg_size) *jpeg_size = 0;
+  if (trace_out) *trace_out = nullptr;
+  gzb_encoder* enc = nullptr;
+  int rc = gzb_encoder_create(device, rgb, width, height, butteraugli_target, host_threads, &enc);
+  if (rc != GZB_OK) return rc;
+  rc = gzb_encoder_run(enc, jpeg_out, jpeg_size, stats, trace_out);
+  gzb_encoder_destroy(enc);
+  return rc;
 }
 
 }  // extern "C"

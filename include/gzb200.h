@@ -147,6 +147,8 @@ typedef struct {
   double compare_wall_ms, device_compare_ms, zeroing_wall_ms, device_zeroing_ms, backend_wall_ms;
   double write_hist_ms, write_code_ms, write_encode_ms, write_stitch_ms;   /* parts of host_write_ms */
   double be_weights_ms, be_order_ms, be_walk_ms, be_update_ms, create_ms;  /* parts of the back end */
+  double prepare_ms, run_ms;             /* gzb_encoder_create / gzb_encoder_run wall time */
+  unsigned long long h2d_bytes, d2h_bytes; /* host<->device traffic of the whole encode */
   double final_score;
   float final_distance;
   unsigned long long launches;
@@ -154,6 +156,16 @@ typedef struct {
 int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
                    int host_threads, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
                    char** trace_out);
+/* The same encoder in two steps, so that a caller can separate "inputs resident in HBM" from the
+ * search: create uploads the image, computes its opsin-dynamics image and the q=1 coefficients;
+ * run performs the search (once per encoder). */
+typedef struct gzb_encoder gzb_encoder;
+int gzb_encoder_create(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
+                       int host_threads, gzb_encoder** out);
+int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
+                    char** trace_out);
+gzb_ctx* gzb_encoder_context(gzb_encoder* enc);
+void gzb_encoder_destroy(gzb_encoder* enc);
 const char* gzb_encode_last_error(void);
 void gzb_free(void* p);
 /* guetzli::ButteraugliScoreForQuality (guetzli/quality.cc:76-85). */
@@ -173,6 +185,18 @@ long gzb_write_jpeg(const int16_t* c0, const int16_t* c1, const int16_t* c2, int
 /* name in {"xyb0","xyb1","mhic0","mhic1","edge_map","block_dc","block_ac","combined_sqrt",
  * "diffmap","mask_front"}; copies min(cap, size) floats; *n_out = size in floats. */
 int gzb_debug_fetch(gzb_ctx* ctx, const char* name, float* out, size_t cap, size_t* n_out);
+
+/* ---- per-kernel device timing (CUDA events on the context's stream around every launch) ---- */
+/* Off by default. While on, every kernel launch of this context is bracketed by an event pair and
+ * accumulated per kernel name. */
+int gzb_profile_enable(gzb_ctx* ctx, int on);
+/* Number of kernel classes; name / accumulated ms / launch count of class i. */
+int gzb_profile_count(void);
+const char* gzb_profile_name(int i);
+int gzb_profile_get(gzb_ctx* ctx, int i, double* ms, unsigned long long* launches);
+int gzb_profile_reset(gzb_ctx* ctx);
+/* Host->device and device->host bytes moved by this context since creation. */
+int gzb_get_transfer_bytes(const gzb_ctx* ctx, unsigned long long* h2d, unsigned long long* d2h);
 
 /* ---- timing of the last call on this context (CUDA events on the context's stream) -------- */
 /* Device milliseconds spent by the kernels of the last gzb_compare / zeroing call. */
