@@ -282,6 +282,7 @@ class EncodeStats(C.Structure):
                 ("write_hist_ms", C.c_double), ("write_code_ms", C.c_double), ("write_encode_ms", C.c_double),
                 ("write_stitch_ms", C.c_double), ("be_weights_ms", C.c_double), ("be_order_ms", C.c_double),
                 ("be_walk_ms", C.c_double), ("be_update_ms", C.c_double), ("create_ms", C.c_double),
+                ("be_codes_ms", C.c_double), ("be_sort_ms", C.c_double), ("be_steps", C.c_ulonglong),
                 ("prepare_ms", C.c_double), ("run_ms", C.c_double), ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong),
                 ("final_score", C.c_double), ("final_distance", C.c_float), ("launches", C.c_ulonglong)]
 

@@ -19,8 +19,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <future>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <string>
 #include <thread>
@@ -277,7 +278,6 @@ struct Encoder {
   float target = 0.f;
   gzb_ctx* ctx = nullptr;
   std::vector<int16_t> orig[3];   // q=1 indices (jpg_in.components[c].coeffs)
-  std::vector<int16_t> cur[3];    // OutputImage coefficients (dequantised values)
   std::vector<int16_t> idx[3];    // cur / quant (what the file stores)
   int quant[3][64];
   std::string best_jpeg;
@@ -299,7 +299,7 @@ struct Encoder {
 
   int ncomp_for_output() const {
     for (int c = 1; c < 3; ++c)
-      for (int16_t v : cur[c]) if (v != 0) return 3;
+      for (int16_t v : idx[c]) if (v != 0) return 3;
     return 1;  // SaveToJpegData drops all-zero chroma (output_image.cc:588)
   }
 
@@ -348,19 +348,128 @@ struct Encoder {
     parallel_rows(nb, pool.get(), [&](int b0, int b1) {
       for (int c = 0; c < 3; ++c) {
         const int16_t* o = orig[c].data();
-        int16_t* cu = cur[c].data();
         int16_t* ix = idx[c].data();
         for (size_t i = static_cast<size_t>(b0) * 64; i < static_cast<size_t>(b1) * 64; ++i) {
           const int qq = q[c][i & 63];
-          const int16_t v = quantize_coeff(o[i], qq);
-          cu[i] = v;
-          ix[i] = static_cast<int16_t>(v / qq);
+          ix[i] = static_cast<int16_t>(quantize_coeff(o[i], qq) / qq);
         }
       }
     });
     st.host_quant_ms += now_ms() - t0;
     return true;
   }
+};
+
+
+// ScoreJPEG (guetzli/score.cc:23-41) for a given distance (the writer stage scores a file after the
+// comparator has moved on to the next iteration).
+double score_jpeg(double distance, int size, double target) {
+  const double diff = distance - target;
+  if (diff <= 0.0) return size;
+  const double ex = 50 * diff;
+  if (ex > 10) return 1e30 * std::exp(10.0) * diff + size;
+  return std::exp(ex) * size;
+}
+
+// One back-end iteration's file: the coefficient flips to apply, the AC histograms after them, and
+// what MaybeOutput needs.
+struct WriteJob {
+  std::vector<int32_t> block;
+  std::vector<uint8_t> cidx;
+  std::vector<int16_t> val, newidx;
+  Histogram ac_hist[3];
+  std::string log_head;
+  int est_jpg_size = 0;
+  float distance = 0.f, score_target = 0.f;
+  void add(int b, uint8_t ci, int16_t v, int16_t ni) { block.push_back(b); cidx.push_back(ci); val.push_back(v); newidx.push_back(ni); }
+  void clear() { block.clear(); cidx.clear(); val.clear(); newidx.clear(); log_head.clear(); }
+};
+
+// Writes each iteration's JPEG on its own thread (with its own worker pool and its own copy of the
+// quantised indices), in iteration order, and performs MaybeOutput there. The search thread only
+// waits when two files are already in flight.
+class WriterStage {
+ public:
+  WriterStage(Encoder* e, const Histogram* dc_hist) : e_(e), pool_(std::max(1, e->nthreads - 1)) {
+    for (int c = 0; c < 3; ++c) { idx_[c] = e->idx[c]; dc_hist_[c] = dc_hist[c]; }
+    thread_ = std::thread(&WriterStage::loop, this);
+  }
+  ~WriterStage() { abort(); }
+  WriteJob* new_job() {
+    std::unique_lock<std::mutex> l(mu_);
+    cv_.wait(l, [&] { return !free_.empty() || jobs_made_ < 3; });
+    WriteJob* j;
+    if (!free_.empty()) { j = free_.back(); free_.pop_back(); }
+    else { store_.emplace_back(new WriteJob); j = store_.back().get(); ++jobs_made_; }
+    j->clear();
+    return j;
+  }
+  void submit(WriteJob* j) {
+    { std::lock_guard<std::mutex> l(mu_); queue_.push_back(j); }
+    cv_.notify_all();
+  }
+  void finish() {
+    { std::lock_guard<std::mutex> l(mu_); done_ = true; }
+    cv_.notify_all();
+    if (thread_.joinable()) thread_.join();
+  }
+  void abort() { finish(); }
+
+ private:
+  void loop() {
+    for (;;) {
+      WriteJob* j;
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [&] { return !queue_.empty() || done_; });
+        if (queue_.empty()) return;
+        j = queue_.front();
+        queue_.erase(queue_.begin());
+      }
+      const double t0 = now_ms();
+      for (size_t i = 0; i < j->block.size(); ++i)
+        idx_[j->cidx[i] >> 6][static_cast<size_t>(j->block[i]) * 64 + (j->cidx[i] & 63)] = j->newidx[i];
+      Frame f;
+      f.width = e_->w; f.height = e_->h; f.bw = e_->bw; f.bh = e_->bh;
+      f.ncomp = 1;
+      for (int c = 1; c < 3 && f.ncomp == 1; ++c)
+        for (int16_t v : idx_[c]) if (v != 0) { f.ncomp = 3; break; }
+      for (int c = 0; c < 3; ++c) f.coeffs[c] = idx_[c].data();
+      gzb::jpeg::frame_set_quant(&f, e_->quant);
+      std::string jpg;
+      gzb::jpeg::write_jpeg(f, &jpg, &pool_, dc_hist_, j->ac_hist, &e_->wt);
+      e_->st.host_write_ms += now_ms() - t0;
+      e_->st.num_jpeg_writes++;
+      // GUETZLI_LOG lines of processor.cc:905-913, butteraugli_comparator.cc:69, MaybeOutput 151-160
+      e_->log("%s Out[%7zd] EstErr[%.2f%%]", j->log_head.c_str(), jpg.size(),
+              100.0 - (100.0 * j->est_jpg_size) / jpg.size());
+      e_->log(" BA[100.00%%] D[%6.4f]", j->distance);
+      const double score = score_jpeg(j->distance, static_cast<int>(jpg.size()), j->score_target);
+      e_->log(" Score[%.4f]", score);
+      if (score < e_->best_score || e_->best_score < 0) {
+        e_->best_jpeg.swap(jpg);
+        e_->best_score = score;
+        e_->log(" (*)");
+      }
+      e_->log("\n");
+      {
+        std::lock_guard<std::mutex> l(mu_);
+        free_.push_back(j);
+      }
+      cv_.notify_all();
+    }
+  }
+  Encoder* e_;
+  gzb::WorkerPool pool_;
+  std::vector<int16_t> idx_[3];
+  Histogram dc_hist_[3];
+  std::thread thread_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::vector<WriteJob*> queue_, free_;
+  std::vector<std::unique_ptr<WriteJob>> store_;
+  int jobs_made_ = 0;
+  bool done_ = false;
 };
 
 }  // namespace
@@ -428,6 +537,29 @@ long gzb_write_jpeg(const int16_t* c0, const int16_t* c1, const int16_t* c2, int
   return static_cast<long>(s.size());
 }
 
+// Micro-benchmark hook: repeated WriteJpeg of one frame of quantised indices; returns ms per write
+// and fills parts[4] = {hist, code, encode, stitch} ms per write.
+double gzb_bench_write_jpeg(const int16_t* c0, const int16_t* c1, const int16_t* c2, int width, int height,
+                            int host_threads, int reps, int with_hist, double* parts) {
+  const int bw = (width + 7) / 8, bh = (height + 7) / 8;
+  Frame f;
+  f.width = width; f.height = height; f.bw = bw; f.bh = bh; f.ncomp = 3;
+  f.coeffs[0] = c0; f.coeffs[1] = c1; f.coeffs[2] = c2;
+  int q[3][64];
+  for (int c = 0; c < 3; ++c) for (int k = 0; k < 64; ++k) q[c][k] = 1 + c;
+  gzb::jpeg::frame_set_quant(&f, q);
+  gzb::WorkerPool pool(host_threads > 0 ? host_threads : 1);
+  Histogram dc[3], ac[3];
+  gzb::jpeg::build_histograms(f, dc, ac, &pool);
+  gzb::jpeg::WriteTimers tm;
+  std::string s;
+  const double t0 = now_ms();
+  for (int r = 0; r < reps; ++r) gzb::jpeg::write_jpeg(f, &s, &pool, with_hist ? dc : nullptr, with_hist ? ac : nullptr, &tm);
+  const double dt = (now_ms() - t0) / reps;
+  if (parts) { parts[0] = tm.hist_ms / reps; parts[1] = tm.code_ms / reps; parts[2] = tm.encode_ms / reps; parts[3] = tm.stitch_ms / reps; }
+  return dt;
+}
+
 // Test hooks: the lazy order must equal std::sort's permutation on the consumed prefix.
 void gzb_test_lazy_sort(int* first, float* second, size_t n, size_t prefix) {
   std::vector<OrderEntry> v(n);
@@ -468,7 +600,7 @@ int gzb_encoder_create(int device, const uint8_t* rgb, int width, int height, fl
   e.nthreads = host_threads > 0 ? host_threads : static_cast<int>(std::max(1u, std::min(16u, hc)));
   e.pool.reset(new gzb::WorkerPool(e.nthreads));
   const size_t ncoef = static_cast<size_t>(e.nb) * 64;
-  for (int c = 0; c < 3; ++c) { e.orig[c].resize(ncoef); e.cur[c].resize(ncoef); e.idx[c].resize(ncoef); }
+  for (int c = 0; c < 3; ++c) { e.orig[c].resize(ncoef); e.idx[c].resize(ncoef); }
   const double t_create = now_ms();
   int rc = gzb_create(device, width, height, rgb, butteraugli_target, &e.ctx);
   if (rc != GZB_OK) { g_encode_err = gzb_last_error(nullptr); delete enc; return rc; }
@@ -619,6 +751,15 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         dc_size = static_cast<int>(gzb::jpeg::cluster_histograms(tmp, &num, ix, dd));
       }
     }
+    // zig-zag non-zero masks of every block: a coefficient flip then touches O(1) symbols
+    std::vector<uint64_t> zmask[3];
+    for (int c = 0; c < 3; ++c) zmask[c].resize(num_blocks);
+    parallel_rows(num_blocks, e.pool.get(), [&](int b0, int b1) {
+      for (int c = 0; c < 3; ++c)
+        for (int b = b0; b < b1; ++b) zmask[c][b] = gzb::jpeg::zigzag_nonzero_mask(e.idx[c].data() + static_cast<size_t>(b) * 64);
+    });
+    // the writer works on its own copy of the indices so that it can overlap the next iteration
+    WriterStage writer(&e, dc_hist);
     std::vector<uint8_t> ac_depths(3 * Histogram::kSize);
     // ComputeEntropyCodes (processor.cc:517-536)
     auto compute_entropy_codes = [&]() -> size_t {
@@ -658,11 +799,12 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
     std::vector<int> last_indexes(num_blocks);
     std::vector<float> block_weight(num_blocks);
     std::vector<OrderEntry> global_order;
-    std::vector<int32_t> upd_block;
-    std::vector<uint8_t> upd_idx;
-    std::vector<int16_t> upd_val;
+    std::vector<uint8_t> touched(num_blocks, 0);
+    std::vector<int> touched_list;
     bool first_up_iter = true;
     const int directions[2] = {1, -1};
+    const int n_cerr = static_cast<int>(cand_errors.size());
+    const int n_ccoef = static_cast<int>(cand_coeffs.size());
     for (int direction : directions) {
       for (;;) {
         int blocks_to_change = 0;
@@ -673,24 +815,53 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           if (gzb_compute_block_error_adjustment_weights(e.ctx, direction, rblock, target_mul, nullptr,
                                                          block_weight.data()) != GZB_OK) return fail(GZB_ERR_CUDA);
           { const double t1 = now_ms(); e.st.be_weights_ms += t1 - tt; tt = t1; }
-          global_order.clear();
-          blocks_to_change = 0;
-          for (int b = 0; b < num_blocks; ++b) {
-            const int last_index = last_indexes[b];
-            const int offset = std::max(0, std::min(cand_offsets[b], static_cast<int>(cand_errors.size()) - 1));
-            const int num_candidates = cand_offsets[b + 1] - offset;
-            const float* errs = cand_errors.data() + offset;
-            const float max_err = max_block_error[b];
-            if (block_weight[b] == 0) continue;
-            if (direction > 0) {
-              for (int i = last_index; i < num_candidates; ++i)
-                global_order.push_back(std::make_pair(b, (errs[i] - max_err) / block_weight[b]));
-              blocks_to_change += last_index < num_candidates ? 1 : 0;
-            } else {
-              for (int i = last_index - 1; i >= 0; --i)
-                global_order.push_back(std::make_pair(b, (max_err - errs[i]) / block_weight[b]));
-              blocks_to_change += last_index > 0 ? 1 : 0;
-            }
+          // global_order in block order (processor.cc:786-813), built in parallel: count, then fill
+          {
+            const int T = std::max(1, std::min(e.pool->size(), num_blocks / 1024 + 1));
+            std::vector<size_t> cnt(T + 1, 0);
+            std::vector<int> btc(T, 0);
+            auto range = [&](int t, int* b0, int* b1) {
+              *b0 = static_cast<int>(static_cast<int64_t>(num_blocks) * t / T);
+              *b1 = static_cast<int>(static_cast<int64_t>(num_blocks) * (t + 1) / T);
+            };
+            auto count_block = [&](int b) -> int {
+              if (block_weight[b] == 0) return 0;
+              const int offset = std::max(0, std::min(cand_offsets[b], n_cerr - 1));
+              const int num_candidates = cand_offsets[b + 1] - offset;
+              return direction > 0 ? std::max(0, num_candidates - last_indexes[b]) : std::max(0, last_indexes[b]);
+            };
+            e.pool->run(T, [&](int t) {
+              int b0, b1;
+              range(t, &b0, &b1);
+              size_t n = 0;
+              int k = 0;
+              for (int b = b0; b < b1; ++b) { const int cb = count_block(b); n += cb; k += cb > 0; }
+              cnt[t + 1] = n;
+              btc[t] = k;
+            });
+            for (int t = 0; t < T; ++t) cnt[t + 1] += cnt[t];
+            global_order.resize(cnt[T]);
+            blocks_to_change = 0;
+            for (int t = 0; t < T; ++t) blocks_to_change += btc[t];
+            e.pool->run(T, [&](int t) {
+              int b0, b1;
+              range(t, &b0, &b1);
+              OrderEntry* o = global_order.data() + cnt[t];
+              for (int b = b0; b < b1; ++b) {
+                if (block_weight[b] == 0) continue;
+                const int last_index = last_indexes[b];
+                const int offset = std::max(0, std::min(cand_offsets[b], n_cerr - 1));
+                const int num_candidates = cand_offsets[b + 1] - offset;
+                const float* errs = cand_errors.data() + offset;
+                const float max_err = max_block_error[b];
+                const float wgt = block_weight[b];
+                if (direction > 0) {
+                  for (int i = last_index; i < num_candidates; ++i) *o++ = std::make_pair(b, (errs[i] - max_err) / wgt);
+                } else {
+                  for (int i = last_index - 1; i >= 0; --i) *o++ = std::make_pair(b, (max_err - errs[i]) / wgt);
+                }
+              }
+            });
           }
           { const double t1 = now_ms(); e.st.be_order_ms += t1 - tt; tt = t1; }
           if (!global_order.empty()) break;
@@ -711,59 +882,99 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           min_coeffs_to_change = std::max<int>(min_coeffs_to_change, static_cast<int>(below));
           first_up_iter = false;
         }
-        std::set<int> changed_blocks;
         float val_threshold = 0.0;
         int changed_coeffs = 0;
         int est_jpg_size = prev_size;
-        upd_block.clear(); upd_idx.clear(); upd_val.clear();
+        WriteJob* job = writer.new_job();
         const size_t order_size = global_order.size();
+        const size_t kAhead = 24;
         for (size_t i = 0; i < order_size; ++i) {
-          sorter.ensure(i);
+          if (sorter.sorted() <= std::min(i + kAhead, order_size - 1)) {
+            const double ts = now_ms();
+            sorter.ensure(std::min(i + kAhead, order_size - 1));
+            e.st.be_sort_ms += now_ms() - ts;
+          }
+          // three-stage software prefetch of the randomly scattered per-block state
+          if (i + kAhead < order_size) {
+            const int pb = global_order[i + kAhead].first;
+            __builtin_prefetch(&last_indexes[pb]);
+            __builtin_prefetch(&cand_offsets[pb]);
+          }
+          if (i + kAhead / 2 < order_size) {
+            const int pb = global_order[i + kAhead / 2].first;
+            const int po = std::max(0, std::min(cand_offsets[pb], n_ccoef - 1));
+            __builtin_prefetch(&cand_coeffs[po + std::max(0, last_indexes[pb] + std::min(direction, 0))]);
+          }
+          if (i + kAhead / 4 < order_size) {
+            const int pb = global_order[i + kAhead / 4].first;
+            const int po = std::max(0, std::min(cand_offsets[pb], n_ccoef - 1));
+            const int pi = cand_coeffs[po + std::max(0, last_indexes[pb] + std::min(direction, 0))];
+            const int pc = pi >> 6;
+            __builtin_prefetch(&zmask[pc][pb]);
+            __builtin_prefetch(e.idx[pc].data() + static_cast<size_t>(pb) * 64);
+            __builtin_prefetch(e.idx[pc].data() + static_cast<size_t>(pb) * 64 + 32);
+            if (direction < 0) __builtin_prefetch(e.orig[pc].data() + static_cast<size_t>(pb) * 64 + (pi & 63));
+          }
           const int b = global_order[i].first;
           const int last_idx = last_indexes[b];
-          const int offset = std::max(0, std::min(cand_offsets[b], static_cast<int>(cand_coeffs.size()) - 1));
+          const int offset = std::max(0, std::min(cand_offsets[b], n_ccoef - 1));
           const uint8_t* candidates = cand_coeffs.data() + offset;
-          const int idx = candidates[last_idx + std::min(direction, 0)];
-          const int c = idx / 64, k = idx % 64;
+          const int cidx = candidates[last_idx + std::min(direction, 0)];
+          const int c = cidx / 64, k = cidx % 64, z = gzb::jpeg::kZigZag[k];
           const int* qc = e.quant[c];
-          int16_t* blk = e.cur[c].data() + static_cast<size_t>(b) * 64;
           int16_t* blk_idx = e.idx[c].data() + static_cast<size_t>(b) * 64;
           const int16_t newval = direction > 0 ? 0 : quantize_coeff(e.orig[c][static_cast<size_t>(b) * 64 + k], qc[k]);
-          // UpdateACHistogram(-1, old) ; UpdateACHistogram(+1, new) (processor.cc:491-515, 871-873),
-          // with the cached raw bit sums following the histogram
-          auto apply = [&](int weight) {
-            int run = 0;
-            Histogram& hh = ac_hist[c];
-            const uint8_t* d = &ac_depths[c * Histogram::kSize];
-            for (int z = 1; z < 64; ++z) {
-              const int v = blk_idx[gzb::jpeg::kNaturalOrder[z]];
-              if (v == 0) { ++run; continue; }
-              while (run > 15) { hh.add(0xf0, weight); raw_bits[c] += static_cast<int64_t>(weight) * (d[0xf0] + 0); run -= 16; }
-              const int nbits = 32 - __builtin_clz(static_cast<unsigned>(std::abs(v)));
-              const int sym = (run << 4) + nbits;
-              hh.add(sym, weight);
-              raw_bits[c] += static_cast<int64_t>(weight) * (d[sym] + (sym & 0xf));
-              run = 0;
-            }
-            if (run > 0) { hh.add(0, weight); raw_bits[c] += static_cast<int64_t>(weight) * d[0]; }
+          const int16_t new_idx = static_cast<int16_t>(newval / qc[k]);
+          const int16_t old_idx = blk_idx[k];
+          // UpdateACHistogram(-1, old block); UpdateACHistogram(+1, new block) (processor.cc:491-515,
+          // 871-873) restricted to the symbols that differ: those between the previous (p) and the
+          // next (n) non-zero coefficient around zig-zag position z.
+          uint64_t& m = zmask[c][b];
+          const uint64_t lower = m & ((1ULL << z) - 1);
+          const int p = lower ? 63 - __builtin_clzll(lower) : 0;
+          const uint64_t upper = z < 63 ? (m >> (z + 1)) : 0;
+          const int n = upper ? z + 1 + __builtin_ctzll(upper) : 64;
+          const int v_n = n < 64 ? blk_idx[gzb::jpeg::kNaturalOrder[n]] : 0;
+          Histogram& hh = ac_hist[c];
+          const uint8_t* d = &ac_depths[c * Histogram::kSize];
+          auto add_sym = [&](int sym, int weight) {
+            hh.add(sym, weight);
+            raw_bits[c] += static_cast<int64_t>(weight) * (d[sym] + (sym & 0xf));
           };
-          apply(-1);
-          blk[k] = newval;
-          blk_idx[k] = static_cast<int16_t>(newval / qc[k]);
-          apply(1);
-          upd_block.push_back(b); upd_idx.push_back(static_cast<uint8_t>(idx)); upd_val.push_back(newval);
+          auto add_run = [&](int run, int v, int weight) {
+            while (run > 15) { add_sym(0xf0, weight); run -= 16; }
+            add_sym((run << 4) + (32 - __builtin_clz(static_cast<unsigned>(std::abs(v)))), weight);
+          };
+          auto emit = [&](int v_z, int weight) {
+            if (v_z != 0) {
+              add_run(z - p - 1, v_z, weight);
+              if (n < 64) add_run(n - z - 1, v_n, weight);
+              else if (z != 63) add_sym(0, weight);
+            } else {
+              if (n < 64) add_run(n - p - 1, v_n, weight);
+              else add_sym(0, weight);
+            }
+          };
+          emit(old_idx, -1);
+          emit(new_idx, 1);
+          blk_idx[k] = new_idx;
+          if (new_idx != 0) m |= 1ULL << z; else m &= ~(1ULL << z);
+          job->add(b, static_cast<uint8_t>(cidx), newval, new_idx);
           last_indexes[b] += direction;
-          changed_blocks.insert(b);
+          if (!touched[b]) { touched[b] = 1; touched_list.push_back(b); }
           val_threshold = global_order[i].second;
           ++changed_coeffs;
+          ++e.st.be_steps;
           if (i % 10 == 0) {
             // Evaluate only where the result can be observed: by the break test within the next 10
             // steps, or as prev_size when the order is about to run out.
             const bool needed = static_cast<long long>(i) + 9 >= min_coeffs_to_change ||
                                 i + 9 >= order_size - 1;
             if (needed) {
+              const double tb = now_ms();
               ac_histogram_size = static_cast<int>(compute_entropy_codes());
               recount_bits();
+              e.st.be_codes_ms += now_ms() - tb;
             }
           }
           if (changed_coeffs > min_coeffs_to_change || i + 1 == order_size) {
@@ -771,27 +982,34 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
             if (changed_coeffs > min_coeffs_to_change && std::abs(est_jpg_size - prev_size) > min_size_delta) break;
           }
         }
+        const size_t changed_blocks = touched_list.size();
+        for (int tb : touched_list) touched[tb] = 0;
+        touched_list.clear();
         for (int i = 0; i < num_blocks; ++i) max_block_error[i] += block_weight[i] * val_threshold * direction;
         { const double t1 = now_ms(); e.st.be_walk_ms += t1 - tt; tt = t1; }
         ++e.st.num_iterations;
         if (direction > 0) ++e.st.num_iterations_up; else ++e.st.num_iterations_down;
-        // push the changed coefficients to the device, write the file while the GPU compares
-        if (gzb_update_coeffs(e.ctx, upd_block.data(), upd_idx.data(), upd_val.data(), upd_block.size()) != GZB_OK)
+        // push the changed coefficients to the device; the file is written by the writer stage while
+        // the GPU compares and the next iteration walks
+        if (gzb_update_coeffs(e.ctx, job->block.data(), job->cidx.data(), job->val.data(), job->block.size()) != GZB_OK)
           return fail(GZB_ERR_CUDA);
         { const double t1 = now_ms(); e.st.be_update_ms += t1 - tt; tt = t1; }
-        std::string jpg;
+        for (int c = 0; c < 3; ++c) job->ac_hist[c] = ac_hist[c];
         const bool ok = e.compare(true);
-        e.write_candidate(&jpg, dc_hist, ac_hist);
-        if (!ok) return fail(GZB_ERR_CUDA);
-        e.log("Iter %2d: f111111(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
-              e.st.num_iterations, comp_mask, direction > 0 ? "up" : "down", changed_coeffs, order_size,
-              changed_blocks.size(), blocks_to_change, num_blocks, val_threshold, jpg.size(),
-              100.0 - (100.0 * est_jpg_size) / jpg.size());
-        e.log(" BA[100.00%%] D[%6.4f]", e.distance);
-        e.maybe_output(jpg);
+        if (!ok) { writer.abort(); return fail(GZB_ERR_CUDA); }
+        char head[256];
+        snprintf(head, sizeof(head), "Iter %2d: f111111(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f]",
+                 e.st.num_iterations, comp_mask, direction > 0 ? "up" : "down", changed_coeffs, order_size,
+                 changed_blocks, blocks_to_change, num_blocks, val_threshold);
+        job->log_head = head;
+        job->est_jpg_size = est_jpg_size;
+        job->distance = e.distance;
+        job->score_target = e.target;
+        writer.submit(job);
         prev_size = est_jpg_size;
       }
     }
+    writer.finish();
     e.st.backend_wall_ms = now_ms() - t_be;
   }
 

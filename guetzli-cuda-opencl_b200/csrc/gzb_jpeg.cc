@@ -124,16 +124,27 @@ size_t cluster_histograms(Histogram* histo, size_t* num, int* indexes, uint8_t* 
   return (total + 7) / 8;
 }
 
+// Bit k (1..63) set iff the coefficient at zig-zag position k is non-zero. Branch-free: the
+// zero/non-zero pattern of real coefficient data is what makes a per-coefficient branch slow.
+uint64_t zigzag_nonzero_mask(const int16_t* q) {
+  uint64_t m = 0;
+#pragma GCC unroll 63
+  for (int k = 1; k < 64; ++k) m |= static_cast<uint64_t>(q[kNaturalOrder[k]] != 0) << k;
+  return m;
+}
+
 void ac_histogram_add_block(const int16_t* q, int weight, Histogram* h) {
-  int run = 0;
-  for (int k = 1; k < 64; ++k) {
-    const int v = q[kNaturalOrder[k]];
-    if (v == 0) { ++run; continue; }
+  uint64_t m = zigzag_nonzero_mask(q);
+  int prev = 0;
+  while (m) {
+    const int k = __builtin_ctzll(m);
+    m &= m - 1;
+    int run = k - prev - 1;
+    prev = k;
     while (run > 15) { h->add(0xf0, weight); run -= 16; }
-    h->add((run << 4) + bit_length(static_cast<uint32_t>(std::abs(v))), weight);
-    run = 0;
+    h->add((run << 4) + bit_length(static_cast<uint32_t>(std::abs(static_cast<int>(q[kNaturalOrder[k]])))), weight);
   }
-  if (run > 0) h->add(0, weight);
+  if (prev != 63) h->add(0, weight);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -242,19 +253,44 @@ void make_code(const uint8_t* depth257, int counts[17], int values[257], CodeTab
 }
 
 // MSB-first bit accumulator without byte stuffing (stuffing is applied when bands are stitched).
+// Bits collect in a 64-bit register and leave 32 at a time into a buffer that the caller keeps
+// large enough (reserve() before every block).
 struct BitBuf {
-  std::vector<uint8_t> bytes;
+  std::vector<uint8_t> bytes;   // valid prefix: [0, size_) after finish()
+  uint8_t* ptr = nullptr;
   uint64_t acc = 0;
-  int nacc = 0;  // bits held in acc (< 8 after flush)
+  int nacc = 0;                 // bits held in acc
   size_t total_bits = 0;
-  inline void put(int nbits, uint32_t bits) {
+  void reserve(size_t extra) {
+    const size_t used = ptr ? static_cast<size_t>(ptr - bytes.data()) : 0;
+    if (bytes.size() < used + extra) {
+      bytes.resize(std::max(bytes.size() * 2, used + extra + 4096));
+      ptr = bytes.data() + used;
+    }
+    if (!ptr) ptr = bytes.data();
+  }
+  inline void put(int nbits, uint64_t bits) {  // nbits <= 32
     acc = (acc << nbits) | bits;
     nacc += nbits;
-    total_bits += nbits;
+    if (nacc >= 32) {
+      nacc -= 32;
+      const uint32_t w = __builtin_bswap32(static_cast<uint32_t>(acc >> nacc));
+      memcpy(ptr, &w, 4);
+      ptr += 4;
+    }
+  }
+  // Leaves whole bytes in `bytes` and the remaining (< 8) bits in acc/nacc.
+  void finish() {
+    size_t used = ptr ? static_cast<size_t>(ptr - bytes.data()) : 0;
+    total_bits = used * 8 + nacc;
+    reserve(8);
     while (nacc >= 8) {
       nacc -= 8;
-      bytes.push_back(static_cast<uint8_t>(acc >> nacc));
+      *ptr++ = static_cast<uint8_t>(acc >> nacc);
     }
+    used = static_cast<size_t>(ptr - bytes.data());
+    bytes.resize(used);
+    ptr = nullptr;
   }
 };
 
@@ -262,10 +298,11 @@ void encode_band(const Frame& f, const CodeTable* dc, const CodeTable* ac, int b
   int last_dc[3] = {0, 0, 0};
   if (by0 > 0)
     for (int c = 0; c < f.ncomp; ++c) last_dc[c] = f.coeffs[c][(static_cast<size_t>(by0) * f.bw - 1) * 64];
-  out->bytes.reserve(static_cast<size_t>(by1 - by0) * f.bw * 24);
+  // code and magnitude bits of a symbol merged into one put: (code << nbits) | lowbits
   for (int by = by0; by < by1; ++by)
     for (int bx = 0; bx < f.bw; ++bx) {
       const size_t b = static_cast<size_t>(by) * f.bw + bx;
+      out->reserve(static_cast<size_t>(f.ncomp) * 64 * 4 + 16);
       for (int c = 0; c < f.ncomp; ++c) {
         const int16_t* q = f.coeffs[c] + b * 64;
         const CodeTable& dct = dc[c];
@@ -276,24 +313,28 @@ void encode_band(const Frame& f, const CodeTable* dc, const CodeTable* ac, int b
         if (diff < 0) { mag = -diff; low = diff - 1; }
         mag = static_cast<int16_t>(mag);
         int nbits = bit_length(static_cast<uint32_t>(mag));
-        out->put(dct.depth[nbits], dct.code[nbits]);
-        if (nbits > 0) out->put(nbits, static_cast<uint32_t>(low) & ((1u << nbits) - 1));
-        int run = 0;
-        for (int k = 1; k < 64; ++k) {
+        out->put(dct.depth[nbits] + nbits,
+                 (static_cast<uint64_t>(dct.code[nbits]) << nbits) | (static_cast<uint32_t>(low) & ((1u << nbits) - 1)));
+        uint64_t m = zigzag_nonzero_mask(q);
+        int prev = 0;
+        while (m) {
+          const int k = __builtin_ctzll(m);
+          m &= m - 1;
+          int run = k - prev - 1;
+          prev = k;
           const int v = q[kNaturalOrder[k]];
-          if (v == 0) { ++run; continue; }
           const int a = v < 0 ? -v : v;
-          const int lowbits = v < 0 ? ~a : a;
+          const int lowbits = v + (v >> 31);  // v < 0 ? ~a : a
           while (run > 15) { out->put(act.depth[0xf0], act.code[0xf0]); run -= 16; }
           nbits = bit_length(static_cast<uint32_t>(a));
           const int sym = (run << 4) + nbits;
-          out->put(act.depth[sym], act.code[sym]);
-          out->put(nbits, static_cast<uint32_t>(lowbits) & ((1u << nbits) - 1));
-          run = 0;
+          out->put(act.depth[sym] + nbits,
+                   (static_cast<uint64_t>(act.code[sym]) << nbits) | (static_cast<uint32_t>(lowbits) & ((1u << nbits) - 1)));
         }
-        if (run > 0) out->put(act.depth[0], act.code[0]);
+        if (prev != 63) out->put(act.depth[0], act.code[0]);
       }
     }
+  out->finish();
 }
 
 inline void emit_stuffed(std::string* out, uint8_t b) {

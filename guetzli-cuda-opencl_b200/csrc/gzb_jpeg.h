@@ -71,6 +71,7 @@ size_t entropy_cost_bits(const Histogram& h, const uint8_t* depth);  // Histogra
 // ClusterHistograms: merges trailing histograms while that is cheaper; returns bytes.
 size_t cluster_histograms(Histogram* histo, size_t* num, int* indexes, uint8_t* depth);
 
+uint64_t zigzag_nonzero_mask(const int16_t* q);
 // AC symbols of one block of QUANTISED indices in natural order (UpdateACHistogramForDCTBlock).
 void ac_histogram_add_block(const int16_t* q, int weight, Histogram* h);
 

@@ -147,6 +147,8 @@ typedef struct {
   double compare_wall_ms, device_compare_ms, zeroing_wall_ms, device_zeroing_ms, backend_wall_ms;
   double write_hist_ms, write_code_ms, write_encode_ms, write_stitch_ms;   /* parts of host_write_ms */
   double be_weights_ms, be_order_ms, be_walk_ms, be_update_ms, create_ms;  /* parts of the back end */
+  double be_codes_ms, be_sort_ms;        /* inside be_walk_ms: entropy-code rebuilds, lazy sort */
+  unsigned long long be_steps;           /* coefficients flipped by the back end */
   double prepare_ms, run_ms;             /* gzb_encoder_create / gzb_encoder_run wall time */
   unsigned long long h2d_bytes, d2h_bytes; /* host<->device traffic of the whole encode */
   double final_score;
