@@ -735,7 +735,7 @@ static int run_zeroing(gzb_ctx* c, int comp_mask, int mode) {
   CK(cudaEventRecord(c->ev0, c->stream));
   KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<ctas, 32 * kZeroWarps, 0, c->stream>>>(
       c->d_orig, c->d_coef, cs, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, c->nblocks, c->d_mask_scale, comp_mask,
-      c->target, 3, mode, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1));
+      c->target, 3, mode, 0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1));
   CK(cudaEventRecord(c->ev1, c->stream));
   return 0;
 }
@@ -765,6 +765,23 @@ int gzb_compare_blocks(gzb_ctx* c, float* err_out) {
   GZB_END(c)
 }
 
+int gzb_compare_block(gzb_ctx* c, int block_x, int block_y, const int16_t* candidate192, double* err) {
+  GZB_TRY(c)
+  if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_compare_block: StartBlockComparisons not called");
+  if (!candidate192 || !err || block_x < 0 || block_x >= c->bw || block_y < 0 || block_y >= c->bh)
+    return fail(c, GZB_ERR_BAD_ARG, "gzb_compare_block: bad argument");
+  int16_t* d_cand = reinterpret_cast<int16_t*>(c->d_upd);  // 384 bytes of the update staging area
+  CK(cudaMemcpyAsync(d_cand, candidate192, 192 * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += 384;
+  CK(cudaMemsetAsync(c->d_scalars + 1, 0, sizeof(unsigned int), c->stream));
+  KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<1, 32 * kZeroWarps, 0, c->stream>>>(
+      d_cand, d_cand, 64, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, 1, c->d_mask_scale, 7, c->target, 3, 2,
+      block_y * c->bw + block_x, nullptr, c->d_block_err, nullptr, c->d_scalars + 1));
+  CK(cudaMemcpyAsync(c->h_pinned, c->d_block_err, sizeof(float), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 4;
+  sync_check(c);
+  *err = static_cast<double>(c->h_pinned[0]);
+  GZB_END(c)
+}
+
 int gzb_compute_block_zeroing_order(gzb_ctx* c, int comp_mask, gzb_coeff_data* out) {
   GZB_TRY(c)
   if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_compute_block_zeroing_order: StartBlockComparisons not called");
@@ -780,16 +797,17 @@ int gzb_compute_block_zeroing_order(gzb_ctx* c, int comp_mask, gzb_coeff_data* o
 int gzb_compute_block_error_adjustment_weights(gzb_ctx* c, int direction, int max_block_dist, double target_mul,
                                                const float* distmap, float* block_weight) {
   GZB_TRY(c)
-  if (distmap) {
-    CK(cudaMemcpy2DAsync(c->d_diffmap, c->P * sizeof(float), distmap, c->W * sizeof(float), c->W * sizeof(float), c->H,
-                         cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (static_cast<unsigned long long>(c->W * sizeof(float)) * (c->H));
-    c->have_distmap = false;  // the resident map no longer belongs to the last Compare
+  const float* dm = c->d_diffmap;
+  if (distmap) {  // a caller-provided map is staged in the blur scratch; the resident map is kept
+    CK(cudaMemcpy2DAsync(c->d_tmp, c->P * sizeof(float), distmap, c->W * sizeof(float), c->W * sizeof(float), c->H,
+                         cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += static_cast<unsigned long long>(c->W * sizeof(float)) * (c->H);
+    dm = c->d_tmp;
   } else if (!c->have_distmap) {
     return fail(c, GZB_ERR_STATE, "gzb_compute_block_error_adjustment_weights: no distance map");
   }
   const double target = static_cast<double>(c->target) * target_mul;
   const int g = (c->nblocks + 255) / 256;
-  KLAUNCH(c, KC_WEIGHTS, k_block_max<<<g, 256, 0, c->stream>>>(c->d_diffmap, c->P, c->W, c->H, c->bw, c->bh, c->d_bmax));
+  KLAUNCH(c, KC_WEIGHTS, k_block_max<<<g, 256, 0, c->stream>>>(dm, c->P, c->W, c->H, c->bw, c->bh, c->d_bmax));
   KLAUNCH(c, KC_WEIGHTS, k_block_flags<<<g, 256, 0, c->stream>>>(c->d_bmax, c->bw, c->bh, direction, max_block_dist, target, c->d_flags));
   KLAUNCH(c, KC_WEIGHTS, k_block_weights<<<g, 256, 0, c->stream>>>(c->d_flags, c->bw, c->bh, direction, max_block_dist, c->d_weight));
   CK(cudaMemcpyAsync(block_weight, c->d_weight, sizeof(float) * c->nblocks, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(float) * c->nblocks);

@@ -224,85 +224,104 @@ __device__ __forceinline__ double remove_range_around_zero(double v, double rang
 // ButteraugliBlockDiff, warp-cooperative (ba.cc:602-684).
 //   fa, fb : the two 8x8x3 blocks as floats in shared memory, [c*64 + 8*y + x]
 //   ws     : per-warp scratch of kBlockDiffScratchDoubles doubles in shared memory
+//   csf_a / csf_b : kCsf8x8[4 + lane] and kCsf8x8[36] (hoisted by the caller: loop invariant)
 // Returns dc[3], ac[3], edge[3] in ALL lanes. Sequential sums keep the reference's order.
 // All 32 lanes must call. Ends with __syncwarp(); fa/fb are not modified.
+//
+// Shared-memory layout (doubles), padded so that the 64-bit accesses of a half-warp fall into
+// distinct banks: planes [4][8 rows][9] (stride 72 per plane), row spectra re/im [4][56] with bin u
+// at +9u and row r at +r.
 // ---------------------------------------------------------------------------------------------
-constexpr int kBlockDiffScratchDoubles = 4 * 64 + 4 * 5 * 16;  // planes + row spectra (576)
+constexpr int kBdPlane = 72, kBdSpec = 56;
+constexpr int kBlockDiffScratchDoubles = 4 * kBdPlane + 2 * 4 * kBdSpec;  // 736
 
 __device__ __forceinline__ void warp_block_diff(const float* __restrict__ fa,
                                                 const float* __restrict__ fb, double* ws,
-                                                double dc[3], double ac[3], double edge[3]) {
+                                                double csf_a, double csf_b, double dc[3],
+                                                double ac[3], double edge[3]) {
   const int lane = threadIdx.x & 31;
-  double* pl = ws;            // [4][64]: y_avg, x_halfdiff, y_halfdiff, z_halfdiff
-  double* cs = ws + 4 * 64;   // [4][5][8][2]: row spectra, later reused for terms
+  double* pl = ws;                       // [4][72]: y_avg, x_halfdiff, y_halfdiff, z_halfdiff
+  double* sre = ws + 4 * kBdPlane;       // [4][56]
+  double* sim = sre + 4 * kBdSpec;       // [4][56]
 
-  // (1) means and edge means: 15 independent in-order accumulations.
-  double acc = 0.0;
-  if (lane < 3) {
-    const float* a = fa + 64 * lane;
-    const float* b = fb + 64 * lane;
-    for (int i = 0; i < 64; ++i) acc += (static_cast<double>(a[i]) - static_cast<double>(b[i])) / 64;
-  } else if (lane < 15) {
-    const int e = lane - 3, c = e >> 2, side = e & 3;
-    const float* a = fa + 64 * c;
-    const float* b = fb + 64 * c;
-    // side 0: kx==0, 1: ky==0, 2: kx==7, 3: ky==7 (ba.cc:619-626)
-    const int base = side == 0 ? 0 : side == 1 ? 0 : side == 2 ? 7 : 56;
-    const int stride = (side & 1) ? 1 : 8;
-    for (int t = 0; t < 8; ++t) {
-      const int i = base + t * stride;
-      acc += (static_cast<double>(a[i]) - static_cast<double>(b[i])) / 8;
-    }
-  }
-  // (2) average / half-difference planes.
+  // (1) average / half-difference planes (8 values per lane).
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
-    const int i = lane + 32 * k;
+    const int i = lane + 32 * k, o = (i >> 3) * 9 + (i & 7);
     const double a0 = fa[i], b0 = fb[i], a1 = fa[64 + i], b1 = fb[64 + i], a2 = fa[128 + i],
                  b2 = fb[128 + i];
-    pl[i] = (a1 + b1) / 2;
-    pl[64 + i] = (a0 - b0) / 2;
-    pl[128 + i] = (a1 - b1) / 2;
-    pl[192 + i] = (a2 - b2) / 2;
+    pl[o] = (a1 + b1) / 2;
+    pl[kBdPlane + o] = (a0 - b0) / 2;
+    pl[2 * kBdPlane + o] = (a1 - b1) / 2;
+    pl[3 * kBdPlane + o] = (a2 - b2) / 2;
   }
   __syncwarp();
-  // gather the 15 sums into lane 0 and evaluate the DC / edge-DC metric there.
-  double m[15];
+  // (2) means and edge means: 15 independent in-order accumulations. The reference adds
+  // diff/64 (diff/8 for edges) term by term; half-differences are diff/2 exactly and scaling by a
+  // power of two commutes with rounding, so sum(diff/64) == sum(halfdiff)/32 bit for bit.
+  double acc = 0.0;
+  if (lane < 3) {
+    const double* h = pl + (1 + lane) * kBdPlane;
 #pragma unroll
-  for (int i = 0; i < 15; ++i) m[i] = __shfl_sync(0xffffffffu, acc, i);
-  double dcv[3] = {0.0, 0.0, 0.0}, edv[3] = {0.0, 0.0, 0.0};
-  if (lane == 0) {
-    const double mean[3] = {m[0], m[1], m[2]};
-    lowfreq_sq_acc0(mean, kCsf8x8[0], dcv);
+    for (int y = 0; y < 8; ++y)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const double v[3] = {m[3 + e], m[7 + e], m[11 + e]};
-      lowfreq_sq_acc0(v, kCsf8x8[0], edv);
+      for (int x = 0; x < 8; ++x) acc += h[9 * y + x];
+    acc = acc / 32;
+  } else if (lane < 15) {
+    const int e = lane - 3, c = e >> 2, side = e & 3;
+    const double* h = pl + (1 + c) * kBdPlane;
+    // side 0: kx==0, 1: ky==0, 2: kx==7, 3: ky==7 (ba.cc:619-626)
+    const int base = side == 0 ? 0 : side == 1 ? 0 : side == 2 ? 7 : 63;
+    const int stride = (side & 1) ? 1 : 9;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc += h[base + t * stride];
+    acc = acc / 4;
+  }
+  // five low-frequency colour evaluations on lanes 0..4 (0: mean, 1..4: the four edges)
+  double sq[3] = {0.0, 0.0, 0.0};
+  {
+    const int e = lane - 1;
+    const int s0 = lane == 0 ? 0 : 3 + e, s1 = lane == 0 ? 1 : 7 + e, s2 = lane == 0 ? 2 : 11 + e;
+    const double v0 = __shfl_sync(0xffffffffu, acc, s0 & 31);
+    const double v1 = __shfl_sync(0xffffffffu, acc, s1 & 31);
+    const double v2 = __shfl_sync(0xffffffffu, acc, s2 & 31);
+    if (lane < 5) {
+      const double v[3] = {v0, v1, v2};
+      lowfreq_sq_acc0(v, kCsf8x8[0], sq);
     }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    dc[c] = __shfl_sync(0xffffffffu, sq[c], 0);
+    double ed = 0.0;
+#pragma unroll
+    for (int e = 1; e <= 4; ++e) ed += __shfl_sync(0xffffffffu, sq[c], e);
+    edge[c] = ed;
   }
   // (3) row transforms: lane = plane*8 + row.
   {
     const int plane = lane >> 3, row = lane & 7;
     double x[8], re[5], im[5];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = pl[64 * plane + 8 * row + k];
+    for (int k = 0; k < 8; ++k) x[k] = pl[kBdPlane * plane + 9 * row + k];
     rfft8_half(x, re, im);
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
-      cs[((plane * 5 + u) * 8 + row) * 2 + 0] = re[u];
-      cs[((plane * 5 + u) * 8 + row) * 2 + 1] = im[u];
+      sre[plane * kBdSpec + 9 * u + row] = re[u];
+      sim[plane * kBdSpec + 9 * u + row] = im[u];
     }
   }
   __syncwarp();
-  // (4) column transforms: 20 tasks = plane*5 + u; power into pl[plane*64 + 8u + v].
+  // (4) column transforms: 20 tasks = plane*5 + u; power into pl[plane*72 + 8u + v].
   if (lane < 20) {
     const int plane = lane / 5, u = lane - 5 * plane;
-    const double* src = cs + (plane * 5 + u) * 16;
-    double* dst = pl + 64 * plane + 8 * u;
+    const double* cre = sre + plane * kBdSpec + 9 * u;
+    const double* cim = sim + plane * kBdSpec + 9 * u;
+    double* dst = pl + kBdPlane * plane + 8 * u;
     if (u == 0 || u == 4) {
       double x[8], re[5], im[5];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x[k] = src[2 * k];
+      for (int k = 0; k < 8; ++k) x[k] = cre[k];
       rfft8_half(x, re, im);
       if (u == 0) {  // needs v = 4..7 : |F4|, |F5|=|F3|, |F6|=|F2|, |F7|=|F1|
         dst[4] = (re[4] * re[4] + im[4] * im[4]) * 0.000064;
@@ -316,7 +335,7 @@ __device__ __forceinline__ void warp_block_diff(const float* __restrict__ fa,
     } else {
       double re[8], im[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { re[k] = src[2 * k]; im[k] = src[2 * k + 1]; }
+      for (int k = 0; k < 8; ++k) { re[k] = cre[k]; im[k] = cim[k]; }
       cfft8(re, im);
 #pragma unroll
       for (int v = 0; v < 8; ++v) dst[v] = (re[v] * re[v] + im[v] * im[v]) * 0.000064;
@@ -324,12 +343,12 @@ __device__ __forceinline__ void warp_block_diff(const float* __restrict__ fa,
   }
   __syncwarp();
   // (5) per-frequency terms i = 4..36 (lane L -> i = 4+L; lane 0 also i = 36), then in-order sums.
-  double* term = cs;  // [3][33]
+  double* term = sre;  // [3][33]
   for (int i = 4 + lane; i < 37; i += 32) {
-    const double d = kCsf8x8[i];
-    term[i - 4] = d * 64.8 * pl[64 + i];
-    term[66 + i - 4] = d * 2.4 * pl[192 + i];
-    const double ya = sqrt(pl[i]), yh = sqrt(pl[128 + i]);
+    const double d = i == 36 ? csf_b : csf_a;
+    term[i - 4] = d * 64.8 * pl[kBdPlane + i];
+    term[66 + i - 4] = d * 2.4 * pl[3 * kBdPlane + i];
+    const double ya = sqrt(pl[i]), yh = sqrt(pl[2 * kBdPlane + i]);
     const double y0 = remove_range_around_zero(ya - yh, 0.04);
     const double y1 = remove_range_around_zero(ya + yh, 0.04);
     double ty = 0.0;
@@ -345,14 +364,11 @@ __device__ __forceinline__ void warp_block_diff(const float* __restrict__ fa,
   double s = 0.0;
   if (lane < 3) {
     const double* t = term + 33 * lane;
+#pragma unroll
     for (int i = 0; i < 33; ++i) s += t[i];
   }
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    ac[c] = __shfl_sync(0xffffffffu, s, c);
-    dc[c] = __shfl_sync(0xffffffffu, dcv[c], 0);
-    edge[c] = __shfl_sync(0xffffffffu, edv[c], 0);
-  }
+  for (int c = 0; c < 3; ++c) ac[c] = __shfl_sync(0xffffffffu, s, c);
   __syncwarp();
 }
 

@@ -443,6 +443,7 @@ k_block_diff_map(const float* __restrict__ a, const float* __restrict__ b, size_
   __shared__ double s_ws[kBdmWarps][kBlockDiffScratchDoubles];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = ncx * ncy;
+  const double csf_a = kCsf8x8[4 + lane], csf_b = kCsf8x8[36];
   for (int cell = blockIdx.x * kBdmWarps + warp; cell < total; cell += gridDim.x * kBdmWarps) {
     const int ry = cell / ncx, rx = cell - ry * ncx;
     const int ox = min(3 * rx, W - 8), oy = min(3 * ry, H - 8);
@@ -455,7 +456,7 @@ k_block_diff_map(const float* __restrict__ a, const float* __restrict__ b, size_
     }
     __syncwarp();
     double dc[3], ac[3], edge[3];
-    warp_block_diff(s_a[warp], s_b[warp], s_ws[warp], dc, ac, edge);
+    warp_block_diff(s_a[warp], s_b[warp], s_ws[warp], csf_a, csf_b, dc, ac, edge);
     if (lane < 3) {
       const size_t o = 3 * (static_cast<size_t>(ry) * rxs + rx) + lane;
       dc_out[o] = static_cast<float>(lane == 0 ? dc[0] : lane == 1 ? dc[1] : dc[2]);

@@ -82,7 +82,7 @@ __device__ __forceinline__ void warp_block_opsin(const float* lin, float* hb, fl
 // (zidx < 0: the processed block itself). Returns the error in all lanes.
 __device__ __forceinline__ float warp_compare_block(ZeroWarpSmem& s, const float* lut, int zidx,
                                                     int vx, int vy, const float scale[3],
-                                                    int lane) {
+                                                    double csf_a, double csf_b, int lane) {
   const int zc = zidx >= 0 ? zidx >> 6 : -1;
   if (zidx >= 0) {
     const int k = zidx & 63, kx = k & 7, ky = k >> 3;
@@ -146,7 +146,7 @@ __device__ __forceinline__ float warp_compare_block(ZeroWarpSmem& s, const float
   }
   __syncwarp();
   double dc[3], ac[3], edge[3];
-  warp_block_diff(s.bufA, s.bufB, s.ws, dc, ac, edge);
+  warp_block_diff(s.bufA, s.bufB, s.ws, csf_a, csf_b, dc, ac, edge);
   double diff = 0.0, diff_edge = 0.0;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -184,11 +184,13 @@ constexpr int kZeroWarps = 4;
 
 // mode 0: full zeroing order -> out[block*192 + r]
 // mode 1: single CompareBlock of `cur` with no zeroing -> err_out[block] (stage test entry)
+// mode 2: CompareBlock of ONE block `single_block` whose candidate coefficients are the 192 values
+//         at `cur` (comp_stride 64, nblocks 1) -> err_out[0] (Comparator::CompareBlock adaptor)
 __global__ void __launch_bounds__(32 * kZeroWarps)
 k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cur,
                 size_t comp_stride, const uint8_t* __restrict__ rgb_planes, size_t plane_stride,
                 int P, int W, int H, int bw, int nblocks, const float* __restrict__ mask_scale,
-                int comp_mask, float limit, int lookahead, int mode,
+                int comp_mask, float limit, int lookahead, int mode, int single_block,
                 CoeffDataDev* __restrict__ out, float* __restrict__ err_out,
                 float* __restrict__ pregamma_out, unsigned int* __restrict__ counter) {
   __shared__ ZeroWarpSmem sm[kZeroWarps];
@@ -197,6 +199,7 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ZeroWarpSmem& s = sm[warp];
+  const double csf_a = kCsf8x8[4 + lane], csf_b = kCsf8x8[36];
   s.basis[lane] = kIdctBasis[lane];
   s.basis[32 + lane] = kIdctBasis[32 + lane];
   __syncwarp();
@@ -205,7 +208,8 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
     if (lane == 0) b = atomicAdd(counter, 1u);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= static_cast<unsigned int>(nblocks)) break;
-    const int bx = b % bw, by = b / bw;
+    const int blk = mode == 2 ? single_block : static_cast<int>(b);  // image block (b indexes coefficients)
+    const int bx = blk % bw, by = blk / bw;
     const int vx = min(8, W - 8 * bx), vy = min(8, H - 8 * by);
     // ---- load block state ----
 #pragma unroll
@@ -230,9 +234,9 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
     }
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) warp_full_idct(s, c, lane);
-    const float scale[3] = {mask_scale[3 * b], mask_scale[3 * b + 1], mask_scale[3 * b + 2]};
-    if (mode == 1) {
-      const float e = warp_compare_block(s, s_lut, -1, vx, vy, scale, lane);
+    const float scale[3] = {mask_scale[3 * blk], mask_scale[3 * blk + 1], mask_scale[3 * blk + 2]};
+    if (mode >= 1) {
+      const float e = warp_compare_block(s, s_lut, -1, vx, vy, scale, csf_a, csf_b, lane);
       if (lane == 0) err_out[b] = e;
       continue;
     }
@@ -271,7 +275,7 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
       float best_err = 1e17f;
       int best_i = 0;
       for (int i = 0; i < nwin; ++i) {
-        const float err = warp_compare_block(s, s_lut, win[i], vx, vy, scale, lane);
+        const float err = warp_compare_block(s, s_lut, win[i], vx, vy, scale, csf_a, csf_b, lane);
         const float max_err = fmaxf(0.0f, err);
         if (max_err < best_err) { best_err = max_err; best_i = i; }
       }

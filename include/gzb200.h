@@ -101,6 +101,11 @@ int gzb_get_block_lists(gzb_ctx* ctx, float* mask_scale_out, float* opsin_blocks
 /* CompareBlock for every 8x8 block of the resident candidate at once (factor 1, comp_mask 7):
  * err_out[block]. (guetzli/butteraugli_comparator.cc:113-163) */
 int gzb_compare_blocks(gzb_ctx* ctx, float* err_out);
+/* Comparator::CompareBlock after SwitchBlock(block_x, block_y, 1, 1): the error of one 8x8 block
+ * whose candidate coefficients are candidate192 = [Y64 Cb64 Cr64] (dequantised values). One tiny
+ * launch per call -- correct but latency-bound; the batched call below is the fast path.
+ * (guetzli/butteraugli_comparator.cc:85-163) */
+int gzb_compare_block(gzb_ctx* ctx, int block_x, int block_y, const int16_t* candidate192, double* err);
 /* cuComputeBlockZeroingOrder (clguetzli/cuguetzli.h:30-40) == the per-block loop of
  * Processor::SelectFrequencyMasking over ComputeBlockZeroingOrder (guetzli/processor.cc:376-487,
  * 638-672), MODE_CPU semantics. out: nblocks*192 records, zero-filled, packed from slot 0 in

@@ -1,6 +1,7 @@
 // integration/gzb_comparator.cc -- see gzb_comparator.h.
 #include "gzb_comparator.h"
 
+#include <cassert>
 #include <cstdio>
 #include <cstdlib>
 

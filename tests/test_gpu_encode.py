@@ -79,3 +79,45 @@ def test_encode_rejects_bad_input(gz):
         gz.Process(img, 2.5)            # quality < 84 is refused (processor.cc:939-945)
     with pytest.raises(gz.GzbError):
         gz.Process(img[:16, :16], 1.0)  # < 32 px
+
+
+def test_unmodified_reference_processor_drives_b200_comparator(gz):
+    """Drop-in: the reference's own Processor::ProcessJpegData (compiled from /root/reference into
+    oracle/_ref) running against integration/gzb_comparator.cc must emit the reference's bytes."""
+    import ctypes as C
+    import _libs
+    if not _libs.have_ref():
+        pytest.skip("oracle/_ref not present")
+    L = _libs.ref()
+    L.ref_process_rgb_b200.restype = C.c_long
+    gold_all = json.load(open(os.path.join(GOLD, "synth_encodes.json")))
+    for key in ["97x61_q84_s1254", "128x96_q90_s1234"]:
+        gold = gold_all[key]
+        m = re.match(r"(\d+)x(\d+)_q(\d+)_s(\d+)", key)
+        w, h, q, seed = map(int, m.groups())
+        img = synth_image(w, h, seed)
+        out = np.zeros(w * h * 3 + (1 << 16), np.uint8)
+        iters = C.c_int()
+        n = L.ref_process_rgb_b200(_libs.p(img), w, h, C.c_float(gold["target"]), 0, _libs.p(out), C.c_long(out.size),
+                                   C.byref(iters))
+        assert n == gold["size"] and iters.value == gold["iterations"]
+        assert hashlib.sha256(out[:n].tobytes()).hexdigest() == gold["sha256"]
+
+
+def test_compare_block_single_equals_batched(gz):
+    import ctypes as C
+    img = synth_image(64, 48)
+    c = gz.ButteraugliComparator(64, 48, img, 0.97)
+    co = gz.RgbToJpegCoeffs(img)
+    c.SetJpegCoeffs(co); c.CopyFromJpegData(); c.ApplyGlobalQuantization(np.full(192, 3, np.int32))
+    cur = c.GetCoeffs()
+    c.StartBlockComparisons()
+    want = c.CompareBlocks()
+    L = gz.lib()
+    L.gzb_compare_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+    for b in range(c.num_blocks):
+        cand = np.ascontiguousarray(cur[:, b, :].reshape(192))
+        e = C.c_double()
+        assert L.gzb_compare_block(c._ctx, b % c.block_width, b // c.block_width, cand.ctypes.data, C.byref(e)) == 0
+        assert np.float32(e.value) == want[b]
+    c.close()
