@@ -205,6 +205,19 @@ class ButteraugliComparator:
         _check(lib().gzb_compute_block_zeroing_order(self._ctx, comp_mask, _p(out)), self._ctx)
         return out
 
+    def ComputeBlockZeroingCandidates(self, comp_mask=7):
+        """(candidate_coeff_offsets[nblocks+1], candidate_coeffs u8, candidate_coeff_errors f32)."""
+        L = lib()
+        L.gzb_compute_block_zeroing_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                           C.c_size_t, C.POINTER(C.c_size_t)]
+        off = np.zeros(self.num_blocks + 1, np.int32)
+        cap = self.num_blocks * 192
+        idx = np.zeros(cap, np.uint8)
+        err = np.zeros(cap, np.float32)
+        n = C.c_size_t()
+        _check(L.gzb_compute_block_zeroing_candidates(self._ctx, comp_mask, _p(off), _p(idx), _p(err), cap, C.byref(n)), self._ctx)
+        return off, idx[:n.value].copy(), err[:n.value].copy()
+
     def ComputeBlockErrorAdjustmentWeights(self, direction, max_block_dist, target_mul, distmap=None):
         w = np.zeros(self.num_blocks, np.float32)
         dm = None if distmap is None else np.ascontiguousarray(distmap, np.float32)
@@ -428,3 +441,11 @@ def profile_get(ctx):
         if n.value:
             out[L.gzb_profile_name(i).decode()] = (ms.value, n.value)
     return out
+
+
+def DctDouble(blocks, inverse=False, device=0):
+    """ComputeBlockDCTDouble / ComputeBlockIDCTDouble on [n, 64] float64 blocks (returns a copy)."""
+    a = np.ascontiguousarray(blocks, np.float64).copy().reshape(-1, 64)
+    lib().gzb_dct_double.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+    _check(lib().gzb_dct_double(device, _p(a), a.shape[0], 1 if inverse else 0))
+    return a

@@ -105,6 +105,17 @@ static void init_device_tables(int device) {
   for (int x = 0; x < 8; ++x) s8[x] = border_scale(g_hk[kB11], x, 8, 0.0);
   CK(cudaMemcpyToSymbol(c_scale8, s8, sizeof(s8)));
   CK(cudaMemcpyToSymbol(c_taps11, g_hk[kB11].taps, 5 * sizeof(float)));
+  {  // kDCTMatrix of guetzli/dct_double.cc:28-45: 0.5*alpha(u)*cos((2x+1)u*pi/16) with 10 decimals
+    double m[64];
+    for (int u = 0; u < 8; ++u)
+      for (int x = 0; x < 8; ++x) {
+        const double v = 0.5 * (u == 0 ? std::sqrt(0.5) : 1.0) * std::cos((2 * x + 1) * u * M_PI / 16);
+        char buf[64];
+        snprintf(buf, sizeof(buf), "%.10f", v);
+        m[8 * u + x] = strtod(buf, nullptr);
+      }
+    CK(cudaMemcpyToSymbol(c_dct_matrix, m, sizeof(m)));
+  }
   if (device < 64) g_dev_ready[device] = true;
 }
 
@@ -240,6 +251,8 @@ struct gzb_ctx {
   struct Req { void** pp; size_t bytes; };
   std::vector<Req> reqs;
   bool upd_own = false;
+  bool packed_valid = false;   // packed zeroing candidates still sit in d_tmp
+  int packed_mask = 0;
   Prof prof;
   bool have_orig_coeffs = false, have_coeffs = false, block_cmp = false, have_distmap = false;
   int sm_count = 148;
@@ -307,6 +320,7 @@ void dmalloc(T** p, size_t n) { CK(cudaMalloc(reinterpret_cast<void**>(p), std::
 void run_blur(gzb_ctx* c, const BlurPlan& pl, const float* in, size_t in_stride, int planes,
               float* out, size_t out_stride, int out_pitch) {
   const BlurGeom& g = pl.g;
+  c->packed_valid = false;
   if (g.nx <= 0 || g.ny <= 0) return;
   dim3 blk(32, 8);
   dim3 gh((g.nx + g.oxn - 1) / g.oxn, (g.in_h + kBhRows - 1) / kBhRows, planes);
@@ -318,6 +332,7 @@ void run_blur(gzb_ctx* c, const BlurPlan& pl, const float* in, size_t in_stride,
 }
 
 void render_candidate(gzb_ctx* c, int op) {
+  c->packed_valid = false;
   const int grid = (c->nblocks + 31) / 32;
   const size_t cs = static_cast<size_t>(c->nblocks) * 64;
   const size_t us = static_cast<size_t>(c->P) * c->HP;
@@ -794,6 +809,57 @@ int gzb_compute_block_zeroing_order(gzb_ctx* c, int comp_mask, gzb_coeff_data* o
   GZB_END(c)
 }
 
+int gzb_compute_block_zeroing_candidates(gzb_ctx* c, int comp_mask, int* offsets, uint8_t* cand_idx, float* cand_err,
+                                         size_t cap, size_t* n_out) {
+  GZB_TRY(c)
+  if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_compute_block_zeroing_candidates: StartBlockComparisons not called");
+  if (!c->have_coeffs || !c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compute_block_zeroing_candidates: coefficients missing");
+  if (comp_mask < 1 || comp_mask > 7 || !offsets || !n_out) return fail(c, GZB_ERR_BAD_ARG, "gzb_compute_block_zeroing_candidates: bad argument");
+  // d_tmp (6 planes of scratch) holds counts | offsets | packed idx | packed err
+  int* d_counts = reinterpret_cast<int*>(c->d_tmp);
+  int* d_offsets = d_counts + c->nblocks + 32;
+  float* d_err = reinterpret_cast<float*>(d_offsets + c->nblocks + 32);
+  uint8_t* d_idx = reinterpret_cast<uint8_t*>(d_err + static_cast<size_t>(192) * c->nblocks);
+  if (!(c->packed_valid && c->packed_mask == comp_mask)) {  // a repeated call only re-fetches
+    run_zeroing(c, comp_mask, 0);
+    const int g = (c->nblocks * 32 + 255) / 256;
+    KLAUNCH(c, KC_MISC, k_count_candidates<<<g, 256, 0, c->stream>>>(reinterpret_cast<const CoeffRec*>(c->d_order), c->nblocks, c->target, d_counts));
+    KLAUNCH(c, KC_MISC, k_scan_counts<<<1, 1024, 0, c->stream>>>(d_counts, c->nblocks, d_offsets));
+    KLAUNCH(c, KC_MISC, k_pack_candidates<<<g, 256, 0, c->stream>>>(reinterpret_cast<const CoeffRec*>(c->d_order), c->nblocks, c->target, d_offsets, d_idx, d_err));
+    c->packed_valid = true;
+    c->packed_mask = comp_mask;
+  }
+  CK(cudaMemcpyAsync(offsets, d_offsets, (static_cast<size_t>(c->nblocks) + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (static_cast<size_t>(c->nblocks) + 1) * sizeof(int);
+  sync_check(c);
+  CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  const size_t n = static_cast<size_t>(offsets[c->nblocks]);
+  *n_out = n;
+  if (n > 0 && cand_idx && cand_err && cap >= n) {
+    CK(cudaMemcpyAsync(cand_idx, d_idx, n, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += n;
+    CK(cudaMemcpyAsync(cand_err, d_err, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += n * sizeof(float);
+    sync_check(c);
+  }
+  GZB_END(c)
+}
+
+int gzb_dct_double(int device, double* blocks, size_t nblocks, int inverse) {
+  if (!blocks) return fail(nullptr, GZB_ERR_BAD_ARG, "gzb_dct_double: null argument");
+  if (nblocks == 0) return GZB_OK;
+  try {
+    CK(cudaSetDevice(device));
+    init_device_tables(device);
+    double* d = nullptr;
+    dmalloc(&d, nblocks * 64);
+    CK(cudaMemcpy(d, blocks, nblocks * 64 * sizeof(double), cudaMemcpyHostToDevice));
+    k_dct_double<<<static_cast<unsigned>((nblocks + 3) / 4), 256>>>(d, nblocks, inverse);
+    CK(cudaDeviceSynchronize());
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(blocks, d, nblocks * 64 * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+  } catch (const std::string& e) { return fail(nullptr, GZB_ERR_CUDA, e); }
+  return GZB_OK;
+}
+
 int gzb_compute_block_error_adjustment_weights(gzb_ctx* c, int direction, int max_block_dist, double target_mul,
                                                const float* distmap, float* block_weight) {
   GZB_TRY(c)
@@ -802,6 +868,7 @@ int gzb_compute_block_error_adjustment_weights(gzb_ctx* c, int direction, int ma
     CK(cudaMemcpy2DAsync(c->d_tmp, c->P * sizeof(float), distmap, c->W * sizeof(float), c->W * sizeof(float), c->H,
                          cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += static_cast<unsigned long long>(c->W * sizeof(float)) * (c->H);
     dm = c->d_tmp;
+    c->packed_valid = false;
   } else if (!c->have_distmap) {
     return fail(c, GZB_ERR_STATE, "gzb_compute_block_error_adjustment_weights: no distance map");
   }

@@ -712,21 +712,21 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   {
     if (gzb_start_block_comparisons(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
     const double t0 = now_ms();
-    std::vector<gzb_coeff_data> order(static_cast<size_t>(num_blocks) * 192);
-    if (gzb_compute_block_zeroing_order(e.ctx, comp_mask, order.data()) != GZB_OK) return fail(GZB_ERR_CUDA);
+    size_t ncand = 0;
+    cand_coeffs.resize(static_cast<size_t>(num_blocks) * 48);
+    cand_errors.resize(cand_coeffs.size());
+    if (gzb_compute_block_zeroing_candidates(e.ctx, comp_mask, cand_offsets.data(), cand_coeffs.data(), cand_errors.data(),
+                                             cand_coeffs.size(), &ncand) != GZB_OK) return fail(GZB_ERR_CUDA);
+    if (ncand > cand_coeffs.size()) {  // more than 48 candidates per block on average: fetch again (no recompute)
+      cand_coeffs.resize(ncand);
+      cand_errors.resize(ncand);
+      if (gzb_compute_block_zeroing_candidates(e.ctx, comp_mask, cand_offsets.data(), cand_coeffs.data(), cand_errors.data(),
+                                               ncand, &ncand) != GZB_OK) return fail(GZB_ERR_CUDA);
+    }
+    cand_coeffs.resize(ncand);
+    cand_errors.resize(ncand);
     e.st.device_zeroing_ms = gzb_last_device_ms(e.ctx);
     e.st.zeroing_wall_ms = now_ms() - t0;
-    const float limit = gzb_block_error_limit(e.ctx);
-    for (int b = 0; b < num_blocks; ++b) {
-      const gzb_coeff_data* p = &order[static_cast<size_t>(b) * 192];
-      cand_offsets[b] = static_cast<int>(cand_coeffs.size());
-      for (int i = 0; i < 192; ++i)
-        if (p[i].block_err > 0 && p[i].block_err <= limit) {
-          cand_coeffs.push_back(static_cast<uint8_t>(p[i].idx));
-          cand_errors.push_back(p[i].block_err);
-        }
-    }
-    cand_offsets[num_blocks] = static_cast<int>(cand_coeffs.size());
     gzb_finish_block_comparisons(e.ctx);
   }
 

@@ -730,4 +730,97 @@ __global__ void k_block_weights(const unsigned char* __restrict__ flags, int bw,
   weight[b] = w;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K12: double-precision 8x8 DCT / IDCT (guetzli/dct_double.cc:28-85), batched: 64 threads per block,
+// columns then rows, each output an in-order 8-term double sum against the 10-decimal matrix.
+// Only the 4:2:0 path of the reference reaches it (output_image.cc:100-122, 496-531).
+// ---------------------------------------------------------------------------------------------
+__constant__ double c_dct_matrix[64];   // kDCTMatrix[8*u + x], filled by init_device_tables()
+
+__global__ void __launch_bounds__(256)
+k_dct_double(double* __restrict__ blocks, size_t nblocks, int inverse) {
+  __shared__ double s_in[4][64];
+  __shared__ double s_tmp[4][64];
+  const int lb = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const size_t b = blockIdx.x * static_cast<size_t>(4) + lb;
+  const bool live = b < nblocks;
+  if (live) s_in[lb][t] = blocks[b * 64 + t];
+  __syncthreads();
+  {  // column pass: tmp[8*xo + col] = sum_u M(xo,u) * in[8*u + col]
+    const int xo = t >> 3, col = t & 7;
+    double acc = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += (inverse ? c_dct_matrix[8 * u + xo] : c_dct_matrix[8 * xo + u]) * s_in[lb][8 * u + col];
+    s_tmp[lb][8 * xo + col] = acc;
+  }
+  __syncthreads();
+  {  // row pass: out[8*row + xo] = sum_u M(xo,u) * tmp[8*row + u]
+    const int row = t >> 3, xo = t & 7;
+    double acc = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += (inverse ? c_dct_matrix[8 * u + xo] : c_dct_matrix[8 * xo + u]) * s_tmp[lb][8 * row + u];
+    if (live) blocks[b * 64 + 8 * row + xo] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K13: candidate packing of SelectFrequencyMasking (guetzli/processor.cc:694-712) on the device:
+// per block the records with 0 < err <= limit, in order; offsets by an exclusive scan.
+// ---------------------------------------------------------------------------------------------
+struct CoeffRec { int idx; float err; };
+__global__ void k_count_candidates(const CoeffRec* __restrict__ order, int nblocks, float limit,
+                                   int* __restrict__ counts) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nblocks) return;
+  const CoeffRec* p = order + static_cast<size_t>(warp) * 192;
+  int n = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float e = p[lane + 32 * k].err;
+    n += __popc(__ballot_sync(0xffffffffu, e > 0 && e <= limit));
+  }
+  if (lane == 0) counts[warp] = n;
+}
+// Single-CTA exclusive scan (nblocks <= a few hundred thousand): offsets[0..nblocks].
+__global__ void __launch_bounds__(1024)
+k_scan_counts(const int* __restrict__ counts, int nblocks, int* __restrict__ offsets) {
+  __shared__ int s_part[1024];
+  const int t = threadIdx.x;
+  const int per = (nblocks + 1023) / 1024;
+  const int b0 = min(nblocks, t * per), b1 = min(nblocks, b0 + per);
+  int sum = 0;
+  for (int b = b0; b < b1; ++b) sum += counts[b];
+  s_part[t] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int v = t >= off ? s_part[t - off] : 0;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  int run = s_part[t] - sum;
+  for (int b = b0; b < b1; ++b) { offsets[b] = run; run += counts[b]; }
+  if (t == 1023) offsets[nblocks] = s_part[1023];
+}
+__global__ void k_pack_candidates(const CoeffRec* __restrict__ order, int nblocks, float limit,
+                                  const int* __restrict__ offsets, uint8_t* __restrict__ out_idx,
+                                  float* __restrict__ out_err) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nblocks) return;
+  const CoeffRec* p = order + static_cast<size_t>(warp) * 192;
+  int base = offsets[warp];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const CoeffRec r = p[lane + 32 * k];
+    const bool take = r.err > 0 && r.err <= limit;
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (take) {
+      const int o = base + __popc(m & ((1u << lane) - 1));
+      out_idx[o] = static_cast<uint8_t>(r.idx);
+      out_err[o] = r.err;
+    }
+    base += __popc(m);
+  }
+}
+
 }  // namespace gzb

@@ -112,6 +112,15 @@ int gzb_compare_block(gzb_ctx* ctx, int block_x, int block_y, const int16_t* can
  * zeroing order, entries with err <= BlockErrorLimit only. Needs gzb_set_jpeg_coeffs (the original
  * coefficients) and gzb_start_block_comparisons. */
 int gzb_compute_block_zeroing_order(gzb_ctx* ctx, int comp_mask, gzb_coeff_data* out);
+/* Same search, with the candidate packing of SelectFrequencyMasking (guetzli/processor.cc:694-712)
+ * done on the device: offsets[nblocks+1] (candidate_coeff_offsets) and, for the records with
+ * 0 < err <= BlockErrorLimit in order, cand_idx (candidate_coeffs) / cand_err
+ * (candidate_coeff_errors). *n_out = total candidates; the two arrays are filled when cap >= n. */
+int gzb_compute_block_zeroing_candidates(gzb_ctx* ctx, int comp_mask, int* offsets, uint8_t* cand_idx,
+                                         float* cand_err, size_t cap, size_t* n_out);
+/* ComputeBlockDCTDouble / ComputeBlockIDCTDouble (guetzli/dct_double.cc:47-85), batched: nblocks
+ * blocks of 64 doubles, in place. Only the reference's 4:2:0 path uses these transforms. */
+int gzb_dct_double(int device, double* blocks, size_t nblocks, int inverse);
 /* ComputeBlockErrorAdjustmentWeights (guetzli/butteraugli_comparator.cc:169-233), factor 1.
  * distmap == NULL uses the device-resident map of the last Compare. block_weight: nblocks floats,
  * overwritten (the reference passes a zero vector, guetzli/processor.cc:776-783). */

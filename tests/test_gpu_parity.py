@@ -161,6 +161,13 @@ def test_block_comparisons_and_zeroing_order(gz, w, h):
     report("zeroing idx", zo["idx"], zo_o["idx"])
     report("zeroing err", zo["err"], zo_o["err"])
     assert (zo["err"] > 0).sum() > cmp_.num_blocks
+    # device-side candidate packing (processor.cc:694-712) against the same filter on the host
+    off, cidx, cerr = cmp_.ComputeBlockZeroingCandidates(7)
+    keep = (zo_o["err"] > 0) & (zo_o["err"] <= np.float32(target))
+    want_off = np.concatenate([[0], np.cumsum(keep.sum(axis=1))]).astype(np.int32)
+    report("candidate offsets", off, want_off)
+    report("candidate idx", cidx, zo_o["idx"][keep].astype(np.uint8))
+    report("candidate err", cerr, zo_o["err"][keep])
     cmp_.FinishBlockComparisons()
     cmp_.close()
 
@@ -190,6 +197,20 @@ def test_compare_against_compiled_reference_bees(gz):
     report("bees zeroing idx", zo["idx"][:nb], zo_ref["idx"])
     report("bees zeroing err", zo["err"][:nb], zo_ref["err"])
     cmp_.close(); s.close()
+
+
+def test_dct_double(gz):
+    """ComputeBlockDCTDouble / IDCTDouble (guetzli/dct_double.cc:47-85), bit-exact."""
+    rng = np.random.default_rng(8)
+    blocks = rng.normal(0, 60, (1000, 64))
+    for inv in (False, True):
+        want = blocks.copy()
+        for b in want:
+            oracle().gzo_dct_double(p(b), 1 if inv else 0)
+        report("dct_double inverse=%s" % inv, gz.DctDouble(blocks, inv), want)
+    # round trip is the identity up to the matrix's 10-decimal rounding
+    rt = gz.DctDouble(gz.DctDouble(blocks, False), True)
+    assert np.abs(rt - blocks).max() < 1e-6
 
 
 def test_error_paths(gz):
