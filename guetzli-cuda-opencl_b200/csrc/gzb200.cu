@@ -587,6 +587,7 @@ int gzb_set_jpeg_coeffs(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const 
   for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(c->d_orig + k * cs, src[k], cs * 2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (cs * 2);
   sync_check(c);
   c->have_orig_coeffs = true;
+  c->packed_valid = false;
   GZB_END(c)
 }
 
