@@ -217,7 +217,9 @@ struct OrderLess {
 
 class LazySort {
  public:
-  LazySort(OrderEntry* data, size_t n) : d_(data), n_(n), sorted_(0) {
+  // pool (optional) parallelises the partition of large ranges; the result is the same array.
+  LazySort(OrderEntry* data, size_t n, gzb::WorkerPool* pool = nullptr)
+      : d_(data), n_(n), sorted_(0), pool_(pool) {
     if (n_ > 1) pending_.push_back({0, n_, 2 * static_cast<int>(std::__lg(n_))});
     else sorted_ = n_;
   }
@@ -225,10 +227,101 @@ class LazySort {
   void ensure(size_t i) {
     while (sorted_ <= i && sorted_ < n_) advance();
   }
+  // Same, for a long prefix that is known to be needed: the partition tree is split on this thread
+  // until the pieces covering [0, i] are small, then the pieces (independent sub-ranges, each with
+  // its own depth budget) are finished on the pool. Identical result to ensure(i).
+  void ensure_bulk(size_t i) {
+    if (!pool_ || pool_->size() < 2 || i < sorted_ + (size_t(1) << 16)) { ensure(i); return; }
+    i = std::min(i, n_ - 1);
+    const size_t kPiece = size_t(1) << 15;
+    auto comp = __gnu_cxx::__ops::__iter_comp_iter(OrderLess());
+    std::vector<Range> pieces;
+    // pending_.back() is the leftmost range; split until every range that intersects [sorted_, i] is small
+    while (!pending_.empty() && pending_.back().first <= i) {
+      Range r = pending_.back();
+      pending_.pop_back();
+      if (r.last - r.first <= kPiece || r.depth == 0) { pieces.push_back(r); continue; }
+      --r.depth;
+      OrderEntry* cut = (r.last - r.first >= kParallelMin) ? parallel_partition_pivot(d_ + r.first, d_ + r.last)
+                                                          : std::__unguarded_partition_pivot(d_ + r.first, d_ + r.last, comp);
+      const size_t c = static_cast<size_t>(cut - d_);
+      pending_.push_back({c, r.last, r.depth});
+      pending_.push_back({r.first, c, r.depth});
+    }
+    if (pieces.empty()) return;
+    pool_->run(static_cast<int>(pieces.size()), [&](int t) {
+      const Range& r = pieces[t];
+      auto cmp = __gnu_cxx::__ops::__iter_comp_iter(OrderLess());
+      if (r.last - r.first > 1) {
+        std::__introsort_loop(d_ + r.first, d_ + r.last, static_cast<long>(r.depth), cmp);
+        std::__insertion_sort(d_ + r.first, d_ + r.last, cmp);  // stable: equals the chunk-local passes
+      }
+    });
+    sorted_ = pieces.back().last;
+  }
   size_t sorted() const { return sorted_; }
 
  private:
   struct Range { size_t first, last; int depth; };
+  static constexpr size_t kParallelMin = size_t(1) << 18;
+
+  // std::__unguarded_partition_pivot(first, last) evaluated in parallel. The sequential scan swaps
+  // the k-th element (from the left) that is not less than the pivot with the k-th element (from
+  // the right) that is not greater, for as long as the former lies left of the latter; both lists
+  // can be read off the ORIGINAL array, so ranks come from prefix sums and the swaps commute.
+  OrderEntry* parallel_partition_pivot(OrderEntry* first, OrderEntry* last) {
+    auto comp = __gnu_cxx::__ops::__iter_comp_iter(OrderLess());
+    OrderEntry* mid = first + (last - first) / 2;
+    std::__move_median_to_first(first, first + 1, mid, last - 1, comp);
+    const float pv = first->second;
+    OrderEntry* a = first + 1;
+    const size_t n = static_cast<size_t>(last - a);
+    const int T = std::max(1, std::min<int>(4 * pool_->size(), static_cast<int>(n >> 15)));
+    std::vector<size_t> cl(T + 1, 0), cr(T + 1, 0);
+    auto bounds = [&](int t, size_t* b0, size_t* b1) { *b0 = n * t / T; *b1 = n * (t + 1) / T; };
+    pool_->run(T, [&](int t) {
+      size_t b0, b1, nl = 0, nr = 0;
+      bounds(t, &b0, &b1);
+      for (size_t i = b0; i < b1; ++i) { const float v = a[i].second; nl += !(v < pv); nr += !(pv < v); }
+      cl[t + 1] = nl;
+      cr[t + 1] = nr;
+    });
+    for (int t = 0; t < T; ++t) { cl[t + 1] += cl[t]; cr[t + 1] += cr[t]; }
+    const size_t NL = cl[T], NR = cr[T];
+    if (lpos_.size() < NL) lpos_.resize(NL);
+    if (rpos_.size() < NR) rpos_.resize(NR);
+    // L ascending from the left; R indexed from the right (R[0] = right-most)
+    pool_->run(T, [&](int t) {
+      size_t b0, b1;
+      bounds(t, &b0, &b1);
+      size_t il = cl[t];
+      size_t ir = NR - cr[t];   // number of right-stoppers at or after b0
+      for (size_t i = b0; i < b1; ++i) {
+        const float v = a[i].second;
+        if (!(v < pv)) lpos_[il++] = static_cast<uint32_t>(i);
+        if (!(pv < v)) rpos_[--ir] = static_cast<uint32_t>(i);
+      }
+    });
+    // K = number of k with L[k] < R[k] (monotone: L ascends, R descends)
+    size_t lo = 0, hi = std::min(NL, NR);
+    while (lo < hi) {
+      const size_t m = (lo + hi) / 2;
+      if (lpos_[m] < rpos_[m]) lo = m + 1; else hi = m;
+    }
+    const size_t K = lo;
+    if (K > 0) {
+      const int TS = std::max(1, std::min<int>(pool_->size(), static_cast<int>(K >> 12) + 1));
+      pool_->run(TS, [&](int t) {
+        const size_t k0 = K * t / TS, k1 = K * (t + 1) / TS;
+        for (size_t k = k0; k < k1; ++k) std::swap(a[lpos_[k]], a[rpos_[k]]);
+      });
+    }
+    size_t cut = n;  // the scan is guarded: a stopper exists
+    if (K < NL) cut = std::min<size_t>(cut, lpos_[K]);
+    if (K > 0) cut = std::min<size_t>(cut, rpos_[K - 1]);
+    return a + cut;
+  }
+
   void advance() {
     // Leftmost pending range starts at sorted_.
     Range r = pending_.back();
@@ -241,32 +334,31 @@ class LazySort {
         return;
       }
       --r.depth;
-      OrderEntry* cut = std::__unguarded_partition_pivot(d_ + r.first, d_ + r.last, comp);
+      OrderEntry* cut = (pool_ && pool_->size() > 1 && r.last - r.first >= kParallelMin)
+                            ? parallel_partition_pivot(d_ + r.first, d_ + r.last)
+                            : std::__unguarded_partition_pivot(d_ + r.first, d_ + r.last, comp);
       const size_t c = static_cast<size_t>(cut - d_);
       pending_.push_back({c, r.last, r.depth});
       r.last = c;
     }
     finish_chunk(r.first, r.last, false);
   }
-  // Final insertion sort restricted to one chunk: the first 16 elements of the whole array use the
-  // guarded variant, everything else the unguarded one (std::__final_insertion_sort).
+  // Final insertion sort restricted to one chunk. std::__final_insertion_sort runs a guarded
+  // insertion sort on the first 16 elements and an unguarded one on the rest; both are stable
+  // insertion sorts, chunks are separated by pivots (everything left <= everything right), so
+  // sorting each chunk with a stable insertion sort gives the same arrangement.
   void finish_chunk(size_t first, size_t last, bool already_sorted) {
     if (!already_sorted) {
       auto comp = __gnu_cxx::__ops::__iter_comp_iter(OrderLess());
-      if (n_ <= 16) {
-        std::__insertion_sort(d_ + first, d_ + last, comp);
-      } else {
-        // Elements with global index < 16 are handled by __insertion_sort(first, first+16) over
-        // the whole array; since chunks are separated by pivots, sorting chunk-locally with a
-        // guarded insertion sort gives the same arrangement as both library passes.
-        std::__insertion_sort(d_ + first, d_ + last, comp);
-      }
+      std::__insertion_sort(d_ + first, d_ + last, comp);
     }
     sorted_ = last;
   }
   OrderEntry* d_;
   size_t n_, sorted_;
+  gzb::WorkerPool* pool_;
   std::vector<Range> pending_;
+  std::vector<uint32_t> lpos_, rpos_;
 };
 
 // ---- encoder state ----------------------------------------------------------------------------
@@ -564,8 +656,12 @@ double gzb_bench_write_jpeg(const int16_t* c0, const int16_t* c1, const int16_t*
 void gzb_test_lazy_sort(int* first, float* second, size_t n, size_t prefix) {
   std::vector<OrderEntry> v(n);
   for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(first[i], second[i]);
-  LazySort ls(v.data(), n);
-  if (prefix > 0) ls.ensure(std::min(prefix, n) - 1);
+  gzb::WorkerPool pool(6);
+  LazySort ls(v.data(), n, &pool);
+  if (prefix > 0) {
+    if ((n ^ prefix) & 1) ls.ensure_bulk(std::min(prefix, n) - 1);   // exercise both entry points
+    else { ls.ensure_bulk((std::min(prefix, n) - 1) / 2); ls.ensure(std::min(prefix, n) - 1); }
+  }
   for (size_t i = 0; i < n; ++i) { first[i] = v[i].first; second[i] = v[i].second; }
 }
 void gzb_test_std_sort(int* first, float* second, size_t n) {
@@ -868,7 +964,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         }
         if (global_order.empty()) break;
 
-        LazySort sorter(global_order.data(), global_order.size());
+        LazySort sorter(global_order.data(), global_order.size(), e.pool.get());
         double rel_size_delta = direction > 0 ? 0.01 : 0.0005;
         if (direction > 0 && gzb_distance_ok(e.ctx, 1.0)) rel_size_delta = 0.05;
         const double min_size_delta = base_size * rel_size_delta;
@@ -885,6 +981,11 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         float val_threshold = 0.0;
         int changed_coeffs = 0;
         int est_jpg_size = prev_size;
+        if (min_coeffs_to_change > 0) {  // the walk cannot stop before min_coeffs_to_change + 1 entries
+          const double ts = now_ms();
+          sorter.ensure_bulk(std::min<size_t>(static_cast<size_t>(min_coeffs_to_change), global_order.size() - 1));
+          e.st.be_sort_ms += now_ms() - ts;
+        }
         WriteJob* job = writer.new_job();
         const size_t order_size = global_order.size();
         const size_t kAhead = 24;

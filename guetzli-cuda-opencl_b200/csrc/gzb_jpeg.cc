@@ -524,10 +524,10 @@ void write_jpeg(const Frame& f, std::string* out, WorkerPool* pool, const Histog
     for (int t = 0; t < T; ++t) off[t + 1] = off[t] + bands[t].total_bits;
     std::vector<uint16_t> head16(T + 1, 0xffff);
     for (int t = 0; t < T; ++t) head16[t] = static_cast<uint16_t>((bands[t].bytes[0] << 8) | bands[t].bytes[1]);
-    std::vector<std::vector<uint8_t>> stuffed(T);
+    // pass 1: per band, append the two virtual tail bytes and count owned bytes and 0xff bytes
+    std::vector<size_t> nbytes(T + 1, 0);
     pool->run(T, [&](int t) {
       BitBuf& b = bands[t];
-      const size_t B = b.bytes.size();
       const uint32_t tailbits = b.nacc ? static_cast<uint32_t>(b.acc & ((1u << b.nacc) - 1)) : 0;
       const uint32_t V = ((tailbits << (16 - b.nacc)) | (static_cast<uint32_t>(head16[t + 1]) >> b.nacc)) & 0xffff;
       b.bytes.push_back(static_cast<uint8_t>(V >> 8));
@@ -535,25 +535,37 @@ void write_jpeg(const Frame& f, std::string* out, WorkerPool* pool, const Histog
       const uint64_t j0 = (off[t] + 7) / 8, j1 = (off[t + 1] + 7) / 8;
       const int s0 = static_cast<int>(8 * j0 - off[t]);
       const size_t count = static_cast<size_t>(j1 - j0);
-      (void)B;
-      std::vector<uint8_t>& o = stuffed[t];
-      o.reserve(count + count / 32 + 16);
       const uint8_t* L = b.bytes.data();
+      size_t ff = 0;
       if (s0 == 0) {
-        for (size_t m = 0; m < count; ++m) { const uint8_t v = L[m]; o.push_back(v); if (v == 0xff) o.push_back(0); }
+        for (size_t m = 0; m < count; ++m) ff += L[m] == 0xff;
+      } else {
+        for (size_t m = 0; m < count; ++m) ff += static_cast<uint8_t>(((L[m] << 8) | L[m + 1]) >> (8 - s0)) == 0xff;
+      }
+      nbytes[t + 1] = count + ff;
+    });
+    const size_t base = out->size();
+    for (int t = 0; t < T; ++t) nbytes[t + 1] += nbytes[t];
+    out->resize(base + nbytes[T]);
+    char* dst0 = &(*out)[0] + base;
+    // pass 2: shifted + stuffed bytes straight into the output
+    pool->run(T, [&](int t) {
+      const BitBuf& b = bands[t];
+      const uint64_t j0 = (off[t] + 7) / 8, j1 = (off[t + 1] + 7) / 8;
+      const int s0 = static_cast<int>(8 * j0 - off[t]);
+      const size_t count = static_cast<size_t>(j1 - j0);
+      const uint8_t* L = b.bytes.data();
+      uint8_t* o = reinterpret_cast<uint8_t*>(dst0) + nbytes[t];
+      if (s0 == 0) {
+        for (size_t m = 0; m < count; ++m) { const uint8_t v = L[m]; *o++ = v; if (v == 0xff) *o++ = 0; }
       } else {
         for (size_t m = 0; m < count; ++m) {
           const uint8_t v = static_cast<uint8_t>(((L[m] << 8) | L[m + 1]) >> (8 - s0));
-          o.push_back(v);
-          if (v == 0xff) o.push_back(0);
+          *o++ = v;
+          if (v == 0xff) *o++ = 0;
         }
       }
     });
-    std::vector<size_t> pos(T + 1, out->size());
-    for (int t = 0; t < T; ++t) pos[t + 1] = pos[t] + stuffed[t].size();
-    out->resize(pos[T]);
-    char* base = &(*out)[0];
-    pool->run(T, [&](int t) { if (!stuffed[t].empty()) memcpy(base + pos[t], stuffed[t].data(), stuffed[t].size()); });
   }
   out->push_back(static_cast<char>(0xff));
   out->push_back(static_cast<char>(0xd9));

@@ -115,7 +115,7 @@ def test_lazy_sort_equals_std_sort(gz):
     L.gzb_test_lazy_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
     L.gzb_test_std_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     rng = np.random.default_rng(4)
-    for n in [0, 1, 2, 15, 16, 17, 33, 100, 1000, 5000, 70000]:
+    for n in [0, 1, 2, 15, 16, 17, 33, 100, 1000, 5000, 70000, 600000, 1500000]:   # >= 2^18: parallel partition
         for kind in range(4):
             if kind == 0:
                 v = rng.random(n).astype(np.float32)
@@ -133,4 +133,4 @@ def test_lazy_sort_equals_std_sort(gz):
                 L.gzb_test_lazy_sort(p(b_id), p(b_v), n, prefix)
                 assert np.array_equal(b_id[:prefix], a_id[:prefix]), (n, kind, prefix)
                 assert np.array_equal(b_v[:prefix], a_v[:prefix])
-                assert sorted(b_id.tolist()) == list(range(n))
+                assert np.array_equal(np.sort(b_id), np.arange(n, dtype=np.int32))
