@@ -652,6 +652,44 @@ double gzb_bench_write_jpeg(const int16_t* c0, const int16_t* c1, const int16_t*
   return dt;
 }
 
+// Micro-benchmark hook: ComputeEntropyCodes-style clustering of a frame's three AC histograms with a
+// small perturbation per repetition; returns microseconds per call.
+double gzb_bench_cluster(const int16_t* c0, const int16_t* c1, const int16_t* c2, int width, int height, int reps,
+                         int use_cache) {
+  gzb::jpeg::HuffCache caches[5];
+  const int bw = (width + 7) / 8, bh = (height + 7) / 8;
+  Frame f;
+  f.width = width; f.height = height; f.bw = bw; f.bh = bh; f.ncomp = 3;
+  f.coeffs[0] = c0; f.coeffs[1] = c1; f.coeffs[2] = c2;
+  Histogram dc[3], ac[3];
+  gzb::jpeg::build_histograms(f, dc, ac, nullptr);
+  size_t sink = 0;
+  const double t0 = now_ms();
+  for (int r = 0; r < reps; ++r) {
+    ac[r % 3].counts[(r * 7) % 200 + 1] += 2;
+    Histogram clustered[3] = {ac[0], ac[1], ac[2]};
+    size_t num = 3;
+    int indexes[4];
+    uint8_t cd[3 * Histogram::kSize];
+    sink += gzb::jpeg::cluster_histograms(clustered, &num, indexes, cd, use_cache ? caches : nullptr);
+  }
+  const double us = (now_ms() - t0) * 1e3 / reps;
+  return sink == 12345 ? -us : us;
+}
+
+// Test hook: huffman_depths on a 257-entry histogram (optionally through a warm HuffCache).
+void gzb_test_huffman_depths(const uint32_t* counts257, uint8_t* depth257, const uint32_t* warm_counts257) {
+  memset(depth257, 0, 257);
+  if (warm_counts257) {
+    gzb::jpeg::HuffCache cache;
+    uint8_t tmp[257] = {0};
+    gzb::jpeg::huffman_depths(warm_counts257, 257, 16, tmp, &cache);
+    gzb::jpeg::huffman_depths(counts257, 257, 16, depth257, &cache);
+  } else {
+    gzb::jpeg::huffman_depths(counts257, 257, 16, depth257, nullptr);
+  }
+}
+
 // Test hooks: the lazy order must equal std::sort's permutation on the consumed prefix.
 void gzb_test_lazy_sort(int* first, float* second, size_t n, size_t prefix) {
   std::vector<OrderEntry> v(n);
@@ -858,12 +896,13 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
     WriterStage writer(&e, dc_hist);
     std::vector<uint8_t> ac_depths(3 * Histogram::kSize);
     // ComputeEntropyCodes (processor.cc:517-536)
+    gzb::jpeg::HuffCache huff_caches[5];
     auto compute_entropy_codes = [&]() -> size_t {
       Histogram clustered[3] = {ac_hist[0], ac_hist[1], ac_hist[2]};
       size_t num = ncomp;
       int indexes[4];
       uint8_t cd[3 * Histogram::kSize];
-      gzb::jpeg::cluster_histograms(clustered, &num, indexes, cd);
+      gzb::jpeg::cluster_histograms(clustered, &num, indexes, cd, huff_caches);
       for (int i = 0; i < ncomp; ++i)
         memcpy(&ac_depths[i * Histogram::kSize], &cd[indexes[i] * Histogram::kSize], Histogram::kSize);
       size_t hs = 0;

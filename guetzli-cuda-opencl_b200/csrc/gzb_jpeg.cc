@@ -49,20 +49,59 @@ bool assign_depths(int root, const Node* pool, uint8_t* depth, int max_depth) {
 }
 }  // namespace
 
-void huffman_depths(const uint32_t* counts, int length, int limit, uint8_t* depth) {
+void huffman_depths(const uint32_t* counts, int length, int limit, uint8_t* depth, HuffCache* cache) {
   Node tree[2 * Histogram::kSize + 1];
-  for (uint32_t floor_count = 1;; floor_count *= 2) {
-    int n = 0;
-    for (int i = length; i-- > 0;)
-      if (counts[i]) tree[n++] = Node{std::max(counts[i], floor_count), -1, static_cast<int16_t>(i)};
-    if (n == 1) {
-      depth[tree[0].right_or_value] = 1;
-      return;
+  // Leaves ordered by (count ascending, symbol descending): a strict total order, so any sorting
+  // algorithm gives the reference's arrangement. One 64-bit key per leaf: count << 16 | (0xffff - symbol).
+  uint64_t keys[Histogram::kSize];
+  int n = 0;
+  if (cache && cache->n > 0) {
+    // start from the previous call's order (the histogram moved by a few counts): insertion sort
+    // is then close to linear
+    bool seen[Histogram::kSize] = {false};
+    for (int k = 0; k < cache->n; ++k) {
+      const int i = cache->order[k];
+      seen[i] = true;
+      if (i < length && counts[i]) keys[n++] = (static_cast<uint64_t>(counts[i]) << 16) | static_cast<uint64_t>(0xffff - i);
     }
-    std::sort(tree, tree + n, [](const Node& a, const Node& b) {
-      if (a.count != b.count) return a.count < b.count;
-      return a.right_or_value > b.right_or_value;
-    });
+    for (int i = length; i-- > 0;)
+      if (counts[i] && !seen[i]) keys[n++] = (static_cast<uint64_t>(counts[i]) << 16) | static_cast<uint64_t>(0xffff - i);
+    for (int k = 1; k < n; ++k) {
+      const uint64_t v = keys[k];
+      int j = k - 1;
+      while (j >= 0 && keys[j] > v) { keys[j + 1] = keys[j]; --j; }
+      keys[j + 1] = v;
+    }
+  } else {
+    for (int i = length; i-- > 0;)
+      if (counts[i]) keys[n++] = (static_cast<uint64_t>(counts[i]) << 16) | static_cast<uint64_t>(0xffff - i);
+    if (n > 1) std::sort(keys, keys + n);
+  }
+  if (cache) {
+    cache->n = n;
+    for (int k = 0; k < n; ++k) cache->order[k] = static_cast<int16_t>(0xffff - static_cast<int>(keys[k] & 0xffff));
+  }
+  if (n == 1) {
+    depth[0xffff - static_cast<int>(keys[0] & 0xffff)] = 1;
+    return;
+  }
+  // Attempts with a rising count floor until the tree fits `limit` bits. Raising the floor only
+  // changes the leading leaves (count <= floor): they all tie at the floor and must then order by
+  // descending symbol; the tail keeps its order. So each attempt re-sorts just that prefix.
+  int16_t pref[Histogram::kSize];
+  int P = 0;  // leaves [0, P) have count <= floor_count
+  for (uint32_t floor_count = 1;; floor_count *= 2) {
+    if (floor_count > 1) {
+      const int P0 = P;
+      while (P < n && static_cast<uint32_t>(keys[P] >> 16) <= floor_count) {
+        pref[P] = static_cast<int16_t>(0xffff - static_cast<int>(keys[P] & 0xffff));
+        ++P;
+      }
+      if (P > P0 || P0 == 0) std::sort(pref, pref + P, [](int16_t x, int16_t y) { return x > y; });
+      for (int k = 0; k < P; ++k) tree[k] = Node{floor_count, -1, pref[k]};
+    }
+    for (int k = P; k < n; ++k)
+      tree[k] = Node{static_cast<uint32_t>(keys[k] >> 16), -1, static_cast<int16_t>(0xffff - static_cast<int>(keys[k] & 0xffff))};
     const Node sentinel{~0u, -1, -1};
     tree[n] = sentinel;
     tree[n + 1] = sentinel;
@@ -94,12 +133,12 @@ size_t entropy_cost_bits(const Histogram& h, const uint8_t* depth) {
   return bits;
 }
 
-size_t cluster_histograms(Histogram* histo, size_t* num, int* indexes, uint8_t* depth) {
+size_t cluster_histograms(Histogram* histo, size_t* num, int* indexes, uint8_t* depth, HuffCache* caches) {
   memset(depth, 0, *num * Histogram::kSize);
   size_t costs[4];
   for (size_t i = 0; i < *num; ++i) {
     indexes[i] = static_cast<int>(i);
-    huffman_depths(histo[i].counts, Histogram::kSize, 16, depth + i * Histogram::kSize);
+    huffman_depths(histo[i].counts, Histogram::kSize, 16, depth + i * Histogram::kSize, caches ? &caches[i] : nullptr);
     costs[i] = header_cost_bits(histo[i]) + entropy_cost_bits(histo[i], depth + i * Histogram::kSize);
   }
   const size_t orig_num = *num;
@@ -108,7 +147,7 @@ size_t cluster_histograms(Histogram* histo, size_t* num, int* indexes, uint8_t* 
     Histogram both(histo[last]);
     both.merge(histo[prev]);
     uint8_t depth_both[Histogram::kSize] = {0};
-    huffman_depths(both.counts, Histogram::kSize, 16, depth_both);
+    huffman_depths(both.counts, Histogram::kSize, 16, depth_both, caches ? &caches[3 + (orig_num - *num)] : nullptr);
     const size_t cost_both = header_cost_bits(both) + entropy_cost_bits(both, depth_both);
     if (!(cost_both < costs[last] + costs[prev])) break;
     histo[prev] = both;

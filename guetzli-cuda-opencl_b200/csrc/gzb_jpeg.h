@@ -64,12 +64,16 @@ struct Histogram {
   }
 };
 
+// Leaf order of a previous huffman_depths call on a nearby histogram (speeds up the next one;
+// never changes the result).
+struct HuffCache { int n = 0; int16_t order[257]; };
 // Length-limited Huffman depths (CreateHuffmanTree).
-void huffman_depths(const uint32_t* counts, int length, int limit, uint8_t* depth);
+void huffman_depths(const uint32_t* counts, int length, int limit, uint8_t* depth, HuffCache* cache = nullptr);
 size_t header_cost_bits(const Histogram& h);                        // HistogramHeaderCost
 size_t entropy_cost_bits(const Histogram& h, const uint8_t* depth);  // HistogramEntropyCost
 // ClusterHistograms: merges trailing histograms while that is cheaper; returns bytes.
-size_t cluster_histograms(Histogram* histo, size_t* num, int* indexes, uint8_t* depth);
+// caches: optional HuffCache[5] (three inputs + the two possible merges), kept between calls.
+size_t cluster_histograms(Histogram* histo, size_t* num, int* indexes, uint8_t* depth, HuffCache* caches = nullptr);
 
 uint64_t zigzag_nonzero_mask(const int16_t* q);
 // AC symbols of one block of QUANTISED indices in natural order (UpdateACHistogramForDCTBlock).

@@ -32,6 +32,7 @@
 #undef private
 #undef protected
 
+#include "guetzli/entropy_encode.h"
 #include "guetzli/gamma_correct.h"
 #include "guetzli/idct.h"
 #include "guetzli/fdct.h"
@@ -104,6 +105,13 @@ void ref_color_tables(int* cr_r, int* cb_b, int* cr_g, int* cb_g, uint8_t* range
 }
 void ref_ycbcr_to_rgb(uint8_t* pixels, int n) {
   for (int i = 0; i < n; ++i) guetzli::ColorTransformYCbCrToRGB(pixels + 3 * i);
+}
+
+// CreateHuffmanTree (guetzli/entropy_encode.cc:68-143) on a 257-entry histogram, limit 16.
+void ref_create_huffman_tree(const uint32_t* counts257, uint8_t* depth257) {
+  std::vector<guetzli::HuffmanTree> tree(2 * 257 + 1);
+  memset(depth257, 0, 257);
+  guetzli::CreateHuffmanTree(counts257, 257, 16, &tree[0], depth257);
 }
 
 // ---------------------------------------------------------------- integer transforms

@@ -134,3 +134,30 @@ def test_lazy_sort_equals_std_sort(gz):
                 assert np.array_equal(b_id[:prefix], a_id[:prefix]), (n, kind, prefix)
                 assert np.array_equal(b_v[:prefix], a_v[:prefix])
                 assert np.array_equal(np.sort(b_id), np.arange(n, dtype=np.int32))
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_huffman_depths_equal_reference(gz):
+    """Length-limited Huffman depths vs CreateHuffmanTree, including histograms whose unconstrained
+    tree is deeper than 16 bits (rising count floor) and the warm-cache path."""
+    L = gz.lib()
+    R = ref()
+    rng = np.random.default_rng(12)
+    for trial in range(300):
+        counts = np.zeros(257, np.uint32)
+        nsym = int(rng.integers(1, 200))
+        syms = rng.choice(256, nsym, replace=False)
+        spread = int(rng.integers(1, 24))
+        counts[syms] = (2 * (1 + rng.integers(0, 1 << rng.integers(0, spread + 1, nsym)))).astype(np.uint32)
+        if trial % 5 == 0:   # Fibonacci-like counts force deep trees
+            f = [1, 1]
+            while len(f) < nsym: f.append(min(f[-1] + f[-2], 1 << 22))
+            counts[syms] = 2 * np.array(f[:nsym], dtype=np.uint32)
+        counts[256] = 1
+        want = np.zeros(257, np.uint8); got = np.zeros(257, np.uint8); got2 = np.zeros(257, np.uint8)
+        R.ref_create_huffman_tree(p(counts), p(want))
+        L.gzb_test_huffman_depths(p(counts), p(got), None)
+        warm = counts.copy(); warm[syms[: max(1, nsym // 3)]] += np.uint32(2 * int(rng.integers(1, 50)))
+        L.gzb_test_huffman_depths(p(counts), p(got2), p(warm))
+        assert np.array_equal(got, want), trial
+        assert np.array_equal(got2, want), trial
