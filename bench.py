@@ -193,12 +193,20 @@ def run_ours(a, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize()
 
+    group = a.mode == "group"
+
     def one_image(step):
-        return _libs.synth_image(w, h, 1234 + 10 * (step * world + rank))
+        # batch mode: every rank its own image; group mode: all ranks share the step's image
+        return _libs.synth_image(w, h, 1234 + 10 * (step if group else step * world + rank))
+
+    allgather = None
+    if group and world > 1:
+        allgather = gz.torch_allgather(dist, torch.device("cuda", local))   # NCCL over NVLink
 
     images = [one_image(s) for s in range(a.warmup + a.steps)]
     sampler = ClockSampler(local)
     run_ms, e2e_ms, launches, h2d, d2h = [], [], 0, 0, 0
+    rounds, trials = [], []
     kt = {}
     n_cmp = 0
     for step in range(a.warmup + a.steps):
@@ -208,6 +216,8 @@ def run_ours(a, rank, world, local):
         img = images[step]
         # ---- device-resident arm: create outside, run inside the timed region
         enc = gz.Encoder(img, target, device=local, host_threads=host_threads, profile=timed)
+        if allgather is not None:
+            enc.set_group(rank, world, allgather)
         flush.fill_(step & 0xff)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -229,9 +239,14 @@ def run_ours(a, rank, world, local):
         flush.fill_((step + 1) & 0xff)
         barrier()
         t0 = time.perf_counter()
-        jpg2, st2, _ = gz.Process(img, target, device=local, host_threads=host_threads)
+        if allgather is not None:
+            jpg2, st2, _ = gz.ProcessGroup(img, target, dist, device=local, host_threads=host_threads)
+        else:
+            jpg2, st2, _ = gz.Process(img, target, device=local, host_threads=host_threads)
         dt2 = (time.perf_counter() - t0) * 1e3
         assert jpg2 == jpg
+        if timed:
+            rounds.append(st["search_rounds"]); trials.append(st["search_trials"])
         if timed:
             e2e_ms.append(dt2)
             h2d += st2["h2d_bytes"]; d2h += st2["d2h_bytes"] + len(jpg2) * 0
@@ -255,8 +270,9 @@ def run_ours(a, rank, world, local):
     total_e2e = reduce_max(sum(e2e_ms))
     launches_all = int(reduce_sum(launches))
     mpix = w * h / 1e6
-    value = world * mpix * a.steps / (total_run / 1e3)
-    e2e_value = world * mpix * a.steps / (total_e2e / 1e3)
+    images_per_step = 1 if group else world
+    value = images_per_step * mpix * a.steps / (total_run / 1e3)
+    e2e_value = images_per_step * mpix * a.steps / (total_e2e / 1e3)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -276,10 +292,15 @@ def run_ours(a, rank, world, local):
     kernels = {k: {"ms_per_step": ms / a.steps, "launches_per_step": n / a.steps} for k, (ms, n) in sorted(kt.items(), key=lambda kv: -kv[1][0])}
     line = {
         "metric": "end-to-end encode MPix/s", "value": value, "unit": "MPix/s", "n_gpus": world, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": total_run / a.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": a.warmup, "ms_per_step": total_run / a.steps, "higher_is_better": True, "scaling": "strong" if group else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic %dx%d sRGB (SURVEY 8d generator, seed 1234+10k), quality %g, one image per GPU per step, "
-                               "guetzli::Process" % (w, h, a.quality),
+        "config": {"workload": "synthetic %dx%d sRGB (SURVEY 8d generator, seed 1234+10k), quality %g, %s, "
+                               "guetzli::Process" % (w, h, a.quality,
+                                                     "ONE image per step shared by all GPUs: SelectQuantMatrix candidates and "
+                                                     "zeroing blocks sharded, NCCL all-gather per round" if group
+                                                     else "one image per GPU per step"),
+                   "mode": a.mode, "search_rounds_per_step": sum(rounds) / max(1, len(rounds)),
+                   "search_trials_per_step": sum(trials) / max(1, len(trials)),
                    "l2": "256 MiB buffer written between timed steps (L2 flush)", "host_threads_per_gpu": host_threads,
                    "compares_per_step": n_cmp / a.steps},
         "e2e": {"value": e2e_value, "unit": "MPix/s", "ms_per_step": total_e2e / a.steps,
@@ -297,6 +318,62 @@ def run_ours(a, rank, world, local):
         dist.destroy_process_group()
 
 
+def run_butteraugli_sweep(a, local):
+    """BASELINE configs[4]: standalone butteraugli Compare over 0.25-24 MPix (M2, SURVEY 8d: the
+    candidate is the image after ApplyGlobalQuantization with the all-3 matrix, resident as
+    coefficients; diffmap + distance produced on the device) and an encode quality sweep 84-100 on a
+    3840x2160 image. One GPU. Prints one JSON line."""
+    import torch
+    import __graft_entry__ as ge
+    import _libs
+    gz = ge.load_package()
+    if not torch.cuda.is_available() or gz.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    peak, peak_src = peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    sweep = []
+    for (w, h) in [(512, 512), (1024, 1024), (2048, 2048), (4000, 3000), (6000, 4000)]:
+        img = _libs.synth_image(w, h, 1234)
+        c = gz.ButteraugliComparator(w, h, img, 1.0, device=local)
+        c.SetJpegCoeffs(gz.RgbToJpegCoeffs(img))
+        c.CopyFromJpegData()
+        c.ApplyGlobalQuantization(np.full(192, 3, np.int32))
+        dev_ms, wall_ms = [], []
+        for it in range(a.warmup + a.steps):
+            flush.fill_(it & 0xff)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            d = c.Compare()
+            wall = (time.perf_counter() - t0) * 1e3
+            if it >= a.warmup:
+                dev_ms.append(c.last_device_ms()); wall_ms.append(wall)
+        ms = sum(dev_ms) / len(dev_ms)
+        sweep.append({"size": "%dx%d" % (w, h), "mpix": w * h / 1e6, "compare_device_ms": ms,
+                      "compare_wall_ms": sum(wall_ms) / len(wall_ms), "mpix_per_s": w * h / 1e6 / (ms / 1e3),
+                      "hbm_frac_U1": ALGO_BYTES_COMPARE_PER_PX * w * h / (ms / 1e3) / 1e9 / peak, "distance": float(d)})
+        c.close()
+    qsweep = []
+    w, h = 3840, 2160
+    img = _libs.synth_image(w, h, 1234)
+    for q in range(84, 101, 2):
+        target = np.float32(gz.ButteraugliScoreForQuality(q))
+        t0 = time.perf_counter()
+        jpg, st, _ = gz.Process(img, target, device=local, host_threads=min(16, os.cpu_count() or 1))
+        dt = time.perf_counter() - t0
+        qsweep.append({"quality": q, "target": float(target), "encode_s": dt, "mpix_per_s": w * h / 1e6 / dt,
+                       "bytes": len(jpg), "iterations": st["num_iterations"], "compares": st["num_compares"],
+                       "device_compare_ms": st["device_compare_ms"], "device_zeroing_ms": st["device_zeroing_ms"]})
+    big = sweep[3]
+    print(json.dumps({"metric": "butteraugli MPix/s", "value": big["mpix_per_s"], "unit": "MPix/s", "n_gpus": 1,
+                      "steps": a.steps, "warmup": a.warmup, "ms_per_step": big["compare_device_ms"],
+                      "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "standalone butteraugli Compare of the all-3-quantised candidate vs the original, "
+                                             "value quoted at 4000x3000; l2 flushed between calls", "mode": "butteraugli"},
+                      "peak_hbm_gbs": peak, "peak_source": peak_src, "algorithmic_bytes_per_px": ALGO_BYTES_COMPARE_PER_PX,
+                      "sweep": sweep, "quality_sweep_3840x2160": qsweep}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -306,10 +383,16 @@ def main():
     ap.add_argument("--size", default="1024x1024", type=lambda s: tuple(int(v) for v in s.lower().split("x")))
     ap.add_argument("--quality", type=float, default=90.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="batch", choices=["batch", "group", "butteraugli"],
+                    help="batch: one image per GPU (BASELINE configs[1]/[3]); group: one image shared by all GPUs "
+                         "(configs[2]); butteraugli: standalone Compare sweep + quality sweep (configs[4])")
     a = ap.parse_args()
     rank, world, local = dist_env()
     if a.impl == "reference":
         run_reference(a, rank, world)
+    elif a.mode == "butteraugli":
+        if rank == 0:
+            run_butteraugli_sweep(a, local)
     else:
         run_ours(a, rank, world, local)
 

@@ -205,17 +205,21 @@ class ButteraugliComparator:
         _check(lib().gzb_compute_block_zeroing_order(self._ctx, comp_mask, _p(out)), self._ctx)
         return out
 
-    def ComputeBlockZeroingCandidates(self, comp_mask=7):
-        """(candidate_coeff_offsets[nblocks+1], candidate_coeffs u8, candidate_coeff_errors f32)."""
+    def ComputeBlockZeroingCandidates(self, comp_mask=7, block_begin=0, block_end=None):
+        """(candidate_coeff_offsets[n+1], candidate_coeffs u8, candidate_coeff_errors f32) of the
+        blocks [block_begin, block_end) (default: all)."""
         L = lib()
-        L.gzb_compute_block_zeroing_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                           C.c_size_t, C.POINTER(C.c_size_t)]
-        off = np.zeros(self.num_blocks + 1, np.int32)
-        cap = self.num_blocks * 192
+        L.gzb_compute_block_zeroing_candidates_range.argtypes = [
+            C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        b1 = self.num_blocks if block_end is None else block_end
+        nloc = b1 - block_begin
+        off = np.zeros(nloc + 1, np.int32)
+        cap = max(1, nloc * 192)
         idx = np.zeros(cap, np.uint8)
         err = np.zeros(cap, np.float32)
         n = C.c_size_t()
-        _check(L.gzb_compute_block_zeroing_candidates(self._ctx, comp_mask, _p(off), _p(idx), _p(err), cap, C.byref(n)), self._ctx)
+        _check(L.gzb_compute_block_zeroing_candidates_range(self._ctx, comp_mask, block_begin, b1, _p(off), _p(idx), _p(err),
+                                                            cap, C.byref(n)), self._ctx)
         return off, idx[:n.value].copy(), err[:n.value].copy()
 
     def ComputeBlockErrorAdjustmentWeights(self, direction, max_block_dist, target_mul, distmap=None):
@@ -297,7 +301,8 @@ class EncodeStats(C.Structure):
                 ("be_walk_ms", C.c_double), ("be_update_ms", C.c_double), ("create_ms", C.c_double),
                 ("be_codes_ms", C.c_double), ("be_sort_ms", C.c_double), ("be_steps", C.c_ulonglong),
                 ("prepare_ms", C.c_double), ("run_ms", C.c_double), ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong),
-                ("final_score", C.c_double), ("final_distance", C.c_float), ("launches", C.c_ulonglong)]
+                ("final_score", C.c_double), ("final_distance", C.c_float), ("launches", C.c_ulonglong),
+                ("search_rounds", C.c_int), ("search_trials", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -408,6 +413,17 @@ class Encoder:
             L.gzb_free(tr)
         return data, st.as_dict(), trace
 
+    def set_group(self, rank, world, allgather):
+        """gzb_encoder_set_group: this encoder becomes rank `rank` of `world` encoders of the SAME
+        image (one per GPU). `allgather(send: bytes-like) -> bytes` must return the concatenation of
+        every rank's buffer in rank order (see torch_allgather)."""
+        self._cb = make_allgather_callback(allgather, world)   # keep the thunk alive
+        L = lib()
+        L.gzb_encoder_set_group.argtypes = [C.c_void_p, C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p]
+        rc = L.gzb_encoder_set_group(self._enc, rank, world, self._cb, None)
+        if rc != 0:
+            raise GzbError("gzb_encoder_set_group failed (%d): %s" % (rc, L.gzb_encode_last_error().decode(errors="replace")))
+
     def kernel_times(self):
         return profile_get(self._ctx)
 
@@ -421,6 +437,83 @@ class Encoder:
             self.close()
         except Exception:
             pass
+
+
+# ---- multi-GPU group plumbing (gzb_allgather_fn) -------------------------------------------------
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+def make_allgather_callback(allgather, world):
+    def thunk(user, send, nbytes, recv):
+        try:
+            out = allgather(C.string_at(send, nbytes))
+            if len(out) != world * nbytes:
+                return -1
+            C.memmove(recv, bytes(out), world * nbytes)
+            return 0
+        except Exception:  # never let an exception cross the C boundary
+            import traceback
+            traceback.print_exc()
+            return -2
+    return ALLGATHER_FN(thunk)
+
+
+def torch_allgather(dist, device):
+    """An allgather(bytes)->bytes over torch.distributed: NCCL over NVLink/NVSwitch when `device` is
+    a CUDA device (the exchange buffers are staged through HBM), gloo for the CPU tests."""
+    import torch
+    world = dist.get_world_size()
+
+    def allgather(buf):
+        t = torch.frombuffer(bytearray(buf), dtype=torch.uint8).to(device)
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return b"".join(o.cpu().numpy().tobytes() for o in outs)
+    return allgather
+
+
+def ProcessGroup(rgb, butteraugli_target, dist, device=0, host_threads=0, want_trace=False):
+    """guetzli::Process of ONE image by all ranks of a torch.distributed group (one rank per GPU):
+    SelectQuantMatrix candidates and zeroing-search blocks are sharded, rank 0 returns the JPEG
+    (other ranks return b""). Returns (jpeg_bytes, stats_dict, trace_or_None)."""
+    import torch
+    dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    enc = Encoder(rgb, butteraugli_target, device=device, host_threads=host_threads)
+    try:
+        enc.set_group(dist.get_rank(), dist.get_world_size(), torch_allgather(dist, dev))
+        return enc.run(want_trace)
+    finally:
+        enc.close()
+
+
+def QuantSearchSimulate(rank, world, allgather, target, eval_fn):
+    """Test hook (no GPU): runs the speculative SelectQuantMatrix search of gzb_quant_search.h with
+    `eval_fn(original, q[192]) -> (distance, jpg_size)` standing in for the GPU trial. Returns
+    {"visited": [(original, hscore, distance, size)], "best_q": [192], "best_ok": bool, "rounds": n,
+     "evaluated_here": n, "evaluated_total": n}."""
+    L = lib()
+    EVAL = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_uint64))
+
+    def ev(user, original, q, dist_out, size_out):
+        d, sz = eval_fn(bool(original), [q[i] for i in range(192)])
+        dist_out[0] = d
+        size_out[0] = sz
+        return 0
+    ev_c = EVAL(ev)
+    cb = make_allgather_callback(allgather, world) if world > 1 else ALLGATHER_FN(0)
+    cap = 256
+    vis = np.zeros((cap, 4), np.float64)
+    nvis = C.c_int()
+    best_q = np.zeros(192, np.int32)
+    info = np.zeros(4, np.int32)
+    L.gzb_test_quant_search.argtypes = [C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p, EVAL, C.c_void_p, C.c_float,
+                                        C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+    rc = L.gzb_test_quant_search(rank, world, cb, None, ev_c, None, C.c_float(target), _p(vis), cap, C.byref(nvis),
+                                 _p(best_q), _p(info))
+    if rc != 0:
+        raise GzbError("gzb_test_quant_search failed (%d)" % rc)
+    return {"visited": [tuple(v) for v in vis[:nvis.value].tolist()], "best_q": best_q.tolist(), "best_ok": bool(info[0]),
+            "rounds": int(info[1]), "evaluated_here": int(info[2]), "evaluated_total": int(info[3])}
 
 
 def profile_enable(ctx, on=True):

@@ -252,7 +252,7 @@ struct gzb_ctx {
   std::vector<Req> reqs;
   bool upd_own = false;
   bool packed_valid = false;   // packed zeroing candidates still sit in d_tmp
-  int packed_mask = 0;
+  int packed_mask = 0, packed_b0 = 0, packed_b1 = 0;
   Prof prof;
   bool have_orig_coeffs = false, have_coeffs = false, block_cmp = false, have_distmap = false;
   int sm_count = 148;
@@ -289,7 +289,7 @@ struct gzb_ctx {
   BlurPlan p_ops, p_ed[3], p_lf, p_mk[3], p_mkb2, p_dm;
 };
 
-static std::string g_create_err;
+static thread_local std::string g_create_err;
 
 namespace {
 
@@ -743,15 +743,18 @@ int gzb_finish_block_comparisons(gzb_ctx* c) {
   return GZB_OK;
 }
 
-static int run_zeroing(gzb_ctx* c, int comp_mask, int mode) {
+static int run_zeroing(gzb_ctx* c, int comp_mask, int mode, int b0 = 0, int b1 = -1) {
   const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+  if (b1 < 0) b1 = c->nblocks;
   CK(cudaMemsetAsync(c->d_scalars + 1, 0, sizeof(unsigned int), c->stream));
-  if (mode == 0) CK(cudaMemsetAsync(c->d_order, 0, sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(c->nblocks), c->stream));
-  const int ctas = std::min((c->nblocks + kZeroWarps - 1) / kZeroWarps, c->sm_count * 5);
+  if (mode == 0)
+    CK(cudaMemsetAsync(c->d_order + 192 * static_cast<size_t>(b0), 0,
+                       sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(b1 - b0), c->stream));
+  const int ctas = std::max(1, std::min((b1 - b0 + kZeroWarps - 1) / kZeroWarps, c->sm_count * 5));
   CK(cudaEventRecord(c->ev0, c->stream));
   KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<ctas, 32 * kZeroWarps, 0, c->stream>>>(
-      c->d_orig, c->d_coef, cs, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, c->nblocks, c->d_mask_scale, comp_mask,
-      c->target, 3, mode, 0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1));
+      c->d_orig, c->d_coef, cs, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, b1, c->d_mask_scale, comp_mask,
+      c->target, 3, mode, 0, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1));
   CK(cudaEventRecord(c->ev1, c->stream));
   return 0;
 }
@@ -791,7 +794,7 @@ int gzb_compare_block(gzb_ctx* c, int block_x, int block_y, const int16_t* candi
   CK(cudaMemsetAsync(c->d_scalars + 1, 0, sizeof(unsigned int), c->stream));
   KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<1, 32 * kZeroWarps, 0, c->stream>>>(
       d_cand, d_cand, 64, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, 1, c->d_mask_scale, 7, c->target, 3, 2,
-      block_y * c->bw + block_x, nullptr, c->d_block_err, nullptr, c->d_scalars + 1));
+      block_y * c->bw + block_x, 0, nullptr, c->d_block_err, nullptr, c->d_scalars + 1));
   CK(cudaMemcpyAsync(c->h_pinned, c->d_block_err, sizeof(float), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 4;
   sync_check(c);
   *err = static_cast<double>(c->h_pinned[0]);
@@ -810,30 +813,36 @@ int gzb_compute_block_zeroing_order(gzb_ctx* c, int comp_mask, gzb_coeff_data* o
   GZB_END(c)
 }
 
-int gzb_compute_block_zeroing_candidates(gzb_ctx* c, int comp_mask, int* offsets, uint8_t* cand_idx, float* cand_err,
-                                         size_t cap, size_t* n_out) {
+int gzb_compute_block_zeroing_candidates_range(gzb_ctx* c, int comp_mask, int block_begin, int block_end, int* offsets,
+                                               uint8_t* cand_idx, float* cand_err, size_t cap, size_t* n_out) {
   GZB_TRY(c)
   if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_compute_block_zeroing_candidates: StartBlockComparisons not called");
   if (!c->have_coeffs || !c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compute_block_zeroing_candidates: coefficients missing");
-  if (comp_mask < 1 || comp_mask > 7 || !offsets || !n_out) return fail(c, GZB_ERR_BAD_ARG, "gzb_compute_block_zeroing_candidates: bad argument");
-  // d_tmp (6 planes of scratch) holds counts | offsets | packed idx | packed err
+  if (comp_mask < 1 || comp_mask > 7 || !offsets || !n_out || block_begin < 0 || block_end > c->nblocks || block_begin > block_end)
+    return fail(c, GZB_ERR_BAD_ARG, "gzb_compute_block_zeroing_candidates: bad argument");
+  const int nloc = block_end - block_begin;
+  if (nloc == 0) { offsets[0] = 0; *n_out = 0; return GZB_OK; }
+  // d_tmp (6 planes of scratch) holds counts | offsets | packed err | packed idx
   int* d_counts = reinterpret_cast<int*>(c->d_tmp);
   int* d_offsets = d_counts + c->nblocks + 32;
   float* d_err = reinterpret_cast<float*>(d_offsets + c->nblocks + 32);
   uint8_t* d_idx = reinterpret_cast<uint8_t*>(d_err + static_cast<size_t>(192) * c->nblocks);
-  if (!(c->packed_valid && c->packed_mask == comp_mask)) {  // a repeated call only re-fetches
-    run_zeroing(c, comp_mask, 0);
-    const int g = (c->nblocks * 32 + 255) / 256;
-    KLAUNCH(c, KC_MISC, k_count_candidates<<<g, 256, 0, c->stream>>>(reinterpret_cast<const CoeffRec*>(c->d_order), c->nblocks, c->target, d_counts));
-    KLAUNCH(c, KC_MISC, k_scan_counts<<<1, 1024, 0, c->stream>>>(d_counts, c->nblocks, d_offsets));
-    KLAUNCH(c, KC_MISC, k_pack_candidates<<<g, 256, 0, c->stream>>>(reinterpret_cast<const CoeffRec*>(c->d_order), c->nblocks, c->target, d_offsets, d_idx, d_err));
+  if (!(c->packed_valid && c->packed_mask == comp_mask && c->packed_b0 == block_begin && c->packed_b1 == block_end)) {
+    run_zeroing(c, comp_mask, 0, block_begin, block_end);  // a repeated call only re-fetches
+    const CoeffRec* recs = reinterpret_cast<const CoeffRec*>(c->d_order) + static_cast<size_t>(block_begin) * 192;
+    const int g = (nloc * 32 + 255) / 256;
+    KLAUNCH(c, KC_MISC, k_count_candidates<<<g, 256, 0, c->stream>>>(recs, nloc, c->target, d_counts));
+    KLAUNCH(c, KC_MISC, k_scan_counts<<<1, 1024, 0, c->stream>>>(d_counts, nloc, d_offsets));
+    KLAUNCH(c, KC_MISC, k_pack_candidates<<<g, 256, 0, c->stream>>>(recs, nloc, c->target, d_offsets, d_idx, d_err));
     c->packed_valid = true;
     c->packed_mask = comp_mask;
+    c->packed_b0 = block_begin;
+    c->packed_b1 = block_end;
   }
-  CK(cudaMemcpyAsync(offsets, d_offsets, (static_cast<size_t>(c->nblocks) + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (static_cast<size_t>(c->nblocks) + 1) * sizeof(int);
+  CK(cudaMemcpyAsync(offsets, d_offsets, (static_cast<size_t>(nloc) + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (static_cast<size_t>(nloc) + 1) * sizeof(int);
   sync_check(c);
   CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
-  const size_t n = static_cast<size_t>(offsets[c->nblocks]);
+  const size_t n = static_cast<size_t>(offsets[nloc]);
   *n_out = n;
   if (n > 0 && cand_idx && cand_err && cap >= n) {
     CK(cudaMemcpyAsync(cand_idx, d_idx, n, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += n;
@@ -841,6 +850,12 @@ int gzb_compute_block_zeroing_candidates(gzb_ctx* c, int comp_mask, int* offsets
     sync_check(c);
   }
   GZB_END(c)
+}
+
+int gzb_compute_block_zeroing_candidates(gzb_ctx* c, int comp_mask, int* offsets, uint8_t* cand_idx, float* cand_err,
+                                         size_t cap, size_t* n_out) {
+  if (!c) return GZB_ERR_BAD_ARG;
+  return gzb_compute_block_zeroing_candidates_range(c, comp_mask, 0, c->nblocks, offsets, cand_idx, cand_err, cap, n_out);
 }
 
 int gzb_dct_double(int device, double* blocks, size_t nblocks, int inverse) {

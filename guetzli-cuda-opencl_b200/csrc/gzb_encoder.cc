@@ -29,6 +29,7 @@
 
 #include "../../include/gzb200.h"
 #include "gzb_jpeg.h"
+#include "gzb_quant_search.h"
 
 namespace {
 
@@ -129,81 +130,10 @@ inline int16_t quantize_coeff(int16_t raw, int q) {
   return static_cast<int16_t>(raw + delta);
 }
 
-// ---- QuantMatrixGenerator (guetzli/processor.cc:162-308) --------------------------------------
-struct QuantData { int q[3][64]; size_t jpg_size; bool dist_ok; };
-
-double contrast_sensitivity(int k) { return 1.0 / (1.0 + gzb::jpeg::kZigZag[k] / 2.0); }
-
-double quant_heuristic_score(const int q[3][64]) {
-  double score = 0.0;
-  for (int c = 0; c < 3; ++c)
-    for (int k = 0; k < 64; ++k) score += 0.5 * (q[c][k] - 1.0) * contrast_sensitivity(k);
-  return score;
-}
-
-class QuantGenerator {
- public:
-  QuantGenerator() : a_(-1.0), b_(-1.0), total_csf_(0.0) {
-    for (int k = 0; k < 64; ++k) total_csf_ += 3.0 * contrast_sensitivity(k);
-  }
-  bool next(int q[3][64]) {
-    for (int iter = 0; iter < 1000; ++iter) {
-      double hscore;
-      if (b_ == -1.0) {
-        if (a_ == -1.0) hscore = total_csf_;
-        else if (a_ < 5.0 * total_csf_) hscore = a_ + total_csf_;
-        else hscore = 2 * (a_ + total_csf_);
-        if (hscore > 100 * total_csf_) return false;
-      } else if (b_ == 0.0) {
-        return false;
-      } else if (a_ == -1.0) {
-        hscore = 0.0;
-      } else {
-        int lo[3][64], hi[3][64];
-        const double eps = 0.05;
-        matrix_for((1 - eps) * a_ + eps * 0.5 * (a_ + b_), lo);
-        matrix_for((1 - eps) * b_ + eps * 0.5 * (a_ + b_), hi);
-        if (memcmp(lo, hi, sizeof(lo)) == 0) return false;
-        hscore = (a_ + b_) * 0.5;
-      }
-      matrix_for(hscore, q);
-      bool retry = false;
-      for (const QuantData& d : seen_)
-        if (memcmp(q, d.q, sizeof(d.q)) == 0) {
-          if (d.dist_ok) a_ = hscore; else b_ = hscore;
-          retry = true;
-          break;
-        }
-      if (!retry) return true;
-    }
-    return false;
-  }
-  void add(const QuantData& d) {
-    seen_.push_back(d);
-    const double hs = quant_heuristic_score(d.q);
-    if (d.dist_ok) a_ = std::max(a_, hs);
-    else b_ = b_ == -1.0 ? hs : std::min(b_, hs);
-  }
-
- private:
-  void matrix_for(double score, int q[3][64]) const {
-    const int level = static_cast<int>(score / total_csf_);
-    score -= level * total_csf_;
-    for (int k = 63; k >= 0; --k) {
-      const int nat = gzb::jpeg::kNaturalOrder[k];
-      for (int c = 0; c < 3; ++c) q[c][nat] = 2 * level + (score > 0.0 ? 3 : 1);
-      score -= 3.0 * contrast_sensitivity(nat);
-    }
-  }
-  double a_, b_, total_csf_;
-  std::vector<QuantData> seen_;
-};
-
-bool quant_data_better(const QuantData& a, const QuantData& b) {
-  if (a.dist_ok && !b.dist_ok) return true;
-  if (!a.dist_ok && b.dist_ok) return false;
-  return a.jpg_size < b.jpg_size;
-}
+using gzb::QuantData;
+using gzb::QuantGenerator;
+using gzb::quant_heuristic_score;
+using gzb::quant_data_better;
 
 // ---- lazy std::sort ---------------------------------------------------------------------------
 // Produces, for any prefix that is asked for, exactly the permutation libstdc++'s std::sort would
@@ -378,6 +308,10 @@ struct Encoder {
   std::string trace;
   bool want_trace = false, ran = false;
   float distance = 0.f;
+  gzb::Group group;                 // multi-GPU candidate sharding (gzb_encoder_set_group)
+  bool best_remote = false;         // the best file so far was written on another rank
+  gzb::Trial best_trial{};          // ... and this is the trial that produced it
+  int search_rounds = 0, search_trials = 0;
 
   void log(const char* fmt, ...) {
     if (!want_trace) return;
@@ -408,15 +342,21 @@ struct Encoder {
     st.num_jpeg_writes++;
   }
 
-  void maybe_output(const std::string& jpeg) {
-    const double score = gzb_score_output_size(ctx, static_cast<int>(jpeg.size()));
-    log(" Score[%.4f]", score);
-    if (score < best_score || best_score < 0) {
-      best_jpeg = jpeg;
-      best_score = score;
-      log(" (*)");
-    }
-    log("\n");
+  // MaybeOutput (processor.cc:151-160) for a trial that may have been evaluated on another rank.
+  void maybe_output_trial(const gzb::Trial& t, const gzb::TrialOutcome& o);
+
+  // the quantised indices of ApplyGlobalQuantization(q) on the q=1 input (host mirror)
+  void quantize_host(const int q[3][64], std::vector<int16_t>* out3) {
+    parallel_rows(nb, pool.get(), [&](int b0, int b1) {
+      for (int c = 0; c < 3; ++c) {
+        const int16_t* o = orig[c].data();
+        int16_t* ix = out3[c].data();
+        for (size_t i = static_cast<size_t>(b0) * 64; i < static_cast<size_t>(b1) * 64; ++i) {
+          const int qq = q[c][i & 63];
+          ix[i] = static_cast<int16_t>(quantize_coeff(o[i], qq) / qq);
+        }
+      }
+    });
   }
 
   bool compare(bool quiet = false) {
@@ -437,16 +377,7 @@ struct Encoder {
     if (gzb_copy_from_jpeg(ctx, ones) != GZB_OK) return false;
     if (gzb_apply_global_quantization(ctx, &q[0][0]) != GZB_OK) return false;
     memcpy(quant, q, sizeof(quant));
-    parallel_rows(nb, pool.get(), [&](int b0, int b1) {
-      for (int c = 0; c < 3; ++c) {
-        const int16_t* o = orig[c].data();
-        int16_t* ix = idx[c].data();
-        for (size_t i = static_cast<size_t>(b0) * 64; i < static_cast<size_t>(b1) * 64; ++i) {
-          const int qq = q[c][i & 63];
-          ix[i] = static_cast<int16_t>(quantize_coeff(o[i], qq) / qq);
-        }
-      }
-    });
+    quantize_host(q, idx);
     st.host_quant_ms += now_ms() - t0;
     return true;
   }
@@ -461,6 +392,24 @@ double score_jpeg(double distance, int size, double target) {
   const double ex = 50 * diff;
   if (ex > 10) return 1e30 * std::exp(10.0) * diff + size;
   return std::exp(ex) * size;
+}
+
+void Encoder::maybe_output_trial(const gzb::Trial& t, const gzb::TrialOutcome& o) {
+  const double score = score_jpeg(o.distance, static_cast<int>(o.jpg_size), target);
+  log(" Score[%.4f]", score);
+  if (score < best_score || best_score < 0) {
+    best_score = score;
+    if (o.owner == group.rank) {
+      best_jpeg = o.jpeg;
+      best_remote = false;
+    } else {  // the bytes live on another rank: remember how to rebuild them if they stay the best
+      best_jpeg.clear();
+      best_remote = true;
+      best_trial = t;
+    }
+    log(" (*)");
+  }
+  log("\n");
 }
 
 // One back-end iteration's file: the coefficient flips to apply, the AC histograms after them, and
@@ -541,6 +490,7 @@ class WriterStage {
       if (score < e_->best_score || e_->best_score < 0) {
         e_->best_jpeg.swap(jpg);
         e_->best_score = score;
+        e_->best_remote = false;
         e_->log(" (*)");
       }
       e_->log("\n");
@@ -586,7 +536,7 @@ double gzb_butteraugli_score_for_quality(double quality) {
 
 void gzb_free(void* p) { free(p); }
 
-static std::string g_encode_err;
+static thread_local std::string g_encode_err;
 const char* gzb_encode_last_error(void) { return g_encode_err.c_str(); }
 
 int gzb_rgb_to_jpeg_coeffs(const uint8_t* rgb, int width, int height, int16_t* c0, int16_t* c1, int16_t* c2) {
@@ -691,6 +641,44 @@ void gzb_test_huffman_depths(const uint32_t* counts257, uint8_t* depth257, const
 }
 
 // Test hooks: the lazy order must equal std::sort's permutation on the consumed prefix.
+// Test hook (CPU only): the speculative SelectQuantMatrix search with a caller-provided evaluator.
+// visited: rows of {original, heuristic score, distance, jpg_size}; info: {best.dist_ok, rounds,
+// evaluated on this rank, evaluated by the group}.
+int gzb_test_quant_search(int rank, int world, gzb_allgather_fn allgather, void* user,
+                          int (*eval_fn)(void*, int, const int*, float*, uint64_t*), void* eval_user, float target,
+                          double* visited, int cap, int* nvisited, int* best_q192, int* info) {
+  gzb::Group g;
+  g.rank = rank; g.world = world; g.allgather = allgather; g.user = user;
+  gzb::QuantSearch search(g, target);
+  int n = 0;
+  const bool ok = search.run(
+      [&](const gzb::Trial& t, gzb::TrialOutcome* o) {
+        float d = 0.f;
+        uint64_t sz = 0;
+        if (eval_fn(eval_user, t.original, &t.q[0][0], &d, &sz) != 0) return false;
+        o->distance = d;
+        o->jpg_size = sz;
+        return true;
+      },
+      [&](const gzb::Trial& t, const gzb::TrialOutcome& o) {
+        if (n < cap) {
+          visited[4 * n] = t.original;
+          visited[4 * n + 1] = quant_heuristic_score(t.q);
+          visited[4 * n + 2] = o.distance;
+          visited[4 * n + 3] = static_cast<double>(o.jpg_size);
+        }
+        ++n;
+      });
+  if (!ok) return GZB_ERR_STATE;
+  *nvisited = std::min(n, cap);
+  memcpy(best_q192, search.best().q, sizeof(int) * 192);
+  info[0] = search.best().dist_ok ? 1 : 0;
+  info[1] = search.rounds();
+  info[2] = search.evaluated_here();
+  info[3] = search.evaluated_total();
+  return GZB_OK;
+}
+
 void gzb_test_lazy_sort(int* first, float* second, size_t n, size_t prefix) {
   std::vector<OrderEntry> v(n);
   for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(first[i], second[i]);
@@ -765,6 +753,19 @@ void gzb_encoder_destroy(gzb_encoder* enc) {
 
 gzb_ctx* gzb_encoder_context(gzb_encoder* enc) { return enc ? enc->e.ctx : nullptr; }
 
+int gzb_encoder_set_group(gzb_encoder* enc, int rank, int world, gzb_allgather_fn allgather, void* user) {
+  if (!enc || world < 1 || rank < 0 || rank >= world || (world > 1 && !allgather)) {
+    g_encode_err = "gzb_encoder_set_group: bad argument";
+    return GZB_ERR_BAD_ARG;
+  }
+  if (enc->e.ran) { g_encode_err = "gzb_encoder_set_group: the encoder has already run"; return GZB_ERR_STATE; }
+  enc->e.group.rank = rank;
+  enc->e.group.world = world;
+  enc->e.group.allgather = allgather;
+  enc->e.group.user = user;
+  return GZB_OK;
+}
+
 int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
                     char** trace_out) {
   if (!enc || !jpeg_out || !jpeg_size) { g_encode_err = "gzb_encoder_run: null argument"; return GZB_ERR_BAD_ARG; }
@@ -783,57 +784,61 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   int ones[3][64];
   for (int c = 0; c < 3; ++c) for (int k = 0; k < 64; ++k) ones[c][k] = 1;
   // "Original": the q=1 input as a JPEG with three index-0 tables (processor.cc:967-985)
-  std::string encoded;
-  {
+  auto write_original = [&](std::string* out) {
     Frame f;
     f.width = width; f.height = height; f.bw = e.bw; f.bh = e.bh; f.ncomp = 3;
     for (int c = 0; c < 3; ++c) f.coeffs[c] = e.orig[c].data();
     gzb::jpeg::frame_set_quant_input(&f, ones);
     const double t0 = now_ms();
-    gzb::jpeg::write_jpeg(f, &encoded, e.pool.get(), nullptr, nullptr, &e.wt);
+    gzb::jpeg::write_jpeg(f, out, e.pool.get(), nullptr, nullptr, &e.wt);
     e.st.host_write_ms += now_ms() - t0;
     e.st.num_jpeg_writes++;
-  }
-  e.log("Original Out[%7zd]", encoded.size());
-  if (gzb_copy_from_jpeg(e.ctx, &ones[0][0]) != GZB_OK) return fail(GZB_ERR_CUDA);
-  if (!e.compare()) return fail(GZB_ERR_CUDA);
-  e.maybe_output(encoded);
-
-  // ---- SelectQuantMatrix (processor.cc:310-372) ----
-  int best_q[3][64];
-  memcpy(best_q, ones, sizeof(best_q));
-  auto try_quant = [&](int q[3][64], QuantData* data) -> bool {
-    memcpy(data->q, q, sizeof(data->q));
-    if (!e.set_global_quant(q)) return false;
-    std::string jpg;
-    e.write_candidate(&jpg);
-    e.log("Iter %2d: f111111 GQ[%5.2f] Out[%7zd]", e.st.num_iterations + 1, quant_heuristic_score(q), jpg.size());
-    ++e.st.num_iterations;
-    if (!e.compare()) return false;
-    data->dist_ok = gzb_distance_ok(e.ctx, 0.97f) != 0;  // target_mul_high is a float constant
-    data->jpg_size = jpg.size();
-    e.maybe_output(jpg);
-    return true;
   };
-  QuantData best;
-  if (!try_quant(best_q, &best)) return fail(GZB_ERR_CUDA);
+
+  // ---- the original + SelectQuantMatrix (processor.cc:310-372, 986-1003) ----
+  // Trials are evaluated one per rank of the group (gzb_quant_search.h) and visited in the
+  // reference's order; with a group of one this is the reference's sequential loop.
+  int best_q[3][64];
   {
-    QuantGenerator gen;
-    for (;;) {
-      int q_next[3][64];
-      if (!gen.next(q_next)) break;
-      QuantData data;
-      if (!try_quant(q_next, &data)) return fail(GZB_ERR_CUDA);
-      gen.add(data);
-      if (quant_data_better(data, best)) {
-        best = data;
-        if (data.dist_ok && !gzb_distance_ok(e.ctx, 0.95f)) break;
+    gzb::QuantSearch search(e.group, e.target);
+    auto evaluate = [&](const gzb::Trial& t, gzb::TrialOutcome* o) -> bool {
+      if (t.original) {
+        write_original(&o->jpeg);
+        if (gzb_copy_from_jpeg(e.ctx, &ones[0][0]) != GZB_OK) return false;
+      } else {
+        int q[3][64];
+        memcpy(q, t.q, sizeof(q));
+        if (!e.set_global_quant(q)) return false;
+        e.write_candidate(&o->jpeg);
       }
+      if (!e.compare(true)) return false;
+      o->distance = e.distance;
+      o->jpg_size = o->jpeg.size();
+      return true;
+    };
+    auto visit = [&](const gzb::Trial& t, const gzb::TrialOutcome& o) {
+      if (t.original) {
+        e.log("Original Out[%7zd]", static_cast<size_t>(o.jpg_size));
+      } else {
+        e.log("Iter %2d: f111111 GQ[%5.2f] Out[%7zd]", e.st.num_iterations + 1, quant_heuristic_score(t.q),
+              static_cast<size_t>(o.jpg_size));
+        ++e.st.num_iterations;
+      }
+      e.log(" BA[100.00%%] D[%6.4f]", o.distance);
+      e.maybe_output_trial(t, o);
+    };
+    if (!search.run(evaluate, visit)) {
+      if (g_encode_err.empty()) g_encode_err = gzb_last_error(e.ctx);
+      if (g_encode_err.empty()) g_encode_err = "gzb_encoder_run: the group exchange failed";
+      return GZB_ERR_CUDA;
     }
+    e.search_rounds = search.rounds();
+    e.search_trials = search.evaluated_total();
+    const QuantData& best = search.best();
+    memcpy(best_q, best.q, sizeof(best_q));
+    if (!best.dist_ok)
+      for (int c = 0; c < 3; ++c) for (int k = 0; k < 64; ++k) best_q[c][k] = 1;
   }
-  memcpy(best_q, best.q, sizeof(best_q));
-  if (!best.dist_ok)
-    for (int c = 0; c < 3; ++c) for (int k = 0; k < 64; ++k) best_q[c][k] = 1;
   if (!e.set_global_quant(best_q)) return fail(GZB_ERR_CUDA);
 
   // ---- SelectFrequencyMasking(jpg, img, 7, 1.0, false) (processor.cc:559-721) ----
@@ -846,22 +851,90 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   {
     if (gzb_start_block_comparisons(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
     const double t0 = now_ms();
+    // the blocks are independent: rank r of the group searches blocks [nb*r/world, nb*(r+1)/world)
+    const int world = e.group.world, rank = e.group.rank;
+    const int b0 = static_cast<int>(static_cast<int64_t>(num_blocks) * rank / world);
+    const int b1 = static_cast<int>(static_cast<int64_t>(num_blocks) * (rank + 1) / world);
+    const int nloc = b1 - b0;
+    std::vector<int> loc_off(nloc + 1);
     size_t ncand = 0;
-    cand_coeffs.resize(static_cast<size_t>(num_blocks) * 48);
+    cand_coeffs.resize(static_cast<size_t>(nloc) * 48 + 16);
     cand_errors.resize(cand_coeffs.size());
-    if (gzb_compute_block_zeroing_candidates(e.ctx, comp_mask, cand_offsets.data(), cand_coeffs.data(), cand_errors.data(),
-                                             cand_coeffs.size(), &ncand) != GZB_OK) return fail(GZB_ERR_CUDA);
+    if (gzb_compute_block_zeroing_candidates_range(e.ctx, comp_mask, b0, b1, loc_off.data(), cand_coeffs.data(),
+                                                   cand_errors.data(), cand_coeffs.size(), &ncand) != GZB_OK) return fail(GZB_ERR_CUDA);
     if (ncand > cand_coeffs.size()) {  // more than 48 candidates per block on average: fetch again (no recompute)
       cand_coeffs.resize(ncand);
       cand_errors.resize(ncand);
-      if (gzb_compute_block_zeroing_candidates(e.ctx, comp_mask, cand_offsets.data(), cand_coeffs.data(), cand_errors.data(),
-                                               ncand, &ncand) != GZB_OK) return fail(GZB_ERR_CUDA);
+      if (gzb_compute_block_zeroing_candidates_range(e.ctx, comp_mask, b0, b1, loc_off.data(), cand_coeffs.data(),
+                                                     cand_errors.data(), ncand, &ncand) != GZB_OK) return fail(GZB_ERR_CUDA);
     }
     cand_coeffs.resize(ncand);
     cand_errors.resize(ncand);
     e.st.device_zeroing_ms = gzb_last_device_ms(e.ctx);
+    if (world == 1) {
+      cand_offsets = loc_off;
+    } else {
+      // all-gather 1: every rank's per-block offsets (padded to the longest range) -> global offsets
+      const int maxloc = (num_blocks + world - 1) / world + 1;
+      std::vector<int> send_off(maxloc + 1, 0), all_off(static_cast<size_t>(world) * (maxloc + 1));
+      memcpy(send_off.data(), loc_off.data(), sizeof(int) * (nloc + 1));
+      send_off[maxloc] = static_cast<int>(ncand);
+      if (e.group.allgather(e.group.user, send_off.data(), sizeof(int) * (maxloc + 1), all_off.data()) != 0) {
+        g_encode_err = "gzb_encoder_run: the group exchange failed";
+        return GZB_ERR_CUDA;
+      }
+      size_t maxn = 0, total = 0;
+      std::vector<size_t> base(world + 1, 0);
+      for (int r = 0; r < world; ++r) {
+        const size_t n = static_cast<size_t>(all_off[static_cast<size_t>(r) * (maxloc + 1) + maxloc]);
+        maxn = std::max(maxn, n);
+        base[r + 1] = base[r] + n;
+        total += n;
+      }
+      for (int r = 0; r < world; ++r) {
+        const int rb0 = static_cast<int>(static_cast<int64_t>(num_blocks) * r / world);
+        const int rb1 = static_cast<int>(static_cast<int64_t>(num_blocks) * (r + 1) / world);
+        const int* ro = &all_off[static_cast<size_t>(r) * (maxloc + 1)];
+        for (int b = rb0; b < rb1; ++b) cand_offsets[b] = static_cast<int>(base[r]) + ro[b - rb0];
+      }
+      cand_offsets[num_blocks] = static_cast<int>(total);
+      // all-gather 2: the packed candidates, [errors | coefficient indices], padded to the longest
+      const size_t rec = maxn * 5;
+      std::vector<uint8_t> send(rec + 1, 0), all(static_cast<size_t>(world) * (rec + 1));
+      memcpy(send.data(), cand_errors.data(), ncand * sizeof(float));
+      memcpy(send.data() + maxn * 4, cand_coeffs.data(), ncand);
+      if (e.group.allgather(e.group.user, send.data(), rec + 1, all.data()) != 0) {
+        g_encode_err = "gzb_encoder_run: the group exchange failed";
+        return GZB_ERR_CUDA;
+      }
+      cand_coeffs.resize(total);
+      cand_errors.resize(total);
+      for (int r = 0; r < world; ++r) {
+        const size_t n = base[r + 1] - base[r];
+        const uint8_t* src = all.data() + static_cast<size_t>(r) * (rec + 1);
+        memcpy(cand_errors.data() + base[r], src, n * sizeof(float));
+        memcpy(cand_coeffs.data() + base[r], src + maxn * 4, n);
+      }
+    }
     e.st.zeroing_wall_ms = now_ms() - t0;
     gzb_finish_block_comparisons(e.ctx);
+  }
+
+  // The back end is one sequential walk: rank 0 of a group finishes the image alone.
+  if (e.group.rank != 0) {
+    e.st.launches = gzb_launch_count(e.ctx);
+    gzb_get_transfer_bytes(e.ctx, &e.st.h2d_bytes, &e.st.d2h_bytes);
+    e.st.run_ms = now_ms() - t_start;
+    e.st.total_wall_ms = e.st.prepare_ms + e.st.run_ms;
+    e.st.search_rounds = e.search_rounds;
+    e.st.search_trials = e.search_trials;
+    *jpeg_out = static_cast<uint8_t*>(malloc(1));
+    if (stats) *stats = e.st;
+    if (trace_out) {
+      *trace_out = static_cast<char*>(malloc(e.trace.size() + 1));
+      memcpy(*trace_out, e.trace.c_str(), e.trace.size() + 1);
+    }
+    return GZB_OK;
   }
 
   // ---- SelectFrequencyBackEnd (processor.cc:723-919) ----
@@ -1153,6 +1226,21 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
     e.st.backend_wall_ms = now_ms() - t_be;
   }
 
+  if (e.best_remote) {
+    // the winning file is a SelectQuantMatrix trial that another rank wrote: rebuild its bytes
+    if (e.best_trial.original) {
+      write_original(&e.best_jpeg);
+    } else {
+      int q[3][64];
+      memcpy(q, e.best_trial.q, sizeof(q));
+      e.quantize_host(q, e.idx);
+      memcpy(e.quant, q, sizeof(e.quant));
+      e.write_candidate(&e.best_jpeg);
+    }
+    e.best_remote = false;
+  }
+  e.st.search_rounds = e.search_rounds;
+  e.st.search_trials = e.search_trials;
   e.st.launches = gzb_launch_count(e.ctx);
   e.st.write_hist_ms = e.wt.hist_ms; e.st.write_code_ms = e.wt.code_ms;
   e.st.write_encode_ms = e.wt.encode_ms; e.st.write_stitch_ms = e.wt.stitch_ms;

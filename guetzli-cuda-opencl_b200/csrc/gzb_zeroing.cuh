@@ -186,11 +186,12 @@ constexpr int kZeroWarps = 4;
 // mode 1: single CompareBlock of `cur` with no zeroing -> err_out[block] (stage test entry)
 // mode 2: CompareBlock of ONE block `single_block` whose candidate coefficients are the 192 values
 //         at `cur` (comp_stride 64, nblocks 1) -> err_out[0] (Comparator::CompareBlock adaptor)
+// Blocks [block_begin, nblocks) are processed (a group of GPUs splits the image by block range).
 __global__ void __launch_bounds__(32 * kZeroWarps)
 k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cur,
                 size_t comp_stride, const uint8_t* __restrict__ rgb_planes, size_t plane_stride,
                 int P, int W, int H, int bw, int nblocks, const float* __restrict__ mask_scale,
-                int comp_mask, float limit, int lookahead, int mode, int single_block,
+                int comp_mask, float limit, int lookahead, int mode, int single_block, int block_begin,
                 CoeffDataDev* __restrict__ out, float* __restrict__ err_out,
                 float* __restrict__ pregamma_out, unsigned int* __restrict__ counter) {
   __shared__ ZeroWarpSmem sm[kZeroWarps];
@@ -206,7 +207,7 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
   for (;;) {
     unsigned int b = 0;
     if (lane == 0) b = atomicAdd(counter, 1u);
-    b = __shfl_sync(0xffffffffu, b, 0);
+    b = __shfl_sync(0xffffffffu, b, 0) + static_cast<unsigned int>(block_begin);
     if (b >= static_cast<unsigned int>(nblocks)) break;
     const int blk = mode == 2 ? single_block : static_cast<int>(b);  // image block (b indexes coefficients)
     const int bx = blk % bw, by = blk / bw;

@@ -118,6 +118,11 @@ int gzb_compute_block_zeroing_order(gzb_ctx* ctx, int comp_mask, gzb_coeff_data*
  * (candidate_coeff_errors). *n_out = total candidates; the two arrays are filled when cap >= n. */
 int gzb_compute_block_zeroing_candidates(gzb_ctx* ctx, int comp_mask, int* offsets, uint8_t* cand_idx,
                                          float* cand_err, size_t cap, size_t* n_out);
+/* The same for the blocks [block_begin, block_end) only (a group of GPUs splits the blocks):
+ * offsets[block_end - block_begin + 1] are relative to the range. */
+int gzb_compute_block_zeroing_candidates_range(gzb_ctx* ctx, int comp_mask, int block_begin, int block_end,
+                                               int* offsets, uint8_t* cand_idx, float* cand_err, size_t cap,
+                                               size_t* n_out);
 /* ComputeBlockDCTDouble / ComputeBlockIDCTDouble (guetzli/dct_double.cc:47-85), batched: nblocks
  * blocks of 64 doubles, in place. Only the reference's 4:2:0 path uses these transforms. */
 int gzb_dct_double(int device, double* blocks, size_t nblocks, int inverse);
@@ -168,6 +173,7 @@ typedef struct {
   double final_score;
   float final_distance;
   unsigned long long launches;
+  int search_rounds, search_trials;      /* SelectQuantMatrix: exchange rounds / trials evaluated by the group */
 } gzb_encode_stats;
 int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
                    int host_threads, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
@@ -181,6 +187,21 @@ int gzb_encoder_create(int device, const uint8_t* rgb, int width, int height, fl
 int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
                     char** trace_out);
 gzb_ctx* gzb_encoder_context(gzb_encoder* enc);
+/* Multi-GPU, one large image: the encoders of a group -- one per GPU, one per
+ * process, all created from the SAME image and target -- share the work of one encode.
+ *   * SelectQuantMatrix (guetzli/processor.cc:310-372): the independent TryQuantMatrix candidates
+ *     the generator may ask for next are evaluated one per rank; after each round the ranks
+ *     all-gather {distance, jpg_size} and every rank replays the reference's sequential decisions,
+ *     so the visited sequence, the trace and the chosen matrix equal the single-GPU run's.
+ *   * The block-zeroing search (processor.cc:638-672) is split by block range and its candidate
+ *     lists are all-gathered.
+ *   * The back end (processor.cc:723-919) is one sequential walk: rank 0 runs it and returns the
+ *     JPEG; the other ranks return from gzb_encoder_run with *jpeg_size == 0.
+ * `allgather` must gather `nbytes` from every rank into recv[world*nbytes] in rank order (e.g.
+ * ncclAllGather / torch.distributed.all_gather over NCCL) and return 0; it is called the same
+ * number of times with the same sizes on every rank. Call before gzb_encoder_run. */
+typedef int (*gzb_allgather_fn)(void* user, const void* send, size_t nbytes, void* recv);
+int gzb_encoder_set_group(gzb_encoder* enc, int rank, int world, gzb_allgather_fn allgather, void* user);
 void gzb_encoder_destroy(gzb_encoder* enc);
 const char* gzb_encode_last_error(void);
 void gzb_free(void* p);

@@ -121,3 +121,69 @@ def test_compare_block_single_equals_batched(gz):
         assert L.gzb_compare_block(c._ctx, b % c.block_width, b // c.block_width, cand.ctypes.data, C.byref(e)) == 0
         assert np.float32(e.value) == want[b]
     c.close()
+
+
+def run_thread_group(gz, img, target, world):
+    """`world` encoders of the same image as the ranks of a group, one host thread each, on the one
+    GPU of the test box (the exchange is a thread barrier; across GPUs it is NCCL, bench.py)."""
+    import threading
+    from test_quant_search_cpu import BarrierAllGather
+    ag = BarrierAllGather(world)
+    res, err = [None] * world, []
+
+    def work(r):
+        try:
+            enc = gz.Encoder(img, target, host_threads=2)
+            enc.set_group(r, world, ag.for_rank(r))
+            res[r] = enc.run(want_trace=True)
+            enc.close()
+        except Exception as e:  # a dead rank would leave the others at the barrier
+            err.append(e)
+            ag.bar.abort()
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(600)
+    assert not err, err
+    return res
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_group_encode_equals_single_gpu_encode(gz, world):
+    """SelectQuantMatrix candidates and zeroing blocks sharded over a group produce the
+    same trace and the same bytes as the single-GPU encode (== the reference's)."""
+    gold = json.load(open(os.path.join(GOLD, "synth_encodes.json")))["160x120_q95_s1244"]
+    img = synth_image(160, 120, 1244)
+    res = run_thread_group(gz, img, np.float32(gold["target"]), world)
+    jpg, st, trace = res[0]
+    assert hashlib.sha256(jpg).hexdigest() == gold["sha256"]
+    got = trace_records([l for l in trace.splitlines() if "Out[" in l])
+    assert got == trace_records(gold["trace"])
+    assert st["num_iterations"] == gold["iterations"]
+    for r in range(1, world):
+        assert res[r][0] == b""                      # only rank 0 returns the file
+        assert res[r][1]["search_rounds"] == st["search_rounds"]
+    quant_trials = sum(1 for l in gold["trace"] if "GQ[" in l) + 1
+    assert st["search_rounds"] < quant_trials        # fewer serial rounds than trials
+    assert sum(r[1]["num_compares"] for r in res[1:]) > 0   # the other ranks did evaluate trials
+
+
+def test_group_encode_bees_golden(gz):
+    gold = json.load(open(os.path.join(GOLD, "bees_q95.json")))
+    res = run_thread_group(gz, bees(), np.float32(gold["target"]), 4)
+    assert hashlib.sha256(res[0][0]).hexdigest() == gold["sha256"]
+
+
+def test_zeroing_candidates_by_block_range_equal_whole(gz):
+    img = synth_image(96, 72)
+    c = gz.ButteraugliComparator(96, 72, img, 0.97)
+    c.SetJpegCoeffs(gz.RgbToJpegCoeffs(img)); c.CopyFromJpegData(); c.ApplyGlobalQuantization(np.full(192, 2, np.int32))
+    c.StartBlockComparisons()
+    off, idx, err = c.ComputeBlockZeroingCandidates(7)
+    nb = c.num_blocks
+    for (b0, b1) in [(0, nb // 3), (nb // 3, nb - 1), (nb - 1, nb), (5, 5)]:
+        o, i, e = c.ComputeBlockZeroingCandidates(7, b0, b1)
+        assert np.array_equal(o, off[b0:b1 + 1] - off[b0])
+        assert np.array_equal(i, idx[off[b0]:off[b1]]) and np.array_equal(e, err[off[b0]:off[b1]])
+    c.close()

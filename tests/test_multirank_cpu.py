@@ -52,3 +52,46 @@ def test_reference_arm_other_ranks_exit_without_work():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+GROUP_WORKER = textwrap.dedent('''
+    import os, sys, json
+    import torch, torch.distributed as dist
+    sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+    import __graft_entry__ as ge
+    import test_quant_search_cpu as T
+    gz = ge.load_package()
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ev = T.make_eval("typical")
+    # the product's own exchange path (torch.distributed all_gather; NCCL on the GPU box, gloo here)
+    res = gz.QuantSearchSimulate(rank, world, gz.torch_allgather(dist, torch.device("cpu")), 0.971769, ev)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+    if rank == 0:
+        want, best = T.reference_search(ev, 0.971769)
+        print(json.dumps({"res": gathered, "want": want, "best_q": best[0]}))
+    dist.destroy_process_group()
+''') % (ROOT, ROOT)
+
+
+def test_candidate_sharded_quant_search_two_ranks_gloo(tmp_path):
+    """SelectQuantMatrix candidates sharded over 2 ranks with the all-gather going through
+    torch.distributed: both ranks replay the reference's visiting sequence in fewer rounds."""
+    script = tmp_path / "group_worker.py"
+    script.write_text(GROUP_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29519", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    want = [tuple(v) for v in res["want"]]
+    for r in res["res"]:
+        got = [tuple(v) for v in r["visited"]]
+        assert len(got) == len(want)
+        assert all(g[0] == w[0] and abs(g[1] - w[1]) < 1e-9 and g[2] == w[2] and g[3] == w[3] for g, w in zip(got, want))
+        assert r["best_q"] == res["best_q"]
+    assert res["res"][0]["rounds"] == res["res"][1]["rounds"] < len(want)
+    assert res["res"][0]["evaluated_here"] + res["res"][1]["evaluated_here"] == res["res"][0]["evaluated_total"]
