@@ -13,6 +13,7 @@
 //     yields exactly std::sort's permutation for the prefix actually consumed;
 //   * WriteJpeg runs block-row bands on host threads and overlaps the GPU Compare.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -189,6 +190,38 @@ class LazySort {
     });
     sorted_ = pieces.back().last;
   }
+  // Makes positions [0, p) hold exactly the p entries std::sort would put there -- in any order --
+  // and everything from p on final up to sorted(). Used when the first p entries are all consumed
+  // with no observable intermediate state: partition ranges that lie wholly inside [0, p) are never
+  // sorted; only the one range that straddles p is split further and finished.
+  void ensure_set(size_t p) {
+    p = std::min(p, n_);
+    if (p <= sorted_) return;
+    const size_t kPiece = size_t(1) << 14;
+    auto comp = __gnu_cxx::__ops::__iter_comp_iter(OrderLess());
+    size_t done = p;
+    while (!pending_.empty() && pending_.back().first < p) {
+      Range r = pending_.back();
+      pending_.pop_back();
+      if (r.last <= p) continue;  // wholly inside the set
+      if (r.last - r.first <= kPiece || r.depth == 0) {
+        if (r.last - r.first > 1) {
+          std::__introsort_loop(d_ + r.first, d_ + r.last, static_cast<long>(r.depth), comp);
+          std::__insertion_sort(d_ + r.first, d_ + r.last, comp);
+        }
+        done = r.last;
+        break;  // ranges are disjoint and ordered: nothing else starts before p
+      }
+      --r.depth;
+      OrderEntry* cut = (pool_ && pool_->size() > 1 && r.last - r.first >= kParallelMin)
+                            ? parallel_partition_pivot(d_ + r.first, d_ + r.last)
+                            : std::__unguarded_partition_pivot(d_ + r.first, d_ + r.last, comp);
+      const size_t c = static_cast<size_t>(cut - d_);
+      pending_.push_back({c, r.last, r.depth});
+      pending_.push_back({r.first, c, r.depth});
+    }
+    sorted_ = std::max(sorted_, done);
+  }
   size_t sorted() const { return sorted_; }
 
  private:
@@ -346,14 +379,39 @@ struct Encoder {
   void maybe_output_trial(const gzb::Trial& t, const gzb::TrialOutcome& o);
 
   // the quantised indices of ApplyGlobalQuantization(q) on the q=1 input (host mirror)
+  // Quantize(raw, q) / q (quantize.h:24-29) == sign(raw) * (|raw| / q + (2 * (|raw| % q) > q)); the
+  // division is a multiplication by ceil(2^32 / q), exact for |raw| <= 2^15 and q < 2^16.
   void quantize_host(const int q[3][64], std::vector<int16_t>* out3) {
+    uint64_t magic[3][64];
+    bool small = true;
+    for (int c = 0; c < 3; ++c)
+      for (int k = 0; k < 64; ++k) {
+        magic[c][k] = (uint64_t(1) << 32) / static_cast<uint32_t>(q[c][k]) + 1;
+        small = small && q[c][k] < (1 << 16);
+      }
     parallel_rows(nb, pool.get(), [&](int b0, int b1) {
       for (int c = 0; c < 3; ++c) {
         const int16_t* o = orig[c].data();
         int16_t* ix = out3[c].data();
-        for (size_t i = static_cast<size_t>(b0) * 64; i < static_cast<size_t>(b1) * 64; ++i) {
-          const int qq = q[c][i & 63];
-          ix[i] = static_cast<int16_t>(quantize_coeff(o[i], qq) / qq);
+        if (!small) {
+          for (size_t i = static_cast<size_t>(b0) * 64; i < static_cast<size_t>(b1) * 64; ++i) {
+            const int qq = q[c][i & 63];
+            ix[i] = static_cast<int16_t>(quantize_coeff(o[i], qq) / qq);
+          }
+          continue;
+        }
+        for (int b = b0; b < b1; ++b) {
+          const int16_t* ob = o + static_cast<size_t>(b) * 64;
+          int16_t* xb = ix + static_cast<size_t>(b) * 64;
+          for (int k = 0; k < 64; ++k) {
+            const int raw = ob[k];
+            const uint32_t qq = static_cast<uint32_t>(q[c][k]);
+            const uint32_t n = static_cast<uint32_t>(raw < 0 ? -raw : raw);
+            uint32_t qn = static_cast<uint32_t>((n * magic[c][k]) >> 32);
+            const uint32_t rn = n - qn * qq;
+            qn += 2 * rn > qq ? 1 : 0;
+            xb[k] = static_cast<int16_t>(raw < 0 ? -static_cast<int>(qn) : static_cast<int>(qn));
+          }
         }
       }
     });
@@ -369,16 +427,23 @@ struct Encoder {
     return true;
   }
 
-  // img.CopyFromJpegData(jpg) ; img.ApplyGlobalQuantization(q)  (host mirror + device)
-  bool set_global_quant(const int q[3][64]) {
-    const double t0 = now_ms();
+  // img.CopyFromJpegData(jpg) ; img.ApplyGlobalQuantization(q): the device candidate ...
+  bool set_global_quant_device(const int q[3][64]) {
     int ones[192];
     for (int i = 0; i < 192; ++i) ones[i] = 1;
     if (gzb_copy_from_jpeg(ctx, ones) != GZB_OK) return false;
-    if (gzb_apply_global_quantization(ctx, &q[0][0]) != GZB_OK) return false;
+    return gzb_apply_global_quantization(ctx, &q[0][0]) == GZB_OK;
+  }
+  // ... and its host mirror (the quantised indices the JPEG writer codes)
+  void set_global_quant_host(const int q[3][64]) {
+    const double t0 = now_ms();
     memcpy(quant, q, sizeof(quant));
     quantize_host(q, idx);
     st.host_quant_ms += now_ms() - t0;
+  }
+  bool set_global_quant(const int q[3][64]) {
+    if (!set_global_quant_device(q)) return false;
+    set_global_quant_host(q);
     return true;
   }
 };
@@ -679,6 +744,28 @@ int gzb_test_quant_search(int rank, int world, gzb_allgather_fn allgather, void*
   return GZB_OK;
 }
 
+// Exhaustive check of the multiply-based quantiser of Encoder::quantize_host against
+// Quantize(raw, q) / q (quantize.h:24-29) for every int16 raw and q in [1, qmax]; returns mismatches.
+long gzb_test_quantize_magic(int qmax) {
+  long bad = 0;
+  for (int q = 1; q <= qmax; ++q) {
+    const uint64_t magic = (uint64_t(1) << 32) / static_cast<uint32_t>(q) + 1;
+    for (int raw = -32768; raw <= 32767; ++raw) {
+      const uint32_t n = static_cast<uint32_t>(raw < 0 ? -raw : raw);
+      uint32_t qn = static_cast<uint32_t>((n * magic) >> 32);
+      const uint32_t rn = n - qn * static_cast<uint32_t>(q);
+      qn += 2 * rn > static_cast<uint32_t>(q) ? 1 : 0;
+      const int got = raw < 0 ? -static_cast<int>(qn) : static_cast<int>(qn);
+      // the reference in int arithmetic (int16 overflow of raw + delta cannot occur for the compared quotient)
+      const int r = raw % q;
+      const int delta = 2 * r > q ? q - r : (-2) * r > q ? -q - r : -r;
+      const int want = (raw + delta) / q;
+      bad += got != want;
+    }
+  }
+  return bad;
+}
+
 void gzb_test_lazy_sort(int* first, float* second, size_t n, size_t prefix) {
   std::vector<OrderEntry> v(n);
   for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(first[i], second[i]);
@@ -688,6 +775,17 @@ void gzb_test_lazy_sort(int* first, float* second, size_t n, size_t prefix) {
     if ((n ^ prefix) & 1) ls.ensure_bulk(std::min(prefix, n) - 1);   // exercise both entry points
     else { ls.ensure_bulk((std::min(prefix, n) - 1) / 2); ls.ensure(std::min(prefix, n) - 1); }
   }
+  for (size_t i = 0; i < n; ++i) { first[i] = v[i].first; second[i] = v[i].second; }
+}
+// ensure_set(p) followed by ensure(upto): [0,p) must be std::sort's first p entries as a set and
+// [p, upto] must be final.
+void gzb_test_lazy_sort_set(int* first, float* second, size_t n, size_t p, size_t upto) {
+  std::vector<OrderEntry> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(first[i], second[i]);
+  gzb::WorkerPool pool(6);
+  LazySort ls(v.data(), n, &pool);
+  ls.ensure_set(p);
+  if (n > 0) ls.ensure(std::min(upto, n - 1));
   for (size_t i = 0; i < n; ++i) { first[i] = v[i].first; second[i] = v[i].second; }
 }
 void gzb_test_std_sort(int* first, float* second, size_t n) {
@@ -806,10 +904,20 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         write_original(&o->jpeg);
         if (gzb_copy_from_jpeg(e.ctx, &ones[0][0]) != GZB_OK) return false;
       } else {
+        // TryQuantMatrix (processor.cc:279-308): the file is written on a host thread while the
+        // GPU quantises, reconstructs and compares the same candidate
         int q[3][64];
         memcpy(q, t.q, sizeof(q));
-        if (!e.set_global_quant(q)) return false;
-        e.write_candidate(&o->jpeg);
+        std::thread host([&] {
+          e.set_global_quant_host(q);
+          e.write_candidate(&o->jpeg);
+        });
+        const bool ok = e.set_global_quant_device(q) && e.compare(true);
+        host.join();
+        if (!ok) return false;
+        o->distance = e.distance;
+        o->jpg_size = o->jpeg.size();
+        return true;
       }
       if (!e.compare(true)) return false;
       o->distance = e.distance;
@@ -1009,6 +1117,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
     std::vector<OrderEntry> global_order;
     std::vector<uint8_t> touched(num_blocks, 0);
     std::vector<int> touched_list;
+    std::vector<uint32_t> prefix_count;
     bool first_up_iter = true;
     const int directions[2] = {1, -1};
     const int n_cerr = static_cast<int>(cand_errors.size());
@@ -1093,15 +1202,113 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         float val_threshold = 0.0;
         int changed_coeffs = 0;
         int est_jpg_size = prev_size;
-        if (min_coeffs_to_change > 0) {  // the walk cannot stop before min_coeffs_to_change + 1 entries
+        WriteJob* job = writer.new_job();
+        const size_t order_size = global_order.size();
+        const size_t kAhead = 24;
+        // ---- the silent prefix ----
+        // While i + 9 < min_coeffs_to_change and i + 9 < order_size - 1 the reference's loop can
+        // neither stop nor have its entropy-code rebuild observed (processor.cc:879-903), so the
+        // first `prefix` entries of the sorted order are consumed as a SET: they need not be sorted,
+        // each block just takes as many of its next candidates as it has entries in the set, and the
+        // blocks are processed in parallel in block order (sequential memory) instead of in the
+        // order's random order. Histogram sums are order-independent.
+        size_t prefix = 0;
+        if (min_coeffs_to_change > 9 && order_size > 10)
+          prefix = std::min(static_cast<size_t>(min_coeffs_to_change - 9), order_size - 10);
+        if (prefix < 8192 || e.pool->size() < 2) prefix = 0;
+        if (prefix > 0) {
+          const double ts = now_ms();
+          sorter.ensure_set(prefix);
+          e.st.be_sort_ms += now_ms() - ts;
+          const int T = e.pool->size();
+          if (prefix_count.empty()) prefix_count.assign(num_blocks, 0);
+          e.pool->run(T, [&](int t) {
+            const size_t i0 = prefix * t / T, i1 = prefix * (t + 1) / T;
+            for (size_t i = i0; i < i1; ++i) __atomic_fetch_add(&prefix_count[global_order[i].first], 1u, __ATOMIC_RELAXED);
+          });
+          struct Local {
+            std::vector<int32_t> block; std::vector<uint8_t> cidx; std::vector<int16_t> val, newidx;
+            std::vector<int> touched;
+            int64_t hist[3][Histogram::kSize];
+          };
+          std::vector<Local> loc(T);
+          std::atomic<int> next_chunk(0);
+          const int kChunk = 512;
+          e.pool->run(T, [&](int t) {
+            Local& L = loc[t];
+            memset(L.hist, 0, sizeof(L.hist));
+            for (;;) {
+              const int b_begin = next_chunk.fetch_add(kChunk);
+              if (b_begin >= num_blocks) break;
+              const int b_end = std::min(num_blocks, b_begin + kChunk);
+              for (int b = b_begin; b < b_end; ++b) {
+                const uint32_t times = prefix_count[b];
+                if (!times) continue;
+                prefix_count[b] = 0;
+                L.touched.push_back(b);
+                const int offset = std::max(0, std::min(cand_offsets[b], n_ccoef - 1));
+                const uint8_t* candidates = cand_coeffs.data() + offset;
+                for (uint32_t rep = 0; rep < times; ++rep) {
+                  const int last_idx = last_indexes[b];
+                  const int cidx = candidates[last_idx + std::min(direction, 0)];
+                  const int c = cidx / 64, k = cidx % 64, z = gzb::jpeg::kZigZag[k];
+                  const int* qc = e.quant[c];
+                  int16_t* blk_idx = e.idx[c].data() + static_cast<size_t>(b) * 64;
+                  const int16_t newval = direction > 0 ? 0 : quantize_coeff(e.orig[c][static_cast<size_t>(b) * 64 + k], qc[k]);
+                  const int16_t new_idx = static_cast<int16_t>(newval / qc[k]);
+                  const int16_t old_idx = blk_idx[k];
+                  uint64_t& m = zmask[c][b];
+                  const uint64_t lower = m & ((1ULL << z) - 1);
+                  const int p = lower ? 63 - __builtin_clzll(lower) : 0;
+                  const uint64_t upper = z < 63 ? (m >> (z + 1)) : 0;
+                  const int n = upper ? z + 1 + __builtin_ctzll(upper) : 64;
+                  const int v_n = n < 64 ? blk_idx[gzb::jpeg::kNaturalOrder[n]] : 0;
+                  int64_t* hh = L.hist[c];
+                  auto add_run = [&](int run, int v, int weight) {
+                    while (run > 15) { hh[0xf0] += weight; run -= 16; }
+                    hh[(run << 4) + (32 - __builtin_clz(static_cast<unsigned>(std::abs(v))))] += weight;
+                  };
+                  auto emit = [&](int v_z, int weight) {
+                    if (v_z != 0) {
+                      add_run(z - p - 1, v_z, weight);
+                      if (n < 64) add_run(n - z - 1, v_n, weight);
+                      else if (z != 63) hh[0] += weight;
+                    } else {
+                      if (n < 64) add_run(n - p - 1, v_n, weight);
+                      else hh[0] += weight;
+                    }
+                  };
+                  emit(old_idx, -1);
+                  emit(new_idx, 1);
+                  blk_idx[k] = new_idx;
+                  if (new_idx != 0) m |= 1ULL << z; else m &= ~(1ULL << z);
+                  L.block.push_back(b); L.cidx.push_back(static_cast<uint8_t>(cidx)); L.val.push_back(newval); L.newidx.push_back(new_idx);
+                  last_indexes[b] += direction;
+                }
+              }
+            }
+          });
+          for (int t = 0; t < T; ++t) {
+            Local& L = loc[t];
+            for (int c = 0; c < 3; ++c)
+              for (int i = 0; i + 1 < Histogram::kSize; ++i)
+                if (L.hist[c][i]) ac_hist[c].counts[i] = static_cast<uint32_t>(static_cast<int64_t>(ac_hist[c].counts[i]) + 2 * L.hist[c][i]);
+            job->block.insert(job->block.end(), L.block.begin(), L.block.end());
+            job->cidx.insert(job->cidx.end(), L.cidx.begin(), L.cidx.end());
+            job->val.insert(job->val.end(), L.val.begin(), L.val.end());
+            job->newidx.insert(job->newidx.end(), L.newidx.begin(), L.newidx.end());
+            for (int b : L.touched) if (!touched[b]) { touched[b] = 1; touched_list.push_back(b); }
+          }
+          recount_bits();  // raw bit sums for the current codes and the new histograms
+          changed_coeffs = static_cast<int>(prefix);
+          e.st.be_steps += prefix;
+          e.st.be_prefix_steps += prefix;
+        } else if (min_coeffs_to_change > 0) {  // the walk cannot stop before min_coeffs_to_change + 1 entries
           const double ts = now_ms();
           sorter.ensure_bulk(std::min<size_t>(static_cast<size_t>(min_coeffs_to_change), global_order.size() - 1));
           e.st.be_sort_ms += now_ms() - ts;
         }
-        WriteJob* job = writer.new_job();
-        const size_t order_size = global_order.size();
-        const size_t kAhead = 24;
-        for (size_t i = 0; i < order_size; ++i) {
+        for (size_t i = prefix; i < order_size; ++i) {
           if (sorter.sorted() <= std::min(i + kAhead, order_size - 1)) {
             const double ts = now_ms();
             sorter.ensure(std::min(i + kAhead, order_size - 1));

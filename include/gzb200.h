@@ -173,6 +173,7 @@ typedef struct {
   double final_score;
   float final_distance;
   unsigned long long launches;
+  unsigned long long be_prefix_steps;    /* of be_steps: applied block-parallel in the silent prefix */
   int search_rounds, search_trials;      /* SelectQuantMatrix: exchange rounds / trials evaluated by the group */
 } gzb_encode_stats;
 int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,

@@ -15,3 +15,9 @@ for rep in range(2):
     print("encode %dx%d q%g: %.3f s -> %.3f MPix/s, %d bytes, iters %d" % (w, h, q, dt, w * h / 1e6 / dt, len(jpg), st["num_iterations"]))
     print(json.dumps({k: (round(v, 2) if isinstance(v, float) else v) for k, v in st.items()}))
 os.system("nproc; grep -m1 'model name' /proc/cpuinfo")
+# two-step: where does the wall time outside gzb_encoder_run go?
+for rep in range(2):
+    t0 = time.time(); enc = gz.Encoder(img, t, host_threads=nt); t1 = time.time()
+    jpg, st, _ = enc.run(); t2 = time.time(); enc.close(); t3 = time.time()
+    print("two-step: create %.1f ms (lib prepare %.1f)  run %.1f ms (lib run %.1f)  close %.1f ms" %
+          ((t1 - t0) * 1e3, st["prepare_ms"], (t2 - t1) * 1e3, st["run_ms"], (t3 - t2) * 1e3))

@@ -136,6 +136,40 @@ def test_lazy_sort_equals_std_sort(gz):
                 assert np.array_equal(np.sort(b_id), np.arange(n, dtype=np.int32))
 
 
+def test_multiply_quantiser_is_exact(gz):
+    L = gz.lib()
+    L.gzb_test_quantize_magic.restype = C.c_long
+    assert L.gzb_test_quantize_magic(700) == 0
+
+
+def test_lazy_sort_set_prefix_is_std_sorts_prefix_as_a_set(gz):
+    """LazySort::ensure_set(p): positions [0,p) hold std::sort's first p entries (any order, ties
+    included) and the walk can continue with exact positions from p on (the back end's silent prefix)."""
+    L = gz.lib()
+    L.gzb_test_lazy_sort_set.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
+    L.gzb_test_std_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(9)
+    for n in [40, 1000, 70000, 600000, 1200000]:
+        for kind in range(3):
+            if kind == 0:
+                v = rng.random(n).astype(np.float32)
+            elif kind == 1:
+                v = rng.integers(0, 5, n).astype(np.float32)           # heavy ties: the set is not key-determined
+            else:
+                v = (rng.integers(0, max(1, n // 3), n) / 8.0).astype(np.float32)
+            ids = np.arange(n, dtype=np.int32)
+            a_id, a_v = ids.copy(), v.copy()
+            L.gzb_test_std_sort(p(a_id), p(a_v), n)
+            for pfx in sorted({0, 1, n // 50, n // 3, n - 10, n}):
+                upto = min(n - 1, pfx + max(30, n // 20))
+                b_id, b_v = ids.copy(), v.copy()
+                L.gzb_test_lazy_sort_set(p(b_id), p(b_v), n, pfx, upto)
+                assert np.array_equal(np.sort(b_id[:pfx]), np.sort(a_id[:pfx])), (n, kind, pfx)
+                assert np.array_equal(b_id[pfx:upto + 1], a_id[pfx:upto + 1]), (n, kind, pfx)
+                assert np.array_equal(b_v[pfx:upto + 1], a_v[pfx:upto + 1])
+                assert np.array_equal(np.sort(b_id), ids)
+
+
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
 def test_huffman_depths_equal_reference(gz):
     """Length-limited Huffman depths vs CreateHuffmanTree, including histograms whose unconstrained
