@@ -302,7 +302,8 @@ class EncodeStats(C.Structure):
                 ("be_codes_ms", C.c_double), ("be_sort_ms", C.c_double), ("be_steps", C.c_ulonglong),
                 ("prepare_ms", C.c_double), ("run_ms", C.c_double), ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong),
                 ("final_score", C.c_double), ("final_distance", C.c_float), ("launches", C.c_ulonglong),
-                ("be_prefix_steps", C.c_ulonglong), ("search_rounds", C.c_int), ("search_trials", C.c_int)]
+                ("be_prefix_steps", C.c_ulonglong), ("search_wall_ms", C.c_double), ("trial_host_ms", C.c_double),
+                ("trial_device_ms", C.c_double), ("search_rounds", C.c_int), ("search_trials", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

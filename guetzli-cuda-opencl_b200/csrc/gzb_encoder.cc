@@ -898,6 +898,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   // reference's order; with a group of one this is the reference's sequential loop.
   int best_q[3][64];
   {
+    const double t_search = now_ms();
     gzb::QuantSearch search(e.group, e.target);
     auto evaluate = [&](const gzb::Trial& t, gzb::TrialOutcome* o) -> bool {
       if (t.original) {
@@ -908,11 +909,14 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         // GPU quantises, reconstructs and compares the same candidate
         int q[3][64];
         memcpy(q, t.q, sizeof(q));
+        const double th0 = now_ms();
         std::thread host([&] {
           e.set_global_quant_host(q);
           e.write_candidate(&o->jpeg);
+          e.st.trial_host_ms += now_ms() - th0;
         });
         const bool ok = e.set_global_quant_device(q) && e.compare(true);
+        e.st.trial_device_ms += now_ms() - th0;
         host.join();
         if (!ok) return false;
         o->distance = e.distance;
@@ -940,6 +944,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       if (g_encode_err.empty()) g_encode_err = "gzb_encoder_run: the group exchange failed";
       return GZB_ERR_CUDA;
     }
+    e.st.search_wall_ms = now_ms() - t_search;
     e.search_rounds = search.rounds();
     e.search_trials = search.evaluated_total();
     const QuantData& best = search.best();

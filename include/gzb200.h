@@ -174,6 +174,7 @@ typedef struct {
   float final_distance;
   unsigned long long launches;
   unsigned long long be_prefix_steps;    /* of be_steps: applied block-parallel in the silent prefix */
+  double search_wall_ms, trial_host_ms, trial_device_ms;  /* SelectQuantMatrix phase; host/device legs of its trials */
   int search_rounds, search_trials;      /* SelectQuantMatrix: exchange rounds / trials evaluated by the group */
 } gzb_encode_stats;
 int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,

@@ -1,0 +1,21 @@
+"""One Compare + one zeroing-order pass of the bench workload (1024x1024) between
+cudaProfilerStart/Stop, for `ncu --profile-from-start off --set full` (see profiles/README.md)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+from _libs import synth_image
+import __graft_entry__ as ge
+gz = ge.load_package()
+w, h = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1024, 1024)
+img = synth_image(w, h)
+c = gz.ButteraugliComparator(w, h, img, np.float32(gz.ButteraugliScoreForQuality(90)))
+c.SetJpegCoeffs(gz.RgbToJpegCoeffs(img)); c.CopyFromJpegData(); c.ApplyGlobalQuantization(np.full(192, 3, np.int32))
+c.Compare(); c.StartBlockComparisons()
+rt = torch.cuda.cudart()
+rt.cudaProfilerStart()
+c.Compare()
+c.ComputeBlockZeroingCandidates(7)
+rt.cudaProfilerStop()
+print("probe done: distance %.4f" % c.distance)
