@@ -157,6 +157,20 @@ class ButteraugliComparator:
         _check(lib().gzb_to_srgb(self._ctx, _p(out)), self._ctx)
         return out
 
+    def WriteJpeg(self, q, input_tables=False, want_bytes=True):
+        """SaveToJpegData + WriteJpeg of the resident candidate, the scan Huffman-coded on the device.
+        q[192]: the matrix the candidate's values are multiples of. Returns (size, bytes or None)."""
+        L = lib()
+        L.gzb_write_candidate_jpeg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        qq = np.ascontiguousarray(q, np.int32).reshape(192)
+        n = C.c_size_t()
+        _check(L.gzb_write_candidate_jpeg(self._ctx, _p(qq), int(input_tables), None, 0, C.byref(n)), self._ctx)
+        if not want_bytes:
+            return n.value, None
+        buf = np.zeros(n.value, np.uint8)
+        _check(L.gzb_write_candidate_jpeg(self._ctx, _p(qq), int(input_tables), _p(buf), buf.size, C.byref(n)), self._ctx)
+        return n.value, buf.tobytes()
+
     # ---- Comparator interface -------------------------------------------------------------
     def Compare(self):
         d = C.c_float()
@@ -302,7 +316,7 @@ class EncodeStats(C.Structure):
                 ("be_codes_ms", C.c_double), ("be_sort_ms", C.c_double), ("be_steps", C.c_ulonglong),
                 ("prepare_ms", C.c_double), ("run_ms", C.c_double), ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong),
                 ("final_score", C.c_double), ("final_distance", C.c_float), ("launches", C.c_ulonglong),
-                ("be_prefix_steps", C.c_ulonglong), ("search_wall_ms", C.c_double), ("trial_host_ms", C.c_double),
+                ("be_prefix_steps", C.c_ulonglong), ("device_write_ms", C.c_double), ("search_wall_ms", C.c_double), ("trial_host_ms", C.c_double),
                 ("trial_device_ms", C.c_double), ("search_rounds", C.c_int), ("search_trials", C.c_int)]
 
     def as_dict(self):
@@ -487,7 +501,7 @@ def ProcessGroup(rgb, butteraugli_target, dist, device=0, host_threads=0, want_t
         enc.close()
 
 
-def QuantSearchSimulate(rank, world, allgather, target, eval_fn):
+def QuantSearchSimulate(rank, world, allgather, target, eval_fn, batch=1):
     """Test hook (no GPU): runs the speculative SelectQuantMatrix search of gzb_quant_search.h with
     `eval_fn(original, q[192]) -> (distance, jpg_size)` standing in for the GPU trial. Returns
     {"visited": [(original, hscore, distance, size)], "best_q": [192], "best_ok": bool, "rounds": n,
@@ -508,9 +522,9 @@ def QuantSearchSimulate(rank, world, allgather, target, eval_fn):
     best_q = np.zeros(192, np.int32)
     info = np.zeros(4, np.int32)
     L.gzb_test_quant_search.argtypes = [C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p, EVAL, C.c_void_p, C.c_float,
-                                        C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+                                        C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int]
     rc = L.gzb_test_quant_search(rank, world, cb, None, ev_c, None, C.c_float(target), _p(vis), cap, C.byref(nvis),
-                                 _p(best_q), _p(info))
+                                 _p(best_q), _p(info), batch)
     if rc != 0:
         raise GzbError("gzb_test_quant_search failed (%d)" % rc)
     return {"visited": [tuple(v) for v in vis[:nvis.value].tolist()], "best_q": best_q.tolist(), "best_ok": bool(info[0]),

@@ -11,6 +11,7 @@
 #include "../../include/gzb200.h"
 #include "gzb_kernels.cuh"
 #include "gzb_zeroing.cuh"
+#include "gzb_huffman.cuh"
 
 namespace gzb {
 
@@ -214,11 +215,11 @@ using namespace gzb;
 // Per-kernel event profiling (off by default)
 // ---------------------------------------------------------------------------------------------
 enum KClass { KC_IDCT = 0, KC_OPSIN, KC_MHIC, KC_BLUR_H, KC_BLUR_V, KC_EDGE_MAP, KC_BLOCK_DIFF, KC_LOWFREQ,
-              KC_MASK_FRONT, KC_COMBINE, KC_DIFFMAP_FINAL, KC_ZEROING, KC_BLOCK_MASK, KC_WEIGHTS, KC_MISC, KC_COUNT };
+              KC_MASK_FRONT, KC_COMBINE, KC_DIFFMAP_FINAL, KC_ZEROING, KC_BLOCK_MASK, KC_WEIGHTS, KC_MISC, KC_HUFFMAN, KC_COUNT };
 static const char* const kClassNames[KC_COUNT] = {
     "k_coeffs_to_rgb8", "k_opsin_dynamics", "k_mask_high_intensity_change", "k_blur_h", "k_blur_v",
     "k_edge_detector_map", "k_block_diff_map", "k_edge_lowfreq", "k_mask_front", "k_combine",
-    "k_diffmap_final", "k_zeroing_order", "k_block_mask_scale", "k_block_weights", "misc"};
+    "k_diffmap_final", "k_zeroing_order", "k_block_mask_scale", "k_block_weights", "misc", "k_huffman"};
 struct Prof {
   bool on = false;
   struct Pend { int k; cudaEvent_t a, b; };
@@ -725,6 +726,13 @@ double gzb_score_output_size(const gzb_ctx* c, int size) {
 
 float gzb_block_error_limit(const gzb_ctx* c) { return c ? c->target : 0.f; }
 
+int gzb_image_size(const gzb_ctx* c, int* width, int* height) {
+  if (!c || !width || !height) return GZB_ERR_BAD_ARG;
+  *width = c->W;
+  *height = c->H;
+  return GZB_OK;
+}
+
 int gzb_start_block_comparisons(gzb_ctx* c) {
   GZB_TRY(c)
   CK(cudaEventRecord(c->ev0, c->stream));
@@ -856,6 +864,103 @@ int gzb_compute_block_zeroing_candidates(gzb_ctx* c, int comp_mask, int* offsets
                                          size_t cap, size_t* n_out) {
   if (!c) return GZB_ERR_BAD_ARG;
   return gzb_compute_block_zeroing_candidates_range(c, comp_mask, 0, c->nblocks, offsets, cand_idx, cand_err, cap, n_out);
+}
+
+// ---- entropy-coded segment on the device (gzb_huffman.cuh) -----------------------------------
+// Scratch: the zeroing-order record array (1536 bytes per block), idle outside the zeroing search.
+namespace {
+struct HuffScratch {
+  unsigned int* unit_bits;
+  unsigned long long* unit_off;
+  unsigned int* hist;            // [3][16] dc | [3][256] ac
+  unsigned long long* out2;
+  HuffDeviceTables* tables;
+  unsigned int* words;
+  size_t stream_cap;             // bytes
+};
+HuffScratch huff_scratch(gzb_ctx* c) {
+  HuffScratch h;
+  uint8_t* base = reinterpret_cast<uint8_t*>(c->d_order);
+  const size_t total = sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(c->nblocks);
+  const size_t nunits = 3 * static_cast<size_t>(c->nblocks);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { uint8_t* p = base + o; o += (bytes + 255) & ~size_t(255); return p; };
+  h.unit_off = reinterpret_cast<unsigned long long*>(take((nunits + 1) * 8));
+  h.unit_bits = reinterpret_cast<unsigned int*>(take(nunits * 4));
+  h.hist = reinterpret_cast<unsigned int*>(take((48 + 768) * 4));
+  h.out2 = reinterpret_cast<unsigned long long*>(take(16));
+  h.tables = reinterpret_cast<HuffDeviceTables*>(take(sizeof(HuffDeviceTables)));
+  h.words = reinterpret_cast<unsigned int*>(base + o);
+  h.stream_cap = total > o + 64 ? total - o - 64 : 0;
+  return h;
+}
+}  // namespace
+
+int gzb_candidate_symbol_histograms(gzb_ctx* c, const int* q192, uint32_t* dc_hist48, uint32_t* ac_hist768) {
+  GZB_TRY(c)
+  if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_candidate_symbol_histograms: no candidate coefficients");
+  if (!dc_hist48 || !ac_hist768) return fail(c, GZB_ERR_BAD_ARG, "gzb_candidate_symbol_histograms: null argument");
+  if (q192) { CK(cudaMemcpyAsync(c->d_q, q192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += 192 * sizeof(int); }
+  const HuffScratch h = huff_scratch(c);
+  const long long nunits = 3ll * c->nblocks;
+  CK(cudaMemsetAsync(h.hist, 0, (48 + 768) * 4, c->stream));
+  KLAUNCH(c, KC_HUFFMAN, k_huff_histogram<<<static_cast<unsigned>((nunits + kHuffThreads - 1) / kHuffThreads), kHuffThreads, 0, c->stream>>>(
+      c->d_coef, static_cast<size_t>(c->nblocks) * 64, c->d_q, 3, nunits, h.hist, h.hist + 48));
+  CK(cudaMemcpyAsync(c->h_pinned, h.hist, (48 + 768) * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (48 + 768) * 4;
+  sync_check(c);
+  memcpy(dc_hist48, c->h_pinned, 48 * 4);
+  memcpy(ac_hist768, reinterpret_cast<const uint32_t*>(c->h_pinned) + 48, 768 * 4);
+  GZB_END(c)
+}
+
+int gzb_candidate_entropy_code(gzb_ctx* c, int ncomp, const uint16_t* dc_code, const uint8_t* dc_len,
+                               const uint16_t* ac_code, const uint8_t* ac_len, uint64_t* scan_bytes, uint64_t* ff_bytes) {
+  GZB_TRY(c)
+  if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_candidate_entropy_code: no candidate coefficients");
+  if ((ncomp != 1 && ncomp != 3) || !dc_code || !dc_len || !ac_code || !ac_len || !scan_bytes || !ff_bytes)
+    return fail(c, GZB_ERR_BAD_ARG, "gzb_candidate_entropy_code: bad argument");
+  const HuffScratch h = huff_scratch(c);
+  HuffDeviceTables t;
+  memcpy(t.dc_code, dc_code, sizeof(t.dc_code));
+  memcpy(t.dc_len, dc_len, sizeof(t.dc_len));
+  memcpy(t.ac_code, ac_code, sizeof(t.ac_code));
+  memcpy(t.ac_len, ac_len, sizeof(t.ac_len));
+  CK(cudaMemcpyAsync(h.tables, &t, sizeof(t), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += sizeof(t);
+  const long long nunits = static_cast<long long>(ncomp) * c->nblocks;
+  const unsigned grid = static_cast<unsigned>((nunits + kHuffThreads - 1) / kHuffThreads);
+  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+  CK(cudaEventRecord(c->ev0, c->stream));
+  KLAUNCH(c, KC_HUFFMAN, k_huff_code<false><<<grid, kHuffThreads, 0, c->stream>>>(c->d_coef, cs, c->d_q, ncomp, nunits, h.tables,
+                                                                                  h.unit_bits, nullptr, nullptr));
+  KLAUNCH(c, KC_HUFFMAN, k_scan_u64<<<1, 1024, 0, c->stream>>>(h.unit_bits, nunits, h.unit_off));
+  unsigned long long* hp = reinterpret_cast<unsigned long long*>(c->h_pinned);
+  CK(cudaMemcpyAsync(hp, h.unit_off + nunits, 8, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 8;
+  sync_check(c);
+  const unsigned long long total_bits = hp[0];
+  const size_t nbytes = static_cast<size_t>((total_bits + 7) / 8);
+  if (nbytes + 8 > h.stream_cap) return fail(c, GZB_ERR_UNSUPPORTED, "gzb_candidate_entropy_code: scan larger than the device buffer");
+  CK(cudaMemsetAsync(h.words, 0, (nbytes + 7) & ~size_t(3), c->stream));
+  CK(cudaMemsetAsync(h.out2, 0, 16, c->stream));
+  KLAUNCH(c, KC_HUFFMAN, k_huff_code<true><<<grid, kHuffThreads, 0, c->stream>>>(c->d_coef, cs, c->d_q, ncomp, nunits, h.tables,
+                                                                                 nullptr, h.unit_off, h.words));
+  const unsigned fgrid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(static_cast<size_t>(c->sm_count) * 8, (nbytes + 4095) / 4096)));
+  KLAUNCH(c, KC_HUFFMAN, k_huff_finish<<<fgrid, 256, 0, c->stream>>>(reinterpret_cast<unsigned char*>(h.words), h.unit_off + nunits, h.out2));
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaMemcpyAsync(hp, h.out2, 16, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 16;
+  sync_check(c);
+  CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  *scan_bytes = hp[0];
+  *ff_bytes = hp[1];
+  GZB_END(c)
+}
+
+int gzb_candidate_fetch_scan(gzb_ctx* c, uint8_t* out, uint64_t nbytes) {
+  GZB_TRY(c)
+  const HuffScratch h = huff_scratch(c);
+  if (!out || nbytes > h.stream_cap) return fail(c, GZB_ERR_BAD_ARG, "gzb_candidate_fetch_scan: bad argument");
+  CK(cudaMemcpyAsync(out, h.words, nbytes, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += nbytes;
+  sync_check(c);
+  GZB_END(c)
 }
 
 int gzb_dct_double(int device, double* blocks, size_t nblocks, int inverse) {

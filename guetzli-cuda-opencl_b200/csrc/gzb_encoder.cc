@@ -324,6 +324,93 @@ class LazySort {
   std::vector<uint32_t> lpos_, rpos_;
 };
 
+// ---- the candidate as a JPEG, coded on the device ------------------------------------------------
+// Header (DQT/SOF/DHT/SOS with the clustered Huffman codes) on the host, scan on the GPU
+// (gzb_candidate_entropy_code). Only the size is needed to score a candidate; the bytes are fetched
+// for a candidate that becomes the best so far.
+struct DeviceJpeg {
+  std::string header;
+  uint64_t scan_bytes = 0, ff_bytes = 0;
+  size_t size() const { return header.size() + static_cast<size_t>(scan_bytes + ff_bytes) + 2; }
+};
+
+void histogram_from_counts(const uint32_t* counts, int n, Histogram* h) {
+  *h = Histogram();
+  for (int i = 0; i < n; ++i) if (counts[i]) h->add(i, static_cast<int>(counts[i]));
+}
+
+// SaveToJpegData drops chroma planes that are entirely zero (output_image.cc:588): every block then
+// codes a zero DC difference and a lone end-of-block.
+int ncomp_from_histograms(const Histogram* dc, const Histogram* ac, int nblocks) {
+  for (int c = 1; c < 3; ++c)
+    if (dc[c].counts[0] != 2u * nblocks || ac[c].counts[0] != 2u * nblocks) return 3;
+  return 1;
+}
+
+// Codes the resident candidate. dc_hist/ac_hist: its per-component histograms if the caller has them
+// (the back end maintains them incrementally), else they are counted on the device.
+bool device_code_candidate(gzb_ctx* ctx, int w, int h, int nblocks, const int q[3][64], bool input_tables,
+                           const Histogram* dc_hist, const Histogram* ac_hist, DeviceJpeg* out) {
+  Histogram hd[3], ha[3];
+  if (!dc_hist || !ac_hist) {
+    uint32_t dc[48], ac[768];
+    if (gzb_candidate_symbol_histograms(ctx, nullptr, dc, ac) != GZB_OK) return false;
+    for (int c = 0; c < 3; ++c) {
+      histogram_from_counts(dc + 16 * c, 16, &hd[c]);
+      histogram_from_counts(ac + 256 * c, 256, &ha[c]);
+    }
+    dc_hist = hd;
+    ac_hist = ha;
+  }
+  Frame f;
+  f.width = w; f.height = h; f.bw = (w + 7) / 8; f.bh = (h + 7) / 8;
+  if (input_tables) {
+    f.ncomp = 3;
+    gzb::jpeg::frame_set_quant_input(&f, q);
+  } else {
+    f.ncomp = ncomp_from_histograms(dc_hist, ac_hist, nblocks);
+    gzb::jpeg::frame_set_quant(&f, q);
+  }
+  gzb::jpeg::CodeTable dct[3], act[3];
+  gzb::jpeg::write_jpeg_header(f, dc_hist, ac_hist, &out->header, dct, act);
+  uint16_t dc_code[3][16], ac_code[3][256];
+  uint8_t dc_len[3][16], ac_len[3][256];
+  memset(dc_code, 0, sizeof(dc_code)); memset(ac_code, 0, sizeof(ac_code));
+  memset(dc_len, 0, sizeof(dc_len)); memset(ac_len, 0, sizeof(ac_len));
+  for (int c = 0; c < f.ncomp; ++c) {
+    for (int i = 0; i < 16; ++i) { dc_code[c][i] = dct[c].code[i]; dc_len[c][i] = dct[c].depth[i] == 255 ? 0 : dct[c].depth[i]; }
+    for (int i = 0; i < 256; ++i) { ac_code[c][i] = act[c].code[i]; ac_len[c][i] = act[c].depth[i] == 255 ? 0 : act[c].depth[i]; }
+  }
+  return gzb_candidate_entropy_code(ctx, f.ncomp, &dc_code[0][0], &dc_len[0][0], &ac_code[0][0], &ac_len[0][0],
+                                    &out->scan_bytes, &out->ff_bytes) == GZB_OK;
+}
+
+// header + byte-stuffed scan + EOI
+void assemble_jpeg(const std::string& header, const uint8_t* scan, size_t scan_bytes, size_t ff_bytes, std::string* out) {
+  out->resize(header.size() + scan_bytes + ff_bytes + 2);
+  memcpy(&(*out)[0], header.data(), header.size());
+  uint8_t* o = reinterpret_cast<uint8_t*>(&(*out)[0]) + header.size();
+  const uint8_t* p = scan;
+  const uint8_t* end = scan + scan_bytes;
+  while (p < end) {
+    const uint8_t* ff = static_cast<const uint8_t*>(memchr(p, 0xff, static_cast<size_t>(end - p)));
+    const size_t n = static_cast<size_t>((ff ? ff + 1 : end) - p);
+    memcpy(o, p, n);
+    o += n;
+    p += n;
+    if (ff) *o++ = 0;
+  }
+  *o++ = 0xff;
+  *o++ = 0xd9;
+}
+
+bool device_fetch_jpeg(gzb_ctx* ctx, const DeviceJpeg& dj, std::string* out) {
+  std::vector<uint8_t> scan(static_cast<size_t>(dj.scan_bytes) + 8);
+  if (gzb_candidate_fetch_scan(ctx, scan.data(), dj.scan_bytes) != GZB_OK) return false;
+  assemble_jpeg(dj.header, scan.data(), static_cast<size_t>(dj.scan_bytes), static_cast<size_t>(dj.ff_bytes), out);
+  return true;
+}
+
 // ---- encoder state ----------------------------------------------------------------------------
 struct Encoder {
   int w = 0, h = 0, bw = 0, bh = 0, nb = 0;
@@ -381,7 +468,8 @@ struct Encoder {
   // the quantised indices of ApplyGlobalQuantization(q) on the q=1 input (host mirror)
   // Quantize(raw, q) / q (quantize.h:24-29) == sign(raw) * (|raw| / q + (2 * (|raw| % q) > q)); the
   // division is a multiplication by ceil(2^32 / q), exact for |raw| <= 2^15 and q < 2^16.
-  void quantize_host(const int q[3][64], std::vector<int16_t>* out3) {
+  void quantize_host(const int q[3][64], std::vector<int16_t>* out3, gzb::WorkerPool* use_pool = nullptr) {
+    if (!use_pool) use_pool = pool.get();
     uint64_t magic[3][64];
     bool small = true;
     for (int c = 0; c < 3; ++c)
@@ -389,7 +477,7 @@ struct Encoder {
         magic[c][k] = (uint64_t(1) << 32) / static_cast<uint32_t>(q[c][k]) + 1;
         small = small && q[c][k] < (1 << 16);
       }
-    parallel_rows(nb, pool.get(), [&](int b0, int b1) {
+    parallel_rows(nb, use_pool, [&](int b0, int b1) {
       for (int c = 0; c < 3; ++c) {
         const int16_t* o = orig[c].data();
         int16_t* ix = out3[c].data();
@@ -465,7 +553,8 @@ void Encoder::maybe_output_trial(const gzb::Trial& t, const gzb::TrialOutcome& o
   if (score < best_score || best_score < 0) {
     best_score = score;
     if (o.owner == group.rank) {
-      best_jpeg = o.jpeg;
+      assemble_jpeg(o.jpeg, reinterpret_cast<const uint8_t*>(o.scan.data()), o.scan.size(),
+                    static_cast<size_t>(o.jpg_size) - o.jpeg.size() - o.scan.size() - 2, &best_jpeg);
       best_remote = false;
     } else {  // the bytes live on another rank: remember how to rebuild them if they stay the best
       best_jpeg.clear();
@@ -476,108 +565,6 @@ void Encoder::maybe_output_trial(const gzb::Trial& t, const gzb::TrialOutcome& o
   }
   log("\n");
 }
-
-// One back-end iteration's file: the coefficient flips to apply, the AC histograms after them, and
-// what MaybeOutput needs.
-struct WriteJob {
-  std::vector<int32_t> block;
-  std::vector<uint8_t> cidx;
-  std::vector<int16_t> val, newidx;
-  Histogram ac_hist[3];
-  std::string log_head;
-  int est_jpg_size = 0;
-  float distance = 0.f, score_target = 0.f;
-  void add(int b, uint8_t ci, int16_t v, int16_t ni) { block.push_back(b); cidx.push_back(ci); val.push_back(v); newidx.push_back(ni); }
-  void clear() { block.clear(); cidx.clear(); val.clear(); newidx.clear(); log_head.clear(); }
-};
-
-// Writes each iteration's JPEG on its own thread (with its own worker pool and its own copy of the
-// quantised indices), in iteration order, and performs MaybeOutput there. The search thread only
-// waits when two files are already in flight.
-class WriterStage {
- public:
-  WriterStage(Encoder* e, const Histogram* dc_hist) : e_(e), pool_(std::max(1, e->nthreads - 1)) {
-    for (int c = 0; c < 3; ++c) { idx_[c] = e->idx[c]; dc_hist_[c] = dc_hist[c]; }
-    thread_ = std::thread(&WriterStage::loop, this);
-  }
-  ~WriterStage() { abort(); }
-  WriteJob* new_job() {
-    std::unique_lock<std::mutex> l(mu_);
-    cv_.wait(l, [&] { return !free_.empty() || jobs_made_ < 3; });
-    WriteJob* j;
-    if (!free_.empty()) { j = free_.back(); free_.pop_back(); }
-    else { store_.emplace_back(new WriteJob); j = store_.back().get(); ++jobs_made_; }
-    j->clear();
-    return j;
-  }
-  void submit(WriteJob* j) {
-    { std::lock_guard<std::mutex> l(mu_); queue_.push_back(j); }
-    cv_.notify_all();
-  }
-  void finish() {
-    { std::lock_guard<std::mutex> l(mu_); done_ = true; }
-    cv_.notify_all();
-    if (thread_.joinable()) thread_.join();
-  }
-  void abort() { finish(); }
-
- private:
-  void loop() {
-    for (;;) {
-      WriteJob* j;
-      {
-        std::unique_lock<std::mutex> l(mu_);
-        cv_.wait(l, [&] { return !queue_.empty() || done_; });
-        if (queue_.empty()) return;
-        j = queue_.front();
-        queue_.erase(queue_.begin());
-      }
-      const double t0 = now_ms();
-      for (size_t i = 0; i < j->block.size(); ++i)
-        idx_[j->cidx[i] >> 6][static_cast<size_t>(j->block[i]) * 64 + (j->cidx[i] & 63)] = j->newidx[i];
-      Frame f;
-      f.width = e_->w; f.height = e_->h; f.bw = e_->bw; f.bh = e_->bh;
-      f.ncomp = 1;
-      for (int c = 1; c < 3 && f.ncomp == 1; ++c)
-        for (int16_t v : idx_[c]) if (v != 0) { f.ncomp = 3; break; }
-      for (int c = 0; c < 3; ++c) f.coeffs[c] = idx_[c].data();
-      gzb::jpeg::frame_set_quant(&f, e_->quant);
-      std::string jpg;
-      gzb::jpeg::write_jpeg(f, &jpg, &pool_, dc_hist_, j->ac_hist, &e_->wt);
-      e_->st.host_write_ms += now_ms() - t0;
-      e_->st.num_jpeg_writes++;
-      // GUETZLI_LOG lines of processor.cc:905-913, butteraugli_comparator.cc:69, MaybeOutput 151-160
-      e_->log("%s Out[%7zd] EstErr[%.2f%%]", j->log_head.c_str(), jpg.size(),
-              100.0 - (100.0 * j->est_jpg_size) / jpg.size());
-      e_->log(" BA[100.00%%] D[%6.4f]", j->distance);
-      const double score = score_jpeg(j->distance, static_cast<int>(jpg.size()), j->score_target);
-      e_->log(" Score[%.4f]", score);
-      if (score < e_->best_score || e_->best_score < 0) {
-        e_->best_jpeg.swap(jpg);
-        e_->best_score = score;
-        e_->best_remote = false;
-        e_->log(" (*)");
-      }
-      e_->log("\n");
-      {
-        std::lock_guard<std::mutex> l(mu_);
-        free_.push_back(j);
-      }
-      cv_.notify_all();
-    }
-  }
-  Encoder* e_;
-  gzb::WorkerPool pool_;
-  std::vector<int16_t> idx_[3];
-  Histogram dc_hist_[3];
-  std::thread thread_;
-  std::mutex mu_;
-  std::condition_variable cv_;
-  std::vector<WriteJob*> queue_, free_;
-  std::vector<std::unique_ptr<WriteJob>> store_;
-  int jobs_made_ = 0;
-  bool done_ = false;
-};
 
 }  // namespace
 
@@ -706,23 +693,50 @@ void gzb_test_huffman_depths(const uint32_t* counts257, uint8_t* depth257, const
 }
 
 // Test hooks: the lazy order must equal std::sort's permutation on the consumed prefix.
+int gzb_write_candidate_jpeg(gzb_ctx* ctx, const int* q192, int input_tables, uint8_t* out, size_t cap, size_t* size_out) {
+  if (!ctx || !q192 || !size_out) return GZB_ERR_BAD_ARG;
+  int w = 0, h = 0;
+  if (gzb_image_size(ctx, &w, &h) != GZB_OK) return GZB_ERR_BAD_ARG;
+  int q[3][64];
+  memcpy(q, q192, sizeof(q));
+  uint32_t dc[48], ac[768];
+  int rc = gzb_candidate_symbol_histograms(ctx, q192, dc, ac);  // also makes q192 the device's matrix
+  if (rc != GZB_OK) return rc;
+  Histogram hd[3], ha[3];
+  for (int c = 0; c < 3; ++c) {
+    histogram_from_counts(dc + 16 * c, 16, &hd[c]);
+    histogram_from_counts(ac + 256 * c, 256, &ha[c]);
+  }
+  DeviceJpeg dj;
+  if (!device_code_candidate(ctx, w, h, ((w + 7) / 8) * ((h + 7) / 8), q, input_tables != 0, hd, ha, &dj)) return GZB_ERR_CUDA;
+  *size_out = dj.size();
+  if (out && cap >= dj.size()) {
+    std::string bytes;
+    if (!device_fetch_jpeg(ctx, dj, &bytes)) return GZB_ERR_CUDA;
+    memcpy(out, bytes.data(), bytes.size());
+  }
+  return GZB_OK;
+}
+
 // Test hook (CPU only): the speculative SelectQuantMatrix search with a caller-provided evaluator.
 // visited: rows of {original, heuristic score, distance, jpg_size}; info: {best.dist_ok, rounds,
 // evaluated on this rank, evaluated by the group}.
 int gzb_test_quant_search(int rank, int world, gzb_allgather_fn allgather, void* user,
                           int (*eval_fn)(void*, int, const int*, float*, uint64_t*), void* eval_user, float target,
-                          double* visited, int cap, int* nvisited, int* best_q192, int* info) {
+                          double* visited, int cap, int* nvisited, int* best_q192, int* info, int batch) {
   gzb::Group g;
   g.rank = rank; g.world = world; g.allgather = allgather; g.user = user;
-  gzb::QuantSearch search(g, target);
+  gzb::QuantSearch search(g, target, batch);
   int n = 0;
   const bool ok = search.run(
-      [&](const gzb::Trial& t, gzb::TrialOutcome* o) {
-        float d = 0.f;
-        uint64_t sz = 0;
-        if (eval_fn(eval_user, t.original, &t.q[0][0], &d, &sz) != 0) return false;
-        o->distance = d;
-        o->jpg_size = sz;
+      [&](const std::vector<gzb::Trial>& ts, std::vector<gzb::TrialOutcome>* os) {
+        for (size_t j = 0; j < ts.size(); ++j) {
+          float d = 0.f;
+          uint64_t sz = 0;
+          if (eval_fn(eval_user, ts[j].original, &ts[j].q[0][0], &d, &sz) != 0) return false;
+          (*os)[j].distance = d;
+          (*os)[j].jpg_size = sz;
+        }
         return true;
       },
       [&](const gzb::Trial& t, const gzb::TrialOutcome& o) {
@@ -899,33 +913,28 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   int best_q[3][64];
   {
     const double t_search = now_ms();
-    gzb::QuantSearch search(e.group, e.target);
-    auto evaluate = [&](const gzb::Trial& t, gzb::TrialOutcome* o) -> bool {
-      if (t.original) {
-        write_original(&o->jpeg);
-        if (gzb_copy_from_jpeg(e.ctx, &ones[0][0]) != GZB_OK) return false;
-      } else {
-        // TryQuantMatrix (processor.cc:279-308): the file is written on a host thread while the
-        // GPU quantises, reconstructs and compares the same candidate
-        int q[3][64];
-        memcpy(q, t.q, sizeof(q));
-        const double th0 = now_ms();
-        std::thread host([&] {
-          e.set_global_quant_host(q);
-          e.write_candidate(&o->jpeg);
-          e.st.trial_host_ms += now_ms() - th0;
-        });
-        const bool ok = e.set_global_quant_device(q) && e.compare(true);
-        e.st.trial_device_ms += now_ms() - th0;
-        host.join();
-        if (!ok) return false;
-        o->distance = e.distance;
-        o->jpg_size = o->jpeg.size();
-        return true;
+    // TryQuantMatrix (processor.cc:279-308) entirely on the device: quantise + IDCT, Huffman-code the
+    // candidate (its size is what the search needs), Compare. The scan is kept (unstuffed) so that
+    // the file can be assembled if this trial turns out to be the best so far.
+    gzb::QuantSearch search(e.group, e.target, 1);
+    auto evaluate = [&](const std::vector<gzb::Trial>& ts, std::vector<gzb::TrialOutcome>* os) -> bool {
+      for (size_t j = 0; j < ts.size(); ++j) {
+        const gzb::Trial& t = ts[j];
+        gzb::TrialOutcome& o = (*os)[j];
+        const double t0 = now_ms();
+        if (t.original ? gzb_copy_from_jpeg(e.ctx, &ones[0][0]) != GZB_OK : !e.set_global_quant_device(t.q)) return false;
+        DeviceJpeg dj;
+        if (!device_code_candidate(e.ctx, width, height, e.nb, t.q, t.original != 0, nullptr, nullptr, &dj)) return false;
+        o.scan.resize(static_cast<size_t>(dj.scan_bytes));
+        if (dj.scan_bytes && gzb_candidate_fetch_scan(e.ctx, reinterpret_cast<uint8_t*>(&o.scan[0]), dj.scan_bytes) != GZB_OK) return false;
+        o.jpg_size = dj.size();
+        o.jpeg.swap(dj.header);
+        e.st.num_jpeg_writes++;
+        e.st.device_write_ms += now_ms() - t0;
+        if (!e.compare(true)) return false;
+        o.distance = e.distance;
+        e.st.trial_device_ms += now_ms() - t0;
       }
-      if (!e.compare(true)) return false;
-      o->distance = e.distance;
-      o->jpg_size = o->jpeg.size();
       return true;
     };
     auto visit = [&](const gzb::Trial& t, const gzb::TrialOutcome& o) {
@@ -1062,7 +1071,11 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       for (int c = 0; c < 3; ++c) f.coeffs[c] = e.idx[c].data();
       gzb::jpeg::frame_set_quant(&f, e.quant);
       header_size = static_cast<int>(gzb::jpeg::header_size(f));
-      gzb::jpeg::build_histograms(f, dc_hist, ac_hist, e.pool.get());
+      {  // all three components: the device writer decides from them whether chroma is dropped
+        Frame f3 = f;
+        f3.ncomp = 3;
+        gzb::jpeg::build_histograms(f3, dc_hist, ac_hist, e.pool.get());
+      }
       {  // EstimateDCSize (processor.cc:548-555)
         Histogram tmp[3] = {dc_hist[0], dc_hist[1], dc_hist[2]};
         size_t num = f.ncomp;
@@ -1078,8 +1091,11 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       for (int c = 0; c < 3; ++c)
         for (int b = b0; b < b1; ++b) zmask[c][b] = gzb::jpeg::zigzag_nonzero_mask(e.idx[c].data() + static_cast<size_t>(b) * 64);
     });
-    // the writer works on its own copy of the indices so that it can overlap the next iteration
-    WriterStage writer(&e, dc_hist);
+    // the coefficient flips of one iteration, pushed to the device before its Compare
+    struct Flips {
+      std::vector<int32_t> block; std::vector<uint8_t> cidx; std::vector<int16_t> val;
+      void clear() { block.clear(); cidx.clear(); val.clear(); }
+    } flips;
     std::vector<uint8_t> ac_depths(3 * Histogram::kSize);
     // ComputeEntropyCodes (processor.cc:517-536)
     gzb::jpeg::HuffCache huff_caches[5];
@@ -1207,7 +1223,8 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         float val_threshold = 0.0;
         int changed_coeffs = 0;
         int est_jpg_size = prev_size;
-        WriteJob* job = writer.new_job();
+        Flips* job = &flips;
+        job->clear();
         const size_t order_size = global_order.size();
         const size_t kAhead = 24;
         // ---- the silent prefix ----
@@ -1232,7 +1249,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
             for (size_t i = i0; i < i1; ++i) __atomic_fetch_add(&prefix_count[global_order[i].first], 1u, __ATOMIC_RELAXED);
           });
           struct Local {
-            std::vector<int32_t> block; std::vector<uint8_t> cidx; std::vector<int16_t> val, newidx;
+            std::vector<int32_t> block; std::vector<uint8_t> cidx; std::vector<int16_t> val;
             std::vector<int> touched;
             int64_t hist[3][Histogram::kSize];
           };
@@ -1287,7 +1304,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
                   emit(new_idx, 1);
                   blk_idx[k] = new_idx;
                   if (new_idx != 0) m |= 1ULL << z; else m &= ~(1ULL << z);
-                  L.block.push_back(b); L.cidx.push_back(static_cast<uint8_t>(cidx)); L.val.push_back(newval); L.newidx.push_back(new_idx);
+                  L.block.push_back(b); L.cidx.push_back(static_cast<uint8_t>(cidx)); L.val.push_back(newval);
                   last_indexes[b] += direction;
                 }
               }
@@ -1301,7 +1318,6 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
             job->block.insert(job->block.end(), L.block.begin(), L.block.end());
             job->cidx.insert(job->cidx.end(), L.cidx.begin(), L.cidx.end());
             job->val.insert(job->val.end(), L.val.begin(), L.val.end());
-            job->newidx.insert(job->newidx.end(), L.newidx.begin(), L.newidx.end());
             for (int b : L.touched) if (!touched[b]) { touched[b] = 1; touched_list.push_back(b); }
           }
           recount_bits();  // raw bit sums for the current codes and the new histograms
@@ -1384,7 +1400,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           emit(new_idx, 1);
           blk_idx[k] = new_idx;
           if (new_idx != 0) m |= 1ULL << z; else m &= ~(1ULL << z);
-          job->add(b, static_cast<uint8_t>(cidx), newval, new_idx);
+          job->block.push_back(b); job->cidx.push_back(static_cast<uint8_t>(cidx)); job->val.push_back(newval);
           last_indexes[b] += direction;
           if (!touched[b]) { touched[b] = 1; touched_list.push_back(b); }
           val_threshold = global_order[i].second;
@@ -1419,22 +1435,32 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         if (gzb_update_coeffs(e.ctx, job->block.data(), job->cidx.data(), job->val.data(), job->block.size()) != GZB_OK)
           return fail(GZB_ERR_CUDA);
         { const double t1 = now_ms(); e.st.be_update_ms += t1 - tt; tt = t1; }
-        for (int c = 0; c < 3; ++c) job->ac_hist[c] = ac_hist[c];
-        const bool ok = e.compare(true);
-        if (!ok) { writer.abort(); return fail(GZB_ERR_CUDA); }
-        char head[256];
-        snprintf(head, sizeof(head), "Iter %2d: f111111(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f]",
-                 e.st.num_iterations, comp_mask, direction > 0 ? "up" : "down", changed_coeffs, order_size,
-                 changed_blocks, blocks_to_change, num_blocks, val_threshold);
-        job->log_head = head;
-        job->est_jpg_size = est_jpg_size;
-        job->distance = e.distance;
-        job->score_target = e.target;
-        writer.submit(job);
+        if (!e.compare(true)) return fail(GZB_ERR_CUDA);
+        // the iteration's file: coded on the device with the histograms the walk maintains; only its
+        // size is needed unless it becomes the best (processor.cc:897-915, MaybeOutput 151-160)
+        const double tw = now_ms();
+        DeviceJpeg dj;
+        if (!device_code_candidate(e.ctx, width, height, e.nb, e.quant, false, dc_hist, ac_hist, &dj)) return fail(GZB_ERR_CUDA);
+        e.st.num_jpeg_writes++;
+        const size_t jpg_size = dj.size();
+        e.log("Iter %2d: f111111(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
+              e.st.num_iterations, comp_mask, direction > 0 ? "up" : "down", changed_coeffs, order_size,
+              changed_blocks, blocks_to_change, num_blocks, val_threshold, jpg_size,
+              100.0 - (100.0 * est_jpg_size) / jpg_size);
+        e.log(" BA[100.00%%] D[%6.4f]", e.distance);
+        const double score = score_jpeg(e.distance, static_cast<int>(jpg_size), e.target);
+        e.log(" Score[%.4f]", score);
+        if (score < e.best_score || e.best_score < 0) {
+          if (!device_fetch_jpeg(e.ctx, dj, &e.best_jpeg)) return fail(GZB_ERR_CUDA);
+          e.best_score = score;
+          e.best_remote = false;
+          e.log(" (*)");
+        }
+        e.log("\n");
+        e.st.device_write_ms += now_ms() - tw;
         prev_size = est_jpg_size;
       }
     }
-    writer.finish();
     e.st.backend_wall_ms = now_ms() - t_be;
   }
 

@@ -263,8 +263,6 @@ void build_ac_histograms(const Frame& f, Histogram* h) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-struct CodeTable { uint8_t depth[256]; uint16_t code[256]; };
-
 // Canonical code from depths; the sentinel (symbol 256, deepest, last) is dropped
 // (BuildHuffmanCode + BuildHuffmanCodeTable, jpeg_data_writer.cc:136-187).
 void make_code(const uint8_t* depth257, int counts[17], int values[257], CodeTable* table) {
@@ -419,9 +417,8 @@ void build_histograms(const Frame& f, Histogram* dc, Histogram* ac, WorkerPool* 
   }
 }
 
-void write_jpeg(const Frame& f, std::string* out, WorkerPool* pool, const Histogram* dc_hist,
-                const Histogram* ac_hist, WriteTimers* tm) {
-  double t0 = now_ms_();
+void write_jpeg_header(const Frame& f, const Histogram* dc_hist, const Histogram* ac_hist, std::string* out,
+                       CodeTable* dc_tab, CodeTable* ac_tab) {
   out->clear();
   const int ncomp = f.ncomp;
   // SOI + APP0 (stripped metadata always writes the fixed JFIF header)
@@ -457,15 +454,13 @@ void write_jpeg(const Frame& f, std::string* out, WorkerPool* pool, const Histog
     }
   }
   // Huffman codes: DC histograms clustered, then AC histograms clustered.
-  Histogram histo[6], hdc[3], hac[3];
+  Histogram histo[6];
   uint8_t depths[6 * Histogram::kSize];
-  if (!dc_hist || !ac_hist) build_histograms(f, hdc, hac, pool);
-  for (int c = 0; c < ncomp; ++c) histo[c] = dc_hist ? dc_hist[c] : hdc[c];
-  if (tm) { const double t1 = now_ms_(); tm->hist_ms += t1 - t0; t0 = t1; }
+  for (int c = 0; c < ncomp; ++c) histo[c] = dc_hist[c];
   size_t num_dc = ncomp;
   int dc_idx[4], ac_idx[4];
   cluster_histograms(histo, &num_dc, dc_idx, depths);
-  for (int c = 0; c < ncomp; ++c) histo[num_dc + c] = ac_hist ? ac_hist[c] : hac[c];
+  for (int c = 0; c < ncomp; ++c) histo[num_dc + c] = ac_hist[c];
   size_t num_ac = ncomp;
   cluster_histograms(histo + num_dc, &num_ac, ac_idx, depths + num_dc * Histogram::kSize);
   const int num_histo = static_cast<int>(num_dc + num_ac);
@@ -474,7 +469,6 @@ void write_jpeg(const Frame& f, std::string* out, WorkerPool* pool, const Histog
   const int dht_len = 2 + num_histo * 17 + total_symbols;
   out->push_back(static_cast<char>(0xff)); out->push_back(static_cast<char>(0xc4));
   out->push_back(static_cast<char>(dht_len >> 8)); out->push_back(static_cast<char>(dht_len & 0xff));
-  CodeTable dc_tab[3], ac_tab[3];
   for (int i = 0; i < num_histo; ++i) {
     const bool is_dc = i < static_cast<int>(num_dc);
     const int idx = is_dc ? i : i - static_cast<int>(num_dc);
@@ -505,6 +499,22 @@ void write_jpeg(const Frame& f, std::string* out, WorkerPool* pool, const Histog
     }
     out->push_back(0); out->push_back(63); out->push_back(0);
   }
+}
+
+void write_jpeg(const Frame& f, std::string* out, WorkerPool* pool, const Histogram* dc_hist,
+                const Histogram* ac_hist, WriteTimers* tm) {
+  double t0 = now_ms_();
+  const int ncomp = f.ncomp;
+  Histogram hdc[3], hac[3];
+  if (!dc_hist || !ac_hist) {
+    build_histograms(f, hdc, hac, pool);
+    dc_hist = hdc;
+    ac_hist = hac;
+  }
+  if (tm) { const double t1 = now_ms_(); tm->hist_ms += t1 - t0; t0 = t1; }
+  CodeTable dc_tab[3], ac_tab[3];
+  write_jpeg_header(f, dc_hist, ac_hist, out, dc_tab, ac_tab);
+  (void)ncomp;
   if (tm) { const double t1 = now_ms_(); tm->code_ms += t1 - t0; t0 = t1; }
   // Entropy-coded segment: bands of block rows coded in parallel.
   const int T = pool ? std::max(1, std::min(pool->size(), f.bh)) : 1;

@@ -104,6 +104,14 @@ void build_ac_histograms(const Frame& f, Histogram* h /*[ncomp]*/);
 // Per-component DC / AC histograms of a frame (unclustered), band-parallel.
 void build_histograms(const Frame& f, Histogram* dc /*[ncomp]*/, Histogram* ac /*[ncomp]*/, WorkerPool* pool);
 
+// Canonical Huffman code of one table: depth 255 marks an unused symbol.
+struct CodeTable { uint8_t depth[256]; uint16_t code[256]; };
+// Everything of WriteJpeg up to and including the SOS header (SOI, APP0, DQT, SOF, DHT, SOS):
+// clusters the per-component DC and AC histograms, builds the codes and returns the per-component
+// code tables the scan is coded with.
+void write_jpeg_header(const Frame& f, const Histogram* dc_hist /*[ncomp]*/, const Histogram* ac_hist /*[ncomp]*/,
+                       std::string* out, CodeTable* dc_tab /*[3]*/, CodeTable* ac_tab /*[3]*/);
+
 struct WriteTimers { double hist_ms = 0, code_ms = 0, encode_ms = 0, stitch_ms = 0; };
 
 // WriteJpeg(jpg, strip_metadata=true, out). With a pool, block-row bands are Huffman-coded in

@@ -10,7 +10,9 @@
 // all-gathers {distance, jpg_size} (16 bytes per rank) and then REPLAYS the reference's sequential
 // logic over the cached results in the reference's visiting order. Decisions, the verbose trace and
 // the chosen matrix are therefore identical to the single-GPU run for any world size; speculative
-// results that the replay never reaches are simply unused.
+// results that the replay never reaches are simply unused. A rank may also take `batch` trials per
+// round (their host legs -- quantise + Huffman-code the file -- run concurrently on host threads
+// while the GPU compares them one after the other), so even a single GPU needs fewer serial rounds.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -121,16 +123,17 @@ struct TrialOutcome {
   float distance = 0.f;
   uint64_t jpg_size = 0;
   int owner = 0;      // rank that evaluated it (its JPEG bytes exist there only)
-  std::string jpeg;   // filled on the owner
+  std::string jpeg;   // on the owner: the file's header (everything up to the scan) ...
+  std::string scan;   // ... and its entropy-coded segment before byte stuffing
 };
 
 class QuantSearch {
  public:
   // evaluate: run the trial on this rank's GPU. visit: called once per trial in the reference's order.
-  typedef std::function<bool(const Trial&, TrialOutcome*)> EvalFn;
+  typedef std::function<bool(const std::vector<Trial>&, std::vector<TrialOutcome>*)> EvalFn;
   typedef std::function<void(const Trial&, const TrialOutcome&)> VisitFn;
 
-  QuantSearch(const Group& g, float target) : g_(g), target_(target) {}
+  QuantSearch(const Group& g, float target, int batch = 1) : g_(g), target_(target), batch_(std::max(1, batch)) {}
 
   bool run(const EvalFn& evaluate, const VisitFn& visit) {
     State st;
@@ -218,7 +221,8 @@ class QuantSearch {
     int seq = 0;
     pq.push(Node{1.0, seq++, from});
     int expanded = 0;
-    while (static_cast<int>(list.size()) < g_.world && !pq.empty() && expanded < 64 * g_.world) {
+    const int want = g_.world * batch_;
+    while (static_cast<int>(list.size()) < want && !pq.empty() && expanded < 64 * want) {
       Node n = pq.top();
       pq.pop();
       ++expanded;
@@ -246,30 +250,39 @@ class QuantSearch {
       }
     }
     ++rounds_;
+    // list[r * batch + j] goes to rank r
     struct Rec { int32_t valid; float distance; uint64_t jpg_size; };
-    Rec mine{0, 0.f, 0};
-    TrialOutcome local;
-    if (g_.rank < static_cast<int>(list.size())) {
-      if (!evaluate(list[g_.rank], &local)) return false;
-      ++evaluated_here_;
-      mine.valid = 1;
-      mine.distance = local.distance;
-      mine.jpg_size = local.jpg_size;
+    std::vector<Rec> mine(batch_, Rec{0, 0.f, 0});
+    std::vector<Trial> my_trials;
+    for (int j = 0; j < batch_; ++j) {
+      const size_t k = static_cast<size_t>(g_.rank) * batch_ + j;
+      if (k < list.size()) my_trials.push_back(list[k]);
     }
-    std::vector<Rec> all(g_.world);
+    std::vector<TrialOutcome> local(my_trials.size());
+    if (!my_trials.empty()) {
+      if (!evaluate(my_trials, &local)) return false;
+      evaluated_here_ += static_cast<int>(my_trials.size());
+      for (size_t j = 0; j < my_trials.size(); ++j) mine[j] = Rec{1, local[j].distance, local[j].jpg_size};
+    }
+    std::vector<Rec> all(static_cast<size_t>(g_.world) * batch_);
     if (g_.world > 1) {
-      if (!g_.allgather || g_.allgather(g_.user, &mine, sizeof(Rec), all.data()) != 0) return false;
+      if (!g_.allgather || g_.allgather(g_.user, mine.data(), sizeof(Rec) * batch_, all.data()) != 0) return false;
     } else {
-      all[0] = mine;
+      all = mine;
     }
-    for (int r = 0; r < static_cast<int>(list.size()); ++r) {
-      if (!all[r].valid) return false;
+    for (size_t k = 0; k < list.size(); ++k) {
+      if (!all[k].valid) return false;
+      const int r = static_cast<int>(k / batch_);
       TrialOutcome o;
-      o.distance = all[r].distance;
-      o.jpg_size = all[r].jpg_size;
+      o.distance = all[k].distance;
+      o.jpg_size = all[k].jpg_size;
       o.owner = r;
-      if (r == g_.rank) o.jpeg.swap(local.jpeg);
-      keys_.push_back(list[r]);
+      if (r == g_.rank) {
+        TrialOutcome& mine_o = local[k - static_cast<size_t>(r) * batch_];
+        o.jpeg.swap(mine_o.jpeg);
+        o.scan.swap(mine_o.scan);
+      }
+      keys_.push_back(list[k]);
       cache_.push_back(std::move(o));
     }
     return true;
@@ -277,6 +290,7 @@ class QuantSearch {
 
   Group g_;
   float target_;
+  int batch_;
   std::vector<Trial> keys_;
   std::vector<TrialOutcome> cache_;
   QuantData best_{};

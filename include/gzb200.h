@@ -90,6 +90,8 @@ int gzb_get_distmap(gzb_ctx* ctx, float* distmap_out);
 int gzb_distance_ok(const gzb_ctx* ctx, double target_mul);
 double gzb_score_output_size(const gzb_ctx* ctx, int size);
 float gzb_block_error_limit(const gzb_ctx* ctx);
+/* Image geometry of the context. */
+int gzb_image_size(const gzb_ctx* ctx, int* width, int* height);
 /* StartBlockComparisons / FinishBlockComparisons (guetzli/butteraugli_comparator.cc:72-83):
  * builds the per-block mask scale (mask_xyz_ at each block's top-left pixel) on the device. */
 int gzb_start_block_comparisons(gzb_ctx* ctx);
@@ -123,6 +125,29 @@ int gzb_compute_block_zeroing_candidates(gzb_ctx* ctx, int comp_mask, int* offse
 int gzb_compute_block_zeroing_candidates_range(gzb_ctx* ctx, int comp_mask, int block_begin, int block_end,
                                                int* offsets, uint8_t* cand_idx, float* cand_err, size_t cap,
                                                size_t* n_out);
+/* ---- the candidate as a JPEG, coded on the device ----------------------------------------------
+ * OutputImage::SaveToJpegData + WriteJpeg (guetzli/output_image.cc:579-640, guetzli/jpeg_data_writer.cc:
+ * 361-553) for the resident candidate: the reference serialises every candidate only to learn its
+ * size (guetzli/processor.cc:290-296, 897-903). */
+/* BuildDCHistograms / BuildACHistograms (jpeg_data_writer.cc:189-247) of the quantised candidate:
+ * raw symbol counts, dc_hist[3][16], ac_hist[3][256]. q192 (may be NULL = the matrix last given to
+ * gzb_copy_from_jpeg / gzb_apply_global_quantization) is what the candidate's values are multiples of. */
+int gzb_candidate_symbol_histograms(gzb_ctx* ctx, const int* q192, uint32_t* dc_hist48, uint32_t* ac_hist768);
+/* EncodeScan (jpeg_data_writer.cc:249-359) with the given per-component code tables
+ * (dc_code/dc_len[3][16], ac_code/ac_len[3][256]); ncomp is 1 when both chroma planes are all zero
+ * (output_image.cc:588), else 3. The scan stays on the device; *scan_bytes is its length before
+ * byte stuffing (the last byte padded with ones), *ff_bytes the number of 0xff bytes in it:
+ * file size = header + scan_bytes + ff_bytes + 2. */
+int gzb_candidate_entropy_code(gzb_ctx* ctx, int ncomp, const uint16_t* dc_code, const uint8_t* dc_len,
+                               const uint16_t* ac_code, const uint8_t* ac_len, uint64_t* scan_bytes,
+                               uint64_t* ff_bytes);
+/* Copies the (unstuffed) scan of the last gzb_candidate_entropy_code to the host. */
+int gzb_candidate_fetch_scan(gzb_ctx* ctx, uint8_t* out, uint64_t nbytes);
+/* The whole file: histograms, ClusterHistograms + code construction (host), scan on the device.
+ * input_tables != 0 writes the q tables the way the RGB front end leaves them. *size_out is the file
+ * size; the bytes are produced (header + stuffed scan + EOI) only when out != NULL and cap suffices. */
+int gzb_write_candidate_jpeg(gzb_ctx* ctx, const int* q192, int input_tables, uint8_t* out, size_t cap,
+                             size_t* size_out);
 /* ComputeBlockDCTDouble / ComputeBlockIDCTDouble (guetzli/dct_double.cc:47-85), batched: nblocks
  * blocks of 64 doubles, in place. Only the reference's 4:2:0 path uses these transforms. */
 int gzb_dct_double(int device, double* blocks, size_t nblocks, int inverse);
@@ -174,6 +199,7 @@ typedef struct {
   float final_distance;
   unsigned long long launches;
   unsigned long long be_prefix_steps;    /* of be_steps: applied block-parallel in the silent prefix */
+  double device_write_ms;                /* candidate files coded on the device (histograms, codes, scan, fetch) */
   double search_wall_ms, trial_host_ms, trial_device_ms;  /* SelectQuantMatrix phase; host/device legs of its trials */
   int search_rounds, search_trials;      /* SelectQuantMatrix: exchange rounds / trials evaluated by the group */
 } gzb_encode_stats;

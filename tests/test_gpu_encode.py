@@ -187,3 +187,28 @@ def test_zeroing_candidates_by_block_range_equal_whole(gz):
         assert np.array_equal(o, off[b0:b1 + 1] - off[b0])
         assert np.array_equal(i, idx[off[b0]:off[b1]]) and np.array_equal(e, err[off[b0]:off[b1]])
     c.close()
+
+
+@pytest.mark.parametrize("w,h,q,seed", [(64, 48, 1, 1234), (97, 61, 5, 1244), (200, 133, 2, 1254), (444, 258, 3, 0),
+                                        (160, 120, 40, 1264), (256, 192, 200, 1274)])
+def test_device_huffman_writer_bytes_equal_host_writer(gz, w, h, q, seed):
+    """gzb_write_candidate_jpeg (scan coded on the GPU) == the host writer (which test_host_cpu pins
+    byte for byte to the reference's WriteJpeg), including grey-only output when chroma quantises to
+    zero (q=200) and the input-table variant of the q=1 original."""
+    img = bees() if seed == 0 else synth_image(w, h, seed)
+    c = gz.ButteraugliComparator(w, h, img, 0.97)
+    co = gz.RgbToJpegCoeffs(img)
+    c.SetJpegCoeffs(co)
+    c.CopyFromJpegData()
+    qm = np.full(192, q, np.int32)
+    qm[64:] += (seed % 3)              # different chroma tables
+    c.ApplyGlobalQuantization(qm)
+    cur = c.GetCoeffs()
+    want = gz.WriteJpeg(cur, w, h, qm, input_tables=False, host_threads=3)   # takes dequantised values
+    size, got = c.WriteJpeg(qm)
+    assert size == len(want) and got == want
+    assert c.WriteJpeg(qm, want_bytes=False)[0] == len(want)
+    if q == 1:
+        want_in = gz.WriteJpeg(cur, w, h, qm, input_tables=True, host_threads=1)
+        assert c.WriteJpeg(qm, input_tables=True)[1] == want_in
+    c.close()

@@ -154,14 +154,14 @@ class BarrierAllGather:
         return ag
 
 
-def run_group(gz, world, target, ev):
+def run_group(gz, world, target, ev, batch=1):
     if world == 1:
-        return [gz.QuantSearchSimulate(0, 1, None, target, ev)]
+        return [gz.QuantSearchSimulate(0, 1, None, target, ev, batch)]
     ag = BarrierAllGather(world)
     res = [None] * world
 
     def work(r):
-        res[r] = gz.QuantSearchSimulate(r, world, ag.for_rank(r), target, ev)
+        res[r] = gz.QuantSearchSimulate(r, world, ag.for_rank(r), target, ev, batch)
     th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
     for t in th:
         t.start()
@@ -209,3 +209,21 @@ def test_eight_ranks_need_about_a_third_of_the_rounds(gz):
     r2 = run_group(gz, 2, 0.971769, ev)[0]
     assert r8["rounds"] <= math.ceil(len(want_visited) / 2.5)
     assert r8["rounds"] <= r2["rounds"] < len(want_visited)
+
+
+@pytest.mark.parametrize("kind", ["typical", "never_ok", "always_ok", "early_exit", "wobbly"])
+@pytest.mark.parametrize("world,batch", [(1, 2), (1, 4), (2, 3), (4, 4)])
+def test_batched_trials_per_rank_replay_the_reference_sequence(gz, kind, world, batch):
+    """Several trials per rank and round (concurrent host legs on one GPU) change nothing either."""
+    target = 0.971769
+    ev = make_eval(kind)
+    want_visited, want_best = reference_search(ev, target)
+    res = run_group(gz, world, target, ev, batch)
+    for r in res:
+        assert len(r["visited"]) == len(want_visited)
+        for g, w in zip(r["visited"], want_visited):
+            assert g[0] == w[0] and abs(g[1] - w[1]) < 1e-9 and g[2] == w[2] and g[3] == w[3]
+        assert r["best_q"] == want_best[0] and r["best_ok"] == want_best[1]
+    distinct = len({(v[0], v[1]) for v in want_visited})
+    assert res[0]["rounds"] < distinct
+    assert sum(r["evaluated_here"] for r in res) == res[0]["evaluated_total"]
