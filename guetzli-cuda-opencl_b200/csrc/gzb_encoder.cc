@@ -1139,6 +1139,22 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
     std::vector<uint8_t> touched(num_blocks, 0);
     std::vector<int> touched_list;
     std::vector<uint32_t> prefix_count;
+    // windowed evaluation of the entropy-code rebuilds (see the walk below)
+    struct SymDelta { int16_t sym; int8_t c; int8_t w; };
+    struct UndoRec { int block; uint8_t c, k; int16_t old_idx; uint64_t old_mask; bool newly_touched; uint32_t delta_begin; };
+    struct CodeWindow {
+      size_t first = 0;
+      int nsteps = 0, changed_first = 0, break_step = -1, ac_histogram_size = 0;
+      uint32_t delta_begin[11];
+      Histogram hist[3];
+      uint8_t depths[3 * Histogram::kSize];
+      uint64_t raw[10][3];
+      int est[10];
+      gzb::jpeg::HuffCache caches[5];
+    };
+    std::vector<CodeWindow> windows;
+    std::vector<SymDelta> dlog;
+    std::vector<UndoRec> ulog;
     bool first_up_iter = true;
     const int directions[2] = {1, -1};
     const int n_cerr = static_cast<int>(cand_errors.size());
@@ -1329,7 +1345,10 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           sorter.ensure_bulk(std::min<size_t>(static_cast<size_t>(min_coeffs_to_change), global_order.size() - 1));
           e.st.be_sort_ms += now_ms() - ts;
         }
-        for (size_t i = prefix; i < order_size; ++i) {
+        // One step of the walk (processor.cc:843-876): flips the next candidate of the order's i-th
+        // block and updates the AC histograms by the symbols that change. With `dlog` the symbol
+        // deltas and an undo record are logged instead of being priced with the current codes.
+        auto flip = [&](size_t i, std::vector<SymDelta>* dlog, std::vector<UndoRec>* ulog) {
           if (sorter.sorted() <= std::min(i + kAhead, order_size - 1)) {
             const double ts = now_ms();
             sorter.ensure(std::min(i + kAhead, order_size - 1));
@@ -1371,6 +1390,8 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           // 871-873) restricted to the symbols that differ: those between the previous (p) and the
           // next (n) non-zero coefficient around zig-zag position z.
           uint64_t& m = zmask[c][b];
+          if (ulog) ulog->push_back(UndoRec{b, static_cast<uint8_t>(c), static_cast<uint8_t>(k), old_idx, m, touched[b] == 0,
+                                            static_cast<uint32_t>(dlog->size())});
           const uint64_t lower = m & ((1ULL << z) - 1);
           const int p = lower ? 63 - __builtin_clzll(lower) : 0;
           const uint64_t upper = z < 63 ? (m >> (z + 1)) : 0;
@@ -1380,7 +1401,8 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           const uint8_t* d = &ac_depths[c * Histogram::kSize];
           auto add_sym = [&](int sym, int weight) {
             hh.add(sym, weight);
-            raw_bits[c] += static_cast<int64_t>(weight) * (d[sym] + (sym & 0xf));
+            if (dlog) dlog->push_back(SymDelta{static_cast<int16_t>(sym), static_cast<int8_t>(c), static_cast<int8_t>(weight)});
+            else raw_bits[c] += static_cast<int64_t>(weight) * (d[sym] + (sym & 0xf));
           };
           auto add_run = [&](int run, int v, int weight) {
             while (run > 15) { add_sym(0xf0, weight); run -= 16; }
@@ -1403,26 +1425,131 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           job->block.push_back(b); job->cidx.push_back(static_cast<uint8_t>(cidx)); job->val.push_back(newval);
           last_indexes[b] += direction;
           if (!touched[b]) { touched[b] = 1; touched_list.push_back(b); }
-          val_threshold = global_order[i].second;
           ++changed_coeffs;
           ++e.st.be_steps;
-          if (i % 10 == 0) {
-            // Evaluate only where the result can be observed: by the break test within the next 10
-            // steps, or as prev_size when the order is about to run out.
-            const bool needed = static_cast<long long>(i) + 9 >= min_coeffs_to_change ||
-                                i + 9 >= order_size - 1;
-            if (needed) {
-              const double tb = now_ms();
-              ac_histogram_size = static_cast<int>(compute_entropy_codes());
-              recount_bits();
-              e.st.be_codes_ms += now_ms() - tb;
-            }
+        };
+        auto rebuild_needed = [&](size_t i) {
+          // Evaluate only where the result can be observed: by the break test within the next 10
+          // steps, or as prev_size when the order is about to run out.
+          return static_cast<long long>(i) + 9 >= min_coeffs_to_change || i + 9 >= order_size - 1;
+        };
+        const bool windowed = e.pool->size() >= 4;
+        size_t i = prefix;
+        bool stopped = false;
+        size_t last_step = prefix;   // index of the last step that stays applied
+        // ---- the steps up to the first observable entropy-code rebuild: the reference's loop as is ----
+        for (; i < order_size; ++i) {
+          if (windowed && i % 10 == 0 && rebuild_needed(i)) break;
+          flip(i, nullptr, nullptr);
+          last_step = i;
+          if (i % 10 == 0 && rebuild_needed(i)) {
+            const double tb = now_ms();
+            ac_histogram_size = static_cast<int>(compute_entropy_codes());
+            recount_bits();
+            e.st.be_codes_ms += now_ms() - tb;
           }
           if (changed_coeffs > min_coeffs_to_change || i + 1 == order_size) {
             est_jpg_size = header_size + dc_size + ac_histogram_size + static_cast<int>(coded_size());
-            if (changed_coeffs > min_coeffs_to_change && std::abs(est_jpg_size - prev_size) > min_size_delta) break;
+            if (changed_coeffs > min_coeffs_to_change && std::abs(est_jpg_size - prev_size) > min_size_delta) { stopped = true; break; }
           }
         }
+        // ---- from there on: windows of ten steps, each opening with a ComputeEntropyCodes rebuild ----
+        // The flips do not depend on the codes (only the stopping test does), so this thread walks a
+        // batch of windows ahead, logging symbol deltas and undo records, the pool rebuilds the codes
+        // of every window and replays its size estimates in parallel, and the flips past the first
+        // window that stops are undone. Decisions are those of the one-step-at-a-time loop.
+        if (windowed && !stopped && i < order_size) {
+          const int NB = 2 * e.pool->size();
+          if (static_cast<int>(windows.size()) < NB) windows.resize(NB);
+          while (!stopped && i < order_size) {
+            const double tb = now_ms();
+            dlog.clear();
+            ulog.clear();
+            const size_t i0 = i;
+            int nw = 0;
+            while (nw < NB && i < order_size) {
+              CodeWindow& W = windows[nw++];
+              W.first = i;
+              W.nsteps = 0;
+              W.break_step = -1;
+              for (int st = 0; st < 10 && i < order_size; ++st, ++i) {
+                W.delta_begin[st] = static_cast<uint32_t>(dlog.size());
+                flip(i, &dlog, &ulog);
+                if (st == 0) {
+                  for (int c = 0; c < 3; ++c) W.hist[c] = ac_hist[c];
+                  W.changed_first = changed_coeffs;
+                }
+                ++W.nsteps;
+              }
+              W.delta_begin[W.nsteps] = static_cast<uint32_t>(dlog.size());
+            }
+            e.pool->run(nw, [&](int w) {
+              CodeWindow& W = windows[w];
+              Histogram clustered[3] = {W.hist[0], W.hist[1], W.hist[2]};
+              size_t num = ncomp;
+              int indexes[4];
+              uint8_t cd[3 * Histogram::kSize];
+              gzb::jpeg::cluster_histograms(clustered, &num, indexes, cd, W.caches);
+              for (int c = 0; c < ncomp; ++c)
+                memcpy(&W.depths[c * Histogram::kSize], &cd[indexes[c] * Histogram::kSize], Histogram::kSize);
+              size_t hs = 0;
+              for (size_t k = 0; k < num; ++k) hs += gzb::jpeg::header_cost_bits(clustered[k]) / 8;
+              W.ac_histogram_size = static_cast<int>(hs);
+              uint64_t raw[3] = {0, 0, 0};
+              for (int c = 0; c < ncomp; ++c) {
+                const uint8_t* d = &W.depths[c * Histogram::kSize];
+                uint64_t bits = 0;
+                for (int k = 0; k + 1 < Histogram::kSize; ++k) bits += static_cast<uint64_t>(W.hist[c].counts[k] / 2) * (d[k] + (k & 0xf));
+                raw[c] = bits;
+              }
+              for (int st = 0; st < W.nsteps; ++st) {
+                if (st > 0)
+                  for (uint32_t j = W.delta_begin[st]; j < W.delta_begin[st + 1]; ++j) {
+                    const SymDelta& dl = dlog[j];
+                    raw[dl.c] += static_cast<int64_t>(dl.w) * (W.depths[dl.c * Histogram::kSize + dl.sym] + (dl.sym & 0xf));
+                  }
+                for (int c = 0; c < 3; ++c) W.raw[st][c] = raw[c];
+                const int changed = W.changed_first + st;
+                W.est[st] = -1;
+                if (changed > min_coeffs_to_change || W.first + st + 1 == order_size) {
+                  size_t numbits = 0;
+                  for (int c = 0; c < ncomp; ++c) numbits += raw[c] + ((raw[c] * 3 + 512) >> 10);
+                  const int est = header_size + dc_size + W.ac_histogram_size + static_cast<int>((numbits + 7) / 8);
+                  W.est[st] = est;
+                  if (changed > min_coeffs_to_change && std::abs(est - prev_size) > min_size_delta) { W.break_step = st; break; }
+                }
+              }
+            });
+            int final_w = nw - 1, final_st = windows[nw - 1].nsteps - 1;
+            for (int w = 0; w < nw; ++w)
+              if (windows[w].break_step >= 0) { final_w = w; final_st = windows[w].break_step; stopped = true; break; }
+            const CodeWindow& F = windows[final_w];
+            e.st.num_entropy_code_builds += final_w + 1;
+            last_step = F.first + final_st;
+            if (stopped) {  // undo the steps walked past the stop
+              const size_t keep = last_step + 1 - i0;
+              if (keep < ulog.size()) {
+                for (size_t j = dlog.size(); j-- > ulog[keep].delta_begin;) ac_hist[dlog[j].c].add(dlog[j].sym, -dlog[j].w);
+                for (size_t j = ulog.size(); j-- > keep;) {
+                  const UndoRec& u = ulog[j];
+                  e.idx[u.c][static_cast<size_t>(u.block) * 64 + u.k] = u.old_idx;
+                  zmask[u.c][u.block] = u.old_mask;
+                  last_indexes[u.block] -= direction;
+                  if (u.newly_touched) { touched[u.block] = 0; touched_list.pop_back(); }
+                  job->block.pop_back(); job->cidx.pop_back(); job->val.pop_back();
+                  --changed_coeffs;
+                  --e.st.be_steps;
+                }
+              }
+            }
+            memcpy(ac_depths.data(), F.depths, 3 * Histogram::kSize);
+            ac_histogram_size = F.ac_histogram_size;
+            for (int c = 0; c < 3; ++c) raw_bits[c] = F.raw[final_st][c];
+            if (F.est[final_st] >= 0) est_jpg_size = F.est[final_st];
+            e.st.be_codes_ms += now_ms() - tb;
+          }
+        }
+        if (changed_coeffs > 0) val_threshold = global_order[last_step].second;
         const size_t changed_blocks = touched_list.size();
         for (int tb : touched_list) touched[tb] = 0;
         touched_list.clear();
