@@ -4,6 +4,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <ctime>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -241,6 +243,7 @@ struct Prof {
 struct gzb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // entropy coding of the candidate, concurrent with its Compare
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int W = 0, H = 0, P = 0, HP = 0, bw = 0, bh = 0, nblocks = 0, rxs = 0, rys = 0, sqp = 0;
   size_t ps = 0;       // floats per full-res plane (P * HP)
@@ -256,6 +259,7 @@ struct gzb_ctx {
   int packed_mask = 0, packed_b0 = 0, packed_b1 = 0;
   Prof prof;
   bool have_orig_coeffs = false, have_coeffs = false, block_cmp = false, have_distmap = false;
+  bool compare_pending = false;
   int sm_count = 148;
   std::string err;
 
@@ -295,15 +299,16 @@ static thread_local std::string g_create_err;
 namespace {
 
 // Launch wrapper: counts the launch and, when profiling, brackets it with an event pair.
-#define KLAUNCH(c, kclass, ...)                                        \
+#define KLAUNCH_S(c, strm, kclass, ...)                                \
   do {                                                                 \
     cudaEvent_t ea_ = nullptr;                                         \
-    if ((c)->prof.on) { ea_ = (c)->prof.get(); cudaEventRecord(ea_, (c)->stream); } \
+    if ((c)->prof.on) { ea_ = (c)->prof.get(); cudaEventRecord(ea_, (strm)); } \
     __VA_ARGS__;                                                       \
-    if ((c)->prof.on) { cudaEvent_t eb_ = (c)->prof.get(); cudaEventRecord(eb_, (c)->stream); \
+    if ((c)->prof.on) { cudaEvent_t eb_ = (c)->prof.get(); cudaEventRecord(eb_, (strm)); \
                         (c)->prof.pend.push_back({kclass, ea_, eb_}); } \
     (c)->launches += 1;                                                \
   } while (0)
+#define KLAUNCH(c, kclass, ...) KLAUNCH_S(c, (c)->stream, kclass, __VA_ARGS__)
 
 void prof_resolve(gzb_ctx* c) {
   for (auto& p : c->prof.pend) {
@@ -418,6 +423,7 @@ void free_ctx(gzb_ctx* c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   delete c;
 }
 
@@ -443,6 +449,7 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     init_device_tables(device);
     CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     c->W = W; c->H = H; c->target = target;
@@ -540,6 +547,12 @@ void sync_check(gzb_ctx* c) {
   CK(cudaGetLastError());
   if (!c->prof.pend.empty()) prof_resolve(c);
 }
+// The side stream of the entropy coder. Pending profile events are resolved by the next sync_check
+// (main-stream events may still be in flight here).
+void sync_check2(gzb_ctx* c) {
+  CK(cudaStreamSynchronize(c->stream2));
+  CK(cudaGetLastError());
+}
 
 }  // namespace
 
@@ -632,30 +645,48 @@ int gzb_get_coeffs(gzb_ctx* c, int16_t* c0, int16_t* c1, int16_t* c2) {
   GZB_END(c)
 }
 
+static double dbg_now_ms() {
+  timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 int gzb_update_coeffs(gzb_ctx* c, const int32_t* block_ix, const uint8_t* idx, const int16_t* val, size_t n) {
   GZB_TRY(c)
+  static const bool dbg = getenv("GZB_DEBUG") != nullptr;
+  const double d0 = dbg_now_ms();
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_update_coeffs: no candidate coefficients");
   for (size_t i = 0; i < n; ++i)
     if (block_ix[i] < 0 || block_ix[i] >= c->nblocks || idx[i] >= 192) return fail(c, GZB_ERR_BAD_ARG, "gzb_update_coeffs: index out of range");
   if (n > 0) {
-    if (n > c->upd_cap) {
-      if (c->upd_own && c->d_upd) cudaFree(c->d_upd);
-      c->upd_cap = n + n / 2 + 1024;
-      dmalloc(&c->d_upd, c->upd_cap * 8);
-      c->upd_own = true;
+    // staging: the blur scratch (6 planes, >= 24 bytes per pixel) holds 8 bytes per record for up to
+    // three records per pixel -- more than there are AC coefficients; larger batches get their own
+    c->packed_valid = false;
+    uint8_t* stage = reinterpret_cast<uint8_t*>(c->d_tmp);
+    size_t cap = 6 * c->ps * sizeof(float) / 8;
+    if (n > cap) {
+      if (n > c->upd_cap) {
+        if (c->upd_own && c->d_upd) cudaFree(c->d_upd);
+        c->upd_cap = n + n / 2 + 1024;
+        dmalloc(&c->d_upd, c->upd_cap * 8);
+        c->upd_own = true;
+      }
+      stage = c->d_upd;
+      cap = c->upd_cap;
     }
+    const double d1 = dbg_now_ms();
     // records are applied in order (later writes to the same coefficient win): one thread walks
     // duplicates, so pack {block, idx, val} and let the kernel resolve by record index
-    CK(cudaMemcpyAsync(c->d_upd, block_ix, n * 4, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n * 4);
-    CK(cudaMemcpyAsync(c->d_upd + c->upd_cap * 4, val, n * 2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n * 2);
-    CK(cudaMemcpyAsync(c->d_upd + c->upd_cap * 6, idx, n, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n);
+    CK(cudaMemcpyAsync(stage, block_ix, n * 4, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n * 4);
+    CK(cudaMemcpyAsync(stage + cap * 4, val, n * 2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n * 2);
+    CK(cudaMemcpyAsync(stage + cap * 6, idx, n, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n);
     const size_t cs = static_cast<size_t>(c->nblocks) * 64;
     KLAUNCH(c, KC_MISC, k_scatter_coeffs<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(
-        reinterpret_cast<const int*>(c->d_upd), reinterpret_cast<const int16_t*>(c->d_upd + c->upd_cap * 4),
-        c->d_upd + c->upd_cap * 6, n, cs, c->d_coef));
+        reinterpret_cast<const int*>(stage), reinterpret_cast<const int16_t*>(stage + cap * 4),
+        stage + cap * 6, n, cs, c->d_coef));
+    if (dbg) { sync_check(c); fprintf(stderr, "update n=%zu validate %.3f ms, h2d+scatter %.3f ms\n", n, d1 - d0, dbg_now_ms() - d1); }
   }
+  const double d2 = dbg_now_ms();
   render_candidate(c, kCoeffKeep);
   sync_check(c);
+  if (dbg) fprintf(stderr, "update render %.3f ms\n", dbg_now_ms() - d2);
   GZB_END(c)
 }
 
@@ -684,7 +715,7 @@ int gzb_to_srgb(gzb_ctx* c, uint8_t* rgb_out) {
   GZB_END(c)
 }
 
-int gzb_compare(gzb_ctx* c, float* distance) {
+int gzb_compare_begin(gzb_ctx* c) {
   GZB_TRY(c)
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compare: no candidate coefficients");
   CK(cudaEventRecord(c->ev0, c->stream));
@@ -692,12 +723,25 @@ int gzb_compare(gzb_ctx* c, float* distance) {
   run_diffmap(c, c->d_xyb0, c->d_xyb1);
   CK(cudaEventRecord(c->ev1, c->stream));
   CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(unsigned int));
+  c->compare_pending = true;
+  GZB_END(c)
+}
+
+int gzb_compare_end(gzb_ctx* c, float* distance) {
+  GZB_TRY(c)
+  if (!c->compare_pending) return fail(c, GZB_ERR_STATE, "gzb_compare_end: no Compare in flight");
+  c->compare_pending = false;
   sync_check(c);
   CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   memcpy(&c->distance, c->h_pinned, sizeof(float));
   c->have_distmap = true;
   if (distance) *distance = c->distance;
   GZB_END(c)
+}
+
+int gzb_compare(gzb_ctx* c, float* distance) {
+  const int rc = gzb_compare_begin(c);
+  return rc != GZB_OK ? rc : gzb_compare_end(c, distance);
 }
 
 int gzb_get_distmap(gzb_ctx* c, float* out) {
@@ -900,16 +944,17 @@ int gzb_candidate_symbol_histograms(gzb_ctx* c, const int* q192, uint32_t* dc_hi
   GZB_TRY(c)
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_candidate_symbol_histograms: no candidate coefficients");
   if (!dc_hist48 || !ac_hist768) return fail(c, GZB_ERR_BAD_ARG, "gzb_candidate_symbol_histograms: null argument");
-  if (q192) { CK(cudaMemcpyAsync(c->d_q, q192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += 192 * sizeof(int); }
+  if (q192) { CK(cudaMemcpyAsync(c->d_q, q192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream2)); c->h2d_bytes += 192 * sizeof(int); }
   const HuffScratch h = huff_scratch(c);
   const long long nunits = 3ll * c->nblocks;
-  CK(cudaMemsetAsync(h.hist, 0, (48 + 768) * 4, c->stream));
-  KLAUNCH(c, KC_HUFFMAN, k_huff_histogram<<<static_cast<unsigned>((nunits + kHuffThreads - 1) / kHuffThreads), kHuffThreads, 0, c->stream>>>(
+  CK(cudaMemsetAsync(h.hist, 0, (48 + 768) * 4, c->stream2));
+  KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_histogram<<<static_cast<unsigned>((nunits + kHuffThreads - 1) / kHuffThreads), kHuffThreads, 0, c->stream2>>>(
       c->d_coef, static_cast<size_t>(c->nblocks) * 64, c->d_q, 3, nunits, h.hist, h.hist + 48));
-  CK(cudaMemcpyAsync(c->h_pinned, h.hist, (48 + 768) * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (48 + 768) * 4;
-  sync_check(c);
-  memcpy(dc_hist48, c->h_pinned, 48 * 4);
-  memcpy(ac_hist768, reinterpret_cast<const uint32_t*>(c->h_pinned) + 48, 768 * 4);
+  uint32_t* hh = reinterpret_cast<uint32_t*>(c->h_pinned) + 128;  // bytes 512.. of the pinned page (Compare owns the start)
+  CK(cudaMemcpyAsync(hh, h.hist, (48 + 768) * 4, cudaMemcpyDeviceToHost, c->stream2)); c->d2h_bytes += (48 + 768) * 4;
+  sync_check2(c);
+  memcpy(dc_hist48, hh, 48 * 4);
+  memcpy(ac_hist768, hh + 48, 768 * 4);
   GZB_END(c)
 }
 
@@ -925,30 +970,27 @@ int gzb_candidate_entropy_code(gzb_ctx* c, int ncomp, const uint16_t* dc_code, c
   memcpy(t.dc_len, dc_len, sizeof(t.dc_len));
   memcpy(t.ac_code, ac_code, sizeof(t.ac_code));
   memcpy(t.ac_len, ac_len, sizeof(t.ac_len));
-  CK(cudaMemcpyAsync(h.tables, &t, sizeof(t), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += sizeof(t);
+  CK(cudaMemcpyAsync(h.tables, &t, sizeof(t), cudaMemcpyHostToDevice, c->stream2)); c->h2d_bytes += sizeof(t);
   const long long nunits = static_cast<long long>(ncomp) * c->nblocks;
   const unsigned grid = static_cast<unsigned>((nunits + kHuffThreads - 1) / kHuffThreads);
   const size_t cs = static_cast<size_t>(c->nblocks) * 64;
-  CK(cudaEventRecord(c->ev0, c->stream));
-  KLAUNCH(c, KC_HUFFMAN, k_huff_code<false><<<grid, kHuffThreads, 0, c->stream>>>(c->d_coef, cs, c->d_q, ncomp, nunits, h.tables,
+  KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_code<false><<<grid, kHuffThreads, 0, c->stream2>>>(c->d_coef, cs, c->d_q, ncomp, nunits, h.tables,
                                                                                   h.unit_bits, nullptr, nullptr));
-  KLAUNCH(c, KC_HUFFMAN, k_scan_u64<<<1, 1024, 0, c->stream>>>(h.unit_bits, nunits, h.unit_off));
-  unsigned long long* hp = reinterpret_cast<unsigned long long*>(c->h_pinned);
-  CK(cudaMemcpyAsync(hp, h.unit_off + nunits, 8, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 8;
-  sync_check(c);
+  KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_scan_u64<<<1, 1024, 0, c->stream2>>>(h.unit_bits, nunits, h.unit_off));
+  unsigned long long* hp = reinterpret_cast<unsigned long long*>(c->h_pinned) + 32;  // bytes 256..
+  CK(cudaMemcpyAsync(hp, h.unit_off + nunits, 8, cudaMemcpyDeviceToHost, c->stream2)); c->d2h_bytes += 8;
+  sync_check2(c);
   const unsigned long long total_bits = hp[0];
   const size_t nbytes = static_cast<size_t>((total_bits + 7) / 8);
   if (nbytes + 8 > h.stream_cap) return fail(c, GZB_ERR_UNSUPPORTED, "gzb_candidate_entropy_code: scan larger than the device buffer");
-  CK(cudaMemsetAsync(h.words, 0, (nbytes + 7) & ~size_t(3), c->stream));
-  CK(cudaMemsetAsync(h.out2, 0, 16, c->stream));
-  KLAUNCH(c, KC_HUFFMAN, k_huff_code<true><<<grid, kHuffThreads, 0, c->stream>>>(c->d_coef, cs, c->d_q, ncomp, nunits, h.tables,
+  CK(cudaMemsetAsync(h.words, 0, (nbytes + 7) & ~size_t(3), c->stream2));
+  CK(cudaMemsetAsync(h.out2, 0, 16, c->stream2));
+  KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_code<true><<<grid, kHuffThreads, 0, c->stream2>>>(c->d_coef, cs, c->d_q, ncomp, nunits, h.tables,
                                                                                  nullptr, h.unit_off, h.words));
   const unsigned fgrid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(static_cast<size_t>(c->sm_count) * 8, (nbytes + 4095) / 4096)));
-  KLAUNCH(c, KC_HUFFMAN, k_huff_finish<<<fgrid, 256, 0, c->stream>>>(reinterpret_cast<unsigned char*>(h.words), h.unit_off + nunits, h.out2));
-  CK(cudaEventRecord(c->ev1, c->stream));
-  CK(cudaMemcpyAsync(hp, h.out2, 16, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 16;
-  sync_check(c);
-  CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_finish<<<fgrid, 256, 0, c->stream2>>>(reinterpret_cast<unsigned char*>(h.words), h.unit_off + nunits, h.out2));
+  CK(cudaMemcpyAsync(hp, h.out2, 16, cudaMemcpyDeviceToHost, c->stream2)); c->d2h_bytes += 16;
+  sync_check2(c);
   *scan_bytes = hp[0];
   *ff_bytes = hp[1];
   GZB_END(c)
@@ -958,8 +1000,8 @@ int gzb_candidate_fetch_scan(gzb_ctx* c, uint8_t* out, uint64_t nbytes) {
   GZB_TRY(c)
   const HuffScratch h = huff_scratch(c);
   if (!out || nbytes > h.stream_cap) return fail(c, GZB_ERR_BAD_ARG, "gzb_candidate_fetch_scan: bad argument");
-  CK(cudaMemcpyAsync(out, h.words, nbytes, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += nbytes;
-  sync_check(c);
+  CK(cudaMemcpyAsync(out, h.words, nbytes, cudaMemcpyDeviceToHost, c->stream2)); c->d2h_bytes += nbytes;
+  sync_check2(c);
   GZB_END(c)
 }
 

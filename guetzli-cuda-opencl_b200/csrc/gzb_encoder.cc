@@ -226,7 +226,7 @@ class LazySort {
 
  private:
   struct Range { size_t first, last; int depth; };
-  static constexpr size_t kParallelMin = size_t(1) << 18;
+  static constexpr size_t kParallelMin = size_t(1) << 16;
 
   // std::__unguarded_partition_pivot(first, last) evaluated in parallel. The sequential scan swaps
   // the k-th element (from the left) that is not less than the pivot with the k-th element (from
@@ -239,7 +239,7 @@ class LazySort {
     const float pv = first->second;
     OrderEntry* a = first + 1;
     const size_t n = static_cast<size_t>(last - a);
-    const int T = std::max(1, std::min<int>(4 * pool_->size(), static_cast<int>(n >> 15)));
+    const int T = std::max(1, std::min<int>(4 * pool_->size(), static_cast<int>(n >> 13)));
     std::vector<size_t> cl(T + 1, 0), cr(T + 1, 0);
     auto bounds = [&](int t, size_t* b0, size_t* b1) { *b0 = n * t / T; *b1 = n * (t + 1) / T; };
     pool_->run(T, [&](int t) {
@@ -411,6 +411,56 @@ bool device_fetch_jpeg(gzb_ctx* ctx, const DeviceJpeg& dj, std::string* out) {
   return true;
 }
 
+// ---- pooled host arrays -------------------------------------------------------------------------
+// The coefficient mirrors are tens of megabytes; a fresh allocation pays a page fault per 4 KB on
+// first touch (~0.25 ms/MB), more than the whole front end. Released arrays are kept (a few per
+// process) so that back-to-back encodes reuse resident pages -- the host-side twin of the device
+// slab cache. Contents are NOT zeroed on reuse: every user writes before it reads.
+template <typename T>
+class PooledArray {
+ public:
+  PooledArray() = default;
+  PooledArray(const PooledArray&) = delete;
+  PooledArray& operator=(const PooledArray&) = delete;
+  ~PooledArray() { release(); }
+  void resize(size_t n) {
+    if (n * sizeof(T) <= cap_) { n_ = n; return; }
+    release();
+    const size_t bytes = n * sizeof(T);
+    {
+      std::lock_guard<std::mutex> l(mu());
+      auto& v = store();
+      int best = -1;
+      for (size_t i = 0; i < v.size(); ++i)
+        if (v[i].second >= bytes && v[i].second <= bytes + bytes / 2 + (1u << 20) && (best < 0 || v[i].second < v[best].second)) best = static_cast<int>(i);
+      if (best >= 0) { p_ = static_cast<T*>(v[best].first); cap_ = v[best].second; v.erase(v.begin() + best); }
+    }
+    if (!p_) { p_ = static_cast<T*>(malloc(std::max<size_t>(bytes, 64))); cap_ = bytes; }
+    n_ = n;
+  }
+  T* data() { return p_; }
+  const T* data() const { return p_; }
+  size_t size() const { return n_; }
+  T& operator[](size_t i) { return p_[i]; }
+  const T& operator[](size_t i) const { return p_[i]; }
+  const T* begin() const { return p_; }
+  const T* end() const { return p_ + n_; }
+
+ private:
+  void release() {
+    if (!p_) return;
+    std::lock_guard<std::mutex> l(mu());
+    auto& v = store();
+    if (v.size() >= 16) { free(v.front().first); v.erase(v.begin()); }
+    v.emplace_back(p_, cap_);
+    p_ = nullptr; cap_ = 0; n_ = 0;
+  }
+  static std::mutex& mu() { static std::mutex m; return m; }
+  static std::vector<std::pair<void*, size_t>>& store() { static std::vector<std::pair<void*, size_t>> v; return v; }
+  T* p_ = nullptr;
+  size_t n_ = 0, cap_ = 0;
+};
+
 // ---- encoder state ----------------------------------------------------------------------------
 struct Encoder {
   int w = 0, h = 0, bw = 0, bh = 0, nb = 0;
@@ -419,8 +469,8 @@ struct Encoder {
   gzb::jpeg::WriteTimers wt;
   float target = 0.f;
   gzb_ctx* ctx = nullptr;
-  std::vector<int16_t> orig[3];   // q=1 indices (jpg_in.components[c].coeffs)
-  std::vector<int16_t> idx[3];    // cur / quant (what the file stores)
+  PooledArray<int16_t> orig[3];   // q=1 indices (jpg_in.components[c].coeffs)
+  PooledArray<int16_t> idx[3];    // cur / quant (what the file stores)
   int quant[3][64];
   std::string best_jpeg;
   double best_score = -1;
@@ -468,7 +518,7 @@ struct Encoder {
   // the quantised indices of ApplyGlobalQuantization(q) on the q=1 input (host mirror)
   // Quantize(raw, q) / q (quantize.h:24-29) == sign(raw) * (|raw| / q + (2 * (|raw| % q) > q)); the
   // division is a multiplication by ceil(2^32 / q), exact for |raw| <= 2^15 and q < 2^16.
-  void quantize_host(const int q[3][64], std::vector<int16_t>* out3, gzb::WorkerPool* use_pool = nullptr) {
+  void quantize_host(const int q[3][64], PooledArray<int16_t>* out3, gzb::WorkerPool* use_pool = nullptr) {
     if (!use_pool) use_pool = pool.get();
     uint64_t magic[3][64];
     bool small = true;
@@ -505,6 +555,15 @@ struct Encoder {
     });
   }
 
+  bool compare_begin() { t_cmp = now_ms(); return gzb_compare_begin(ctx) == GZB_OK; }
+  bool compare_end() {
+    if (gzb_compare_end(ctx, &distance) != GZB_OK) return false;
+    st.device_compare_ms += gzb_last_device_ms(ctx);
+    st.compare_wall_ms += now_ms() - t_cmp;
+    st.num_compares++;
+    return true;
+  }
+  double t_cmp = 0;
   bool compare(bool quiet = false) {
     const double t0 = now_ms();
     if (gzb_compare(ctx, &distance) != GZB_OK) return false;
@@ -923,6 +982,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         gzb::TrialOutcome& o = (*os)[j];
         const double t0 = now_ms();
         if (t.original ? gzb_copy_from_jpeg(e.ctx, &ones[0][0]) != GZB_OK : !e.set_global_quant_device(t.q)) return false;
+        if (!e.compare_begin()) return false;   // the Compare runs while the file is coded on the second stream
         DeviceJpeg dj;
         if (!device_code_candidate(e.ctx, width, height, e.nb, t.q, t.original != 0, nullptr, nullptr, &dj)) return false;
         o.scan.resize(static_cast<size_t>(dj.scan_bytes));
@@ -931,7 +991,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         o.jpeg.swap(dj.header);
         e.st.num_jpeg_writes++;
         e.st.device_write_ms += now_ms() - t0;
-        if (!e.compare(true)) return false;
+        if (!e.compare_end()) return false;
         o.distance = e.distance;
         e.st.trial_device_ms += now_ms() - t0;
       }
@@ -1562,13 +1622,16 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         if (gzb_update_coeffs(e.ctx, job->block.data(), job->cidx.data(), job->val.data(), job->block.size()) != GZB_OK)
           return fail(GZB_ERR_CUDA);
         { const double t1 = now_ms(); e.st.be_update_ms += t1 - tt; tt = t1; }
-        if (!e.compare(true)) return fail(GZB_ERR_CUDA);
-        // the iteration's file: coded on the device with the histograms the walk maintains; only its
-        // size is needed unless it becomes the best (processor.cc:897-915, MaybeOutput 151-160)
+        if (!e.compare_begin()) return fail(GZB_ERR_CUDA);
+        // the iteration's file: coded on the device (second stream, concurrently with the Compare)
+        // with the histograms the walk maintains; only its size is needed unless it becomes the best
+        // (processor.cc:897-915, MaybeOutput 151-160)
         const double tw = now_ms();
         DeviceJpeg dj;
         if (!device_code_candidate(e.ctx, width, height, e.nb, e.quant, false, dc_hist, ac_hist, &dj)) return fail(GZB_ERR_CUDA);
         e.st.num_jpeg_writes++;
+        e.st.device_write_ms += now_ms() - tw;
+        if (!e.compare_end()) return fail(GZB_ERR_CUDA);
         const size_t jpg_size = dj.size();
         e.log("Iter %2d: f111111(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
               e.st.num_iterations, comp_mask, direction > 0 ? "up" : "down", changed_coeffs, order_size,
@@ -1584,7 +1647,6 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           e.log(" (*)");
         }
         e.log("\n");
-        e.st.device_write_ms += now_ms() - tw;
         prev_size = est_jpg_size;
       }
     }

@@ -84,6 +84,11 @@ int gzb_to_srgb(gzb_ctx* ctx, uint8_t* rgb_out);
  * stays on the device. *distance = distmap_aggregate(). Replaces ButteraugliComparatorEx::Compare
  * (clguetzli/clguetzli.cl.cpp:71-152). */
 int gzb_compare(gzb_ctx* ctx, float* distance);
+/* The same in two halves: begin enqueues the kernels and returns, end waits and reads the distance.
+ * Between them the candidate may be entropy-coded (gzb_candidate_* run on a second stream), but not
+ * modified. */
+int gzb_compare_begin(gzb_ctx* ctx);
+int gzb_compare_end(gzb_ctx* ctx, float* distance);
 /* distmap(): width*height floats. */
 int gzb_get_distmap(gzb_ctx* ctx, float* distmap_out);
 /* DistanceOK(target_mul) / ScoreOutputSize(size) / BlockErrorLimit() for the last Compare. */
