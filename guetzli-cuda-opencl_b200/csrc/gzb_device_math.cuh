@@ -313,33 +313,22 @@ __device__ __forceinline__ void warp_block_diff(const float* __restrict__ fa,
   }
   __syncwarp();
   // (4) column transforms: 20 tasks = plane*5 + u; power into pl[plane*72 + 8u + v].
+  // Columns u = 0 and u = 4 of a real input are themselves real (their stored imaginary parts are
+  // exactly 0.0); running them through the complex transform gives the same bits as the reference's
+  // real transform up to the sign of zeros (x - 0 = x, 0 - x = -x, (-x - y) = -(x + y) are exact), and
+  // only re^2 + im^2 is used. One code path for all 20 lanes instead of two divergent ones. Bins the
+  // reference does not compute (u = 0: v < 4; u = 4: v > 4) land in slots nobody reads.
   if (lane < 20) {
     const int plane = lane / 5, u = lane - 5 * plane;
     const double* cre = sre + plane * kBdSpec + 9 * u;
     const double* cim = sim + plane * kBdSpec + 9 * u;
     double* dst = pl + kBdPlane * plane + 8 * u;
-    if (u == 0 || u == 4) {
-      double x[8], re[5], im[5];
+    double re[8], im[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x[k] = cre[k];
-      rfft8_half(x, re, im);
-      if (u == 0) {  // needs v = 4..7 : |F4|, |F5|=|F3|, |F6|=|F2|, |F7|=|F1|
-        dst[4] = (re[4] * re[4] + im[4] * im[4]) * 0.000064;
-        dst[5] = (re[3] * re[3] + im[3] * im[3]) * 0.000064;
-        dst[6] = (re[2] * re[2] + im[2] * im[2]) * 0.000064;
-        dst[7] = (re[1] * re[1] + im[1] * im[1]) * 0.000064;
-      } else {  // v = 0..4
+    for (int k = 0; k < 8; ++k) { re[k] = cre[k]; im[k] = cim[k]; }
+    cfft8(re, im);
 #pragma unroll
-        for (int v = 0; v < 5; ++v) dst[v] = (re[v] * re[v] + im[v] * im[v]) * 0.000064;
-      }
-    } else {
-      double re[8], im[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { re[k] = cre[k]; im[k] = cim[k]; }
-      cfft8(re, im);
-#pragma unroll
-      for (int v = 0; v < 8; ++v) dst[v] = (re[v] * re[v] + im[v] * im[v]) * 0.000064;
-    }
+    for (int v = 0; v < 8; ++v) dst[v] = (re[v] * re[v] + im[v] * im[v]) * 0.000064;
   }
   __syncwarp();
   // (5) per-frequency terms i = 4..36 (lane L -> i = 4+L; lane 0 also i = 36), then in-order sums.

@@ -632,59 +632,73 @@ WorkerPool::WorkerPool(int nthreads) : nthreads_(std::max(1, nthreads)) {
 WorkerPool::~WorkerPool() {
   {
     std::lock_guard<std::mutex> l(mu_);
-    stop_ = true;
+    stop_.store(true);
   }
   cv_start_.notify_all();
   for (auto& t : threads_) t.join();
 }
+
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#endif
+}
+
+// Protocol: run() publishes a Job (on its stack), bumps the epoch, works, waits for pending == 0,
+// clears job_ and then waits until no worker is still inside a job section (active_ == 0). A worker
+// raises active_ BEFORE it reads job_, so it either sees nullptr or keeps run() from returning while
+// it holds the pointer.
 void WorkerPool::worker() {
   unsigned long long seen = 0;
+  const int kSpin = 4000;   // ~20-50 us of polling before sleeping
   for (;;) {
-    const std::function<void(int)>* fn;
-    {
+    int spins = 0;
+    while (epoch_.load(std::memory_order_acquire) == seen && !stop_.load(std::memory_order_relaxed)) {
+      if (++spins < kSpin) { cpu_relax(); continue; }
       std::unique_lock<std::mutex> l(mu_);
-      cv_start_.wait(l, [&] { return stop_ || epoch_ != seen; });
-      if (stop_) return;
-      seen = epoch_;
-      fn = fn_;
+      sleepers_.fetch_add(1);
+      cv_start_.wait(l, [&] { return stop_.load() || epoch_.load() != seen; });
+      sleepers_.fetch_sub(1);
     }
-    for (;;) {
-      int i;
-      {
-        std::lock_guard<std::mutex> l(mu_);
-        if (epoch_ != seen || next_ >= n_) break;
-        i = next_++;
-      }
-      (*fn)(i);
-      {
-        std::lock_guard<std::mutex> l(mu_);
-        if (--pending_ == 0) cv_done_.notify_all();
+    if (stop_.load()) return;
+    seen = epoch_.load(std::memory_order_acquire);
+    active_.fetch_add(1);
+    Job* j = job_.load();
+    if (j) {
+      for (;;) {
+        const int i = j->next.fetch_add(1);
+        if (i >= j->n) break;
+        (*j->fn)(i);
+        j->pending.fetch_sub(1);
       }
     }
+    active_.fetch_sub(1);
   }
 }
+
 void WorkerPool::run(int n, const std::function<void(int)>& fn) {
   if (n <= 0) return;
   if (nthreads_ == 1 || n == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
-  {
-    std::lock_guard<std::mutex> l(mu_);
-    fn_ = &fn; n_ = n; next_ = 0; pending_ = n; ++epoch_;
+  Job job;
+  job.fn = &fn;
+  job.n = n;
+  job.pending.store(n);
+  job_.store(&job);
+  epoch_.fetch_add(1, std::memory_order_release);
+  if (sleepers_.load() > 0) {
+    std::lock_guard<std::mutex> l(mu_);   // a sleeper checks the epoch under this mutex
+    cv_start_.notify_all();
   }
-  cv_start_.notify_all();
   for (;;) {  // the caller works too
-    int i;
-    {
-      std::lock_guard<std::mutex> l(mu_);
-      if (next_ >= n_) break;
-      i = next_++;
-    }
+    const int i = job.next.fetch_add(1);
+    if (i >= n) break;
     fn(i);
-    std::lock_guard<std::mutex> l(mu_);
-    if (--pending_ == 0) cv_done_.notify_all();
+    job.pending.fetch_sub(1);
   }
-  std::unique_lock<std::mutex> l(mu_);
-  cv_done_.wait(l, [&] { return pending_ == 0; });
-  n_ = 0;
+  int spins = 0;
+  while (job.pending.load(std::memory_order_acquire) != 0) { if (++spins < 64) cpu_relax(); else std::this_thread::yield(); }
+  job_.store(nullptr);
+  while (active_.load() != 0) cpu_relax();
 }
 
 }  // namespace gzb

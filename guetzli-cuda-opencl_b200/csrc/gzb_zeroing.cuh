@@ -29,7 +29,6 @@ struct ZeroWarpSmem {
   float bufA[192];   // linear rgb -> fa (original after MaskHighIntensityChange)
   float bufB[192];   // H-pass -> fb (candidate after MaskHighIntensityChange)
   float key[192];
-  int basis[64];
   short cf[192];     // processed coefficients
   short colv[192];   // column-pass values of the processed state
   short ccol[8];     // candidate's replacement column
@@ -80,7 +79,7 @@ __device__ __forceinline__ void warp_block_opsin(const float* lin, float* hb, fl
 
 // CompareBlock on the state in `s`: candidate = processed with coefficient `zidx` zeroed
 // (zidx < 0: the processed block itself). Returns the error in all lanes.
-__device__ __forceinline__ float warp_compare_block(ZeroWarpSmem& s, const float* lut, int zidx,
+__device__ __forceinline__ float warp_compare_block(ZeroWarpSmem& s, const int* s_basis, const float* lut, int zidx,
                                                     int vx, int vy, const float scale[3],
                                                     double csf_a, double csf_b, int lane) {
   const int zc = zidx >= 0 ? zidx >> 6 : -1;
@@ -92,7 +91,7 @@ __device__ __forceinline__ float warp_compare_block(ZeroWarpSmem& s, const float
 #pragma unroll
       for (int v = 0; v < 8; ++v) {
         const int cv = v == ky ? 0 : s.cf[64 * zc + 8 * v + kx];
-        acc += s.basis[8 * lane + v] * cv;
+        acc += s_basis[8 * lane + v] * cv;
       }
       s.ccol[lane] = static_cast<short>(idct_col_round(acc));
     }
@@ -104,7 +103,7 @@ __device__ __forceinline__ float warp_compare_block(ZeroWarpSmem& s, const float
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int cv = u == kx ? s.ccol[y] : s.colv[64 * zc + 8 * y + u];
-        acc += s.basis[8 * x + u] * cv;
+        acc += s_basis[8 * x + u] * cv;
       }
       s.cpx[p] = static_cast<unsigned char>(idct_row_round(acc));
     }
@@ -159,13 +158,13 @@ __device__ __forceinline__ float warp_compare_block(ZeroWarpSmem& s, const float
 }
 
 // Rebuilds colv / pix of component c from s.cf (full IDCT, warp-cooperative).
-__device__ __forceinline__ void warp_full_idct(ZeroWarpSmem& s, int c, int lane) {
+__device__ __forceinline__ void warp_full_idct(ZeroWarpSmem& s, const int* s_basis, int c, int lane) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int p = lane + 32 * h, x = p & 7, y = p >> 3;
     int acc = 0;
 #pragma unroll
-    for (int v = 0; v < 8; ++v) acc += s.basis[8 * y + v] * s.cf[64 * c + 8 * v + x];
+    for (int v = 0; v < 8; ++v) acc += s_basis[8 * y + v] * s.cf[64 * c + 8 * v + x];
     s.colv[64 * c + p] = static_cast<short>(idct_col_round(acc));
   }
   __syncwarp();
@@ -174,7 +173,7 @@ __device__ __forceinline__ void warp_full_idct(ZeroWarpSmem& s, int c, int lane)
     const int p = lane + 32 * h, x = p & 7, y = p >> 3;
     int acc = 0;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc += s.basis[8 * x + u] * s.colv[64 * c + 8 * y + u];
+    for (int u = 0; u < 8; ++u) acc += s_basis[8 * x + u] * s.colv[64 * c + 8 * y + u];
     s.pix[64 * c + p] = static_cast<unsigned char>(idct_row_round(acc));
   }
   __syncwarp();
@@ -187,7 +186,7 @@ constexpr int kZeroWarps = 4;
 // mode 2: CompareBlock of ONE block `single_block` whose candidate coefficients are the 192 values
 //         at `cur` (comp_stride 64, nblocks 1) -> err_out[0] (Comparator::CompareBlock adaptor)
 // Blocks [block_begin, nblocks) are processed (a group of GPUs splits the image by block range).
-__global__ void __launch_bounds__(32 * kZeroWarps)
+__global__ void __launch_bounds__(32 * kZeroWarps, 5)
 k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cur,
                 size_t comp_stride, const uint8_t* __restrict__ rgb_planes, size_t plane_stride,
                 int P, int W, int H, int bw, int nblocks, const float* __restrict__ mask_scale,
@@ -195,15 +194,13 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
                 CoeffDataDev* __restrict__ out, float* __restrict__ err_out,
                 float* __restrict__ pregamma_out, unsigned int* __restrict__ counter) {
   __shared__ ZeroWarpSmem sm[kZeroWarps];
-  __shared__ float s_lut[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = g_tab.srgb_lin[i];
+  __shared__ int s_basis[64];
+  const float* s_lut = g_tab.srgb_lin;   // 1 KB, L1-resident; shared memory is the occupancy limiter
+  if (threadIdx.x < 64) s_basis[threadIdx.x] = kIdctBasis[threadIdx.x];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ZeroWarpSmem& s = sm[warp];
   const double csf_a = kCsf8x8[4 + lane], csf_b = kCsf8x8[36];
-  s.basis[lane] = kIdctBasis[lane];
-  s.basis[32 + lane] = kIdctBasis[32 + lane];
-  __syncwarp();
   for (;;) {
     unsigned int b = 0;
     if (lane == 0) b = atomicAdd(counter, 1u);
@@ -234,10 +231,10 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
       for (int k = 0; k < 6; ++k) pregamma_out[static_cast<size_t>(b) * 192 + lane + 32 * k] = s.pg0[lane + 32 * k];
     }
 #pragma unroll 1
-    for (int c = 0; c < 3; ++c) warp_full_idct(s, c, lane);
+    for (int c = 0; c < 3; ++c) warp_full_idct(s, s_basis, c, lane);
     const float scale[3] = {mask_scale[3 * blk], mask_scale[3 * blk + 1], mask_scale[3 * blk + 2]};
     if (mode >= 1) {
-      const float e = warp_compare_block(s, s_lut, -1, vx, vy, scale, csf_a, csf_b, lane);
+      const float e = warp_compare_block(s, s_basis, s_lut, -1, vx, vy, scale, csf_a, csf_b, lane);
       if (lane == 0) err_out[b] = e;
       continue;
     }
@@ -276,7 +273,7 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
       float best_err = 1e17f;
       int best_i = 0;
       for (int i = 0; i < nwin; ++i) {
-        const float err = warp_compare_block(s, s_lut, win[i], vx, vy, scale, csf_a, csf_b, lane);
+        const float err = warp_compare_block(s, s_basis, s_lut, win[i], vx, vy, scale, csf_a, csf_b, lane);
         const float max_err = fmaxf(0.0f, err);
         if (max_err < best_err) { best_err = max_err; best_i = i; }
       }
@@ -289,7 +286,7 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
         if (lane < 8) {
           int acc = 0;
 #pragma unroll
-          for (int v = 0; v < 8; ++v) acc += s.basis[8 * lane + v] * s.cf[64 * c + 8 * v + kx];
+          for (int v = 0; v < 8; ++v) acc += s_basis[8 * lane + v] * s.cf[64 * c + 8 * v + kx];
           s.colv[64 * c + 8 * lane + kx] = static_cast<short>(idct_col_round(acc));
         }
         __syncwarp();
@@ -298,7 +295,7 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
           const int p = lane + 32 * h, x = p & 7, y = p >> 3;
           int acc = 0;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) acc += s.basis[8 * x + u] * s.colv[64 * c + 8 * y + u];
+          for (int u = 0; u < 8; ++u) acc += s_basis[8 * x + u] * s.colv[64 * c + 8 * y + u];
           s.pix[64 * c + p] = static_cast<unsigned char>(idct_row_round(acc));
         }
         __syncwarp();
