@@ -915,7 +915,8 @@ int gzb_compute_block_zeroing_candidates(gzb_ctx* c, int comp_mask, int* offsets
 namespace {
 struct HuffScratch {
   unsigned int* unit_bits;
-  unsigned long long* unit_off;
+  unsigned int* cta_bits;
+  unsigned long long* cta_off;
   unsigned int* hist;            // [3][16] dc | [3][256] ac
   unsigned long long* out2;
   HuffDeviceTables* tables;
@@ -929,7 +930,9 @@ HuffScratch huff_scratch(gzb_ctx* c) {
   const size_t nunits = 3 * static_cast<size_t>(c->nblocks);
   size_t o = 0;
   auto take = [&](size_t bytes) { uint8_t* p = base + o; o += (bytes + 255) & ~size_t(255); return p; };
-  h.unit_off = reinterpret_cast<unsigned long long*>(take((nunits + 1) * 8));
+  const size_t nctas = (nunits + kHuffThreads - 1) / kHuffThreads;
+  h.cta_off = reinterpret_cast<unsigned long long*>(take((nctas + 1) * 8));
+  h.cta_bits = reinterpret_cast<unsigned int*>(take(nctas * 4));
   h.unit_bits = reinterpret_cast<unsigned int*>(take(nunits * 4));
   h.hist = reinterpret_cast<unsigned int*>(take((48 + 768) * 4));
   h.out2 = reinterpret_cast<unsigned long long*>(take(16));
@@ -975,10 +978,10 @@ int gzb_candidate_entropy_code(gzb_ctx* c, int ncomp, const uint16_t* dc_code, c
   const unsigned grid = static_cast<unsigned>((nunits + kHuffThreads - 1) / kHuffThreads);
   const size_t cs = static_cast<size_t>(c->nblocks) * 64;
   KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_code<false><<<grid, kHuffThreads, 0, c->stream2>>>(c->d_coef, cs, c->d_q, ncomp, nunits, h.tables,
-                                                                                  h.unit_bits, nullptr, nullptr));
-  KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_scan_u64<<<1, 1024, 0, c->stream2>>>(h.unit_bits, nunits, h.unit_off));
+                                                                                  h.unit_bits, h.cta_bits, nullptr, nullptr));
+  KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_scan_u64<<<1, 1024, 0, c->stream2>>>(h.cta_bits, static_cast<long long>(grid), h.cta_off));
   unsigned long long* hp = reinterpret_cast<unsigned long long*>(c->h_pinned) + 32;  // bytes 256..
-  CK(cudaMemcpyAsync(hp, h.unit_off + nunits, 8, cudaMemcpyDeviceToHost, c->stream2)); c->d2h_bytes += 8;
+  CK(cudaMemcpyAsync(hp, h.cta_off + grid, 8, cudaMemcpyDeviceToHost, c->stream2)); c->d2h_bytes += 8;
   sync_check2(c);
   const unsigned long long total_bits = hp[0];
   const size_t nbytes = static_cast<size_t>((total_bits + 7) / 8);
@@ -986,9 +989,9 @@ int gzb_candidate_entropy_code(gzb_ctx* c, int ncomp, const uint16_t* dc_code, c
   CK(cudaMemsetAsync(h.words, 0, (nbytes + 7) & ~size_t(3), c->stream2));
   CK(cudaMemsetAsync(h.out2, 0, 16, c->stream2));
   KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_code<true><<<grid, kHuffThreads, 0, c->stream2>>>(c->d_coef, cs, c->d_q, ncomp, nunits, h.tables,
-                                                                                 nullptr, h.unit_off, h.words));
+                                                                                 h.unit_bits, nullptr, h.cta_off, h.words));
   const unsigned fgrid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(static_cast<size_t>(c->sm_count) * 8, (nbytes + 4095) / 4096)));
-  KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_finish<<<fgrid, 256, 0, c->stream2>>>(reinterpret_cast<unsigned char*>(h.words), h.unit_off + nunits, h.out2));
+  KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_finish<<<fgrid, 256, 0, c->stream2>>>(reinterpret_cast<unsigned char*>(h.words), h.cta_off + grid, h.out2));
   CK(cudaMemcpyAsync(hp, h.out2, 16, cudaMemcpyDeviceToHost, c->stream2)); c->d2h_bytes += 16;
   sync_check2(c);
   *scan_bytes = hp[0];

@@ -7,10 +7,11 @@
 // is coded there:
 //   k_huff_histogram : DC/AC symbol histograms per component (BuildDCHistograms /
 //                      BuildACHistograms, jpeg_data_writer.cc:189-247) -> host builds the codes
-//   k_huff_unit_bits : bits of every (block, component) unit under those codes
-//   k_scan_u64       : exclusive scan -> each unit's bit offset in the scan
-//   k_huff_emit      : every unit writes its code words at its offset (EncodeScan/EncodeDCTBlock-
-//                      Sequential, jpeg_data_writer.cc:249-359), MSB first, big-endian bytes
+//   k_huff_code<false> : bits of every (block, component) unit under those codes, summed per CTA
+//   k_scan_u64         : exclusive scan of the CTA totals (a few hundred to a few thousand values)
+//   k_huff_code<true>  : CTA-local scan of the unit bits + the CTA's offset = each unit's bit position;
+//                        every unit writes its code words there (EncodeScan/EncodeDCTBlockSequential,
+//                        jpeg_data_writer.cc:249-359), MSB first, big-endian bytes
 //   k_huff_finish    : pads the last byte with ones (JumpToByteBoundary) and counts 0xff bytes
 // The file size is header + bytes + (#0xff, one stuffing byte each) + 2 (EOI); the bytes themselves
 // are copied to the host only for a candidate that becomes the best so far.
@@ -137,7 +138,9 @@ template <bool EMIT>
 __global__ void __launch_bounds__(kHuffThreads)
 k_huff_code(const int16_t* __restrict__ coef, size_t comp_stride, const int* __restrict__ q192, int ncomp,
             long long nunits, const HuffDeviceTables* __restrict__ tab, unsigned int* __restrict__ unit_bits,
-            const unsigned long long* __restrict__ unit_off, unsigned int* __restrict__ words) {
+            unsigned int* __restrict__ cta_bits, const unsigned long long* __restrict__ cta_off,
+            unsigned int* __restrict__ words) {
+  __shared__ unsigned int s_warp[kHuffThreads / 32];
   __shared__ int16_t s_rows[kHuffThreads * kHuffRow];
   __shared__ int s_q[192];
   __shared__ HuffDeviceTables s_tab;
@@ -152,12 +155,26 @@ k_huff_code(const int16_t* __restrict__ coef, size_t comp_stride, const int* __r
   huff_stage_rows(coef, comp_stride, s_q, ncomp, u0, nunits, s_rows);
   __syncthreads();
   const long long u = u0 + threadIdx.x;
-  if (u >= nunits) return;
-  const long long b = u / ncomp;
-  const int c = static_cast<int>(u - b * ncomp);
+  const bool live = u < nunits;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long start = 0;
+  if (EMIT) {  // exclusive scan of this CTA's unit bits
+    const unsigned int mine = live ? unit_bits[u] : 0u;
+    unsigned int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned int base = 0;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    start = cta_off[blockIdx.x] + base + (incl - mine);
+  }
+  const long long b = live ? u / ncomp : 0;
+  const int c = live ? static_cast<int>(u - b * ncomp) : 0;
   const int16_t* row = s_rows + threadIdx.x * kHuffRow;
   HuffSink<EMIT> sink;
-  sink.init(words, EMIT ? unit_off[u] : 0ull);
+  sink.init(words, start);
+  if (live) {
   {  // DC: coeff_t arithmetic as in the writer (jpeg_data_writer.cc:262-276)
     const int diff = static_cast<int16_t>(row[0] - huff_prev_dc(coef, comp_stride, s_q, b, c));
     int mag = diff, low = diff;
@@ -182,8 +199,22 @@ k_huff_code(const int16_t* __restrict__ coef, size_t comp_stride, const int* __r
     run = 0;
   }
   if (run > 0) sink.put(s_tab.ac_len[c][0], s_tab.ac_code[c][0]);
-  if (EMIT) sink.flush();
-  else unit_bits[u] = sink.count;
+  }
+  if (EMIT) {
+    if (live) sink.flush();
+  } else {
+    if (live) unit_bits[u] = sink.count;
+    unsigned int sum = live ? sink.count : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_warp[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int t = 0;
+      for (int w = 0; w < kHuffThreads / 32; ++w) t += s_warp[w];
+      cta_bits[blockIdx.x] = t;
+    }
+  }
 }
 
 // Single-CTA exclusive scan of n 32-bit counts into 64-bit offsets[0..n].
