@@ -197,7 +197,9 @@ class LazySort {
   void ensure_set(size_t p) {
     p = std::min(p, n_);
     if (p <= sorted_) return;
-    const size_t kPiece = size_t(1) << 14;
+    // split the straddling range all the way down to introsort's own threshold: everything to the
+    // right of p is then finished lazily, only as far as the walk gets
+    const size_t kPiece = 16;
     auto comp = __gnu_cxx::__ops::__iter_comp_iter(OrderLess());
     size_t done = p;
     while (!pending_.empty() && pending_.back().first < p) {
