@@ -344,8 +344,12 @@ void histogram_from_counts(const uint32_t* counts, int n, Histogram* h) {
 // SaveToJpegData drops chroma planes that are entirely zero (output_image.cc:588): every block then
 // codes a zero DC difference and a lone end-of-block.
 int ncomp_from_histograms(const Histogram* dc, const Histogram* ac, int nblocks) {
+  (void)nblocks;
+  // a chroma histogram may also be empty: the back end counts only the components SaveToJpegData
+  // keeps at its start (processor.cc:744-750), like the reference
   for (int c = 1; c < 3; ++c)
-    if (dc[c].counts[0] != 2u * nblocks || ac[c].counts[0] != 2u * nblocks) return 3;
+    for (int i = 1; i + 1 < Histogram::kSize; ++i)
+      if (dc[c].counts[i] != 0 || ac[c].counts[i] != 0) return 3;
   return 1;
 }
 
@@ -1008,6 +1012,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         ++e.st.num_iterations;
       }
       e.log(" BA[100.00%%] D[%6.4f]", o.distance);
+      e.distance = o.distance;   // the comparator's state after this trial, wherever it ran
       e.maybe_output_trial(t, o);
     };
     if (!search.run(evaluate, visit)) {
@@ -1133,11 +1138,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       for (int c = 0; c < 3; ++c) f.coeffs[c] = e.idx[c].data();
       gzb::jpeg::frame_set_quant(&f, e.quant);
       header_size = static_cast<int>(gzb::jpeg::header_size(f));
-      {  // all three components: the device writer decides from them whether chroma is dropped
-        Frame f3 = f;
-        f3.ncomp = 3;
-        gzb::jpeg::build_histograms(f3, dc_hist, ac_hist, e.pool.get());
-      }
+      gzb::jpeg::build_histograms(f, dc_hist, ac_hist, e.pool.get());   // the components SaveToJpegData keeps
       {  // EstimateDCSize (processor.cc:548-555)
         Histogram tmp[3] = {dc_hist[0], dc_hist[1], dc_hist[2]};
         size_t num = f.ncomp;
@@ -1286,7 +1287,9 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
 
         LazySort sorter(global_order.data(), global_order.size(), e.pool.get());
         double rel_size_delta = direction > 0 ? 0.01 : 0.0005;
-        if (direction > 0 && gzb_distance_ok(e.ctx, 1.0)) rel_size_delta = 0.05;
+        // DistanceOK(1.0) of the LAST Compare in the reference's order (in a group that may be a trial
+        // another rank evaluated, so the context's own last distance must not be used)
+        if (direction > 0 && static_cast<double>(e.distance) <= 1.0 * static_cast<double>(e.target)) rel_size_delta = 0.05;
         const double min_size_delta = base_size * rel_size_delta;
         const float coeffs_to_change_per_block = direction > 0 ? 2.0f : 1 * 1 * 0.2f;
         int min_coeffs_to_change = static_cast<int>(coeffs_to_change_per_block * blocks_to_change);

@@ -215,3 +215,37 @@ def bees():
     from PIL import Image
     path = os.path.join(ROOT, "tests", "golden", "bees.png")
     return np.ascontiguousarray(np.asarray(Image.open(path).convert("RGB")))
+
+
+SPECIAL_IMAGES = ["gray_80x64_q90", "min_32x32_q95", "odd_40x33_q100", "flat_64x64_q90", "noise_64x48_q84",
+                  "edges_120x72_q92", "graynoise_48x40_q88"]
+
+
+def special_image(name):
+    """Edge-case inputs of the encoder tests: grey-only (chroma planes quantise to nothing and are
+    dropped from the file), the smallest size the search accepts, sizes that are no multiple of 8, a
+    flat image (no AC energy), white noise (no quant matrix passes), hard edges."""
+    kind, size, q = name.split("_")
+    w, h = (int(v) for v in size.split("x"))
+    quality = int(q[1:])
+    rng = np.random.Generator(np.random.PCG64(77))
+    if kind in ("gray", "graynoise"):
+        g = synth_image(w, h, 4321)[:, :, 0]
+        if kind == "graynoise":
+            g = rng.integers(0, 256, (h, w)).astype(np.uint8)
+        img = np.stack([g, g, g], axis=2)
+    elif kind in ("min", "odd"):
+        img = synth_image(w, h, 999)
+    elif kind == "flat":
+        img = np.full((h, w, 3), 128, np.uint8)
+    elif kind == "noise":
+        img = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+    elif kind == "edges":
+        img = np.zeros((h, w, 3), np.uint8)
+        img[:, w // 3:, 0] = 255
+        img[h // 2:, :, 1] = 200
+        img[::7, :, 2] = 90
+        img[:, ::11, :] //= 2
+    else:
+        raise ValueError(name)
+    return np.ascontiguousarray(img), quality

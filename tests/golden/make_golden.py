@@ -20,6 +20,21 @@ def iter_lines(trace):
     return [l for l in trace.splitlines() if "Out[" in l]
 
 
+def edge_cases():
+    """edge_encodes.json: the reference's bytes and traces on the special images of tests/_libs.py."""
+    from _libs import SPECIAL_IMAGES, special_image
+    L = ref()
+    enc = {}
+    for name in SPECIAL_IMAGES:
+        im, q = special_image(name)
+        t = L.ref_butteraugli_score_for_quality(float(q))
+        jpg, iters, trace = ref_process(im, t, want_trace=True)
+        enc[name] = {"sha256": hashlib.sha256(jpg).hexdigest(), "size": len(jpg), "iterations": iters, "target": t,
+                     "trace": iter_lines(trace)}
+        print(name, len(jpg), iters)
+    json.dump(enc, open(os.path.join(HERE, "edge_encodes.json"), "w"), indent=1)
+
+
 def main():
     L = ref()
     out = {}
@@ -38,6 +53,7 @@ def main():
         enc["%dx%d_q%d_s%d" % (w, h, q, seed)] = {"sha256": hashlib.sha256(jpg).hexdigest(), "size": len(jpg),
                                                    "iterations": iters, "target": t, "trace": iter_lines(trace)}
     json.dump(enc, open(os.path.join(HERE, "synth_encodes.json"), "w"), indent=1)
+    edge_cases()
     w, h, target = 96, 64, 0.971769
     im = synth_image(w, h)
     s = RefSession(im, target)
@@ -51,4 +67,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--edge":
+        edge_cases()
+    else:
+        main()

@@ -212,3 +212,30 @@ def test_device_huffman_writer_bytes_equal_host_writer(gz, w, h, q, seed):
         want_in = gz.WriteJpeg(cur, w, h, qm, input_tables=True, host_threads=1)
         assert c.WriteJpeg(qm, input_tables=True)[1] == want_in
     c.close()
+
+
+from _libs import SPECIAL_IMAGES, special_image
+
+
+@pytest.mark.parametrize("name", SPECIAL_IMAGES)
+def test_edge_case_encodes_equal_reference(gz, name):
+    """Grey-only input (chroma dropped from the file), 32x32, sizes off the 8x8 grid, a flat image,
+    white noise, hard edges: bytes and iteration trace of the reference (tests/golden/edge_encodes.json)."""
+    gold = json.load(open(os.path.join(GOLD, "edge_encodes.json")))[name]
+    img, q = special_image(name)
+    assert abs(gz.ButteraugliScoreForQuality(q) - gold["target"]) < 1e-12
+    check(gz, img, gold)
+
+
+@pytest.mark.parametrize("name", SPECIAL_IMAGES)
+@pytest.mark.parametrize("world", [2, 5])
+def test_group_encode_edge_cases(gz, name, world):
+    """The group path on the edge-case inputs. (The grey image once exposed that DistanceOK(1.0) of
+    the first back-end iteration must see the last trial in the REFERENCE's order, which another
+    rank may have evaluated.)"""
+    gold = json.load(open(os.path.join(GOLD, "edge_encodes.json")))[name]
+    img, _ = special_image(name)
+    res = run_thread_group(gz, img, np.float32(gold["target"]), world)
+    assert hashlib.sha256(res[0][0]).hexdigest() == gold["sha256"]
+    got = trace_records([l for l in res[0][2].splitlines() if "Out[" in l])
+    assert got == trace_records(gold["trace"])
