@@ -386,9 +386,23 @@ void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
   float* m0 = c->d_mh;
   float* m1 = c->d_mh + 3 * c->ps;
   KLAUNCH(c, KC_MHIC, k_mask_high_intensity_change<<<gpx, blk, 0, c->stream>>>(xyb0, xyb1, c->ps, W, H, P, m0, m1));
-  // EdgeDetectorMap
-  for (int k = 0; k < 3; ++k)
-    run_blur(c, c->p_ed[k], c->d_mh + k * c->ps, 3 * c->ps, 2, c->d_bl + k * c->ps, 3 * c->ps, P);
+  // EdgeDetectorMap: the six small-sigma blurs (3 channels x 2 images) in one fused H+V launch
+  {
+    SmallBlur3 sb;
+    bool fused = true;
+    for (int k = 0; k < 3; ++k) {
+      const BlurGeom& g = c->p_ed[k].g;
+      sb.r[k] = g.r; sb.kind[k] = g.kind; sb.sx[k] = c->p_ed[k].d_sx; sb.sy[k] = c->p_ed[k].d_sy;
+      fused = fused && g.r <= kSbR && g.sx == 1 && g.sy == 1 && g.x0 == 0 && g.y0 == 0 && g.ups == 1;
+    }
+    if (fused) {
+      dim3 gsb((W + kSbT - 1) / kSbT, (H + kSbT - 1) / kSbT, 6);
+      KLAUNCH(c, KC_BLUR_H, k_blur_small_hv<<<gsb, blk, 0, c->stream>>>(c->d_mh, c->d_bl, c->ps, W, H, P, sb));
+    } else {
+      for (int k = 0; k < 3; ++k)
+        run_blur(c, c->p_ed[k], c->d_mh + k * c->ps, 3 * c->ps, 2, c->d_bl + k * c->ps, 3 * c->ps, P);
+    }
+  }
   dim3 gres((c->rxs + 31) / 32, (c->rys + 7) / 8);
   KLAUNCH(c, KC_EDGE_MAP, k_edge_detector_map<<<gres, blk, 0, c->stream>>>(c->d_bl, c->d_bl + 3 * c->ps, c->ps, W, H, P, c->rxs, c->d_edm));
   // BlockDiffMap
@@ -398,6 +412,7 @@ void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
   const int cells = ncx * ncy;
   const int ctas = std::min((cells + kBdmWarps - 1) / kBdmWarps, c->sm_count * 16);
   KLAUNCH(c, KC_BLOCK_DIFF, k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, c->stream>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac));
+  KLAUNCH(c, KC_BLOCK_DIFF, k_block_dc<<<(cells + 127) / 128, 128, 0, c->stream>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc));
   // EdgeDetectorLowFreq
   run_blur(c, c->p_lf, c->d_mh, c->ps, 6, c->d_lf, c->lf_stride, c->p_lf.g.tmp_pitch);
   KLAUNCH(c, KC_LOWFREQ, k_edge_lowfreq<<<gres, blk, 0, c->stream>>>(c->d_lf, c->d_lf + 3 * c->lf_stride, c->lf_stride, c->p_lf.g.tmp_pitch,

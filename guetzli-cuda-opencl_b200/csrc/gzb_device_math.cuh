@@ -226,6 +226,9 @@ __device__ __forceinline__ double remove_range_around_zero(double v, double rang
 //   ws     : per-warp scratch of kBlockDiffScratchDoubles doubles in shared memory
 //   csf_a / csf_b : kCsf8x8[4 + lane] and kCsf8x8[36] (hoisted by the caller: loop invariant)
 // Returns dc[3], ac[3], edge[3] in ALL lanes. Sequential sums keep the reference's order.
+// kWithDcEdge = false skips the mean / edge-mean part (dc and edge are then not written): the
+// full-image BlockDiffMap computes its DC term in a lane-per-cell kernel (k_block_dc) where the 64
+// strictly ordered additions cost one instruction stream per 32 cells instead of per cell.
 // All 32 lanes must call. Ends with __syncwarp(); fa/fb are not modified.
 //
 // Shared-memory layout (doubles), padded so that the 64-bit accesses of a half-warp fall into
@@ -235,6 +238,7 @@ __device__ __forceinline__ double remove_range_around_zero(double v, double rang
 constexpr int kBdPlane = 72, kBdSpec = 56;
 constexpr int kBlockDiffScratchDoubles = 4 * kBdPlane + 2 * 4 * kBdSpec;  // 736
 
+template <bool kWithDcEdge = true>
 __device__ __forceinline__ void warp_block_diff(const float* __restrict__ fa,
                                                 const float* __restrict__ fb, double* ws,
                                                 double csf_a, double csf_b, double dc[3],
@@ -256,6 +260,7 @@ __device__ __forceinline__ void warp_block_diff(const float* __restrict__ fa,
     pl[3 * kBdPlane + o] = (a2 - b2) / 2;
   }
   __syncwarp();
+  if (kWithDcEdge) {
   // (2) means and edge means: 15 independent in-order accumulations. The reference adds
   // diff/64 (diff/8 for edges) term by term; half-differences are diff/2 exactly and scaling by a
   // power of two commutes with rounding, so sum(diff/64) == sum(halfdiff)/32 bit for bit.
@@ -297,6 +302,7 @@ __device__ __forceinline__ void warp_block_diff(const float* __restrict__ fa,
 #pragma unroll
     for (int e = 1; e <= 4; ++e) ed += __shfl_sync(0xffffffffu, sq[c], e);
     edge[c] = ed;
+  }
   }
   // (3) row transforms: lane = plane*8 + row.
   {

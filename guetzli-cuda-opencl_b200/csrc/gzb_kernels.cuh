@@ -386,6 +386,68 @@ k_blur_v(const float* __restrict__ tmp, size_t tmp_stride, BlurGeom g,
 }
 
 // ---------------------------------------------------------------------------------------------
+// K4b: both passes of a small-radius (r <= 3, step 1) blur fused, for the six planes EdgeDetectorMap
+// blurs (three channels with their own sigma, two images; butteraugli.cc:1124-1133): one launch
+// instead of six. 32x32 output tile per CTA, halo r; the H-pass result of the (32 + 2r) tile rows
+// stays in shared memory as float, exactly what the two-kernel path stores between its passes.
+// blockIdx.z = image * 3 + channel.
+// ---------------------------------------------------------------------------------------------
+struct SmallBlur3 {
+  int r[3], kind[3];
+  const double* sx[3];
+  const double* sy[3];
+};
+constexpr int kSbT = 32, kSbR = 3;
+__global__ void __launch_bounds__(256)
+k_blur_small_hv(const float* __restrict__ in, float* __restrict__ out, size_t plane_stride, int W, int H, int P,
+                SmallBlur3 sb) {
+  __shared__ float s_in[kSbT + 2 * kSbR][kSbT + 2 * kSbR + 1];
+  __shared__ float s_h[kSbT + 2 * kSbR][kSbT + 1];
+  const int ch = blockIdx.z % 3;
+  const int r = sb.r[ch];
+  const float* taps = c_taps[sb.kind[ch]];
+  const double* __restrict__ scale_x = sb.sx[ch];
+  const double* __restrict__ scale_y = sb.sy[ch];
+  in += blockIdx.z * plane_stride;
+  out += blockIdx.z * plane_stride;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int x0 = blockIdx.x * kSbT, y0 = blockIdx.y * kSbT;
+  const int span = kSbT + 2 * r;
+  for (int i = tid; i < span * span; i += 256) {
+    const int ly = i / span, lx = i - ly * span;
+    const int gx = x0 + lx - r, gy = y0 + ly - r;
+    float v = 0.0f;
+    if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = in[static_cast<size_t>(gy) * P + gx];
+    s_in[ly][lx] = v;
+  }
+  __syncthreads();
+  const int nt = 2 * r + 1;
+  for (int i = tid; i < span * kSbT; i += 256) {
+    const int ly = i >> 5, lx = i & 31;
+    const int gx = x0 + lx, gy = y0 + ly - r;
+    float v = 0.0f;
+    if (gx < W && gy >= 0 && gy < H) {
+      const float* p = &s_in[ly][lx];
+      double acc = 0.0;
+      for (int k = 0; k < nt; ++k) acc += static_cast<double>(p[k] * taps[k]);
+      v = static_cast<float>(acc * scale_x[gx]);
+    }
+    s_h[ly][lx] = v;
+  }
+  __syncthreads();
+  const int gx = x0 + threadIdx.x;
+  if (gx >= W) return;
+#pragma unroll
+  for (int rr = 0; rr < kSbT; rr += 8) {
+    const int ly = threadIdx.y + rr, gy = y0 + ly;
+    if (gy >= H) break;
+    double acc = 0.0;
+    for (int k = 0; k < nt; ++k) acc += static_cast<double>(s_h[ly + k][threadIdx.x] * taps[k]);
+    out[static_cast<size_t>(gy) * P + gx] = static_cast<float>(acc * scale_y[gy]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K5: EdgeDetectorMap consumer (butteraugli.cc:689-738, 1135-1148). One res cell per thread,
 // reads the six small-sigma blurred planes.
 // ---------------------------------------------------------------------------------------------
@@ -456,13 +518,44 @@ k_block_diff_map(const float* __restrict__ a, const float* __restrict__ b, size_
     }
     __syncwarp();
     double dc[3], ac[3], edge[3];
-    warp_block_diff(s_a[warp], s_b[warp], s_ws[warp], csf_a, csf_b, dc, ac, edge);
+    warp_block_diff<false>(s_a[warp], s_b[warp], s_ws[warp], csf_a, csf_b, dc, ac, edge);
     if (lane < 3) {
       const size_t o = 3 * (static_cast<size_t>(ry) * rxs + rx) + lane;
-      dc_out[o] = static_cast<float>(lane == 0 ? dc[0] : lane == 1 ? dc[1] : dc[2]);
       ac_out[o] = static_cast<float>(lane == 0 ? ac[0] : lane == 1 ? ac[1] : ac[2]);
     }
   }
+}
+
+// K6b: the DC term of BlockDiffMap (butteraugli.cc:602-617, 1098-1106), one res cell per thread: the
+// mean of the 64 per-pixel half-differences in the reference's order, then the low-frequency
+// colour metric. (The warp-per-cell kernel would spend 64 dependent additions on three lanes.)
+__global__ void __launch_bounds__(128)
+k_block_dc(const float* __restrict__ a, const float* __restrict__ b, size_t stride, int W, int H, int P,
+           int rxs, int ncx, int ncy, float* __restrict__ dc_out) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ncx * ncy) return;
+  const int ry = cell / ncx, rx = cell - ry * ncx;
+  const int ox = min(3 * rx, W - 8), oy = min(3 * ry, H - 8);
+  double m[3];
+#pragma unroll 1
+  for (int c = 0; c < 3; ++c) {
+    const float* pa = a + c * stride + static_cast<size_t>(oy) * P + ox;
+    const float* pb = b + c * stride + static_cast<size_t>(oy) * P + ox;
+    double acc = 0.0;
+#pragma unroll 1
+    for (int y = 0; y < 8; ++y) {
+#pragma unroll
+      for (int x = 0; x < 8; ++x) acc += (static_cast<double>(pa[x]) - static_cast<double>(pb[x])) / 2;
+      pa += P;
+      pb += P;
+    }
+    m[c] = acc / 32;
+  }
+  double sq[3] = {0.0, 0.0, 0.0};
+  lowfreq_sq_acc0(m, kCsf8x8[0], sq);
+  float* o = dc_out + 3 * (static_cast<size_t>(ry) * rxs + rx);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c] = static_cast<float>(sq[c]);
 }
 
 // ---------------------------------------------------------------------------------------------

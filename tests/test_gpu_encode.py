@@ -239,3 +239,18 @@ def test_group_encode_edge_cases(gz, name, world):
     assert hashlib.sha256(res[0][0]).hexdigest() == gold["sha256"]
     got = trace_records([l for l in res[0][2].splitlines() if "Out[" in l])
     assert got == trace_records(gold["trace"])
+
+
+@pytest.mark.parametrize("key", ["1024x1024_q90_s1234", "4000x3000_q95_s1234"])
+def test_full_bench_workloads_equal_reference(gz, key):
+    """The FULL workloads of BASELINE.json (bench.py's 1 MPix q90 image, the 12 MPix q95 image):
+    bytes and iteration trace of the single-threaded CPU reference (tests/golden/full_encodes.json,
+    two minutes and a quarter of an hour of CPU Guetzli, made by tests/golden/make_full_golden.py)."""
+    path = os.path.join(GOLD, "full_encodes.json")
+    gold_all = json.load(open(path)) if os.path.exists(path) else {}
+    if key not in gold_all:
+        pytest.skip("golden for %s not generated" % key)
+    gold = gold_all[key]
+    m = re.match(r"(\d+)x(\d+)_q(\d+)_s(\d+)", key)
+    w, h, q, seed = map(int, m.groups())
+    check(gz, synth_image(w, h, seed), gold)
