@@ -197,8 +197,11 @@ def run_ours(a, rank, world, local):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w, h = a.size
     target = np.float32(gz.ButteraugliScoreForQuality(a.quality))
-    host_threads = max(1, (os.cpu_count() or 1) // max(1, world))
-    host_threads = min(16, host_threads)
+    cores = os.cpu_count() or 1
+    host_threads = min(16, max(1, cores // max(1, world)))
+    if a.mode == "group" and world > 1:
+        # one image: the sequential back end runs on rank 0 alone, the other ranks only drive their GPU
+        host_threads = min(16, max(1, cores - 2 * (world - 1))) if rank == 0 else 2
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def barrier():

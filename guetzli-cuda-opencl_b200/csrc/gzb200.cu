@@ -244,6 +244,10 @@ struct gzb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // entropy coding of the candidate, concurrent with its Compare
+  cudaStream_t stream_b = nullptr, stream_l = nullptr;   // BlockDiffMap / EdgeDetectorLowFreq branches of a Compare
+  cudaEvent_t ev_fork = nullptr, ev_bdm = nullptr, ev_lf = nullptr;
+  bool concurrent = false;          // the branches' blur scratch regions fit side by side in d_tmp
+  size_t tmp_main_off = 0;          // floats: where the main stream's blur scratch starts in d_tmp
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int W = 0, H = 0, P = 0, HP = 0, bw = 0, bh = 0, nblocks = 0, rxs = 0, rys = 0, sqp = 0;
   size_t ps = 0;       // floats per full-res plane (P * HP)
@@ -324,17 +328,19 @@ template <typename T>
 void dmalloc(T** p, size_t n) { CK(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T))); }
 
 void run_blur(gzb_ctx* c, const BlurPlan& pl, const float* in, size_t in_stride, int planes,
-              float* out, size_t out_stride, int out_pitch) {
+              float* out, size_t out_stride, int out_pitch, cudaStream_t st = nullptr, float* tmp = nullptr) {
   const BlurGeom& g = pl.g;
   c->packed_valid = false;
   if (g.nx <= 0 || g.ny <= 0) return;
+  if (!st) st = c->stream;
+  if (!tmp) tmp = c->d_tmp + c->tmp_main_off;
   dim3 blk(32, 8);
   dim3 gh((g.nx + g.oxn - 1) / g.oxn, (g.in_h + kBhRows - 1) / kBhRows, planes);
   const size_t tstride = pl.tmp_floats();
-  if (g.ups == 1) KLAUNCH(c, KC_BLUR_H, k_blur_h<1><<<gh, blk, 0, c->stream>>>(in, in_stride, g, pl.d_sx, c->d_tmp, tstride));
-  else KLAUNCH(c, KC_BLUR_H, k_blur_h<3><<<gh, blk, 0, c->stream>>>(in, in_stride, g, pl.d_sx, c->d_tmp, tstride));
+  if (g.ups == 1) KLAUNCH_S(c, st, KC_BLUR_H, k_blur_h<1><<<gh, blk, 0, st>>>(in, in_stride, g, pl.d_sx, tmp, tstride));
+  else KLAUNCH_S(c, st, KC_BLUR_H, k_blur_h<3><<<gh, blk, 0, st>>>(in, in_stride, g, pl.d_sx, tmp, tstride));
   dim3 gv((g.nx + 31) / 32, (g.ny + g.oyn - 1) / g.oyn, planes);
-  KLAUNCH(c, KC_BLUR_V, k_blur_v<<<gv, blk, 0, c->stream>>>(c->d_tmp, tstride, g, pl.d_sy, out, out_stride, out_pitch));
+  KLAUNCH_S(c, st, KC_BLUR_V, k_blur_v<<<gv, blk, 0, st>>>(tmp, tstride, g, pl.d_sy, out, out_stride, out_pitch));
 }
 
 void render_candidate(gzb_ctx* c, int op) {
@@ -386,6 +392,7 @@ void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
   float* m0 = c->d_mh;
   float* m1 = c->d_mh + 3 * c->ps;
   KLAUNCH(c, KC_MHIC, k_mask_high_intensity_change<<<gpx, blk, 0, c->stream>>>(xyb0, xyb1, c->ps, W, H, P, m0, m1));
+  if (c->concurrent) CK(cudaEventRecord(c->ev_fork, c->stream));
   // EdgeDetectorMap: the six small-sigma blurs (3 channels x 2 images) in one fused H+V launch
   {
     SmallBlur3 sb;
@@ -405,20 +412,32 @@ void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
   }
   dim3 gres((c->rxs + 31) / 32, (c->rys + 7) / 8);
   KLAUNCH(c, KC_EDGE_MAP, k_edge_detector_map<<<gres, blk, 0, c->stream>>>(c->d_bl, c->d_bl + 3 * c->ps, c->ps, W, H, P, c->rxs, c->d_edm));
-  // BlockDiffMap
+  // BlockDiffMap and EdgeDetectorLowFreq do not depend on the EdgeDetectorMap / Mask chain: they run
+  // on two side streams (forked after MaskHighIntensityChange, joined before CombineChannels) so
+  // that at small image sizes the short kernels of the three branches overlap.
   const size_t rbytes = static_cast<size_t>(3) * c->rxs * c->rys * sizeof(float);
-  CK(cudaMemsetAsync(c->d_ac, 0, rbytes, c->stream));
   const int ncx = (W - 4 + 2) / 3, ncy = (H - 4 + 2) / 3;
   const int cells = ncx * ncy;
   const int ctas = std::min((cells + kBdmWarps - 1) / kBdmWarps, c->sm_count * 16);
-  KLAUNCH(c, KC_BLOCK_DIFF, k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, c->stream>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac));
-  KLAUNCH(c, KC_BLOCK_DIFF, k_block_dc<<<(cells + 127) / 128, 128, 0, c->stream>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc));
-  // EdgeDetectorLowFreq
-  run_blur(c, c->p_lf, c->d_mh, c->ps, 6, c->d_lf, c->lf_stride, c->p_lf.g.tmp_pitch);
-  KLAUNCH(c, KC_LOWFREQ, k_edge_lowfreq<<<gres, blk, 0, c->stream>>>(c->d_lf, c->d_lf + 3 * c->lf_stride, c->lf_stride, c->p_lf.g.tmp_pitch,
+  cudaStream_t sb = c->concurrent ? c->stream_b : c->stream;
+  cudaStream_t sl = c->concurrent ? c->stream_l : c->stream;
+  if (c->concurrent) {
+    CK(cudaStreamWaitEvent(sb, c->ev_fork, 0));
+    CK(cudaStreamWaitEvent(sl, c->ev_fork, 0));
+  }
+  CK(cudaMemsetAsync(c->d_ac, 0, rbytes, sb));
+  KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac));
+  KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_dc<<<(cells + 127) / 128, 128, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc));
+  if (c->concurrent) CK(cudaEventRecord(c->ev_bdm, sb));
+  // EdgeDetectorLowFreq (its blur scratch is the first part of d_tmp, the main stream's the rest)
+  run_blur(c, c->p_lf, c->d_mh, c->ps, 6, c->d_lf, c->lf_stride, c->p_lf.g.tmp_pitch, sl, c->d_tmp);
+  if (c->concurrent) CK(cudaStreamWaitEvent(sl, c->ev_bdm, 0));   // adds into block_diff_ac
+  KLAUNCH_S(c, sl, KC_LOWFREQ, k_edge_lowfreq<<<gres, blk, 0, sl>>>(c->d_lf, c->d_lf + 3 * c->lf_stride, c->lf_stride, c->p_lf.g.tmp_pitch,
                                              c->p_lf.g.sx, W, H, c->rxs, c->d_ac));
+  if (c->concurrent) CK(cudaEventRecord(c->ev_lf, sl));
   // Mask + combine
   run_mask(c, m0, m1, false);
+  if (c->concurrent) CK(cudaStreamWaitEvent(c->stream, c->ev_lf, 0));   // ev_lf follows ev_bdm
   KLAUNCH(c, KC_COMBINE, k_combine<<<gres, blk, 0, c->stream>>>(mask_sample(c, false), c->d_dc, c->d_ac, c->d_edm, W, H, c->rxs, c->rys, c->sqp, c->d_sq));
   // CalculateDiffmap
   run_blur(c, c->p_dm, c->d_sq, 0, 1, c->d_dsmall, 0, c->p_dm.g.tmp_pitch);
@@ -439,6 +458,11 @@ void free_ctx(gzb_ctx* c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->stream_b) cudaStreamDestroy(c->stream_b);
+  if (c->stream_l) cudaStreamDestroy(c->stream_l);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_bdm) cudaEventDestroy(c->ev_bdm);
+  if (c->ev_lf) cudaEventDestroy(c->ev_lf);
   delete c;
 }
 
@@ -465,6 +489,11 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->stream_b, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->stream_l, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_bdm, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_lf, cudaEventDisableTiming));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     c->W = W; c->H = H; c->target = target;
@@ -524,8 +553,16 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     // the blur scratch must hold the widest H-pass output of any plan
     const BlurPlan* all[] = {&c->p_ed[0], &c->p_ed[1], &c->p_ed[2], &c->p_lf, &c->p_mk[0], &c->p_mk[1],
                              &c->p_mk[2], &c->p_mkb2, &c->p_dm};
-    for (const BlurPlan* pl : all)
+    size_t main_need = 0;
+    for (const BlurPlan* pl : all) {
       if (pl->tmp_floats() > c->ps) throw std::string("internal: blur scratch too small");
+      const bool two_planes = pl == &c->p_ed[0] || pl == &c->p_ed[1] || pl == &c->p_ed[2];  // unfused fallback
+      if (pl != &c->p_lf) main_need = std::max(main_need, pl->tmp_floats() * (two_planes ? 2 : 1));
+    }
+    // EdgeDetectorLowFreq's scratch (6 planes of its decimated width) in front, the main stream's behind
+    const size_t lf_need = (6 * c->p_lf.tmp_floats() + 63) & ~size_t(63);
+    c->concurrent = lf_need + main_need <= 6 * c->ps;
+    c->tmp_main_off = c->concurrent ? lf_need : 0;
     CK(cudaStreamSynchronize(c->stream));
     return c;
   } catch (const std::string& e) {

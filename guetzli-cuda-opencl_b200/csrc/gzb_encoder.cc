@@ -845,6 +845,24 @@ long gzb_test_quantize_magic(int qmax) {
   return bad;
 }
 
+// WorkerPool stress (CPU test hook): `jobs` back-to-back run() calls of varying width on a pool of
+// `threads`; every task adds its index to a per-job sum. Returns the number of jobs whose sum is wrong.
+long gzb_test_pool_stress(int threads, int jobs) {
+  gzb::WorkerPool pool(threads);
+  long bad = 0;
+  for (int j = 0; j < jobs; ++j) {
+    const int n = 1 + (j * 7919) % 67;
+    std::atomic<long> sum(0);
+    std::vector<int> hits(n, 0);
+    pool.run(n, [&](int i) { sum.fetch_add(i + 1); ++hits[i]; if ((j & 255) == 0 && i == 0) std::this_thread::yield(); });
+    long want = static_cast<long>(n) * (n + 1) / 2;
+    bool once = true;
+    for (int h : hits) once = once && h == 1;
+    bad += (sum.load() != want || !once) ? 1 : 0;
+  }
+  return bad;
+}
+
 void gzb_test_lazy_sort(int* first, float* second, size_t n, size_t prefix) {
   std::vector<OrderEntry> v(n);
   for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(first[i], second[i]);

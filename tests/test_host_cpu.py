@@ -136,6 +136,24 @@ def test_lazy_sort_equals_std_sort(gz):
                 assert np.array_equal(np.sort(b_id), np.arange(n, dtype=np.int32))
 
 
+def test_worker_pool_runs_every_task_exactly_once(gz):
+    """The spin-then-sleep pool under many short back-to-back jobs, also with several pools alive at
+    once (one per encoder thread in the group tests) and more threads than cores."""
+    import threading
+    L = gz.lib()
+    L.gzb_test_pool_stress.restype = C.c_long
+    L.gzb_test_pool_stress.argtypes = [C.c_int, C.c_int]
+    assert L.gzb_test_pool_stress(1, 1000) == 0
+    assert L.gzb_test_pool_stress(6, 60000) == 0
+    res = []
+    th = [threading.Thread(target=lambda t=t: res.append(L.gzb_test_pool_stress(3 + t, 20000))) for t in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(300)
+    assert res == [0, 0, 0, 0]
+
+
 def test_multiply_quantiser_is_exact(gz):
     L = gz.lib()
     L.gzb_test_quantize_magic.restype = C.c_long
