@@ -530,7 +530,7 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     need(c, &c->d_sq, static_cast<size_t>(c->sqp) * c->rys);
     need(c, &c->d_dsmall, c->p_dm.out_floats());
     need(c, &c->d_diffmap, c->ps);
-    need(c, &c->d_bmax, c->nblocks); need(c, &c->d_weight, c->nblocks);
+    need(c, &c->d_bmax, std::max(c->nblocks, 256)); need(c, &c->d_weight, c->nblocks);  // d_bmax doubles as 193 LPT bins
     need(c, &c->d_mask_scale, static_cast<size_t>(3) * c->nblocks);
     need(c, &c->d_block_err, c->nblocks);
     need(c, &c->d_pregamma, static_cast<size_t>(192) * c->nblocks);
@@ -856,9 +856,22 @@ static int run_zeroing(gzb_ctx* c, int comp_mask, int mode, int b0 = 0, int b1 =
                        sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(b1 - b0), c->stream));
   const int ctas = std::max(1, std::min((b1 - b0 + kZeroWarps - 1) / kZeroWarps, c->sm_count * 5));
   CK(cudaEventRecord(c->ev0, c->stream));
+  const int* lpt = nullptr;
+  if (mode == 0) {
+    // buffers that are idle during the zeroing search: the error array of the single-CompareBlock
+    // modes (block order), the weight flags (per-block cost), the block-max array (193 bins)
+    int* order = reinterpret_cast<int*>(c->d_block_err);
+    unsigned int* bins = reinterpret_cast<unsigned int*>(c->d_bmax);
+    const int g = (b1 - b0 + 255) / 256;
+    CK(cudaMemsetAsync(bins, 0, 193 * sizeof(unsigned int), c->stream));
+    KLAUNCH(c, KC_MISC, k_zero_block_cost<<<g, 256, 0, c->stream>>>(c->d_coef, cs, comp_mask, b0, b1, c->d_flags, bins));
+    KLAUNCH(c, KC_MISC, k_zero_cost_scan<<<1, 32, 0, c->stream>>>(bins));
+    KLAUNCH(c, KC_MISC, k_zero_lpt_scatter<<<g, 256, 0, c->stream>>>(c->d_flags, bins, b0, b1, order));
+    lpt = order;
+  }
   KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<ctas, 32 * kZeroWarps, 0, c->stream>>>(
       c->d_orig, c->d_coef, cs, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, b1, c->d_mask_scale, comp_mask,
-      c->target, 3, mode, 0, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1));
+      c->target, 3, mode, 0, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1, lpt));
   CK(cudaEventRecord(c->ev1, c->stream));
   return 0;
 }
@@ -898,7 +911,7 @@ int gzb_compare_block(gzb_ctx* c, int block_x, int block_y, const int16_t* candi
   CK(cudaMemsetAsync(c->d_scalars + 1, 0, sizeof(unsigned int), c->stream));
   KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<1, 32 * kZeroWarps, 0, c->stream>>>(
       d_cand, d_cand, 64, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, 1, c->d_mask_scale, 7, c->target, 3, 2,
-      block_y * c->bw + block_x, 0, nullptr, c->d_block_err, nullptr, c->d_scalars + 1));
+      block_y * c->bw + block_x, 0, nullptr, c->d_block_err, nullptr, c->d_scalars + 1, nullptr));
   CK(cudaMemcpyAsync(c->h_pinned, c->d_block_err, sizeof(float), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 4;
   sync_check(c);
   *err = static_cast<double>(c->h_pinned[0]);

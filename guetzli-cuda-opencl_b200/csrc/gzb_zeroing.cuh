@@ -181,6 +181,45 @@ __device__ __forceinline__ void warp_full_idct(ZeroWarpSmem& s, const int* s_bas
 
 constexpr int kZeroWarps = 4;
 
+// Longest-processing-time-first order of the blocks [b0, b1): a block's search costs about three
+// CompareBlock trials per non-zero AC coefficient, and at ~1 MPix a warp only gets five or six blocks,
+// so handing out the expensive blocks first shortens the tail of the launch. Counting sort by the
+// number of non-zero AC coefficients, descending (order inside a bucket is arbitrary: blocks are
+// independent, the results do not depend on it): cost + histogram, 193-bin scan, scatter.
+__global__ void __launch_bounds__(256)
+k_zero_block_cost(const int16_t* __restrict__ cur, size_t comp_stride, int comp_mask, int b0, int b1,
+                  unsigned char* __restrict__ cost, unsigned int* __restrict__ bins) {
+  const int b = b0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= b1) return;
+  int nz = 0;
+  for (int c = 0; c < 3; ++c) {
+    if (!((comp_mask >> c) & 1)) continue;
+    const uint4* p = reinterpret_cast<const uint4*>(cur + c * comp_stride + static_cast<size_t>(b) * 64);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint4 v = p[k];
+      const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nz += ((w[j] & 0xffffu) != 0) + ((w[j] >> 16) != 0);
+    }
+    nz -= cur[c * comp_stride + static_cast<size_t>(b) * 64] != 0;   // DC is not a candidate
+  }
+  cost[b - b0] = static_cast<unsigned char>(nz);
+  atomicAdd(&bins[192 - nz], 1u);
+}
+__global__ void k_zero_cost_scan(unsigned int* __restrict__ bins) {
+  if (threadIdx.x != 0) return;
+  unsigned int run = 0;
+  for (int i = 0; i < 193; ++i) { const unsigned int v = bins[i]; bins[i] = run; run += v; }
+}
+__global__ void __launch_bounds__(256)
+k_zero_lpt_scatter(const unsigned char* __restrict__ cost, unsigned int* __restrict__ bins, int b0, int b1,
+                   int* __restrict__ order) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b0 + i >= b1) return;
+  order[atomicAdd(&bins[192 - cost[i]], 1u)] = b0 + i;
+}
+
 // mode 0: full zeroing order -> out[block*192 + r]
 // mode 1: single CompareBlock of `cur` with no zeroing -> err_out[block] (stage test entry)
 // mode 2: CompareBlock of ONE block `single_block` whose candidate coefficients are the 192 values
@@ -192,7 +231,8 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
                 int P, int W, int H, int bw, int nblocks, const float* __restrict__ mask_scale,
                 int comp_mask, float limit, int lookahead, int mode, int single_block, int block_begin,
                 CoeffDataDev* __restrict__ out, float* __restrict__ err_out,
-                float* __restrict__ pregamma_out, unsigned int* __restrict__ counter) {
+                float* __restrict__ pregamma_out, unsigned int* __restrict__ counter,
+                const int* __restrict__ lpt_order) {
   __shared__ ZeroWarpSmem sm[kZeroWarps];
   __shared__ int s_basis[64];
   const float* s_lut = g_tab.srgb_lin;   // 1 KB, L1-resident; shared memory is the occupancy limiter
@@ -206,6 +246,7 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
     if (lane == 0) b = atomicAdd(counter, 1u);
     b = __shfl_sync(0xffffffffu, b, 0) + static_cast<unsigned int>(block_begin);
     if (b >= static_cast<unsigned int>(nblocks)) break;
+    if (lpt_order) b = static_cast<unsigned int>(lpt_order[b - block_begin]);
     const int blk = mode == 2 ? single_block : static_cast<int>(b);  // image block (b indexes coefficients)
     const int bx = blk % bw, by = blk / bw;
     const int vx = min(8, W - 8 * bx), vy = min(8, H - 8 * by);
