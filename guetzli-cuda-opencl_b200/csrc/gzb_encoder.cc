@@ -146,6 +146,9 @@ struct OrderLess {
   bool operator()(const OrderEntry& a, const OrderEntry& b) const { return a.second < b.second; }
 };
 
+struct SortDebug { double set_ms = 0, set_par_ms = 0, set_seq_ms = 0, set_small_ms = 0, tail_ms = 0; long n_total = 0, calls = 0, par_levels = 0, seq_levels = 0; };
+static thread_local SortDebug g_sort_dbg;
+
 class LazySort {
  public:
   // pool (optional) parallelises the partition of large ranges; the result is the same array.
@@ -202,22 +205,28 @@ class LazySort {
     const size_t kPiece = 16;
     auto comp = __gnu_cxx::__ops::__iter_comp_iter(OrderLess());
     size_t done = p;
+    g_sort_dbg.calls++; g_sort_dbg.n_total += static_cast<long>(n_);
     while (!pending_.empty() && pending_.back().first < p) {
       Range r = pending_.back();
       pending_.pop_back();
       if (r.last <= p) continue;  // wholly inside the set
       if (r.last - r.first <= kPiece || r.depth == 0) {
+        const double t0 = now_ms();
         if (r.last - r.first > 1) {
           std::__introsort_loop(d_ + r.first, d_ + r.last, static_cast<long>(r.depth), comp);
           std::__insertion_sort(d_ + r.first, d_ + r.last, comp);
         }
+        g_sort_dbg.set_small_ms += now_ms() - t0;
         done = r.last;
         break;  // ranges are disjoint and ordered: nothing else starts before p
       }
       --r.depth;
-      OrderEntry* cut = (pool_ && pool_->size() > 1 && r.last - r.first >= kParallelMin)
-                            ? parallel_partition_pivot(d_ + r.first, d_ + r.last)
+      const bool par = pool_ && pool_->size() > 1 && r.last - r.first >= kParallelMin;
+      const double t0 = now_ms();
+      OrderEntry* cut = par ? parallel_partition_pivot(d_ + r.first, d_ + r.last)
                             : std::__unguarded_partition_pivot(d_ + r.first, d_ + r.last, comp);
+      if (par) { g_sort_dbg.set_par_ms += now_ms() - t0; g_sort_dbg.par_levels++; }
+      else { g_sort_dbg.set_seq_ms += now_ms() - t0; g_sort_dbg.seq_levels++; }
       const size_t c = static_cast<size_t>(cut - d_);
       pending_.push_back({c, r.last, r.depth});
       pending_.push_back({r.first, c, r.depth});
@@ -1336,7 +1345,9 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         size_t prefix = 0;
         if (min_coeffs_to_change > 9 && order_size > 10)
           prefix = std::min(static_cast<size_t>(min_coeffs_to_change - 9), order_size - 10);
-        if (prefix < 8192 || e.pool->size() < 2) prefix = 0;
+        // short prefixes are still consumed as a set (no sorting) but applied on this thread, below
+        size_t small_prefix = 0;
+        if (prefix < 8192 || e.pool->size() < 2) { small_prefix = prefix >= 64 ? prefix : 0; prefix = 0; }
         if (prefix > 0) {
           const double ts = now_ms();
           sorter.ensure_set(prefix);
@@ -1423,6 +1434,10 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           changed_coeffs = static_cast<int>(prefix);
           e.st.be_steps += prefix;
           e.st.be_prefix_steps += prefix;
+        } else if (small_prefix > 0) {
+          const double ts = now_ms();
+          sorter.ensure_set(small_prefix);
+          e.st.be_sort_ms += now_ms() - ts;
         } else if (min_coeffs_to_change > 0) {  // the walk cannot stop before min_coeffs_to_change + 1 entries
           const double ts = now_ms();
           sorter.ensure_bulk(std::min<size_t>(static_cast<size_t>(min_coeffs_to_change), global_order.size() - 1));
@@ -1516,6 +1531,12 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           // steps, or as prev_size when the order is about to run out.
           return static_cast<long long>(i) + 9 >= min_coeffs_to_change || i + 9 >= order_size - 1;
         };
+        if (small_prefix > 0) {   // the set, in array order (any order gives the same state)
+          for (size_t i = 0; i < small_prefix; ++i) flip(i, nullptr, nullptr);
+          recount_bits();
+          e.st.be_prefix_steps += small_prefix;
+          prefix = small_prefix;
+        }
         const bool windowed = e.pool->size() >= 4;
         size_t i = prefix;
         bool stopped = false;
@@ -1688,6 +1709,12 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       e.write_candidate(&e.best_jpeg);
     }
     e.best_remote = false;
+  }
+  if (getenv("GZB_DEBUG")) {
+    const SortDebug& d = g_sort_dbg;
+    fprintf(stderr, "sort: calls %ld avg_n %.0f par %.2f ms (%ld levels) seq %.2f ms (%ld levels) small %.2f ms\n", d.calls,
+            d.calls ? static_cast<double>(d.n_total) / d.calls : 0.0, d.set_par_ms, d.par_levels, d.set_seq_ms, d.seq_levels, d.set_small_ms);
+    g_sort_dbg = SortDebug();
   }
   e.st.search_rounds = e.search_rounds;
   e.st.search_trials = e.search_trials;
