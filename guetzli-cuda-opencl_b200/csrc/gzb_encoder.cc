@@ -251,48 +251,85 @@ class LazySort {
     OrderEntry* a = first + 1;
     const size_t n = static_cast<size_t>(last - a);
     const int T = std::max(1, std::min<int>(4 * pool_->size(), static_cast<int>(n >> 13)));
+    // One pass: chunk t writes its left stoppers (ascending) to lpos_[b0..] and its right stoppers
+    // (ascending) to rpos_[b0..] -- chunk-private slices of two position arrays of n entries -- and
+    // counts them. The global lists are the concatenations (L in chunk order, R in reverse chunk
+    // order, each chunk's R read backwards).
+    if (lpos_.size() < n) lpos_.resize(n);
+    if (rpos_.size() < n) rpos_.resize(n);
     std::vector<size_t> cl(T + 1, 0), cr(T + 1, 0);
     auto bounds = [&](int t, size_t* b0, size_t* b1) { *b0 = n * t / T; *b1 = n * (t + 1) / T; };
     pool_->run(T, [&](int t) {
-      size_t b0, b1, nl = 0, nr = 0;
+      size_t b0, b1;
       bounds(t, &b0, &b1);
-      for (size_t i = b0; i < b1; ++i) { const float v = a[i].second; nl += !(v < pv); nr += !(pv < v); }
+      uint32_t* lp = lpos_.data() + b0;
+      uint32_t* rp = rpos_.data() + b0;
+      size_t nl = 0, nr = 0;
+      for (size_t i = b0; i < b1; ++i) {
+        const float v = a[i].second;
+        lp[nl] = static_cast<uint32_t>(i);
+        nl += !(v < pv);
+        rp[nr] = static_cast<uint32_t>(i);
+        nr += !(pv < v);
+      }
       cl[t + 1] = nl;
       cr[t + 1] = nr;
     });
-    for (int t = 0; t < T; ++t) { cl[t + 1] += cl[t]; cr[t + 1] += cr[t]; }
-    const size_t NL = cl[T], NR = cr[T];
-    if (lpos_.size() < NL) lpos_.resize(NL);
-    if (rpos_.size() < NR) rpos_.resize(NR);
-    // L ascending from the left; R indexed from the right (R[0] = right-most)
-    pool_->run(T, [&](int t) {
+    // cl[t]: left stoppers before chunk t; crr[t]: right stoppers AFTER chunk t (R is indexed from the right)
+    for (int t = 0; t < T; ++t) cl[t + 1] += cl[t];
+    std::vector<size_t> crr(T + 1, 0);
+    for (int t = T - 1; t >= 0; --t) crr[t] = crr[t + 1] + cr[t + 1];
+    const size_t NL = cl[T], NR = crr[0];
+    auto Lk = [&](size_t k) -> uint32_t {   // k-th left stopper (from the left)
+      int t = static_cast<int>(std::upper_bound(cl.begin(), cl.end(), k) - cl.begin()) - 1;
       size_t b0, b1;
       bounds(t, &b0, &b1);
-      size_t il = cl[t];
-      size_t ir = NR - cr[t];   // number of right-stoppers at or after b0
-      for (size_t i = b0; i < b1; ++i) {
-        const float v = a[i].second;
-        if (!(v < pv)) lpos_[il++] = static_cast<uint32_t>(i);
-        if (!(pv < v)) rpos_[--ir] = static_cast<uint32_t>(i);
-      }
-    });
+      return lpos_[b0 + (k - cl[t])];
+    };
+    auto Rk = [&](size_t k) -> uint32_t {   // k-th right stopper (from the right)
+      // chunks in reverse order: chunk t holds global right-ranks [crr[t+1], crr[t+1] + cr[t+1])
+      int lo = 0, hi = T - 1;
+      while (lo < hi) { const int m = (lo + hi) / 2; if (crr[m + 1] <= k) hi = m; else lo = m + 1; }
+      const int t = lo;
+      size_t b0, b1;
+      bounds(t, &b0, &b1);
+      const size_t within = k - crr[t + 1];           // 0 = right-most stopper of the chunk
+      return rpos_[b0 + (cr[t + 1] - 1 - within)];
+    };
     // K = number of k with L[k] < R[k] (monotone: L ascends, R descends)
     size_t lo = 0, hi = std::min(NL, NR);
     while (lo < hi) {
       const size_t m = (lo + hi) / 2;
-      if (lpos_[m] < rpos_[m]) lo = m + 1; else hi = m;
+      if (Lk(m) < Rk(m)) lo = m + 1; else hi = m;
     }
     const size_t K = lo;
     if (K > 0) {
       const int TS = std::max(1, std::min<int>(pool_->size(), static_cast<int>(K >> 12) + 1));
       pool_->run(TS, [&](int t) {
         const size_t k0 = K * t / TS, k1 = K * (t + 1) / TS;
-        for (size_t k = k0; k < k1; ++k) std::swap(a[lpos_[k]], a[rpos_[k]]);
+        if (k0 >= k1) return;
+        // walk both lists incrementally from their k0-th elements
+        int tl = static_cast<int>(std::upper_bound(cl.begin(), cl.end(), k0) - cl.begin()) - 1;
+        size_t lb0, lb1;
+        bounds(tl, &lb0, &lb1);
+        size_t li = k0 - cl[tl];
+        int tr;
+        { int l2 = 0, h2 = T - 1; while (l2 < h2) { const int m = (l2 + h2) / 2; if (crr[m + 1] <= k0) h2 = m; else l2 = m + 1; } tr = l2; }
+        size_t rb0, rb1;
+        bounds(tr, &rb0, &rb1);
+        size_t ri = k0 - crr[tr + 1];   // index from the right inside chunk tr
+        for (size_t k = k0; k < k1; ++k) {
+          while (li >= cl[tl + 1] - cl[tl]) { ++tl; bounds(tl, &lb0, &lb1); li = 0; }
+          while (ri >= cr[tr + 1]) { --tr; bounds(tr, &rb0, &rb1); ri = 0; }
+          std::swap(a[lpos_[lb0 + li]], a[rpos_[rb0 + (cr[tr + 1] - 1 - ri)]]);
+          ++li;
+          ++ri;
+        }
       });
     }
     size_t cut = n;  // the scan is guarded: a stopper exists
-    if (K < NL) cut = std::min<size_t>(cut, lpos_[K]);
-    if (K > 0) cut = std::min<size_t>(cut, rpos_[K - 1]);
+    if (K < NL) cut = std::min<size_t>(cut, Lk(K));
+    if (K > 0) cut = std::min<size_t>(cut, Rk(K - 1));
     return a + cut;
   }
 
