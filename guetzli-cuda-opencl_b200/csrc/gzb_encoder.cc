@@ -534,6 +534,7 @@ struct Encoder {
   bool best_remote = false;         // the best file so far was written on another rank
   gzb::Trial best_trial{};          // ... and this is the trial that produced it
   int search_rounds = 0, search_trials = 0;
+  unsigned long long code_gen = 0;  // counts device codings: tells whether a trial's scan is still resident
 
   void log(const char* fmt, ...) {
     if (!want_trace) return;
@@ -663,10 +664,19 @@ void Encoder::maybe_output_trial(const gzb::Trial& t, const gzb::TrialOutcome& o
   log(" Score[%.4f]", score);
   if (score < best_score || best_score < 0) {
     best_score = score;
-    if (o.owner == group.rank) {
-      assemble_jpeg(o.jpeg, reinterpret_cast<const uint8_t*>(o.scan.data()), o.scan.size(),
-                    static_cast<size_t>(o.jpg_size) - o.jpeg.size() - o.scan.size() - 2, &best_jpeg);
-      best_remote = false;
+    if (o.owner == group.rank && (o.resident_gen == 0 || o.resident_gen == code_gen)) {
+      if (o.resident_gen != 0) {   // still on the device: fetch it now
+        DeviceJpeg dj;
+        dj.header = o.jpeg;
+        dj.scan_bytes = o.scan_bytes;
+        dj.ff_bytes = o.ff_bytes;
+        if (!device_fetch_jpeg(ctx, dj, &best_jpeg)) { best_jpeg.clear(); best_remote = true; best_trial = t; }
+        else best_remote = false;
+      } else {
+        assemble_jpeg(o.jpeg, reinterpret_cast<const uint8_t*>(o.scan.data()), o.scan.size(),
+                      static_cast<size_t>(o.jpg_size) - o.jpeg.size() - o.scan.size() - 2, &best_jpeg);
+        best_remote = false;
+      }
     } else {  // the bytes live on another rank: remember how to rebuild them if they stay the best
       best_jpeg.clear();
       best_remote = true;
@@ -1055,8 +1065,15 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         if (!e.compare_begin()) return false;   // the Compare runs while the file is coded on the second stream
         DeviceJpeg dj;
         if (!device_code_candidate(e.ctx, width, height, e.nb, t.q, t.original != 0, nullptr, nullptr, &dj)) return false;
-        o.scan.resize(static_cast<size_t>(dj.scan_bytes));
-        if (dj.scan_bytes && gzb_candidate_fetch_scan(e.ctx, reinterpret_cast<uint8_t*>(&o.scan[0]), dj.scan_bytes) != GZB_OK) return false;
+        ++e.code_gen;
+        o.scan_bytes = dj.scan_bytes;
+        o.ff_bytes = dj.ff_bytes;
+        if (e.group.world == 1) {
+          o.resident_gen = e.code_gen;   // visited right after this round: fetched only if it becomes the best
+        } else {
+          o.scan.resize(static_cast<size_t>(dj.scan_bytes));
+          if (dj.scan_bytes && gzb_candidate_fetch_scan(e.ctx, reinterpret_cast<uint8_t*>(&o.scan[0]), dj.scan_bytes) != GZB_OK) return false;
+        }
         o.jpg_size = dj.size();
         o.jpeg.swap(dj.header);
         e.st.num_jpeg_writes++;
@@ -1710,6 +1727,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         const double tw = now_ms();
         DeviceJpeg dj;
         if (!device_code_candidate(e.ctx, width, height, e.nb, e.quant, false, dc_hist, ac_hist, &dj)) return fail(GZB_ERR_CUDA);
+        ++e.code_gen;
         e.st.num_jpeg_writes++;
         e.st.device_write_ms += now_ms() - tw;
         if (!e.compare_end()) return fail(GZB_ERR_CUDA);

@@ -125,6 +125,9 @@ struct TrialOutcome {
   int owner = 0;      // rank that evaluated it (its JPEG bytes exist there only)
   std::string jpeg;   // on the owner: the file's header (everything up to the scan) ...
   std::string scan;   // ... and its entropy-coded segment before byte stuffing
+  // single-rank groups leave the scan on the device until the trial turns out to be the best so far:
+  uint64_t scan_bytes = 0, ff_bytes = 0;
+  unsigned long long resident_gen = 0;   // != 0: the scan is the device's coding number `resident_gen`
 };
 
 class QuantSearch {
@@ -281,6 +284,9 @@ class QuantSearch {
         TrialOutcome& mine_o = local[k - static_cast<size_t>(r) * batch_];
         o.jpeg.swap(mine_o.jpeg);
         o.scan.swap(mine_o.scan);
+        o.scan_bytes = mine_o.scan_bytes;
+        o.ff_bytes = mine_o.ff_bytes;
+        o.resident_gen = mine_o.resident_gen;
       }
       keys_.push_back(list[k]);
       cache_.push_back(std::move(o));
