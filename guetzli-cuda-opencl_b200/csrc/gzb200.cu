@@ -264,6 +264,9 @@ struct gzb_ctx {
   Prof prof;
   bool have_orig_coeffs = false, have_coeffs = false, block_cmp = false, have_distmap = false;
   bool compare_pending = false;
+  cudaGraphExec_t cmp_graph_exec = nullptr;   // the Compare pipeline as a graph (gzb_compare_begin)
+  unsigned long long cmp_graph_launches = 0;
+  bool graph_failed = false;
   int sm_count = 148;
   std::string err;
 
@@ -456,6 +459,7 @@ void free_ctx(gzb_ctx* c) {
   for (cudaEvent_t ev : c->prof.free_ev) cudaEventDestroy(ev);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->cmp_graph_exec) cudaGraphExecDestroy(c->cmp_graph_exec);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream_b) cudaStreamDestroy(c->stream_b);
@@ -771,8 +775,46 @@ int gzb_compare_begin(gzb_ctx* c) {
   GZB_TRY(c)
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compare: no candidate coefficients");
   CK(cudaEventRecord(c->ev0, c->stream));
-  opsin_from_u8(c, c->d_rgb1, c->d_xyb1);
-  run_diffmap(c, c->d_xyb0, c->d_xyb1);
+  // Every Compare of a context runs the same ~25 launches on the same buffers (three streams, fork
+  // and join): captured once into a CUDA graph and replayed, which removes the per-launch gaps that
+  // dominate at small image sizes. Per-kernel profiling needs the individual launches.
+  if (c->prof.on || c->graph_failed) {
+    opsin_from_u8(c, c->d_rgb1, c->d_xyb1);
+    run_diffmap(c, c->d_xyb0, c->d_xyb1);
+  } else {
+    if (!c->cmp_graph_exec) {
+      const unsigned long long before = c->launches;
+      const bool pv = c->packed_valid;
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed);
+      if (e == cudaSuccess) {
+        try {
+          opsin_from_u8(c, c->d_rgb1, c->d_xyb1);
+          run_diffmap(c, c->d_xyb0, c->d_xyb1);
+        } catch (const std::string&) { e = cudaErrorUnknown; }
+        const cudaError_t e2 = cudaStreamEndCapture(c->stream, &graph);
+        if (e == cudaSuccess) e = e2;
+      }
+      if (e == cudaSuccess && graph) e = cudaGraphInstantiate(&c->cmp_graph_exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      c->cmp_graph_launches = c->launches - before;
+      c->launches = before;
+      c->packed_valid = pv;
+      if (e != cudaSuccess || !c->cmp_graph_exec) {   // no graph on this driver: plain launches from now on
+        cudaGetLastError();
+        c->cmp_graph_exec = nullptr;
+        c->graph_failed = true;
+      }
+    }
+    if (c->cmp_graph_exec) {
+      c->packed_valid = false;
+      CK(cudaGraphLaunch(c->cmp_graph_exec, c->stream));
+      c->launches += c->cmp_graph_launches;
+    } else {
+      opsin_from_u8(c, c->d_rgb1, c->d_xyb1);
+      run_diffmap(c, c->d_xyb0, c->d_xyb1);
+    }
+  }
   CK(cudaEventRecord(c->ev1, c->stream));
   CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(unsigned int));
   c->compare_pending = true;
