@@ -1118,6 +1118,39 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   std::vector<int> cand_offsets(num_blocks + 1);
   std::vector<uint8_t> cand_coeffs;
   std::vector<float> cand_errors;
+  // What the back end needs from the quantised image -- header size, DC/AC histograms, the DC size
+  // estimate, the zig-zag non-zero masks -- is computed on a host thread while the GPU runs the
+  // zeroing search (the host would otherwise only wait for it).
+  struct BackendPrep {
+    Histogram ac_hist[3], dc_hist[3];
+    int header_size = 0, dc_size = 0;
+    std::vector<uint64_t> zmask[3];
+  } prep;
+  std::thread prep_thread;
+  struct PrepJoin { std::thread& t; ~PrepJoin() { if (t.joinable()) t.join(); } } prep_join{prep_thread};
+  if (e.group.rank == 0) {
+    prep_thread = std::thread([&] {
+      Frame f;
+      f.width = width; f.height = height; f.bw = e.bw; f.bh = e.bh; f.ncomp = e.ncomp_for_output();
+      for (int c = 0; c < 3; ++c) f.coeffs[c] = e.idx[c].data();
+      gzb::jpeg::frame_set_quant(&f, e.quant);
+      prep.header_size = static_cast<int>(gzb::jpeg::header_size(f));
+      gzb::jpeg::build_histograms(f, prep.dc_hist, prep.ac_hist, e.pool.get());   // the components SaveToJpegData keeps
+      {  // EstimateDCSize (processor.cc:548-555)
+        Histogram tmp[3] = {prep.dc_hist[0], prep.dc_hist[1], prep.dc_hist[2]};
+        size_t num = f.ncomp;
+        int ix[4];
+        uint8_t dd[3 * Histogram::kSize];
+        prep.dc_size = static_cast<int>(gzb::jpeg::cluster_histograms(tmp, &num, ix, dd));
+      }
+      // zig-zag non-zero masks of every block: a coefficient flip then touches O(1) symbols
+      for (int c = 0; c < 3; ++c) prep.zmask[c].resize(num_blocks);
+      parallel_rows(num_blocks, e.pool.get(), [&](int b0, int b1) {
+        for (int c = 0; c < 3; ++c)
+          for (int b = b0; b < b1; ++b) prep.zmask[c][b] = gzb::jpeg::zigzag_nonzero_mask(e.idx[c].data() + static_cast<size_t>(b) * 64);
+      });
+    });
+  }
   {
     if (gzb_start_block_comparisons(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
     const double t0 = now_ms();
@@ -1211,30 +1244,11 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   {
     const double t_be = now_ms();
     const int ncomp = 3;
-    Histogram ac_hist[3], dc_hist[3];
-    int header_size, dc_size;
-    {
-      Frame f;
-      f.width = width; f.height = height; f.bw = e.bw; f.bh = e.bh; f.ncomp = e.ncomp_for_output();
-      for (int c = 0; c < 3; ++c) f.coeffs[c] = e.idx[c].data();
-      gzb::jpeg::frame_set_quant(&f, e.quant);
-      header_size = static_cast<int>(gzb::jpeg::header_size(f));
-      gzb::jpeg::build_histograms(f, dc_hist, ac_hist, e.pool.get());   // the components SaveToJpegData keeps
-      {  // EstimateDCSize (processor.cc:548-555)
-        Histogram tmp[3] = {dc_hist[0], dc_hist[1], dc_hist[2]};
-        size_t num = f.ncomp;
-        int ix[4];
-        uint8_t dd[3 * Histogram::kSize];
-        dc_size = static_cast<int>(gzb::jpeg::cluster_histograms(tmp, &num, ix, dd));
-      }
-    }
-    // zig-zag non-zero masks of every block: a coefficient flip then touches O(1) symbols
-    std::vector<uint64_t> zmask[3];
-    for (int c = 0; c < 3; ++c) zmask[c].resize(num_blocks);
-    parallel_rows(num_blocks, e.pool.get(), [&](int b0, int b1) {
-      for (int c = 0; c < 3; ++c)
-        for (int b = b0; b < b1; ++b) zmask[c][b] = gzb::jpeg::zigzag_nonzero_mask(e.idx[c].data() + static_cast<size_t>(b) * 64);
-    });
+    if (prep_thread.joinable()) prep_thread.join();
+    Histogram (&ac_hist)[3] = prep.ac_hist;
+    Histogram (&dc_hist)[3] = prep.dc_hist;
+    const int header_size = prep.header_size, dc_size = prep.dc_size;
+    std::vector<uint64_t> (&zmask)[3] = prep.zmask;
     // the coefficient flips of one iteration, pushed to the device before its Compare
     struct Flips {
       std::vector<int32_t> block; std::vector<uint8_t> cidx; std::vector<int16_t> val;
