@@ -128,6 +128,7 @@ class ButteraugliComparator:
     def SetJpegCoeffs(self, coeffs):
         c = np.ascontiguousarray(coeffs, np.int16).reshape(3, self.num_blocks, 64)
         _check(lib().gzb_set_jpeg_coeffs(self._ctx, _p(c[0]), _p(c[1]), _p(c[2])), self._ctx)
+        self.is_420 = False
 
     def CopyFromJpegData(self, quant=None):
         q = np.ones(192, np.int32) if quant is None else np.ascontiguousarray(quant, np.int32).reshape(192)
@@ -138,13 +139,50 @@ class ButteraugliComparator:
         _check(lib().gzb_apply_global_quantization(self._ctx, _p(q)), self._ctx)
 
     def SetCoeffs(self, coeffs):
-        c = np.ascontiguousarray(coeffs, np.int16).reshape(3, self.num_blocks, 64)
+        if self.is_420:
+            c = [np.ascontiguousarray(coeffs[k], np.int16).reshape(self.ComponentDims(k)[2], 64) for k in range(3)]
+        else:
+            c = np.ascontiguousarray(coeffs, np.int16).reshape(3, self.num_blocks, 64)
         _check(lib().gzb_set_coeffs(self._ctx, _p(c[0]), _p(c[1]), _p(c[2])), self._ctx)
 
     def GetCoeffs(self):
-        c = np.zeros((3, self.num_blocks, 64), np.int16)
+        """[3, num_blocks, 64] int16; for a 4:2:0 image a list of three [blocks_c, 64] arrays."""
+        if self.is_420:
+            c = [np.zeros((self.ComponentDims(k)[2], 64), np.int16) for k in range(3)]
+        else:
+            c = np.zeros((3, self.num_blocks, 64), np.int16)
         _check(lib().gzb_get_coeffs(self._ctx, _p(c[0]), _p(c[1]), _p(c[2])), self._ctx)
         return c
+
+    # ---- YUV 4:2:0 (OutputImage::Downsample + SaveToJpegData) -------------------------------
+    is_420 = False
+
+    def Downsample420(self):
+        L = lib()
+        L.gzb_downsample_420.argtypes = [C.c_void_p]
+        _check(L.gzb_downsample_420(self._ctx), self._ctx)
+        self.is_420 = True
+
+    def ComponentDims(self, comp):
+        """(blocks per row, blocks per column, blocks, sampling factor) of a component's coefficient array."""
+        L = lib()
+        L.gzb_component_dims.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
+        bw, bh, f = C.c_int(), C.c_int(), C.c_int()
+        _check(L.gzb_component_dims(self._ctx, comp, C.byref(bw), C.byref(bh), C.byref(f)), self._ctx)
+        return bw.value, bh.value, bw.value * bh.value, f.value
+
+    def GetJpegCoeffs(self):
+        """The input coefficients (jpg.components[c].coeffs): list of three [blocks_c, 64] arrays."""
+        L = lib()
+        L.gzb_get_jpeg_coeffs.argtypes = [C.c_void_p] * 4
+        c = [np.zeros((self.ComponentDims(k)[2], 64), np.int16) for k in range(3)]
+        _check(L.gzb_get_jpeg_coeffs(self._ctx, _p(c[0]), _p(c[1]), _p(c[2])), self._ctx)
+        return c
+
+    def ZeroingUnits(self, comp_mask):
+        if self.is_420 and (comp_mask & 6):
+            return ((self.width + 15) // 16) * ((self.height + 15) // 16)
+        return self.num_blocks
 
     def UpdateCoeffs(self, block_ix, idx, val):
         b = np.ascontiguousarray(block_ix, np.int32)
@@ -215,7 +253,7 @@ class ButteraugliComparator:
         return out
 
     def ComputeBlockZeroingOrder(self, comp_mask=7):
-        out = np.zeros((self.num_blocks, 192), COEFF_DATA)
+        out = np.zeros((self.ZeroingUnits(comp_mask), 192), COEFF_DATA)
         _check(lib().gzb_compute_block_zeroing_order(self._ctx, comp_mask, _p(out)), self._ctx)
         return out
 
@@ -225,7 +263,7 @@ class ButteraugliComparator:
         L = lib()
         L.gzb_compute_block_zeroing_candidates_range.argtypes = [
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
-        b1 = self.num_blocks if block_end is None else block_end
+        b1 = self.ZeroingUnits(comp_mask) if block_end is None else block_end
         nloc = b1 - block_begin
         off = np.zeros(nloc + 1, np.int32)
         cap = max(1, nloc * 192)
@@ -236,11 +274,15 @@ class ButteraugliComparator:
                                                             cap, C.byref(n)), self._ctx)
         return off, idx[:n.value].copy(), err[:n.value].copy()
 
-    def ComputeBlockErrorAdjustmentWeights(self, direction, max_block_dist, target_mul, distmap=None):
-        w = np.zeros(self.num_blocks, np.float32)
+    def ComputeBlockErrorAdjustmentWeights(self, direction, max_block_dist, target_mul, distmap=None, factor=1):
+        bs = 8 * factor
+        w = np.zeros(((self.width + bs - 1) // bs) * ((self.height + bs - 1) // bs), np.float32)
         dm = None if distmap is None else np.ascontiguousarray(distmap, np.float32)
-        _check(lib().gzb_compute_block_error_adjustment_weights(
-            self._ctx, direction, max_block_dist, float(target_mul),
+        L = lib()
+        L.gzb_compute_block_error_adjustment_weights_f.argtypes = [
+            C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        _check(L.gzb_compute_block_error_adjustment_weights_f(
+            self._ctx, direction, max_block_dist, float(target_mul), int(factor),
             None if dm is None else _p(dm), _p(w)), self._ctx)
         return w
 

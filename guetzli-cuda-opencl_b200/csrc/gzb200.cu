@@ -14,6 +14,7 @@
 #include "gzb_kernels.cuh"
 #include "gzb_zeroing.cuh"
 #include "gzb_huffman.cuh"
+#include "gzb_yuv420.cuh"
 
 namespace gzb {
 
@@ -251,6 +252,12 @@ struct gzb_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int W = 0, H = 0, P = 0, HP = 0, bw = 0, bh = 0, nblocks = 0, rxs = 0, rys = 0, sqp = 0;
   size_t ps = 0;       // floats per full-res plane (P * HP)
+  size_t cs = 0;       // coefficients per component slot of d_orig / d_coef
+  // YUV 4:2:0 (after gzb_downsample_420): chroma has mcw x mch blocks, luma is MCU-padded to cbw0 x cbh0
+  bool mode420 = false;
+  int mcw = 0, mch = 0, cbw0 = 0, cbh0 = 0;
+  uint8_t* d_ycc = nullptr;    // [3] u8 planes: Y samples, Cb / Cr half-resolution samples (4:2:0 only)
+  uint8_t* d_cup = nullptr;    // [2] u8 planes: upsampled Cb / Cr of the candidate (4:2:0 only)
   float target = 0.f;
   float distance = 0.f;
   float last_ms = 0.f;
@@ -346,11 +353,36 @@ void run_blur(gzb_ctx* c, const BlurPlan& pl, const float* in, size_t in_stride,
   KLAUNCH_S(c, st, KC_BLUR_V, k_blur_v<<<gv, blk, 0, st>>>(tmp, tstride, g, pl.d_sy, out, out_stride, out_pitch));
 }
 
+// Block geometry of component k's coefficient array in the context's current sampling mode.
+inline int comp_bw(const gzb_ctx* c, int k) { return !c->mode420 ? c->bw : (k == 0 ? c->cbw0 : c->mcw); }
+inline int comp_bh(const gzb_ctx* c, int k) { return !c->mode420 ? c->bh : (k == 0 ? c->cbh0 : c->mch); }
+inline size_t comp_blocks(const gzb_ctx* c, int k) { return static_cast<size_t>(comp_bw(c, k)) * comp_bh(c, k); }
+
 void render_candidate(gzb_ctx* c, int op) {
   c->packed_valid = false;
-  const int grid = (c->nblocks + 31) / 32;
-  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+  const size_t cs = c->cs;
   const size_t us = static_cast<size_t>(c->P) * c->HP;
+  if (c->mode420) {
+    // per component: (quantise | scale) + IDCT -> Y samples / half-resolution chroma samples, then
+    // the fancy upsampling + colour conversion of OutputImage::ToSRGB
+    for (int k = 0; k < 3; ++k) {
+      const int nb = static_cast<int>(comp_blocks(c, k));
+      const int grid = (nb + 31) / 32;
+      const int16_t* src = (op == kCoeffScale ? c->d_orig : c->d_coef) + k * cs;
+      int16_t* dst = c->d_coef + k * cs;
+      uint8_t* plane = c->d_ycc + k * us;
+      if (op == kCoeffKeep)
+        KLAUNCH(c, KC_IDCT, k420_idct_comp<kCoeffKeep><<<grid, 256, 0, c->stream>>>(src, dst, c->d_q + 64 * k, comp_bw(c, k), nb, c->P, plane));
+      else if (op == kCoeffQuantize)
+        KLAUNCH(c, KC_IDCT, k420_idct_comp<kCoeffQuantize><<<grid, 256, 0, c->stream>>>(src, dst, c->d_q + 64 * k, comp_bw(c, k), nb, c->P, plane));
+      else
+        KLAUNCH(c, KC_IDCT, k420_idct_comp<kCoeffScale><<<grid, 256, 0, c->stream>>>(src, dst, c->d_q + 64 * k, comp_bw(c, k), nb, c->P, plane));
+    }
+    dim3 grd((c->W + 1023) / 1024, c->H);
+    KLAUNCH(c, KC_IDCT, k420_render<<<grd, 256, 0, c->stream>>>(c->d_ycc, us, c->W, c->H, c->P, c->d_rgb1, c->d_cup));
+    return;
+  }
+  const int grid = (c->nblocks + 31) / 32;
   if (op == kCoeffKeep)
     KLAUNCH(c, KC_IDCT, k_coeffs_to_rgb8<kCoeffKeep><<<grid, 256, 0, c->stream>>>(c->d_coef, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us));
   else if (op == kCoeffQuantize)
@@ -503,13 +535,16 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     c->W = W; c->H = H; c->target = target;
     c->P = round_up(W, 32);
     c->bw = (W + 7) / 8; c->bh = (H + 7) / 8; c->nblocks = c->bw * c->bh;
-    c->HP = c->bh * 8;
+    c->HP = round_up(H, 16);   // whole 4:2:0 MCUs
     c->ps = static_cast<size_t>(c->P) * c->HP;
+    c->mcw = (W + 15) / 16; c->mch = (H + 15) / 16; c->cbw0 = 2 * c->mcw; c->cbh0 = 2 * c->mch;
+    c->cs = static_cast<size_t>(c->cbw0) * c->cbh0 * 64;
     c->rxs = (W + 2) / 3; c->rys = (H + 2) / 3; c->sqp = round_up(c->rxs, 32);
     const size_t us = c->ps;
     need(c, &c->d_rgb0, 3 * us); need(c, &c->d_rgb1, 3 * us); need(c, &c->d_stage_u8, static_cast<size_t>(3) * W * H);
-    const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+    const size_t cs = c->cs;
     need(c, &c->d_orig, 3 * cs); need(c, &c->d_coef, 3 * cs);
+    need(c, &c->d_ycc, 3 * us); need(c, &c->d_cup, 2 * us);
     need(c, &c->d_xyb0, 3 * c->ps); need(c, &c->d_xyb1, 3 * c->ps);
     need(c, &c->d_mh, 6 * c->ps); need(c, &c->d_bl, 6 * c->ps); need(c, &c->d_tmp, 6 * c->ps);
     // plans
@@ -652,9 +687,12 @@ void gzb_destroy(gzb_ctx* ctx) { free_ctx(ctx); }
 
 int gzb_set_jpeg_coeffs(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const int16_t* c2) {
   GZB_TRY(c)
-  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+  const size_t cs = c->cs;
   const int16_t* src[3] = {c0, c1, c2};
-  for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(c->d_orig + k * cs, src[k], cs * 2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (cs * 2);
+  c->mode420 = false;   // the input of the RGB front end is 4:4:4
+  c->have_coeffs = false;
+  const size_t nb2 = static_cast<size_t>(c->nblocks) * 64 * 2;
+  for (int k = 0; k < 3; ++k) { CK(cudaMemcpyAsync(c->d_orig + k * cs, src[k], nb2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += nb2; }
   sync_check(c);
   c->have_orig_coeffs = true;
   c->packed_valid = false;
@@ -683,9 +721,12 @@ int gzb_apply_global_quantization(gzb_ctx* c, const int* q192) {
 
 int gzb_set_coeffs(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const int16_t* c2) {
   GZB_TRY(c)
-  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+  const size_t cs = c->cs;
   const int16_t* src[3] = {c0, c1, c2};
-  for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(c->d_coef + k * cs, src[k], cs * 2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (cs * 2);
+  for (int k = 0; k < 3; ++k) {
+    const size_t n2 = comp_blocks(c, k) * 64 * 2;
+    CK(cudaMemcpyAsync(c->d_coef + k * cs, src[k], n2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += n2;
+  }
   render_candidate(c, kCoeffKeep);
   sync_check(c);
   c->have_coeffs = true;
@@ -694,9 +735,12 @@ int gzb_set_coeffs(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const int16
 
 int gzb_get_coeffs(gzb_ctx* c, int16_t* c0, int16_t* c1, int16_t* c2) {
   GZB_TRY(c)
-  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+  const size_t cs = c->cs;
   int16_t* dst[3] = {c0, c1, c2};
-  for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(dst[k], c->d_coef + k * cs, cs * 2, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (cs * 2);
+  for (int k = 0; k < 3; ++k) {
+    const size_t n2 = comp_blocks(c, k) * 64 * 2;
+    CK(cudaMemcpyAsync(dst[k], c->d_coef + k * cs, n2, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += n2;
+  }
   sync_check(c);
   GZB_END(c)
 }
@@ -709,8 +753,11 @@ int gzb_update_coeffs(gzb_ctx* c, const int32_t* block_ix, const uint8_t* idx, c
   static const bool dbg = getenv("GZB_DEBUG") != nullptr;
   const double d0 = dbg_now_ms();
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_update_coeffs: no candidate coefficients");
-  for (size_t i = 0; i < n; ++i)
-    if (block_ix[i] < 0 || block_ix[i] >= c->nblocks || idx[i] >= 192) return fail(c, GZB_ERR_BAD_ARG, "gzb_update_coeffs: index out of range");
+  {
+    const int lim[3] = {static_cast<int>(comp_blocks(c, 0)), static_cast<int>(comp_blocks(c, 1)), static_cast<int>(comp_blocks(c, 2))};
+    for (size_t i = 0; i < n; ++i)
+      if (idx[i] >= 192 || block_ix[i] < 0 || block_ix[i] >= lim[idx[i] >> 6]) return fail(c, GZB_ERR_BAD_ARG, "gzb_update_coeffs: index out of range");
+  }
   if (n > 0) {
     // staging: the blur scratch (6 planes, >= 24 bytes per pixel) holds 8 bytes per record for up to
     // three records per pixel -- more than there are AC coefficients; larger batches get their own
@@ -733,7 +780,7 @@ int gzb_update_coeffs(gzb_ctx* c, const int32_t* block_ix, const uint8_t* idx, c
     CK(cudaMemcpyAsync(stage, block_ix, n * 4, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n * 4);
     CK(cudaMemcpyAsync(stage + cap * 4, val, n * 2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n * 2);
     CK(cudaMemcpyAsync(stage + cap * 6, idx, n, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (n);
-    const size_t cs = static_cast<size_t>(c->nblocks) * 64;
+    const size_t cs = c->cs;
     KLAUNCH(c, KC_MISC, k_scatter_coeffs<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(
         reinterpret_cast<const int*>(stage), reinterpret_cast<const int16_t*>(stage + cap * 4),
         stage + cap * 6, n, cs, c->d_coef));
@@ -889,15 +936,24 @@ int gzb_finish_block_comparisons(gzb_ctx* c) {
   return GZB_OK;
 }
 
+// Number of units of the zeroing search for comp_mask: 8x8 blocks, or 16x16 macro-blocks when the
+// last selected component is sub-sampled (processor.cc:566-572).
+static int zeroing_units(const gzb_ctx* c, int comp_mask) {
+  return (c->mode420 && (comp_mask & 6)) ? c->mcw * c->mch : c->nblocks;
+}
+
 static int run_zeroing(gzb_ctx* c, int comp_mask, int mode, int b0 = 0, int b1 = -1) {
-  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
-  if (b1 < 0) b1 = c->nblocks;
+  const size_t cs = c->cs;
+  const bool mb = c->mode420 && (comp_mask & 6);
+  const int units = zeroing_units(c, comp_mask);
+  if (b1 < 0) b1 = units;
   CK(cudaMemsetAsync(c->d_scalars + 1, 0, sizeof(unsigned int), c->stream));
   if (mode == 0)
     CK(cudaMemsetAsync(c->d_order + 192 * static_cast<size_t>(b0), 0,
                        sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(b1 - b0), c->stream));
-  const int ctas = std::max(1, std::min((b1 - b0 + kZeroWarps - 1) / kZeroWarps, c->sm_count * 5));
   CK(cudaEventRecord(c->ev0, c->stream));
+  const int pass_bw = mb ? c->mcw : c->bw;                       // units per row
+  const int coef_bw = mb ? c->mcw : comp_bw(c, 0);               // coefficient blocks per row of the searched plane
   const int* lpt = nullptr;
   if (mode == 0) {
     // buffers that are idle during the zeroing search: the error array of the single-CompareBlock
@@ -906,14 +962,23 @@ static int run_zeroing(gzb_ctx* c, int comp_mask, int mode, int b0 = 0, int b1 =
     unsigned int* bins = reinterpret_cast<unsigned int*>(c->d_bmax);
     const int g = (b1 - b0 + 255) / 256;
     CK(cudaMemsetAsync(bins, 0, 193 * sizeof(unsigned int), c->stream));
-    KLAUNCH(c, KC_MISC, k_zero_block_cost<<<g, 256, 0, c->stream>>>(c->d_coef, cs, comp_mask, b0, b1, c->d_flags, bins));
+    KLAUNCH(c, KC_MISC, k_zero_block_cost<<<g, 256, 0, c->stream>>>(c->d_coef, cs, comp_mask, b0, b1, pass_bw, coef_bw, c->d_flags, bins));
     KLAUNCH(c, KC_MISC, k_zero_cost_scan<<<1, 32, 0, c->stream>>>(bins));
     KLAUNCH(c, KC_MISC, k_zero_lpt_scatter<<<g, 256, 0, c->stream>>>(c->d_flags, bins, b0, b1, order));
     lpt = order;
   }
-  KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<ctas, 32 * kZeroWarps, 0, c->stream>>>(
-      c->d_orig, c->d_coef, cs, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, b1, c->d_mask_scale, comp_mask,
-      c->target, 3, mode, 0, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1, lpt));
+  if (mb) {
+    const int ctas = std::max(1, std::min(b1 - b0, c->sm_count * 4));
+    KLAUNCH(c, KC_ZEROING, k_zeroing_order_mb<<<ctas, 128, 0, c->stream>>>(
+        c->d_orig, c->d_coef, cs, c->d_rgb0, c->d_ycc, c->ps, c->P, c->W, c->H, c->bw, c->mcw, b1, c->d_mask_scale,
+        c->target, 3, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_scalars + 1, lpt));
+  } else {
+    const int ctas = std::max(1, std::min((b1 - b0 + kZeroWarps - 1) / kZeroWarps, c->sm_count * 5));
+    KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<ctas, 32 * kZeroWarps, 0, c->stream>>>(
+        c->d_orig, c->d_coef, cs, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, b1, c->d_mask_scale, comp_mask,
+        c->target, 3, mode, 0, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1, lpt,
+        coef_bw, c->mode420 ? c->d_cup : nullptr));
+  }
   CK(cudaEventRecord(c->ev1, c->stream));
   return 0;
 }
@@ -921,6 +986,7 @@ static int run_zeroing(gzb_ctx* c, int comp_mask, int mode, int b0 = 0, int b1 =
 int gzb_get_block_lists(gzb_ctx* c, float* mask_scale_out, float* opsin_blocks_out) {
   GZB_TRY(c)
   if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_get_block_lists: StartBlockComparisons not called");
+  if (c->mode420) return fail(c, GZB_ERR_UNSUPPORTED, "gzb_get_block_lists: 4:4:4 candidates only");
   if (opsin_blocks_out) {
     if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_get_block_lists: no candidate coefficients");
     run_zeroing(c, 7, 1);
@@ -935,6 +1001,7 @@ int gzb_get_block_lists(gzb_ctx* c, float* mask_scale_out, float* opsin_blocks_o
 int gzb_compare_blocks(gzb_ctx* c, float* err_out) {
   GZB_TRY(c)
   if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_compare_blocks: StartBlockComparisons not called");
+  if (c->mode420) return fail(c, GZB_ERR_UNSUPPORTED, "gzb_compare_blocks: 4:4:4 candidates only");
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compare_blocks: no candidate coefficients");
   run_zeroing(c, 7, 1);
   CK(cudaMemcpyAsync(err_out, c->d_block_err, sizeof(float) * c->nblocks, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(float) * c->nblocks);
@@ -946,6 +1013,7 @@ int gzb_compare_blocks(gzb_ctx* c, float* err_out) {
 int gzb_compare_block(gzb_ctx* c, int block_x, int block_y, const int16_t* candidate192, double* err) {
   GZB_TRY(c)
   if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_compare_block: StartBlockComparisons not called");
+  if (c->mode420) return fail(c, GZB_ERR_UNSUPPORTED, "gzb_compare_block: 4:4:4 candidates only");
   if (!candidate192 || !err || block_x < 0 || block_x >= c->bw || block_y < 0 || block_y >= c->bh)
     return fail(c, GZB_ERR_BAD_ARG, "gzb_compare_block: bad argument");
   int16_t* d_cand = reinterpret_cast<int16_t*>(c->d_upd);  // 384 bytes of the update staging area
@@ -953,7 +1021,7 @@ int gzb_compare_block(gzb_ctx* c, int block_x, int block_y, const int16_t* candi
   CK(cudaMemsetAsync(c->d_scalars + 1, 0, sizeof(unsigned int), c->stream));
   KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<1, 32 * kZeroWarps, 0, c->stream>>>(
       d_cand, d_cand, 64, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, 1, c->d_mask_scale, 7, c->target, 3, 2,
-      block_y * c->bw + block_x, 0, nullptr, c->d_block_err, nullptr, c->d_scalars + 1, nullptr));
+      block_y * c->bw + block_x, 0, nullptr, c->d_block_err, nullptr, c->d_scalars + 1, nullptr, c->bw, nullptr));
   CK(cudaMemcpyAsync(c->h_pinned, c->d_block_err, sizeof(float), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 4;
   sync_check(c);
   *err = static_cast<double>(c->h_pinned[0]);
@@ -965,8 +1033,10 @@ int gzb_compute_block_zeroing_order(gzb_ctx* c, int comp_mask, gzb_coeff_data* o
   if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_compute_block_zeroing_order: StartBlockComparisons not called");
   if (!c->have_coeffs || !c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compute_block_zeroing_order: coefficients missing");
   if (comp_mask < 1 || comp_mask > 7) return fail(c, GZB_ERR_BAD_ARG, "comp_mask must be in 1..7");
+  if (c->mode420 && comp_mask != 1 && comp_mask != 6) return fail(c, GZB_ERR_BAD_ARG, "4:2:0: comp_mask must be 1 (luma) or 6 (chroma)");
   run_zeroing(c, comp_mask, 0);
-  CK(cudaMemcpyAsync(out, c->d_order, sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(c->nblocks), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(c->nblocks));
+  const size_t nrec = static_cast<size_t>(192) * zeroing_units(c, comp_mask);
+  CK(cudaMemcpyAsync(out, c->d_order, sizeof(gzb_coeff_data) * nrec, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += sizeof(gzb_coeff_data) * nrec;
   sync_check(c);
   CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   GZB_END(c)
@@ -977,8 +1047,9 @@ int gzb_compute_block_zeroing_candidates_range(gzb_ctx* c, int comp_mask, int bl
   GZB_TRY(c)
   if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_compute_block_zeroing_candidates: StartBlockComparisons not called");
   if (!c->have_coeffs || !c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compute_block_zeroing_candidates: coefficients missing");
-  if (comp_mask < 1 || comp_mask > 7 || !offsets || !n_out || block_begin < 0 || block_end > c->nblocks || block_begin > block_end)
+  if (comp_mask < 1 || comp_mask > 7 || !offsets || !n_out || block_begin < 0 || block_end > zeroing_units(c, comp_mask) || block_begin > block_end)
     return fail(c, GZB_ERR_BAD_ARG, "gzb_compute_block_zeroing_candidates: bad argument");
+  if (c->mode420 && comp_mask != 1 && comp_mask != 6) return fail(c, GZB_ERR_BAD_ARG, "4:2:0: comp_mask must be 1 (luma) or 6 (chroma)");
   const int nloc = block_end - block_begin;
   if (nloc == 0) { offsets[0] = 0; *n_out = 0; return GZB_OK; }
   // d_tmp (6 planes of scratch) holds counts | offsets | packed err | packed idx
@@ -1014,7 +1085,7 @@ int gzb_compute_block_zeroing_candidates_range(gzb_ctx* c, int comp_mask, int bl
 int gzb_compute_block_zeroing_candidates(gzb_ctx* c, int comp_mask, int* offsets, uint8_t* cand_idx, float* cand_err,
                                          size_t cap, size_t* n_out) {
   if (!c) return GZB_ERR_BAD_ARG;
-  return gzb_compute_block_zeroing_candidates_range(c, comp_mask, 0, c->nblocks, offsets, cand_idx, cand_err, cap, n_out);
+  return gzb_compute_block_zeroing_candidates_range(c, comp_mask, 0, zeroing_units(c, comp_mask), offsets, cand_idx, cand_err, cap, n_out);
 }
 
 // ---- entropy-coded segment on the device (gzb_huffman.cuh) -----------------------------------
@@ -1034,7 +1105,7 @@ HuffScratch huff_scratch(gzb_ctx* c) {
   HuffScratch h;
   uint8_t* base = reinterpret_cast<uint8_t*>(c->d_order);
   const size_t total = sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(c->nblocks);
-  const size_t nunits = 3 * static_cast<size_t>(c->nblocks);
+  const size_t nunits = 3 * (c->cs / 64);   // upper bound for every layout
   size_t o = 0;
   auto take = [&](size_t bytes) { uint8_t* p = base + o; o += (bytes + 255) & ~size_t(255); return p; };
   const size_t nctas = (nunits + kHuffThreads - 1) / kHuffThreads;
@@ -1048,6 +1119,15 @@ HuffScratch huff_scratch(gzb_ctx* c) {
   h.stream_cap = total > o + 64 ? total - o - 64 : 0;
   return h;
 }
+// Scan layout of the resident candidate written with `ncomp` components.
+HuffLayout huff_layout(const gzb_ctx* c, int ncomp, long long* nunits) {
+  HuffLayout L;
+  L.ncomp = ncomp; L.mcw = c->mcw; L.bw = c->bw; L.cbw0 = c->cbw0;
+  if (!c->mode420) { L.mode = 0; *nunits = static_cast<long long>(ncomp) * c->nblocks; }
+  else if (ncomp == 3) { L.mode = 1; *nunits = 6ll * c->mcw * c->mch; }
+  else { L.mode = 2; *nunits = c->nblocks; }
+  return L;
+}
 }  // namespace
 
 int gzb_candidate_symbol_histograms(gzb_ctx* c, const int* q192, uint32_t* dc_hist48, uint32_t* ac_hist768) {
@@ -1056,10 +1136,11 @@ int gzb_candidate_symbol_histograms(gzb_ctx* c, const int* q192, uint32_t* dc_hi
   if (!dc_hist48 || !ac_hist768) return fail(c, GZB_ERR_BAD_ARG, "gzb_candidate_symbol_histograms: null argument");
   if (q192) { CK(cudaMemcpyAsync(c->d_q, q192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream2)); c->h2d_bytes += 192 * sizeof(int); }
   const HuffScratch h = huff_scratch(c);
-  const long long nunits = 3ll * c->nblocks;
+  long long nunits = 0;
+  const HuffLayout L = huff_layout(c, 3, &nunits);
   CK(cudaMemsetAsync(h.hist, 0, (48 + 768) * 4, c->stream2));
   KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_histogram<<<static_cast<unsigned>((nunits + kHuffThreads - 1) / kHuffThreads), kHuffThreads, 0, c->stream2>>>(
-      c->d_coef, static_cast<size_t>(c->nblocks) * 64, c->d_q, 3, nunits, h.hist, h.hist + 48));
+      c->d_coef, c->cs, c->d_q, L, nunits, h.hist, h.hist + 48));
   uint32_t* hh = reinterpret_cast<uint32_t*>(c->h_pinned) + 128;  // bytes 512.. of the pinned page (Compare owns the start)
   CK(cudaMemcpyAsync(hh, h.hist, (48 + 768) * 4, cudaMemcpyDeviceToHost, c->stream2)); c->d2h_bytes += (48 + 768) * 4;
   sync_check2(c);
@@ -1081,10 +1162,11 @@ int gzb_candidate_entropy_code(gzb_ctx* c, int ncomp, const uint16_t* dc_code, c
   memcpy(t.ac_code, ac_code, sizeof(t.ac_code));
   memcpy(t.ac_len, ac_len, sizeof(t.ac_len));
   CK(cudaMemcpyAsync(h.tables, &t, sizeof(t), cudaMemcpyHostToDevice, c->stream2)); c->h2d_bytes += sizeof(t);
-  const long long nunits = static_cast<long long>(ncomp) * c->nblocks;
+  long long nunits = 0;
+  const HuffLayout L = huff_layout(c, ncomp, &nunits);
   const unsigned grid = static_cast<unsigned>((nunits + kHuffThreads - 1) / kHuffThreads);
-  const size_t cs = static_cast<size_t>(c->nblocks) * 64;
-  KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_code<false><<<grid, kHuffThreads, 0, c->stream2>>>(c->d_coef, cs, c->d_q, ncomp, nunits, h.tables,
+  const size_t cs = c->cs;
+  KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_code<false><<<grid, kHuffThreads, 0, c->stream2>>>(c->d_coef, cs, c->d_q, L, nunits, h.tables,
                                                                                   h.unit_bits, h.cta_bits, nullptr, nullptr));
   KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_scan_u64<<<1, 1024, 0, c->stream2>>>(h.cta_bits, static_cast<long long>(grid), h.cta_off));
   unsigned long long* hp = reinterpret_cast<unsigned long long*>(c->h_pinned) + 32;  // bytes 256..
@@ -1095,7 +1177,7 @@ int gzb_candidate_entropy_code(gzb_ctx* c, int ncomp, const uint16_t* dc_code, c
   if (nbytes + 8 > h.stream_cap) return fail(c, GZB_ERR_UNSUPPORTED, "gzb_candidate_entropy_code: scan larger than the device buffer");
   CK(cudaMemsetAsync(h.words, 0, (nbytes + 7) & ~size_t(3), c->stream2));
   CK(cudaMemsetAsync(h.out2, 0, 16, c->stream2));
-  KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_code<true><<<grid, kHuffThreads, 0, c->stream2>>>(c->d_coef, cs, c->d_q, ncomp, nunits, h.tables,
+  KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_code<true><<<grid, kHuffThreads, 0, c->stream2>>>(c->d_coef, cs, c->d_q, L, nunits, h.tables,
                                                                                  h.unit_bits, nullptr, h.cta_off, h.words));
   const unsigned fgrid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(static_cast<size_t>(c->sm_count) * 8, (nbytes + 4095) / 4096)));
   KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_finish<<<fgrid, 256, 0, c->stream2>>>(reinterpret_cast<unsigned char*>(h.words), h.cta_off + grid, h.out2));
@@ -1133,9 +1215,10 @@ int gzb_dct_double(int device, double* blocks, size_t nblocks, int inverse) {
   return GZB_OK;
 }
 
-int gzb_compute_block_error_adjustment_weights(gzb_ctx* c, int direction, int max_block_dist, double target_mul,
-                                               const float* distmap, float* block_weight) {
+int gzb_compute_block_error_adjustment_weights_f(gzb_ctx* c, int direction, int max_block_dist, double target_mul,
+                                                 int factor, const float* distmap, float* block_weight) {
   GZB_TRY(c)
+  if (factor != 1 && factor != 2) return fail(c, GZB_ERR_BAD_ARG, "gzb_compute_block_error_adjustment_weights: factor must be 1 or 2");
   const float* dm = c->d_diffmap;
   if (distmap) {  // a caller-provided map is staged in the blur scratch; the resident map is kept
     CK(cudaMemcpy2DAsync(c->d_tmp, c->P * sizeof(float), distmap, c->W * sizeof(float), c->W * sizeof(float), c->H,
@@ -1146,11 +1229,104 @@ int gzb_compute_block_error_adjustment_weights(gzb_ctx* c, int direction, int ma
     return fail(c, GZB_ERR_STATE, "gzb_compute_block_error_adjustment_weights: no distance map");
   }
   const double target = static_cast<double>(c->target) * target_mul;
-  const int g = (c->nblocks + 255) / 256;
-  KLAUNCH(c, KC_WEIGHTS, k_block_max<<<g, 256, 0, c->stream>>>(dm, c->P, c->W, c->H, c->bw, c->bh, c->d_bmax));
-  KLAUNCH(c, KC_WEIGHTS, k_block_flags<<<g, 256, 0, c->stream>>>(c->d_bmax, c->bw, c->bh, direction, max_block_dist, target, c->d_flags));
-  KLAUNCH(c, KC_WEIGHTS, k_block_weights<<<g, 256, 0, c->stream>>>(c->d_flags, c->bw, c->bh, direction, max_block_dist, c->d_weight));
-  CK(cudaMemcpyAsync(block_weight, c->d_weight, sizeof(float) * c->nblocks, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(float) * c->nblocks);
+  const int bs = 8 * factor, pbw = (c->W + bs - 1) / bs, pbh = (c->H + bs - 1) / bs, nb = pbw * pbh;
+  const int g = (nb + 255) / 256;
+  KLAUNCH(c, KC_WEIGHTS, k_block_max<<<g, 256, 0, c->stream>>>(dm, c->P, c->W, c->H, pbw, pbh, bs, c->d_bmax));
+  KLAUNCH(c, KC_WEIGHTS, k_block_flags<<<g, 256, 0, c->stream>>>(c->d_bmax, pbw, pbh, direction, max_block_dist, target, c->d_flags));
+  KLAUNCH(c, KC_WEIGHTS, k_block_weights<<<g, 256, 0, c->stream>>>(c->d_flags, pbw, pbh, direction, max_block_dist, c->d_weight));
+  CK(cudaMemcpyAsync(block_weight, c->d_weight, sizeof(float) * nb, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(float) * nb);
+  sync_check(c);
+  GZB_END(c)
+}
+
+int gzb_compute_block_error_adjustment_weights(gzb_ctx* c, int direction, int max_block_dist, double target_mul,
+                                               const float* distmap, float* block_weight) {
+  return gzb_compute_block_error_adjustment_weights_f(c, direction, max_block_dist, target_mul, 1, distmap, block_weight);
+}
+
+// ---- YUV 4:2:0 ---------------------------------------------------------------------------------
+int gzb_downsample_420(gzb_ctx* c) {
+  GZB_TRY(c)
+  if (!c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_downsample_420: gzb_set_jpeg_coeffs not called");
+  if (c->mode420) return fail(c, GZB_ERR_STATE, "gzb_downsample_420: the image is already 4:2:0");
+  const int W = c->W, H = c->H, P = c->P;
+  const size_t cs = c->cs, ps = c->ps;
+  c->packed_valid = false;
+  // scratch (idle outside a Compare): yuv planes | normalised planes | conv temps | u8 maps
+  float* yuv = c->d_mh;            // [3]
+  float* nrm = c->d_mh + 3 * ps;   // [3]
+  float* ts = c->d_bl;             // sharpen H pass
+  float* tb = c->d_bl + ps;        // blur H pass
+  float* yuv2 = c->d_bl + 2 * ps;  // [3] output of a PreProcessChannel call
+  uint8_t* maps = reinterpret_cast<uint8_t*>(c->d_tmp);   // 6 byte maps of P*HP (d_tmp holds 24 bytes per pixel)
+  uint8_t *m_dark = maps, *m_red = maps + ps, *m_a = maps + 2 * ps, *m_b = maps + 3 * ps, *m_sharp = maps + 4 * ps, *m_blur = maps + 5 * ps;
+  // ToFloatPixels of the three 4:4:4 components (output_image.cc:553-556)
+  for (int k = 0; k < 3; ++k)
+    KLAUNCH(c, KC_MISC, k420_to_float<<<(c->nblocks + 3) / 4, 256, 0, c->stream>>>(c->d_orig + k * cs, c->bw, c->nblocks, W, H, P, yuv + k * ps));
+  // PreProcessChannel(w, h, 2, 1.3f, 0.5f, ...) then (w, h, 1, ...) (output_image.cc:558-561)
+  PreProcTaps tp;
+  {
+    auto normal = [](double x, double sigma) { return std::exp(-x * x / (2 * sigma * sigma)) * 0.3989422804014327 / sigma; };
+    const double sig_sharpen = static_cast<double>(1.3f), sig_blur = 1.3;
+    double ks[5], kb[5], ss = 0, sb = 0;
+    for (int i = 0; i < 5; ++i) { ks[i] = normal(1.0 * i - 2, sig_sharpen); kb[i] = normal(1.0 * i - 2, sig_blur); }
+    for (int i = 0; i < 5; ++i) { ss += ks[i]; sb += kb[i]; }
+    for (int i = 0; i < 5; ++i) { tp.sharpen[i] = static_cast<float>(ks[i]); tp.blur[i] = static_cast<float>(kb[i]); }
+    tp.sharpen_mul = static_cast<float>(1.0 / ss);
+    tp.blur_mul = static_cast<float>(1.0 / sb);
+  }
+  dim3 gpx((W + 255) / 256, H);
+  float* in = yuv;
+  float* out = yuv2;
+  for (int channel = 2; channel >= 1; --channel) {
+    KLAUNCH(c, KC_MISC, k_pp_norm<<<gpx, 256, 0, c->stream>>>(in, ps, W, H, P, channel, nrm, m_dark, m_red));
+    // Erode x3 on darkmap: dark -> a -> b -> dark
+    KLAUNCH(c, KC_MISC, k_pp_morph<<<gpx, 256, 0, c->stream>>>(m_dark, m_a, W, H, P, 0));
+    KLAUNCH(c, KC_MISC, k_pp_morph<<<gpx, 256, 0, c->stream>>>(m_a, m_b, W, H, P, 0));
+    KLAUNCH(c, KC_MISC, k_pp_morph<<<gpx, 256, 0, c->stream>>>(m_b, m_dark, W, H, P, 0));
+    // Dilate x3 on redmap
+    KLAUNCH(c, KC_MISC, k_pp_morph<<<gpx, 256, 0, c->stream>>>(m_red, m_a, W, H, P, 1));
+    KLAUNCH(c, KC_MISC, k_pp_morph<<<gpx, 256, 0, c->stream>>>(m_a, m_b, W, H, P, 1));
+    KLAUNCH(c, KC_MISC, k_pp_morph<<<gpx, 256, 0, c->stream>>>(m_b, m_red, W, H, P, 1));
+    KLAUNCH(c, KC_MISC, k_pp_blurmap<<<gpx, 256, 0, c->stream>>>(nrm, ps, W, H, P, channel, m_dark, m_red, m_sharp, m_a));
+    // Erode x2 on blurmap: a -> b -> blur
+    KLAUNCH(c, KC_MISC, k_pp_morph<<<gpx, 256, 0, c->stream>>>(m_a, m_b, W, H, P, 0));
+    KLAUNCH(c, KC_MISC, k_pp_morph<<<gpx, 256, 0, c->stream>>>(m_b, m_blur, W, H, P, 0));
+    KLAUNCH(c, KC_MISC, k_pp_conv_h<<<gpx, 256, 0, c->stream>>>(nrm + channel * ps, W, H, P, tp, ts, tb));
+    KLAUNCH(c, KC_MISC, k_pp_final<<<gpx, 256, 0, c->stream>>>(nrm, ps, W, H, P, channel, tp, 0.5f, ts, tb, m_sharp, m_blur, out));
+    std::swap(in, out);
+  }
+  // `in` now holds the pre-processed planes. SetDownsampledCoefficients for Cb and Cr (563-570);
+  // SaveToJpegData: luma re-laid out MCU-padded (608-632), staged through the candidate array.
+  const int nmb = c->mcw * c->mch;
+  CK(cudaMemcpyAsync(c->d_coef, c->d_orig, static_cast<size_t>(c->nblocks) * 128, cudaMemcpyDeviceToDevice, c->stream));
+  KLAUNCH(c, KC_MISC, k420_pad_luma<<<(c->cbw0 * c->cbh0 * 8 + 255) / 256, 256, 0, c->stream>>>(c->d_coef, c->bw, c->bh, c->cbw0, c->cbh0, c->d_orig));
+  for (int k = 1; k < 3; ++k)
+    KLAUNCH(c, KC_MISC, k420_downsample_chroma<<<(nmb + 3) / 4, 256, 0, c->stream>>>(in + k * ps, W, H, P, c->mcw, nmb, c->d_orig + k * cs));
+  sync_check(c);
+  c->mode420 = true;
+  c->have_coeffs = false;
+  if (c->cmp_graph_exec) { /* the Compare graph reads d_rgb1 only: still valid */ }
+  GZB_END(c)
+}
+
+int gzb_component_dims(const gzb_ctx* c, int comp, int* blocks_w, int* blocks_h, int* factor) {
+  if (!c || comp < 0 || comp > 2) return GZB_ERR_BAD_ARG;
+  if (blocks_w) *blocks_w = comp_bw(c, comp);
+  if (blocks_h) *blocks_h = comp_bh(c, comp);
+  if (factor) *factor = (c->mode420 && comp > 0) ? 2 : 1;
+  return GZB_OK;
+}
+
+int gzb_get_jpeg_coeffs(gzb_ctx* c, int16_t* c0, int16_t* c1, int16_t* c2) {
+  GZB_TRY(c)
+  if (!c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_get_jpeg_coeffs: no input coefficients");
+  int16_t* dst[3] = {c0, c1, c2};
+  for (int k = 0; k < 3; ++k) {
+    if (!dst[k]) continue;
+    const size_t n2 = comp_blocks(c, k) * 64 * 2;
+    CK(cudaMemcpyAsync(dst[k], c->d_orig + k * c->cs, n2, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += n2;
+  }
   sync_check(c);
   GZB_END(c)
 }

@@ -35,23 +35,66 @@ __constant__ uint8_t c_natural_order[64] = {  // zig-zag position -> natural ind
     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
+// Scan order of the coding units (EncodeScan, jpeg_data_writer.cc:506-536):
+//   mode 0: 1x1 MCUs, unit u = block * ncomp + comp (4:4:4, or one component);
+//   mode 1: 4:2:0 MCUs, six units per MCU: the four luma blocks (2mx+ix, 2my+iy) of the MCU-padded luma
+//           plane (cbw0 blocks per row), then Cb and Cr block (mx, my);
+//   mode 2: luma only, image blocks (bw per row) read from the MCU-padded plane (SaveToJpegData drops
+//           all-zero chroma planes and then writes a grey 1x1 file, output_image.cc:588-603).
+struct HuffLayout { int mode, ncomp, mcw, bw, cbw0; };
+
+// unit -> component, coefficient block, coefficient block of the unit's DC predecessor (-1: none)
+__device__ __forceinline__ void huff_map(const HuffLayout& L, long long u, int* c, long long* cb, long long* pcb) {
+  if (L.mode == 0) {
+    const long long b = u / L.ncomp;
+    *c = static_cast<int>(u - b * L.ncomp);
+    *cb = b;
+    *pcb = b - 1;
+  } else if (L.mode == 1) {
+    const long long mcu = u / 6;
+    const int r = static_cast<int>(u - mcu * 6);
+    const long long mx = mcu % L.mcw, my = mcu / L.mcw;
+    if (r < 4) {
+      *c = 0;
+      *cb = (2 * my + (r >> 1)) * L.cbw0 + 2 * mx + (r & 1);
+      if (r > 0) {
+        *pcb = (2 * my + ((r - 1) >> 1)) * L.cbw0 + 2 * mx + ((r - 1) & 1);
+      } else if (mcu > 0) {
+        const long long px = (mcu - 1) % L.mcw, py = (mcu - 1) / L.mcw;
+        *pcb = (2 * py + 1) * L.cbw0 + 2 * px + 1;
+      } else {
+        *pcb = -1;
+      }
+    } else {
+      *c = r - 3;
+      *cb = mcu;
+      *pcb = mcu - 1;
+    }
+  } else {
+    *c = 0;
+    *cb = (u / L.bw) * L.cbw0 + u % L.bw;
+    *pcb = u > 0 ? ((u - 1) / L.bw) * L.cbw0 + (u - 1) % L.bw : -1;
+  }
+}
+
 constexpr int kHuffThreads = 128;
 constexpr int kHuffRow = 66;   // shorts per staged row: 132 bytes = 33 words -> conflict-free columns
 
 __device__ __forceinline__ int bit_length_u(unsigned v) { return 32 - __clz(v); }
 
 // Stages the quantised indices of units [u0, u0 + kHuffThreads) into shared memory.
-// Unit u = block * ncomp + comp; coef holds dequantised values (multiples of q), so index = coef / q.
+// coef holds dequantised values (multiples of q), so index = coef / q.
 __device__ __forceinline__ void huff_stage_rows(const int16_t* __restrict__ coef, size_t comp_stride,
-                                                const int* __restrict__ s_q, int ncomp, long long u0,
+                                                const int* __restrict__ s_q, const HuffLayout& L, long long u0,
                                                 long long nunits, int16_t* s_rows) {
   // 128 rows x 8 chunks of 16 bytes
   for (int i = threadIdx.x; i < kHuffThreads * 8; i += kHuffThreads) {
     const int r = i >> 3, ch = i & 7;
     const long long u = u0 + r;
     if (u >= nunits) continue;
-    const long long b = u / ncomp;
-    const int c = static_cast<int>(u - b * ncomp);
+    int c;
+    long long b, pb;
+    huff_map(L, u, &c, &b, &pb);
     const uint4 v = *reinterpret_cast<const uint4*>(coef + c * comp_stride + static_cast<size_t>(b) * 64 + ch * 8);
     const int16_t* pv = reinterpret_cast<const int16_t*>(&v);
     int16_t* dst = s_rows + r * kHuffRow + ch * 8;
@@ -60,15 +103,15 @@ __device__ __forceinline__ void huff_stage_rows(const int16_t* __restrict__ coef
   }
 }
 
-// DC index of the unit that precedes (block, comp) in scan order (0 for the first block).
+// DC index of the unit that precedes this one in its component's scan order (pb < 0: none).
 __device__ __forceinline__ int huff_prev_dc(const int16_t* __restrict__ coef, size_t comp_stride, const int* s_q,
-                                            long long b, int c) {
-  if (b == 0) return 0;
-  return coef[c * comp_stride + static_cast<size_t>(b - 1) * 64] / s_q[64 * c];
+                                            long long pb, int c) {
+  if (pb < 0) return 0;
+  return coef[c * comp_stride + static_cast<size_t>(pb) * 64] / s_q[64 * c];
 }
 
 __global__ void __launch_bounds__(kHuffThreads)
-k_huff_histogram(const int16_t* __restrict__ coef, size_t comp_stride, const int* __restrict__ q192, int ncomp,
+k_huff_histogram(const int16_t* __restrict__ coef, size_t comp_stride, const int* __restrict__ q192, HuffLayout L,
                  long long nunits, unsigned int* __restrict__ dc_hist /*[3][16]*/,
                  unsigned int* __restrict__ ac_hist /*[3][256]*/) {
   __shared__ int16_t s_rows[kHuffThreads * kHuffRow];
@@ -79,14 +122,15 @@ k_huff_histogram(const int16_t* __restrict__ coef, size_t comp_stride, const int
   for (int i = threadIdx.x; i < 768; i += kHuffThreads) s_ac[i] = 0;
   __syncthreads();
   const long long u0 = static_cast<long long>(blockIdx.x) * kHuffThreads;
-  huff_stage_rows(coef, comp_stride, s_q, ncomp, u0, nunits, s_rows);
+  huff_stage_rows(coef, comp_stride, s_q, L, u0, nunits, s_rows);
   __syncthreads();
   const long long u = u0 + threadIdx.x;
   if (u < nunits) {
-    const long long b = u / ncomp;
-    const int c = static_cast<int>(u - b * ncomp);
+    int c;
+    long long b, pb;
+    huff_map(L, u, &c, &b, &pb);
     const int16_t* row = s_rows + threadIdx.x * kHuffRow;
-    const int diff = row[0] - huff_prev_dc(coef, comp_stride, s_q, b, c);
+    const int diff = row[0] - huff_prev_dc(coef, comp_stride, s_q, pb, c);
     atomicAdd(&s_dc[16 * c + bit_length_u(static_cast<unsigned>(abs(diff)))], 1u);
     int run = 0;
 #pragma unroll 1
@@ -136,7 +180,7 @@ struct HuffSink {
 
 template <bool EMIT>
 __global__ void __launch_bounds__(kHuffThreads)
-k_huff_code(const int16_t* __restrict__ coef, size_t comp_stride, const int* __restrict__ q192, int ncomp,
+k_huff_code(const int16_t* __restrict__ coef, size_t comp_stride, const int* __restrict__ q192, HuffLayout L,
             long long nunits, const HuffDeviceTables* __restrict__ tab, unsigned int* __restrict__ unit_bits,
             unsigned int* __restrict__ cta_bits, const unsigned long long* __restrict__ cta_off,
             unsigned int* __restrict__ words) {
@@ -152,7 +196,7 @@ k_huff_code(const int16_t* __restrict__ coef, size_t comp_stride, const int* __r
   }
   __syncthreads();
   const long long u0 = static_cast<long long>(blockIdx.x) * kHuffThreads;
-  huff_stage_rows(coef, comp_stride, s_q, ncomp, u0, nunits, s_rows);
+  huff_stage_rows(coef, comp_stride, s_q, L, u0, nunits, s_rows);
   __syncthreads();
   const long long u = u0 + threadIdx.x;
   const bool live = u < nunits;
@@ -169,14 +213,15 @@ k_huff_code(const int16_t* __restrict__ coef, size_t comp_stride, const int* __r
     for (int w = 0; w < warp; ++w) base += s_warp[w];
     start = cta_off[blockIdx.x] + base + (incl - mine);
   }
-  const long long b = live ? u / ncomp : 0;
-  const int c = live ? static_cast<int>(u - b * ncomp) : 0;
+  int c = 0;
+  long long b = 0, pb = -1;
+  if (live) huff_map(L, u, &c, &b, &pb);
   const int16_t* row = s_rows + threadIdx.x * kHuffRow;
   HuffSink<EMIT> sink;
   sink.init(words, start);
   if (live) {
   {  // DC: coeff_t arithmetic as in the writer (jpeg_data_writer.cc:262-276)
-    const int diff = static_cast<int16_t>(row[0] - huff_prev_dc(coef, comp_stride, s_q, b, c));
+    const int diff = static_cast<int16_t>(row[0] - huff_prev_dc(coef, comp_stride, s_q, pb, c));
     int mag = diff, low = diff;
     if (diff < 0) { mag = -diff; low = diff - 1; }
     mag = static_cast<int16_t>(mag);

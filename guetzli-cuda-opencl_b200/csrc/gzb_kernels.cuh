@@ -777,16 +777,16 @@ k_diffmap_final(const float* __restrict__ sq, int sq_pitch, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// K11: ComputeBlockErrorAdjustmentWeights (guetzli/butteraugli_comparator.cc:169-233), factor 1.
+// K11: ComputeBlockErrorAdjustmentWeights (guetzli/butteraugli_comparator.cc:169-233); bs = 8 * factor.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_block_max(const float* __restrict__ dm, int pitch, int W, int H, int bw, int bh,
+__global__ void k_block_max(const float* __restrict__ dm, int pitch, int W, int H, int bw, int bh, int bs,
                             float* __restrict__ bmax) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= bw * bh) return;
   const int bx = b % bw, by = b / bw;
   float m = 0.0f;
-  for (int y = 8 * by; y < min(H, 8 * by + 8); ++y)
-    for (int x = 8 * bx; x < min(W, 8 * bx + 8); ++x) m = fmaxf(m, dm[static_cast<size_t>(y) * pitch + x]);
+  for (int y = bs * by; y < min(H, bs * by + bs); ++y)
+    for (int x = bs * bx; x < min(W, bs * bx + bs); ++x) m = fmaxf(m, dm[static_cast<size_t>(y) * pitch + x]);
   bmax[b] = m;
 }
 // flags[b] = 1 if block b passes the per-direction test of the reference.

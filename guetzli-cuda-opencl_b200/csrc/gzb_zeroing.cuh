@@ -77,47 +77,46 @@ __device__ __forceinline__ void warp_block_opsin(const float* lin, float* hb, fl
   __syncwarp();
 }
 
-// CompareBlock on the state in `s`: candidate = processed with coefficient `zidx` zeroed
-// (zidx < 0: the processed block itself). Returns the error in all lanes.
-__device__ __forceinline__ float warp_compare_block(ZeroWarpSmem& s, const int* s_basis, const float* lut, int zidx,
-                                                    int vx, int vy, const float scale[3],
-                                                    double csf_a, double csf_b, int lane) {
-  const int zc = zidx >= 0 ? zidx >> 6 : -1;
-  if (zidx >= 0) {
-    const int k = zidx & 63, kx = k & 7, ky = k >> 3;
-    // replacement column kx of component zc
-    if (lane < 8) {
-      int acc = 0;
+// Candidate = processed state with coefficient `zidx` zeroed: the touched component's samples -> s.cpx
+// (incremental IDCT: one replacement column, then the rows).
+__device__ __forceinline__ void warp_candidate_idct(ZeroWarpSmem& s, const int* s_basis, int zidx, int lane) {
+  const int zc = zidx >> 6, k = zidx & 63, kx = k & 7, ky = k >> 3;
+  if (lane < 8) {
+    int acc = 0;
 #pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        const int cv = v == ky ? 0 : s.cf[64 * zc + 8 * v + kx];
-        acc += s_basis[8 * lane + v] * cv;
-      }
-      s.ccol[lane] = static_cast<short>(idct_col_round(acc));
+    for (int v = 0; v < 8; ++v) {
+      const int cv = v == ky ? 0 : s.cf[64 * zc + 8 * v + kx];
+      acc += s_basis[8 * lane + v] * cv;
     }
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int p = lane + 32 * h, x = p & 7, y = p >> 3;
-      int acc = 0;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int cv = u == kx ? s.ccol[y] : s.colv[64 * zc + 8 * y + u];
-        acc += s_basis[8 * x + u] * cv;
-      }
-      s.cpx[p] = static_cast<unsigned char>(idct_row_round(acc));
-    }
-    __syncwarp();
+    s.ccol[lane] = static_cast<short>(idct_col_round(acc));
   }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = lane + 32 * h, x = p & 7, y = p >> 3;
+    int acc = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int cv = u == kx ? s.ccol[y] : s.colv[64 * zc + 8 * y + u];
+      acc += s_basis[8 * x + u] * cv;
+    }
+    s.cpx[p] = static_cast<unsigned char>(idct_row_round(acc));
+  }
+  __syncwarp();
+}
+
+// CompareBlock (guetzli/butteraugli_comparator.cc:113-163) of the 8x8 window whose Y / Cb / Cr samples
+// are pY / pCb / pCr (64 bytes each) against the original block in s.pg0. Returns the error in all lanes.
+__device__ __forceinline__ float warp_compare_pixels(ZeroWarpSmem& s, const float* lut, const unsigned char* pY,
+                                                     const unsigned char* pCb, const unsigned char* pCr,
+                                                     int vx, int vy, const float scale[3],
+                                                     double csf_a, double csf_b, int lane) {
   // pixels -> linear rgb (window replication past the image edge, output_image.cc:85-97)
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int p = lane + 32 * h, x = min(p & 7, vx - 1), y = min(p >> 3, vy - 1), sp = 8 * y + x;
-    const int Y = zc == 0 ? s.cpx[sp] : s.pix[sp];
-    const int Cb = zc == 1 ? s.cpx[sp] : s.pix[64 + sp];
-    const int Cr = zc == 2 ? s.cpx[sp] : s.pix[128 + sp];
     int r, g, b;
-    ycbcr_to_rgb(Y, Cb, Cr, r, g, b);
+    ycbcr_to_rgb(pY[sp], pCb[sp], pCr[sp], r, g, b);
     s.bufA[p] = lut[r];
     s.bufA[64 + p] = lut[g];
     s.bufA[128 + p] = lut[b];
@@ -157,6 +156,40 @@ __device__ __forceinline__ float warp_compare_block(ZeroWarpSmem& s, const int* 
   return static_cast<float>(sqrt((1 - 0.05) * diff + 0.05 * diff_edge));
 }
 
+// CompareBlock on the state in `s`: candidate = processed with coefficient `zidx` zeroed
+// (zidx < 0: the processed block itself).
+__device__ __forceinline__ float warp_compare_block(ZeroWarpSmem& s, const int* s_basis, const float* lut, int zidx,
+                                                    int vx, int vy, const float scale[3],
+                                                    double csf_a, double csf_b, int lane) {
+  const int zc = zidx >= 0 ? zidx >> 6 : -1;
+  if (zidx >= 0) warp_candidate_idct(s, s_basis, zidx, lane);
+  return warp_compare_pixels(s, lut, zc == 0 ? s.cpx : s.pix, zc == 1 ? s.cpx : s.pix + 64,
+                             zc == 2 ? s.cpx : s.pix + 128, vx, vy, scale, csf_a, csf_b, lane);
+}
+
+// Commits the zeroing of coefficient idx: refreshes the touched column and the component's samples.
+__device__ __forceinline__ void warp_commit_zero(ZeroWarpSmem& s, const int* s_basis, int idx, int lane) {
+  const int c = idx >> 6, k = idx & 63, kx = k & 7;
+  if (lane == 0) s.cf[idx] = 0;
+  __syncwarp();
+  if (lane < 8) {
+    int acc = 0;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) acc += s_basis[8 * lane + v] * s.cf[64 * c + 8 * v + kx];
+    s.colv[64 * c + 8 * lane + kx] = static_cast<short>(idct_col_round(acc));
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = lane + 32 * h, x = p & 7, y = p >> 3;
+    int acc = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += s_basis[8 * x + u] * s.colv[64 * c + 8 * y + u];
+    s.pix[64 * c + p] = static_cast<unsigned char>(idct_row_round(acc));
+  }
+  __syncwarp();
+}
+
 // Rebuilds colv / pix of component c from s.cf (full IDCT, warp-cooperative).
 __device__ __forceinline__ void warp_full_idct(ZeroWarpSmem& s, const int* s_basis, int c, int lane) {
 #pragma unroll
@@ -187,14 +220,15 @@ constexpr int kZeroWarps = 4;
 // number of non-zero AC coefficients, descending (order inside a bucket is arbitrary: blocks are
 // independent, the results do not depend on it): cost + histogram, 193-bin scan, scatter.
 __global__ void __launch_bounds__(256)
-k_zero_block_cost(const int16_t* __restrict__ cur, size_t comp_stride, int comp_mask, int b0, int b1,
+k_zero_block_cost(const int16_t* __restrict__ cur, size_t comp_stride, int comp_mask, int b0, int b1, int bw, int coef_bw,
                   unsigned char* __restrict__ cost, unsigned int* __restrict__ bins) {
   const int b = b0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= b1) return;
+  const size_t cb = coef_bw == bw ? static_cast<size_t>(b) : static_cast<size_t>(b / bw) * coef_bw + b % bw;
   int nz = 0;
   for (int c = 0; c < 3; ++c) {
     if (!((comp_mask >> c) & 1)) continue;
-    const uint4* p = reinterpret_cast<const uint4*>(cur + c * comp_stride + static_cast<size_t>(b) * 64);
+    const uint4* p = reinterpret_cast<const uint4*>(cur + c * comp_stride + cb * 64);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const uint4 v = p[k];
@@ -202,7 +236,7 @@ k_zero_block_cost(const int16_t* __restrict__ cur, size_t comp_stride, int comp_
 #pragma unroll
       for (int j = 0; j < 4; ++j) nz += ((w[j] & 0xffffu) != 0) + ((w[j] >> 16) != 0);
     }
-    nz -= cur[c * comp_stride + static_cast<size_t>(b) * 64] != 0;   // DC is not a candidate
+    nz -= cur[c * comp_stride + cb * 64] != 0;   // DC is not a candidate
   }
   cost[b - b0] = static_cast<unsigned char>(nz);
   atomicAdd(&bins[192 - nz], 1u);
@@ -232,7 +266,7 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
                 int comp_mask, float limit, int lookahead, int mode, int single_block, int block_begin,
                 CoeffDataDev* __restrict__ out, float* __restrict__ err_out,
                 float* __restrict__ pregamma_out, unsigned int* __restrict__ counter,
-                const int* __restrict__ lpt_order) {
+                const int* __restrict__ lpt_order, int coef_bw, const uint8_t* __restrict__ fixed_chroma) {
   __shared__ ZeroWarpSmem sm[kZeroWarps];
   __shared__ int s_basis[64];
   const float* s_lut = g_tab.srgb_lin;   // 1 KB, L1-resident; shared memory is the occupancy limiter
@@ -250,11 +284,13 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
     const int blk = mode == 2 ? single_block : static_cast<int>(b);  // image block (b indexes coefficients)
     const int bx = blk % bw, by = blk / bw;
     const int vx = min(8, W - 8 * bx), vy = min(8, H - 8 * by);
+    // coefficient block: the luma plane of a 4:2:0 image is MCU-padded to coef_bw blocks per row
+    const size_t cb = (mode == 2 || coef_bw == bw) ? static_cast<size_t>(b) : static_cast<size_t>(by) * coef_bw + bx;
     // ---- load block state ----
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const int i = lane + 32 * k, c = i >> 6;
-      s.cf[i] = (comp_mask >> c) & 1 ? cur[c * comp_stride + static_cast<size_t>(b) * 64 + (i & 63)] : 0;
+      s.cf[i] = (comp_mask >> c) & 1 ? cur[c * comp_stride + cb * 64 + (i & 63)] : 0;
     }
     // original pixels, coordinates clamped to the image (SwitchBlock, butteraugli_comparator.cc:96-105)
 #pragma unroll
@@ -273,6 +309,16 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
     }
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) warp_full_idct(s, s_basis, c, lane);
+    if (fixed_chroma) {   // 4:2:0 luma pass: Cb / Cr of the window are the image's upsampled samples
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int p = lane + 32 * h;
+        const size_t g = static_cast<size_t>(8 * by + (p >> 3)) * P + 8 * bx + (p & 7);
+        s.pix[64 + p] = fixed_chroma[g];
+        s.pix[128 + p] = fixed_chroma[plane_stride + g];
+      }
+      __syncwarp();
+    }
     const float scale[3] = {mask_scale[3 * blk], mask_scale[3 * blk + 1], mask_scale[3 * blk + 2]};
     if (mode >= 1) {
       const float e = warp_compare_block(s, s_basis, s_lut, -1, vx, vy, scale, csf_a, csf_b, lane);
@@ -288,7 +334,7 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
       const unsigned int m = __ballot_sync(0xffffffffu, take);
       if (take) {
         const int pos = n + __popc(m & ((1u << lane) - 1));
-        const int o = orig[c * comp_stride + static_cast<size_t>(b) * 64 + (i & 63)];
+        const int o = orig[c * comp_stride + cb * 64 + (i & 63)];
         s.ent[pos] = static_cast<unsigned char>(i);
         s.key[pos] = abs(o) * c_zero_csf[i] + c_zero_bias[i];
       }
@@ -319,28 +365,7 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
         if (max_err < best_err) { best_err = max_err; best_i = i; }
       }
       const int idx = win[best_i];
-      // commit: zero the coefficient, refresh the touched column and the component's pixels
-      {
-        const int c = idx >> 6, k = idx & 63, kx = k & 7;
-        if (lane == 0) s.cf[idx] = 0;
-        __syncwarp();
-        if (lane < 8) {
-          int acc = 0;
-#pragma unroll
-          for (int v = 0; v < 8; ++v) acc += s_basis[8 * lane + v] * s.cf[64 * c + 8 * v + kx];
-          s.colv[64 * c + 8 * lane + kx] = static_cast<short>(idct_col_round(acc));
-        }
-        __syncwarp();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int p = lane + 32 * h, x = p & 7, y = p >> 3;
-          int acc = 0;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) acc += s_basis[8 * x + u] * s.colv[64 * c + 8 * y + u];
-          s.pix[64 * c + p] = static_cast<unsigned char>(idct_row_round(acc));
-        }
-        __syncwarp();
-      }
+      warp_commit_zero(s, s_basis, idx, lane);
       if (lane == 0) { o[nout].idx = idx; o[nout].block_err = best_err; }
       ++nout;
       for (int i = best_i; i + 1 < nwin; ++i) win[i] = win[i + 1];

@@ -163,6 +163,30 @@ int gzb_compute_block_error_adjustment_weights(gzb_ctx* ctx, int direction, int 
                                                double target_mul, const float* distmap,
                                                float* block_weight);
 
+/* The same with the sampling factor of the searched component (1: 8x8 blocks, 2: the 16x16 macro-blocks
+ * of a 4:2:0 image); block_weight has ceil(w/(8f))*ceil(h/(8f)) entries. */
+int gzb_compute_block_error_adjustment_weights_f(gzb_ctx* ctx, int direction, int max_block_dist,
+                                                 double target_mul, int factor, const float* distmap,
+                                                 float* block_weight);
+
+/* ---- YUV 4:2:0 (Params::try_420 / force_420; guetzli/processor.cc:986-1016) ------------------
+ * Processor::DownsampleImage + OutputImage::SaveToJpegData on the q=1 input (guetzli/processor.cc:
+ * 109-116, 994-997; guetzli/output_image.cc:496-640; guetzli/preprocess_downsample.cc:157-281, default
+ * DownsampleConfig): the input coefficients become those of the sharpened / blurred, 2x2-averaged
+ * chroma planes (double-precision DCT, guetzli/dct_double.cc) and the context switches to 4:2:0:
+ * component 0 keeps its blocks, laid out MCU-padded (2*ceil(w/16) x 2*ceil(h/16), padding blocks =
+ * {DC of the predecessor, 0...}), components 1 and 2 have ceil(w/16) x ceil(h/16) blocks. From here on
+ * gzb_copy_from_jpeg / gzb_apply_global_quantization / gzb_set_coeffs / gzb_get_coeffs /
+ * gzb_update_coeffs (block index = index in the component's own layout) / gzb_to_srgb / gzb_compare /
+ * the zeroing search (comp_mask 1: luma blocks, 6: macro-blocks) / gzb_candidate_* work on the
+ * factor-2 image (UpdatePixelsForBlock's fancy upsampling, guetzli/output_image.cc:147-210).
+ * gzb_set_jpeg_coeffs returns the context to 4:4:4. */
+int gzb_downsample_420(gzb_ctx* ctx);
+/* Blocks per row / column of component comp's coefficient arrays and its sampling factor. */
+int gzb_component_dims(const gzb_ctx* ctx, int comp, int* blocks_w, int* blocks_h, int* factor);
+/* The input coefficients (jpg.components[c].coeffs after SaveToJpegData); NULL skips a component. */
+int gzb_get_jpeg_coeffs(gzb_ctx* ctx, int16_t* c0, int16_t* c1, int16_t* c2);
+
 /* ---- stage entry points (the reference's cu* free functions; host planes in, host planes out) */
 /* cuOpsinDynamicsImage (clguetzli/cuguetzli.h:19-21): linear rgb planes in place -> XYB. */
 int gzb_opsin_dynamics_image(int device, float* r, float* g, float* b, size_t xsize, size_t ysize);

@@ -385,6 +385,84 @@ void ref_session_block_weights(void* p, int direction, int max_block_dist, doubl
   memcpy(block_weight_inout, wv.data(), wv.size() * sizeof(float));
 }
 
+// ---------------------------------------------------------------- 4:2:0 path
+// Processor::DownsampleImage + OutputImage::SaveToJpegData, the head of the downsample pass of
+// ProcessJpegData (processor.cc:990-997): the session's image and its jpg become YUV420.
+void ref_session_downsample(void* p) {
+  Session* s = static_cast<Session*>(p);
+  s->img.CopyFromJpegData(s->jpg);
+  s->proc.DownsampleImage(&s->img);
+  s->img.SaveToJpegData(&s->jpg);
+}
+// Block geometry of component c: OutputImage layout, JPEGData (MCU-padded) layout, sampling factor.
+void ref_session_comp_dims(void* p, int c, int* img_bw, int* img_bh, int* jpg_bw, int* jpg_bh, int* factor) {
+  Session* s = static_cast<Session*>(p);
+  *img_bw = s->img.component(c).width_in_blocks();
+  *img_bh = s->img.component(c).height_in_blocks();
+  *jpg_bw = s->jpg.components[c].width_in_blocks;
+  *jpg_bh = s->jpg.components[c].height_in_blocks;
+  *factor = s->img.component(c).factor_x();
+}
+// The MODE_CPU branch of SelectFrequencyMasking (processor.cc:638-672) with the sampling factor of
+// the last component of comp_mask (1 -> 8x8 luma blocks, 6 -> 16x16 macro-blocks of a 4:2:0 image).
+void ref_session_zeroing_order_f(void* p, int comp_mask, int block_begin, int block_end,
+                                 guetzli::CoeffData* out) {
+  Session* s = static_cast<Session*>(p);
+  const int last_c = guetzli::Log2FloorNonZero(comp_mask);
+  const int factor_x = s->img.component(last_c).factor_x();
+  const int factor_y = s->img.component(last_c).factor_y();
+  const int block_width = (s->w + 8 * factor_x - 1) / (8 * factor_x);
+  for (int block_ix = block_begin; block_ix < block_end; ++block_ix) {
+    const int block_x = block_ix % block_width, block_y = block_ix / block_width;
+    coeff_t block[192] = {0};
+    coeff_t orig_block[192] = {0};
+    for (int c = 0; c < 3; ++c) {
+      if (comp_mask & (1 << c)) {
+        s->img.component(c).GetCoeffBlock(block_x, block_y, &block[c * 64]);
+        const guetzli::JPEGComponent& comp = s->jpg.components[c];
+        int jpg_block_ix = block_y * comp.width_in_blocks + block_x;
+        memcpy(&orig_block[c * 64], &comp.coeffs[jpg_block_ix * 64], 64 * sizeof(coeff_t));
+      }
+    }
+    std::vector<guetzli::CoeffData> order;
+    s->proc.ComputeBlockZeroingOrder(block, orig_block, block_x, block_y, factor_x, factor_y,
+                                     static_cast<uint8_t>(comp_mask), &s->img, &order);
+    guetzli::CoeffData* q = out + size_t(block_ix - block_begin) * 192;
+    memset(q, 0, 192 * sizeof(guetzli::CoeffData));
+    for (size_t i = 0; i < order.size(); ++i) q[i] = order[i];
+  }
+}
+void ref_session_block_weights_f(void* p, int direction, int max_block_dist, double target_mul, int factor,
+                                 const float* distmap, float* block_weight_inout, int nblocks) {
+  Session* s = static_cast<Session*>(p);
+  std::vector<float> d(distmap, distmap + size_t(s->w) * s->h);
+  std::vector<float> wv(block_weight_inout, block_weight_inout + nblocks);
+  s->cmp->ComputeBlockErrorAdjustmentWeights(direction, max_block_dist, target_mul, factor, factor, d, &wv);
+  memcpy(block_weight_inout, wv.data(), wv.size() * sizeof(float));
+}
+// guetzli::Process with Params::try_420 / force_420 (processor.h:34-42).
+long ref_process_rgb_params(const uint8_t* rgb, int w, int h, float target, int try_420, int force_420,
+                            uint8_t* out, long cap, char* trace, long trace_cap, int* iters) {
+  guetzli::Params params;
+  params.butteraugli_target = target;
+  params.try_420 = try_420 != 0;
+  params.force_420 = force_420 != 0;
+  guetzli::ProcessStats stats;
+  std::string dbg;
+  if (trace) stats.debug_output = &dbg;
+  std::vector<uint8_t> v(rgb, rgb + size_t(3) * w * h);
+  std::string jpg;
+  if (!guetzli::Process(params, &stats, v, w, h, &jpg)) return -1;
+  if (static_cast<long>(jpg.size()) <= cap) memcpy(out, jpg.data(), jpg.size());
+  if (trace && trace_cap > 0) {
+    size_t n = std::min<size_t>(dbg.size(), trace_cap - 1);
+    memcpy(trace, dbg.data(), n);
+    trace[n] = 0;
+  }
+  if (iters) *iters = stats.counters[guetzli::kNumItersCnt];
+  return static_cast<long>(jpg.size());
+}
+
 // ---------------------------------------------------------------- whole encoder
 // guetzli::Process(params, stats, rgb, w, h, &out) (processor.cc:1157-1185).
 // Returns the JPEG size (copied to `out` if it fits `cap`), or -1 on failure.

@@ -70,6 +70,9 @@ def ref():
         L.ref_session_compare.restype = C.c_float
         L.ref_session_compare_block.restype = C.c_double
         L.ref_process_rgb.restype = C.c_long
+        L.ref_process_rgb_params.restype = C.c_long
+        L.ref_session_block_weights_f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int,
+                                                  c_f32p, c_f32p, C.c_int]
         L.ref_session_block_weights.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double,
                                                 c_f32p, c_f32p]
         for name in ("ref_session_free", "ref_session_dims", "ref_session_jpg_coeffs",
@@ -78,7 +81,8 @@ def ref():
                      "ref_session_compare", "ref_session_jpeg_size", "ref_session_write_jpeg",
                      "ref_session_start_block_comparisons",
                      "ref_session_finish_block_comparisons", "ref_session_switch_block",
-                     "ref_session_compare_block", "ref_session_zeroing_order"):
+                     "ref_session_compare_block", "ref_session_zeroing_order", "ref_session_downsample",
+                     "ref_session_comp_dims", "ref_session_zeroing_order_f"):
             fn = getattr(L, name)
             if fn.argtypes is None:
                 fn.argtypes = None  # first arg passed explicitly as c_void_p by RefSession
@@ -181,6 +185,95 @@ class RefSession:
         return w
 
 
+class RefSession420(RefSession):
+    """The session after Processor::DownsampleImage + SaveToJpegData (processor.cc:994-997)."""
+
+    def __init__(self, rgb, target):
+        RefSession.__init__(self, rgb, target)
+        self.L.ref_session_downsample(self.s)
+        self.img_dims, self.jpg_dims, self.factor = [], [], []
+        for c in range(3):
+            v = [C.c_int() for _ in range(5)]
+            self.L.ref_session_comp_dims(self.s, c, *[C.byref(x) for x in v])
+            self.img_dims.append((v[0].value, v[1].value))
+            self.jpg_dims.append((v[2].value, v[3].value))
+            self.factor.append(v[4].value)
+
+    def jpg_coeffs(self):
+        """jpg.components[c].coeffs (MCU-padded layout): list of [blocks, 64]."""
+        out = [np.zeros((bw * bh, 64), np.int16) for (bw, bh) in self.jpg_dims]
+        for c in range(3):
+            self.L.ref_session_jpg_coeffs(self.s, c, p(out[c]))
+        return out
+
+    def coeffs(self):
+        """OutputImage coefficients (image layout): list of [blocks, 64]."""
+        out = [np.zeros((bw * bh, 64), np.int16) for (bw, bh) in self.img_dims]
+        for c in range(3):
+            self.L.ref_session_get_coeffs(self.s, c, p(out[c]))
+        return out
+
+    def set_coeffs(self, coeffs):
+        for c in range(3):
+            a = np.ascontiguousarray(coeffs[c], np.int16)
+            self.L.ref_session_set_coeffs(self.s, c, p(a))
+
+    def to_padded(self, coeffs):
+        """Image-layout coefficient arrays -> the MCU-padded layout of SaveToJpegData (padding
+        blocks = {DC of the raster predecessor, 0...}, output_image.cc:608-632)."""
+        out = []
+        for c in range(3):
+            (bw, bh), (jw, jh) = self.img_dims[c], self.jpg_dims[c]
+            src = np.asarray(coeffs[c]).reshape(bh, bw, 64)
+            dst = np.zeros((jh, jw, 64), np.int16)
+            last = 0
+            for by in range(jh):
+                for bx in range(jw):
+                    if by < bh and bx < bw:
+                        dst[by, bx] = src[by, bx]
+                    else:
+                        dst[by, bx, 0] = last
+                    last = dst[by, bx, 0]
+            out.append(dst.reshape(-1, 64))
+        return out
+
+    def from_padded(self, coeffs):
+        out = []
+        for c in range(3):
+            (bw, bh), (jw, jh) = self.img_dims[c], self.jpg_dims[c]
+            out.append(np.ascontiguousarray(np.asarray(coeffs[c]).reshape(jh, jw, 64)[:bh, :bw].reshape(-1, 64)))
+        return out
+
+    def zeroing_order_f(self, comp_mask, begin=0, end=None):
+        f = self.factor[2 if comp_mask & 4 else (1 if comp_mask & 2 else 0)]
+        n = ((self.w + 8 * f - 1) // (8 * f)) * ((self.h + 8 * f - 1) // (8 * f))
+        end = n if end is None else end
+        out = np.zeros((end - begin, 192), COEFF_DATA)
+        self.L.ref_session_zeroing_order_f(self.s, comp_mask, begin, end, p(out))
+        return out
+
+    def block_weights_f(self, direction, rblock, target_mul, factor, distmap):
+        bs = 8 * factor
+        n = ((self.w + bs - 1) // bs) * ((self.h + bs - 1) // bs)
+        w = np.zeros(n, np.float32)
+        dm = np.ascontiguousarray(distmap, np.float32).reshape(-1)
+        self.L.ref_session_block_weights_f(self.s, direction, rblock, float(target_mul), factor, dm, w, n)
+        return w
+
+
+def ref_process_params(rgb, target, try_420=False, force_420=False, want_trace=False):
+    L = ref()
+    h, w = rgb.shape[:2]
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    out = np.zeros(w * h * 3 + (1 << 16), np.uint8)
+    trace = C.create_string_buffer(1 << 22) if want_trace else None
+    iters = C.c_int()
+    n = L.ref_process_rgb_params(p(rgb), w, h, C.c_float(target), int(try_420), int(force_420), p(out),
+                                 C.c_long(out.size), trace, C.c_long(1 << 22), C.byref(iters))
+    assert n > 0
+    return out[:n].tobytes(), iters.value, (trace.value.decode() if want_trace else None)
+
+
 def ref_process(rgb, target, want_trace=False):
     L = ref()
     h, w = rgb.shape[:2]
@@ -209,6 +302,28 @@ def synth_image(w, h, seed=1234):
         n2 /= n2.std()
         img[:, :, c] = np.clip(np.rint(base + 24 * n1 + 6 * n2), 0, 255).astype(np.uint8)
     return img
+
+
+def image_420(kind, w, h):
+    """Inputs of the 4:2:0 tests. "red": saturated red texture (PreProcessChannel sharpens V there),
+    dark smooth blue-green (it blurs there), a bright patch and photo-like noise side by side."""
+    if kind == "bees":
+        return bees()
+    if kind == "synth":
+        return synth_image(w, h, 777)
+    rng = np.random.Generator(np.random.PCG64(4242))
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    img = synth_image(w, h, 31).astype(np.float64)
+    a, b = w // 3, 2 * w // 3
+    tex = 25 * np.sin(xx / 2.3) * np.cos(yy / 3.1) + 6 * rng.standard_normal((h, w))
+    img[:, :a, 0] = 170 + tex[:, :a]
+    img[:, :a, 1] = 30 + 0.2 * tex[:, :a]
+    img[:, :a, 2] = 35 + 0.1 * tex[:, :a]
+    img[:, a:b, 0] = 20 + 10 * yy[:, a:b] / h
+    img[:, a:b, 1] = 70 + 20 * xx[:, a:b] / w
+    img[:, a:b, 2] = 110 + 25 * yy[:, a:b] / h
+    img[h // 4:h // 2, a + 4:b - 4, :] = 245
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))
 
 
 def bees():
