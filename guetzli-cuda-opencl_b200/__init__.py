@@ -359,7 +359,8 @@ class EncodeStats(C.Structure):
                 ("prepare_ms", C.c_double), ("run_ms", C.c_double), ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong),
                 ("final_score", C.c_double), ("final_distance", C.c_float), ("launches", C.c_ulonglong),
                 ("be_prefix_steps", C.c_ulonglong), ("device_write_ms", C.c_double), ("search_wall_ms", C.c_double), ("trial_host_ms", C.c_double),
-                ("trial_device_ms", C.c_double), ("search_rounds", C.c_int), ("search_trials", C.c_int)]
+                ("trial_device_ms", C.c_double), ("search_rounds", C.c_int), ("search_trials", C.c_int),
+                ("downsample_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -372,9 +373,9 @@ def ButteraugliScoreForQuality(quality):
     return L.gzb_butteraugli_score_for_quality(float(quality))
 
 
-def Process(rgb, butteraugli_target, device=0, host_threads=0, want_trace=False):
-    """guetzli::Process(params, stats, rgb, w, h, &out) on the B200.
-    Returns (jpeg_bytes, stats_dict, trace_or_None)."""
+def Process(rgb, butteraugli_target, device=0, host_threads=0, want_trace=False, try_420=False, force_420=False):
+    """guetzli::Process(params, stats, rgb, w, h, &out) on the B200 (try_420 / force_420: Params of
+    guetzli/processor.h:34-42). Returns (jpeg_bytes, stats_dict, trace_or_None)."""
     L = lib()
     a = np.ascontiguousarray(rgb, np.uint8)
     h, w = a.shape[:2]
@@ -382,14 +383,14 @@ def Process(rgb, butteraugli_target, device=0, host_threads=0, want_trace=False)
     n = C.c_size_t()
     st = EncodeStats()
     tr = C.c_void_p()
-    L.gzb_encode_rgb.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int,
-                                 C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(EncodeStats),
-                                 C.POINTER(C.c_void_p)]
+    L.gzb_encode_rgb_params.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(EncodeStats),
+                                        C.POINTER(C.c_void_p)]
     L.gzb_encode_last_error.restype = C.c_char_p
     L.gzb_free.argtypes = [C.c_void_p]
     L.gzb_free.restype = None
-    rc = L.gzb_encode_rgb(device, _p(a), w, h, C.c_float(butteraugli_target), host_threads,
-                          C.byref(out), C.byref(n), C.byref(st), C.byref(tr) if want_trace else None)
+    rc = L.gzb_encode_rgb_params(device, _p(a), w, h, C.c_float(butteraugli_target), int(try_420), int(force_420),
+                                 host_threads, C.byref(out), C.byref(n), C.byref(st), C.byref(tr) if want_trace else None)
     if rc != 0:
         raise GzbError("gzb_encode_rgb failed (%d): %s" % (rc, L.gzb_encode_last_error().decode(errors="replace")))
     data = C.string_at(out, n.value)
@@ -432,10 +433,11 @@ class Encoder:
     """Two-step encoder (gzb_encoder_create / gzb_encoder_run): create() leaves the image, its
     opsin-dynamics image and the q=1 coefficients resident in HBM; run() performs the search."""
 
-    def __init__(self, rgb, butteraugli_target, device=0, host_threads=0, profile=False):
+    def __init__(self, rgb, butteraugli_target, device=0, host_threads=0, profile=False, try_420=False, force_420=False):
         L = lib()
         a = np.ascontiguousarray(rgb, np.uint8)
         self.h, self.w = a.shape[:2]
+        self._params = (int(try_420), int(force_420))
         L.gzb_encoder_create.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int,
                                          C.POINTER(C.c_void_p)]
         L.gzb_encoder_run.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
@@ -453,6 +455,8 @@ class Encoder:
         if rc != 0:
             raise GzbError("gzb_encoder_create failed (%d): %s" % (rc, L.gzb_encode_last_error().decode(errors="replace")))
         self._ctx = C.c_void_p(L.gzb_encoder_context(self._enc))
+        L.gzb_encoder_set_params.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.gzb_encoder_set_params(self._enc, *self._params)
         if profile:
             profile_enable(self._ctx, True)
 

@@ -1131,13 +1131,18 @@ HuffLayout huff_layout(const gzb_ctx* c, int ncomp, long long* nunits) {
 }  // namespace
 
 int gzb_candidate_symbol_histograms(gzb_ctx* c, const int* q192, uint32_t* dc_hist48, uint32_t* ac_hist768) {
+  return gzb_candidate_symbol_histograms_n(c, q192, 3, dc_hist48, ac_hist768);
+}
+
+int gzb_candidate_symbol_histograms_n(gzb_ctx* c, const int* q192, int ncomp, uint32_t* dc_hist48, uint32_t* ac_hist768) {
   GZB_TRY(c)
+  if (ncomp != 1 && ncomp != 3) return fail(c, GZB_ERR_BAD_ARG, "gzb_candidate_symbol_histograms: ncomp must be 1 or 3");
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_candidate_symbol_histograms: no candidate coefficients");
   if (!dc_hist48 || !ac_hist768) return fail(c, GZB_ERR_BAD_ARG, "gzb_candidate_symbol_histograms: null argument");
   if (q192) { CK(cudaMemcpyAsync(c->d_q, q192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream2)); c->h2d_bytes += 192 * sizeof(int); }
   const HuffScratch h = huff_scratch(c);
   long long nunits = 0;
-  const HuffLayout L = huff_layout(c, 3, &nunits);
+  const HuffLayout L = huff_layout(c, ncomp, &nunits);
   CK(cudaMemsetAsync(h.hist, 0, (48 + 768) * 4, c->stream2));
   KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_histogram<<<static_cast<unsigned>((nunits + kHuffThreads - 1) / kHuffThreads), kHuffThreads, 0, c->stream2>>>(
       c->d_coef, c->cs, c->d_q, L, nunits, h.hist, h.hist + 48));

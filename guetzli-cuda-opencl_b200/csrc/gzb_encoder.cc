@@ -402,25 +402,31 @@ int ncomp_from_histograms(const Histogram* dc, const Histogram* ac, int nblocks)
 // Codes the resident candidate. dc_hist/ac_hist: its per-component histograms if the caller has them
 // (the back end maintains them incrementally), else they are counted on the device.
 bool device_code_candidate(gzb_ctx* ctx, int w, int h, int nblocks, const int q[3][64], bool input_tables,
-                           const Histogram* dc_hist, const Histogram* ac_hist, DeviceJpeg* out) {
+                           const Histogram* dc_hist, const Histogram* ac_hist, DeviceJpeg* out, bool yuv420 = false) {
   Histogram hd[3], ha[3];
-  if (!dc_hist || !ac_hist) {
+  auto count_on_device = [&](int ncomp) {
     uint32_t dc[48], ac[768];
-    if (gzb_candidate_symbol_histograms(ctx, nullptr, dc, ac) != GZB_OK) return false;
+    if (gzb_candidate_symbol_histograms_n(ctx, nullptr, ncomp, dc, ac) != GZB_OK) return false;
     for (int c = 0; c < 3; ++c) {
       histogram_from_counts(dc + 16 * c, 16, &hd[c]);
       histogram_from_counts(ac + 256 * c, 256, &ha[c]);
     }
     dc_hist = hd;
     ac_hist = ha;
-  }
+    return true;
+  };
+  if ((!dc_hist || !ac_hist) && !count_on_device(3)) return false;
   Frame f;
   f.width = w; f.height = h; f.bw = (w + 7) / 8; f.bh = (h + 7) / 8;
+  f.yuv420 = yuv420;
   if (input_tables) {
     f.ncomp = 3;
     gzb::jpeg::frame_set_quant_input(&f, q);
   } else {
     f.ncomp = ncomp_from_histograms(dc_hist, ac_hist, nblocks);
+    // a 4:2:0 candidate without chroma is written as a plain grey file: its luma DC differences then
+    // follow image block order instead of MCU order
+    if (yuv420 && f.ncomp == 1 && !count_on_device(1)) return false;
     gzb::jpeg::frame_set_quant(&f, q);
   }
   gzb::jpeg::CodeTable dct[3], act[3];
@@ -516,6 +522,23 @@ class PooledArray {
 // ---- encoder state ----------------------------------------------------------------------------
 struct Encoder {
   int w = 0, h = 0, bw = 0, bh = 0, nb = 0;
+  // Coefficient arrays per component (orig / idx): 4:4:4 = bw x bh blocks each; after the 4:2:0
+  // downsampling the luma plane is MCU-padded (2*ceil(w/16) x 2*ceil(h/16)) and the chroma planes have
+  // ceil(w/16) x ceil(h/16) blocks (the layout of JPEGData after SaveToJpegData).
+  bool yuv420 = false;
+  int cbw[3] = {0, 0, 0}, cbh[3] = {0, 0, 0};
+  size_t cnb[3] = {0, 0, 0};
+  bool try_420 = false, force_420 = false;   // Params (guetzli/processor.h:34-42)
+  void set_geometry(bool m420) {
+    yuv420 = m420;
+    const int mcw = (w + 15) / 16, mch = (h + 15) / 16;
+    for (int c = 0; c < 3; ++c) {
+      cbw[c] = !m420 ? bw : (c == 0 ? 2 * mcw : mcw);
+      cbh[c] = !m420 ? bh : (c == 0 ? 2 * mch : mch);
+      cnb[c] = static_cast<size_t>(cbw[c]) * cbh[c];
+    }
+  }
+  const char* frame_type() const { return yuv420 ? "f112222" : "f111111"; }   // OutputImage::FrameTypeStr
   int nthreads = 1;
   std::unique_ptr<gzb::WorkerPool> pool;
   gzb::jpeg::WriteTimers wt;
@@ -580,8 +603,10 @@ struct Encoder {
         magic[c][k] = (uint64_t(1) << 32) / static_cast<uint32_t>(q[c][k]) + 1;
         small = small && q[c][k] < (1 << 16);
       }
-    parallel_rows(nb, use_pool, [&](int b0, int b1) {
+    const int nbmax = static_cast<int>(std::max(cnb[0], std::max(cnb[1], cnb[2])));
+    parallel_rows(nbmax, use_pool, [&](int b0_, int b1_) {
       for (int c = 0; c < 3; ++c) {
+        const int b0 = std::min<int>(b0_, static_cast<int>(cnb[c])), b1 = std::min<int>(b1_, static_cast<int>(cnb[c]));
         const int16_t* o = orig[c].data();
         int16_t* ix = out3[c].data();
         if (!small) {
@@ -829,7 +854,9 @@ int gzb_write_candidate_jpeg(gzb_ctx* ctx, const int* q192, int input_tables, ui
     histogram_from_counts(ac + 256 * c, 256, &ha[c]);
   }
   DeviceJpeg dj;
-  if (!device_code_candidate(ctx, w, h, ((w + 7) / 8) * ((h + 7) / 8), q, input_tables != 0, hd, ha, &dj)) return GZB_ERR_CUDA;
+  int factor = 1;
+  gzb_component_dims(ctx, 1, nullptr, nullptr, &factor);
+  if (!device_code_candidate(ctx, w, h, ((w + 7) / 8) * ((h + 7) / 8), q, input_tables != 0, hd, ha, &dj, factor == 2)) return GZB_ERR_CUDA;
   *size_out = dj.size();
   if (out && cap >= dj.size()) {
     std::string bytes;
@@ -968,6 +995,7 @@ int gzb_encoder_create(int device, const uint8_t* rgb, int width, int height, fl
   enc->t_start = now_ms();
   Encoder& e = enc->e;
   e.w = width; e.h = height; e.bw = (width + 7) / 8; e.bh = (height + 7) / 8; e.nb = e.bw * e.bh;
+  e.set_geometry(false);
   e.target = butteraugli_target;
   const unsigned hc = std::thread::hardware_concurrency();
   e.nthreads = host_threads > 0 ? host_threads : static_cast<int>(std::max(1u, std::min(16u, hc)));
@@ -1003,6 +1031,14 @@ void gzb_encoder_destroy(gzb_encoder* enc) {
 }
 
 gzb_ctx* gzb_encoder_context(gzb_encoder* enc) { return enc ? enc->e.ctx : nullptr; }
+
+int gzb_encoder_set_params(gzb_encoder* enc, int try_420, int force_420) {
+  if (!enc) return GZB_ERR_BAD_ARG;
+  if (enc->e.ran) { g_encode_err = "gzb_encoder_set_params: the encoder has already run"; return GZB_ERR_STATE; }
+  enc->e.try_420 = try_420 != 0;
+  enc->e.force_420 = force_420 != 0;
+  return GZB_OK;
+}
 
 int gzb_encoder_set_group(gzb_encoder* enc, int rank, int world, gzb_allgather_fn allgather, void* user) {
   if (!enc || world < 1 || rank < 0 || rank >= world || (world > 1 && !allgather)) {
@@ -1049,13 +1085,14 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   // ---- the original + SelectQuantMatrix (processor.cc:310-372, 986-1003) ----
   // Trials are evaluated one per rank of the group (gzb_quant_search.h) and visited in the
   // reference's order; with a group of one this is the reference's sequential loop.
-  int best_q[3][64];
-  {
+  // mode: 0 = the original, then the search (the 4:4:4 pass); 1 = the original only (before a forced
+  // downsampling); 2 = the search of a downsampled image (no original, generator starts at score 0).
+  auto select_quant = [&](const int mode, int best_q[3][64]) -> int {
     const double t_search = now_ms();
     // TryQuantMatrix (processor.cc:279-308) entirely on the device: quantise + IDCT, Huffman-code the
     // candidate (its size is what the search needs), Compare. The scan is kept (unstuffed) so that
     // the file can be assembled if this trial turns out to be the best so far.
-    gzb::QuantSearch search(e.group, e.target, 1);
+    gzb::QuantSearch search(e.group, e.target, 1, mode);
     auto evaluate = [&](const std::vector<gzb::Trial>& ts, std::vector<gzb::TrialOutcome>* os) -> bool {
       for (size_t j = 0; j < ts.size(); ++j) {
         const gzb::Trial& t = ts[j];
@@ -1064,7 +1101,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         if (t.original ? gzb_copy_from_jpeg(e.ctx, &ones[0][0]) != GZB_OK : !e.set_global_quant_device(t.q)) return false;
         if (!e.compare_begin()) return false;   // the Compare runs while the file is coded on the second stream
         DeviceJpeg dj;
-        if (!device_code_candidate(e.ctx, width, height, e.nb, t.q, t.original != 0, nullptr, nullptr, &dj)) return false;
+        if (!device_code_candidate(e.ctx, width, height, e.nb, t.q, t.original != 0, nullptr, nullptr, &dj, e.yuv420)) return false;
         ++e.code_gen;
         o.scan_bytes = dj.scan_bytes;
         o.ff_bytes = dj.ff_bytes;
@@ -1088,7 +1125,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       if (t.original) {
         e.log("Original Out[%7zd]", static_cast<size_t>(o.jpg_size));
       } else {
-        e.log("Iter %2d: f111111 GQ[%5.2f] Out[%7zd]", e.st.num_iterations + 1, quant_heuristic_score(t.q),
+        e.log("Iter %2d: %s GQ[%5.2f] Out[%7zd]", e.st.num_iterations + 1, e.frame_type(), quant_heuristic_score(t.q),
               static_cast<size_t>(o.jpg_size));
         ++e.st.num_iterations;
       }
@@ -1101,20 +1138,29 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       if (g_encode_err.empty()) g_encode_err = "gzb_encoder_run: the group exchange failed";
       return GZB_ERR_CUDA;
     }
-    e.st.search_wall_ms = now_ms() - t_search;
-    e.search_rounds = search.rounds();
-    e.search_trials = search.evaluated_total();
+    e.st.search_wall_ms += now_ms() - t_search;
+    e.search_rounds += search.rounds();
+    e.search_trials += search.evaluated_total();
+    if (mode == 1) return GZB_OK;
     const QuantData& best = search.best();
-    memcpy(best_q, best.q, sizeof(best_q));
+    memcpy(best_q, best.q, 192 * sizeof(int));
     if (!best.dist_ok)
       for (int c = 0; c < 3; ++c) for (int k = 0; k < 64; ++k) best_q[c][k] = 1;
-  }
-  if (!e.set_global_quant(best_q)) return fail(GZB_ERR_CUDA);
+    return GZB_OK;
+  };
 
-  // ---- SelectFrequencyMasking(jpg, img, 7, 1.0, false) (processor.cc:559-721) ----
-  const int comp_mask = 7;
-  const double target_mul = 1.0;
-  const int num_blocks = e.nb;
+  // ---- SelectFrequencyMasking(jpg, img, comp_mask, target_mul, stop_early) (processor.cc:559-919) ----
+  // Returns 1 when this rank of a group has nothing left to do (the back end runs on rank 0).
+  auto select_frequency_masking = [&](const int comp_mask, const double target_mul, const bool stop_early) -> int {
+  // units of the pass: 8x8 blocks, or the 16x16 macro-blocks of the sub-sampled chroma planes
+  const int factor = (e.yuv420 && (comp_mask & 6)) ? 2 : 1;
+  const int pass_bw = (width + 8 * factor - 1) / (8 * factor), pass_bh = (height + 8 * factor - 1) / (8 * factor);
+  const int num_blocks = pass_bw * pass_bh;
+  // coefficient block of unit b in the searched planes (the 4:2:0 luma plane is MCU-padded)
+  const int first_c = (comp_mask & 1) ? 0 : 1;
+  const bool remap = e.cbw[first_c] != pass_bw;
+  const int coef_bw = e.cbw[first_c];
+  auto cblock = [&](int b) -> size_t { return remap ? static_cast<size_t>(b / pass_bw) * coef_bw + b % pass_bw : static_cast<size_t>(b); };
   std::vector<int> cand_offsets(num_blocks + 1);
   std::vector<uint8_t> cand_coeffs;
   std::vector<float> cand_errors;
@@ -1128,14 +1174,26 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   } prep;
   std::thread prep_thread;
   struct PrepJoin { std::thread& t; ~PrepJoin() { if (t.joinable()) t.join(); } } prep_join{prep_thread};
+  int back_ncomp = 3;   // jpg.components.size() of the back end: the components SaveToJpegData keeps
   if (e.group.rank == 0) {
+    back_ncomp = e.ncomp_for_output();
+    if (e.yuv420) {
+      // MCU-order DC differences and padded luma blocks: counted by the device coder's histogram kernel
+      uint32_t dc[48], ac[768];
+      if (gzb_candidate_symbol_histograms_n(e.ctx, nullptr, back_ncomp, dc, ac) != GZB_OK) return fail(GZB_ERR_CUDA);
+      for (int c = 0; c < 3; ++c) {
+        histogram_from_counts(dc + 16 * c, 16, &prep.dc_hist[c]);
+        histogram_from_counts(ac + 256 * c, 256, &prep.ac_hist[c]);
+      }
+    }
     prep_thread = std::thread([&] {
       Frame f;
-      f.width = width; f.height = height; f.bw = e.bw; f.bh = e.bh; f.ncomp = e.ncomp_for_output();
+      f.width = width; f.height = height; f.bw = e.bw; f.bh = e.bh; f.ncomp = back_ncomp;
+      f.yuv420 = e.yuv420;
       for (int c = 0; c < 3; ++c) f.coeffs[c] = e.idx[c].data();
       gzb::jpeg::frame_set_quant(&f, e.quant);
       prep.header_size = static_cast<int>(gzb::jpeg::header_size(f));
-      gzb::jpeg::build_histograms(f, prep.dc_hist, prep.ac_hist, e.pool.get());   // the components SaveToJpegData keeps
+      if (!e.yuv420) gzb::jpeg::build_histograms(f, prep.dc_hist, prep.ac_hist, e.pool.get());
       {  // EstimateDCSize (processor.cc:548-555)
         Histogram tmp[3] = {prep.dc_hist[0], prep.dc_hist[1], prep.dc_hist[2]};
         size_t num = f.ncomp;
@@ -1144,10 +1202,12 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         prep.dc_size = static_cast<int>(gzb::jpeg::cluster_histograms(tmp, &num, ix, dd));
       }
       // zig-zag non-zero masks of every block: a coefficient flip then touches O(1) symbols
-      for (int c = 0; c < 3; ++c) prep.zmask[c].resize(num_blocks);
-      parallel_rows(num_blocks, e.pool.get(), [&](int b0, int b1) {
+      for (int c = 0; c < 3; ++c) prep.zmask[c].resize(e.cnb[c]);
+      const int nbmax = static_cast<int>(std::max(e.cnb[0], std::max(e.cnb[1], e.cnb[2])));
+      parallel_rows(nbmax, e.pool.get(), [&](int b0, int b1) {
         for (int c = 0; c < 3; ++c)
-          for (int b = b0; b < b1; ++b) prep.zmask[c][b] = gzb::jpeg::zigzag_nonzero_mask(e.idx[c].data() + static_cast<size_t>(b) * 64);
+          for (int b = b0; b < std::min<int>(b1, static_cast<int>(e.cnb[c])); ++b)
+            prep.zmask[c][b] = gzb::jpeg::zigzag_nonzero_mask(e.idx[c].data() + static_cast<size_t>(b) * 64);
       });
     });
   }
@@ -1173,7 +1233,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
     }
     cand_coeffs.resize(ncand);
     cand_errors.resize(ncand);
-    e.st.device_zeroing_ms = gzb_last_device_ms(e.ctx);
+    e.st.device_zeroing_ms += gzb_last_device_ms(e.ctx);
     if (world == 1) {
       cand_offsets = loc_off;
     } else {
@@ -1219,26 +1279,12 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         memcpy(cand_coeffs.data() + base[r], src + maxn * 4, n);
       }
     }
-    e.st.zeroing_wall_ms = now_ms() - t0;
+    e.st.zeroing_wall_ms += now_ms() - t0;
     gzb_finish_block_comparisons(e.ctx);
   }
 
   // The back end is one sequential walk: rank 0 of a group finishes the image alone.
-  if (e.group.rank != 0) {
-    e.st.launches = gzb_launch_count(e.ctx);
-    gzb_get_transfer_bytes(e.ctx, &e.st.h2d_bytes, &e.st.d2h_bytes);
-    e.st.run_ms = now_ms() - t_start;
-    e.st.total_wall_ms = e.st.prepare_ms + e.st.run_ms;
-    e.st.search_rounds = e.search_rounds;
-    e.st.search_trials = e.search_trials;
-    *jpeg_out = static_cast<uint8_t*>(malloc(1));
-    if (stats) *stats = e.st;
-    if (trace_out) {
-      *trace_out = static_cast<char*>(malloc(e.trace.size() + 1));
-      memcpy(*trace_out, e.trace.c_str(), e.trace.size() + 1);
-    }
-    return GZB_OK;
-  }
+  if (e.group.rank != 0) return 1;
 
   // ---- SelectFrequencyBackEnd (processor.cc:723-919) ----
   {
@@ -1319,13 +1365,15 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
     const int n_ccoef = static_cast<int>(cand_coeffs.size());
     for (int direction : directions) {
       for (;;) {
+        // down-adjusting only makes the output larger (processor.cc:766-774)
+        if (stop_early && direction == -1 && prev_size > 1.01 * e.best_jpeg.size()) break;
         int blocks_to_change = 0;
         double tt = now_ms();
         for (int rblock = 1; rblock <= 4; ++rblock) {
           // distmap is all zeros until the first iteration has compared (processor.cc:777-780)
           if (first_up_iter && gzb_clear_distmap(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
-          if (gzb_compute_block_error_adjustment_weights(e.ctx, direction, rblock, target_mul, nullptr,
-                                                         block_weight.data()) != GZB_OK) return fail(GZB_ERR_CUDA);
+          if (gzb_compute_block_error_adjustment_weights_f(e.ctx, direction, rblock, target_mul, factor, nullptr,
+                                                           block_weight.data()) != GZB_OK) return fail(GZB_ERR_CUDA);
           { const double t1 = now_ms(); e.st.be_weights_ms += t1 - tt; tt = t1; }
           // global_order in block order (processor.cc:786-813), built in parallel: count, then fill
           {
@@ -1386,7 +1434,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         // another rank evaluated, so the context's own last distance must not be used)
         if (direction > 0 && static_cast<double>(e.distance) <= 1.0 * static_cast<double>(e.target)) rel_size_delta = 0.05;
         const double min_size_delta = base_size * rel_size_delta;
-        const float coeffs_to_change_per_block = direction > 0 ? 2.0f : 1 * 1 * 0.2f;
+        const float coeffs_to_change_per_block = direction > 0 ? 2.0f : factor * factor * 0.2f;
         int min_coeffs_to_change = static_cast<int>(coeffs_to_change_per_block * blocks_to_change);
         if (first_up_iter) {
           const float limit = 0.75f * gzb_block_error_limit(e.ctx);
@@ -1453,11 +1501,12 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
                   const int cidx = candidates[last_idx + std::min(direction, 0)];
                   const int c = cidx / 64, k = cidx % 64, z = gzb::jpeg::kZigZag[k];
                   const int* qc = e.quant[c];
-                  int16_t* blk_idx = e.idx[c].data() + static_cast<size_t>(b) * 64;
-                  const int16_t newval = direction > 0 ? 0 : quantize_coeff(e.orig[c][static_cast<size_t>(b) * 64 + k], qc[k]);
+                  const size_t cb = cblock(b);
+                  int16_t* blk_idx = e.idx[c].data() + cb * 64;
+                  const int16_t newval = direction > 0 ? 0 : quantize_coeff(e.orig[c][cb * 64 + k], qc[k]);
                   const int16_t new_idx = static_cast<int16_t>(newval / qc[k]);
                   const int16_t old_idx = blk_idx[k];
-                  uint64_t& m = zmask[c][b];
+                  uint64_t& m = zmask[c][cb];
                   const uint64_t lower = m & ((1ULL << z) - 1);
                   const int p = lower ? 63 - __builtin_clzll(lower) : 0;
                   const uint64_t upper = z < 63 ? (m >> (z + 1)) : 0;
@@ -1482,7 +1531,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
                   emit(new_idx, 1);
                   blk_idx[k] = new_idx;
                   if (new_idx != 0) m |= 1ULL << z; else m &= ~(1ULL << z);
-                  L.block.push_back(b); L.cidx.push_back(static_cast<uint8_t>(cidx)); L.val.push_back(newval);
+                  L.block.push_back(static_cast<int32_t>(cb)); L.cidx.push_back(static_cast<uint8_t>(cidx)); L.val.push_back(newval);
                   last_indexes[b] += direction;
                 }
               }
@@ -1536,10 +1585,11 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
             const int po = std::max(0, std::min(cand_offsets[pb], n_ccoef - 1));
             const int pi = cand_coeffs[po + std::max(0, last_indexes[pb] + std::min(direction, 0))];
             const int pc = pi >> 6;
-            __builtin_prefetch(&zmask[pc][pb]);
-            __builtin_prefetch(e.idx[pc].data() + static_cast<size_t>(pb) * 64);
-            __builtin_prefetch(e.idx[pc].data() + static_cast<size_t>(pb) * 64 + 32);
-            if (direction < 0) __builtin_prefetch(e.orig[pc].data() + static_cast<size_t>(pb) * 64 + (pi & 63));
+            const size_t pcb = cblock(pb);
+            __builtin_prefetch(&zmask[pc][pcb]);
+            __builtin_prefetch(e.idx[pc].data() + pcb * 64);
+            __builtin_prefetch(e.idx[pc].data() + pcb * 64 + 32);
+            if (direction < 0) __builtin_prefetch(e.orig[pc].data() + pcb * 64 + (pi & 63));
           }
           const int b = global_order[i].first;
           const int last_idx = last_indexes[b];
@@ -1548,14 +1598,15 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           const int cidx = candidates[last_idx + std::min(direction, 0)];
           const int c = cidx / 64, k = cidx % 64, z = gzb::jpeg::kZigZag[k];
           const int* qc = e.quant[c];
-          int16_t* blk_idx = e.idx[c].data() + static_cast<size_t>(b) * 64;
-          const int16_t newval = direction > 0 ? 0 : quantize_coeff(e.orig[c][static_cast<size_t>(b) * 64 + k], qc[k]);
+          const size_t cb = cblock(b);
+          int16_t* blk_idx = e.idx[c].data() + cb * 64;
+          const int16_t newval = direction > 0 ? 0 : quantize_coeff(e.orig[c][cb * 64 + k], qc[k]);
           const int16_t new_idx = static_cast<int16_t>(newval / qc[k]);
           const int16_t old_idx = blk_idx[k];
           // UpdateACHistogram(-1, old block); UpdateACHistogram(+1, new block) (processor.cc:491-515,
           // 871-873) restricted to the symbols that differ: those between the previous (p) and the
           // next (n) non-zero coefficient around zig-zag position z.
-          uint64_t& m = zmask[c][b];
+          uint64_t& m = zmask[c][cb];
           if (ulog) ulog->push_back(UndoRec{b, static_cast<uint8_t>(c), static_cast<uint8_t>(k), old_idx, m, touched[b] == 0,
                                             static_cast<uint32_t>(dlog->size())});
           const uint64_t lower = m & ((1ULL << z) - 1);
@@ -1588,7 +1639,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           emit(new_idx, 1);
           blk_idx[k] = new_idx;
           if (new_idx != 0) m |= 1ULL << z; else m &= ~(1ULL << z);
-          job->block.push_back(b); job->cidx.push_back(static_cast<uint8_t>(cidx)); job->val.push_back(newval);
+          job->block.push_back(static_cast<int32_t>(cb)); job->cidx.push_back(static_cast<uint8_t>(cidx)); job->val.push_back(newval);
           last_indexes[b] += direction;
           if (!touched[b]) { touched[b] = 1; touched_list.push_back(b); }
           ++changed_coeffs;
@@ -1704,8 +1755,8 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
                 for (size_t j = dlog.size(); j-- > ulog[keep].delta_begin;) ac_hist[dlog[j].c].add(dlog[j].sym, -dlog[j].w);
                 for (size_t j = ulog.size(); j-- > keep;) {
                   const UndoRec& u = ulog[j];
-                  e.idx[u.c][static_cast<size_t>(u.block) * 64 + u.k] = u.old_idx;
-                  zmask[u.c][u.block] = u.old_mask;
+                  e.idx[u.c][cblock(u.block) * 64 + u.k] = u.old_idx;
+                  zmask[u.c][cblock(u.block)] = u.old_mask;
                   last_indexes[u.block] -= direction;
                   if (u.newly_touched) { touched[u.block] = 0; touched_list.pop_back(); }
                   job->block.pop_back(); job->cidx.pop_back(); job->val.pop_back();
@@ -1740,14 +1791,14 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         // (processor.cc:897-915, MaybeOutput 151-160)
         const double tw = now_ms();
         DeviceJpeg dj;
-        if (!device_code_candidate(e.ctx, width, height, e.nb, e.quant, false, dc_hist, ac_hist, &dj)) return fail(GZB_ERR_CUDA);
+        if (!device_code_candidate(e.ctx, width, height, e.nb, e.quant, false, dc_hist, ac_hist, &dj, e.yuv420)) return fail(GZB_ERR_CUDA);
         ++e.code_gen;
         e.st.num_jpeg_writes++;
         e.st.device_write_ms += now_ms() - tw;
         if (!e.compare_end()) return fail(GZB_ERR_CUDA);
         const size_t jpg_size = dj.size();
-        e.log("Iter %2d: f111111(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
-              e.st.num_iterations, comp_mask, direction > 0 ? "up" : "down", changed_coeffs, order_size,
+        e.log("Iter %2d: %s(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
+              e.st.num_iterations, e.frame_type(), comp_mask, direction > 0 ? "up" : "down", changed_coeffs, order_size,
               changed_blocks, blocks_to_change, num_blocks, val_threshold, jpg_size,
               100.0 - (100.0 * est_jpg_size) / jpg_size);
         e.log(" BA[100.00%%] D[%6.4f]", e.distance);
@@ -1763,7 +1814,68 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         prev_size = est_jpg_size;
       }
     }
-    e.st.backend_wall_ms = now_ms() - t_be;
+    e.st.backend_wall_ms += now_ms() - t_be;
+  }
+  return GZB_OK;
+  };
+
+  // ---- the passes of ProcessJpegData (processor.cc:986-1016) ----
+  bool gray = true;   // IsGrayscale(jpg_in) (processor.cc:920-928)
+  for (int c = 1; c < 3 && gray; ++c)
+    for (size_t i = 0; i < e.orig[c].size(); ++i) if (e.orig[c][i] != 0) { gray = false; break; }
+  const int try_420 = (e.force_420 || (e.try_420 && !gray)) ? 1 : 0;
+  const int force_420 = e.force_420 ? 1 : 0;
+  if (try_420 && e.group.world > 1) {
+    g_encode_err = "gzb_encoder_run: the YUV420 passes are not sharded over a group";
+    return GZB_ERR_UNSUPPORTED;
+  }
+  if (force_420 && gray) {
+    g_encode_err = "gzb_encoder_run: force_420 on a grey image (the reference leaves it 4:4:4) is not supported";
+    return GZB_ERR_UNSUPPORTED;
+  }
+  bool idle_rank = false;
+  if (force_420) {   // the original is compared and output before any pass (processor.cc:967-985)
+    const int rc = select_quant(1, nullptr);
+    if (rc != GZB_OK) return rc;
+  }
+  for (int downsample = force_420; downsample <= try_420 && !idle_rank; ++downsample) {
+    int best_q[3][64];
+    if (downsample) {
+      // DownsampleImage + SaveToJpegData on the q=1 input, on the device; the host mirrors follow
+      const double t0 = now_ms();
+      if (gzb_downsample_420(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
+      e.set_geometry(true);
+      for (int c = 0; c < 3; ++c) { e.orig[c].resize(e.cnb[c] * 64); e.idx[c].resize(e.cnb[c] * 64); }
+      if (gzb_get_jpeg_coeffs(e.ctx, e.orig[0].data(), e.orig[1].data(), e.orig[2].data()) != GZB_OK) return fail(GZB_ERR_CUDA);
+      e.st.downsample_ms += now_ms() - t0;
+    }
+    int rc = select_quant(downsample ? 2 : 0, best_q);
+    if (rc != GZB_OK) return rc;
+    if (!e.set_global_quant(best_q)) return fail(GZB_ERR_CUDA);
+    if (!downsample) {
+      rc = select_frequency_masking(7, 1.0, false);
+    } else {
+      rc = select_frequency_masking(1, static_cast<double>(0.97f), false);   // ymul (processor.cc:1011)
+      if (rc == GZB_OK) rc = select_frequency_masking(6, 1.0, true);
+    }
+    if (rc < 0) return rc;
+    idle_rank = rc == 1;
+  }
+  // The back end is one sequential walk: rank 0 of a group finishes the image alone.
+  if (idle_rank) {
+    e.st.launches = gzb_launch_count(e.ctx);
+    gzb_get_transfer_bytes(e.ctx, &e.st.h2d_bytes, &e.st.d2h_bytes);
+    e.st.run_ms = now_ms() - t_start;
+    e.st.total_wall_ms = e.st.prepare_ms + e.st.run_ms;
+    e.st.search_rounds = e.search_rounds;
+    e.st.search_trials = e.search_trials;
+    *jpeg_out = static_cast<uint8_t*>(malloc(1));
+    if (stats) *stats = e.st;
+    if (trace_out) {
+      *trace_out = static_cast<char*>(malloc(e.trace.size() + 1));
+      memcpy(*trace_out, e.trace.c_str(), e.trace.size() + 1);
+    }
+    return GZB_OK;
   }
 
   if (e.best_remote) {
@@ -1809,12 +1921,20 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
 int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
                    int host_threads, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
                    char** trace_out) {
+  return gzb_encode_rgb_params(device, rgb, width, height, butteraugli_target, 0, 0, host_threads, jpeg_out, jpeg_size,
+                               stats, trace_out);
+}
+
+int gzb_encode_rgb_params(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
+                          int try_420, int force_420, int host_threads, uint8_t** jpeg_out, size_t* jpeg_size,
+                          gzb_encode_stats* stats, char** trace_out) {
   if (jpeg_out) *jpeg_out = nullptr;
   if (jpeg_size) *jpeg_size = 0;
   if (trace_out) *trace_out = nullptr;
   gzb_encoder* enc = nullptr;
   int rc = gzb_encoder_create(device, rgb, width, height, butteraugli_target, host_threads, &enc);
   if (rc != GZB_OK) return rc;
+  gzb_encoder_set_params(enc, try_420, force_420);
   rc = gzb_encoder_run(enc, jpeg_out, jpeg_size, stats, trace_out);
   gzb_encoder_destroy(enc);
   return rc;

@@ -449,7 +449,7 @@ void write_jpeg_header(const Frame& f, const Histogram* dc_hist, const Histogram
     out->append(reinterpret_cast<const char*>(h), sizeof(h));
     for (int c = 0; c < ncomp; ++c) {
       out->push_back(static_cast<char>(c));      // component id
-      out->push_back(static_cast<char>(0x11));   // 1x1 sampling
+      out->push_back(static_cast<char>(f.yuv420 && ncomp == 3 && c == 0 ? 0x22 : 0x11));   // h/v sampling factors
       out->push_back(static_cast<char>(f.table_index[f.comp_table[c]]));
     }
   }

@@ -92,6 +92,9 @@ void ac_histogram_add_block(const int16_t* q, int weight, Histogram* h);
 struct Frame {
   int width = 0, height = 0, ncomp = 3;
   int bw = 0, bh = 0;
+  // YUV 4:2:0 (2x2 luma blocks per MCU): only the header is written on the host for such frames --
+  // their scan is coded on the device (gzb_huffman.cuh). With ncomp == 1 the file is a plain grey one.
+  bool yuv420 = false;
   const int16_t* coeffs[3] = {nullptr, nullptr, nullptr};  // quantised indices [bw*bh*64]
   // quantisation tables as the file will carry them
   int num_tables = 0;

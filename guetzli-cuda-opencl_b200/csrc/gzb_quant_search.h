@@ -40,14 +40,15 @@ inline double quant_heuristic_score(const int q[3][64]) {
 
 class QuantGenerator {
  public:
-  QuantGenerator() : a_(-1.0), b_(-1.0), total_csf_(0.0) {
+  // downsample: the search of a YUV420 image starts at heuristic score 0 (processor.cc:224)
+  explicit QuantGenerator(bool downsample = false) : a_(-1.0), b_(-1.0), total_csf_(0.0), downsample_(downsample) {
     for (int k = 0; k < 64; ++k) total_csf_ += 3.0 * contrast_sensitivity(k);
   }
   bool next(int q[3][64]) {
     for (int iter = 0; iter < 1000; ++iter) {
       double hscore;
       if (b_ == -1.0) {
-        if (a_ == -1.0) hscore = total_csf_;
+        if (a_ == -1.0) hscore = downsample_ ? 0.0 : total_csf_;
         else if (a_ < 5.0 * total_csf_) hscore = a_ + total_csf_;
         else hscore = 2 * (a_ + total_csf_);
         if (hscore > 100 * total_csf_) return false;
@@ -94,6 +95,7 @@ class QuantGenerator {
     }
   }
   double a_, b_, total_csf_;
+  bool downsample_;
   std::vector<QuantData> seen_;
 };
 
@@ -136,10 +138,15 @@ class QuantSearch {
   typedef std::function<bool(const std::vector<Trial>&, std::vector<TrialOutcome>*)> EvalFn;
   typedef std::function<void(const Trial&, const TrialOutcome&)> VisitFn;
 
-  QuantSearch(const Group& g, float target, int batch = 1) : g_(g), target_(target), batch_(std::max(1, batch)) {}
+  // mode 0: original, all-ones matrix, generator loop (the 4:4:4 pass of ProcessJpegData);
+  // mode 1: the original only; mode 2: all-ones matrix + generator loop of a downsampled image.
+  QuantSearch(const Group& g, float target, int batch = 1, int mode = 0)
+      : g_(g), target_(target), batch_(std::max(1, batch)), mode_(mode) {}
 
   bool run(const EvalFn& evaluate, const VisitFn& visit) {
     State st;
+    if (mode_ == 2) { st.phase = 1; st.gen = QuantGenerator(true); }
+    st.only_original = mode_ == 1;
     for (;;) {
       Trial t;
       if (!st.next(&t)) break;
@@ -192,7 +199,7 @@ class QuantSearch {
       return false;
     }
     void advance(bool ok, size_t jpg_size) {  // the generator-visible effect of one trial
-      if (phase == 0) { phase = 1; return; }
+      if (phase == 0) { phase = only_original ? 3 : 1; return; }
       if (phase == 1) {
         for (int c = 0; c < 3; ++c) for (int k = 0; k < 64; ++k) last.q[c][k] = 1;
       } else {
@@ -204,6 +211,7 @@ class QuantSearch {
       phase = 2;
     }
     int pending[3][64];
+    bool only_original = false;
   };
   struct Node {
     double p;
@@ -296,7 +304,7 @@ class QuantSearch {
 
   Group g_;
   float target_;
-  int batch_;
+  int batch_, mode_;
   std::vector<Trial> keys_;
   std::vector<TrialOutcome> cache_;
   QuantData best_{};

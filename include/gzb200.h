@@ -138,6 +138,10 @@ int gzb_compute_block_zeroing_candidates_range(gzb_ctx* ctx, int comp_mask, int 
  * raw symbol counts, dc_hist[3][16], ac_hist[3][256]. q192 (may be NULL = the matrix last given to
  * gzb_copy_from_jpeg / gzb_apply_global_quantization) is what the candidate's values are multiples of. */
 int gzb_candidate_symbol_histograms(gzb_ctx* ctx, const int* q192, uint32_t* dc_hist48, uint32_t* ac_hist768);
+/* The same for a file of ncomp components (1: luma only, in image block order -- what a 4:2:0 candidate
+ * whose chroma planes are all zero is written as; 3: the candidate's own MCU order). */
+int gzb_candidate_symbol_histograms_n(gzb_ctx* ctx, const int* q192, int ncomp, uint32_t* dc_hist48,
+                                      uint32_t* ac_hist768);
 /* EncodeScan (jpeg_data_writer.cc:249-359) with the given per-component code tables
  * (dc_code/dc_len[3][16], ac_code/ac_len[3][256]); ncomp is 1 when both chroma planes are all zero
  * (output_image.cc:588), else 3. The scan stays on the device; *scan_bytes is its length before
@@ -231,10 +235,18 @@ typedef struct {
   double device_write_ms;                /* candidate files coded on the device (histograms, codes, scan, fetch) */
   double search_wall_ms, trial_host_ms, trial_device_ms;  /* SelectQuantMatrix phase; host/device legs of its trials */
   int search_rounds, search_trials;      /* SelectQuantMatrix: exchange rounds / trials evaluated by the group */
+  double downsample_ms;                  /* YUV420 passes: DownsampleImage + SaveToJpegData on the device, coefficients fetched */
 } gzb_encode_stats;
 int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
                    int host_threads, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
                    char** trace_out);
+/* guetzli::Process with Params::try_420 / Params::force_420 (guetzli/processor.h:34-42; the passes of
+ * ProcessJpegData, guetzli/processor.cc:986-1016): try_420 runs the 4:4:4 pass and then the YUV420
+ * pass (downsampling, quant search from score 0, frequency masking of luma then of chroma with early
+ * stop) unless the image is grey; force_420 runs the YUV420 pass only. */
+int gzb_encode_rgb_params(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
+                          int try_420, int force_420, int host_threads, uint8_t** jpeg_out, size_t* jpeg_size,
+                          gzb_encode_stats* stats, char** trace_out);
 /* The same encoder in two steps, so that a caller can separate "inputs resident in HBM" from the
  * search: create uploads the image, computes its opsin-dynamics image and the q=1 coefficients;
  * run performs the search (once per encoder). */
@@ -244,6 +256,8 @@ int gzb_encoder_create(int device, const uint8_t* rgb, int width, int height, fl
 int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
                     char** trace_out);
 gzb_ctx* gzb_encoder_context(gzb_encoder* enc);
+/* Params::try_420 / force_420 for a two-step encoder; call before gzb_encoder_run. */
+int gzb_encoder_set_params(gzb_encoder* enc, int try_420, int force_420);
 /* Multi-GPU, one large image: the encoders of a group -- one per GPU, one per
  * process, all created from the SAME image and target -- share the work of one encode.
  *   * SelectQuantMatrix (guetzli/processor.cc:310-372): the independent TryQuantMatrix candidates

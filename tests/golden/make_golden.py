@@ -5,6 +5,7 @@ oracle/_ref/libgzref.so (run where /root/reference is mounted: `python tests/gol
   bees_q95.json        sha256/size/iterations + the verbose trace of guetzli::Process on
                        tests/bees.png at quality 95 -- must equal tests/golden_checksums.txt:3
   synth_encodes.json   sha256/size/iterations of guetzli::Process on seeded synthetic images
+  yuv420_encodes.json  the same with Params::try_420 / force_420 (the YUV420 passes)
   stage_vectors.npz    small stage-level vectors (diffmap, distance, zeroing order) on a 96x64 image
 """
 import hashlib, json, os, sys
@@ -33,6 +34,28 @@ def edge_cases():
                      "trace": iter_lines(trace)}
         print(name, len(jpg), iters)
     json.dump(enc, open(os.path.join(HERE, "edge_encodes.json"), "w"), indent=1)
+
+
+CASES_420 = [("red", 96, 80, 95, "force"), ("red", 100, 75, 90, "force"), ("red", 129, 66, 92, "try"),
+             ("synth", 96, 80, 95, "try"), ("red", 200, 136, 88, "try"), ("synth", 33, 47, 84, "force"),
+             ("bees", 0, 0, 95, "try"), ("bees", 0, 0, 90, "force")]
+
+
+def yuv420_cases():
+    """yuv420_encodes.json: guetzli::Process with Params::try_420 / force_420 (processor.h:34-42):
+    bytes and iteration traces of the reference."""
+    from _libs import image_420, ref_process_params
+    L = ref()
+    enc = {}
+    for (kind, w, h, q, mode) in CASES_420:
+        im = image_420(kind, w, h)
+        t = L.ref_butteraugli_score_for_quality(float(q))
+        jpg, iters, trace = ref_process_params(im, t, try_420=mode == "try", force_420=mode == "force", want_trace=True)
+        name = "%s_%dx%d_q%d_%s" % (kind, im.shape[1], im.shape[0], q, mode)
+        enc[name] = {"sha256": hashlib.sha256(jpg).hexdigest(), "size": len(jpg), "iterations": iters, "target": t,
+                     "trace": iter_lines(trace)}
+        print(name, len(jpg), iters)
+    json.dump(enc, open(os.path.join(HERE, "yuv420_encodes.json"), "w"), indent=1)
 
 
 def main():
@@ -69,5 +92,7 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--edge":
         edge_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "--420":
+        yuv420_cases()
     else:
         main()

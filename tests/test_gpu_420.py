@@ -140,3 +140,53 @@ def test_block_weights_factor2(gz, direction, rblock):
         want = rs.block_weights_f(direction, rblock, 1.0, factor, dm)
         report("weights f%d" % factor, got, want)
     cmp_.close(); rs.close()
+
+
+@pytest.mark.parametrize("kind,w,h", SIZES)
+def test_candidate_jpeg_bytes(gz, kind, w, h):
+    """SaveToJpegData + WriteJpeg of a 4:2:0 candidate (2x2 MCUs, MCU-padded luma, SOF sampling 0x22):
+    header on the host, scan Huffman-coded on the device -- the reference's bytes."""
+    img, cmp_, rs = make(gz, kind, w, h)
+    q = quant_matrix(5)
+    cmp_.CopyFromJpegData(); cmp_.ApplyGlobalQuantization(q)
+    rs.reset(); rs.apply_quant(q)
+    want = rs.write_jpeg()
+    n, got = cmp_.WriteJpeg(q)
+    assert n == len(want)
+    assert got == want
+    cmp_.close(); rs.close()
+
+
+def trace_records(lines):
+    out = []
+    for l in lines:
+        out.append((l.split("Out[")[1].split("]")[0].strip(), l.split("D[")[1].split("]")[0].strip()))
+    return out
+
+
+GOLD_420 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "yuv420_encodes.json")
+
+
+def _gold_420():
+    return json.load(open(GOLD_420)) if os.path.exists(GOLD_420) else {}
+
+
+@pytest.mark.parametrize("name", sorted(_gold_420().keys()))
+def test_encode_420_golden(gz, name):
+    """guetzli::Process with try_420 / force_420: bytes and iteration trace of the reference
+    (tests/golden/yuv420_encodes.json, generated by tests/golden/make_golden.py --420)."""
+    gold = _gold_420()[name]
+    kind, size, q, mode = name.split("_")
+    w, h = (int(v) for v in size.split("x"))
+    img = image_420(kind, w, h)
+    jpg, st, trace = gz.Process(img, np.float32(gold["target"]), want_trace=True,
+                                try_420=mode == "try", force_420=mode == "force")
+    got = trace_records([l for l in trace.splitlines() if "Out[" in l])
+    want = trace_records(gold["trace"])
+    first_bad = next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), None)
+    assert first_bad is None and len(got) == len(want), \
+        "trace diverges at record %s: got %s want %s" % (first_bad, got[first_bad:first_bad + 2] if first_bad is not None else len(got),
+                                                         want[first_bad:first_bad + 2] if first_bad is not None else len(want))
+    assert len(jpg) == gold["size"]
+    assert hashlib.sha256(jpg).hexdigest() == gold["sha256"]
+    assert st["num_iterations"] == gold["iterations"]
