@@ -1028,6 +1028,44 @@ int gzb_compare_block(gzb_ctx* c, int block_x, int block_y, const int16_t* candi
   GZB_END(c)
 }
 
+int gzb_compare_block_srgb(gzb_ctx* c, int block_x, int block_y, const uint8_t* rgb192, double* err) {
+  GZB_TRY(c)
+  if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_compare_block_srgb: StartBlockComparisons not called");
+  if (!rgb192 || !err || block_x < 0 || block_x >= c->bw || block_y < 0 || block_y >= c->bh)
+    return fail(c, GZB_ERR_BAD_ARG, "gzb_compare_block_srgb: bad argument");
+  uint8_t* d_win = c->d_upd;  // 192 bytes of the update staging area
+  CK(cudaMemcpyAsync(d_win, rgb192, 192, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += 192;
+  KLAUNCH(c, KC_ZEROING, k_compare_block_rgb<<<1, 32, 0, c->stream>>>(d_win, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, block_x, block_y,
+                                                                     c->d_mask_scale, c->d_block_err));
+  CK(cudaMemcpyAsync(c->h_pinned, c->d_block_err, sizeof(float), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 4;
+  sync_check(c);
+  *err = static_cast<double>(c->h_pinned[0]);
+  GZB_END(c)
+}
+
+int gzb_set_sampling(gzb_ctx* c, int chroma_factor) {
+  if (!c) return GZB_ERR_BAD_ARG;
+  if (chroma_factor != 1 && chroma_factor != 2) return fail(c, GZB_ERR_BAD_ARG, "gzb_set_sampling: factor must be 1 or 2");
+  const bool m = chroma_factor == 2;
+  if (m != c->mode420) { c->mode420 = m; c->have_coeffs = false; c->have_orig_coeffs = false; c->packed_valid = false; }
+  return GZB_OK;
+}
+
+int gzb_set_jpeg_coeffs_420(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const int16_t* c2) {
+  GZB_TRY(c)
+  if (!c0 || !c1 || !c2) return fail(c, GZB_ERR_BAD_ARG, "gzb_set_jpeg_coeffs_420: null argument");
+  if (!c->mode420) { c->mode420 = true; c->have_coeffs = false; }
+  const int16_t* src[3] = {c0, c1, c2};
+  for (int k = 0; k < 3; ++k) {
+    const size_t n2 = comp_blocks(c, k) * 64 * 2;
+    CK(cudaMemcpyAsync(c->d_orig + k * c->cs, src[k], n2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += n2;
+  }
+  sync_check(c);
+  c->have_orig_coeffs = true;
+  c->packed_valid = false;
+  GZB_END(c)
+}
+
 int gzb_compute_block_zeroing_order(gzb_ctx* c, int comp_mask, gzb_coeff_data* out) {
   GZB_TRY(c)
   if (!c->block_cmp) return fail(c, GZB_ERR_STATE, "gzb_compute_block_zeroing_order: StartBlockComparisons not called");

@@ -105,8 +105,13 @@ __device__ __forceinline__ void warp_candidate_idct(ZeroWarpSmem& s, const int* 
   __syncwarp();
 }
 
-// CompareBlock (guetzli/butteraugli_comparator.cc:113-163) of the 8x8 window whose Y / Cb / Cr samples
-// are pY / pCb / pCr (64 bytes each) against the original block in s.pg0. Returns the error in all lanes.
+// CompareBlock (guetzli/butteraugli_comparator.cc:113-163) from the point where the candidate window is
+// linear rgb in s.bufA ([c*64 + 8y + x]), against the original block in s.pg0. Returns the error in
+// all lanes.
+__device__ __forceinline__ float warp_compare_linear(ZeroWarpSmem& s, const float scale[3], double csf_a, double csf_b,
+                                                     int lane);
+
+// The same from the window's Y / Cb / Cr samples pY / pCb / pCr (64 bytes each).
 __device__ __forceinline__ float warp_compare_pixels(ZeroWarpSmem& s, const float* lut, const unsigned char* pY,
                                                      const unsigned char* pCb, const unsigned char* pCr,
                                                      int vx, int vy, const float scale[3],
@@ -122,6 +127,11 @@ __device__ __forceinline__ float warp_compare_pixels(ZeroWarpSmem& s, const floa
     s.bufA[128 + p] = lut[b];
   }
   __syncwarp();
+  return warp_compare_linear(s, scale, csf_a, csf_b, lane);
+}
+
+__device__ __forceinline__ float warp_compare_linear(ZeroWarpSmem& s, const float scale[3], double csf_a, double csf_b,
+                                                     int lane) {
   warp_block_opsin(s.bufA, s.bufB, s.cx, lane);
   // MaskHighIntensityChange(8, 8, orig, cand) -> fa (bufA), fb (bufB)
 #pragma unroll
@@ -386,6 +396,40 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
     }
     __syncwarp();
   }
+}
+
+// Comparator::CompareBlock for a caller-rendered window: rgb192 = the 8x8 window of the candidate as
+// interleaved sRGB8 (OutputImage::ToSRGB(xmin, ymin, 8, 8), any chroma sampling), compared against the
+// original's block (bx, by). One warp. -> err_out[0]
+__global__ void __launch_bounds__(32)
+k_compare_block_rgb(const uint8_t* __restrict__ rgb192, const uint8_t* __restrict__ rgb_planes, size_t plane_stride,
+                    int P, int W, int H, int bw, int bx, int by, const float* __restrict__ mask_scale,
+                    float* __restrict__ err_out) {
+  __shared__ ZeroWarpSmem s;
+  const float* lut = g_tab.srgb_lin;
+  const int lane = threadIdx.x;
+  const double csf_a = kCsf8x8[4 + lane], csf_b = kCsf8x8[36];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = lane + 32 * h;
+    const int x = min(8 * bx + (p & 7), W - 1), y = min(8 * by + (p >> 3), H - 1);
+    const size_t g = static_cast<size_t>(y) * P + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s.bufA[64 * c + p] = lut[rgb_planes[c * plane_stride + g]];
+  }
+  __syncwarp();
+  warp_block_opsin(s.bufA, s.bufB, s.pg0, lane);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = lane + 32 * h;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s.bufA[64 * c + p] = lut[rgb192[3 * p + c]];
+  }
+  __syncwarp();
+  const int blk = by * bw + bx;
+  const float scale[3] = {mask_scale[3 * blk], mask_scale[3 * blk + 1], mask_scale[3 * blk + 2]};
+  const float e = warp_compare_linear(s, scale, csf_a, csf_b, lane);
+  if (lane == 0) err_out[0] = e;
 }
 
 }  // namespace gzb

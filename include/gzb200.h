@@ -113,6 +113,12 @@ int gzb_compare_blocks(gzb_ctx* ctx, float* err_out);
  * launch per call -- correct but latency-bound; the batched call below is the fast path.
  * (guetzli/butteraugli_comparator.cc:85-163) */
 int gzb_compare_block(gzb_ctx* ctx, int block_x, int block_y, const int16_t* candidate192, double* err);
+/* Comparator::CompareBlock for any chroma sampling: rgb192 is the candidate's 8x8 window at block
+ * (block_x, block_y) of the 8x8 grid as interleaved sRGB8 -- OutputImage::ToSRGB(8*block_x, 8*block_y,
+ * 8, 8) (guetzli/output_image.cc:642-701), which the caller renders from its own OutputImage. With
+ * SwitchBlock(bx, by, fx, fy) and CompareBlock(img, off_x, off_y, ...) the block is (bx*fx + off_x,
+ * by*fy + off_y) (guetzli/butteraugli_comparator.cc:113-122). One tiny launch per call. */
+int gzb_compare_block_srgb(gzb_ctx* ctx, int block_x, int block_y, const uint8_t* rgb192, double* err);
 /* cuComputeBlockZeroingOrder (clguetzli/cuguetzli.h:30-40) == the per-block loop of
  * Processor::SelectFrequencyMasking over ComputeBlockZeroingOrder (guetzli/processor.cc:376-487,
  * 638-672), MODE_CPU semantics. out: nblocks*192 records, zero-filled, packed from slot 0 in
@@ -186,6 +192,13 @@ int gzb_compute_block_error_adjustment_weights_f(gzb_ctx* ctx, int direction, in
  * factor-2 image (UpdatePixelsForBlock's fancy upsampling, guetzli/output_image.cc:147-210).
  * gzb_set_jpeg_coeffs returns the context to 4:4:4. */
 int gzb_downsample_420(gzb_ctx* ctx);
+/* Switches the context between 4:4:4 (chroma_factor 1) and 4:2:0 (2) without touching any data: a
+ * caller that owns the OutputImage (the Comparator adaptor) then sends coefficients in the layout above
+ * with gzb_set_coeffs / gzb_set_jpeg_coeffs_420. Invalidates the resident coefficients on a change. */
+int gzb_set_sampling(gzb_ctx* ctx, int chroma_factor);
+/* JPEGData of a 4:2:0 image (jpg.components[c].coeffs; luma 2*ceil(w/16) x 2*ceil(h/16) blocks, chroma
+ * ceil(w/16) x ceil(h/16)) as the input coefficients; switches the context to 4:2:0. */
+int gzb_set_jpeg_coeffs_420(gzb_ctx* ctx, const int16_t* c0, const int16_t* c1, const int16_t* c2);
 /* Blocks per row / column of component comp's coefficient arrays and its sampling factor. */
 int gzb_component_dims(const gzb_ctx* ctx, int comp, int* blocks_w, int* blocks_h, int* factor);
 /* The input coefficients (jpg.components[c].coeffs after SaveToJpegData); NULL skips a component. */

@@ -4,6 +4,7 @@
 #include <cassert>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "guetzli/debug_print.h"
 
@@ -11,7 +12,8 @@ namespace guetzli {
 
 B200ButteraugliComparator::B200ButteraugliComparator(int width, int height, const std::vector<uint8_t>* rgb,
                                                      float target_distance, ProcessStats* stats, int device)
-    : width_(width), height_(height), ctx_(nullptr), stats_(stats), distance_(0.0f), block_x_(0), block_y_(0) {
+    : width_(width), height_(height), ctx_(nullptr), stats_(stats), distance_(0.0f), block_x_(0), block_y_(0),
+      factor_x_(1), factor_y_(1) {
   if (gzb_create(device, width, height, rgb->data(), target_distance, &ctx_) != GZB_OK) Die("gzb_create");
 }
 
@@ -24,12 +26,46 @@ void B200ButteraugliComparator::Die(const char* what) const {
   abort();
 }
 
-// OutputImage keeps dequantised coefficients block-major per component: exactly gzb's layout.
+namespace {
+bool Is444(const OutputImage& img) {
+  for (int c = 0; c < 3; ++c)
+    if (img.component(c).factor_x() != 1 || img.component(c).factor_y() != 1) return false;
+  return true;
+}
+bool Is420(const OutputImage& img) {
+  return img.component(0).factor_x() == 1 && img.component(0).factor_y() == 1 &&
+         img.component(1).factor_x() == 2 && img.component(1).factor_y() == 2 &&
+         img.component(2).factor_x() == 2 && img.component(2).factor_y() == 2;
+}
+// The luma plane of a 4:2:0 image in gzb's MCU-padded layout (2*ceil(w/16) blocks per row); the
+// padding blocks only matter to the JPEG writer and stay zero here.
+std::vector<coeff_t> PaddedLuma(const OutputImage& img) {
+  const OutputImageComponent& y = img.component(0);
+  const int bw = y.width_in_blocks(), bh = y.height_in_blocks();
+  const int cbw = 2 * img.component(1).width_in_blocks(), cbh = 2 * img.component(1).height_in_blocks();
+  std::vector<coeff_t> out(static_cast<size_t>(cbw) * cbh * kDCTBlockSize, 0);
+  for (int by = 0; by < bh; ++by)
+    memcpy(&out[static_cast<size_t>(by) * cbw * kDCTBlockSize], y.coeffs() + static_cast<size_t>(by) * bw * kDCTBlockSize,
+           static_cast<size_t>(bw) * kDCTBlockSize * sizeof(coeff_t));
+  return out;
+}
+}  // namespace
+
+// OutputImage keeps dequantised coefficients block-major per component: exactly gzb's layout (for a
+// 4:2:0 image the luma rows are re-pitched to whole MCUs).
 void B200ButteraugliComparator::PushImage(const OutputImage& img) const {
-  if (img.component(0).factor_x() != 1 || img.component(1).factor_x() != 1 || img.component(2).factor_x() != 1)
-    Die("4:2:0 candidate (not supported by gzb200 yet)");
-  if (gzb_set_coeffs(ctx_, img.component(0).coeffs(), img.component(1).coeffs(), img.component(2).coeffs()) != GZB_OK)
-    Die("gzb_set_coeffs");
+  if (Is444(img)) {
+    if (gzb_set_sampling(ctx_, 1) != GZB_OK) Die("gzb_set_sampling");
+    if (gzb_set_coeffs(ctx_, img.component(0).coeffs(), img.component(1).coeffs(), img.component(2).coeffs()) != GZB_OK)
+      Die("gzb_set_coeffs");
+  } else if (Is420(img)) {
+    if (gzb_set_sampling(ctx_, 2) != GZB_OK) Die("gzb_set_sampling");
+    const std::vector<coeff_t> y = PaddedLuma(img);
+    if (gzb_set_coeffs(ctx_, y.data(), img.component(1).coeffs(), img.component(2).coeffs()) != GZB_OK)
+      Die("gzb_set_coeffs");
+  } else {
+    Die("chroma sampling other than 4:4:4 / 4:2:0");
+  }
 }
 
 void B200ButteraugliComparator::Compare(const OutputImage& img) {
@@ -44,18 +80,26 @@ void B200ButteraugliComparator::StartBlockComparisons() {
 void B200ButteraugliComparator::FinishBlockComparisons() { gzb_finish_block_comparisons(ctx_); }
 
 void B200ButteraugliComparator::SwitchBlock(int block_x, int block_y, int factor_x, int factor_y) {
-  if (factor_x != 1 || factor_y != 1) Die("SwitchBlock with subsampling factors");
   block_x_ = block_x;
   block_y_ = block_y;
+  factor_x_ = factor_x;
+  factor_y_ = factor_y;
 }
 
 // Per-call block comparison (one tiny launch per call). Correct but latency-bound: the batched
 // ComputeBlockZeroingOrder below is what a --cuda build should call.
 double B200ButteraugliComparator::CompareBlock(const OutputImage& img, int off_x, int off_y,
                                                const coeff_t* candidate_block, const int comp_mask) const {
-  (void)img; (void)off_x; (void)off_y; (void)comp_mask;
   double err = 0.0;
-  if (gzb_compare_block(ctx_, block_x_, block_y_, candidate_block, &err) != GZB_OK) Die("gzb_compare_block");
+  if (factor_x_ == 1 && factor_y_ == 1 && comp_mask == 7 && Is444(img)) {
+    if (gzb_compare_block(ctx_, block_x_, block_y_, candidate_block, &err) != GZB_OK) Die("gzb_compare_block");
+    return err;
+  }
+  // Any other sampling / component mask: the window is rendered by the caller's OutputImage
+  // (guetzli/butteraugli_comparator.cc:117-126) and compared on the device.
+  const int bx = block_x_ * factor_x_ + off_x, by = block_y_ * factor_y_ + off_y;
+  const std::vector<uint8_t> rgb = img.ToSRGB(8 * bx, 8 * by, 8, 8);
+  if (gzb_compare_block_srgb(ctx_, bx, by, rgb.data(), &err) != GZB_OK) Die("gzb_compare_block_srgb");
   return err;
 }
 
@@ -74,19 +118,25 @@ void B200ButteraugliComparator::ComputeBlockErrorAdjustmentWeights(int direction
                                                                    double target_mul, int factor_x, int factor_y,
                                                                    const std::vector<float>& distmap,
                                                                    std::vector<float>* block_weight) {
-  if (factor_x != 1 || factor_y != 1) Die("ComputeBlockErrorAdjustmentWeights with subsampling factors");
+  if (factor_x != factor_y || (factor_x != 1 && factor_x != 2)) Die("ComputeBlockErrorAdjustmentWeights: sampling factors");
   // The caller's vector is all zeros on entry (guetzli/processor.cc:776); gzb overwrites it.
-  if (gzb_compute_block_error_adjustment_weights(ctx_, direction, max_block_dist, target_mul, distmap.data(),
-                                                 block_weight->data()) != GZB_OK)
+  if (gzb_compute_block_error_adjustment_weights_f(ctx_, direction, max_block_dist, target_mul, factor_x, distmap.data(),
+                                                   block_weight->data()) != GZB_OK)
     Die("gzb_compute_block_error_adjustment_weights");
 }
 
 bool B200ButteraugliComparator::ComputeBlockZeroingOrder(const JPEGData& jpg, const OutputImage& img, int comp_mask,
                                                          std::vector<gzb_coeff_data>* output_order) {
-  const size_t nblocks = static_cast<size_t>(img.component(0).width_in_blocks()) * img.component(0).height_in_blocks();
+  const int last_c = (comp_mask & 4) ? 2 : (comp_mask & 2) ? 1 : 0;   // processor.cc:565-572
+  const size_t nblocks = static_cast<size_t>(img.component(last_c).width_in_blocks()) * img.component(last_c).height_in_blocks();
   output_order->assign(nblocks * 192, gzb_coeff_data{0, 0.0f});
-  if (gzb_set_jpeg_coeffs(ctx_, jpg.components[0].coeffs.data(), jpg.components[1].coeffs.data(),
-                          jpg.components[2].coeffs.data()) != GZB_OK) return false;
+  if (Is444(img)) {
+    if (gzb_set_jpeg_coeffs(ctx_, jpg.components[0].coeffs.data(), jpg.components[1].coeffs.data(),
+                            jpg.components[2].coeffs.data()) != GZB_OK) return false;
+  } else {
+    if (gzb_set_jpeg_coeffs_420(ctx_, jpg.components[0].coeffs.data(), jpg.components[1].coeffs.data(),
+                                jpg.components[2].coeffs.data()) != GZB_OK) return false;
+  }
   PushImage(img);
   return gzb_compute_block_zeroing_order(ctx_, comp_mask, output_order->data()) == GZB_OK;
 }

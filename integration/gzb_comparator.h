@@ -53,7 +53,7 @@ class B200ButteraugliComparator : public Comparator {
   gzb_ctx* ctx_;
   ProcessStats* stats_;
   float distance_;
-  int block_x_, block_y_;
+  int block_x_, block_y_, factor_x_, factor_y_;
 };
 
 }  // namespace guetzli

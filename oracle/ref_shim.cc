@@ -490,10 +490,18 @@ long ref_process_rgb(const uint8_t* rgb, int w, int h, float target, uint8_t* ou
 // The UNMODIFIED reference Processor (guetzli::ProcessJpegData, processor.cc:931-1027) driven by
 // the B200 comparator adaptor of integration/gzb_comparator.{h,cc}: the drop-in test. MODE_CPU
 // control flow, so the per-block CompareBlock virtual is used (one GPU launch per call).
+long ref_process_rgb_b200_params(const uint8_t* rgb, int w, int h, float target, int try_420, int force_420,
+                                 int device, uint8_t* out, long cap, int* iters);
 long ref_process_rgb_b200(const uint8_t* rgb, int w, int h, float target, int device, uint8_t* out,
                           long cap, int* iters) {
+  return ref_process_rgb_b200_params(rgb, w, h, target, 0, 0, device, out, cap, iters);
+}
+long ref_process_rgb_b200_params(const uint8_t* rgb, int w, int h, float target, int try_420, int force_420,
+                                 int device, uint8_t* out, long cap, int* iters) {
   guetzli::Params params;
   params.butteraugli_target = target;
+  params.try_420 = try_420 != 0;
+  params.force_420 = force_420 != 0;
   guetzli::ProcessStats stats;
   std::vector<uint8_t> v(rgb, rgb + size_t(3) * w * h);
   guetzli::JPEGData jpg;

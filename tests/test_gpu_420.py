@@ -190,3 +190,25 @@ def test_encode_420_golden(gz, name):
     assert len(jpg) == gold["size"]
     assert hashlib.sha256(jpg).hexdigest() == gold["sha256"]
     assert st["num_iterations"] == gold["iterations"]
+
+
+@pytest.mark.parametrize("name", ["red_96x80_q95_force", "synth_33x47_q84_force", "synth_96x80_q95_try"])
+def test_unmodified_reference_processor_420_through_b200_comparator(gz, name):
+    """Drop-in: the reference's own ProcessJpegData with Params::force_420 / try_420, running against the
+    Comparator adaptor of integration/gzb_comparator.cc (Compare of a factor-2 OutputImage,
+    SwitchBlock / CompareBlock with sampling factors through gzb_compare_block_srgb, block weights with
+    factor 2), must emit the reference's bytes."""
+    import ctypes as C
+    import _libs
+    L = _libs.ref()
+    L.ref_process_rgb_b200_params.restype = C.c_long
+    gold = _gold_420()[name]
+    kind, size, q, mode = name.split("_")
+    w, h = (int(v) for v in size.split("x"))
+    img = image_420(kind, w, h)
+    out = np.zeros(w * h * 3 + (1 << 16), np.uint8)
+    iters = C.c_int()
+    n = L.ref_process_rgb_b200_params(p(img), w, h, C.c_float(gold["target"]), int(mode == "try"), int(mode == "force"),
+                                      0, p(out), C.c_long(out.size), C.byref(iters))
+    assert n == gold["size"] and iters.value == gold["iterations"]
+    assert hashlib.sha256(out[:n].tobytes()).hexdigest() == gold["sha256"]
