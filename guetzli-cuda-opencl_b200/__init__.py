@@ -547,7 +547,7 @@ def ProcessGroup(rgb, butteraugli_target, dist, device=0, host_threads=0, want_t
         enc.close()
 
 
-def QuantSearchSimulate(rank, world, allgather, target, eval_fn, batch=1):
+def QuantSearchSimulate(rank, world, allgather, target, eval_fn, batch=1, mode=0):
     """Test hook (no GPU): runs the speculative SelectQuantMatrix search of gzb_quant_search.h with
     `eval_fn(original, q[192]) -> (distance, jpg_size)` standing in for the GPU trial. Returns
     {"visited": [(original, hscore, distance, size)], "best_q": [192], "best_ok": bool, "rounds": n,
@@ -567,10 +567,10 @@ def QuantSearchSimulate(rank, world, allgather, target, eval_fn, batch=1):
     nvis = C.c_int()
     best_q = np.zeros(192, np.int32)
     info = np.zeros(4, np.int32)
-    L.gzb_test_quant_search.argtypes = [C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p, EVAL, C.c_void_p, C.c_float,
-                                        C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int]
-    rc = L.gzb_test_quant_search(rank, world, cb, None, ev_c, None, C.c_float(target), _p(vis), cap, C.byref(nvis),
-                                 _p(best_q), _p(info), batch)
+    L.gzb_test_quant_search_mode.argtypes = [C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p, EVAL, C.c_void_p, C.c_float,
+                                             C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    rc = L.gzb_test_quant_search_mode(rank, world, cb, None, ev_c, None, C.c_float(target), _p(vis), cap, C.byref(nvis),
+                                      _p(best_q), _p(info), batch, mode)
     if rc != 0:
         raise GzbError("gzb_test_quant_search failed (%d)" % rc)
     return {"visited": [tuple(v) for v in vis[:nvis.value].tolist()], "best_q": best_q.tolist(), "best_ok": bool(info[0]),

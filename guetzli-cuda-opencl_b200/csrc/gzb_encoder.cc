@@ -869,12 +869,22 @@ int gzb_write_candidate_jpeg(gzb_ctx* ctx, const int* q192, int input_tables, ui
 // Test hook (CPU only): the speculative SelectQuantMatrix search with a caller-provided evaluator.
 // visited: rows of {original, heuristic score, distance, jpg_size}; info: {best.dist_ok, rounds,
 // evaluated on this rank, evaluated by the group}.
+int gzb_test_quant_search_mode(int rank, int world, gzb_allgather_fn allgather, void* user,
+                               int (*eval_fn)(void*, int, const int*, float*, uint64_t*), void* eval_user, float target,
+                               double* visited, int cap, int* nvisited, int* best_q192, int* info, int batch, int mode);
 int gzb_test_quant_search(int rank, int world, gzb_allgather_fn allgather, void* user,
                           int (*eval_fn)(void*, int, const int*, float*, uint64_t*), void* eval_user, float target,
                           double* visited, int cap, int* nvisited, int* best_q192, int* info, int batch) {
+  return gzb_test_quant_search_mode(rank, world, allgather, user, eval_fn, eval_user, target, visited, cap, nvisited,
+                                    best_q192, info, batch, 0);
+}
+// mode 2: the search of a downsampled (YUV420) image -- no original, generator starts at score 0.
+int gzb_test_quant_search_mode(int rank, int world, gzb_allgather_fn allgather, void* user,
+                               int (*eval_fn)(void*, int, const int*, float*, uint64_t*), void* eval_user, float target,
+                               double* visited, int cap, int* nvisited, int* best_q192, int* info, int batch, int mode) {
   gzb::Group g;
   g.rank = rank; g.world = world; g.allgather = allgather; g.user = user;
-  gzb::QuantSearch search(g, target, batch);
+  gzb::QuantSearch search(g, target, batch, mode);
   int n = 0;
   const bool ok = search.run(
       [&](const std::vector<gzb::Trial>& ts, std::vector<gzb::TrialOutcome>* os) {

@@ -30,9 +30,10 @@ def hscore(q):
 
 
 class RefGenerator:
-    """QuantMatrixGenerator, processor.cc:162-271 (downsample=false)."""
+    """QuantMatrixGenerator, processor.cc:162-271."""
 
-    def __init__(self):
+    def __init__(self, downsample=False):
+        self.downsample = downsample
         self.a = self.b = -1.0
         self.total = 0.0
         for k in range(64):
@@ -54,7 +55,7 @@ class RefGenerator:
         for _ in range(1000):
             if self.b == -1.0:
                 if self.a == -1.0:
-                    hs = self.total
+                    hs = 0.0 if self.downsample else self.total
                 elif self.a < 5.0 * self.total:
                     hs = self.a + self.total
                 else:
@@ -91,20 +92,22 @@ class RefGenerator:
             self.b = hs if self.b == -1.0 else min(self.b, hs)
 
 
-def reference_search(eval_fn, target):
-    """processor.cc:986-1003 (original) + SelectQuantMatrix 336-372."""
+def reference_search(eval_fn, target, downsample=False):
+    """processor.cc:986-1003 (original) + SelectQuantMatrix 336-372; downsample: the YUV420 pass (no
+    original, QuantMatrixGenerator(downsample=true))."""
     f32 = np.float32
 
     def ok_at(d, mul):
         return float(f32(d)) <= float(f32(mul)) * float(f32(target))
     visited = []
     ones = [1] * 192
-    d, s = eval_fn(True, ones)
-    visited.append((1.0, 0.0, float(f32(d)), float(s)))
+    if not downsample:
+        d, s = eval_fn(True, ones)
+        visited.append((1.0, 0.0, float(f32(d)), float(s)))
     d, s = eval_fn(False, ones)
     visited.append((0.0, 0.0, float(f32(d)), float(s)))
     best = (ones, ok_at(d, 0.97), s)
-    gen = RefGenerator()
+    gen = RefGenerator(downsample)
     while True:
         q = gen.next()
         if q is None:
@@ -154,14 +157,14 @@ class BarrierAllGather:
         return ag
 
 
-def run_group(gz, world, target, ev, batch=1):
+def run_group(gz, world, target, ev, batch=1, mode=0):
     if world == 1:
-        return [gz.QuantSearchSimulate(0, 1, None, target, ev, batch)]
+        return [gz.QuantSearchSimulate(0, 1, None, target, ev, batch, mode)]
     ag = BarrierAllGather(world)
     res = [None] * world
 
     def work(r):
-        res[r] = gz.QuantSearchSimulate(r, world, ag.for_rank(r), target, ev, batch)
+        res[r] = gz.QuantSearchSimulate(r, world, ag.for_rank(r), target, ev, batch, mode)
     th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
     for t in th:
         t.start()
@@ -227,3 +230,20 @@ def test_batched_trials_per_rank_replay_the_reference_sequence(gz, kind, world, 
     distinct = len({(v[0], v[1]) for v in want_visited})
     assert res[0]["rounds"] < distinct
     assert sum(r["evaluated_here"] for r in res) == res[0]["evaluated_total"]
+
+
+@pytest.mark.parametrize("kind", ["typical", "never_ok", "always_ok", "early_exit", "wobbly"])
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_downsampled_search_replays_the_reference_sequence(gz, kind, world):
+    """The YUV420 pass: SelectQuantMatrix(jpg, downsample=true) -- the generator starts at heuristic
+    score 0, so the all-ones matrix is asked for twice and then the search expands from there."""
+    target = 0.971769
+    ev = make_eval(kind)
+    want_visited, want_best = reference_search(ev, target, downsample=True)
+    assert want_visited[0][:2] == (0.0, 0.0) and want_visited[1][:2] == (0.0, 0.0)
+    for r in run_group(gz, world, target, ev, mode=2):
+        got = r["visited"]
+        assert len(got) == len(want_visited)
+        for g, w in zip(got, want_visited):
+            assert g[0] == w[0] and abs(g[1] - w[1]) < 1e-9 and g[2] == w[2] and g[3] == w[3]
+        assert r["best_q"] == want_best[0] and r["best_ok"] == want_best[1]
