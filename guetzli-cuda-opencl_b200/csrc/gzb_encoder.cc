@@ -1161,7 +1161,9 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
 
   // ---- SelectFrequencyMasking(jpg, img, comp_mask, target_mul, stop_early) (processor.cc:559-919) ----
   // Returns 1 when this rank of a group has nothing left to do (the back end runs on rank 0).
-  auto select_frequency_masking = [&](const int comp_mask, const double target_mul, const bool stop_early) -> int {
+  // jpg_ncomp: jpg.components.size() of the pass (1 only for a grey image after a forced "downsampling").
+  auto select_frequency_masking = [&](const int comp_mask, const double target_mul, const bool stop_early,
+                                      const int jpg_ncomp) -> int {
   // units of the pass: 8x8 blocks, or the 16x16 macro-blocks of the sub-sampled chroma planes
   const int factor = (e.yuv420 && (comp_mask & 6)) ? 2 : 1;
   const int pass_bw = (width + 8 * factor - 1) / (8 * factor), pass_bh = (height + 8 * factor - 1) / (8 * factor);
@@ -1299,7 +1301,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   // ---- SelectFrequencyBackEnd (processor.cc:723-919) ----
   {
     const double t_be = now_ms();
-    const int ncomp = 3;
+    const int ncomp = jpg_ncomp;
     if (prep_thread.joinable()) prep_thread.join();
     Histogram (&ac_hist)[3] = prep.ac_hist;
     Histogram (&dc_hist)[3] = prep.dc_hist;
@@ -1327,7 +1329,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       return hs;
     };
     // EntropyCodedDataSize (processor.cc:538-546), with the raw bit sums cached per component.
-    uint64_t raw_bits[3];
+    uint64_t raw_bits[3] = {0, 0, 0};
     auto recount_bits = [&]() {
       for (int c = 0; c < ncomp; ++c) {
         uint64_t bits = 0;
@@ -1839,10 +1841,10 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
     g_encode_err = "gzb_encoder_run: the YUV420 passes are not sharded over a group";
     return GZB_ERR_UNSUPPORTED;
   }
-  if (force_420 && gray) {
-    g_encode_err = "gzb_encoder_run: force_420 on a grey image (the reference leaves it 4:4:4) is not supported";
-    return GZB_ERR_UNSUPPORTED;
-  }
+  // force_420 on a grey image: OutputImage::Downsample returns early (output_image.cc:536-539), the
+  // image stays 4:4:4 and SaveToJpegData leaves ONE component in jpg, so the pass is the luma-only one
+  // with target_mul 1 (processor.cc:1011-1014; the chroma pass returns at processor.cc:735).
+  const bool gray_force = force_420 && gray;
   bool idle_rank = false;
   if (force_420) {   // the original is compared and output before any pass (processor.cc:967-985)
     const int rc = select_quant(1, nullptr);
@@ -1850,7 +1852,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   }
   for (int downsample = force_420; downsample <= try_420 && !idle_rank; ++downsample) {
     int best_q[3][64];
-    if (downsample) {
+    if (downsample && !gray_force) {
       // DownsampleImage + SaveToJpegData on the q=1 input, on the device; the host mirrors follow
       const double t0 = now_ms();
       if (gzb_downsample_420(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
@@ -1863,10 +1865,12 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
     if (rc != GZB_OK) return rc;
     if (!e.set_global_quant(best_q)) return fail(GZB_ERR_CUDA);
     if (!downsample) {
-      rc = select_frequency_masking(7, 1.0, false);
+      rc = select_frequency_masking(7, 1.0, false, 3);
+    } else if (gray_force) {
+      rc = select_frequency_masking(1, 1.0, false, 1);
     } else {
-      rc = select_frequency_masking(1, static_cast<double>(0.97f), false);   // ymul (processor.cc:1011)
-      if (rc == GZB_OK) rc = select_frequency_masking(6, 1.0, true);
+      rc = select_frequency_masking(1, static_cast<double>(0.97f), false, 3);   // ymul (processor.cc:1011)
+      if (rc == GZB_OK) rc = select_frequency_masking(6, 1.0, true, 3);
     }
     if (rc < 0) return rc;
     idle_rank = rc == 1;

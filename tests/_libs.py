@@ -311,6 +311,9 @@ def image_420(kind, w, h):
         return bees()
     if kind == "synth":
         return synth_image(w, h, 777)
+    if kind == "gray":
+        g = synth_image(w, h, 4321)[:, :, 0]
+        return np.ascontiguousarray(np.stack([g, g, g], axis=2))
     rng = np.random.Generator(np.random.PCG64(4242))
     yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
     img = synth_image(w, h, 31).astype(np.float64)

@@ -38,7 +38,8 @@ def edge_cases():
 
 CASES_420 = [("red", 96, 80, 95, "force"), ("red", 100, 75, 90, "force"), ("red", 129, 66, 92, "try"),
              ("synth", 96, 80, 95, "try"), ("red", 200, 136, 88, "try"), ("synth", 33, 47, 84, "force"),
-             ("bees", 0, 0, 95, "try"), ("bees", 0, 0, 90, "force")]
+             ("bees", 0, 0, 95, "try"), ("bees", 0, 0, 90, "force"),
+             ("gray", 80, 64, 90, "force"), ("gray", 80, 64, 90, "try"), ("red", 32, 32, 95, "force")]
 
 
 def yuv420_cases():
