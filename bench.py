@@ -222,7 +222,10 @@ def run_ours(a, rank, world, local):
     if group and world > 1:
         allgather = gz.torch_allgather(dist, torch.device("cuda", local))   # NCCL over NVLink
 
-    images = [one_image(s) for s in range(a.warmup + a.steps)]
+    K = max(1, a.inflight) if not group else 1
+    if K > 1:
+        host_threads = max(1, host_threads // K)
+    images = [one_image(s) for s in range((a.warmup + a.steps) * K)]
     sampler = ClockSampler(local)
     run_ms, e2e_ms, launches, h2d, d2h = [], [], 0, 0, 0
     z_ms_sum = cmp_ms_sum = 0.0
@@ -233,9 +236,10 @@ def run_ours(a, rank, world, local):
         timed = step >= a.warmup
         if timed and step == a.warmup:
             sampler.start()
-        img = images[step]
+        img = images[step * K]
         # ---- device-resident arm: create outside, run inside the timed region
-        enc = gz.Encoder(img, target, device=local, host_threads=host_threads, profile=False)
+        encs = [gz.Encoder(images[step * K + k], target, device=local, host_threads=host_threads, profile=False) for k in range(K)]
+        enc = encs[0]
         if allgather is not None:
             enc.set_group(rank, world, allgather)
         flush.fill_(step & 0xff)
@@ -243,7 +247,19 @@ def run_ours(a, rank, world, local):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
-        jpg, st, _ = enc.run()
+        if K == 1:
+            jpg, st, _ = enc.run()
+        else:
+            # the encodes of the batch run concurrently: one's host phases overlap the others' kernels
+            res = [None] * K
+            th = [threading.Thread(target=lambda k=k: res.__setitem__(k, encs[k].run())) for k in range(K)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            jpg, st, _ = res[0]
+            for k in range(1, K):
+                st = dict(st, launches=st["launches"] + res[k][1]["launches"], num_compares=st["num_compares"] + res[k][1]["num_compares"])
         e1.record()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) * 1e3
@@ -255,15 +271,27 @@ def run_ours(a, rank, world, local):
             # stream inside the library on every step (no per-launch profiling in the timed region)
             z_ms_sum += st["device_zeroing_ms"]
             cmp_ms_sum += st["device_compare_ms"]
-        enc.close()
+        for en in encs:
+            en.close()
         # ---- end-to-end arm: host RGB buffer -> host JPEG bytes
         flush.fill_((step + 1) & 0xff)
         barrier()
         t0 = time.perf_counter()
         if allgather is not None:
             jpg2, st2, _ = gz.ProcessGroup(img, target, dist, device=local, host_threads=host_threads)
-        else:
+        elif K == 1:
             jpg2, st2, _ = gz.Process(img, target, device=local, host_threads=host_threads)
+        else:
+            res2 = [None] * K
+            th = [threading.Thread(target=lambda k=k: res2.__setitem__(k, gz.Process(images[step * K + k], target, device=local,
+                                                                                     host_threads=host_threads))) for k in range(K)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            jpg2, st2, _ = res2[0]
+            for k in range(1, K):
+                st2 = dict(st2, h2d_bytes=st2["h2d_bytes"] + res2[k][1]["h2d_bytes"], d2h_bytes=st2["d2h_bytes"] + res2[k][1]["d2h_bytes"])
         dt2 = (time.perf_counter() - t0) * 1e3
         assert jpg2 == jpg
         if timed:
@@ -299,7 +327,7 @@ def run_ours(a, rank, world, local):
     total_e2e = reduce_max(sum(e2e_ms))
     launches_all = int(reduce_sum(launches))
     mpix = w * h / 1e6
-    images_per_step = 1 if group else world
+    images_per_step = 1 if group else world * K
     value = images_per_step * mpix * a.steps / (total_run / 1e3)
     e2e_value = images_per_step * mpix * a.steps / (total_e2e / 1e3)
     if rank != 0:
@@ -333,10 +361,11 @@ def run_ours(a, rank, world, local):
                                "guetzli::Process" % (w, h, a.quality,
                                                      "ONE image per step shared by all GPUs: SelectQuantMatrix candidates and "
                                                      "zeroing blocks sharded, NCCL all-gather per round" if group
-                                                     else "one image per GPU per step"),
+                                                     else ("one image per GPU per step" if K == 1 else
+                                                           "%d images per GPU per step, encoded concurrently" % K)),
                    "mode": a.mode, "search_rounds_per_step": sum(rounds) / max(1, len(rounds)),
                    "search_trials_per_step": sum(trials) / max(1, len(trials)),
-                   "l2": "256 MiB buffer written between timed steps (L2 flush)", "host_threads_per_gpu": host_threads,
+                   "l2": "256 MiB buffer written between timed steps (L2 flush)", "host_threads_per_encode": host_threads, "inflight_per_gpu": K,
                    "compares_per_step": n_cmp / a.steps},
         "e2e": {"value": e2e_value, "unit": "MPix/s", "ms_per_step": total_e2e / a.steps,
                 "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps},
@@ -419,6 +448,9 @@ def main():
     ap.add_argument("--size", default="1024x1024", type=lambda s: tuple(int(v) for v in s.lower().split("x")))
     ap.add_argument("--quality", type=float, default=90.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=1,
+                    help="batch mode: images encoded concurrently per GPU (one host thread group + one device context "
+                         "each); a step is then a batch of that many images per GPU. Default 1 = one image per step")
     ap.add_argument("--mode", default="batch", choices=["batch", "group", "butteraugli"],
                     help="batch: one image per GPU (BASELINE configs[1]/[3]); group: one image shared by all GPUs "
                          "(configs[2]); butteraugli: standalone Compare sweep + quality sweep (configs[4])")

@@ -206,7 +206,7 @@ static void slab_release(int device, Slab s) {
   if (!s.base) return;
   std::lock_guard<std::mutex> lock(g_slab_mu);
   std::vector<Slab>& v = g_slab_cache[device & 63];
-  if (v.size() >= 2) { cudaFree(s.base); cudaFreeHost(s.pinned); return; }
+  if (v.size() >= 4) { cudaFree(s.base); cudaFreeHost(s.pinned); return; }
   v.push_back(s);
 }
 

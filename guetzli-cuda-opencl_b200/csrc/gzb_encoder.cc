@@ -1452,7 +1452,17 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           const float limit = 0.75f * gzb_block_error_limit(e.ctx);
           // partition_point on the sorted order == number of entries below the limit
           size_t below = 0;
-          for (const OrderEntry& oe : global_order) below += oe.second < limit ? 1 : 0;
+          {
+            const size_t n = global_order.size();
+            const int T = std::max(1, std::min<int>(e.pool->size(), static_cast<int>(n >> 16) + 1));
+            std::vector<size_t> part(T, 0);
+            e.pool->run(T, [&](int t) {
+              size_t cnt = 0;
+              for (size_t i = n * t / T, i1 = n * (t + 1) / T; i < i1; ++i) cnt += global_order[i].second < limit ? 1 : 0;
+              part[t] = cnt;
+            });
+            for (int t = 0; t < T; ++t) below += part[t];
+          }
           min_coeffs_to_change = std::max<int>(min_coeffs_to_change, static_cast<int>(below));
           first_up_iter = false;
         }
