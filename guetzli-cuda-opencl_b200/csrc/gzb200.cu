@@ -968,12 +968,13 @@ static int run_zeroing(gzb_ctx* c, int comp_mask, int mode, int b0 = 0, int b1 =
     lpt = order;
   }
   if (mb) {
-    const int ctas = std::max(1, std::min(b1 - b0, c->sm_count * 4));
+    const int ctas = std::max(1, std::min(b1 - b0, c->sm_count * 5));
     KLAUNCH(c, KC_ZEROING, k_zeroing_order_mb<<<ctas, 128, 0, c->stream>>>(
         c->d_orig, c->d_coef, cs, c->d_rgb0, c->d_ycc, c->ps, c->P, c->W, c->H, c->bw, c->mcw, b1, c->d_mask_scale,
         c->target, 3, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_scalars + 1, lpt));
   } else {
-    const int ctas = std::max(1, std::min((b1 - b0 + kZeroWarps - 1) / kZeroWarps, c->sm_count * 5));
+    static const int per_sm = getenv("GZB_ZERO_CTAS_PER_SM") ? atoi(getenv("GZB_ZERO_CTAS_PER_SM")) : 6;   // tuning probe (7 fit; the pipes saturate at 5-6)
+    const int ctas = std::max(1, std::min((b1 - b0 + kZeroWarps - 1) / kZeroWarps, c->sm_count * std::max(1, per_sm)));
     KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<ctas, 32 * kZeroWarps, 0, c->stream>>>(
         c->d_orig, c->d_coef, cs, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, b1, c->d_mask_scale, comp_mask,
         c->target, 3, mode, 0, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1, lpt,

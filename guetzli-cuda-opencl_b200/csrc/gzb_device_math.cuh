@@ -223,7 +223,9 @@ __device__ __forceinline__ double remove_range_around_zero(double v, double rang
 // ---------------------------------------------------------------------------------------------
 // ButteraugliBlockDiff, warp-cooperative (ba.cc:602-684).
 //   fa, fb : the two 8x8x3 blocks as floats in shared memory, [c*64 + 8*y + x]
-//   ws     : per-warp scratch of kBlockDiffScratchDoubles doubles in shared memory
+//   pl     : per-warp scratch of 4 * kBdPlane doubles in shared memory (planes, then power spectra)
+//   spec   : per-warp scratch of kBdSpecDoubles doubles (row spectra, then the per-frequency terms). It
+//            MAY ALIAS fa / fb: they are last read in step (1), spec is first written in step (3).
 //   csf_a / csf_b : kCsf8x8[4 + lane] and kCsf8x8[36] (hoisted by the caller: loop invariant)
 // Returns dc[3], ac[3], edge[3] in ALL lanes. Sequential sums keep the reference's order.
 // kWithDcEdge = false skips the mean / edge-mean part (dc and edge are then not written): the
@@ -236,17 +238,18 @@ __device__ __forceinline__ double remove_range_around_zero(double v, double rang
 // at +9u and row r at +r.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBdPlane = 72, kBdSpec = 56;
-constexpr int kBlockDiffScratchDoubles = 4 * kBdPlane + 2 * 4 * kBdSpec;  // 736
+constexpr int kBdSpecHalf = 3 * kBdSpec + 44;        // re (or im) of four planes: the last one needs 9*4 + 8 = 44
+constexpr int kBdSpecDoubles = 2 * kBdSpecHalf;      // 424
+constexpr int kBlockDiffScratchDoubles = 4 * kBdPlane + kBdSpecDoubles;  // 712
 
 template <bool kWithDcEdge = true>
-__device__ __forceinline__ void warp_block_diff(const float* __restrict__ fa,
-                                                const float* __restrict__ fb, double* ws,
+__device__ __forceinline__ void warp_block_diff(const float* fa, const float* fb, double* pl, double* spec,
                                                 double csf_a, double csf_b, double dc[3],
                                                 double ac[3], double edge[3]) {
   const int lane = threadIdx.x & 31;
-  double* pl = ws;                       // [4][72]: y_avg, x_halfdiff, y_halfdiff, z_halfdiff
-  double* sre = ws + 4 * kBdPlane;       // [4][56]
-  double* sim = sre + 4 * kBdSpec;       // [4][56]
+  // pl: [4][72]: y_avg, x_halfdiff, y_halfdiff, z_halfdiff
+  double* sre = spec;                    // [4][56] (44 used of the last)
+  double* sim = spec + kBdSpecHalf;
 
   // (1) average / half-difference planes (8 values per lane).
 #pragma unroll

@@ -518,7 +518,7 @@ k_block_diff_map(const float* __restrict__ a, const float* __restrict__ b, size_
     }
     __syncwarp();
     double dc[3], ac[3], edge[3];
-    warp_block_diff<false>(s_a[warp], s_b[warp], s_ws[warp], csf_a, csf_b, dc, ac, edge);
+    warp_block_diff<false>(s_a[warp], s_b[warp], s_ws[warp], s_ws[warp] + 4 * kBdPlane, csf_a, csf_b, dc, ac, edge);
     if (lane < 3) {
       const size_t o = 3 * (static_cast<size_t>(ry) * rxs + rx) + lane;
       ac_out[o] = static_cast<float>(lane == 0 ? ac[0] : lane == 1 ? ac[1] : ac[2]);

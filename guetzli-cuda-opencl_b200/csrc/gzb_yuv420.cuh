@@ -374,7 +374,7 @@ __device__ __forceinline__ void mb_window(const ZeroMbSmem& m, const unsigned ch
   }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 k_zeroing_order_mb(const int16_t* __restrict__ orig, const int16_t* __restrict__ cur, size_t comp_stride,
                    const uint8_t* __restrict__ rgb_planes, const uint8_t* __restrict__ ycc, size_t plane_stride,
                    int P, int W, int H, int bw, int mcw, int nmb, const float* __restrict__ mask_scale, float limit,

@@ -12,6 +12,7 @@
 #pragma once
 #include "gzb_device_math.cuh"
 #include "gzb_zeroing_model.h"
+#include <cstddef>
 
 namespace gzb {
 
@@ -22,13 +23,19 @@ __constant__ float c_zero_bias[192];
 __constant__ double c_scale8[8];   // border scales of the sigma-1.1 blur on an 8-sample line
 __constant__ float c_taps11[5];    // sigma-1.1 taps
 
+// Per-warp state, 7888 bytes: with four warps per CTA and 72 registers per thread seven CTAs (28
+// warps) are resident per SM. The block-diff row spectra (424 doubles) live on top of bufA / bufB / cx /
+// key (+ spec_tail): those are dead by the time ButteraugliBlockDiff transforms its rows (fa / fb are read
+// in its first step only; cx is rewritten by every trial; key is only used to order the candidates
+// before the greedy loop).
 struct ZeroWarpSmem {
-  double ws[kBlockDiffScratchDoubles];
+  double pl[4 * kBdPlane];   // block-diff planes / power spectra
+  float bufA[192];   // linear rgb -> fa (original after MaskHighIntensityChange)   } also the block-diff
+  float bufB[192];   // H-pass -> fb (candidate after MaskHighIntensityChange)      } spectra, together
+  float cx[192];     // candidate block, opsin dynamics                             } with spec_tail
+  float key[192];    // candidate ordering keys                                     }
+  double spec_tail[kBdSpecDoubles - 4 * 192 / 2];
   float pg0[192];    // original block, opsin dynamics (SwitchBlock)
-  float cx[192];     // candidate block, opsin dynamics
-  float bufA[192];   // linear rgb -> fa (original after MaskHighIntensityChange)
-  float bufB[192];   // H-pass -> fb (candidate after MaskHighIntensityChange)
-  float key[192];
   short cf[192];     // processed coefficients
   short colv[192];   // column-pass values of the processed state
   short ccol[8];     // candidate's replacement column
@@ -37,6 +44,8 @@ struct ZeroWarpSmem {
   unsigned char order[192]; // sorted input order
   unsigned char ent[192];   // unsorted entries
 };
+static_assert(offsetof(ZeroWarpSmem, spec_tail) == offsetof(ZeroWarpSmem, bufA) + 4 * 192 * sizeof(float), "spectra must be contiguous");
+static_assert(offsetof(ZeroWarpSmem, bufA) % 8 == 0, "spectra must be 8-byte aligned");
 
 // 8x8 opsin dynamics of linear rgb in `lin` (smem, [c*64+8y+x]) -> `dst`; `hb` is scratch.
 __device__ __forceinline__ void warp_block_opsin(const float* lin, float* hb, float* dst, int lane) {
@@ -154,7 +163,7 @@ __device__ __forceinline__ float warp_compare_linear(ZeroWarpSmem& s, const floa
   }
   __syncwarp();
   double dc[3], ac[3], edge[3];
-  warp_block_diff(s.bufA, s.bufB, s.ws, csf_a, csf_b, dc, ac, edge);
+  warp_block_diff(s.bufA, s.bufB, s.pl, reinterpret_cast<double*>(s.bufA), csf_a, csf_b, dc, ac, edge);
   double diff = 0.0, diff_edge = 0.0;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -269,7 +278,7 @@ k_zero_lpt_scatter(const unsigned char* __restrict__ cost, unsigned int* __restr
 // mode 2: CompareBlock of ONE block `single_block` whose candidate coefficients are the 192 values
 //         at `cur` (comp_stride 64, nblocks 1) -> err_out[0] (Comparator::CompareBlock adaptor)
 // Blocks [block_begin, nblocks) are processed (a group of GPUs splits the image by block range).
-__global__ void __launch_bounds__(32 * kZeroWarps, 5)
+__global__ void __launch_bounds__(32 * kZeroWarps, 7)
 k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cur,
                 size_t comp_stride, const uint8_t* __restrict__ rgb_planes, size_t plane_stride,
                 int P, int W, int H, int bw, int nblocks, const float* __restrict__ mask_scale,
