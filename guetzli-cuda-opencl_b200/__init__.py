@@ -402,6 +402,38 @@ def Process(rgb, butteraugli_target, device=0, host_threads=0, want_trace=False,
     return data, st.as_dict(), trace
 
 
+def ProcessBatch(images, butteraugli_target, device=0, inflight=3, host_threads_per_encode=0, try_420=False, force_420=False):
+    """gzb_encode_rgb_batch: the images (HxWx3 uint8 arrays) encoded on one GPU with `inflight` encodes
+    running concurrently. Returns [(jpeg_bytes, stats_dict)] in input order."""
+    L = lib()
+    n = len(images)
+    arrs = [np.ascontiguousarray(im, np.uint8) for im in images]
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    ws = (C.c_int * n)(*[a.shape[1] for a in arrs])
+    hs = (C.c_int * n)(*[a.shape[0] for a in arrs])
+    outs = (C.c_void_p * n)()
+    sizes = (C.c_size_t * n)()
+    stats = (EncodeStats * n)()
+    status = (C.c_int * n)()
+    L.gzb_encode_rgb_batch.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gzb_encode_last_error.restype = C.c_char_p
+    L.gzb_free.argtypes = [C.c_void_p]
+    L.gzb_free.restype = None
+    rc = L.gzb_encode_rgb_batch(device, n, ptrs, ws, hs, C.c_float(butteraugli_target), int(try_420), int(force_420),
+                                int(inflight), int(host_threads_per_encode), outs, sizes, stats, status)
+    res = []
+    for i in range(n):
+        if outs[i]:
+            res.append((C.string_at(outs[i], sizes[i]), stats[i].as_dict()))
+            L.gzb_free(outs[i])
+        else:
+            res.append((None, None))
+    if rc != 0:
+        raise GzbError("gzb_encode_rgb_batch failed (%d): %s" % (rc, L.gzb_encode_last_error().decode(errors="replace")))
+    return res
+
+
 def RgbToJpegCoeffs(rgb):
     """guetzli::EncodeRGBToJpeg with q=1 (host code): int16 [3, nblocks, 64]."""
     a = np.ascontiguousarray(rgb, np.uint8)

@@ -1964,4 +1964,41 @@ int gzb_encode_rgb_params(int device, const uint8_t* rgb, int width, int height,
   return rc;
 }
 
+// A batch of images on ONE GPU with `inflight` encodes running concurrently (each on its own host
+// threads, device context and streams): one encode's sequential host phases (sort, entropy-code
+// rebuilds) overlap the other encodes' kernels. Results are those of n independent gzb_encode_rgb_params
+// calls. status[i] receives each image's return code; the function returns the first failure (or GZB_OK).
+int gzb_encode_rgb_batch(int device, int n, const uint8_t* const* rgb, const int* width, const int* height,
+                         float butteraugli_target, int try_420, int force_420, int inflight, int host_threads_per_encode,
+                         uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats, int* status) {
+  if (n < 0 || (n > 0 && (!rgb || !width || !height || !jpeg_out || !jpeg_size))) return GZB_ERR_BAD_ARG;
+  if (inflight < 1) inflight = 1;
+  if (host_threads_per_encode <= 0) {
+    const unsigned hc = std::max(1u, std::thread::hardware_concurrency());
+    host_threads_per_encode = static_cast<int>(std::max(1u, std::min(16u, hc / static_cast<unsigned>(std::min(inflight, std::max(n, 1))))));
+  }
+  std::atomic<int> next(0), first_error(GZB_OK);
+  std::mutex err_mu;
+  std::string err_msg;
+  auto work = [&] {
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n) break;
+      const int rc = gzb_encode_rgb_params(device, rgb[i], width[i], height[i], butteraugli_target, try_420, force_420,
+                                           host_threads_per_encode, &jpeg_out[i], &jpeg_size[i], stats ? &stats[i] : nullptr, nullptr);
+      if (status) status[i] = rc;
+      if (rc != GZB_OK) {
+        std::lock_guard<std::mutex> l(err_mu);
+        if (first_error.load() == GZB_OK) { first_error = rc; err_msg = gzb_encode_last_error(); }
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < std::min(inflight, n); ++t) th.emplace_back(work);
+  work();
+  for (std::thread& t : th) t.join();
+  if (first_error.load() != GZB_OK) g_encode_err = err_msg;
+  return first_error.load();
+}
+
 }  // extern "C"

@@ -260,6 +260,16 @@ int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float 
 int gzb_encode_rgb_params(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
                           int try_420, int force_420, int host_threads, uint8_t** jpeg_out, size_t* jpeg_size,
                           gzb_encode_stats* stats, char** trace_out);
+/* A batch of n images on ONE GPU (BASELINE configs[3], one rank's share) with `inflight` encodes running
+ * concurrently, each on host_threads_per_encode host threads (<= 0: the cores divided by inflight) and its
+ * own device context: the sequential host phases of one encode overlap the kernels of the others
+ * (measured: 1.7x the one-at-a-time throughput with three in flight). rgb / width / height / jpeg_out /
+ * jpeg_size / stats / status are arrays of n; jpeg_out[i] is malloc'ed (gzb_free). Each result equals
+ * that of gzb_encode_rgb_params on its own. Returns the first failing image's code, or GZB_OK. */
+int gzb_encode_rgb_batch(int device, int n, const uint8_t* const* rgb, const int* width, const int* height,
+                         float butteraugli_target, int try_420, int force_420, int inflight,
+                         int host_threads_per_encode, uint8_t** jpeg_out, size_t* jpeg_size,
+                         gzb_encode_stats* stats, int* status);
 /* The same encoder in two steps, so that a caller can separate "inputs resident in HBM" from the
  * search: create uploads the image, computes its opsin-dynamics image and the q=1 coefficients;
  * run performs the search (once per encoder). */

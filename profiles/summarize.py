@@ -3,6 +3,7 @@
 
   python profiles/summarize.py launches <launch.csv> "<command>" > profiles/rN_launches_x.md
   python profiles/summarize.py report <file.ncu-rep> [...] > profiles/rN_ncu_full_x.md
+  python profiles/summarize.py traffic <file.ncu-rep> "<source note>" > profiles/rN_ncu_traffic.json
 
 `launches` reads the CSV of `ncu --metrics gpu__time_duration.sum --clock-control none --csv`;
 `report` reads `ncu --set full` reports through `ncu -i ... --page raw --csv`.
@@ -91,8 +92,43 @@ def report(paths):
             print()
 
 
+def traffic(path, note):
+    """dram bytes per launch, FP64 / XU pipe utilisation and duration per kernel (bench.py reads
+    roofline.traffic and fp64_pipe_pct_of_peak from this file)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+
+    def num(d, key, scale=None):
+        if key not in d or d[key][0] == "":
+            return None
+        v = float(d[key][0].replace(",", ""))
+        u = d[key][1]
+        if scale == "bytes":
+            v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        if scale == "us":
+            v *= {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(u, 1)
+        return v
+    kernels = OrderedDict()
+    for row in rows[2:]:
+        d = {h: (row[i], units[i]) for i, h in enumerate(hdr)}
+        k = short(d["Kernel Name"][0]).replace("void ", "").split("<")[0]
+        e = kernels.setdefault(k, {"launches": 0, "dram_bytes": 0.0, "time_us": 0.0})
+        e["launches"] += 1
+        e["dram_bytes"] += (num(d, "dram__bytes_read.sum", "bytes") or 0) + (num(d, "dram__bytes_write.sum", "bytes") or 0)
+        e["time_us"] += num(d, "gpu__time_duration.sum", "us") or 0
+        e["fp64_pipe_pct"] = num(d, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")
+        e["xu_pipe_pct"] = num(d, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active")
+    for e in kernels.values():
+        e["dram_bytes_per_launch"] = e["dram_bytes"] / e["launches"]
+    print(json.dumps({"source": note, "kernels": kernels}, indent=1))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
     else:
         report(sys.argv[2:])

@@ -254,3 +254,17 @@ def test_full_bench_workloads_equal_reference(gz, key):
     m = re.match(r"(\d+)x(\d+)_q(\d+)_s(\d+)", key)
     w, h, q, seed = map(int, m.groups())
     check(gz, synth_image(w, h, seed), gold)
+
+
+def test_batch_with_encodes_in_flight_equals_single_encodes(gz):
+    """gzb_encode_rgb_batch: several encodes running concurrently on one GPU (separate contexts, host
+    threads split between them) give exactly the bytes of one-at-a-time encodes."""
+    imgs = [synth_image(160, 120, 1244), synth_image(128, 96, 1234), synth_image(97, 61, 1254),
+            synth_image(200, 136, 31), synth_image(64, 64, 5), synth_image(256, 256, 1234)]
+    t = np.float32(gz.ButteraugliScoreForQuality(92))
+    single = [gz.Process(im, t)[0] for im in imgs]
+    for inflight in (1, 3, 6):
+        got = gz.ProcessBatch(imgs, t, inflight=inflight)
+        assert [g[0] for g in got] == single
+    got = gz.ProcessBatch(imgs[:3], t, inflight=2, try_420=True)
+    assert [g[0] for g in got] == [gz.Process(im, t, try_420=True)[0] for im in imgs[:3]]
