@@ -105,6 +105,28 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout. Libraries (NCCL's version banner, torchrun notices) also
+    write to file descriptor 1, so it is pointed at stderr for the whole run and the line goes to a saved
+    duplicate of the original stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(text):
+    data = (text + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text + "\n")
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -130,7 +152,7 @@ def run_reference(a, rank, world):
     import multiprocessing as mp
     import _libs
     if not _libs.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgzref.so not built"}))
+        emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgzref.so not built"}))
         return
     cores = os.cpu_count() or 1
     # bounded sample of the workload: one 256x256 crop-sized synthetic image per core per step
@@ -160,7 +182,7 @@ def run_reference(a, rank, world):
         "e2e": {"value": value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -399,7 +421,7 @@ def run_ours(a, rank, world, local):
         "kernels_note": "one extra untimed step with a CUDA-event pair around every launch; the timed steps carry no per-launch profiling",
         "cpu_baseline": cpu_baseline_single_core(a.quality) if world == 1 and not a.no_cpu_baseline else None,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -451,7 +473,7 @@ def run_butteraugli_sweep(a, local):
                        "bytes": len(jpg), "iterations": st["num_iterations"], "compares": st["num_compares"],
                        "device_compare_ms": st["device_compare_ms"], "device_zeroing_ms": st["device_zeroing_ms"]})
     big = sweep[3]
-    print(json.dumps({"metric": "butteraugli MPix/s", "value": big["mpix_per_s"], "unit": "MPix/s", "n_gpus": 1,
+    emit(json.dumps({"metric": "butteraugli MPix/s", "value": big["mpix_per_s"], "unit": "MPix/s", "n_gpus": 1,
                       "steps": a.steps, "warmup": a.warmup, "ms_per_step": big["compare_device_ms"],
                       "higher_is_better": True, "dtype": "f64", "data": "synthetic",
                       "config": {"workload": "standalone butteraugli Compare of the all-3-quantised candidate vs the original, "
@@ -477,6 +499,7 @@ def main():
                     help="batch: one image per GPU (BASELINE configs[1]/[3]); group: one image shared by all GPUs "
                          "(configs[2]); butteraugli: standalone Compare sweep + quality sweep (configs[4])")
     a = ap.parse_args()
+    guard_stdout()
     rank, world, local = dist_env()
     if a.impl == "reference":
         run_reference(a, rank, world)
