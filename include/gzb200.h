@@ -57,10 +57,13 @@ int gzb_create(int device, int width, int height, const uint8_t* rgb, float targ
                gzb_ctx** out);
 void gzb_destroy(gzb_ctx* ctx);
 
-/* ---- candidate image (device-resident mirror of guetzli::OutputImage, 4:4:4) --------------
+/* ---- candidate image (device-resident mirror of guetzli::OutputImage) ------------------------
  * Coefficient planes are int16, block-major, ceil(w/8)*ceil(h/8)*64 values per component
- * (OutputImageComponent::coeffs(), guetzli/output_image.h). */
-/* Uploads the q=1 JPEG coefficients of the input (jpg.components[c].coeffs). */
+ * (OutputImageComponent::coeffs(), guetzli/output_image.h). After gzb_downsample_420 /
+ * gzb_set_sampling(ctx, 2) the image is YUV 4:2:0 and the component layouts are those described at
+ * gzb_downsample_420 below. */
+/* Uploads the q=1 JPEG coefficients of the (4:4:4) input (jpg.components[c].coeffs); the context
+ * returns to 4:4:4 if it was 4:2:0. */
 int gzb_set_jpeg_coeffs(gzb_ctx* ctx, const int16_t* c0, const int16_t* c1, const int16_t* c2);
 /* OutputImage::CopyFromJpegData (guetzli/output_image.cc:212-228, 481-492): coeff * quant.
  * Replaces cuCopyFromJpegComponent (clguetzli/cuguetzli.h:138-148). quant: int[3][64]. */
@@ -106,7 +109,8 @@ int gzb_finish_block_comparisons(gzb_ctx* ctx);
  * (clguetzli/clguetzli.h:201-217). Either pointer may be NULL. */
 int gzb_get_block_lists(gzb_ctx* ctx, float* mask_scale_out, float* opsin_blocks_out);
 /* CompareBlock for every 8x8 block of the resident candidate at once (factor 1, comp_mask 7):
- * err_out[block]. (guetzli/butteraugli_comparator.cc:113-163) */
+ * err_out[block]. (guetzli/butteraugli_comparator.cc:113-163) 4:4:4 candidates only
+ * (GZB_ERR_UNSUPPORTED otherwise), like gzb_get_block_lists and gzb_compare_block. */
 int gzb_compare_blocks(gzb_ctx* ctx, float* err_out);
 /* Comparator::CompareBlock after SwitchBlock(block_x, block_y, 1, 1): the error of one 8x8 block
  * whose candidate coefficients are candidate192 = [Y64 Cb64 Cr64] (dequantised values). One tiny
@@ -123,7 +127,10 @@ int gzb_compare_block_srgb(gzb_ctx* ctx, int block_x, int block_y, const uint8_t
  * Processor::SelectFrequencyMasking over ComputeBlockZeroingOrder (guetzli/processor.cc:376-487,
  * 638-672), MODE_CPU semantics. out: nblocks*192 records, zero-filled, packed from slot 0 in
  * zeroing order, entries with err <= BlockErrorLimit only. Needs gzb_set_jpeg_coeffs (the original
- * coefficients) and gzb_start_block_comparisons. */
+ * coefficients) and gzb_start_block_comparisons. For a 4:2:0 image comp_mask must be 1 (the luma
+ * blocks; Cb / Cr of each window are the image's upsampled samples) or 6 (nblocks = the 16x16
+ * macro-blocks, ceil(w/16)*ceil(h/16); the error of a trial is the maximum over the macro-block's
+ * 8x8 windows, guetzli/processor.cc:426-441). */
 int gzb_compute_block_zeroing_order(gzb_ctx* ctx, int comp_mask, gzb_coeff_data* out);
 /* Same search, with the candidate packing of SelectFrequencyMasking (guetzli/processor.cc:694-712)
  * done on the device: offsets[nblocks+1] (candidate_coeff_offsets) and, for the records with
