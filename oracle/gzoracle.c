@@ -1184,3 +1184,8 @@ GZO_API void gzo_rgb_to_jpeg_coeffs(const uint8_t* rgb, int xs, int ys, int16_t*
       }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * YUV 4:2:0 branch: Downsample, the factor-2 candidate, zeroing over macro-blocks.
+ * ---------------------------------------------------------------------------------------- */
+#include "gzoracle_yuv420.inc"

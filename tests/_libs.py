@@ -32,11 +32,13 @@ def oracle():
     if _oracle is None:
         path = os.path.join(ORACLE_DIR, "libgzoracle.so")
         src = os.path.join(ORACLE_DIR, "gzoracle.c")
-        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        inc = os.path.join(ORACLE_DIR, "gzoracle_yuv420.inc")
+        if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(src), os.path.getmtime(inc)):
             _build("port")
         _oracle = C.CDLL(path)
         L = _oracle
         L.gzo_compare.restype = C.c_float
+        L.gzo420_compare.restype = C.c_float
         L.gzo_compare_block.restype = C.c_double
         L.gzo_score_from_diffmap.restype = C.c_float
         L.gzo_score_jpeg.restype = C.c_double

@@ -236,3 +236,113 @@ def test_front_end_fdct_and_rgb_to_coeffs():
     oracle().gzo_rgb_to_jpeg_coeffs(p(img), w, h, p(c[0]), p(c[1]), p(c[2]))
     assert np.array_equal(c, s.jpg_coeffs())
     s.close()
+
+
+# ---- YUV 4:2:0 branch (oracle/gzoracle_yuv420.inc) -------------------------------------------------
+from _libs import RefSession420, image_420   # noqa: E402
+
+SIZES_420 = [("red", 48, 40), ("red", 100, 75), ("synth", 33, 47), ("red", 129, 66)]
+
+
+def _jpeg_coeffs(img):
+    h, w = img.shape[:2]
+    nb = ((w + 7) // 8) * ((h + 7) // 8)
+    c = np.zeros((3, nb, 64), np.int16)
+    oracle().gzo_rgb_to_jpeg_coeffs(p(img), w, h, p(c[0]), p(c[1]), p(c[2]))
+    return c
+
+
+def _oracle_downsample(img):
+    h, w = img.shape[:2]
+    c = _jpeg_coeffs(img)
+    mcw, mch = (w + 15) // 16, (h + 15) // 16
+    out = [np.zeros((4 * mcw * mch, 64), np.int16), np.zeros((mcw * mch, 64), np.int16), np.zeros((mcw * mch, 64), np.int16)]
+    assert oracle().gzo420_downsample(p(c[0]), p(c[1]), p(c[2]), w, h, p(out[0]), p(out[1]), p(out[2])) == 1
+    return out
+
+
+@pytest.mark.parametrize("kind,w,h", SIZES_420 + [("bees", 0, 0)])
+def test_420_downsample(kind, w, h):
+    """OutputImage::Downsample (PreProcessChannel for V then U, 2x2 average, double DCT) + SaveToJpegData."""
+    img = image_420(kind, w, h)
+    rs = RefSession420(img, 0.97)
+    got, want = _oracle_downsample(img), rs.jpg_coeffs()
+    for c in range(3):
+        assert got[c].shape == want[c].shape and np.array_equal(got[c], want[c]), "component %d" % c
+    rs.close()
+
+
+def test_420_downsample_skips_grey():
+    g = synth_image(48, 40, 3)[:, :, 0]
+    img = np.ascontiguousarray(np.stack([g, g, g], axis=2))
+    c = _jpeg_coeffs(img)
+    dummy = np.zeros((64, 64), np.int16)
+    assert oracle().gzo420_downsample(p(c[0]), p(c[1]), p(c[2]), 48, 40, p(dummy), p(dummy), p(dummy)) == 0
+
+
+@pytest.mark.parametrize("kind,w,h", SIZES_420)
+def test_420_candidate_closed_form_upsampling_and_compare(kind, w, h):
+    """The factor-2 candidate as a per-pixel function of the coefficients equals the reference's
+    block-by-block UpdatePixelsForBlock state -- after a full copy, after quantisation and after
+    sparse SetCoeffBlock updates in an arbitrary order."""
+    img = image_420(kind, w, h)
+    h, w = img.shape[:2]
+    rs = RefSession420(img, 0.97)
+    rng = np.random.default_rng(5)
+    q = rng.integers(1, 9, (3, 64)).astype(np.int32)
+    rs.reset(); rs.apply_quant(q)
+    coeffs = rs.coeffs()
+    # scattered single-block updates (each re-renders an 18x18 pixel neighbourhood in the reference)
+    for c in (1, 2, 1, 2, 0):
+        nb = coeffs[c].shape[0]
+        for b in rng.choice(nb, size=min(nb, 5), replace=False):
+            coeffs[c][b, int(rng.integers(0, 64))] = int(rng.integers(-3, 4)) * int(q[c].max())
+            rs.set_coeffs(coeffs)
+    pad = rs.to_padded(rs.coeffs())
+    got = np.zeros((h, w, 3), np.uint8)
+    oracle().gzo420_to_srgb(p(pad[0]), p(pad[1]), p(pad[2]), w, h, p(got))
+    assert np.array_equal(got, rs.to_srgb())
+    dm = np.zeros((h, w), np.float32)
+    d = oracle().gzo420_compare(p(img), p(pad[0]), p(pad[1]), p(pad[2]), w, h, p(dm))
+    d_ref, dm_ref = rs.compare()
+    assert np.array_equal(dm, dm_ref) and d == d_ref
+    rs.close()
+
+
+@pytest.mark.parametrize("kind,w,h", SIZES_420[:3])
+@pytest.mark.parametrize("comp_mask", [1, 6])
+def test_420_zeroing_order(kind, w, h, comp_mask):
+    img = image_420(kind, w, h)
+    h, w = img.shape[:2]
+    target = 3.0 if comp_mask == 6 else 1.5
+    rs = RefSession420(img, target)
+    q = np.minimum(np.random.default_rng(3).integers(1, 9, (3, 64)), 3).astype(np.int32)
+    rs.reset(); rs.apply_quant(q)
+    mask = rs.start_block_comparisons()
+    want = rs.zeroing_order_f(comp_mask)
+    n = want.shape[0] if kind != "red" or w < 64 else min(want.shape[0], 24)   # bounded CPU time
+    orig, cur = rs.jpg_coeffs(), rs.to_padded(rs.coeffs())
+    got = np.zeros((n, 192), COEFF_DATA)
+    oracle().gzo420_zeroing_order(p(img), w, h, p(orig[0]), p(orig[1]), p(orig[2]), p(cur[0]), p(cur[1]), p(cur[2]),
+                                  p(mask), comp_mask, C.c_float(target), 0, n, p(got))
+    assert np.array_equal(got["idx"], want["idx"][:n]) and np.array_equal(got["err"], want["err"][:n])
+    assert (want["err"][:n] > 0).sum() > 10
+    rs.close()
+
+
+@pytest.mark.parametrize("direction,rblock", [(1, 1), (1, 3), (-1, 2), (-1, 4)])
+@pytest.mark.parametrize("factor", [1, 2])
+def test_block_weights_with_factor(direction, rblock, factor):
+    img = image_420("red", 129, 66)
+    rs = RefSession420(img, 0.6)
+    rs.reset(); rs.apply_quant(np.full((3, 64), 5, np.int32))
+    d, dm = rs.compare()
+    mul = 1.0 if direction < 0 else 0.8 * float(dm.max()) / 0.6   # all but the worst region pass
+    want = rs.block_weights_f(direction, rblock, mul, factor, dm)
+    got = np.zeros_like(want)
+    oracle().gzo_block_weights_f.argtypes = [np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), C.c_int, C.c_int,
+                                             C.c_float, C.c_int, C.c_int, C.c_double, C.c_int,
+                                             np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")]
+    oracle().gzo_block_weights_f(np.ascontiguousarray(dm), 129, 66, np.float32(0.6), direction, rblock, mul, factor, got)
+    assert np.array_equal(got, want) and got.max() > 0
+    rs.close()
