@@ -1,9 +1,10 @@
 // gzb_encoder.cc -- host search driver: guetzli::Process(rgb -> jpeg) with every butteraugli
 // evaluation, IDCT/quantisation pass and the block-zeroing search running on the B200 through the
 // C ABI of this library. The control flow and every scalar decision follow the reference's
-// Processor (guetzli/processor.cc:151-372, 559-1020, 1157-1185) for the default flags
-// (4:4:4, try_420=false, clear_metadata=true, zeroing_greedy_lookahead=3, new_zeroing_model=true),
-// so that the emitted JPEG is byte-identical to the CPU reference's.
+// Processor (guetzli/processor.cc:151-372, 559-1020, 1157-1185) for clear_metadata=true,
+// zeroing_greedy_lookahead=3, new_zeroing_model=true, use_silver_screen=false and any try_420 /
+// force_420 (the 4:4:4 pass and the YUV420 pass with its two frequency-masking passes), so that the
+// emitted JPEG is byte-identical to the CPU reference's.
 //
 // Host-side accelerations that do not change any result:
 //   * ComputeEntropyCodes is evaluated only at the steps whose value can be observed
@@ -1164,680 +1165,680 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   // jpg_ncomp: jpg.components.size() of the pass (1 only for a grey image after a forced "downsampling").
   auto select_frequency_masking = [&](const int comp_mask, const double target_mul, const bool stop_early,
                                       const int jpg_ncomp) -> int {
-  // units of the pass: 8x8 blocks, or the 16x16 macro-blocks of the sub-sampled chroma planes
-  const int factor = (e.yuv420 && (comp_mask & 6)) ? 2 : 1;
-  const int pass_bw = (width + 8 * factor - 1) / (8 * factor), pass_bh = (height + 8 * factor - 1) / (8 * factor);
-  const int num_blocks = pass_bw * pass_bh;
-  // coefficient block of unit b in the searched planes (the 4:2:0 luma plane is MCU-padded)
-  const int first_c = (comp_mask & 1) ? 0 : 1;
-  const bool remap = e.cbw[first_c] != pass_bw;
-  const int coef_bw = e.cbw[first_c];
-  auto cblock = [&](int b) -> size_t { return remap ? static_cast<size_t>(b / pass_bw) * coef_bw + b % pass_bw : static_cast<size_t>(b); };
-  std::vector<int> cand_offsets(num_blocks + 1);
-  std::vector<uint8_t> cand_coeffs;
-  std::vector<float> cand_errors;
-  // What the back end needs from the quantised image -- header size, DC/AC histograms, the DC size
-  // estimate, the zig-zag non-zero masks -- is computed on a host thread while the GPU runs the
-  // zeroing search (the host would otherwise only wait for it).
-  struct BackendPrep {
-    Histogram ac_hist[3], dc_hist[3];
-    int header_size = 0, dc_size = 0;
-    std::vector<uint64_t> zmask[3];
-  } prep;
-  std::thread prep_thread;
-  struct PrepJoin { std::thread& t; ~PrepJoin() { if (t.joinable()) t.join(); } } prep_join{prep_thread};
-  int back_ncomp = 3;   // jpg.components.size() of the back end: the components SaveToJpegData keeps
-  if (e.group.rank == 0) {
-    back_ncomp = e.ncomp_for_output();
-    if (e.yuv420) {
-      // MCU-order DC differences and padded luma blocks: counted by the device coder's histogram kernel
-      uint32_t dc[48], ac[768];
-      if (gzb_candidate_symbol_histograms_n(e.ctx, nullptr, back_ncomp, dc, ac) != GZB_OK) return fail(GZB_ERR_CUDA);
-      for (int c = 0; c < 3; ++c) {
-        histogram_from_counts(dc + 16 * c, 16, &prep.dc_hist[c]);
-        histogram_from_counts(ac + 256 * c, 256, &prep.ac_hist[c]);
+    // units of the pass: 8x8 blocks, or the 16x16 macro-blocks of the sub-sampled chroma planes
+    const int factor = (e.yuv420 && (comp_mask & 6)) ? 2 : 1;
+    const int pass_bw = (width + 8 * factor - 1) / (8 * factor), pass_bh = (height + 8 * factor - 1) / (8 * factor);
+    const int num_blocks = pass_bw * pass_bh;
+    // coefficient block of unit b in the searched planes (the 4:2:0 luma plane is MCU-padded)
+    const int first_c = (comp_mask & 1) ? 0 : 1;
+    const bool remap = e.cbw[first_c] != pass_bw;
+    const int coef_bw = e.cbw[first_c];
+    auto cblock = [&](int b) -> size_t { return remap ? static_cast<size_t>(b / pass_bw) * coef_bw + b % pass_bw : static_cast<size_t>(b); };
+    std::vector<int> cand_offsets(num_blocks + 1);
+    std::vector<uint8_t> cand_coeffs;
+    std::vector<float> cand_errors;
+    // What the back end needs from the quantised image -- header size, DC/AC histograms, the DC size
+    // estimate, the zig-zag non-zero masks -- is computed on a host thread while the GPU runs the
+    // zeroing search (the host would otherwise only wait for it).
+    struct BackendPrep {
+      Histogram ac_hist[3], dc_hist[3];
+      int header_size = 0, dc_size = 0;
+      std::vector<uint64_t> zmask[3];
+    } prep;
+    std::thread prep_thread;
+    struct PrepJoin { std::thread& t; ~PrepJoin() { if (t.joinable()) t.join(); } } prep_join{prep_thread};
+    int back_ncomp = 3;   // jpg.components.size() of the back end: the components SaveToJpegData keeps
+    if (e.group.rank == 0) {
+      back_ncomp = e.ncomp_for_output();
+      if (e.yuv420) {
+        // MCU-order DC differences and padded luma blocks: counted by the device coder's histogram kernel
+        uint32_t dc[48], ac[768];
+        if (gzb_candidate_symbol_histograms_n(e.ctx, nullptr, back_ncomp, dc, ac) != GZB_OK) return fail(GZB_ERR_CUDA);
+        for (int c = 0; c < 3; ++c) {
+          histogram_from_counts(dc + 16 * c, 16, &prep.dc_hist[c]);
+          histogram_from_counts(ac + 256 * c, 256, &prep.ac_hist[c]);
+        }
       }
-    }
-    prep_thread = std::thread([&] {
-      Frame f;
-      f.width = width; f.height = height; f.bw = e.bw; f.bh = e.bh; f.ncomp = back_ncomp;
-      f.yuv420 = e.yuv420;
-      for (int c = 0; c < 3; ++c) f.coeffs[c] = e.idx[c].data();
-      gzb::jpeg::frame_set_quant(&f, e.quant);
-      prep.header_size = static_cast<int>(gzb::jpeg::header_size(f));
-      if (!e.yuv420) gzb::jpeg::build_histograms(f, prep.dc_hist, prep.ac_hist, e.pool.get());
-      {  // EstimateDCSize (processor.cc:548-555)
-        Histogram tmp[3] = {prep.dc_hist[0], prep.dc_hist[1], prep.dc_hist[2]};
-        size_t num = f.ncomp;
-        int ix[4];
-        uint8_t dd[3 * Histogram::kSize];
-        prep.dc_size = static_cast<int>(gzb::jpeg::cluster_histograms(tmp, &num, ix, dd));
-      }
-      // zig-zag non-zero masks of every block: a coefficient flip then touches O(1) symbols
-      for (int c = 0; c < 3; ++c) prep.zmask[c].resize(e.cnb[c]);
-      const int nbmax = static_cast<int>(std::max(e.cnb[0], std::max(e.cnb[1], e.cnb[2])));
-      parallel_rows(nbmax, e.pool.get(), [&](int b0, int b1) {
-        for (int c = 0; c < 3; ++c)
-          for (int b = b0; b < std::min<int>(b1, static_cast<int>(e.cnb[c])); ++b)
-            prep.zmask[c][b] = gzb::jpeg::zigzag_nonzero_mask(e.idx[c].data() + static_cast<size_t>(b) * 64);
+      prep_thread = std::thread([&] {
+        Frame f;
+        f.width = width; f.height = height; f.bw = e.bw; f.bh = e.bh; f.ncomp = back_ncomp;
+        f.yuv420 = e.yuv420;
+        for (int c = 0; c < 3; ++c) f.coeffs[c] = e.idx[c].data();
+        gzb::jpeg::frame_set_quant(&f, e.quant);
+        prep.header_size = static_cast<int>(gzb::jpeg::header_size(f));
+        if (!e.yuv420) gzb::jpeg::build_histograms(f, prep.dc_hist, prep.ac_hist, e.pool.get());
+        {  // EstimateDCSize (processor.cc:548-555)
+          Histogram tmp[3] = {prep.dc_hist[0], prep.dc_hist[1], prep.dc_hist[2]};
+          size_t num = f.ncomp;
+          int ix[4];
+          uint8_t dd[3 * Histogram::kSize];
+          prep.dc_size = static_cast<int>(gzb::jpeg::cluster_histograms(tmp, &num, ix, dd));
+        }
+        // zig-zag non-zero masks of every block: a coefficient flip then touches O(1) symbols
+        for (int c = 0; c < 3; ++c) prep.zmask[c].resize(e.cnb[c]);
+        const int nbmax = static_cast<int>(std::max(e.cnb[0], std::max(e.cnb[1], e.cnb[2])));
+        parallel_rows(nbmax, e.pool.get(), [&](int b0, int b1) {
+          for (int c = 0; c < 3; ++c)
+            for (int b = b0; b < std::min<int>(b1, static_cast<int>(e.cnb[c])); ++b)
+              prep.zmask[c][b] = gzb::jpeg::zigzag_nonzero_mask(e.idx[c].data() + static_cast<size_t>(b) * 64);
+        });
       });
-    });
-  }
-  {
-    if (gzb_start_block_comparisons(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
-    const double t0 = now_ms();
-    // the blocks are independent: rank r of the group searches blocks [nb*r/world, nb*(r+1)/world)
-    const int world = e.group.world, rank = e.group.rank;
-    const int b0 = static_cast<int>(static_cast<int64_t>(num_blocks) * rank / world);
-    const int b1 = static_cast<int>(static_cast<int64_t>(num_blocks) * (rank + 1) / world);
-    const int nloc = b1 - b0;
-    std::vector<int> loc_off(nloc + 1);
-    size_t ncand = 0;
-    cand_coeffs.resize(static_cast<size_t>(nloc) * 48 + 16);
-    cand_errors.resize(cand_coeffs.size());
-    if (gzb_compute_block_zeroing_candidates_range(e.ctx, comp_mask, b0, b1, loc_off.data(), cand_coeffs.data(),
-                                                   cand_errors.data(), cand_coeffs.size(), &ncand) != GZB_OK) return fail(GZB_ERR_CUDA);
-    if (ncand > cand_coeffs.size()) {  // more than 48 candidates per block on average: fetch again (no recompute)
+    }
+    {
+      if (gzb_start_block_comparisons(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
+      const double t0 = now_ms();
+      // the blocks are independent: rank r of the group searches blocks [nb*r/world, nb*(r+1)/world)
+      const int world = e.group.world, rank = e.group.rank;
+      const int b0 = static_cast<int>(static_cast<int64_t>(num_blocks) * rank / world);
+      const int b1 = static_cast<int>(static_cast<int64_t>(num_blocks) * (rank + 1) / world);
+      const int nloc = b1 - b0;
+      std::vector<int> loc_off(nloc + 1);
+      size_t ncand = 0;
+      cand_coeffs.resize(static_cast<size_t>(nloc) * 48 + 16);
+      cand_errors.resize(cand_coeffs.size());
+      if (gzb_compute_block_zeroing_candidates_range(e.ctx, comp_mask, b0, b1, loc_off.data(), cand_coeffs.data(),
+                                                     cand_errors.data(), cand_coeffs.size(), &ncand) != GZB_OK) return fail(GZB_ERR_CUDA);
+      if (ncand > cand_coeffs.size()) {  // more than 48 candidates per block on average: fetch again (no recompute)
+        cand_coeffs.resize(ncand);
+        cand_errors.resize(ncand);
+        if (gzb_compute_block_zeroing_candidates_range(e.ctx, comp_mask, b0, b1, loc_off.data(), cand_coeffs.data(),
+                                                       cand_errors.data(), ncand, &ncand) != GZB_OK) return fail(GZB_ERR_CUDA);
+      }
       cand_coeffs.resize(ncand);
       cand_errors.resize(ncand);
-      if (gzb_compute_block_zeroing_candidates_range(e.ctx, comp_mask, b0, b1, loc_off.data(), cand_coeffs.data(),
-                                                     cand_errors.data(), ncand, &ncand) != GZB_OK) return fail(GZB_ERR_CUDA);
+      e.st.device_zeroing_ms += gzb_last_device_ms(e.ctx);
+      if (world == 1) {
+        cand_offsets = loc_off;
+      } else {
+        // all-gather 1: every rank's per-block offsets (padded to the longest range) -> global offsets
+        const int maxloc = (num_blocks + world - 1) / world + 1;
+        std::vector<int> send_off(maxloc + 1, 0), all_off(static_cast<size_t>(world) * (maxloc + 1));
+        memcpy(send_off.data(), loc_off.data(), sizeof(int) * (nloc + 1));
+        send_off[maxloc] = static_cast<int>(ncand);
+        if (e.group.allgather(e.group.user, send_off.data(), sizeof(int) * (maxloc + 1), all_off.data()) != 0) {
+          g_encode_err = "gzb_encoder_run: the group exchange failed";
+          return GZB_ERR_CUDA;
+        }
+        size_t maxn = 0, total = 0;
+        std::vector<size_t> base(world + 1, 0);
+        for (int r = 0; r < world; ++r) {
+          const size_t n = static_cast<size_t>(all_off[static_cast<size_t>(r) * (maxloc + 1) + maxloc]);
+          maxn = std::max(maxn, n);
+          base[r + 1] = base[r] + n;
+          total += n;
+        }
+        for (int r = 0; r < world; ++r) {
+          const int rb0 = static_cast<int>(static_cast<int64_t>(num_blocks) * r / world);
+          const int rb1 = static_cast<int>(static_cast<int64_t>(num_blocks) * (r + 1) / world);
+          const int* ro = &all_off[static_cast<size_t>(r) * (maxloc + 1)];
+          for (int b = rb0; b < rb1; ++b) cand_offsets[b] = static_cast<int>(base[r]) + ro[b - rb0];
+        }
+        cand_offsets[num_blocks] = static_cast<int>(total);
+        // all-gather 2: the packed candidates, [errors | coefficient indices], padded to the longest
+        const size_t rec = maxn * 5;
+        std::vector<uint8_t> send(rec + 1, 0), all(static_cast<size_t>(world) * (rec + 1));
+        memcpy(send.data(), cand_errors.data(), ncand * sizeof(float));
+        memcpy(send.data() + maxn * 4, cand_coeffs.data(), ncand);
+        if (e.group.allgather(e.group.user, send.data(), rec + 1, all.data()) != 0) {
+          g_encode_err = "gzb_encoder_run: the group exchange failed";
+          return GZB_ERR_CUDA;
+        }
+        cand_coeffs.resize(total);
+        cand_errors.resize(total);
+        for (int r = 0; r < world; ++r) {
+          const size_t n = base[r + 1] - base[r];
+          const uint8_t* src = all.data() + static_cast<size_t>(r) * (rec + 1);
+          memcpy(cand_errors.data() + base[r], src, n * sizeof(float));
+          memcpy(cand_coeffs.data() + base[r], src + maxn * 4, n);
+        }
+      }
+      e.st.zeroing_wall_ms += now_ms() - t0;
+      gzb_finish_block_comparisons(e.ctx);
     }
-    cand_coeffs.resize(ncand);
-    cand_errors.resize(ncand);
-    e.st.device_zeroing_ms += gzb_last_device_ms(e.ctx);
-    if (world == 1) {
-      cand_offsets = loc_off;
-    } else {
-      // all-gather 1: every rank's per-block offsets (padded to the longest range) -> global offsets
-      const int maxloc = (num_blocks + world - 1) / world + 1;
-      std::vector<int> send_off(maxloc + 1, 0), all_off(static_cast<size_t>(world) * (maxloc + 1));
-      memcpy(send_off.data(), loc_off.data(), sizeof(int) * (nloc + 1));
-      send_off[maxloc] = static_cast<int>(ncand);
-      if (e.group.allgather(e.group.user, send_off.data(), sizeof(int) * (maxloc + 1), all_off.data()) != 0) {
-        g_encode_err = "gzb_encoder_run: the group exchange failed";
-        return GZB_ERR_CUDA;
-      }
-      size_t maxn = 0, total = 0;
-      std::vector<size_t> base(world + 1, 0);
-      for (int r = 0; r < world; ++r) {
-        const size_t n = static_cast<size_t>(all_off[static_cast<size_t>(r) * (maxloc + 1) + maxloc]);
-        maxn = std::max(maxn, n);
-        base[r + 1] = base[r] + n;
-        total += n;
-      }
-      for (int r = 0; r < world; ++r) {
-        const int rb0 = static_cast<int>(static_cast<int64_t>(num_blocks) * r / world);
-        const int rb1 = static_cast<int>(static_cast<int64_t>(num_blocks) * (r + 1) / world);
-        const int* ro = &all_off[static_cast<size_t>(r) * (maxloc + 1)];
-        for (int b = rb0; b < rb1; ++b) cand_offsets[b] = static_cast<int>(base[r]) + ro[b - rb0];
-      }
-      cand_offsets[num_blocks] = static_cast<int>(total);
-      // all-gather 2: the packed candidates, [errors | coefficient indices], padded to the longest
-      const size_t rec = maxn * 5;
-      std::vector<uint8_t> send(rec + 1, 0), all(static_cast<size_t>(world) * (rec + 1));
-      memcpy(send.data(), cand_errors.data(), ncand * sizeof(float));
-      memcpy(send.data() + maxn * 4, cand_coeffs.data(), ncand);
-      if (e.group.allgather(e.group.user, send.data(), rec + 1, all.data()) != 0) {
-        g_encode_err = "gzb_encoder_run: the group exchange failed";
-        return GZB_ERR_CUDA;
-      }
-      cand_coeffs.resize(total);
-      cand_errors.resize(total);
-      for (int r = 0; r < world; ++r) {
-        const size_t n = base[r + 1] - base[r];
-        const uint8_t* src = all.data() + static_cast<size_t>(r) * (rec + 1);
-        memcpy(cand_errors.data() + base[r], src, n * sizeof(float));
-        memcpy(cand_coeffs.data() + base[r], src + maxn * 4, n);
-      }
-    }
-    e.st.zeroing_wall_ms += now_ms() - t0;
-    gzb_finish_block_comparisons(e.ctx);
-  }
 
-  // The back end is one sequential walk: rank 0 of a group finishes the image alone.
-  if (e.group.rank != 0) return 1;
+    // The back end is one sequential walk: rank 0 of a group finishes the image alone.
+    if (e.group.rank != 0) return 1;
 
-  // ---- SelectFrequencyBackEnd (processor.cc:723-919) ----
-  {
-    const double t_be = now_ms();
-    const int ncomp = jpg_ncomp;
-    if (prep_thread.joinable()) prep_thread.join();
-    Histogram (&ac_hist)[3] = prep.ac_hist;
-    Histogram (&dc_hist)[3] = prep.dc_hist;
-    const int header_size = prep.header_size, dc_size = prep.dc_size;
-    std::vector<uint64_t> (&zmask)[3] = prep.zmask;
-    // the coefficient flips of one iteration, pushed to the device before its Compare
-    struct Flips {
-      std::vector<int32_t> block; std::vector<uint8_t> cidx; std::vector<int16_t> val;
-      void clear() { block.clear(); cidx.clear(); val.clear(); }
-    } flips;
-    std::vector<uint8_t> ac_depths(3 * Histogram::kSize);
-    // ComputeEntropyCodes (processor.cc:517-536)
-    gzb::jpeg::HuffCache huff_caches[5];
-    auto compute_entropy_codes = [&]() -> size_t {
-      Histogram clustered[3] = {ac_hist[0], ac_hist[1], ac_hist[2]};
-      size_t num = ncomp;
-      int indexes[4];
-      uint8_t cd[3 * Histogram::kSize];
-      gzb::jpeg::cluster_histograms(clustered, &num, indexes, cd, huff_caches);
-      for (int i = 0; i < ncomp; ++i)
-        memcpy(&ac_depths[i * Histogram::kSize], &cd[indexes[i] * Histogram::kSize], Histogram::kSize);
-      size_t hs = 0;
-      for (size_t i = 0; i < num; ++i) hs += gzb::jpeg::header_cost_bits(clustered[i]) / 8;
-      ++e.st.num_entropy_code_builds;
-      return hs;
-    };
-    // EntropyCodedDataSize (processor.cc:538-546), with the raw bit sums cached per component.
-    uint64_t raw_bits[3] = {0, 0, 0};
-    auto recount_bits = [&]() {
-      for (int c = 0; c < ncomp; ++c) {
-        uint64_t bits = 0;
-        const uint8_t* d = &ac_depths[c * Histogram::kSize];
-        for (int i = 0; i + 1 < Histogram::kSize; ++i) bits += static_cast<uint64_t>(ac_hist[c].counts[i] / 2) * (d[i] + (i & 0xf));
-        raw_bits[c] = bits;
-      }
-    };
-    auto coded_size = [&]() -> size_t {
-      size_t numbits = 0;
-      for (int c = 0; c < ncomp; ++c) numbits += raw_bits[c] + ((raw_bits[c] * 3 + 512) >> 10);
-      return (numbits + 7) / 8;
-    };
-    int ac_histogram_size = static_cast<int>(compute_entropy_codes());
-    recount_bits();
-    const int base_size = header_size + dc_size + ac_histogram_size + static_cast<int>(coded_size());
-    int prev_size = base_size;
+    // ---- SelectFrequencyBackEnd (processor.cc:723-919) ----
+    {
+      const double t_be = now_ms();
+      const int ncomp = jpg_ncomp;
+      if (prep_thread.joinable()) prep_thread.join();
+      Histogram (&ac_hist)[3] = prep.ac_hist;
+      Histogram (&dc_hist)[3] = prep.dc_hist;
+      const int header_size = prep.header_size, dc_size = prep.dc_size;
+      std::vector<uint64_t> (&zmask)[3] = prep.zmask;
+      // the coefficient flips of one iteration, pushed to the device before its Compare
+      struct Flips {
+        std::vector<int32_t> block; std::vector<uint8_t> cidx; std::vector<int16_t> val;
+        void clear() { block.clear(); cidx.clear(); val.clear(); }
+      } flips;
+      std::vector<uint8_t> ac_depths(3 * Histogram::kSize);
+      // ComputeEntropyCodes (processor.cc:517-536)
+      gzb::jpeg::HuffCache huff_caches[5];
+      auto compute_entropy_codes = [&]() -> size_t {
+        Histogram clustered[3] = {ac_hist[0], ac_hist[1], ac_hist[2]};
+        size_t num = ncomp;
+        int indexes[4];
+        uint8_t cd[3 * Histogram::kSize];
+        gzb::jpeg::cluster_histograms(clustered, &num, indexes, cd, huff_caches);
+        for (int i = 0; i < ncomp; ++i)
+          memcpy(&ac_depths[i * Histogram::kSize], &cd[indexes[i] * Histogram::kSize], Histogram::kSize);
+        size_t hs = 0;
+        for (size_t i = 0; i < num; ++i) hs += gzb::jpeg::header_cost_bits(clustered[i]) / 8;
+        ++e.st.num_entropy_code_builds;
+        return hs;
+      };
+      // EntropyCodedDataSize (processor.cc:538-546), with the raw bit sums cached per component.
+      uint64_t raw_bits[3] = {0, 0, 0};
+      auto recount_bits = [&]() {
+        for (int c = 0; c < ncomp; ++c) {
+          uint64_t bits = 0;
+          const uint8_t* d = &ac_depths[c * Histogram::kSize];
+          for (int i = 0; i + 1 < Histogram::kSize; ++i) bits += static_cast<uint64_t>(ac_hist[c].counts[i] / 2) * (d[i] + (i & 0xf));
+          raw_bits[c] = bits;
+        }
+      };
+      auto coded_size = [&]() -> size_t {
+        size_t numbits = 0;
+        for (int c = 0; c < ncomp; ++c) numbits += raw_bits[c] + ((raw_bits[c] * 3 + 512) >> 10);
+        return (numbits + 7) / 8;
+      };
+      int ac_histogram_size = static_cast<int>(compute_entropy_codes());
+      recount_bits();
+      const int base_size = header_size + dc_size + ac_histogram_size + static_cast<int>(coded_size());
+      int prev_size = base_size;
 
-    std::vector<float> max_block_error(num_blocks);
-    std::vector<int> last_indexes(num_blocks);
-    std::vector<float> block_weight(num_blocks);
-    std::vector<OrderEntry> global_order;
-    std::vector<uint8_t> touched(num_blocks, 0);
-    std::vector<int> touched_list;
-    std::vector<uint32_t> prefix_count;
-    // windowed evaluation of the entropy-code rebuilds (see the walk below)
-    struct SymDelta { int16_t sym; int8_t c; int8_t w; };
-    struct UndoRec { int block; uint8_t c, k; int16_t old_idx; uint64_t old_mask; bool newly_touched; uint32_t delta_begin; };
-    struct CodeWindow {
-      size_t first = 0;
-      int nsteps = 0, changed_first = 0, break_step = -1, ac_histogram_size = 0;
-      uint32_t delta_begin[11];
-      Histogram hist[3];
-      uint8_t depths[3 * Histogram::kSize];
-      uint64_t raw[10][3];
-      int est[10];
-      gzb::jpeg::HuffCache caches[5];
-    };
-    std::vector<CodeWindow> windows;
-    std::vector<SymDelta> dlog;
-    std::vector<UndoRec> ulog;
-    bool first_up_iter = true;
-    const int directions[2] = {1, -1};
-    const int n_cerr = static_cast<int>(cand_errors.size());
-    const int n_ccoef = static_cast<int>(cand_coeffs.size());
-    for (int direction : directions) {
-      for (;;) {
-        // down-adjusting only makes the output larger (processor.cc:766-774)
-        if (stop_early && direction == -1 && prev_size > 1.01 * e.best_jpeg.size()) break;
-        int blocks_to_change = 0;
-        double tt = now_ms();
-        for (int rblock = 1; rblock <= 4; ++rblock) {
-          // distmap is all zeros until the first iteration has compared (processor.cc:777-780)
-          if (first_up_iter && gzb_clear_distmap(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
-          if (gzb_compute_block_error_adjustment_weights_f(e.ctx, direction, rblock, target_mul, factor, nullptr,
-                                                           block_weight.data()) != GZB_OK) return fail(GZB_ERR_CUDA);
-          { const double t1 = now_ms(); e.st.be_weights_ms += t1 - tt; tt = t1; }
-          // global_order in block order (processor.cc:786-813), built in parallel: count, then fill
-          {
-            const int T = std::max(1, std::min(e.pool->size(), num_blocks / 1024 + 1));
-            std::vector<size_t> cnt(T + 1, 0);
-            std::vector<int> btc(T, 0);
-            auto range = [&](int t, int* b0, int* b1) {
-              *b0 = static_cast<int>(static_cast<int64_t>(num_blocks) * t / T);
-              *b1 = static_cast<int>(static_cast<int64_t>(num_blocks) * (t + 1) / T);
-            };
-            auto count_block = [&](int b) -> int {
-              if (block_weight[b] == 0) return 0;
-              const int offset = std::max(0, std::min(cand_offsets[b], n_cerr - 1));
-              const int num_candidates = cand_offsets[b + 1] - offset;
-              return direction > 0 ? std::max(0, num_candidates - last_indexes[b]) : std::max(0, last_indexes[b]);
-            };
-            e.pool->run(T, [&](int t) {
-              int b0, b1;
-              range(t, &b0, &b1);
-              size_t n = 0;
-              int k = 0;
-              for (int b = b0; b < b1; ++b) { const int cb = count_block(b); n += cb; k += cb > 0; }
-              cnt[t + 1] = n;
-              btc[t] = k;
-            });
-            for (int t = 0; t < T; ++t) cnt[t + 1] += cnt[t];
-            global_order.resize(cnt[T]);
-            blocks_to_change = 0;
-            for (int t = 0; t < T; ++t) blocks_to_change += btc[t];
-            e.pool->run(T, [&](int t) {
-              int b0, b1;
-              range(t, &b0, &b1);
-              OrderEntry* o = global_order.data() + cnt[t];
-              for (int b = b0; b < b1; ++b) {
-                if (block_weight[b] == 0) continue;
-                const int last_index = last_indexes[b];
+      std::vector<float> max_block_error(num_blocks);
+      std::vector<int> last_indexes(num_blocks);
+      std::vector<float> block_weight(num_blocks);
+      std::vector<OrderEntry> global_order;
+      std::vector<uint8_t> touched(num_blocks, 0);
+      std::vector<int> touched_list;
+      std::vector<uint32_t> prefix_count;
+      // windowed evaluation of the entropy-code rebuilds (see the walk below)
+      struct SymDelta { int16_t sym; int8_t c; int8_t w; };
+      struct UndoRec { int block; uint8_t c, k; int16_t old_idx; uint64_t old_mask; bool newly_touched; uint32_t delta_begin; };
+      struct CodeWindow {
+        size_t first = 0;
+        int nsteps = 0, changed_first = 0, break_step = -1, ac_histogram_size = 0;
+        uint32_t delta_begin[11];
+        Histogram hist[3];
+        uint8_t depths[3 * Histogram::kSize];
+        uint64_t raw[10][3];
+        int est[10];
+        gzb::jpeg::HuffCache caches[5];
+      };
+      std::vector<CodeWindow> windows;
+      std::vector<SymDelta> dlog;
+      std::vector<UndoRec> ulog;
+      bool first_up_iter = true;
+      const int directions[2] = {1, -1};
+      const int n_cerr = static_cast<int>(cand_errors.size());
+      const int n_ccoef = static_cast<int>(cand_coeffs.size());
+      for (int direction : directions) {
+        for (;;) {
+          // down-adjusting only makes the output larger (processor.cc:766-774)
+          if (stop_early && direction == -1 && prev_size > 1.01 * e.best_jpeg.size()) break;
+          int blocks_to_change = 0;
+          double tt = now_ms();
+          for (int rblock = 1; rblock <= 4; ++rblock) {
+            // distmap is all zeros until the first iteration has compared (processor.cc:777-780)
+            if (first_up_iter && gzb_clear_distmap(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
+            if (gzb_compute_block_error_adjustment_weights_f(e.ctx, direction, rblock, target_mul, factor, nullptr,
+                                                             block_weight.data()) != GZB_OK) return fail(GZB_ERR_CUDA);
+            { const double t1 = now_ms(); e.st.be_weights_ms += t1 - tt; tt = t1; }
+            // global_order in block order (processor.cc:786-813), built in parallel: count, then fill
+            {
+              const int T = std::max(1, std::min(e.pool->size(), num_blocks / 1024 + 1));
+              std::vector<size_t> cnt(T + 1, 0);
+              std::vector<int> btc(T, 0);
+              auto range = [&](int t, int* b0, int* b1) {
+                *b0 = static_cast<int>(static_cast<int64_t>(num_blocks) * t / T);
+                *b1 = static_cast<int>(static_cast<int64_t>(num_blocks) * (t + 1) / T);
+              };
+              auto count_block = [&](int b) -> int {
+                if (block_weight[b] == 0) return 0;
                 const int offset = std::max(0, std::min(cand_offsets[b], n_cerr - 1));
                 const int num_candidates = cand_offsets[b + 1] - offset;
-                const float* errs = cand_errors.data() + offset;
-                const float max_err = max_block_error[b];
-                const float wgt = block_weight[b];
-                if (direction > 0) {
-                  for (int i = last_index; i < num_candidates; ++i) *o++ = std::make_pair(b, (errs[i] - max_err) / wgt);
-                } else {
-                  for (int i = last_index - 1; i >= 0; --i) *o++ = std::make_pair(b, (max_err - errs[i]) / wgt);
+                return direction > 0 ? std::max(0, num_candidates - last_indexes[b]) : std::max(0, last_indexes[b]);
+              };
+              e.pool->run(T, [&](int t) {
+                int b0, b1;
+                range(t, &b0, &b1);
+                size_t n = 0;
+                int k = 0;
+                for (int b = b0; b < b1; ++b) { const int cb = count_block(b); n += cb; k += cb > 0; }
+                cnt[t + 1] = n;
+                btc[t] = k;
+              });
+              for (int t = 0; t < T; ++t) cnt[t + 1] += cnt[t];
+              global_order.resize(cnt[T]);
+              blocks_to_change = 0;
+              for (int t = 0; t < T; ++t) blocks_to_change += btc[t];
+              e.pool->run(T, [&](int t) {
+                int b0, b1;
+                range(t, &b0, &b1);
+                OrderEntry* o = global_order.data() + cnt[t];
+                for (int b = b0; b < b1; ++b) {
+                  if (block_weight[b] == 0) continue;
+                  const int last_index = last_indexes[b];
+                  const int offset = std::max(0, std::min(cand_offsets[b], n_cerr - 1));
+                  const int num_candidates = cand_offsets[b + 1] - offset;
+                  const float* errs = cand_errors.data() + offset;
+                  const float max_err = max_block_error[b];
+                  const float wgt = block_weight[b];
+                  if (direction > 0) {
+                    for (int i = last_index; i < num_candidates; ++i) *o++ = std::make_pair(b, (errs[i] - max_err) / wgt);
+                  } else {
+                    for (int i = last_index - 1; i >= 0; --i) *o++ = std::make_pair(b, (max_err - errs[i]) / wgt);
+                  }
                 }
-              }
-            });
-          }
-          { const double t1 = now_ms(); e.st.be_order_ms += t1 - tt; tt = t1; }
-          if (!global_order.empty()) break;
-        }
-        if (global_order.empty()) break;
-
-        LazySort sorter(global_order.data(), global_order.size(), e.pool.get());
-        double rel_size_delta = direction > 0 ? 0.01 : 0.0005;
-        // DistanceOK(1.0) of the LAST Compare in the reference's order (in a group that may be a trial
-        // another rank evaluated, so the context's own last distance must not be used)
-        if (direction > 0 && static_cast<double>(e.distance) <= 1.0 * static_cast<double>(e.target)) rel_size_delta = 0.05;
-        const double min_size_delta = base_size * rel_size_delta;
-        const float coeffs_to_change_per_block = direction > 0 ? 2.0f : factor * factor * 0.2f;
-        int min_coeffs_to_change = static_cast<int>(coeffs_to_change_per_block * blocks_to_change);
-        if (first_up_iter) {
-          const float limit = 0.75f * gzb_block_error_limit(e.ctx);
-          // partition_point on the sorted order == number of entries below the limit
-          size_t below = 0;
-          {
-            const size_t n = global_order.size();
-            const int T = std::max(1, std::min<int>(e.pool->size(), static_cast<int>(n >> 16) + 1));
-            std::vector<size_t> part(T, 0);
-            e.pool->run(T, [&](int t) {
-              size_t cnt = 0;
-              for (size_t i = n * t / T, i1 = n * (t + 1) / T; i < i1; ++i) cnt += global_order[i].second < limit ? 1 : 0;
-              part[t] = cnt;
-            });
-            for (int t = 0; t < T; ++t) below += part[t];
-          }
-          min_coeffs_to_change = std::max<int>(min_coeffs_to_change, static_cast<int>(below));
-          first_up_iter = false;
-        }
-        float val_threshold = 0.0;
-        int changed_coeffs = 0;
-        int est_jpg_size = prev_size;
-        Flips* job = &flips;
-        job->clear();
-        const size_t order_size = global_order.size();
-        const size_t kAhead = 24;
-        // ---- the silent prefix ----
-        // While i + 9 < min_coeffs_to_change and i + 9 < order_size - 1 the reference's loop can
-        // neither stop nor have its entropy-code rebuild observed (processor.cc:879-903), so the
-        // first `prefix` entries of the sorted order are consumed as a SET: they need not be sorted,
-        // each block just takes as many of its next candidates as it has entries in the set, and the
-        // blocks are processed in parallel in block order (sequential memory) instead of in the
-        // order's random order. Histogram sums are order-independent.
-        size_t prefix = 0;
-        if (min_coeffs_to_change > 9 && order_size > 10)
-          prefix = std::min(static_cast<size_t>(min_coeffs_to_change - 9), order_size - 10);
-        // short prefixes are still consumed as a set (no sorting) but applied on this thread, below
-        size_t small_prefix = 0;
-        if (prefix < 8192 || e.pool->size() < 2) { small_prefix = prefix >= 64 ? prefix : 0; prefix = 0; }
-        if (prefix > 0) {
-          const double ts = now_ms();
-          sorter.ensure_set(prefix);
-          e.st.be_sort_ms += now_ms() - ts;
-          const int T = e.pool->size();
-          if (prefix_count.empty()) prefix_count.assign(num_blocks, 0);
-          e.pool->run(T, [&](int t) {
-            const size_t i0 = prefix * t / T, i1 = prefix * (t + 1) / T;
-            for (size_t i = i0; i < i1; ++i) __atomic_fetch_add(&prefix_count[global_order[i].first], 1u, __ATOMIC_RELAXED);
-          });
-          struct Local {
-            std::vector<int32_t> block; std::vector<uint8_t> cidx; std::vector<int16_t> val;
-            std::vector<int> touched;
-            int64_t hist[3][Histogram::kSize];
-          };
-          std::vector<Local> loc(T);
-          std::atomic<int> next_chunk(0);
-          const int kChunk = 512;
-          e.pool->run(T, [&](int t) {
-            Local& L = loc[t];
-            memset(L.hist, 0, sizeof(L.hist));
-            for (;;) {
-              const int b_begin = next_chunk.fetch_add(kChunk);
-              if (b_begin >= num_blocks) break;
-              const int b_end = std::min(num_blocks, b_begin + kChunk);
-              for (int b = b_begin; b < b_end; ++b) {
-                const uint32_t times = prefix_count[b];
-                if (!times) continue;
-                prefix_count[b] = 0;
-                L.touched.push_back(b);
-                const int offset = std::max(0, std::min(cand_offsets[b], n_ccoef - 1));
-                const uint8_t* candidates = cand_coeffs.data() + offset;
-                for (uint32_t rep = 0; rep < times; ++rep) {
-                  const int last_idx = last_indexes[b];
-                  const int cidx = candidates[last_idx + std::min(direction, 0)];
-                  const int c = cidx / 64, k = cidx % 64, z = gzb::jpeg::kZigZag[k];
-                  const int* qc = e.quant[c];
-                  const size_t cb = cblock(b);
-                  int16_t* blk_idx = e.idx[c].data() + cb * 64;
-                  const int16_t newval = direction > 0 ? 0 : quantize_coeff(e.orig[c][cb * 64 + k], qc[k]);
-                  const int16_t new_idx = static_cast<int16_t>(newval / qc[k]);
-                  const int16_t old_idx = blk_idx[k];
-                  uint64_t& m = zmask[c][cb];
-                  const uint64_t lower = m & ((1ULL << z) - 1);
-                  const int p = lower ? 63 - __builtin_clzll(lower) : 0;
-                  const uint64_t upper = z < 63 ? (m >> (z + 1)) : 0;
-                  const int n = upper ? z + 1 + __builtin_ctzll(upper) : 64;
-                  const int v_n = n < 64 ? blk_idx[gzb::jpeg::kNaturalOrder[n]] : 0;
-                  int64_t* hh = L.hist[c];
-                  auto add_run = [&](int run, int v, int weight) {
-                    while (run > 15) { hh[0xf0] += weight; run -= 16; }
-                    hh[(run << 4) + (32 - __builtin_clz(static_cast<unsigned>(std::abs(v))))] += weight;
-                  };
-                  auto emit = [&](int v_z, int weight) {
-                    if (v_z != 0) {
-                      add_run(z - p - 1, v_z, weight);
-                      if (n < 64) add_run(n - z - 1, v_n, weight);
-                      else if (z != 63) hh[0] += weight;
-                    } else {
-                      if (n < 64) add_run(n - p - 1, v_n, weight);
-                      else hh[0] += weight;
-                    }
-                  };
-                  emit(old_idx, -1);
-                  emit(new_idx, 1);
-                  blk_idx[k] = new_idx;
-                  if (new_idx != 0) m |= 1ULL << z; else m &= ~(1ULL << z);
-                  L.block.push_back(static_cast<int32_t>(cb)); L.cidx.push_back(static_cast<uint8_t>(cidx)); L.val.push_back(newval);
-                  last_indexes[b] += direction;
-                }
-              }
+              });
             }
-          });
-          for (int t = 0; t < T; ++t) {
-            Local& L = loc[t];
-            for (int c = 0; c < 3; ++c)
-              for (int i = 0; i + 1 < Histogram::kSize; ++i)
-                if (L.hist[c][i]) ac_hist[c].counts[i] = static_cast<uint32_t>(static_cast<int64_t>(ac_hist[c].counts[i]) + 2 * L.hist[c][i]);
-            job->block.insert(job->block.end(), L.block.begin(), L.block.end());
-            job->cidx.insert(job->cidx.end(), L.cidx.begin(), L.cidx.end());
-            job->val.insert(job->val.end(), L.val.begin(), L.val.end());
-            for (int b : L.touched) if (!touched[b]) { touched[b] = 1; touched_list.push_back(b); }
+            { const double t1 = now_ms(); e.st.be_order_ms += t1 - tt; tt = t1; }
+            if (!global_order.empty()) break;
           }
-          recount_bits();  // raw bit sums for the current codes and the new histograms
-          changed_coeffs = static_cast<int>(prefix);
-          e.st.be_steps += prefix;
-          e.st.be_prefix_steps += prefix;
-        } else if (small_prefix > 0) {
-          const double ts = now_ms();
-          sorter.ensure_set(small_prefix);
-          e.st.be_sort_ms += now_ms() - ts;
-        } else if (min_coeffs_to_change > 0) {  // the walk cannot stop before min_coeffs_to_change + 1 entries
-          const double ts = now_ms();
-          sorter.ensure_bulk(std::min<size_t>(static_cast<size_t>(min_coeffs_to_change), global_order.size() - 1));
-          e.st.be_sort_ms += now_ms() - ts;
-        }
-        // One step of the walk (processor.cc:843-876): flips the next candidate of the order's i-th
-        // block and updates the AC histograms by the symbols that change. With `dlog` the symbol
-        // deltas and an undo record are logged instead of being priced with the current codes.
-        auto flip = [&](size_t i, std::vector<SymDelta>* dlog, std::vector<UndoRec>* ulog) {
-          if (sorter.sorted() <= std::min(i + kAhead, order_size - 1)) {
+          if (global_order.empty()) break;
+
+          LazySort sorter(global_order.data(), global_order.size(), e.pool.get());
+          double rel_size_delta = direction > 0 ? 0.01 : 0.0005;
+          // DistanceOK(1.0) of the LAST Compare in the reference's order (in a group that may be a trial
+          // another rank evaluated, so the context's own last distance must not be used)
+          if (direction > 0 && static_cast<double>(e.distance) <= 1.0 * static_cast<double>(e.target)) rel_size_delta = 0.05;
+          const double min_size_delta = base_size * rel_size_delta;
+          const float coeffs_to_change_per_block = direction > 0 ? 2.0f : factor * factor * 0.2f;
+          int min_coeffs_to_change = static_cast<int>(coeffs_to_change_per_block * blocks_to_change);
+          if (first_up_iter) {
+            const float limit = 0.75f * gzb_block_error_limit(e.ctx);
+            // partition_point on the sorted order == number of entries below the limit
+            size_t below = 0;
+            {
+              const size_t n = global_order.size();
+              const int T = std::max(1, std::min<int>(e.pool->size(), static_cast<int>(n >> 16) + 1));
+              std::vector<size_t> part(T, 0);
+              e.pool->run(T, [&](int t) {
+                size_t cnt = 0;
+                for (size_t i = n * t / T, i1 = n * (t + 1) / T; i < i1; ++i) cnt += global_order[i].second < limit ? 1 : 0;
+                part[t] = cnt;
+              });
+              for (int t = 0; t < T; ++t) below += part[t];
+            }
+            min_coeffs_to_change = std::max<int>(min_coeffs_to_change, static_cast<int>(below));
+            first_up_iter = false;
+          }
+          float val_threshold = 0.0;
+          int changed_coeffs = 0;
+          int est_jpg_size = prev_size;
+          Flips* job = &flips;
+          job->clear();
+          const size_t order_size = global_order.size();
+          const size_t kAhead = 24;
+          // ---- the silent prefix ----
+          // While i + 9 < min_coeffs_to_change and i + 9 < order_size - 1 the reference's loop can
+          // neither stop nor have its entropy-code rebuild observed (processor.cc:879-903), so the
+          // first `prefix` entries of the sorted order are consumed as a SET: they need not be sorted,
+          // each block just takes as many of its next candidates as it has entries in the set, and the
+          // blocks are processed in parallel in block order (sequential memory) instead of in the
+          // order's random order. Histogram sums are order-independent.
+          size_t prefix = 0;
+          if (min_coeffs_to_change > 9 && order_size > 10)
+            prefix = std::min(static_cast<size_t>(min_coeffs_to_change - 9), order_size - 10);
+          // short prefixes are still consumed as a set (no sorting) but applied on this thread, below
+          size_t small_prefix = 0;
+          if (prefix < 8192 || e.pool->size() < 2) { small_prefix = prefix >= 64 ? prefix : 0; prefix = 0; }
+          if (prefix > 0) {
             const double ts = now_ms();
-            sorter.ensure(std::min(i + kAhead, order_size - 1));
+            sorter.ensure_set(prefix);
+            e.st.be_sort_ms += now_ms() - ts;
+            const int T = e.pool->size();
+            if (prefix_count.empty()) prefix_count.assign(num_blocks, 0);
+            e.pool->run(T, [&](int t) {
+              const size_t i0 = prefix * t / T, i1 = prefix * (t + 1) / T;
+              for (size_t i = i0; i < i1; ++i) __atomic_fetch_add(&prefix_count[global_order[i].first], 1u, __ATOMIC_RELAXED);
+            });
+            struct Local {
+              std::vector<int32_t> block; std::vector<uint8_t> cidx; std::vector<int16_t> val;
+              std::vector<int> touched;
+              int64_t hist[3][Histogram::kSize];
+            };
+            std::vector<Local> loc(T);
+            std::atomic<int> next_chunk(0);
+            const int kChunk = 512;
+            e.pool->run(T, [&](int t) {
+              Local& L = loc[t];
+              memset(L.hist, 0, sizeof(L.hist));
+              for (;;) {
+                const int b_begin = next_chunk.fetch_add(kChunk);
+                if (b_begin >= num_blocks) break;
+                const int b_end = std::min(num_blocks, b_begin + kChunk);
+                for (int b = b_begin; b < b_end; ++b) {
+                  const uint32_t times = prefix_count[b];
+                  if (!times) continue;
+                  prefix_count[b] = 0;
+                  L.touched.push_back(b);
+                  const int offset = std::max(0, std::min(cand_offsets[b], n_ccoef - 1));
+                  const uint8_t* candidates = cand_coeffs.data() + offset;
+                  for (uint32_t rep = 0; rep < times; ++rep) {
+                    const int last_idx = last_indexes[b];
+                    const int cidx = candidates[last_idx + std::min(direction, 0)];
+                    const int c = cidx / 64, k = cidx % 64, z = gzb::jpeg::kZigZag[k];
+                    const int* qc = e.quant[c];
+                    const size_t cb = cblock(b);
+                    int16_t* blk_idx = e.idx[c].data() + cb * 64;
+                    const int16_t newval = direction > 0 ? 0 : quantize_coeff(e.orig[c][cb * 64 + k], qc[k]);
+                    const int16_t new_idx = static_cast<int16_t>(newval / qc[k]);
+                    const int16_t old_idx = blk_idx[k];
+                    uint64_t& m = zmask[c][cb];
+                    const uint64_t lower = m & ((1ULL << z) - 1);
+                    const int p = lower ? 63 - __builtin_clzll(lower) : 0;
+                    const uint64_t upper = z < 63 ? (m >> (z + 1)) : 0;
+                    const int n = upper ? z + 1 + __builtin_ctzll(upper) : 64;
+                    const int v_n = n < 64 ? blk_idx[gzb::jpeg::kNaturalOrder[n]] : 0;
+                    int64_t* hh = L.hist[c];
+                    auto add_run = [&](int run, int v, int weight) {
+                      while (run > 15) { hh[0xf0] += weight; run -= 16; }
+                      hh[(run << 4) + (32 - __builtin_clz(static_cast<unsigned>(std::abs(v))))] += weight;
+                    };
+                    auto emit = [&](int v_z, int weight) {
+                      if (v_z != 0) {
+                        add_run(z - p - 1, v_z, weight);
+                        if (n < 64) add_run(n - z - 1, v_n, weight);
+                        else if (z != 63) hh[0] += weight;
+                      } else {
+                        if (n < 64) add_run(n - p - 1, v_n, weight);
+                        else hh[0] += weight;
+                      }
+                    };
+                    emit(old_idx, -1);
+                    emit(new_idx, 1);
+                    blk_idx[k] = new_idx;
+                    if (new_idx != 0) m |= 1ULL << z; else m &= ~(1ULL << z);
+                    L.block.push_back(static_cast<int32_t>(cb)); L.cidx.push_back(static_cast<uint8_t>(cidx)); L.val.push_back(newval);
+                    last_indexes[b] += direction;
+                  }
+                }
+              }
+            });
+            for (int t = 0; t < T; ++t) {
+              Local& L = loc[t];
+              for (int c = 0; c < 3; ++c)
+                for (int i = 0; i + 1 < Histogram::kSize; ++i)
+                  if (L.hist[c][i]) ac_hist[c].counts[i] = static_cast<uint32_t>(static_cast<int64_t>(ac_hist[c].counts[i]) + 2 * L.hist[c][i]);
+              job->block.insert(job->block.end(), L.block.begin(), L.block.end());
+              job->cidx.insert(job->cidx.end(), L.cidx.begin(), L.cidx.end());
+              job->val.insert(job->val.end(), L.val.begin(), L.val.end());
+              for (int b : L.touched) if (!touched[b]) { touched[b] = 1; touched_list.push_back(b); }
+            }
+            recount_bits();  // raw bit sums for the current codes and the new histograms
+            changed_coeffs = static_cast<int>(prefix);
+            e.st.be_steps += prefix;
+            e.st.be_prefix_steps += prefix;
+          } else if (small_prefix > 0) {
+            const double ts = now_ms();
+            sorter.ensure_set(small_prefix);
+            e.st.be_sort_ms += now_ms() - ts;
+          } else if (min_coeffs_to_change > 0) {  // the walk cannot stop before min_coeffs_to_change + 1 entries
+            const double ts = now_ms();
+            sorter.ensure_bulk(std::min<size_t>(static_cast<size_t>(min_coeffs_to_change), global_order.size() - 1));
             e.st.be_sort_ms += now_ms() - ts;
           }
-          // three-stage software prefetch of the randomly scattered per-block state
-          if (i + kAhead < order_size) {
-            const int pb = global_order[i + kAhead].first;
-            __builtin_prefetch(&last_indexes[pb]);
-            __builtin_prefetch(&cand_offsets[pb]);
-          }
-          if (i + kAhead / 2 < order_size) {
-            const int pb = global_order[i + kAhead / 2].first;
-            const int po = std::max(0, std::min(cand_offsets[pb], n_ccoef - 1));
-            __builtin_prefetch(&cand_coeffs[po + std::max(0, last_indexes[pb] + std::min(direction, 0))]);
-          }
-          if (i + kAhead / 4 < order_size) {
-            const int pb = global_order[i + kAhead / 4].first;
-            const int po = std::max(0, std::min(cand_offsets[pb], n_ccoef - 1));
-            const int pi = cand_coeffs[po + std::max(0, last_indexes[pb] + std::min(direction, 0))];
-            const int pc = pi >> 6;
-            const size_t pcb = cblock(pb);
-            __builtin_prefetch(&zmask[pc][pcb]);
-            __builtin_prefetch(e.idx[pc].data() + pcb * 64);
-            __builtin_prefetch(e.idx[pc].data() + pcb * 64 + 32);
-            if (direction < 0) __builtin_prefetch(e.orig[pc].data() + pcb * 64 + (pi & 63));
-          }
-          const int b = global_order[i].first;
-          const int last_idx = last_indexes[b];
-          const int offset = std::max(0, std::min(cand_offsets[b], n_ccoef - 1));
-          const uint8_t* candidates = cand_coeffs.data() + offset;
-          const int cidx = candidates[last_idx + std::min(direction, 0)];
-          const int c = cidx / 64, k = cidx % 64, z = gzb::jpeg::kZigZag[k];
-          const int* qc = e.quant[c];
-          const size_t cb = cblock(b);
-          int16_t* blk_idx = e.idx[c].data() + cb * 64;
-          const int16_t newval = direction > 0 ? 0 : quantize_coeff(e.orig[c][cb * 64 + k], qc[k]);
-          const int16_t new_idx = static_cast<int16_t>(newval / qc[k]);
-          const int16_t old_idx = blk_idx[k];
-          // UpdateACHistogram(-1, old block); UpdateACHistogram(+1, new block) (processor.cc:491-515,
-          // 871-873) restricted to the symbols that differ: those between the previous (p) and the
-          // next (n) non-zero coefficient around zig-zag position z.
-          uint64_t& m = zmask[c][cb];
-          if (ulog) ulog->push_back(UndoRec{b, static_cast<uint8_t>(c), static_cast<uint8_t>(k), old_idx, m, touched[b] == 0,
-                                            static_cast<uint32_t>(dlog->size())});
-          const uint64_t lower = m & ((1ULL << z) - 1);
-          const int p = lower ? 63 - __builtin_clzll(lower) : 0;
-          const uint64_t upper = z < 63 ? (m >> (z + 1)) : 0;
-          const int n = upper ? z + 1 + __builtin_ctzll(upper) : 64;
-          const int v_n = n < 64 ? blk_idx[gzb::jpeg::kNaturalOrder[n]] : 0;
-          Histogram& hh = ac_hist[c];
-          const uint8_t* d = &ac_depths[c * Histogram::kSize];
-          auto add_sym = [&](int sym, int weight) {
-            hh.add(sym, weight);
-            if (dlog) dlog->push_back(SymDelta{static_cast<int16_t>(sym), static_cast<int8_t>(c), static_cast<int8_t>(weight)});
-            else raw_bits[c] += static_cast<int64_t>(weight) * (d[sym] + (sym & 0xf));
-          };
-          auto add_run = [&](int run, int v, int weight) {
-            while (run > 15) { add_sym(0xf0, weight); run -= 16; }
-            add_sym((run << 4) + (32 - __builtin_clz(static_cast<unsigned>(std::abs(v)))), weight);
-          };
-          auto emit = [&](int v_z, int weight) {
-            if (v_z != 0) {
-              add_run(z - p - 1, v_z, weight);
-              if (n < 64) add_run(n - z - 1, v_n, weight);
-              else if (z != 63) add_sym(0, weight);
-            } else {
-              if (n < 64) add_run(n - p - 1, v_n, weight);
-              else add_sym(0, weight);
+          // One step of the walk (processor.cc:843-876): flips the next candidate of the order's i-th
+          // block and updates the AC histograms by the symbols that change. With `dlog` the symbol
+          // deltas and an undo record are logged instead of being priced with the current codes.
+          auto flip = [&](size_t i, std::vector<SymDelta>* dlog, std::vector<UndoRec>* ulog) {
+            if (sorter.sorted() <= std::min(i + kAhead, order_size - 1)) {
+              const double ts = now_ms();
+              sorter.ensure(std::min(i + kAhead, order_size - 1));
+              e.st.be_sort_ms += now_ms() - ts;
             }
+            // three-stage software prefetch of the randomly scattered per-block state
+            if (i + kAhead < order_size) {
+              const int pb = global_order[i + kAhead].first;
+              __builtin_prefetch(&last_indexes[pb]);
+              __builtin_prefetch(&cand_offsets[pb]);
+            }
+            if (i + kAhead / 2 < order_size) {
+              const int pb = global_order[i + kAhead / 2].first;
+              const int po = std::max(0, std::min(cand_offsets[pb], n_ccoef - 1));
+              __builtin_prefetch(&cand_coeffs[po + std::max(0, last_indexes[pb] + std::min(direction, 0))]);
+            }
+            if (i + kAhead / 4 < order_size) {
+              const int pb = global_order[i + kAhead / 4].first;
+              const int po = std::max(0, std::min(cand_offsets[pb], n_ccoef - 1));
+              const int pi = cand_coeffs[po + std::max(0, last_indexes[pb] + std::min(direction, 0))];
+              const int pc = pi >> 6;
+              const size_t pcb = cblock(pb);
+              __builtin_prefetch(&zmask[pc][pcb]);
+              __builtin_prefetch(e.idx[pc].data() + pcb * 64);
+              __builtin_prefetch(e.idx[pc].data() + pcb * 64 + 32);
+              if (direction < 0) __builtin_prefetch(e.orig[pc].data() + pcb * 64 + (pi & 63));
+            }
+            const int b = global_order[i].first;
+            const int last_idx = last_indexes[b];
+            const int offset = std::max(0, std::min(cand_offsets[b], n_ccoef - 1));
+            const uint8_t* candidates = cand_coeffs.data() + offset;
+            const int cidx = candidates[last_idx + std::min(direction, 0)];
+            const int c = cidx / 64, k = cidx % 64, z = gzb::jpeg::kZigZag[k];
+            const int* qc = e.quant[c];
+            const size_t cb = cblock(b);
+            int16_t* blk_idx = e.idx[c].data() + cb * 64;
+            const int16_t newval = direction > 0 ? 0 : quantize_coeff(e.orig[c][cb * 64 + k], qc[k]);
+            const int16_t new_idx = static_cast<int16_t>(newval / qc[k]);
+            const int16_t old_idx = blk_idx[k];
+            // UpdateACHistogram(-1, old block); UpdateACHistogram(+1, new block) (processor.cc:491-515,
+            // 871-873) restricted to the symbols that differ: those between the previous (p) and the
+            // next (n) non-zero coefficient around zig-zag position z.
+            uint64_t& m = zmask[c][cb];
+            if (ulog) ulog->push_back(UndoRec{b, static_cast<uint8_t>(c), static_cast<uint8_t>(k), old_idx, m, touched[b] == 0,
+                                              static_cast<uint32_t>(dlog->size())});
+            const uint64_t lower = m & ((1ULL << z) - 1);
+            const int p = lower ? 63 - __builtin_clzll(lower) : 0;
+            const uint64_t upper = z < 63 ? (m >> (z + 1)) : 0;
+            const int n = upper ? z + 1 + __builtin_ctzll(upper) : 64;
+            const int v_n = n < 64 ? blk_idx[gzb::jpeg::kNaturalOrder[n]] : 0;
+            Histogram& hh = ac_hist[c];
+            const uint8_t* d = &ac_depths[c * Histogram::kSize];
+            auto add_sym = [&](int sym, int weight) {
+              hh.add(sym, weight);
+              if (dlog) dlog->push_back(SymDelta{static_cast<int16_t>(sym), static_cast<int8_t>(c), static_cast<int8_t>(weight)});
+              else raw_bits[c] += static_cast<int64_t>(weight) * (d[sym] + (sym & 0xf));
+            };
+            auto add_run = [&](int run, int v, int weight) {
+              while (run > 15) { add_sym(0xf0, weight); run -= 16; }
+              add_sym((run << 4) + (32 - __builtin_clz(static_cast<unsigned>(std::abs(v)))), weight);
+            };
+            auto emit = [&](int v_z, int weight) {
+              if (v_z != 0) {
+                add_run(z - p - 1, v_z, weight);
+                if (n < 64) add_run(n - z - 1, v_n, weight);
+                else if (z != 63) add_sym(0, weight);
+              } else {
+                if (n < 64) add_run(n - p - 1, v_n, weight);
+                else add_sym(0, weight);
+              }
+            };
+            emit(old_idx, -1);
+            emit(new_idx, 1);
+            blk_idx[k] = new_idx;
+            if (new_idx != 0) m |= 1ULL << z; else m &= ~(1ULL << z);
+            job->block.push_back(static_cast<int32_t>(cb)); job->cidx.push_back(static_cast<uint8_t>(cidx)); job->val.push_back(newval);
+            last_indexes[b] += direction;
+            if (!touched[b]) { touched[b] = 1; touched_list.push_back(b); }
+            ++changed_coeffs;
+            ++e.st.be_steps;
           };
-          emit(old_idx, -1);
-          emit(new_idx, 1);
-          blk_idx[k] = new_idx;
-          if (new_idx != 0) m |= 1ULL << z; else m &= ~(1ULL << z);
-          job->block.push_back(static_cast<int32_t>(cb)); job->cidx.push_back(static_cast<uint8_t>(cidx)); job->val.push_back(newval);
-          last_indexes[b] += direction;
-          if (!touched[b]) { touched[b] = 1; touched_list.push_back(b); }
-          ++changed_coeffs;
-          ++e.st.be_steps;
-        };
-        auto rebuild_needed = [&](size_t i) {
-          // Evaluate only where the result can be observed: by the break test within the next 10
-          // steps, or as prev_size when the order is about to run out.
-          return static_cast<long long>(i) + 9 >= min_coeffs_to_change || i + 9 >= order_size - 1;
-        };
-        if (small_prefix > 0) {   // the set, in array order (any order gives the same state)
-          for (size_t i = 0; i < small_prefix; ++i) flip(i, nullptr, nullptr);
-          recount_bits();
-          e.st.be_prefix_steps += small_prefix;
-          prefix = small_prefix;
-        }
-        const bool windowed = e.pool->size() >= 4;
-        size_t i = prefix;
-        bool stopped = false;
-        size_t last_step = prefix;   // index of the last step that stays applied
-        // ---- the steps up to the first observable entropy-code rebuild: the reference's loop as is ----
-        for (; i < order_size; ++i) {
-          if (windowed && i % 10 == 0 && rebuild_needed(i)) break;
-          flip(i, nullptr, nullptr);
-          last_step = i;
-          if (i % 10 == 0 && rebuild_needed(i)) {
-            const double tb = now_ms();
-            ac_histogram_size = static_cast<int>(compute_entropy_codes());
+          auto rebuild_needed = [&](size_t i) {
+            // Evaluate only where the result can be observed: by the break test within the next 10
+            // steps, or as prev_size when the order is about to run out.
+            return static_cast<long long>(i) + 9 >= min_coeffs_to_change || i + 9 >= order_size - 1;
+          };
+          if (small_prefix > 0) {   // the set, in array order (any order gives the same state)
+            for (size_t i = 0; i < small_prefix; ++i) flip(i, nullptr, nullptr);
             recount_bits();
-            e.st.be_codes_ms += now_ms() - tb;
+            e.st.be_prefix_steps += small_prefix;
+            prefix = small_prefix;
           }
-          if (changed_coeffs > min_coeffs_to_change || i + 1 == order_size) {
-            est_jpg_size = header_size + dc_size + ac_histogram_size + static_cast<int>(coded_size());
-            if (changed_coeffs > min_coeffs_to_change && std::abs(est_jpg_size - prev_size) > min_size_delta) { stopped = true; break; }
-          }
-        }
-        // ---- from there on: windows of ten steps, each opening with a ComputeEntropyCodes rebuild ----
-        // The flips do not depend on the codes (only the stopping test does), so this thread walks a
-        // batch of windows ahead, logging symbol deltas and undo records, the pool rebuilds the codes
-        // of every window and replays its size estimates in parallel, and the flips past the first
-        // window that stops are undone. Decisions are those of the one-step-at-a-time loop.
-        if (windowed && !stopped && i < order_size) {
-          const int NB = 2 * e.pool->size();
-          if (static_cast<int>(windows.size()) < NB) windows.resize(NB);
-          while (!stopped && i < order_size) {
-            const double tb = now_ms();
-            dlog.clear();
-            ulog.clear();
-            const size_t i0 = i;
-            int nw = 0;
-            while (nw < NB && i < order_size) {
-              CodeWindow& W = windows[nw++];
-              W.first = i;
-              W.nsteps = 0;
-              W.break_step = -1;
-              for (int st = 0; st < 10 && i < order_size; ++st, ++i) {
-                W.delta_begin[st] = static_cast<uint32_t>(dlog.size());
-                flip(i, &dlog, &ulog);
-                if (st == 0) {
-                  for (int c = 0; c < 3; ++c) W.hist[c] = ac_hist[c];
-                  W.changed_first = changed_coeffs;
-                }
-                ++W.nsteps;
-              }
-              W.delta_begin[W.nsteps] = static_cast<uint32_t>(dlog.size());
+          const bool windowed = e.pool->size() >= 4;
+          size_t i = prefix;
+          bool stopped = false;
+          size_t last_step = prefix;   // index of the last step that stays applied
+          // ---- the steps up to the first observable entropy-code rebuild: the reference's loop as is ----
+          for (; i < order_size; ++i) {
+            if (windowed && i % 10 == 0 && rebuild_needed(i)) break;
+            flip(i, nullptr, nullptr);
+            last_step = i;
+            if (i % 10 == 0 && rebuild_needed(i)) {
+              const double tb = now_ms();
+              ac_histogram_size = static_cast<int>(compute_entropy_codes());
+              recount_bits();
+              e.st.be_codes_ms += now_ms() - tb;
             }
-            e.pool->run(nw, [&](int w) {
-              CodeWindow& W = windows[w];
-              Histogram clustered[3] = {W.hist[0], W.hist[1], W.hist[2]};
-              size_t num = ncomp;
-              int indexes[4];
-              uint8_t cd[3 * Histogram::kSize];
-              gzb::jpeg::cluster_histograms(clustered, &num, indexes, cd, W.caches);
-              for (int c = 0; c < ncomp; ++c)
-                memcpy(&W.depths[c * Histogram::kSize], &cd[indexes[c] * Histogram::kSize], Histogram::kSize);
-              size_t hs = 0;
-              for (size_t k = 0; k < num; ++k) hs += gzb::jpeg::header_cost_bits(clustered[k]) / 8;
-              W.ac_histogram_size = static_cast<int>(hs);
-              uint64_t raw[3] = {0, 0, 0};
-              for (int c = 0; c < ncomp; ++c) {
-                const uint8_t* d = &W.depths[c * Histogram::kSize];
-                uint64_t bits = 0;
-                for (int k = 0; k + 1 < Histogram::kSize; ++k) bits += static_cast<uint64_t>(W.hist[c].counts[k] / 2) * (d[k] + (k & 0xf));
-                raw[c] = bits;
-              }
-              for (int st = 0; st < W.nsteps; ++st) {
-                if (st > 0)
-                  for (uint32_t j = W.delta_begin[st]; j < W.delta_begin[st + 1]; ++j) {
-                    const SymDelta& dl = dlog[j];
-                    raw[dl.c] += static_cast<int64_t>(dl.w) * (W.depths[dl.c * Histogram::kSize + dl.sym] + (dl.sym & 0xf));
+            if (changed_coeffs > min_coeffs_to_change || i + 1 == order_size) {
+              est_jpg_size = header_size + dc_size + ac_histogram_size + static_cast<int>(coded_size());
+              if (changed_coeffs > min_coeffs_to_change && std::abs(est_jpg_size - prev_size) > min_size_delta) { stopped = true; break; }
+            }
+          }
+          // ---- from there on: windows of ten steps, each opening with a ComputeEntropyCodes rebuild ----
+          // The flips do not depend on the codes (only the stopping test does), so this thread walks a
+          // batch of windows ahead, logging symbol deltas and undo records, the pool rebuilds the codes
+          // of every window and replays its size estimates in parallel, and the flips past the first
+          // window that stops are undone. Decisions are those of the one-step-at-a-time loop.
+          if (windowed && !stopped && i < order_size) {
+            const int NB = 2 * e.pool->size();
+            if (static_cast<int>(windows.size()) < NB) windows.resize(NB);
+            while (!stopped && i < order_size) {
+              const double tb = now_ms();
+              dlog.clear();
+              ulog.clear();
+              const size_t i0 = i;
+              int nw = 0;
+              while (nw < NB && i < order_size) {
+                CodeWindow& W = windows[nw++];
+                W.first = i;
+                W.nsteps = 0;
+                W.break_step = -1;
+                for (int st = 0; st < 10 && i < order_size; ++st, ++i) {
+                  W.delta_begin[st] = static_cast<uint32_t>(dlog.size());
+                  flip(i, &dlog, &ulog);
+                  if (st == 0) {
+                    for (int c = 0; c < 3; ++c) W.hist[c] = ac_hist[c];
+                    W.changed_first = changed_coeffs;
                   }
-                for (int c = 0; c < 3; ++c) W.raw[st][c] = raw[c];
-                const int changed = W.changed_first + st;
-                W.est[st] = -1;
-                if (changed > min_coeffs_to_change || W.first + st + 1 == order_size) {
-                  size_t numbits = 0;
-                  for (int c = 0; c < ncomp; ++c) numbits += raw[c] + ((raw[c] * 3 + 512) >> 10);
-                  const int est = header_size + dc_size + W.ac_histogram_size + static_cast<int>((numbits + 7) / 8);
-                  W.est[st] = est;
-                  if (changed > min_coeffs_to_change && std::abs(est - prev_size) > min_size_delta) { W.break_step = st; break; }
+                  ++W.nsteps;
+                }
+                W.delta_begin[W.nsteps] = static_cast<uint32_t>(dlog.size());
+              }
+              e.pool->run(nw, [&](int w) {
+                CodeWindow& W = windows[w];
+                Histogram clustered[3] = {W.hist[0], W.hist[1], W.hist[2]};
+                size_t num = ncomp;
+                int indexes[4];
+                uint8_t cd[3 * Histogram::kSize];
+                gzb::jpeg::cluster_histograms(clustered, &num, indexes, cd, W.caches);
+                for (int c = 0; c < ncomp; ++c)
+                  memcpy(&W.depths[c * Histogram::kSize], &cd[indexes[c] * Histogram::kSize], Histogram::kSize);
+                size_t hs = 0;
+                for (size_t k = 0; k < num; ++k) hs += gzb::jpeg::header_cost_bits(clustered[k]) / 8;
+                W.ac_histogram_size = static_cast<int>(hs);
+                uint64_t raw[3] = {0, 0, 0};
+                for (int c = 0; c < ncomp; ++c) {
+                  const uint8_t* d = &W.depths[c * Histogram::kSize];
+                  uint64_t bits = 0;
+                  for (int k = 0; k + 1 < Histogram::kSize; ++k) bits += static_cast<uint64_t>(W.hist[c].counts[k] / 2) * (d[k] + (k & 0xf));
+                  raw[c] = bits;
+                }
+                for (int st = 0; st < W.nsteps; ++st) {
+                  if (st > 0)
+                    for (uint32_t j = W.delta_begin[st]; j < W.delta_begin[st + 1]; ++j) {
+                      const SymDelta& dl = dlog[j];
+                      raw[dl.c] += static_cast<int64_t>(dl.w) * (W.depths[dl.c * Histogram::kSize + dl.sym] + (dl.sym & 0xf));
+                    }
+                  for (int c = 0; c < 3; ++c) W.raw[st][c] = raw[c];
+                  const int changed = W.changed_first + st;
+                  W.est[st] = -1;
+                  if (changed > min_coeffs_to_change || W.first + st + 1 == order_size) {
+                    size_t numbits = 0;
+                    for (int c = 0; c < ncomp; ++c) numbits += raw[c] + ((raw[c] * 3 + 512) >> 10);
+                    const int est = header_size + dc_size + W.ac_histogram_size + static_cast<int>((numbits + 7) / 8);
+                    W.est[st] = est;
+                    if (changed > min_coeffs_to_change && std::abs(est - prev_size) > min_size_delta) { W.break_step = st; break; }
+                  }
+                }
+              });
+              int final_w = nw - 1, final_st = windows[nw - 1].nsteps - 1;
+              for (int w = 0; w < nw; ++w)
+                if (windows[w].break_step >= 0) { final_w = w; final_st = windows[w].break_step; stopped = true; break; }
+              const CodeWindow& F = windows[final_w];
+              e.st.num_entropy_code_builds += final_w + 1;
+              last_step = F.first + final_st;
+              if (stopped) {  // undo the steps walked past the stop
+                const size_t keep = last_step + 1 - i0;
+                if (keep < ulog.size()) {
+                  for (size_t j = dlog.size(); j-- > ulog[keep].delta_begin;) ac_hist[dlog[j].c].add(dlog[j].sym, -dlog[j].w);
+                  for (size_t j = ulog.size(); j-- > keep;) {
+                    const UndoRec& u = ulog[j];
+                    e.idx[u.c][cblock(u.block) * 64 + u.k] = u.old_idx;
+                    zmask[u.c][cblock(u.block)] = u.old_mask;
+                    last_indexes[u.block] -= direction;
+                    if (u.newly_touched) { touched[u.block] = 0; touched_list.pop_back(); }
+                    job->block.pop_back(); job->cidx.pop_back(); job->val.pop_back();
+                    --changed_coeffs;
+                    --e.st.be_steps;
+                  }
                 }
               }
-            });
-            int final_w = nw - 1, final_st = windows[nw - 1].nsteps - 1;
-            for (int w = 0; w < nw; ++w)
-              if (windows[w].break_step >= 0) { final_w = w; final_st = windows[w].break_step; stopped = true; break; }
-            const CodeWindow& F = windows[final_w];
-            e.st.num_entropy_code_builds += final_w + 1;
-            last_step = F.first + final_st;
-            if (stopped) {  // undo the steps walked past the stop
-              const size_t keep = last_step + 1 - i0;
-              if (keep < ulog.size()) {
-                for (size_t j = dlog.size(); j-- > ulog[keep].delta_begin;) ac_hist[dlog[j].c].add(dlog[j].sym, -dlog[j].w);
-                for (size_t j = ulog.size(); j-- > keep;) {
-                  const UndoRec& u = ulog[j];
-                  e.idx[u.c][cblock(u.block) * 64 + u.k] = u.old_idx;
-                  zmask[u.c][cblock(u.block)] = u.old_mask;
-                  last_indexes[u.block] -= direction;
-                  if (u.newly_touched) { touched[u.block] = 0; touched_list.pop_back(); }
-                  job->block.pop_back(); job->cidx.pop_back(); job->val.pop_back();
-                  --changed_coeffs;
-                  --e.st.be_steps;
-                }
-              }
+              memcpy(ac_depths.data(), F.depths, 3 * Histogram::kSize);
+              ac_histogram_size = F.ac_histogram_size;
+              for (int c = 0; c < 3; ++c) raw_bits[c] = F.raw[final_st][c];
+              if (F.est[final_st] >= 0) est_jpg_size = F.est[final_st];
+              e.st.be_codes_ms += now_ms() - tb;
             }
-            memcpy(ac_depths.data(), F.depths, 3 * Histogram::kSize);
-            ac_histogram_size = F.ac_histogram_size;
-            for (int c = 0; c < 3; ++c) raw_bits[c] = F.raw[final_st][c];
-            if (F.est[final_st] >= 0) est_jpg_size = F.est[final_st];
-            e.st.be_codes_ms += now_ms() - tb;
           }
+          if (changed_coeffs > 0) val_threshold = global_order[last_step].second;
+          const size_t changed_blocks = touched_list.size();
+          for (int tb : touched_list) touched[tb] = 0;
+          touched_list.clear();
+          for (int i = 0; i < num_blocks; ++i) max_block_error[i] += block_weight[i] * val_threshold * direction;
+          { const double t1 = now_ms(); e.st.be_walk_ms += t1 - tt; tt = t1; }
+          ++e.st.num_iterations;
+          if (direction > 0) ++e.st.num_iterations_up; else ++e.st.num_iterations_down;
+          // push the changed coefficients to the device; the file is written by the writer stage while
+          // the GPU compares and the next iteration walks
+          if (gzb_update_coeffs(e.ctx, job->block.data(), job->cidx.data(), job->val.data(), job->block.size()) != GZB_OK)
+            return fail(GZB_ERR_CUDA);
+          { const double t1 = now_ms(); e.st.be_update_ms += t1 - tt; tt = t1; }
+          if (!e.compare_begin()) return fail(GZB_ERR_CUDA);
+          // the iteration's file: coded on the device (second stream, concurrently with the Compare)
+          // with the histograms the walk maintains; only its size is needed unless it becomes the best
+          // (processor.cc:897-915, MaybeOutput 151-160)
+          const double tw = now_ms();
+          DeviceJpeg dj;
+          if (!device_code_candidate(e.ctx, width, height, e.nb, e.quant, false, dc_hist, ac_hist, &dj, e.yuv420)) return fail(GZB_ERR_CUDA);
+          ++e.code_gen;
+          e.st.num_jpeg_writes++;
+          e.st.device_write_ms += now_ms() - tw;
+          if (!e.compare_end()) return fail(GZB_ERR_CUDA);
+          const size_t jpg_size = dj.size();
+          e.log("Iter %2d: %s(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
+                e.st.num_iterations, e.frame_type(), comp_mask, direction > 0 ? "up" : "down", changed_coeffs, order_size,
+                changed_blocks, blocks_to_change, num_blocks, val_threshold, jpg_size,
+                100.0 - (100.0 * est_jpg_size) / jpg_size);
+          e.log(" BA[100.00%%] D[%6.4f]", e.distance);
+          const double score = score_jpeg(e.distance, static_cast<int>(jpg_size), e.target);
+          e.log(" Score[%.4f]", score);
+          if (score < e.best_score || e.best_score < 0) {
+            if (!device_fetch_jpeg(e.ctx, dj, &e.best_jpeg)) return fail(GZB_ERR_CUDA);
+            e.best_score = score;
+            e.best_remote = false;
+            e.log(" (*)");
+          }
+          e.log("\n");
+          prev_size = est_jpg_size;
         }
-        if (changed_coeffs > 0) val_threshold = global_order[last_step].second;
-        const size_t changed_blocks = touched_list.size();
-        for (int tb : touched_list) touched[tb] = 0;
-        touched_list.clear();
-        for (int i = 0; i < num_blocks; ++i) max_block_error[i] += block_weight[i] * val_threshold * direction;
-        { const double t1 = now_ms(); e.st.be_walk_ms += t1 - tt; tt = t1; }
-        ++e.st.num_iterations;
-        if (direction > 0) ++e.st.num_iterations_up; else ++e.st.num_iterations_down;
-        // push the changed coefficients to the device; the file is written by the writer stage while
-        // the GPU compares and the next iteration walks
-        if (gzb_update_coeffs(e.ctx, job->block.data(), job->cidx.data(), job->val.data(), job->block.size()) != GZB_OK)
-          return fail(GZB_ERR_CUDA);
-        { const double t1 = now_ms(); e.st.be_update_ms += t1 - tt; tt = t1; }
-        if (!e.compare_begin()) return fail(GZB_ERR_CUDA);
-        // the iteration's file: coded on the device (second stream, concurrently with the Compare)
-        // with the histograms the walk maintains; only its size is needed unless it becomes the best
-        // (processor.cc:897-915, MaybeOutput 151-160)
-        const double tw = now_ms();
-        DeviceJpeg dj;
-        if (!device_code_candidate(e.ctx, width, height, e.nb, e.quant, false, dc_hist, ac_hist, &dj, e.yuv420)) return fail(GZB_ERR_CUDA);
-        ++e.code_gen;
-        e.st.num_jpeg_writes++;
-        e.st.device_write_ms += now_ms() - tw;
-        if (!e.compare_end()) return fail(GZB_ERR_CUDA);
-        const size_t jpg_size = dj.size();
-        e.log("Iter %2d: %s(%d) %s Coeffs[%d/%zd] Blocks[%zd/%d/%d] ValThres[%.4f] Out[%7zd] EstErr[%.2f%%]",
-              e.st.num_iterations, e.frame_type(), comp_mask, direction > 0 ? "up" : "down", changed_coeffs, order_size,
-              changed_blocks, blocks_to_change, num_blocks, val_threshold, jpg_size,
-              100.0 - (100.0 * est_jpg_size) / jpg_size);
-        e.log(" BA[100.00%%] D[%6.4f]", e.distance);
-        const double score = score_jpeg(e.distance, static_cast<int>(jpg_size), e.target);
-        e.log(" Score[%.4f]", score);
-        if (score < e.best_score || e.best_score < 0) {
-          if (!device_fetch_jpeg(e.ctx, dj, &e.best_jpeg)) return fail(GZB_ERR_CUDA);
-          e.best_score = score;
-          e.best_remote = false;
-          e.log(" (*)");
-        }
-        e.log("\n");
-        prev_size = est_jpg_size;
       }
+      e.st.backend_wall_ms += now_ms() - t_be;
     }
-    e.st.backend_wall_ms += now_ms() - t_be;
-  }
   return GZB_OK;
   };
 
