@@ -306,6 +306,12 @@ class ButteraugliComparator:
     def launch_count(self):
         return int(lib().gzb_launch_count(self._ctx))
 
+    def incremental_compare_count(self):
+        L = lib()
+        L.gzb_incremental_compare_count.restype = C.c_ulonglong
+        L.gzb_incremental_compare_count.argtypes = [C.c_void_p]
+        return int(L.gzb_incremental_compare_count(self._ctx))
+
 
 # ---- stage entry points (roles of the reference's cu* free functions) ----------------------
 def OpsinDynamicsImage(planes, device=0):

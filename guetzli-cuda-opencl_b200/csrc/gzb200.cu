@@ -177,7 +177,8 @@ struct BlurPlan {
 // that back-to-back encodes do not pay the driver's map/unmap cost (the reference's cumem_pool
 // plays this role, clguetzli/cumem_pool.cpp:28-112).
 // ---------------------------------------------------------------------------------------------
-struct Slab { void* base = nullptr; size_t cap = 0; void* pinned = nullptr; };
+struct Slab { void* base = nullptr; size_t cap = 0; void* pinned = nullptr; void* pinned2 = nullptr; size_t pinned2_cap = 0; };
+static void slab_free(Slab& s) { cudaFree(s.base); cudaFreeHost(s.pinned); if (s.pinned2) cudaFreeHost(s.pinned2); s = Slab(); }
 static std::mutex g_slab_mu;
 static std::vector<Slab> g_slab_cache[64];
 
@@ -193,7 +194,7 @@ static Slab slab_acquire(int device, size_t bytes) {
       v.erase(v.begin() + best);
       return s;
     }
-    for (Slab& s : v) { cudaFree(s.base); cudaFreeHost(s.pinned); }  // wrong sizes: drop them
+    for (Slab& s : v) slab_free(s);  // wrong sizes: drop them
     v.clear();
   }
   Slab s;
@@ -206,7 +207,7 @@ static void slab_release(int device, Slab s) {
   if (!s.base) return;
   std::lock_guard<std::mutex> lock(g_slab_mu);
   std::vector<Slab>& v = g_slab_cache[device & 63];
-  if (v.size() >= 4) { cudaFree(s.base); cudaFreeHost(s.pinned); return; }
+  if (v.size() >= 4) { slab_free(s); return; }
   v.push_back(s);
 }
 
@@ -306,7 +307,23 @@ struct gzb_ctx {
   size_t lf_stride = 0;
 
   BlurPlan p_ops, p_ed[3], p_lf, p_mk[3], p_mkb2, p_dm;
+
+  // ---- incremental Compare (see DirtyMask in gzb_kernels.cuh) ----
+  uint8_t* d_dirty = nullptr;        // [DS_COUNT][mtw * mth] per-stage dirty tiles
+  uint8_t* h_dirty = nullptr;        // pinned staging of the same
+  int mtw = 0, mth = 0;
+  bool dirty_is_all = false;         // d_dirty currently holds all ones
+  unsigned int* d_ctamax = nullptr;  // per-CTA maxima of k_diffmap_final (persist between Compares)
+  int n_ctamax = 0;
+  float* d_lft = nullptr;            // EdgeDetectorLowFreq term, res map x3 floats
+  bool inter_valid = false;          // the buffers of the last Compare describe the candidate before `changed`
+  bool changed_overflow = false;     // too many changes since the last Compare to track
+  std::vector<int4> changed;         // pixel rectangles (x0, y0, x1, y1) whose samples changed since the last Compare
+  unsigned long long incremental_compares = 0;
 };
+
+enum DirtyStage { DS_OPS = 0, DS_MHIC, DS_EB, DS_EDM, DS_BDM, DS_LFH, DS_LFV, DS_LOW, DS_MKH0, DS_MKV0, DS_MKH1, DS_MKV1,
+                  DS_MKH2, DS_MKV2, DS_COMB, DS_DMH, DS_DMV, DS_FIN, DS_COUNT };
 
 static thread_local std::string g_create_err;
 
@@ -324,6 +341,14 @@ namespace {
   } while (0)
 #define KLAUNCH(c, kclass, ...) KLAUNCH_S(c, (c)->stream, kclass, __VA_ARGS__)
 
+inline DirtyMask dmask(const gzb_ctx* c, int stage) {
+  DirtyMask d;
+  d.m = c->d_dirty ? c->d_dirty + static_cast<size_t>(stage) * c->mtw * c->mth : nullptr;
+  d.tw = c->mtw; d.th = c->mth;
+  return d;
+}
+const DirtyMask kAllDirty = {nullptr, 0, 0};
+
 void prof_resolve(gzb_ctx* c) {
   for (auto& p : c->prof.pend) {
     float ms = 0.f;
@@ -338,7 +363,8 @@ template <typename T>
 void dmalloc(T** p, size_t n) { CK(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T))); }
 
 void run_blur(gzb_ctx* c, const BlurPlan& pl, const float* in, size_t in_stride, int planes,
-              float* out, size_t out_stride, int out_pitch, cudaStream_t st = nullptr, float* tmp = nullptr) {
+              float* out, size_t out_stride, int out_pitch, cudaStream_t st = nullptr, float* tmp = nullptr,
+              DirtyMask mh = kAllDirty, DirtyMask mv = kAllDirty) {
   const BlurGeom& g = pl.g;
   c->packed_valid = false;
   if (g.nx <= 0 || g.ny <= 0) return;
@@ -347,10 +373,10 @@ void run_blur(gzb_ctx* c, const BlurPlan& pl, const float* in, size_t in_stride,
   dim3 blk(32, 8);
   dim3 gh((g.nx + g.oxn - 1) / g.oxn, (g.in_h + kBhRows - 1) / kBhRows, planes);
   const size_t tstride = pl.tmp_floats();
-  if (g.ups == 1) KLAUNCH_S(c, st, KC_BLUR_H, k_blur_h<1><<<gh, blk, 0, st>>>(in, in_stride, g, pl.d_sx, tmp, tstride));
-  else KLAUNCH_S(c, st, KC_BLUR_H, k_blur_h<3><<<gh, blk, 0, st>>>(in, in_stride, g, pl.d_sx, tmp, tstride));
+  if (g.ups == 1) KLAUNCH_S(c, st, KC_BLUR_H, k_blur_h<1><<<gh, blk, 0, st>>>(in, in_stride, g, pl.d_sx, tmp, tstride, mh));
+  else KLAUNCH_S(c, st, KC_BLUR_H, k_blur_h<3><<<gh, blk, 0, st>>>(in, in_stride, g, pl.d_sx, tmp, tstride, mh));
   dim3 gv((g.nx + 31) / 32, (g.ny + g.oyn - 1) / g.oyn, planes);
-  KLAUNCH_S(c, st, KC_BLUR_V, k_blur_v<<<gv, blk, 0, st>>>(tmp, tstride, g, pl.d_sy, out, out_stride, out_pitch));
+  KLAUNCH_S(c, st, KC_BLUR_V, k_blur_v<<<gv, blk, 0, st>>>(tmp, tstride, g, pl.d_sy, out, out_stride, out_pitch, mv));
 }
 
 // Block geometry of component k's coefficient array in the context's current sampling mode.
@@ -391,10 +417,10 @@ void render_candidate(gzb_ctx* c, int op) {
     KLAUNCH(c, KC_IDCT, k_coeffs_to_rgb8<kCoeffScale><<<grid, 256, 0, c->stream>>>(c->d_orig, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us));
 }
 
-void opsin_from_u8(gzb_ctx* c, const uint8_t* planes, float* xyb) {
+void opsin_from_u8(gzb_ctx* c, const uint8_t* planes, float* xyb, bool masked = false) {
   dim3 blk(32, 8), grd((c->W + 31) / 32, (c->H + 31) / 32);
   KLAUNCH(c, KC_OPSIN, k_opsin_dynamics<<<grd, blk, 0, c->stream>>>(planes, static_cast<size_t>(c->P) * c->HP, c->W, c->H, c->P,
-                                               c->p_ops.d_sx, c->p_ops.d_sy, xyb, c->ps));
+                                               c->p_ops.d_sx, c->p_ops.d_sy, xyb, c->ps, masked ? dmask(c, DS_OPS) : kAllDirty));
 }
 
 MaskSample mask_sample(gzb_ctx* c, bool for_blocks) {
@@ -411,12 +437,16 @@ MaskSample mask_sample(gzb_ctx* c, bool for_blocks) {
 // Mask front + blurs for (a, b) image pair (planes with stride ps); for_blocks selects the
 // channel-2 lattice.
 void run_mask(gzb_ctx* c, const float* a, const float* b, bool for_blocks) {
+  // the block-comparison mask (of the original against itself) is always computed in full
+  const bool masked = !for_blocks;
   dim3 blk(32, 8), grd((c->W + 31) / 32, (c->H + 31) / 32, 3);
-  KLAUNCH(c, KC_MASK_FRONT, k_mask_front<<<grd, blk, 0, c->stream>>>(a, b, c->ps, c->W, c->H, c->P, c->d_bl));
+  KLAUNCH(c, KC_MASK_FRONT, k_mask_front<<<grd, blk, 0, c->stream>>>(a, b, c->ps, c->W, c->H, c->P, c->d_bl,
+                                                                   masked ? dmask(c, DS_EB) : kAllDirty));
   for (int k = 0; k < 3; ++k) {
     const BlurPlan& pl = (k == 2 && for_blocks) ? c->p_mkb2 : c->p_mk[k];
     float* out = (k == 2 && for_blocks) ? c->d_msb2 : c->d_ms[k];
-    run_blur(c, pl, c->d_bl + k * c->ps, 0, 1, out, 0, pl.g.tmp_pitch);
+    run_blur(c, pl, c->d_bl + k * c->ps, 0, 1, out, 0, pl.g.tmp_pitch, nullptr, nullptr,
+             masked ? dmask(c, DS_MKH0 + 2 * k) : kAllDirty, masked ? dmask(c, DS_MKV0 + 2 * k) : kAllDirty);
   }
 }
 
@@ -426,7 +456,7 @@ void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
   dim3 blk(32, 8), gpx((W + 31) / 32, (H + 7) / 8);
   float* m0 = c->d_mh;
   float* m1 = c->d_mh + 3 * c->ps;
-  KLAUNCH(c, KC_MHIC, k_mask_high_intensity_change<<<gpx, blk, 0, c->stream>>>(xyb0, xyb1, c->ps, W, H, P, m0, m1));
+  KLAUNCH(c, KC_MHIC, k_mask_high_intensity_change<<<gpx, blk, 0, c->stream>>>(xyb0, xyb1, c->ps, W, H, P, m0, m1, dmask(c, DS_MHIC)));
   if (c->concurrent) CK(cudaEventRecord(c->ev_fork, c->stream));
   // EdgeDetectorMap: the six small-sigma blurs (3 channels x 2 images) in one fused H+V launch
   {
@@ -439,18 +469,17 @@ void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
     }
     if (fused) {
       dim3 gsb((W + kSbT - 1) / kSbT, (H + kSbT - 1) / kSbT, 6);
-      KLAUNCH(c, KC_BLUR_H, k_blur_small_hv<<<gsb, blk, 0, c->stream>>>(c->d_mh, c->d_bl, c->ps, W, H, P, sb));
+      KLAUNCH(c, KC_BLUR_H, k_blur_small_hv<<<gsb, blk, 0, c->stream>>>(c->d_mh, c->d_bl, c->ps, W, H, P, sb, dmask(c, DS_EB)));
     } else {
-      for (int k = 0; k < 3; ++k)
+      for (int k = 0; k < 3; ++k)   // (never taken with the reference's sigmas; unmasked, so Compares are then always full)
         run_blur(c, c->p_ed[k], c->d_mh + k * c->ps, 3 * c->ps, 2, c->d_bl + k * c->ps, 3 * c->ps, P);
     }
   }
   dim3 gres((c->rxs + 31) / 32, (c->rys + 7) / 8);
-  KLAUNCH(c, KC_EDGE_MAP, k_edge_detector_map<<<gres, blk, 0, c->stream>>>(c->d_bl, c->d_bl + 3 * c->ps, c->ps, W, H, P, c->rxs, c->d_edm));
+  KLAUNCH(c, KC_EDGE_MAP, k_edge_detector_map<<<gres, blk, 0, c->stream>>>(c->d_bl, c->d_bl + 3 * c->ps, c->ps, W, H, P, c->rxs, c->d_edm, dmask(c, DS_EDM)));
   // BlockDiffMap and EdgeDetectorLowFreq do not depend on the EdgeDetectorMap / Mask chain: they run
   // on two side streams (forked after MaskHighIntensityChange, joined before CombineChannels) so
   // that at small image sizes the short kernels of the three branches overlap.
-  const size_t rbytes = static_cast<size_t>(3) * c->rxs * c->rys * sizeof(float);
   const int ncx = (W - 4 + 2) / 3, ncy = (H - 4 + 2) / 3;
   const int cells = ncx * ncy;
   const int ctas = std::min((cells + kBdmWarps - 1) / kBdmWarps, c->sm_count * 16);
@@ -460,25 +489,27 @@ void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
     CK(cudaStreamWaitEvent(sb, c->ev_fork, 0));
     CK(cudaStreamWaitEvent(sl, c->ev_fork, 0));
   }
-  CK(cudaMemsetAsync(c->d_ac, 0, rbytes, sb));
-  KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac));
-  KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_dc<<<(cells + 127) / 128, 128, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc));
+  // (block_diff_ac cells outside the kernel's domain were zeroed once, at context creation)
+  KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac, dmask(c, DS_BDM)));
+  KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_dc<<<(cells + 127) / 128, 128, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, dmask(c, DS_BDM)));
   if (c->concurrent) CK(cudaEventRecord(c->ev_bdm, sb));
   // EdgeDetectorLowFreq (its blur scratch is the first part of d_tmp, the main stream's the rest)
-  run_blur(c, c->p_lf, c->d_mh, c->ps, 6, c->d_lf, c->lf_stride, c->p_lf.g.tmp_pitch, sl, c->d_tmp);
-  if (c->concurrent) CK(cudaStreamWaitEvent(sl, c->ev_bdm, 0));   // adds into block_diff_ac
+  run_blur(c, c->p_lf, c->d_mh, c->ps, 6, c->d_lf, c->lf_stride, c->p_lf.g.tmp_pitch, sl, c->d_tmp, dmask(c, DS_LFH), dmask(c, DS_LFV));
+  if (c->concurrent) CK(cudaStreamWaitEvent(sl, c->ev_bdm, 0));   // joins the BlockDiffMap branch
   KLAUNCH_S(c, sl, KC_LOWFREQ, k_edge_lowfreq<<<gres, blk, 0, sl>>>(c->d_lf, c->d_lf + 3 * c->lf_stride, c->lf_stride, c->p_lf.g.tmp_pitch,
-                                             c->p_lf.g.sx, W, H, c->rxs, c->d_ac));
+                                             c->p_lf.g.sx, W, H, c->rxs, c->d_lft, dmask(c, DS_LOW)));
   if (c->concurrent) CK(cudaEventRecord(c->ev_lf, sl));
   // Mask + combine
   run_mask(c, m0, m1, false);
   if (c->concurrent) CK(cudaStreamWaitEvent(c->stream, c->ev_lf, 0));   // ev_lf follows ev_bdm
-  KLAUNCH(c, KC_COMBINE, k_combine<<<gres, blk, 0, c->stream>>>(mask_sample(c, false), c->d_dc, c->d_ac, c->d_edm, W, H, c->rxs, c->rys, c->sqp, c->d_sq));
+  KLAUNCH(c, KC_COMBINE, k_combine<<<gres, blk, 0, c->stream>>>(mask_sample(c, false), c->d_dc, c->d_ac, c->d_lft, c->d_edm, W, H, c->rxs, c->rys, c->sqp, c->d_sq,
+                                                               dmask(c, DS_COMB)));
   // CalculateDiffmap
-  run_blur(c, c->p_dm, c->d_sq, 0, 1, c->d_dsmall, 0, c->p_dm.g.tmp_pitch);
+  run_blur(c, c->p_dm, c->d_sq, 0, 1, c->d_dsmall, 0, c->p_dm.g.tmp_pitch, nullptr, nullptr, dmask(c, DS_DMH), dmask(c, DS_DMV));
   CK(cudaMemsetAsync(c->d_scalars, 0, sizeof(unsigned int), c->stream));
   KLAUNCH(c, KC_DIFFMAP_FINAL, k_diffmap_final<<<gpx, blk, 0, c->stream>>>(c->d_sq, c->sqp, c->d_dsmall, c->p_dm.g.tmp_pitch, c->p_dm.g.sx, W, H, P,
-                                             c->d_diffmap, c->d_scalars));
+                                             c->d_diffmap, c->d_ctamax, dmask(c, DS_FIN)));
+  KLAUNCH(c, KC_DIFFMAP_FINAL, k_max_u32<<<std::min(64, (c->n_ctamax + 255) / 256), 256, 0, c->stream>>>(c->d_ctamax, c->n_ctamax, c->d_scalars));
 }
 
 void free_ctx(gzb_ctx* c) {
@@ -565,7 +596,11 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     for (int k = 0; k < 3; ++k) need(c, &c->d_ms[k], c->p_mk[k].out_floats());
     need(c, &c->d_msb2, c->p_mkb2.out_floats());
     const size_t rn = static_cast<size_t>(c->rxs) * c->rys;
-    need(c, &c->d_edm, 3 * rn); need(c, &c->d_dc, 3 * rn); need(c, &c->d_ac, 3 * rn);
+    need(c, &c->d_edm, 3 * rn); need(c, &c->d_dc, 3 * rn); need(c, &c->d_ac, 3 * rn); need(c, &c->d_lft, 3 * rn);
+    c->mtw = (W + 31) / 32; c->mth = (H + 31) / 32;
+    need(c, &c->d_dirty, static_cast<size_t>(DS_COUNT) * c->mtw * c->mth);
+    c->n_ctamax = ((W + 31) / 32) * ((H + 7) / 8);
+    need(c, &c->d_ctamax, c->n_ctamax);
     need(c, &c->d_sq, static_cast<size_t>(c->sqp) * c->rys);
     need(c, &c->d_dsmall, c->p_dm.out_floats());
     need(c, &c->d_diffmap, c->ps);
@@ -589,6 +624,12 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     CK(cudaMemsetAsync(c->d_rgb1, 0, 3 * us, c->stream));
     CK(cudaMemsetAsync(c->d_edm, 0, 3 * rn * sizeof(float), c->stream));
     CK(cudaMemsetAsync(c->d_dc, 0, 3 * rn * sizeof(float), c->stream));
+    CK(cudaMemsetAsync(c->d_ac, 0, 3 * rn * sizeof(float), c->stream));
+    CK(cudaMemsetAsync(c->d_lft, 0, 3 * rn * sizeof(float), c->stream));
+    CK(cudaMemsetAsync(c->d_ctamax, 0, c->n_ctamax * sizeof(unsigned int), c->stream));
+    CK(cudaMemsetAsync(c->d_dirty, 1, static_cast<size_t>(DS_COUNT) * c->mtw * c->mth, c->stream));
+    c->dirty_is_all = true;
+
     // the blur scratch must hold the widest H-pass output of any plan
     const BlurPlan* all[] = {&c->p_ed[0], &c->p_ed[1], &c->p_ed[2], &c->p_lf, &c->p_mk[0], &c->p_mk[1],
                              &c->p_mk[2], &c->p_mkb2, &c->p_dm};
@@ -619,6 +660,112 @@ void upload_original(gzb_ctx* c, const uint8_t* rgb) {
   opsin_from_u8(c, c->d_rgb0, c->d_xyb0);
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaGetLastError());
+}
+
+// ---- incremental Compare: per-stage dirty-tile masks from the changed pixel rectangles --------------
+// A mask marks the 32x32-pixel tiles in which an output of the stage may change. Radii follow the
+// supports of the stages (butteraugli.cc): opsin blur 2, MaskHighIntensityChange 1, EdgeDetectorMap
+// blurs <= 3 and its +-3 differences on the (clamped) 8x8 block of a res cell, the 8x8 windows of
+// BlockDiffMap, the sigma-14 lattice (radius 31, step 4) and the +8 / -6 offsets of EdgeDetectorLowFreq,
+// the mask front (-2 .. +5) and its three blurs, CombineChannels' sample at (+3, +3), the diffmap blur
+// (radius 19 on the 3x-replicated res map, step 2) and the (x - 2) / 3 indexing of the final map. All are
+// rounded up generously; a superfluous dirty tile only costs time.
+// Buffers that do NOT survive a Compare (the H-pass scratch of every blur; planes 0..2 of d_bl, which
+// hold the EdgeDetectorMap blurs and then the mask front) are refreshed over the whole footprint of their
+// dirty consumers: those masks are dilations of the consumers' tile sets.
+struct MaskBuilder {
+  int tw, th, W, H;
+  uint8_t* base;
+  uint8_t* m(int stage) const { return base + static_cast<size_t>(stage) * tw * th; }
+  void mark(int stage, int x0, int y0, int x1, int y1) const {
+    if (x1 < 0 || y1 < 0 || x0 >= W || y0 >= H) return;
+    const int tx0 = std::max(x0, 0) >> 5, ty0 = std::max(y0, 0) >> 5;
+    const int tx1 = std::min(x1, W - 1) >> 5, ty1 = std::min(y1, H - 1) >> 5;
+    uint8_t* p = m(stage);
+    for (int ty = ty0; ty <= ty1; ++ty) memset(p + ty * tw + tx0, 1, tx1 - tx0 + 1);
+  }
+  // dst |= tiles within (fx, fy) pixels of a dirty tile of src
+  void dilate(int src, int dst, int fx, int fy) const {
+    const uint8_t* sp = m(src);
+    for (int ty = 0; ty < th; ++ty)
+      for (int tx = 0; tx < tw; ++tx)
+        if (sp[ty * tw + tx]) mark(dst, 32 * tx - fx, 32 * ty - fy, 32 * tx + 31 + fx, 32 * ty + 31 + fy);
+  }
+  size_t count(int stage) const {
+    size_t n = 0;
+    const uint8_t* p = m(stage);
+    for (int i = 0; i < tw * th; ++i) n += p[i];
+    return n;
+  }
+};
+
+// Fills h_dirty for the rectangles in c->changed; returns the fraction of tiles the last stage touches.
+double build_dirty_masks(gzb_ctx* c) {
+  MaskBuilder b{c->mtw, c->mth, c->W, c->H, c->h_dirty};
+  memset(c->h_dirty, 0, static_cast<size_t>(DS_COUNT) * c->mtw * c->mth);
+  const int r_lf = c->p_lf.g.r, s_lf = c->p_lf.g.sx, r_dm = c->p_dm.g.r, s_dm = c->p_dm.g.sx;
+  for (const int4& q : c->changed) {
+    auto grow = [&](int stage, int r) { b.mark(stage, q.x - r, q.y - r, q.z + r, q.w + r); };
+    grow(DS_OPS, 2);
+    grow(DS_MHIC, 3);
+    grow(DS_EDM, 20);
+    grow(DS_BDM, 20);
+    grow(DS_EB, 9);
+    grow(DS_LFV, 3 + r_lf + s_lf + 1);
+    for (int k = 0; k < 3; ++k) grow(DS_MKV0 + 2 * k, 9 + c->p_mk[k].g.r + c->p_mk[k].g.sx);
+  }
+  b.dilate(DS_EDM, DS_EB, 11, 11);
+  b.dilate(DS_LFV, DS_LFH, 0, r_lf);
+  b.dilate(DS_LFV, DS_LOW, 16, 16);
+  for (int k = 0; k < 3; ++k) b.dilate(DS_MKV0 + 2 * k, DS_MKH0 + 2 * k, 0, c->p_mk[k].g.r);
+  b.dilate(DS_EDM, DS_COMB, 0, 0);
+  b.dilate(DS_BDM, DS_COMB, 0, 0);
+  b.dilate(DS_LOW, DS_COMB, 8, 1);
+  for (int k = 0; k < 3; ++k) b.dilate(DS_MKV0 + 2 * k, DS_COMB, c->p_mk[k].g.sx + 4, c->p_mk[k].g.sx + 4);
+  b.dilate(DS_COMB, DS_DMV, 3 + r_dm + s_dm + 4, 3 + r_dm + s_dm + 4);
+  b.dilate(DS_DMV, DS_DMH, 0, r_dm + 2);
+  b.dilate(DS_DMV, DS_FIN, 4 + s_dm, 4 + s_dm);
+  b.dilate(DS_COMB, DS_FIN, 6, 6);
+  return static_cast<double>(b.count(DS_FIN)) / (static_cast<double>(c->mtw) * c->mth);
+}
+
+// Everything a full-image operation on the candidate (or anything that overwrites buffers a Compare
+// leaves behind) must do: the next Compare recomputes every tile.
+void invalidate_compare_state(gzb_ctx* c) {
+  c->inter_valid = false;
+  c->changed.clear();
+  c->changed_overflow = false;
+}
+
+// Chooses between a full and an incremental Compare and makes d_dirty say so (on the main stream).
+void prepare_dirty_masks(gzb_ctx* c) {
+  static const bool disabled = getenv("GZB_NO_INCREMENTAL") != nullptr;
+  const size_t total = static_cast<size_t>(DS_COUNT) * c->mtw * c->mth;
+  bool fused = true;   // the unfused EdgeDetectorMap blur fallback of run_diffmap is not masked
+  for (int k = 0; k < 3; ++k) {
+    const BlurGeom& g = c->p_ed[k].g;
+    fused = fused && g.r <= kSbR && g.sx == 1 && g.sy == 1 && g.x0 == 0 && g.y0 == 0 && g.ups == 1;
+  }
+  bool incremental = !disabled && fused && c->inter_valid && !c->changed_overflow && !c->changed.empty();
+  if (incremental) {
+    if (c->slab.pinned2_cap < total) {
+      if (c->slab.pinned2) cudaFreeHost(c->slab.pinned2);
+      c->slab.pinned2 = nullptr;
+      c->slab.pinned2_cap = 0;
+      CK(cudaMallocHost(&c->slab.pinned2, total));
+      c->slab.pinned2_cap = total;
+    }
+    c->h_dirty = static_cast<uint8_t*>(c->slab.pinned2);
+    incremental = build_dirty_masks(c) < 0.6;
+  }
+  if (incremental) {
+    CK(cudaMemcpyAsync(c->d_dirty, c->h_dirty, total, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += total;
+    c->dirty_is_all = false;
+    ++c->incremental_compares;
+  } else if (!c->dirty_is_all) {
+    CK(cudaMemsetAsync(c->d_dirty, 1, total, c->stream));
+    c->dirty_is_all = true;
+  }
 }
 
 int fail(gzb_ctx* c, int code, const std::string& msg) {
@@ -691,6 +838,7 @@ int gzb_set_jpeg_coeffs(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const 
   const int16_t* src[3] = {c0, c1, c2};
   c->mode420 = false;   // the input of the RGB front end is 4:4:4
   c->have_coeffs = false;
+  invalidate_compare_state(c);
   const size_t nb2 = static_cast<size_t>(c->nblocks) * 64 * 2;
   for (int k = 0; k < 3; ++k) { CK(cudaMemcpyAsync(c->d_orig + k * cs, src[k], nb2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += nb2; }
   sync_check(c);
@@ -703,6 +851,7 @@ int gzb_copy_from_jpeg(gzb_ctx* c, const int* quant192) {
   GZB_TRY(c)
   if (!c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_copy_from_jpeg: gzb_set_jpeg_coeffs not called");
   CK(cudaMemcpyAsync(c->d_q, quant192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (192 * sizeof(int));
+  invalidate_compare_state(c);
   render_candidate(c, kCoeffScale);
   sync_check(c);
   c->have_coeffs = true;
@@ -714,6 +863,7 @@ int gzb_apply_global_quantization(gzb_ctx* c, const int* q192) {
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_apply_global_quantization: no candidate coefficients");
   for (int i = 0; i < 192; ++i) if (q192[i] <= 0) return fail(c, GZB_ERR_BAD_ARG, "quantiser must be positive");
   CK(cudaMemcpyAsync(c->d_q, q192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (192 * sizeof(int));
+  invalidate_compare_state(c);
   render_candidate(c, kCoeffQuantize);
   sync_check(c);
   GZB_END(c)
@@ -727,6 +877,7 @@ int gzb_set_coeffs(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const int16
     const size_t n2 = comp_blocks(c, k) * 64 * 2;
     CK(cudaMemcpyAsync(c->d_coef + k * cs, src[k], n2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += n2;
   }
+  invalidate_compare_state(c);
   render_candidate(c, kCoeffKeep);
   sync_check(c);
   c->have_coeffs = true;
@@ -757,6 +908,25 @@ int gzb_update_coeffs(gzb_ctx* c, const int32_t* block_ix, const uint8_t* idx, c
     const int lim[3] = {static_cast<int>(comp_blocks(c, 0)), static_cast<int>(comp_blocks(c, 1)), static_cast<int>(comp_blocks(c, 2))};
     for (size_t i = 0; i < n; ++i)
       if (idx[i] >= 192 || block_ix[i] < 0 || block_ix[i] >= lim[idx[i] >> 6]) return fail(c, GZB_ERR_BAD_ARG, "gzb_update_coeffs: index out of range");
+  }
+  if (c->inter_valid && !c->changed_overflow) {
+    // pixel rectangles whose samples change: an 8x8 block, or the 16x16 area (+1: fancy upsampling) of a
+    // sub-sampled chroma block. Large batches are not tracked -- the next Compare is then a full one.
+    if (n + c->changed.size() > 256) {
+      c->changed_overflow = true;
+      c->changed.clear();
+    } else {
+      for (size_t i = 0; i < n; ++i) {
+        const int comp = idx[i] >> 6, bwc = comp_bw(c, comp);
+        const int bx = block_ix[i] % bwc, by = block_ix[i] / bwc;
+        int4 q;
+        if (c->mode420 && comp > 0) q = make_int4(16 * bx - 1, 16 * by - 1, 16 * bx + 16, 16 * by + 16);
+        else q = make_int4(8 * bx, 8 * by, 8 * bx + 7, 8 * by + 7);
+        bool dup = false;
+        for (const int4& o : c->changed) dup = dup || (o.x == q.x && o.y == q.y && o.z == q.z && o.w == q.w);
+        if (!dup) c->changed.push_back(q);
+      }
+    }
   }
   if (n > 0) {
     // staging: the blur scratch (6 planes, >= 24 bytes per pixel) holds 8 bytes per record for up to
@@ -796,6 +966,7 @@ int gzb_update_coeffs(gzb_ctx* c, const int32_t* block_ix, const uint8_t* idx, c
 int gzb_clear_distmap(gzb_ctx* c) {
   GZB_TRY(c)
   CK(cudaMemsetAsync(c->d_diffmap, 0, c->ps * sizeof(float), c->stream));
+  invalidate_compare_state(c);
   c->have_distmap = true;
   GZB_END(c)
 }
@@ -822,11 +993,13 @@ int gzb_compare_begin(gzb_ctx* c) {
   GZB_TRY(c)
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compare: no candidate coefficients");
   CK(cudaEventRecord(c->ev0, c->stream));
+  // Full or incremental: the per-stage dirty masks decide which tiles the kernels below recompute.
+  prepare_dirty_masks(c);
   // Every Compare of a context runs the same ~25 launches on the same buffers (three streams, fork
   // and join): captured once into a CUDA graph and replayed, which removes the per-launch gaps that
   // dominate at small image sizes. Per-kernel profiling needs the individual launches.
   if (c->prof.on || c->graph_failed) {
-    opsin_from_u8(c, c->d_rgb1, c->d_xyb1);
+    opsin_from_u8(c, c->d_rgb1, c->d_xyb1, true);
     run_diffmap(c, c->d_xyb0, c->d_xyb1);
   } else {
     if (!c->cmp_graph_exec) {
@@ -836,7 +1009,7 @@ int gzb_compare_begin(gzb_ctx* c) {
       cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed);
       if (e == cudaSuccess) {
         try {
-          opsin_from_u8(c, c->d_rgb1, c->d_xyb1);
+          opsin_from_u8(c, c->d_rgb1, c->d_xyb1, true);
           run_diffmap(c, c->d_xyb0, c->d_xyb1);
         } catch (const std::string&) { e = cudaErrorUnknown; }
         const cudaError_t e2 = cudaStreamEndCapture(c->stream, &graph);
@@ -858,10 +1031,14 @@ int gzb_compare_begin(gzb_ctx* c) {
       CK(cudaGraphLaunch(c->cmp_graph_exec, c->stream));
       c->launches += c->cmp_graph_launches;
     } else {
-      opsin_from_u8(c, c->d_rgb1, c->d_xyb1);
+      opsin_from_u8(c, c->d_rgb1, c->d_xyb1, true);
       run_diffmap(c, c->d_xyb0, c->d_xyb1);
     }
   }
+  // from here on the context's buffers describe this candidate
+  c->inter_valid = true;
+  c->changed.clear();
+  c->changed_overflow = false;
   CK(cudaEventRecord(c->ev1, c->stream));
   CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(unsigned int));
   c->compare_pending = true;
@@ -921,6 +1098,7 @@ int gzb_image_size(const gzb_ctx* c, int* width, int* height) {
 int gzb_start_block_comparisons(gzb_ctx* c) {
   GZB_TRY(c)
   CK(cudaEventRecord(c->ev0, c->stream));
+  invalidate_compare_state(c);   // the mask of the original overwrites the mask buffers of the last Compare
   run_mask(c, c->d_xyb0, c->d_xyb0, true);
   KLAUNCH(c, KC_BLOCK_MASK, k_block_mask_scale<<<(c->nblocks + 255) / 256, 256, 0, c->stream>>>(mask_sample(c, true), c->bw, c->bh, c->d_mask_scale));
   CK(cudaEventRecord(c->ev1, c->stream));
@@ -1048,14 +1226,14 @@ int gzb_set_sampling(gzb_ctx* c, int chroma_factor) {
   if (!c) return GZB_ERR_BAD_ARG;
   if (chroma_factor != 1 && chroma_factor != 2) return fail(c, GZB_ERR_BAD_ARG, "gzb_set_sampling: factor must be 1 or 2");
   const bool m = chroma_factor == 2;
-  if (m != c->mode420) { c->mode420 = m; c->have_coeffs = false; c->have_orig_coeffs = false; c->packed_valid = false; }
+  if (m != c->mode420) { c->mode420 = m; c->have_coeffs = false; c->have_orig_coeffs = false; c->packed_valid = false; invalidate_compare_state(c); }
   return GZB_OK;
 }
 
 int gzb_set_jpeg_coeffs_420(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const int16_t* c2) {
   GZB_TRY(c)
   if (!c0 || !c1 || !c2) return fail(c, GZB_ERR_BAD_ARG, "gzb_set_jpeg_coeffs_420: null argument");
-  if (!c->mode420) { c->mode420 = true; c->have_coeffs = false; }
+  if (!c->mode420) { c->mode420 = true; c->have_coeffs = false; invalidate_compare_state(c); }
   const int16_t* src[3] = {c0, c1, c2};
   for (int k = 0; k < 3; ++k) {
     const size_t n2 = comp_blocks(c, k) * 64 * 2;
@@ -1350,7 +1528,7 @@ int gzb_downsample_420(gzb_ctx* c) {
   sync_check(c);
   c->mode420 = true;
   c->have_coeffs = false;
-  if (c->cmp_graph_exec) { /* the Compare graph reads d_rgb1 only: still valid */ }
+  invalidate_compare_state(c);   // the scratch planes used above are the Compare's
   GZB_END(c)
 }
 
@@ -1402,6 +1580,12 @@ int gzb_debug_fetch(gzb_ctx* c, const char* name, float* out, size_t cap, size_t
   } else if (flat) {
     if (n_out) *n_out = flat_n;
     if (cap >= flat_n) CK(cudaMemcpyAsync(out, flat, flat_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (flat_n * sizeof(float));
+    if (cap >= flat_n && s == "block_ac") {   // the reference's block_diff_ac includes the EdgeDetectorLowFreq term
+      std::vector<float> lft(flat_n);
+      CK(cudaMemcpyAsync(lft.data(), c->d_lft, flat_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (flat_n * sizeof(float));
+      CK(cudaStreamSynchronize(c->stream));
+      for (size_t i = 0; i < flat_n; ++i) out[i] = out[i] + lft[i];
+    }
   } else {  // combined_sqrt: res map with pitch
     if (n_out) *n_out = rn;
     if (cap >= rn)
@@ -1438,6 +1622,7 @@ int gzb_get_transfer_bytes(const gzb_ctx* c, unsigned long long* h2d, unsigned l
 }
 float gzb_last_device_ms(const gzb_ctx* c) { return c ? c->last_ms : 0.f; }
 unsigned long long gzb_launch_count(const gzb_ctx* c) { return c ? c->launches : 0; }
+unsigned long long gzb_incremental_compare_count(const gzb_ctx* c) { return c ? c->incremental_compares : 0; }
 
 // ---- stage entry points ----------------------------------------------------------------------
 int gzb_blur(int device, float* plane, size_t xsize, size_t ysize, double sigma, double border_ratio) {
@@ -1462,9 +1647,9 @@ int gzb_blur(int device, float* plane, size_t xsize, size_t ysize, double sigma,
     CK(cudaMemcpy2D(d_in, P * sizeof(float), plane, W * sizeof(float), W * sizeof(float), H, cudaMemcpyHostToDevice));
     dim3 blk(32, 8);
     dim3 gh((pl.g.nx + pl.g.oxn - 1) / pl.g.oxn, (H + kBhRows - 1) / kBhRows, 1);
-    k_blur_h<1><<<gh, blk>>>(d_in, 0, pl.g, pl.d_sx, d_tmp, 0);
+    k_blur_h<1><<<gh, blk>>>(d_in, 0, pl.g, pl.d_sx, d_tmp, 0, kAllDirty);
     dim3 gv((pl.g.nx + 31) / 32, (pl.g.ny + pl.g.oyn - 1) / pl.g.oyn, 1);
-    k_blur_v<<<gv, blk>>>(d_tmp, 0, pl.g, pl.d_sy, d_out, 0, pl.g.tmp_pitch);
+    k_blur_v<<<gv, blk>>>(d_tmp, 0, pl.g, pl.d_sy, d_out, 0, pl.g.tmp_pitch, kAllDirty);
     CK(cudaDeviceSynchronize());
     CK(cudaGetLastError());
     std::vector<float> small(pl.out_floats());

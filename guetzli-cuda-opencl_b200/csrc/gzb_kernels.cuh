@@ -19,6 +19,29 @@ __constant__ float c_taps[12][kMaxTaps];  // one row per blur kernel (see BlurKi
 __host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // ---------------------------------------------------------------------------------------------
+// Incremental Compare: between two Compares of the back end only a few blocks change, and every
+// stage has bounded support, so each stage owns a byte mask over 32x32-pixel tiles of the image
+// ("an output anchored in this tile may change") and skips clean outputs; their values are still in
+// the context's buffers from the previous Compare. m == nullptr: everything is dirty.
+// ---------------------------------------------------------------------------------------------
+struct DirtyMask { const uint8_t* m; int tw, th; };
+__device__ __forceinline__ bool dirty_at(const DirtyMask& d, int x, int y) {
+  if (!d.m) return true;
+  const int tx = min(max(x, 0) >> 5, d.tw - 1), ty = min(max(y, 0) >> 5, d.th - 1);
+  return d.m[ty * d.tw + tx] != 0;
+}
+// any tile intersecting the pixel rectangle [x0, x1] x [y0, y1] dirty? (uniform per CTA when the arguments are)
+__device__ __forceinline__ bool dirty_any(const DirtyMask& d, int x0, int y0, int x1, int y1) {
+  if (!d.m) return true;
+  const int tx0 = min(max(x0, 0) >> 5, d.tw - 1), ty0 = min(max(y0, 0) >> 5, d.th - 1);
+  const int tx1 = min(max(x1, 0) >> 5, d.tw - 1), ty1 = min(max(y1, 0) >> 5, d.th - 1);
+  for (int ty = ty0; ty <= ty1; ++ty)
+    for (int tx = tx0; tx <= tx1; ++tx)
+      if (d.m[ty * d.tw + tx]) return true;
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K0: interleaved sRGB8 -> planar u8 with pitch (upload helper)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_deinterleave_rgb(const uint8_t* __restrict__ rgb, int W, int H, int P,
@@ -132,12 +155,13 @@ constexpr int kOpsTile = 32;
 __global__ void __launch_bounds__(256)
 k_opsin_dynamics(const uint8_t* __restrict__ planes, size_t plane_stride, int W, int H, int P,
                  const double* __restrict__ scale_x, const double* __restrict__ scale_y,
-                 float* __restrict__ xyb, size_t xyb_stride) {
+                 float* __restrict__ xyb, size_t xyb_stride, DirtyMask dm) {
   __shared__ float s_lin[3][kOpsTile + 4][kOpsTile + 4 + 1];
   __shared__ float s_h[3][kOpsTile + 4][kOpsTile + 1];
   __shared__ float s_lut[256];
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int x0 = blockIdx.x * kOpsTile, y0 = blockIdx.y * kOpsTile;
+  if (!dirty_at(dm, x0, y0)) return;   // the CTA's tile is the mask's tile
   s_lut[tid] = g_tab.srgb_lin[tid];
   __syncthreads();
   for (int i = tid; i < 3 * 36 * 36; i += 256) {
@@ -269,10 +293,11 @@ k_opsin_dynamics_f32(const float* __restrict__ lin, size_t lin_stride, int W, in
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_mask_high_intensity_change(const float* __restrict__ a, const float* __restrict__ b, size_t stride,
-                             int W, int H, int P, float* __restrict__ oa, float* __restrict__ ob) {
+                             int W, int H, int P, float* __restrict__ oa, float* __restrict__ ob, DirtyMask dm) {
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = blockIdx.y * 8 + threadIdx.y;
   if (x >= W || y >= H) return;
+  if (!dirty_at(dm, x, y)) return;
   const size_t ix = static_cast<size_t>(y) * P + x;
   const float c0[3] = {a[ix], a[stride + ix], a[2 * stride + ix]};
   const float c1[3] = {b[ix], b[stride + ix], b[2 * stride + ix]};
@@ -316,12 +341,14 @@ constexpr int kBhOx = 32, kBhRows = 16, kBhMaxSpan = kBhOx * 4 + 2 * 32;  // 192
 template <int UPS>
 __global__ void __launch_bounds__(256)
 k_blur_h(const float* __restrict__ in, size_t in_stride, BlurGeom g,
-         const double* __restrict__ scale_x, float* __restrict__ tmp, size_t tmp_stride) {
+         const double* __restrict__ scale_x, float* __restrict__ tmp, size_t tmp_stride, DirtyMask dm) {
   __shared__ float s[kBhRows][kBhMaxSpan + 1];
   in += blockIdx.z * in_stride;
   tmp += blockIdx.z * tmp_stride;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int ox0 = blockIdx.x * g.oxn, yb = blockIdx.y * kBhRows;
+  // outputs are anchored at pixel (x0 + ox * sx, row)
+  if (!dirty_any(dm, g.x0 + ox0 * g.sx, yb, g.x0 + (ox0 + g.oxn - 1) * g.sx, yb + kBhRows - 1)) return;
   const int xs = g.x0 + ox0 * g.sx - g.r;  // first input column of the tile
   const int span = (g.oxn - 1) * g.sx + 2 * g.r + 1;
   for (int i = tid; i < kBhRows * span; i += 256) {
@@ -343,6 +370,7 @@ k_blur_h(const float* __restrict__ in, size_t in_stride, BlurGeom g,
   for (int rr = 0; rr < kBhRows; rr += 8) {
     const int ly = threadIdx.y + rr, gy = yb + ly;
     if (gy >= g.in_h) break;
+    if (!dirty_at(dm, g.x0 + ox * g.sx, gy)) continue;
     const float* p = &s[ly][threadIdx.x * g.sx];
     double acc = 0.0;
     for (int k = 0; k < nt; ++k) acc += static_cast<double>(p[k] * taps[k]);
@@ -354,12 +382,14 @@ constexpr int kBvOy = 16, kBvMaxRows = (kBvOy - 1) * 4 + 2 * 32 + 1;  // 125
 __global__ void __launch_bounds__(256)
 k_blur_v(const float* __restrict__ tmp, size_t tmp_stride, BlurGeom g,
          const double* __restrict__ scale_y, float* __restrict__ out, size_t out_stride,
-         int out_pitch) {
+         int out_pitch, DirtyMask dm) {
   __shared__ float s[kBvMaxRows][33];
   tmp += blockIdx.z * tmp_stride;
   out += blockIdx.z * out_stride;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * g.oyn;
+  // outputs are anchored at pixel (x0 + ox * sx, y0 + oy * sy)
+  if (!dirty_any(dm, g.x0 + ox0 * g.sx, g.y0 + oy0 * g.sy, g.x0 + (ox0 + 31) * g.sx, g.y0 + (oy0 + g.oyn - 1) * g.sy)) return;
   const int ys = g.y0 + oy0 * g.sy - g.r;
   const int rows = (g.oyn - 1) * g.sy + 2 * g.r + 1;
   for (int i = tid; i < rows * 32; i += 256) {
@@ -378,6 +408,7 @@ k_blur_v(const float* __restrict__ tmp, size_t tmp_stride, BlurGeom g,
   for (int rr = 0; rr < kBvOy; rr += 8) {
     const int loy = threadIdx.y + rr, oy = oy0 + loy;
     if (oy >= g.ny || loy >= g.oyn) break;
+    if (!dirty_at(dm, g.x0 + ox * g.sx, g.y0 + oy * g.sy)) continue;
     double acc = 0.0;
     const int base = loy * g.sy;
     for (int k = 0; k < nt; ++k) acc += static_cast<double>(s[base + k][threadIdx.x] * taps[k]);
@@ -400,9 +431,10 @@ struct SmallBlur3 {
 constexpr int kSbT = 32, kSbR = 3;
 __global__ void __launch_bounds__(256)
 k_blur_small_hv(const float* __restrict__ in, float* __restrict__ out, size_t plane_stride, int W, int H, int P,
-                SmallBlur3 sb) {
+                SmallBlur3 sb, DirtyMask dm) {
   __shared__ float s_in[kSbT + 2 * kSbR][kSbT + 2 * kSbR + 1];
   __shared__ float s_h[kSbT + 2 * kSbR][kSbT + 1];
+  if (!dirty_at(dm, blockIdx.x * kSbT, blockIdx.y * kSbT)) return;   // the CTA's tile is the mask's tile
   const int ch = blockIdx.z % 3;
   const int r = sb.r[ch];
   const float* taps = c_taps[sb.kind[ch]];
@@ -453,10 +485,11 @@ k_blur_small_hv(const float* __restrict__ in, float* __restrict__ out, size_t pl
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_edge_detector_map(const float* __restrict__ bl0, const float* __restrict__ bl1, size_t stride,
-                    int W, int H, int P, int rxs, float* __restrict__ out) {
+                    int W, int H, int P, int rxs, float* __restrict__ out, DirtyMask dm) {
   const int rx = blockIdx.x * 32 + threadIdx.x, ry = blockIdx.y * 8 + threadIdx.y;
   const int res_x = 3 * rx, res_y = 3 * ry;
   if (!(res_x + 5 < W && res_y + 5 < H)) return;
+  if (!dirty_at(dm, res_x, res_y)) return;
   const int px = min(res_x, W - 8), py = min(res_y, H - 8);
   const double w = 0.711100840192;
   double acc[3] = {0.0, 0.0, 0.0};
@@ -499,7 +532,7 @@ constexpr int kBdmWarps = 4;
 __global__ void __launch_bounds__(32 * kBdmWarps)
 k_block_diff_map(const float* __restrict__ a, const float* __restrict__ b, size_t stride, int W,
                  int H, int P, int rxs, int ncx, int ncy, float* __restrict__ dc_out,
-                 float* __restrict__ ac_out) {
+                 float* __restrict__ ac_out, DirtyMask dm) {
   __shared__ float s_a[kBdmWarps][192];
   __shared__ float s_b[kBdmWarps][192];
   __shared__ double s_ws[kBdmWarps][kBlockDiffScratchDoubles];
@@ -508,6 +541,7 @@ k_block_diff_map(const float* __restrict__ a, const float* __restrict__ b, size_
   const double csf_a = kCsf8x8[4 + lane], csf_b = kCsf8x8[36];
   for (int cell = blockIdx.x * kBdmWarps + warp; cell < total; cell += gridDim.x * kBdmWarps) {
     const int ry = cell / ncx, rx = cell - ry * ncx;
+    if (!dirty_at(dm, 3 * rx, 3 * ry)) continue;
     const int ox = min(3 * rx, W - 8), oy = min(3 * ry, H - 8);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -531,10 +565,11 @@ k_block_diff_map(const float* __restrict__ a, const float* __restrict__ b, size_
 // colour metric. (The warp-per-cell kernel would spend 64 dependent additions on three lanes.)
 __global__ void __launch_bounds__(128)
 k_block_dc(const float* __restrict__ a, const float* __restrict__ b, size_t stride, int W, int H, int P,
-           int rxs, int ncx, int ncy, float* __restrict__ dc_out) {
+           int rxs, int ncx, int ncy, float* __restrict__ dc_out, DirtyMask dm) {
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= ncx * ncy) return;
   const int ry = cell / ncx, rx = cell - ry * ncx;
+  if (!dirty_at(dm, 3 * rx, 3 * ry)) return;
   const int ox = min(3 * rx, W - 8), oy = min(3 * ry, H - 8);
   double m[3];
 #pragma unroll 1
@@ -560,14 +595,17 @@ k_block_dc(const float* __restrict__ a, const float* __restrict__ b, size_t stri
 
 // ---------------------------------------------------------------------------------------------
 // K7: EdgeDetectorLowFreq consumer (butteraugli.cc:1164-1204). Reads the decimated sigma-14 maps:
-// blurred[y][x] == small[y/4][x/4]. One lattice point per thread; adds into block_diff_ac.
+// blurred[y][x] == small[y/4][x/4]. One lattice point per thread. The reference adds the term into
+// block_diff_ac; here it is stored in its own res map (same cell, two to the right of the lattice
+// point) and k_combine performs the float addition, so that the term can be refreshed on its own.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_edge_lowfreq(const float* __restrict__ s0, const float* __restrict__ s1, size_t stride,
-               int spitch, int step, int W, int H, int rxs, float* __restrict__ ac_io) {
+               int spitch, int step, int W, int H, int rxs, float* __restrict__ term_out, DirtyMask dm) {
   const int cx = blockIdx.x * 32 + threadIdx.x, cy = blockIdx.y * 8 + threadIdx.y;
   const int x = 3 * cx, y = 3 * cy;
   if (!(x + 8 < W && y + 8 < H)) return;
+  if (!dirty_at(dm, x, y)) return;
   const int ox[4] = {x + 8, x, x + 6, x - 6};
   const int oy[4] = {y, y + 8, y + 6, y + 6};
   const size_t i0 = static_cast<size_t>(y / step) * spitch + x / step;
@@ -589,9 +627,9 @@ k_edge_lowfreq(const float* __restrict__ s0, const float* __restrict__ s1, size_
 #pragma unroll
     for (int c = 0; c < 3; ++c) best[c] = best[c] < sq[c] ? sq[c] : best[c];
   }
-  float* o = ac_io + 3 * (static_cast<size_t>(cy) * rxs + cx + 2);
+  float* o = term_out + 3 * (static_cast<size_t>(cy) * rxs + cx + 2);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) o[c] += static_cast<float>(10 * best[c]);
+  for (int c = 0; c < 3; ++c) o[c] = static_cast<float>(10 * best[c]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -602,7 +640,8 @@ k_edge_lowfreq(const float* __restrict__ s0, const float* __restrict__ s1, size_
 constexpr int kMpT = 32;
 __global__ void __launch_bounds__(256)
 k_mask_front(const float* __restrict__ a, const float* __restrict__ b, size_t stride, int W, int H,
-             int P, float* __restrict__ out) {
+             int P, float* __restrict__ out, DirtyMask dm) {
+  if (!dirty_at(dm, blockIdx.x * kMpT, blockIdx.y * kMpT)) return;   // the CTA's tile is the mask's tile
   __shared__ float s_a[kMpT + 7][kMpT + 7 + 1];   // xyb tile, origin (-2,-2), 39 x 39
   __shared__ float s_b[kMpT + 7][kMpT + 7 + 1];
   __shared__ float s_p[kMpT + 5][kMpT + 5 + 1];   // precompute, origin (-1,-1)
@@ -714,18 +753,21 @@ __device__ __forceinline__ void mask_at(const MaskSample& ms, int px, int py, do
 }
 
 __global__ void __launch_bounds__(256)
-k_combine(MaskSample ms, const float* __restrict__ dc, const float* __restrict__ ac,
+k_combine(MaskSample ms, const float* __restrict__ dc, const float* __restrict__ ac, const float* __restrict__ lft,
           const float* __restrict__ edm, int W, int H, int rxs, int rys, int sq_pitch,
-          float* __restrict__ sq) {
+          float* __restrict__ sq, DirtyMask dm) {
   const int rx = blockIdx.x * 32 + threadIdx.x, ry = blockIdx.y * 8 + threadIdx.y;
   if (rx >= rxs || ry >= rys) return;
+  if (!dirty_at(dm, 3 * rx, 3 * ry)) return;
   float r = 0.0f;
   if (3 * rx + 5 < W && 3 * ry + 5 < H) {
     double mask[3], mdc[3];
     mask_at(ms, 3 * rx + 3, 3 * ry + 3, mask, mdc, true);
     const size_t o = 3 * (static_cast<size_t>(ry) * rxs + rx);
     const double t0 = dc[o] * mdc[0] + dc[o + 1] * mdc[1] + dc[o + 2] * mdc[2];
-    const double t1 = ac[o] * mask[0] + ac[o + 1] * mask[1] + ac[o + 2] * mask[2];
+    // block_diff_ac after EdgeDetectorLowFreq: the float sum the reference keeps (butteraugli.cc:1201)
+    const float a0 = ac[o] + lft[o], a1 = ac[o + 1] + lft[o + 1], a2 = ac[o + 2] + lft[o + 2];
+    const double t1 = a0 * mask[0] + a1 * mask[1] + a2 * mask[2];
     const double t2 = edm[o] * mask[0] + edm[o + 1] * mask[1] + edm[o + 2] * mask[2];
     const float v = static_cast<float>(t0 + t1 + t2);
     r = v < (1.0 / (100.0f * 100.0f)) ? 100.0f * v : sqrtf(v);
@@ -752,8 +794,12 @@ __global__ void k_block_mask_scale(MaskSample ms, int bw, int bh, float* __restr
 __global__ void __launch_bounds__(256)
 k_diffmap_final(const float* __restrict__ sq, int sq_pitch, const float* __restrict__ small,
                 int small_pitch, int bstep, int W, int H, int out_pitch, float* __restrict__ out,
-                unsigned int* __restrict__ dist_bits) {
+                unsigned int* __restrict__ cta_max, DirtyMask dm) {
+  __shared__ unsigned int s_max;
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (!dirty_at(dm, blockIdx.x * 32, blockIdx.y * 8)) return;   // a 32x8 CTA lies inside one mask tile
+  if (threadIdx.x == 0 && threadIdx.y == 0) s_max = 0u;
+  __syncthreads();
   float v = 0.0f;
   if (x < W && y < H) {
     float up = 0.0f;
@@ -773,7 +819,21 @@ k_diffmap_final(const float* __restrict__ sq, int sq_pitch, const float* __restr
   unsigned int bits = __float_as_uint(v > 0.0f ? v : 0.0f);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
-  if (threadIdx.x == 0 && bits != 0) atomicMax(dist_bits, bits);
+  if (threadIdx.x == 0 && bits != 0) atomicMax(&s_max, bits);
+  __syncthreads();
+  // the maximum of every CTA's pixels stays in cta_max, so that a later Compare that skips this CTA
+  // still finds it (k_max_u32 reduces the array)
+  if (threadIdx.x == 0 && threadIdx.y == 0) cta_max[blockIdx.y * gridDim.x + blockIdx.x] = s_max;
+}
+
+// Maximum of n unsigned values into *out (which the caller zeroes): the score of the diffmap.
+__global__ void __launch_bounds__(256)
+k_max_u32(const unsigned int* __restrict__ v, int n, unsigned int* __restrict__ out) {
+  unsigned int m = 0u;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, v[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(out, m);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -341,6 +341,12 @@ int gzb_get_transfer_bytes(const gzb_ctx* ctx, unsigned long long* h2d, unsigned
 float gzb_last_device_ms(const gzb_ctx* ctx);
 /* Number of kernels launched by this context since creation (bench `gpu_launches`). */
 unsigned long long gzb_launch_count(const gzb_ctx* ctx);
+/* Number of Compares of this context that were incremental: between two Compares separated only by
+ * gzb_update_coeffs calls touching few blocks (the back end's iterations), every stage of the pipeline
+ * recomputes only the 32x32-pixel tiles the changed blocks can reach (bounded supports of the blurs and
+ * block transforms); all other values are still in the context's buffers. The results are bit-identical
+ * to a full Compare. GZB_NO_INCREMENTAL=1 in the environment disables it. */
+unsigned long long gzb_incremental_compare_count(const gzb_ctx* ctx);
 
 #ifdef __cplusplus
 }

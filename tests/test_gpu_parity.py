@@ -223,3 +223,50 @@ def test_error_paths(gz):
     with pytest.raises(gz.GzbError):
         cmp_.ComputeBlockZeroingOrder(7)                         # StartBlockComparisons missing
     cmp_.close()
+
+
+@pytest.mark.parametrize("w,h,yuv420,maxchg", [(200, 133, False, 8), (1000, 700, False, 2), (2048, 1536, False, 6),
+                                               (257, 131, True, 4), (1200, 800, True, 2)])
+def test_incremental_compare_equals_full(gz, w, h, yuv420, maxchg):
+    """Compares that follow sparse coefficient updates recompute only the tiles the changed blocks can
+    reach; diffmap and distance must equal those of a full Compare of the same coefficients (a second
+    context that never saw the earlier states), bit for bit, over a chain of updates."""
+    img = synth_image(w, h, 21)
+    target = 0.97
+    a = gz.ButteraugliComparator(w, h, img, target)
+    b = gz.ButteraugliComparator(w, h, img, target)
+    co = gz.RgbToJpegCoeffs(img)
+    for c in (a, b):
+        c.SetJpegCoeffs(co)
+        if yuv420:
+            c.Downsample420()
+        c.CopyFromJpegData()
+        c.ApplyGlobalQuantization(np.full(192, 4, np.int32))
+    a.Compare()
+    rng = np.random.default_rng(9)
+    base = a.incremental_compare_count()
+    assert base == 0
+    for step in range(12):
+        cur = a.GetCoeffs()
+        blocks, idxs, vals = [], [], []
+        nchg = int(rng.integers(1, maxchg + 1))
+        for _ in range(nchg):
+            comp = int(rng.integers(0, 3))
+            nb = cur[comp].shape[0]
+            # favour the image border and corners, where the clamped windows and blur borders live
+            blk = int(rng.integers(0, nb)) if rng.random() < 0.6 else int(rng.choice([0, nb - 1, nb // 2]))
+            k = int(rng.integers(0, 64))
+            v = int(rng.integers(-8, 9)) * 4
+            blocks.append(blk); idxs.append(64 * comp + k); vals.append(v)
+        a.UpdateCoeffs(blocks, idxs, vals)
+        d = a.Compare()
+        b.SetCoeffs(a.GetCoeffs())
+        d_full = b.Compare()
+        report("incremental diffmap step %d" % step, a.distmap(), b.distmap())
+        assert float(d) == float(d_full)
+    if w * h >= 700000:
+        assert a.incremental_compare_count() >= 8, a.incremental_compare_count()
+    else:   # the reachable area covers most of a small image: the Compares stay full
+        assert a.incremental_compare_count() == 0
+    assert b.incremental_compare_count() == 0
+    a.close(); b.close()
