@@ -177,7 +177,7 @@ class LazySort {
       pending_.pop_back();
       if (r.last - r.first <= kPiece || r.depth == 0) { pieces.push_back(r); continue; }
       --r.depth;
-      OrderEntry* cut = (r.last - r.first >= kParallelMin) ? parallel_partition_pivot(d_ + r.first, d_ + r.last)
+      OrderEntry* cut = (r.last - r.first >= par_min()) ? parallel_partition_pivot(d_ + r.first, d_ + r.last)
                                                           : std::__unguarded_partition_pivot(d_ + r.first, d_ + r.last, comp);
       const size_t c = static_cast<size_t>(cut - d_);
       pending_.push_back({c, r.last, r.depth});
@@ -222,7 +222,7 @@ class LazySort {
         break;  // ranges are disjoint and ordered: nothing else starts before p
       }
       --r.depth;
-      const bool par = pool_ && pool_->size() > 1 && r.last - r.first >= kParallelMin;
+      const bool par = pool_ && pool_->size() > 1 && r.last - r.first >= par_min();
       const double t0 = now_ms();
       OrderEntry* cut = par ? parallel_partition_pivot(d_ + r.first, d_ + r.last)
                             : std::__unguarded_partition_pivot(d_ + r.first, d_ + r.last, comp);
@@ -238,7 +238,11 @@ class LazySort {
 
  private:
   struct Range { size_t first, last; int depth; };
-  static constexpr size_t kParallelMin = size_t(1) << 16;
+  // smallest range partitioned in parallel (GZB_PAR_MIN overrides it: tuning probe)
+  static size_t par_min() {
+    static const size_t v = getenv("GZB_PAR_MIN") ? static_cast<size_t>(atol(getenv("GZB_PAR_MIN"))) : (size_t(1) << 16);
+    return v;
+  }
 
   // std::__unguarded_partition_pivot(first, last) evaluated in parallel. The sequential scan swaps
   // the k-th element (from the left) that is not less than the pivot with the k-th element (from
@@ -346,7 +350,7 @@ class LazySort {
         return;
       }
       --r.depth;
-      OrderEntry* cut = (pool_ && pool_->size() > 1 && r.last - r.first >= kParallelMin)
+      OrderEntry* cut = (pool_ && pool_->size() > 1 && r.last - r.first >= par_min())
                             ? parallel_partition_pivot(d_ + r.first, d_ + r.last)
                             : std::__unguarded_partition_pivot(d_ + r.first, d_ + r.last, comp);
       const size_t c = static_cast<size_t>(cut - d_);
