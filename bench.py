@@ -67,7 +67,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.mark_at = index, [], None, 0
+
+    def mark(self):
+        """Rows from here on belong to the timed region (the sampler is started earlier, during warm-up,
+        so that nvidia-smi's start-up time does not eat a short timed region)."""
+        self.mark_at = len(self.rows)
 
     def start(self):
         try:
@@ -92,7 +97,8 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows[self.mark_at:] if len(self.rows) > self.mark_at else self.rows
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
@@ -256,8 +262,10 @@ def run_ours(a, rank, world, local):
     n_cmp = 0
     for step in range(a.warmup + a.steps):
         timed = step >= a.warmup
-        if timed and step == a.warmup:
+        if step == 0:
             sampler.start()
+        if timed and step == a.warmup:
+            sampler.mark()
         img = images[step * K]
         # ---- device-resident arm: create outside, run inside the timed region
         encs = [gz.Encoder(images[step * K + k], target, device=local, host_threads=host_threads, profile=False) for k in range(K)]

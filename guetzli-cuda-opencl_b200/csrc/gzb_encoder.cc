@@ -240,7 +240,7 @@ class LazySort {
   struct Range { size_t first, last; int depth; };
   // smallest range partitioned in parallel (GZB_PAR_MIN overrides it: tuning probe)
   static size_t par_min() {
-    static const size_t v = getenv("GZB_PAR_MIN") ? static_cast<size_t>(atol(getenv("GZB_PAR_MIN"))) : (size_t(1) << 16);
+    static const size_t v = getenv("GZB_PAR_MIN") ? static_cast<size_t>(atol(getenv("GZB_PAR_MIN"))) : (size_t(1) << 14);
     return v;
   }
 
