@@ -130,6 +130,14 @@ class ButteraugliComparator:
         _check(lib().gzb_set_jpeg_coeffs(self._ctx, _p(c[0]), _p(c[1]), _p(c[2])), self._ctx)
         self.is_420 = False
 
+    def RgbToJpegCoeffsDevice(self):
+        """EncodeRGBToJpeg (q = 1) of the context's original image on the device; returns [3, blocks, 64]."""
+        L = lib()
+        L.gzb_rgb_to_jpeg_coeffs_device.argtypes = [C.c_void_p]
+        _check(L.gzb_rgb_to_jpeg_coeffs_device(self._ctx), self._ctx)
+        self.is_420 = False
+        return np.stack(self.GetJpegCoeffs())
+
     def CopyFromJpegData(self, quant=None):
         q = np.ones(192, np.int32) if quant is None else np.ascontiguousarray(quant, np.int32).reshape(192)
         _check(lib().gzb_copy_from_jpeg(self._ctx, _p(q)), self._ctx)

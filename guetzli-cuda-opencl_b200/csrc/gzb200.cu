@@ -847,6 +847,19 @@ int gzb_set_jpeg_coeffs(gzb_ctx* c, const int16_t* c0, const int16_t* c1, const 
   GZB_END(c)
 }
 
+int gzb_rgb_to_jpeg_coeffs_device(gzb_ctx* c) {
+  GZB_TRY(c)
+  c->mode420 = false;
+  c->have_coeffs = false;
+  invalidate_compare_state(c);
+  KLAUNCH(c, KC_MISC, k_rgb_to_coeffs<<<(c->nblocks + 31) / 32, 256, 0, c->stream>>>(c->d_rgb0, c->ps, c->W, c->H, c->P, c->bw, c->nblocks,
+                                                                                c->d_orig, c->cs));
+  sync_check(c);
+  c->have_orig_coeffs = true;
+  c->packed_valid = false;
+  GZB_END(c)
+}
+
 int gzb_copy_from_jpeg(gzb_ctx* c, const int* quant192) {
   GZB_TRY(c)
   if (!c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_copy_from_jpeg: gzb_set_jpeg_coeffs not called");

@@ -1021,14 +1021,23 @@ int gzb_encoder_create(int device, const uint8_t* rgb, int width, int height, fl
   int rc = gzb_create(device, width, height, rgb, butteraugli_target, &e.ctx);
   if (rc != GZB_OK) { g_encode_err = gzb_last_error(nullptr); delete enc; return rc; }
   e.st.create_ms = now_ms() - t_create;
-  // EncodeRGBToJpeg (q = 1)
+  // EncodeRGBToJpeg (q = 1): on the device, from the image gzb_create has just uploaded; the host mirror
+  // the back end needs comes back in one copy. (GZB_HOST_FRONTEND=1: the host implementation + upload.)
+  static const bool host_frontend = getenv("GZB_HOST_FRONTEND") != nullptr;
+  bool ok = true;
   {
     const double t0 = now_ms();
-    int16_t* o3[3] = {e.orig[0].data(), e.orig[1].data(), e.orig[2].data()};
-    parallel_rows(e.bh, e.pool.get(), [&](int y0, int y1) { rgb_to_coeffs_rows(rgb, width, height, e.bw, y0, y1, o3); });
+    if (host_frontend) {
+      int16_t* o3[3] = {e.orig[0].data(), e.orig[1].data(), e.orig[2].data()};
+      parallel_rows(e.bh, e.pool.get(), [&](int y0, int y1) { rgb_to_coeffs_rows(rgb, width, height, e.bw, y0, y1, o3); });
+      ok = gzb_set_jpeg_coeffs(e.ctx, e.orig[0].data(), e.orig[1].data(), e.orig[2].data()) == GZB_OK;
+    } else {
+      ok = gzb_rgb_to_jpeg_coeffs_device(e.ctx) == GZB_OK &&
+           gzb_get_jpeg_coeffs(e.ctx, e.orig[0].data(), e.orig[1].data(), e.orig[2].data()) == GZB_OK;
+    }
     e.st.host_frontend_ms = now_ms() - t0;
   }
-  if (gzb_set_jpeg_coeffs(e.ctx, e.orig[0].data(), e.orig[1].data(), e.orig[2].data()) != GZB_OK) {
+  if (!ok) {
     g_encode_err = gzb_last_error(e.ctx);
     gzb_destroy(e.ctx);
     delete enc;

@@ -70,6 +70,110 @@ __global__ void k_scatter_coeffs(const int* __restrict__ block_ix, const int16_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// K0b: the RGB front end on the device: EncodeRGBToJpeg with the all-ones quantiser
+//   (guetzli/jpeg_data_encoder.cc:28-117): RGB -> YCbCr in 16.16 fixed point, the integer forward DCT
+//   (guetzli/fdct.cc:28-240: column pass then row pass, truncating shifts, int16 stores) and the q = 1
+//   "quantisation" ((v * 65537 + (0x80 << 12)) >> 20). Window columns / rows past the image replicate
+//   the last one. CTA = 256 threads = 32 blocks x 8 threads; thread t owns row t, column t, row t.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fd_mul16(int a, int b) { return (a * b) >> 16; }
+__device__ __forceinline__ int fd_s16(int v) { return static_cast<int>(static_cast<int16_t>(v)); }
+
+__device__ __forceinline__ void fdct_column8(int v[8]) {
+  const int i0 = v[0], i1 = v[1], i2 = v[2], i3 = v[3], i4 = v[4], i5 = v[5], i6 = v[6], i7 = v[7];
+  int d07 = i0 - i7, s07 = i0 + i7, d25 = i2 - i5, s25 = i2 + i5;
+  int d34 = i3 - i4, s34 = i3 + i4, d16 = i1 - i6, s16 = i1 + i6;
+  int e0 = s07 - s34, e1 = s07 + s34, e2 = s16 - s25, e3 = s16 + s25;
+  e1 <<= 3; e3 <<= 3;
+  v[0] = fd_s16(e1 + e3);
+  v[4] = fd_s16(e1 - e3);
+  e0 <<= 3; e2 <<= 3; d34 <<= 3; d07 <<= 3;
+  v[2] = fd_s16(fd_mul16(27146, e2) + e0);
+  v[6] = fd_s16(fd_mul16(27146, e0) - e2);
+  d25 <<= 4; d16 <<= 4;
+  const int r = fd_mul16(d16 + d25, 23170), s = fd_mul16(d16 - d25, 23170);
+  const int p3 = d34 - s, p1 = d34 + s, p0 = d07 - r, p2 = d07 + r;
+  const int q3 = fd_mul16(p3, -21746) + p3 + 1;
+  const int q1 = fd_mul16(p1, 13036) + p2 + 1;
+  const int q4 = fd_mul16(-21746, p0) + p0;
+  const int q5 = fd_mul16(13036, p2);
+  v[1] = fd_s16(q1);
+  v[3] = fd_s16(p0 - q3);
+  v[5] = fd_s16(p3 + q4);
+  v[7] = fd_s16(q5 - p1);
+}
+
+__constant__ const int kFdctRowTab[4][7] = {{22725, 21407, 19266, 16384, 12873, 8867, 4520},
+                                            {31521, 29692, 26722, 22725, 17855, 12299, 6270},
+                                            {29692, 27969, 25172, 21407, 16819, 11585, 5906},
+                                            {26722, 25172, 22654, 19266, 15137, 10426, 5315}};
+
+__device__ __forceinline__ void fdct_row8(int in[8], int row) {
+  const int sel = row == 0 || row == 4 ? 0 : (row == 1 || row == 7) ? 1 : (row == 2 || row == 6) ? 2 : 3;
+  const int* t = kFdctRowTab[sel];
+  const int a0 = in[0] + in[7], b0 = in[0] - in[7], a1 = in[1] + in[6], b1 = in[1] - in[6];
+  const int a2 = in[2] + in[5], b2 = in[2] - in[5], a3 = in[3] + in[4], b3 = in[3] - in[4];
+  const int C1 = t[0], C2 = t[1], C3 = t[2], C4 = t[3], C5 = t[4], C6 = t[5], C7 = t[6];
+  const int c0 = a0 + a3, c1 = a0 - a3, c2 = a1 + a2, c3 = a1 - a2;
+  in[0] = fd_s16((C4 * (c0 + c2)) >> 16);
+  in[4] = fd_s16((C4 * (c0 - c2)) >> 16);
+  in[2] = fd_s16((C2 * c1 + C6 * c3) >> 16);
+  in[6] = fd_s16((C6 * c1 - C2 * c3) >> 16);
+  in[1] = fd_s16((C1 * b0 + C3 * b1 + C5 * b2 + C7 * b3) >> 16);
+  in[3] = fd_s16((C3 * b0 - C7 * b1 - C1 * b2 - C5 * b3) >> 16);
+  in[5] = fd_s16((C5 * b0 - C1 * b1 + C7 * b2 + C3 * b3) >> 16);
+  in[7] = fd_s16((C7 * b0 - C5 * b1 + C3 * b2 - C1 * b3) >> 16);
+}
+
+__global__ void __launch_bounds__(256)
+k_rgb_to_coeffs(const uint8_t* __restrict__ planes, size_t plane_stride, int W, int H, int P, int bw, int nblocks,
+                int16_t* __restrict__ out, size_t comp_stride) {
+  __shared__ int s[3][32][8][9];
+  const int lb = threadIdx.x >> 3, t = threadIdx.x & 7;
+  const int b = blockIdx.x * 32 + lb;
+  const bool live = b < nblocks;
+  const int bx = live ? b % bw : 0, by = live ? b / bw : 0;
+  {  // row t of the window: RGB -> YCbCr (int16 like the reference's block arrays)
+    const int y = min(H - 1, 8 * by + t);
+#pragma unroll
+    for (int ix = 0; ix < 8; ++ix) {
+      const int x = min(W - 1, 8 * bx + ix);
+      const size_t g = static_cast<size_t>(y) * P + x;
+      const int r = planes[g], gg = planes[plane_stride + g], bl = planes[2 * plane_stride + g];
+      s[0][lb][t][ix] = fd_s16((19595 * r + 38469 * gg + 7471 * bl - (128 << 16) + 32768) >> 16);
+      s[1][lb][t][ix] = fd_s16((-11059 * r - 21709 * gg + 32768 * bl + 32768 - 1) >> 16);
+      s[2][lb][t][ix] = fd_s16((32768 * r - 27439 * gg - 5329 * bl + 32768 - 1) >> 16);
+    }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int c = 0; c < 3; ++c) {
+    int v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = s[c][lb][k][t];   // column t
+    fdct_column8(v);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[c][lb][k][t] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = s[c][lb][t][k];   // row t
+    fdct_row8(v, t);
+    if (live) {
+      int e[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e[k] = fd_s16((v[k] * 65537 + (0x80 << 12)) >> 20);
+      int4 o;
+      o.x = (e[0] & 0xffff) | (e[1] << 16);
+      o.y = (e[2] & 0xffff) | (e[3] << 16);
+      o.z = (e[4] & 0xffff) | (e[5] << 16);
+      o.w = (e[6] & 0xffff) | (e[7] << 16);
+      reinterpret_cast<int4*>(out + c * comp_stride)[static_cast<size_t>(b) * 8 + t] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1: coefficients -> candidate sRGB8 planes (integer IDCT + YCbCr->RGB).
 //   guetzli/output_image.cc:124-146 (SetCoeffBlock), 68-98 (ToPixels), 642-652 (ToSRGB);
 //   in 4:4:4 the stored pixel is idct<<4 and (p+8-(x&1))>>4 returns the idct value.

@@ -65,6 +65,10 @@ void gzb_destroy(gzb_ctx* ctx);
 /* Uploads the q=1 JPEG coefficients of the (4:4:4) input (jpg.components[c].coeffs); the context
  * returns to 4:4:4 if it was 4:2:0. */
 int gzb_set_jpeg_coeffs(gzb_ctx* ctx, const int16_t* c0, const int16_t* c1, const int16_t* c2);
+/* The same coefficients computed ON THE DEVICE from the context's original image: EncodeRGBToJpeg with
+ * the all-ones quantiser (guetzli/jpeg_data_encoder.cc:28-117, guetzli/fdct.cc:28-240; exact integer
+ * arithmetic). gzb_get_jpeg_coeffs returns them to the host. */
+int gzb_rgb_to_jpeg_coeffs_device(gzb_ctx* ctx);
 /* OutputImage::CopyFromJpegData (guetzli/output_image.cc:212-228, 481-492): coeff * quant.
  * Replaces cuCopyFromJpegComponent (clguetzli/cuguetzli.h:138-148). quant: int[3][64]. */
 int gzb_copy_from_jpeg(gzb_ctx* ctx, const int* quant192);

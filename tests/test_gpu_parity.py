@@ -270,3 +270,16 @@ def test_incremental_compare_equals_full(gz, w, h, yuv420, maxchg):
         assert a.incremental_compare_count() == 0
     assert b.incremental_compare_count() == 0
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("w,h", [(32, 32), (33, 47), (97, 61), (200, 133), (444, 258), (1024, 768)])
+def test_rgb_front_end_on_device(gz, w, h):
+    """EncodeRGBToJpeg with q = 1 (RGB -> YCbCr fixed point, integer forward DCT) on the device equals the
+    oracle's restatement (itself pinned to the reference) and the library's host implementation."""
+    rng = np.random.default_rng(4)
+    img = synth_image(w, h, 77) if (w + h) % 2 else rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+    c = gz.ButteraugliComparator(w, h, img, 0.97)
+    got = c.RgbToJpegCoeffsDevice()
+    report("device front end vs oracle", got, jpeg_coeffs(img))
+    report("device front end vs host", got, gz.RgbToJpegCoeffs(img))
+    c.close()
