@@ -394,13 +394,15 @@ void render_candidate(gzb_ctx* c, int op) {
     for (int k = 0; k < 3; ++k) {
       const int nb = static_cast<int>(comp_blocks(c, k));
       const int grid = (nb + 31) / 32;
-      const int16_t* src = (op == kCoeffScale ? c->d_orig : c->d_coef) + k * cs;
+      const int16_t* src = ((op == kCoeffScale || op == kCoeffQuantizeSrc) ? c->d_orig : c->d_coef) + k * cs;
       int16_t* dst = c->d_coef + k * cs;
       uint8_t* plane = c->d_ycc + k * us;
       if (op == kCoeffKeep)
         KLAUNCH(c, KC_IDCT, k420_idct_comp<kCoeffKeep><<<grid, 256, 0, c->stream>>>(src, dst, c->d_q + 64 * k, comp_bw(c, k), nb, c->P, plane));
       else if (op == kCoeffQuantize)
         KLAUNCH(c, KC_IDCT, k420_idct_comp<kCoeffQuantize><<<grid, 256, 0, c->stream>>>(src, dst, c->d_q + 64 * k, comp_bw(c, k), nb, c->P, plane));
+      else if (op == kCoeffQuantizeSrc)
+        KLAUNCH(c, KC_IDCT, k420_idct_comp<kCoeffQuantizeSrc><<<grid, 256, 0, c->stream>>>(src, dst, c->d_q + 64 * k, comp_bw(c, k), nb, c->P, plane));
       else
         KLAUNCH(c, KC_IDCT, k420_idct_comp<kCoeffScale><<<grid, 256, 0, c->stream>>>(src, dst, c->d_q + 64 * k, comp_bw(c, k), nb, c->P, plane));
     }
@@ -413,6 +415,8 @@ void render_candidate(gzb_ctx* c, int op) {
     KLAUNCH(c, KC_IDCT, k_coeffs_to_rgb8<kCoeffKeep><<<grid, 256, 0, c->stream>>>(c->d_coef, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us));
   else if (op == kCoeffQuantize)
     KLAUNCH(c, KC_IDCT, k_coeffs_to_rgb8<kCoeffQuantize><<<grid, 256, 0, c->stream>>>(c->d_coef, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us));
+  else if (op == kCoeffQuantizeSrc)
+    KLAUNCH(c, KC_IDCT, k_coeffs_to_rgb8<kCoeffQuantizeSrc><<<grid, 256, 0, c->stream>>>(c->d_orig, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us));
   else
     KLAUNCH(c, KC_IDCT, k_coeffs_to_rgb8<kCoeffScale><<<grid, 256, 0, c->stream>>>(c->d_orig, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us));
 }
@@ -866,6 +870,18 @@ int gzb_copy_from_jpeg(gzb_ctx* c, const int* quant192) {
   CK(cudaMemcpyAsync(c->d_q, quant192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (192 * sizeof(int));
   invalidate_compare_state(c);
   render_candidate(c, kCoeffScale);
+  sync_check(c);
+  c->have_coeffs = true;
+  GZB_END(c)
+}
+
+int gzb_quantize_from_jpeg(gzb_ctx* c, const int* q192) {
+  GZB_TRY(c)
+  if (!c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_quantize_from_jpeg: gzb_set_jpeg_coeffs not called");
+  for (int i = 0; i < 192; ++i) if (q192[i] <= 0) return fail(c, GZB_ERR_BAD_ARG, "quantiser must be positive");
+  CK(cudaMemcpyAsync(c->d_q, q192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (192 * sizeof(int));
+  invalidate_compare_state(c);
+  render_candidate(c, kCoeffQuantizeSrc);
   sync_check(c);
   c->have_coeffs = true;
   GZB_END(c)

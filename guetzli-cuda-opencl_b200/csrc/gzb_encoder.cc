@@ -659,10 +659,7 @@ struct Encoder {
 
   // img.CopyFromJpegData(jpg) ; img.ApplyGlobalQuantization(q): the device candidate ...
   bool set_global_quant_device(const int q[3][64]) {
-    int ones[192];
-    for (int i = 0; i < 192; ++i) ones[i] = 1;
-    if (gzb_copy_from_jpeg(ctx, ones) != GZB_OK) return false;
-    return gzb_apply_global_quantization(ctx, &q[0][0]) == GZB_OK;
+    return gzb_quantize_from_jpeg(ctx, &q[0][0]) == GZB_OK;
   }
   // ... and its host mirror (the quantised indices the JPEG writer codes)
   void set_global_quant_host(const int q[3][64]) {

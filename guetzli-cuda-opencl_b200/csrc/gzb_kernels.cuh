@@ -181,7 +181,9 @@ k_rgb_to_coeffs(const uint8_t* __restrict__ planes, size_t plane_stride, int W, 
 // Optionally applies a global quantiser first (ApplyGlobalQuantization, output_image.cc:349-360)
 // or the coeff*quant copy (CopyFromJpegComponent, 212-228) and writes the coefficients back.
 // ---------------------------------------------------------------------------------------------
-enum CoeffOp { kCoeffKeep = 0, kCoeffQuantize = 1, kCoeffScale = 2 };
+// kCoeffQuantizeSrc: quantise `src` (the q = 1 input) into `dst`: CopyFromJpegData with the all-ones matrix
+// followed by ApplyGlobalQuantization, in one pass.
+enum CoeffOp { kCoeffKeep = 0, kCoeffQuantize = 1, kCoeffScale = 2, kCoeffQuantizeSrc = 3 };
 
 template <int OP>
 __global__ void __launch_bounds__(256)
@@ -203,8 +205,8 @@ k_coeffs_to_rgb8(const int16_t* __restrict__ src, int16_t* __restrict__ dst, siz
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int q = q192[64 * c + 8 * t + k];
-          e[k] = OP == kCoeffQuantize ? quantize_coeff(e[k], q)
-                                      : static_cast<int>(static_cast<int16_t>(e[k] * q));
+          e[k] = (OP == kCoeffQuantize || OP == kCoeffQuantizeSrc) ? quantize_coeff(e[k], q)
+                                                                   : static_cast<int>(static_cast<int16_t>(e[k] * q));
         }
         int4 o;
         o.x = (e[0] & 0xffff) | (e[1] << 16);

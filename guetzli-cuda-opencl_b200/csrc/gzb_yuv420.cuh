@@ -43,7 +43,7 @@ k420_idct_comp(const int16_t* __restrict__ src, int16_t* __restrict__ dst, const
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int q = q64[8 * t + k];
-        e[k] = OP == kCoeffQuantize ? quantize_coeff(e[k], q) : static_cast<int>(static_cast<int16_t>(e[k] * q));
+        e[k] = (OP == kCoeffQuantize || OP == kCoeffQuantizeSrc) ? quantize_coeff(e[k], q) : static_cast<int>(static_cast<int16_t>(e[k] * q));
       }
       int4 o;
       o.x = (e[0] & 0xffff) | (e[1] << 16);

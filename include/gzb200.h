@@ -75,6 +75,9 @@ int gzb_copy_from_jpeg(gzb_ctx* ctx, const int* quant192);
 /* OutputImage::ApplyGlobalQuantization (guetzli/output_image.cc:349-360, 573-577).
  * Replaces cuApplyGlobalQuantization (clguetzli/cuguetzli.h:150-156). q: int[3][64]. */
 int gzb_apply_global_quantization(gzb_ctx* ctx, const int* q192);
+/* img.CopyFromJpegData(jpg) with the all-ones matrix followed by img.ApplyGlobalQuantization(q) -- the
+ * head of TryQuantMatrix (guetzli/processor.cc:283-284) -- in one pass over the input coefficients. */
+int gzb_quantize_from_jpeg(gzb_ctx* ctx, const int* q192);
 /* Replaces the candidate's coefficients wholesale (SetCoeffBlock for every block). */
 int gzb_set_coeffs(gzb_ctx* ctx, const int16_t* c0, const int16_t* c1, const int16_t* c2);
 int gzb_get_coeffs(gzb_ctx* ctx, int16_t* c0, int16_t* c1, int16_t* c2);
