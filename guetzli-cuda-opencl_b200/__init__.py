@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgzb200.so")
+LIB_PATH = os.environ.get("GZB200_LIB") or os.path.join(_HERE, "libgzb200.so")   # GZB200_LIB: A/B timing of two builds
 
 COEFF_DATA = np.dtype([("idx", np.int32), ("err", np.float32)])
 

@@ -248,6 +248,7 @@ struct gzb_ctx {
   cudaStream_t stream2 = nullptr;   // entropy coding of the candidate, concurrent with its Compare
   cudaStream_t stream_b = nullptr, stream_l = nullptr;   // BlockDiffMap / EdgeDetectorLowFreq branches of a Compare
   cudaEvent_t ev_fork = nullptr, ev_bdm = nullptr, ev_lf = nullptr;
+  cudaEvent_t ev_cand = nullptr;    // the candidate (coefficients, quantiser, samples) is complete on the main stream
   bool concurrent = false;          // the branches' blur scratch regions fit side by side in d_tmp
   size_t tmp_main_off = 0;          // floats: where the main stream's blur scratch starts in d_tmp
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -408,6 +409,7 @@ void render_candidate(gzb_ctx* c, int op) {
     }
     dim3 grd((c->W + 1023) / 1024, c->H);
     KLAUNCH(c, KC_IDCT, k420_render<<<grd, 256, 0, c->stream>>>(c->d_ycc, us, c->W, c->H, c->P, c->d_rgb1, c->d_cup));
+    CK(cudaEventRecord(c->ev_cand, c->stream));
     return;
   }
   const int grid = (c->nblocks + 31) / 32;
@@ -419,6 +421,7 @@ void render_candidate(gzb_ctx* c, int op) {
     KLAUNCH(c, KC_IDCT, k_coeffs_to_rgb8<kCoeffQuantizeSrc><<<grid, 256, 0, c->stream>>>(c->d_orig, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us));
   else
     KLAUNCH(c, KC_IDCT, k_coeffs_to_rgb8<kCoeffScale><<<grid, 256, 0, c->stream>>>(c->d_orig, c->d_coef, cs, c->d_q, c->bw, c->nblocks, c->P, c->d_rgb1, us));
+  CK(cudaEventRecord(c->ev_cand, c->stream));
 }
 
 void opsin_from_u8(gzb_ctx* c, const uint8_t* planes, float* xyb, bool masked = false) {
@@ -534,6 +537,7 @@ void free_ctx(gzb_ctx* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_bdm) cudaEventDestroy(c->ev_bdm);
   if (c->ev_lf) cudaEventDestroy(c->ev_lf);
+  if (c->ev_cand) cudaEventDestroy(c->ev_cand);
   delete c;
 }
 
@@ -565,6 +569,7 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_bdm, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_lf, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_cand, cudaEventDisableTiming));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     c->W = W; c->H = H; c->target = target;
@@ -881,8 +886,7 @@ int gzb_quantize_from_jpeg(gzb_ctx* c, const int* q192) {
   for (int i = 0; i < 192; ++i) if (q192[i] <= 0) return fail(c, GZB_ERR_BAD_ARG, "quantiser must be positive");
   CK(cudaMemcpyAsync(c->d_q, q192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (192 * sizeof(int));
   invalidate_compare_state(c);
-  render_candidate(c, kCoeffQuantizeSrc);
-  sync_check(c);
+  render_candidate(c, kCoeffQuantizeSrc);   // no host sync: later calls are ordered by the stream / ev_cand
   c->have_coeffs = true;
   GZB_END(c)
 }
@@ -986,8 +990,7 @@ int gzb_update_coeffs(gzb_ctx* c, const int32_t* block_ix, const uint8_t* idx, c
     if (dbg) { sync_check(c); fprintf(stderr, "update n=%zu validate %.3f ms, h2d+scatter %.3f ms\n", n, d1 - d0, dbg_now_ms() - d1); }
   }
   const double d2 = dbg_now_ms();
-  render_candidate(c, kCoeffKeep);
-  sync_check(c);
+  render_candidate(c, kCoeffKeep);   // no host sync: later calls are ordered by the stream / ev_cand
   if (dbg) fprintf(stderr, "update render %.3f ms\n", dbg_now_ms() - d2);
   GZB_END(c)
 }
@@ -1389,6 +1392,7 @@ int gzb_candidate_symbol_histograms_n(gzb_ctx* c, const int* q192, int ncomp, ui
   const HuffScratch h = huff_scratch(c);
   long long nunits = 0;
   const HuffLayout L = huff_layout(c, ncomp, &nunits);
+  CK(cudaStreamWaitEvent(c->stream2, c->ev_cand, 0));   // the candidate may still be rendering on the main stream
   CK(cudaMemsetAsync(h.hist, 0, (48 + 768) * 4, c->stream2));
   KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_histogram<<<static_cast<unsigned>((nunits + kHuffThreads - 1) / kHuffThreads), kHuffThreads, 0, c->stream2>>>(
       c->d_coef, c->cs, c->d_q, L, nunits, h.hist, h.hist + 48));
@@ -1402,6 +1406,12 @@ int gzb_candidate_symbol_histograms_n(gzb_ctx* c, const int* q192, int ncomp, ui
 
 int gzb_candidate_entropy_code(gzb_ctx* c, int ncomp, const uint16_t* dc_code, const uint8_t* dc_len,
                                const uint16_t* ac_code, const uint8_t* ac_len, uint64_t* scan_bytes, uint64_t* ff_bytes) {
+  return gzb_candidate_entropy_code_sized(c, ncomp, dc_code, dc_len, ac_code, ac_len, ~0ull, scan_bytes, ff_bytes);
+}
+
+int gzb_candidate_entropy_code_sized(gzb_ctx* c, int ncomp, const uint16_t* dc_code, const uint8_t* dc_len,
+                                     const uint16_t* ac_code, const uint8_t* ac_len, uint64_t total_bits_known,
+                                     uint64_t* scan_bytes, uint64_t* ff_bytes) {
   GZB_TRY(c)
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_candidate_entropy_code: no candidate coefficients");
   if ((ncomp != 1 && ncomp != 3) || !dc_code || !dc_len || !ac_code || !ac_len || !scan_bytes || !ff_bytes)
@@ -1412,6 +1422,7 @@ int gzb_candidate_entropy_code(gzb_ctx* c, int ncomp, const uint16_t* dc_code, c
   memcpy(t.dc_len, dc_len, sizeof(t.dc_len));
   memcpy(t.ac_code, ac_code, sizeof(t.ac_code));
   memcpy(t.ac_len, ac_len, sizeof(t.ac_len));
+  CK(cudaStreamWaitEvent(c->stream2, c->ev_cand, 0));   // the candidate may still be rendering on the main stream
   CK(cudaMemcpyAsync(h.tables, &t, sizeof(t), cudaMemcpyHostToDevice, c->stream2)); c->h2d_bytes += sizeof(t);
   long long nunits = 0;
   const HuffLayout L = huff_layout(c, ncomp, &nunits);
@@ -1421,9 +1432,12 @@ int gzb_candidate_entropy_code(gzb_ctx* c, int ncomp, const uint16_t* dc_code, c
                                                                                   h.unit_bits, h.cta_bits, nullptr, nullptr));
   KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_scan_u64<<<1, 1024, 0, c->stream2>>>(h.cta_bits, static_cast<long long>(grid), h.cta_off));
   unsigned long long* hp = reinterpret_cast<unsigned long long*>(c->h_pinned) + 32;  // bytes 256..
-  CK(cudaMemcpyAsync(hp, h.cta_off + grid, 8, cudaMemcpyDeviceToHost, c->stream2)); c->d2h_bytes += 8;
-  sync_check2(c);
-  const unsigned long long total_bits = hp[0];
+  unsigned long long total_bits = total_bits_known;
+  if (total_bits_known == ~0ull) {   // the caller does not know the size: read the total back before the emission pass
+    CK(cudaMemcpyAsync(hp, h.cta_off + grid, 8, cudaMemcpyDeviceToHost, c->stream2)); c->d2h_bytes += 8;
+    sync_check2(c);
+    total_bits = hp[0];
+  }
   const size_t nbytes = static_cast<size_t>((total_bits + 7) / 8);
   if (nbytes + 8 > h.stream_cap) return fail(c, GZB_ERR_UNSUPPORTED, "gzb_candidate_entropy_code: scan larger than the device buffer");
   CK(cudaMemsetAsync(h.words, 0, (nbytes + 7) & ~size_t(3), c->stream2));
@@ -1434,6 +1448,7 @@ int gzb_candidate_entropy_code(gzb_ctx* c, int ncomp, const uint16_t* dc_code, c
   KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_finish<<<fgrid, 256, 0, c->stream2>>>(reinterpret_cast<unsigned char*>(h.words), h.cta_off + grid, h.out2));
   CK(cudaMemcpyAsync(hp, h.out2, 16, cudaMemcpyDeviceToHost, c->stream2)); c->d2h_bytes += 16;
   sync_check2(c);
+  if (hp[0] != nbytes) return fail(c, GZB_ERR_STATE, "gzb_candidate_entropy_code: the size given does not match the candidate");
   *scan_bytes = hp[0];
   *ff_bytes = hp[1];
   GZB_END(c)

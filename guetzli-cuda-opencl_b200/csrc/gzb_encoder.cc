@@ -444,8 +444,15 @@ bool device_code_candidate(gzb_ctx* ctx, int w, int h, int nblocks, const int q[
     for (int i = 0; i < 16; ++i) { dc_code[c][i] = dct[c].code[i]; dc_len[c][i] = dct[c].depth[i] == 255 ? 0 : dct[c].depth[i]; }
     for (int i = 0; i < 256; ++i) { ac_code[c][i] = act[c].code[i]; ac_len[c][i] = act[c].depth[i] == 255 ? 0 : act[c].depth[i]; }
   }
-  return gzb_candidate_entropy_code(ctx, f.ncomp, &dc_code[0][0], &dc_len[0][0], &ac_code[0][0], &ac_len[0][0],
-                                    &out->scan_bytes, &out->ff_bytes) == GZB_OK;
+  // the scan's length follows from the histograms and the code lengths (every symbol is counted twice in a
+  // Histogram): DC symbols carry `symbol` extra bits, AC symbols `symbol & 15`
+  uint64_t total_bits = 0;
+  for (int c = 0; c < f.ncomp; ++c) {
+    for (int i = 0; i < 16; ++i) total_bits += static_cast<uint64_t>(dc_hist[c].counts[i] / 2) * (dc_len[c][i] + i);
+    for (int i = 0; i < 256; ++i) total_bits += static_cast<uint64_t>(ac_hist[c].counts[i] / 2) * (ac_len[c][i] + (i & 15));
+  }
+  return gzb_candidate_entropy_code_sized(ctx, f.ncomp, &dc_code[0][0], &dc_len[0][0], &ac_code[0][0], &ac_len[0][0],
+                                          total_bits, &out->scan_bytes, &out->ff_bytes) == GZB_OK;
 }
 
 // header + byte-stuffed scan + EOI

@@ -170,6 +170,12 @@ int gzb_candidate_symbol_histograms_n(gzb_ctx* ctx, const int* q192, int ncomp, 
 int gzb_candidate_entropy_code(gzb_ctx* ctx, int ncomp, const uint16_t* dc_code, const uint8_t* dc_len,
                                const uint16_t* ac_code, const uint8_t* ac_len, uint64_t* scan_bytes,
                                uint64_t* ff_bytes);
+/* The same when the caller knows the scan's length in bits (it follows from the symbol histograms and the
+ * code lengths): saves the round trip between the sizing and the emission pass. Fails with GZB_ERR_STATE
+ * if the length does not match the candidate. */
+int gzb_candidate_entropy_code_sized(gzb_ctx* ctx, int ncomp, const uint16_t* dc_code, const uint8_t* dc_len,
+                                     const uint16_t* ac_code, const uint8_t* ac_len, uint64_t total_bits,
+                                     uint64_t* scan_bytes, uint64_t* ff_bytes);
 /* Copies the (unstuffed) scan of the last gzb_candidate_entropy_code to the host. */
 int gzb_candidate_fetch_scan(gzb_ctx* ctx, uint8_t* out, uint64_t nbytes);
 /* The whole file: histograms, ClusterHistograms + code construction (host), scan on the device.
