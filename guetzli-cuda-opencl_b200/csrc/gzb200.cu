@@ -131,6 +131,9 @@ struct BlurPlan {
   double* d_sx = nullptr;
   double* d_sy = nullptr;
   bool own = false;            // tables allocated with their own cudaMalloc (stage entry points)
+  CUtensorMap tmap;            // TMA descriptor of the H pass's input planes (when has_tmap)
+  bool has_tmap = false;
+  int box_w = 0;
   std::vector<double> hx, hy;  // host copies of the scale tables
   void build(const HostKernel& hk, int kind, int in_w, int in_h, int in_pitch, int x0, int sx, int nx,
              int y0, int sy, int ny, double border_ratio, int ups) {
@@ -171,6 +174,42 @@ struct BlurPlan {
   size_t tmp_floats() const { return static_cast<size_t>(g.tmp_pitch) * g.in_h; }
   size_t out_floats() const { return static_cast<size_t>(g.tmp_pitch) * std::max(g.ny, 1); }
 };
+
+// TMA descriptor for the H pass of a plan whose input is `planes` float planes of in_pitch x in_h (plane stride
+// `plane_stride` floats) at `in`: a 3-D tiled map (x, y, plane) with a box of box_w x kBhRows x 1 and zero
+// fill outside [0, in_w) x [0, in_h). cuTensorMapEncodeTiled is looked up through the runtime, so the library
+// does not link against libcuda. Returns false (the scalar loader is used) if anything is not as required.
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_blur_tmap(BlurPlan* pl, const float* in, size_t plane_stride, int planes) {
+  static const bool disabled = getenv("GZB_NO_TMA") != nullptr;
+  pl->has_tmap = false;
+  if (disabled || pl->g.ups != 1 || pl->g.nx <= 0) return false;
+  static TensorMapEncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) fn = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<TensorMapEncodeFn>(fn);
+  }();
+  if (!encode) return false;
+  const int span = (pl->g.oxn - 1) * pl->g.sx + 2 * pl->g.r + 1;
+  const int box_w = (span + 3 + 3) & ~3;   // the box starts at a 16-byte boundary up to 3 floats left of the span
+  if (box_w > kBhTmaMaxBox || (reinterpret_cast<uintptr_t>(in) & 15) || (pl->g.in_pitch & 3) || (plane_stride & 3)) return false;
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(pl->g.in_w), static_cast<cuuint64_t>(pl->g.in_h), static_cast<cuuint64_t>(planes)};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(pl->g.in_pitch) * sizeof(float),
+                                 static_cast<cuuint64_t>(std::max<size_t>(plane_stride, static_cast<size_t>(pl->g.in_pitch) * pl->g.in_h)) * sizeof(float)};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(kBhRows), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (encode(&pl->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+  pl->box_w = box_w;
+  pl->has_tmap = true;
+  return true;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Device slabs: one cudaMalloc per context, sub-allocated; released slabs are cached per device so
@@ -374,7 +413,8 @@ void run_blur(gzb_ctx* c, const BlurPlan& pl, const float* in, size_t in_stride,
   dim3 blk(32, 8);
   dim3 gh((g.nx + g.oxn - 1) / g.oxn, (g.in_h + kBhRows - 1) / kBhRows, planes);
   const size_t tstride = pl.tmp_floats();
-  if (g.ups == 1) KLAUNCH_S(c, st, KC_BLUR_H, k_blur_h<1><<<gh, blk, 0, st>>>(in, in_stride, g, pl.d_sx, tmp, tstride, mh));
+  if (pl.has_tmap) KLAUNCH_S(c, st, KC_BLUR_H, k_blur_h_tma<<<gh, blk, 0, st>>>(pl.tmap, g, pl.box_w, pl.d_sx, tmp, tstride, mh));
+  else if (g.ups == 1) KLAUNCH_S(c, st, KC_BLUR_H, k_blur_h<1><<<gh, blk, 0, st>>>(in, in_stride, g, pl.d_sx, tmp, tstride, mh));
   else KLAUNCH_S(c, st, KC_BLUR_H, k_blur_h<3><<<gh, blk, 0, st>>>(in, in_stride, g, pl.d_sx, tmp, tstride, mh));
   dim3 gv((g.nx + 31) / 32, (g.ny + g.oyn - 1) / g.oyn, planes);
   KLAUNCH_S(c, st, KC_BLUR_V, k_blur_v<<<gv, blk, 0, st>>>(tmp, tstride, g, pl.d_sy, out, out_stride, out_pitch, mv));
@@ -628,6 +668,11 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     for (BlurPlan* pl : plans) { need(c, &pl->d_sx, pl->hx.size()); need(c, &pl->d_sy, pl->hy.size()); }
     commit_slab(c);
     for (BlurPlan* pl : plans) pl->upload(c->stream);
+    // TMA descriptors for the H passes whose input planes are fixed: the sigma-14 blur of the six
+    // MaskHighIntensityChange planes and the three mask blurs (+ the block-comparison lattice)
+    make_blur_tmap(&c->p_lf, c->d_mh, c->ps, 6);
+    for (int k = 0; k < 3; ++k) make_blur_tmap(&c->p_mk[k], c->d_bl + k * c->ps, c->ps, 1);
+    make_blur_tmap(&c->p_mkb2, c->d_bl + 2 * c->ps, c->ps, 1);
     c->h_pinned = static_cast<float*>(c->slab.pinned);
     CK(cudaMemsetAsync(c->d_rgb0, 0, 3 * us, c->stream));
     CK(cudaMemsetAsync(c->d_rgb1, 0, 3 * us, c->stream));

@@ -9,6 +9,7 @@
 // Grids are sized from the image; the heavy warp-per-cell kernels run persistent CTAs in
 // multiples of the SM count.
 #pragma once
+#include <cuda.h>   // CUtensorMap (the encoder entry point is resolved at run time: no libcuda link dependency)
 #include "gzb_device_math.cuh"
 
 namespace gzb {
@@ -478,6 +479,68 @@ k_blur_h(const float* __restrict__ in, size_t in_stride, BlurGeom g,
     if (gy >= g.in_h) break;
     if (!dirty_at(dm, g.x0 + ox * g.sx, gy)) continue;
     const float* p = &s[ly][threadIdx.x * g.sx];
+    double acc = 0.0;
+    for (int k = 0; k < nt; ++k) acc += static_cast<double>(p[k] * taps[k]);
+    tmp[static_cast<size_t>(gy) * g.tmp_pitch + ox] = static_cast<float>(acc * sc);
+  }
+}
+
+// The same H pass with its halo tile brought in by the TMA unit: one elected thread arms an mbarrier with
+// the tile's byte count and issues cp.async.bulk.tensor (3-D map: x, y, plane) for the box
+// [xa, xa + box_w) x [yb, yb + 16) of plane blockIdx.z; coordinates left of / beyond the plane are zero
+// filled by the hardware -- exactly the "taps outside the image read 0.0f" rule of the scalar loader.
+// The innermost coordinate of a non-swizzled tiled load must be a multiple of 16 bytes (measured: an odd
+// start faults with "illegal instruction", tests/probes/tma_probe.cu), so the box starts at xs rounded
+// down to 4 floats and is up to 3 floats wider; the taps read from the offset xs - xa.
+constexpr int kBhTmaMaxBox = 196;
+__global__ void __launch_bounds__(256)
+k_blur_h_tma(const __grid_constant__ CUtensorMap tmap, BlurGeom g, int box_w,
+             const double* __restrict__ scale_x, float* __restrict__ tmp, size_t tmp_stride, DirtyMask dm) {
+  __shared__ __align__(128) float s[kBhRows * kBhTmaMaxBox];
+  __shared__ __align__(8) unsigned long long mbar;
+  tmp += blockIdx.z * tmp_stride;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int ox0 = blockIdx.x * g.oxn, yb = blockIdx.y * kBhRows;
+  if (!dirty_any(dm, g.x0 + ox0 * g.sx, yb, g.x0 + (ox0 + g.oxn - 1) * g.sx, yb + kBhRows - 1)) return;
+  const int xs = g.x0 + ox0 * g.sx - g.r;  // first input column of the tile (may be negative)
+  const int xa = xs & ~3;                  // ... rounded down to a 16-byte boundary (two's complement: also for xs < 0)
+  const unsigned mbar_addr = static_cast<unsigned>(__cvta_generic_to_shared(&mbar));
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the initialised barrier must be visible to the async proxy
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned bytes = static_cast<unsigned>(box_w) * kBhRows * sizeof(float);
+    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(s));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_addr), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(mbar_addr), "r"(xa), "r"(yb),
+          "r"(static_cast<int>(blockIdx.z))
+        : "memory");
+  }
+  {  // every thread waits for the bytes to land (phase 0 of the barrier)
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(mbar_addr) : "memory");
+    }
+  }
+  const int ox = ox0 + threadIdx.x;
+  if (ox >= g.nx || threadIdx.x >= g.oxn) return;
+  const double sc = scale_x[ox];
+  const float* taps = c_taps[g.kind];
+  const int nt = 2 * g.r + 1;
+#pragma unroll
+  for (int rr = 0; rr < kBhRows; rr += 8) {
+    const int ly = threadIdx.y + rr, gy = yb + ly;
+    if (gy >= g.in_h) break;
+    if (!dirty_at(dm, g.x0 + ox * g.sx, gy)) continue;
+    const float* p = &s[ly * box_w + (xs - xa) + threadIdx.x * g.sx];
     double acc = 0.0;
     for (int k = 0; k < nt; ++k) acc += static_cast<double>(p[k] * taps[k]);
     tmp[static_cast<size_t>(gy) * g.tmp_pitch + ox] = static_cast<float>(acc * sc);
