@@ -134,6 +134,10 @@ struct BlurPlan {
   CUtensorMap tmap;            // TMA descriptor of the H pass's input planes (when has_tmap)
   bool has_tmap = false;
   int box_w = 0;
+  CUtensorMap tmap_v;          // TMA descriptor of the V pass's input: the H-pass scratch at tmap_v_base
+  bool has_tmap_v = false;
+  int box_rows = 0;
+  const float* tmap_v_base = nullptr;
   std::vector<double> hx, hy;  // host copies of the scale tables
   void build(const HostKernel& hk, int kind, int in_w, int in_h, int in_pitch, int x0, int sx, int nx,
              int y0, int sy, int ny, double border_ratio, int ups) {
@@ -210,6 +214,33 @@ static bool make_blur_tmap(BlurPlan* pl, const float* in, size_t plane_stride, i
   pl->has_tmap = true;
   return true;
 }
+static bool make_blur_tmap_v(BlurPlan* pl, const float* tmp, int planes) {
+  static const bool disabled = getenv("GZB_NO_TMA") != nullptr;
+  pl->has_tmap_v = false;
+  if (disabled || pl->g.nx <= 0 || pl->g.ny <= 0) return false;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || !fn) { cudaGetLastError(); return false; }
+  const int rows = (pl->g.oyn - 1) * pl->g.sy + 2 * pl->g.r + 1;
+  if (rows > kBvMaxRows || (reinterpret_cast<uintptr_t>(tmp) & 15) || (pl->g.tmp_pitch & 3)) return false;
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(pl->g.nx), static_cast<cuuint64_t>(pl->g.in_h), static_cast<cuuint64_t>(planes)};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(pl->g.tmp_pitch) * sizeof(float),
+                                 static_cast<cuuint64_t>(pl->tmp_floats()) * sizeof(float)};
+  const cuuint32_t box[3] = {32, static_cast<cuuint32_t>(rows), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (reinterpret_cast<TensorMapEncodeFn>(fn)(&pl->tmap_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(tmp), gdim, gstride, box,
+                                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+  pl->box_rows = rows;
+  pl->tmap_v_base = tmp;
+  pl->has_tmap_v = true;
+  return true;
+}
+
+// The same for the V pass: its input is the H-pass scratch (nx columns at pitch tmp_pitch, in_h rows, `planes`
+// planes of tmp_floats() each) at `tmp`; box = 32 columns x rows x 1.
+static bool make_blur_tmap_v(BlurPlan* pl, const float* tmp, int planes);
 
 // ---------------------------------------------------------------------------------------------
 // Device slabs: one cudaMalloc per context, sub-allocated; released slabs are cached per device so
@@ -417,7 +448,10 @@ void run_blur(gzb_ctx* c, const BlurPlan& pl, const float* in, size_t in_stride,
   else if (g.ups == 1) KLAUNCH_S(c, st, KC_BLUR_H, k_blur_h<1><<<gh, blk, 0, st>>>(in, in_stride, g, pl.d_sx, tmp, tstride, mh));
   else KLAUNCH_S(c, st, KC_BLUR_H, k_blur_h<3><<<gh, blk, 0, st>>>(in, in_stride, g, pl.d_sx, tmp, tstride, mh));
   dim3 gv((g.nx + 31) / 32, (g.ny + g.oyn - 1) / g.oyn, planes);
-  KLAUNCH_S(c, st, KC_BLUR_V, k_blur_v<<<gv, blk, 0, st>>>(tmp, tstride, g, pl.d_sy, out, out_stride, out_pitch, mv));
+  if (pl.has_tmap_v && pl.tmap_v_base == tmp)
+    KLAUNCH_S(c, st, KC_BLUR_V, k_blur_v_tma<<<gv, blk, 0, st>>>(pl.tmap_v, g, pl.box_rows, pl.d_sy, out, out_stride, out_pitch, mv));
+  else
+    KLAUNCH_S(c, st, KC_BLUR_V, k_blur_v<<<gv, blk, 0, st>>>(tmp, tstride, g, pl.d_sy, out, out_stride, out_pitch, mv));
 }
 
 // Block geometry of component k's coefficient array in the context's current sampling mode.
@@ -697,6 +731,11 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     const size_t lf_need = (6 * c->p_lf.tmp_floats() + 63) & ~size_t(63);
     c->concurrent = lf_need + main_need <= 6 * c->ps;
     c->tmp_main_off = c->concurrent ? lf_need : 0;
+    // TMA descriptors for the V passes: their input is the H-pass scratch, whose place is now known
+    make_blur_tmap_v(&c->p_lf, c->d_tmp, 6);
+    for (int k = 0; k < 3; ++k) make_blur_tmap_v(&c->p_mk[k], c->d_tmp + c->tmp_main_off, 1);
+    make_blur_tmap_v(&c->p_mkb2, c->d_tmp + c->tmp_main_off, 1);
+    make_blur_tmap_v(&c->p_dm, c->d_tmp + c->tmp_main_off, 1);
     CK(cudaStreamSynchronize(c->stream));
     return c;
   } catch (const std::string& e) {

@@ -585,6 +585,62 @@ k_blur_v(const float* __restrict__ tmp, size_t tmp_stride, BlurGeom g,
   }
 }
 
+// The V pass with its (rows x 32 columns) tile of the H-pass scratch brought in by TMA: box = 32 x rows x 1 at
+// (ox0, ys, plane); ox0 is a multiple of 32 (16-byte rule), rows above / below the plane and columns >= nx
+// are zero filled like the scalar loader's bounds checks. Dense 32-float rows in shared memory (a warp reads
+// 32 consecutive columns of one row: conflict-free without padding).
+__global__ void __launch_bounds__(256)
+k_blur_v_tma(const __grid_constant__ CUtensorMap tmap, BlurGeom g, int box_rows,
+             const double* __restrict__ scale_y, float* __restrict__ out, size_t out_stride, int out_pitch, DirtyMask dm) {
+  __shared__ __align__(128) float s[kBvMaxRows * 32];
+  __shared__ __align__(8) unsigned long long mbar;
+  out += blockIdx.z * out_stride;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * g.oyn;
+  if (!dirty_any(dm, g.x0 + ox0 * g.sx, g.y0 + oy0 * g.sy, g.x0 + (ox0 + 31) * g.sx, g.y0 + (oy0 + g.oyn - 1) * g.sy)) return;
+  const int ys = g.y0 + oy0 * g.sy - g.r;
+  const unsigned mbar_addr = static_cast<unsigned>(__cvta_generic_to_shared(&mbar));
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned bytes = static_cast<unsigned>(box_rows) * 32 * sizeof(float);
+    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(s));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_addr), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(mbar_addr), "r"(ox0), "r"(ys),
+          "r"(static_cast<int>(blockIdx.z))
+        : "memory");
+  }
+  {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(mbar_addr) : "memory");
+    }
+  }
+  const int ox = ox0 + threadIdx.x;
+  if (ox >= g.nx) return;
+  const float* taps = c_taps[g.kind];
+  const int nt = 2 * g.r + 1;
+#pragma unroll
+  for (int rr = 0; rr < kBvOy; rr += 8) {
+    const int loy = threadIdx.y + rr, oy = oy0 + loy;
+    if (oy >= g.ny || loy >= g.oyn) break;
+    if (!dirty_at(dm, g.x0 + ox * g.sx, g.y0 + oy * g.sy)) continue;
+    double acc = 0.0;
+    const int base = loy * g.sy;
+    for (int k = 0; k < nt; ++k) acc += static_cast<double>(s[(base + k) * 32 + threadIdx.x] * taps[k]);
+    out[static_cast<size_t>(oy) * out_pitch + ox] = static_cast<float>(acc * scale_y[oy]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K4b: both passes of a small-radius (r <= 3, step 1) blur fused, for the six planes EdgeDetectorMap
 // blurs (three channels with their own sigma, two images; butteraugli.cc:1124-1133): one launch
