@@ -26,31 +26,14 @@ static inline int bit_length(uint32_t n) { return n == 0 ? 0 : log2_floor_nz(n) 
 // Huffman depths: package-free two-queue construction with a rising count floor until the tree
 // fits `limit` bits (entropy_encode.cc:68-143). Ties: equal counts order by descending symbol.
 // ---------------------------------------------------------------------------------------------
-namespace {
-struct Node { uint32_t count; int16_t left; int16_t right_or_value; };
-
-bool assign_depths(int root, const Node* pool, uint8_t* depth, int max_depth) {
-  int stack[17];
-  int level = 0, p = root;
-  stack[0] = -1;
-  for (;;) {
-    if (pool[p].left >= 0) {
-      if (++level > max_depth) return false;
-      stack[level] = pool[p].right_or_value;
-      p = pool[p].left;
-      continue;
-    }
-    depth[pool[p].right_or_value] = static_cast<uint8_t>(level);
-    while (level >= 0 && stack[level] == -1) --level;
-    if (level < 0) return true;
-    p = stack[level];
-    stack[level] = -1;
-  }
-}
-}  // namespace
-
 void huffman_depths(const uint32_t* counts, int length, int limit, uint8_t* depth, HuffCache* cache) {
-  Node tree[2 * Histogram::kSize + 1];
+  // Node k: leaves [0, n), a sentinel at n, parents [n + 1, 2n), as parallel arrays. An attempt
+  // tracks node heights while it merges, so one that cannot fit `limit` bits stops at the first
+  // node that is too high and never walks its tree.
+  constexpr int kMaxNodes = 2 * Histogram::kSize + 2;
+  uint32_t cnt[kMaxNodes];
+  int16_t lhs[kMaxNodes], rhs[kMaxNodes], sym[Histogram::kSize];
+  uint16_t level[kMaxNodes], height[kMaxNodes];
   // Leaves ordered by (count ascending, symbol descending): a strict total order, so any sorting
   // algorithm gives the reference's arrangement. One 64-bit key per leaf: count << 16 | (0xffff - symbol).
   uint64_t keys[Histogram::kSize];
@@ -58,14 +41,18 @@ void huffman_depths(const uint32_t* counts, int length, int limit, uint8_t* dept
   if (cache && cache->n > 0) {
     // start from the previous call's order (the histogram moved by a few counts): insertion sort
     // is then close to linear
-    bool seen[Histogram::kSize] = {false};
+    int nonzero = 0;
+    for (int i = 0; i < length; ++i) nonzero += counts[i] != 0;
     for (int k = 0; k < cache->n; ++k) {
       const int i = cache->order[k];
-      seen[i] = true;
       if (i < length && counts[i]) keys[n++] = (static_cast<uint64_t>(counts[i]) << 16) | static_cast<uint64_t>(0xffff - i);
     }
-    for (int i = length; i-- > 0;)
-      if (counts[i] && !seen[i]) keys[n++] = (static_cast<uint64_t>(counts[i]) << 16) | static_cast<uint64_t>(0xffff - i);
+    if (n != nonzero) {  // symbols the previous histogram did not have
+      bool seen[Histogram::kSize] = {false};
+      for (int k = 0; k < cache->n; ++k) seen[cache->order[k]] = true;
+      for (int i = length; i-- > 0;)
+        if (counts[i] && !seen[i]) keys[n++] = (static_cast<uint64_t>(counts[i]) << 16) | static_cast<uint64_t>(0xffff - i);
+    }
     for (int k = 1; k < n; ++k) {
       const uint64_t v = keys[k];
       int j = k - 1;
@@ -77,46 +64,59 @@ void huffman_depths(const uint32_t* counts, int length, int limit, uint8_t* dept
       if (counts[i]) keys[n++] = (static_cast<uint64_t>(counts[i]) << 16) | static_cast<uint64_t>(0xffff - i);
     if (n > 1) std::sort(keys, keys + n);
   }
+  if (n == 0) return;
+  for (int k = 0; k < n; ++k) {
+    cnt[k] = static_cast<uint32_t>(keys[k] >> 16);
+    sym[k] = static_cast<int16_t>(0xffff - static_cast<int>(keys[k] & 0xffff));
+  }
   if (cache) {
     cache->n = n;
-    for (int k = 0; k < n; ++k) cache->order[k] = static_cast<int16_t>(0xffff - static_cast<int>(keys[k] & 0xffff));
+    memcpy(cache->order, sym, n * sizeof(int16_t));
   }
   if (n == 1) {
-    depth[0xffff - static_cast<int>(keys[0] & 0xffff)] = 1;
+    depth[sym[0]] = 1;
     return;
   }
   // Attempts with a rising count floor until the tree fits `limit` bits. Raising the floor only
   // changes the leading leaves (count <= floor): they all tie at the floor and must then order by
   // descending symbol; the tail keeps its order. So each attempt re-sorts just that prefix.
-  int16_t pref[Histogram::kSize];
+  for (int k = 0; k < n; ++k) height[k] = 0;
   int P = 0;  // leaves [0, P) have count <= floor_count
   for (uint32_t floor_count = 1;; floor_count *= 2) {
     if (floor_count > 1) {
       const int P0 = P;
-      while (P < n && static_cast<uint32_t>(keys[P] >> 16) <= floor_count) {
-        pref[P] = static_cast<int16_t>(0xffff - static_cast<int>(keys[P] & 0xffff));
-        ++P;
-      }
-      if (P > P0 || P0 == 0) std::sort(pref, pref + P, [](int16_t x, int16_t y) { return x > y; });
-      for (int k = 0; k < P; ++k) tree[k] = Node{floor_count, -1, pref[k]};
+      while (P < n && cnt[P] <= floor_count) ++P;
+      if (P > P0) std::sort(sym, sym + P, [](int16_t x, int16_t y) { return x > y; });
+      for (int k = 0; k < P; ++k) cnt[k] = floor_count;
     }
-    for (int k = P; k < n; ++k)
-      tree[k] = Node{static_cast<uint32_t>(keys[k] >> 16), -1, static_cast<int16_t>(0xffff - static_cast<int>(keys[k] & 0xffff))};
-    const Node sentinel{~0u, -1, -1};
-    tree[n] = sentinel;
-    tree[n + 1] = sentinel;
+    cnt[n] = ~0u;
+    cnt[n + 1] = ~0u;
     int i = 0, j = n + 1;
-    for (int k = n - 1; k != 0; --k) {
+    bool fits = true;
+    for (int parent = n + 1; parent < 2 * n; ++parent) {
       int left, right;
-      if (tree[i].count <= tree[j].count) left = i++; else left = j++;
-      if (tree[i].count <= tree[j].count) right = i++; else right = j++;
-      const int parent = 2 * n - k;
-      tree[parent].count = tree[left].count + tree[right].count;
-      tree[parent].left = static_cast<int16_t>(left);
-      tree[parent].right_or_value = static_cast<int16_t>(right);
-      tree[parent + 1] = sentinel;
+      if (cnt[i] <= cnt[j]) left = i++; else left = j++;
+      if (cnt[i] <= cnt[j]) right = i++; else right = j++;
+      cnt[parent] = cnt[left] + cnt[right];
+      lhs[parent] = static_cast<int16_t>(left);
+      rhs[parent] = static_cast<int16_t>(right);
+      // height above the leaves: the root's is the longest code of this attempt
+      const uint16_t hl = height[left], hr = height[right];
+      const int hp = (hl > hr ? hl : hr) + 1;
+      if (hp > limit) { fits = false; break; }  // the root can only be higher
+      height[parent] = static_cast<uint16_t>(hp);
+      cnt[parent + 1] = ~0u;
     }
-    if (assign_depths(2 * n - 1, tree, depth, limit)) return;
+    if (!fits) continue;
+    // Children always precede their parent, so one downward sweep gives every node's level.
+    level[2 * n - 1] = 0;
+    for (int p = 2 * n - 1; p > n; --p) {
+      const uint16_t d = static_cast<uint16_t>(level[p] + 1);
+      level[lhs[p]] = d;
+      level[rhs[p]] = d;
+    }
+    for (int k = 0; k < n; ++k) depth[sym[k]] = static_cast<uint8_t>(level[k]);
+    return;
   }
 }
 
