@@ -71,7 +71,7 @@ void huffman_depths(const uint32_t* counts, int length, int limit, uint8_t* dept
   }
   if (cache) {
     cache->n = n;
-    memcpy(cache->order, sym, n * sizeof(int16_t));
+    std::copy(sym, sym + n, cache->order);
   }
   if (n == 1) {
     depth[sym[0]] = 1;

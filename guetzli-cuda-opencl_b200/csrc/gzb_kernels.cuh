@@ -540,9 +540,40 @@ k_blur_h_tma(const __grid_constant__ CUtensorMap tmap, BlurGeom g, int box_w,
     const int ly = threadIdx.y + rr, gy = yb + ly;
     if (gy >= g.in_h) break;
     if (!dirty_at(dm, g.x0 + ox * g.sx, gy)) continue;
-    const float* p = &s[ly * box_w + (xs - xa) + threadIdx.x * g.sx];
     double acc = 0.0;
-    for (int k = 0; k < nt; ++k) acc += static_cast<double>(p[k] * taps[k]);
+    if (g.sx == 4) {
+      // Outputs four pixels apart: scalar reads would put the 32 lanes on 8 banks (4-way conflict, the
+      // shared pipe was the limiter of the sigma-14 passes). Each lane instead streams 16-byte chunks from
+      // its own 16-byte aligned position (box_w and 4 * lane are multiples of four floats): a warp reads
+      // 512 contiguous bytes per instruction. Stream element j is tap j - off; same order of additions.
+      const float4* q = reinterpret_cast<const float4*>(&s[ly * box_w + 4 * threadIdx.x]);
+      const int off = xs - xa;   // 0..3, the same for the whole CTA
+      int k = 0, m = 0;
+      if (off) {
+        const float4 v = q[m++];
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 1; t < 4; ++t)
+          if (t >= off) acc += static_cast<double>(e[t] * taps[k++]);
+      }
+      for (; k + 4 <= nt; k += 4) {
+        const float4 v = q[m++];
+        acc += static_cast<double>(v.x * taps[k]);
+        acc += static_cast<double>(v.y * taps[k + 1]);
+        acc += static_cast<double>(v.z * taps[k + 2]);
+        acc += static_cast<double>(v.w * taps[k + 3]);
+      }
+      if (k < nt) {
+        const float4 v = q[m];
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          if (k + t < nt) acc += static_cast<double>(e[t] * taps[k + t]);
+      }
+    } else {
+      const float* p = &s[ly * box_w + (xs - xa) + threadIdx.x * g.sx];
+      for (int k = 0; k < nt; ++k) acc += static_cast<double>(p[k] * taps[k]);
+    }
     tmp[static_cast<size_t>(gy) * g.tmp_pitch + ox] = static_cast<float>(acc * sc);
   }
 }
