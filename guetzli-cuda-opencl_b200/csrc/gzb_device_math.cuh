@@ -321,14 +321,18 @@ __device__ __forceinline__ void warp_block_diff(const float* fa, const float* fb
     }
   }
   __syncwarp();
-  // (4) column transforms: 20 tasks = plane*5 + u; power into pl[plane*72 + 8u + v].
+  // (4) column transforms: 20 tasks = plane*5 + u; power into pl[plane*72 + 8u + (v ^ u)]: the row of
+  // eight is XOR-swizzled by u, otherwise the 20 lanes (plane strides of 72, rows of 8 doubles) store
+  // bin v into only two bank pairs.
   // Columns u = 0 and u = 4 of a real input are themselves real (their stored imaginary parts are
   // exactly 0.0); running them through the complex transform gives the same bits as the reference's
   // real transform up to the sign of zeros (x - 0 = x, 0 - x = -x, (-x - y) = -(x + y) are exact), and
   // only re^2 + im^2 is used. One code path for all 20 lanes instead of two divergent ones. Bins the
   // reference does not compute (u = 0: v < 4; u = 4: v > 4) land in slots nobody reads.
-  if (lane < 20) {
-    const int plane = lane / 5, u = lane - 5 * plane;
+  // Tasks of planes 0, 1 run on lanes 0..9 and those of planes 2, 3 on lanes 16..25: a 64-bit access is
+  // served per half-warp, and planes p and p + 2 sit an even number of 128-byte lines apart (same banks).
+  if ((lane & 15) < 10) {
+    const int hl = lane & 15, plane = 2 * (lane >> 4) + (hl >= 5 ? 1 : 0), u = hl >= 5 ? hl - 5 : hl;
     const double* cre = sre + plane * kBdSpec + 9 * u;
     const double* cim = sim + plane * kBdSpec + 9 * u;
     double* dst = pl + kBdPlane * plane + 8 * u;
@@ -337,16 +341,17 @@ __device__ __forceinline__ void warp_block_diff(const float* fa, const float* fb
     for (int k = 0; k < 8; ++k) { re[k] = cre[k]; im[k] = cim[k]; }
     cfft8(re, im);
 #pragma unroll
-    for (int v = 0; v < 8; ++v) dst[v] = (re[v] * re[v] + im[v] * im[v]) * 0.000064;
+    for (int v = 0; v < 8; ++v) dst[v ^ u] = (re[v] * re[v] + im[v] * im[v]) * 0.000064;
   }
   __syncwarp();
   // (5) per-frequency terms i = 4..36 (lane L -> i = 4+L; lane 0 also i = 36), then in-order sums.
   double* term = sre;  // [3][33]
   for (int i = 4 + lane; i < 37; i += 32) {
     const double d = i == 36 ? csf_b : csf_a;
-    term[i - 4] = d * 64.8 * pl[kBdPlane + i];
-    term[66 + i - 4] = d * 2.4 * pl[3 * kBdPlane + i];
-    const double ya = sqrt(pl[i]), yh = sqrt(pl[2 * kBdPlane + i]);
+    const int pi = i ^ (i >> 3);   // bin i = 8u + v sits at 8u + (v ^ u), u <= 4
+    term[i - 4] = d * 64.8 * pl[kBdPlane + pi];
+    term[66 + i - 4] = d * 2.4 * pl[3 * kBdPlane + pi];
+    const double ya = sqrt(pl[pi]), yh = sqrt(pl[2 * kBdPlane + pi]);
     const double y0 = remove_range_around_zero(ya - yh, 0.04);
     const double y1 = remove_range_around_zero(ya + yh, 0.04);
     double ty = 0.0;
