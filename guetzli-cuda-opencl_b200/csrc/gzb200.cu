@@ -15,6 +15,7 @@
 #include "gzb_zeroing.cuh"
 #include "gzb_huffman.cuh"
 #include "gzb_yuv420.cuh"
+#include "gzb_backend.cuh"
 
 namespace gzb {
 
@@ -247,8 +248,18 @@ static bool make_blur_tmap_v(BlurPlan* pl, const float* tmp, int planes);
 // that back-to-back encodes do not pay the driver's map/unmap cost (the reference's cumem_pool
 // plays this role, clguetzli/cumem_pool.cpp:28-112).
 // ---------------------------------------------------------------------------------------------
-struct Slab { void* base = nullptr; size_t cap = 0; void* pinned = nullptr; void* pinned2 = nullptr; size_t pinned2_cap = 0; };
-static void slab_free(Slab& s) { cudaFree(s.base); cudaFreeHost(s.pinned); if (s.pinned2) cudaFreeHost(s.pinned2); s = Slab(); }
+struct Slab {
+  void* base = nullptr; size_t cap = 0; void* pinned = nullptr; void* pinned2 = nullptr; size_t pinned2_cap = 0;
+  void* be = nullptr; size_t be_cap = 0;            // back-end arrays (gzb_backend.cuh), sized by the candidate count
+  void* be_pinned = nullptr; size_t be_pinned_cap = 0;
+};
+static void slab_free(Slab& s) {
+  cudaFree(s.base); cudaFreeHost(s.pinned);
+  if (s.pinned2) cudaFreeHost(s.pinned2);
+  if (s.be) cudaFree(s.be);
+  if (s.be_pinned) cudaFreeHost(s.be_pinned);
+  s = Slab();
+}
 static std::mutex g_slab_mu;
 static std::vector<Slab> g_slab_cache[64];
 
@@ -391,6 +402,25 @@ struct gzb_ctx {
   bool changed_overflow = false;     // too many changes since the last Compare to track
   std::vector<int4> changed;         // pixel rectangles (x0, y0, x1, y1) whose samples changed since the last Compare
   unsigned long long incremental_compares = 0;
+
+  // ---- SelectFrequencyBackEnd on the device (gzb_backend.cuh); pointers into slab.be ----
+  struct Backend {
+    bool active = false;
+    int comp_mask = 0, factor = 1, num_blocks = 0, total = 0;
+    BeGeom geom{};
+    BeState* st = nullptr;
+    BeEntry* small = nullptr;          // directly behind *st: one copy brings both to the host
+    int* cand_off = nullptr; uint8_t* cand_idx = nullptr; float* cand_err = nullptr;
+    int* last_index = nullptr; float* max_err = nullptr;
+    int* counts = nullptr; int* offsets = nullptr; unsigned* pcount = nullptr;
+    BeEntry* order = nullptr; unsigned* lpos = nullptr; unsigned* rpos = nullptr; unsigned* tcl = nullptr; unsigned* tcr = nullptr;
+    int* req_blocks = nullptr; BeBlockState* req_out = nullptr;
+    unsigned int* hist = nullptr;      // [48 + 768]
+    unsigned* flag = nullptr;
+    int select_grid = 0;
+    unsigned long long n = 0;          // entries of the current order
+    unsigned long long selects = 0, levels = 0, host_ranges = 0;
+  } be;
 };
 
 enum DirtyStage { DS_OPS = 0, DS_MHIC, DS_EB, DS_EDM, DS_BDM, DS_LFH, DS_LFV, DS_LOW, DS_MKH0, DS_MKV0, DS_MKH1, DS_MKV1,
@@ -1236,6 +1266,14 @@ static int zeroing_units(const gzb_ctx* c, int comp_mask) {
   return (c->mode420 && (comp_mask & 6)) ? c->mcw * c->mch : c->nblocks;
 }
 
+// Where gzb_compute_block_zeroing_candidates_range packs its lists: d_tmp (6 planes of scratch).
+static void packed_ptrs(gzb_ctx* c, int** d_counts, int** d_offsets, float** d_err, uint8_t** d_idx) {
+  *d_counts = reinterpret_cast<int*>(c->d_tmp);
+  *d_offsets = *d_counts + c->nblocks + 32;
+  *d_err = reinterpret_cast<float*>(*d_offsets + c->nblocks + 32);
+  *d_idx = reinterpret_cast<uint8_t*>(*d_err + static_cast<size_t>(192) * c->nblocks);
+}
+
 static int run_zeroing(gzb_ctx* c, int comp_mask, int mode, int b0 = 0, int b1 = -1) {
   const size_t cs = c->cs;
   const bool mb = c->mode420 && (comp_mask & 6);
@@ -1386,10 +1424,8 @@ int gzb_compute_block_zeroing_candidates_range(gzb_ctx* c, int comp_mask, int bl
   const int nloc = block_end - block_begin;
   if (nloc == 0) { offsets[0] = 0; *n_out = 0; return GZB_OK; }
   // d_tmp (6 planes of scratch) holds counts | offsets | packed err | packed idx
-  int* d_counts = reinterpret_cast<int*>(c->d_tmp);
-  int* d_offsets = d_counts + c->nblocks + 32;
-  float* d_err = reinterpret_cast<float*>(d_offsets + c->nblocks + 32);
-  uint8_t* d_idx = reinterpret_cast<uint8_t*>(d_err + static_cast<size_t>(192) * c->nblocks);
+  int* d_counts; int* d_offsets; float* d_err; uint8_t* d_idx;
+  packed_ptrs(c, &d_counts, &d_offsets, &d_err, &d_idx);
   if (!(c->packed_valid && c->packed_mask == comp_mask && c->packed_b0 == block_begin && c->packed_b1 == block_end)) {
     run_zeroing(c, comp_mask, 0, block_begin, block_end);  // a repeated call only re-fetches
     const CoeffRec* recs = reinterpret_cast<const CoeffRec*>(c->d_order) + static_cast<size_t>(block_begin) * 192;
@@ -1407,9 +1443,9 @@ int gzb_compute_block_zeroing_candidates_range(gzb_ctx* c, int comp_mask, int bl
   CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   const size_t n = static_cast<size_t>(offsets[nloc]);
   *n_out = n;
-  if (n > 0 && cand_idx && cand_err && cap >= n) {
+  if (n > 0 && cand_idx && cap >= n) {   // cand_err == NULL: the errors stay on the device (gzb_be_begin)
     CK(cudaMemcpyAsync(cand_idx, d_idx, n, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += n;
-    CK(cudaMemcpyAsync(cand_err, d_err, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += n * sizeof(float);
+    if (cand_err) { CK(cudaMemcpyAsync(cand_err, d_err, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += n * sizeof(float); }
     sync_check(c);
   }
   GZB_END(c)
@@ -1472,11 +1508,12 @@ int gzb_candidate_symbol_histograms_n(gzb_ctx* c, const int* q192, int ncomp, ui
   if (ncomp != 1 && ncomp != 3) return fail(c, GZB_ERR_BAD_ARG, "gzb_candidate_symbol_histograms: ncomp must be 1 or 3");
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_candidate_symbol_histograms: no candidate coefficients");
   if (!dc_hist48 || !ac_hist768) return fail(c, GZB_ERR_BAD_ARG, "gzb_candidate_symbol_histograms: null argument");
+  // the candidate may still be rendering on the main stream (render_candidate reads d_q too): wait first
+  CK(cudaStreamWaitEvent(c->stream2, c->ev_cand, 0));
   if (q192) { CK(cudaMemcpyAsync(c->d_q, q192, 192 * sizeof(int), cudaMemcpyHostToDevice, c->stream2)); c->h2d_bytes += 192 * sizeof(int); }
   const HuffScratch h = huff_scratch(c);
   long long nunits = 0;
   const HuffLayout L = huff_layout(c, ncomp, &nunits);
-  CK(cudaStreamWaitEvent(c->stream2, c->ev_cand, 0));   // the candidate may still be rendering on the main stream
   CK(cudaMemsetAsync(h.hist, 0, (48 + 768) * 4, c->stream2));
   KLAUNCH_S(c, c->stream2, KC_HUFFMAN, k_huff_histogram<<<static_cast<unsigned>((nunits + kHuffThreads - 1) / kHuffThreads), kHuffThreads, 0, c->stream2>>>(
       c->d_coef, c->cs, c->d_q, L, nunits, h.hist, h.hist + 48));
@@ -1565,6 +1602,17 @@ int gzb_dct_double(int device, double* blocks, size_t nblocks, int inverse) {
   return GZB_OK;
 }
 
+// ComputeBlockErrorAdjustmentWeights (butteraugli_comparator.cc:160-222) into c->d_weight; returns the block count.
+static int launch_block_weights(gzb_ctx* c, const float* dm, int direction, int max_block_dist, double target_mul, int factor) {
+  const double target = static_cast<double>(c->target) * target_mul;
+  const int bs = 8 * factor, pbw = (c->W + bs - 1) / bs, pbh = (c->H + bs - 1) / bs, nb = pbw * pbh;
+  const int g = (nb + 255) / 256;
+  KLAUNCH(c, KC_WEIGHTS, k_block_max<<<g, 256, 0, c->stream>>>(dm, c->P, c->W, c->H, pbw, pbh, bs, c->d_bmax));
+  KLAUNCH(c, KC_WEIGHTS, k_block_flags<<<g, 256, 0, c->stream>>>(c->d_bmax, pbw, pbh, direction, max_block_dist, target, c->d_flags));
+  KLAUNCH(c, KC_WEIGHTS, k_block_weights<<<g, 256, 0, c->stream>>>(c->d_flags, pbw, pbh, direction, max_block_dist, c->d_weight));
+  return nb;
+}
+
 int gzb_compute_block_error_adjustment_weights_f(gzb_ctx* c, int direction, int max_block_dist, double target_mul,
                                                  int factor, const float* distmap, float* block_weight) {
   GZB_TRY(c)
@@ -1578,12 +1626,7 @@ int gzb_compute_block_error_adjustment_weights_f(gzb_ctx* c, int direction, int 
   } else if (!c->have_distmap) {
     return fail(c, GZB_ERR_STATE, "gzb_compute_block_error_adjustment_weights: no distance map");
   }
-  const double target = static_cast<double>(c->target) * target_mul;
-  const int bs = 8 * factor, pbw = (c->W + bs - 1) / bs, pbh = (c->H + bs - 1) / bs, nb = pbw * pbh;
-  const int g = (nb + 255) / 256;
-  KLAUNCH(c, KC_WEIGHTS, k_block_max<<<g, 256, 0, c->stream>>>(dm, c->P, c->W, c->H, pbw, pbh, bs, c->d_bmax));
-  KLAUNCH(c, KC_WEIGHTS, k_block_flags<<<g, 256, 0, c->stream>>>(c->d_bmax, pbw, pbh, direction, max_block_dist, target, c->d_flags));
-  KLAUNCH(c, KC_WEIGHTS, k_block_weights<<<g, 256, 0, c->stream>>>(c->d_flags, pbw, pbh, direction, max_block_dist, c->d_weight));
+  const int nb = launch_block_weights(c, dm, direction, max_block_dist, target_mul, factor);
   CK(cudaMemcpyAsync(block_weight, c->d_weight, sizeof(float) * nb, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (sizeof(float) * nb);
   sync_check(c);
   GZB_END(c)
@@ -1592,6 +1635,357 @@ int gzb_compute_block_error_adjustment_weights_f(gzb_ctx* c, int direction, int 
 int gzb_compute_block_error_adjustment_weights(gzb_ctx* c, int direction, int max_block_dist, double target_mul,
                                                const float* distmap, float* block_weight) {
   return gzb_compute_block_error_adjustment_weights_f(c, direction, max_block_dist, target_mul, 1, distmap, block_weight);
+}
+
+// ---- SelectFrequencyBackEnd on the device (gzb_backend.cuh) --------------------------------------
+namespace {
+const size_t kBePinState = 0;                      // BeState + small entries
+const size_t kBePinHist = 64 << 10;                // 816 counters + scalars
+const size_t kBePinGather = 72 << 10;              // gathered block states
+const size_t kBePinBytes = kBePinGather + sizeof(BeBlockState) * kBeSmallMax;
+
+// (Re)allocates the back-end arrays for num_blocks units and `total` candidates / order entries.
+void be_reserve(gzb_ctx* c, int num_blocks, size_t total) {
+  gzb_ctx::Backend& B = c->be;
+  const size_t nb = static_cast<size_t>(num_blocks), T = std::max<size_t>(total, 1);
+  const size_t ntiles = T / kBeTile + 2;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) & ~size_t(255); return at; };
+  const size_t o_state = take(sizeof(BeState) + sizeof(BeEntry) * kBeSmallMax);
+  const size_t o_hist = take((48 + 768 + 8) * 4);
+  const size_t o_off = take((nb + 1) * 4), o_li = take(nb * 4), o_me = take(nb * 4), o_cnt = take(nb * 4);
+  const size_t o_offs = take((nb + 1) * 4), o_pc = take(nb * 4);
+  const size_t o_req = take(kBeSmallMax * 4), o_out = take(sizeof(BeBlockState) * kBeSmallMax);
+  const size_t o_tcl = take(ntiles * 4), o_tcr = take(ntiles * 4);
+  const size_t o_idx = take(T), o_err = take(T * 4), o_order = take(T * 8), o_lp = take(T * 4), o_rp = take(T * 4);
+  if (c->slab.be_cap < o) {
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->slab.be) cudaFree(c->slab.be);
+    c->slab.be = nullptr;
+    c->slab.be_cap = 0;
+    const size_t want = o + o / 4;   // headroom: the next image of a batch rarely has exactly as many candidates
+    CK(cudaMalloc(&c->slab.be, want));
+    c->slab.be_cap = want;
+  }
+  if (c->slab.be_pinned_cap < kBePinBytes) {
+    if (c->slab.be_pinned) cudaFreeHost(c->slab.be_pinned);
+    c->slab.be_pinned = nullptr;
+    c->slab.be_pinned_cap = 0;
+    CK(cudaMallocHost(&c->slab.be_pinned, kBePinBytes));
+    c->slab.be_pinned_cap = kBePinBytes;
+  }
+  char* base = static_cast<char*>(c->slab.be);
+  B.st = reinterpret_cast<BeState*>(base + o_state);
+  B.small = reinterpret_cast<BeEntry*>(base + o_state + sizeof(BeState));
+  B.hist = reinterpret_cast<unsigned int*>(base + o_hist);
+  B.flag = B.hist + 48 + 768;
+  B.cand_off = reinterpret_cast<int*>(base + o_off);
+  B.last_index = reinterpret_cast<int*>(base + o_li);
+  B.max_err = reinterpret_cast<float*>(base + o_me);
+  B.counts = reinterpret_cast<int*>(base + o_cnt);
+  B.offsets = reinterpret_cast<int*>(base + o_offs);
+  B.pcount = reinterpret_cast<unsigned*>(base + o_pc);
+  B.req_blocks = reinterpret_cast<int*>(base + o_req);
+  B.req_out = reinterpret_cast<BeBlockState*>(base + o_out);
+  B.tcl = reinterpret_cast<unsigned*>(base + o_tcl);
+  B.tcr = reinterpret_cast<unsigned*>(base + o_tcr);
+  B.cand_idx = reinterpret_cast<uint8_t*>(base + o_idx);
+  B.cand_err = reinterpret_cast<float*>(base + o_err);
+  B.order = reinterpret_cast<BeEntry*>(base + o_order);
+  B.lpos = reinterpret_cast<unsigned*>(base + o_lp);
+  B.rpos = reinterpret_cast<unsigned*>(base + o_rp);
+  if (B.select_grid == 0) {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_be_select, kBeThreads, 0));
+    static const int want = getenv("GZB_BE_CTAS_PER_SM") ? atoi(getenv("GZB_BE_CTAS_PER_SM")) : 2;
+    B.select_grid = c->sm_count * std::max(1, std::min(per_sm, want));
+  }
+}
+char* be_pinned(gzb_ctx* c) { return static_cast<char*>(c->slab.be_pinned); }
+BeCands be_cands(const gzb_ctx* c) { return BeCands{c->be.cand_off, c->be.cand_idx, c->be.cand_err, c->be.total}; }
+}  // namespace
+
+int gzb_be_begin(gzb_ctx* c, int comp_mask, const int* offsets, const uint8_t* cand_idx, const float* cand_err, size_t total) {
+  GZB_TRY(c)
+  if (!c->have_coeffs || !c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_be_begin: coefficients missing");
+  if (comp_mask < 1 || comp_mask > 7 || (c->mode420 && comp_mask != 1 && comp_mask != 6)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_begin: bad comp_mask");
+  if (total >= (size_t(1) << 31)) return fail(c, GZB_ERR_UNSUPPORTED, "gzb_be_begin: too many candidates");
+  gzb_ctx::Backend& B = c->be;
+  const int units = zeroing_units(c, comp_mask);
+  const bool resident = offsets == nullptr;
+  if (resident && !(c->packed_valid && c->packed_mask == comp_mask && c->packed_b0 == 0 && c->packed_b1 == units))
+    return fail(c, GZB_ERR_STATE, "gzb_be_begin: no resident candidate lists for this comp_mask");
+  if (!resident && total > 0 && (!cand_idx || !cand_err)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_begin: null candidate arrays");
+  be_reserve(c, units, total);
+  B.comp_mask = comp_mask;
+  B.factor = (c->mode420 && (comp_mask & 6)) ? 2 : 1;
+  B.num_blocks = units;
+  B.total = static_cast<int>(total);
+  const int bs = 8 * B.factor;
+  B.geom.num_blocks = units;
+  B.geom.pass_bw = (c->W + bs - 1) / bs;
+  B.geom.coef_bw = comp_bw(c, (comp_mask & 1) ? 0 : 1);
+  B.geom.cs = c->cs;
+  if (resident) {
+    int* d_counts; int* d_offsets; float* d_err; uint8_t* d_idx;
+    packed_ptrs(c, &d_counts, &d_offsets, &d_err, &d_idx);
+    CK(cudaMemcpyAsync(B.cand_off, d_offsets, (static_cast<size_t>(units) + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (total) {
+      CK(cudaMemcpyAsync(B.cand_idx, d_idx, total, cudaMemcpyDeviceToDevice, c->stream));
+      CK(cudaMemcpyAsync(B.cand_err, d_err, total * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+  } else {
+    if (offsets[units] != static_cast<int>(total)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_begin: offsets[num_blocks] != total");
+    CK(cudaMemcpyAsync(B.cand_off, offsets, (static_cast<size_t>(units) + 1) * 4, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (static_cast<size_t>(units) + 1) * 4;
+    if (total) {
+      CK(cudaMemcpyAsync(B.cand_idx, cand_idx, total, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += total;
+      CK(cudaMemcpyAsync(B.cand_err, cand_err, total * 4, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += total * 4;
+    }
+  }
+  CK(cudaMemsetAsync(B.st, 0, sizeof(BeState), c->stream));
+  CK(cudaMemsetAsync(B.last_index, 0, static_cast<size_t>(units) * 4, c->stream));
+  CK(cudaMemsetAsync(B.max_err, 0, static_cast<size_t>(units) * 4, c->stream));
+  CK(cudaMemsetAsync(B.pcount, 0, static_cast<size_t>(units) * 4, c->stream));
+  sync_check(c);   // the host arrays may be released by the caller
+  B.active = true;
+  B.n = 0;
+  GZB_END(c)
+}
+
+int gzb_be_build_order(gzb_ctx* c, int direction, double target_mul, float below_limit, uint64_t* n, int* blocks_to_change,
+                       uint64_t* below, int* rblock_out) {
+  GZB_TRY(c)
+  gzb_ctx::Backend& B = c->be;
+  if (!B.active) return fail(c, GZB_ERR_STATE, "gzb_be_build_order: gzb_be_begin not called");
+  if (!c->have_distmap) return fail(c, GZB_ERR_STATE, "gzb_be_build_order: no distance map");
+  if (!n || !blocks_to_change || !below || (direction != 1 && direction != -1)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_build_order: bad argument");
+  const int nb = B.num_blocks;
+  const BeCands cands = be_cands(c);
+  unsigned* hs = reinterpret_cast<unsigned*>(be_pinned(c) + kBePinState);
+  int rblock = 1;
+  for (; rblock <= 4; ++rblock) {
+    launch_block_weights(c, c->d_diffmap, direction, rblock, target_mul, B.factor);
+    CK(cudaMemsetAsync(B.st, 0, 16, c->stream));   // n, blocks_to_change, below, changed_blocks
+    KLAUNCH(c, KC_MISC, k_be_count<<<(nb + 255) / 256, 256, 0, c->stream>>>(cands, c->d_weight, B.last_index, nb, direction, B.counts, B.st));
+    KLAUNCH(c, KC_MISC, k_scan_counts<<<1, 1024, 0, c->stream>>>(B.counts, nb, B.offsets));
+    KLAUNCH(c, KC_MISC, k_be_set_n<<<1, 1, 0, c->stream>>>(B.offsets, nb, B.st));
+    KLAUNCH(c, KC_MISC, k_be_fill<<<(nb * 32 + 255) / 256, 256, 0, c->stream>>>(cands, c->d_weight, B.last_index, B.max_err, B.counts, B.offsets, nb,
+                                                                                direction, below_limit, B.order, B.st));
+    KLAUNCH(c, KC_MISC, k_be_sort_begin<<<1, 1, 0, c->stream>>>(B.st));
+    CK(cudaMemcpyAsync(hs, B.st, 16, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 16;
+    sync_check(c);
+    if (hs[0] > 0) break;
+  }
+  B.n = hs[0];
+  *n = hs[0];
+  *blocks_to_change = static_cast<int>(hs[1]);
+  *below = hs[2];
+  if (rblock_out) *rblock_out = std::min(rblock, 4);
+  c->packed_valid = false;
+  GZB_END(c)
+}
+
+int gzb_be_select(gzb_ctx* c, uint64_t p_set, int small_max, int* status, uint64_t* first, uint64_t* last, int* depth,
+                  gzb_order_entry* entries_out) {
+  GZB_TRY(c)
+  gzb_ctx::Backend& B = c->be;
+  if (!B.active) return fail(c, GZB_ERR_STATE, "gzb_be_select: gzb_be_begin not called");
+  if (!status || !first || !last || !depth || small_max < 16 || small_max > kBeSmallMax) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_select: bad argument");
+  KLAUNCH(c, KC_MISC, k_be_select_args<<<1, 1, 0, c->stream>>>(B.st, static_cast<unsigned>(std::min<uint64_t>(p_set, B.n)), static_cast<unsigned>(small_max)));
+  {
+    BeEntry* a = B.order; unsigned* lp = B.lpos; unsigned* rp = B.rpos; unsigned* tl = B.tcl; unsigned* tr = B.tcr;
+    BeState* st = B.st; BeEntry* sm = B.small;
+    void* args[] = {&a, &lp, &rp, &tl, &tr, &st, &sm};
+    KLAUNCH(c, KC_MISC, CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k_be_select), dim3(B.select_grid), dim3(kBeThreads), args, 0, c->stream)));
+  }
+  const size_t bytes = sizeof(BeState) + sizeof(BeEntry) * static_cast<size_t>(small_max);
+  BeState* hst = reinterpret_cast<BeState*>(be_pinned(c) + kBePinState);
+  CK(cudaMemcpyAsync(hst, B.st, bytes, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += bytes;
+  sync_check(c);
+  ++B.selects;
+  B.levels += hst->levels;
+  *status = hst->status;
+  if (hst->status == BE_EMPTY || hst->top <= 0) {
+    *status = BE_EMPTY;
+    *first = *last = B.n;
+    *depth = 0;
+  } else {
+    const BeRange r = hst->stack[hst->top - 1];
+    *first = r.first; *last = r.last; *depth = r.depth;
+    if (hst->status == BE_SMALL && entries_out)
+      memcpy(entries_out, reinterpret_cast<const char*>(hst) + sizeof(BeState), sizeof(BeEntry) * (r.last - r.first));
+  }
+  GZB_END(c)
+}
+
+int gzb_be_fetch_order(gzb_ctx* c, uint64_t first, gzb_order_entry* out, size_t n) {
+  GZB_TRY(c)
+  if (!c->be.active || !out || first + n > c->be.n) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_fetch_order: bad argument");
+  CK(cudaMemcpyAsync(out, c->be.order + first, n * 8, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += n * 8;
+  sync_check(c);
+  GZB_END(c)
+}
+
+int gzb_be_store_order(gzb_ctx* c, uint64_t first, const gzb_order_entry* in, size_t n) {
+  GZB_TRY(c)
+  if (!c->be.active || !in || first + n > c->be.n) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_store_order: bad argument");
+  CK(cudaMemcpyAsync(c->be.order + first, in, n * 8, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += n * 8;
+  sync_check(c);
+  GZB_END(c)
+}
+
+namespace {
+void be_launch_gather(gzb_ctx* c, const int* blocks, int nreq, int direction) {
+  gzb_ctx::Backend& B = c->be;
+  CK(cudaMemcpyAsync(B.req_blocks, blocks, static_cast<size_t>(nreq) * 4, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += static_cast<size_t>(nreq) * 4;
+  KLAUNCH(c, KC_MISC, k_be_gather<<<(nreq * 32 + 255) / 256, 256, 0, c->stream>>>(B.geom, B.req_blocks, nreq, c->d_coef, c->d_orig, c->d_q, B.last_index,
+                                                                                B.pcount, B.comp_mask, direction < 0 ? 1 : 0, B.req_out));
+  CK(cudaMemcpyAsync(be_pinned(c) + kBePinGather, B.req_out, sizeof(BeBlockState) * static_cast<size_t>(nreq), cudaMemcpyDeviceToHost, c->stream));
+  c->d2h_bytes += sizeof(BeBlockState) * static_cast<size_t>(nreq);
+}
+}  // namespace
+
+int gzb_be_apply_prefix(gzb_ctx* c, uint64_t p, int direction, int hist_ncomp, uint32_t* ac_hist768, int* changed_blocks,
+                        const int* blocks, int nreq, gzb_be_block_state* states_out) {
+  GZB_TRY(c)
+  static_assert(sizeof(gzb_be_block_state) == sizeof(BeBlockState), "gzb_be_block_state layout");
+  gzb_ctx::Backend& B = c->be;
+  if (!B.active) return fail(c, GZB_ERR_STATE, "gzb_be_apply_prefix: gzb_be_begin not called");
+  if (p > B.n || nreq < 0 || nreq > kBeSmallMax || (nreq > 0 && (!blocks || !states_out)) || (hist_ncomp != 1 && hist_ncomp != 3))
+    return fail(c, GZB_ERR_BAD_ARG, "gzb_be_apply_prefix: bad argument");
+  for (int i = 0; i < nreq; ++i) if (blocks[i] < 0 || blocks[i] >= B.num_blocks) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_apply_prefix: block out of range");
+  unsigned* hh = reinterpret_cast<unsigned*>(be_pinned(c) + kBePinHist);
+  CK(cudaMemsetAsync(&B.st->changed_blocks, 0, 4, c->stream));
+  if (p > 0) {
+    const unsigned pp = static_cast<unsigned>(p);
+    KLAUNCH(c, KC_MISC, k_be_prefix_count<<<(pp + 255) / 256, 256, 0, c->stream>>>(B.order, pp, B.pcount));
+    KLAUNCH(c, KC_MISC, k_be_apply_prefix<<<(B.num_blocks + 255) / 256, 256, 0, c->stream>>>(be_cands(c), B.geom, B.pcount, direction, c->d_orig, c->d_q,
+                                                                                            c->d_coef, B.last_index, B.st));
+    // the samples of most blocks change: the next Compare is a full one
+    c->changed_overflow = true;
+    c->changed.clear();
+  }
+  if (ac_hist768) {
+    long long nunits = 0;
+    const HuffLayout L = huff_layout(c, hist_ncomp, &nunits);
+    CK(cudaMemsetAsync(B.hist, 0, (48 + 768) * 4, c->stream));
+    KLAUNCH(c, KC_HUFFMAN, k_huff_histogram<<<static_cast<unsigned>((nunits + kHuffThreads - 1) / kHuffThreads), kHuffThreads, 0, c->stream>>>(
+        c->d_coef, c->cs, c->d_q, L, nunits, B.hist, B.hist + 48));
+    CK(cudaMemcpyAsync(hh, B.hist, (48 + 768) * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (48 + 768) * 4;
+  }
+  CK(cudaMemcpyAsync(hh + 48 + 768, &B.st->changed_blocks, 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 4;
+  if (nreq > 0) be_launch_gather(c, blocks, nreq, direction);
+  sync_check(c);
+  if (ac_hist768) memcpy(ac_hist768, hh + 48, 768 * 4);
+  if (changed_blocks) *changed_blocks = static_cast<int>(hh[48 + 768]);
+  if (nreq > 0) memcpy(states_out, be_pinned(c) + kBePinGather, sizeof(BeBlockState) * static_cast<size_t>(nreq));
+  GZB_END(c)
+}
+
+int gzb_be_gather(gzb_ctx* c, const int* blocks, int nreq, int direction, gzb_be_block_state* states_out) {
+  GZB_TRY(c)
+  gzb_ctx::Backend& B = c->be;
+  if (!B.active) return fail(c, GZB_ERR_STATE, "gzb_be_gather: gzb_be_begin not called");
+  if (nreq < 0 || nreq > kBeSmallMax || (nreq > 0 && (!blocks || !states_out))) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_gather: bad argument");
+  for (int i = 0; i < nreq; ++i) if (blocks[i] < 0 || blocks[i] >= B.num_blocks) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_gather: block out of range");
+  if (nreq == 0) return GZB_OK;
+  be_launch_gather(c, blocks, nreq, direction);
+  sync_check(c);
+  memcpy(states_out, be_pinned(c) + kBePinGather, sizeof(BeBlockState) * static_cast<size_t>(nreq));
+  GZB_END(c)
+}
+
+int gzb_be_finish_iteration(gzb_ctx* c, const int32_t* blocks, const uint8_t* cidx, const int16_t* val, size_t n, int direction,
+                            float val_threshold) {
+  GZB_TRY(c)
+  gzb_ctx::Backend& B = c->be;
+  if (!B.active) return fail(c, GZB_ERR_STATE, "gzb_be_finish_iteration: gzb_be_begin not called");
+  if (n > 0 && (!blocks || !cidx || !val)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_finish_iteration: null argument");
+  for (size_t i = 0; i < n; ++i)
+    if (blocks[i] < 0 || blocks[i] >= B.num_blocks || cidx[i] >= 192 || !(B.comp_mask >> (cidx[i] >> 6) & 1))
+      return fail(c, GZB_ERR_BAD_ARG, "gzb_be_finish_iteration: flip out of range");
+  if (c->inter_valid && !c->changed_overflow) {
+    // pixel rectangles whose samples change (see gzb_update_coeffs)
+    if (n + c->changed.size() > 256) {
+      c->changed_overflow = true;
+      c->changed.clear();
+    } else {
+      for (size_t i = 0; i < n; ++i) {
+        const int comp = cidx[i] >> 6;
+        const int bx = blocks[i] % B.geom.pass_bw, by = blocks[i] / B.geom.pass_bw;
+        int4 q;
+        if (c->mode420 && comp > 0) q = make_int4(16 * bx - 1, 16 * by - 1, 16 * bx + 16, 16 * by + 16);
+        else q = make_int4(8 * bx, 8 * by, 8 * bx + 7, 8 * by + 7);
+        bool dup = false;
+        for (const int4& o : c->changed) dup = dup || (o.x == q.x && o.y == q.y && o.z == q.z && o.w == q.w);
+        if (!dup) c->changed.push_back(q);
+      }
+    }
+  }
+  if (n > 0) {
+    if (n > c->upd_cap) {
+      if (c->upd_own && c->d_upd) cudaFree(c->d_upd);
+      c->upd_cap = n + n / 2 + 1024;
+      dmalloc(&c->d_upd, c->upd_cap * 8);
+      c->upd_own = true;
+    }
+    uint8_t* stage = c->d_upd;
+    const size_t cap = c->upd_cap;
+    CK(cudaMemcpyAsync(stage, blocks, n * 4, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += n * 4;
+    CK(cudaMemcpyAsync(stage + cap * 4, val, n * 2, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += n * 2;
+    CK(cudaMemcpyAsync(stage + cap * 6, cidx, n, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += n;
+    KLAUNCH(c, KC_MISC, k_be_apply_walk<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(
+        B.geom, reinterpret_cast<const int*>(stage), stage + cap * 6, reinterpret_cast<const int16_t*>(stage + cap * 4), static_cast<int>(n),
+        direction, c->d_coef, B.last_index));
+  }
+  KLAUNCH(c, KC_MISC, k_be_update_max_err<<<(B.num_blocks + 255) / 256, 256, 0, c->stream>>>(c->d_weight, val_threshold, direction, B.num_blocks, B.max_err));
+  CK(cudaMemsetAsync(B.pcount, 0, static_cast<size_t>(B.num_blocks) * 4, c->stream));
+  c->packed_valid = false;
+  render_candidate(c, kCoeffKeep);   // no host sync: later calls are ordered by the stream / ev_cand
+  GZB_END(c)
+}
+
+int gzb_input_is_gray(gzb_ctx* c, int* gray) {
+  GZB_TRY(c)
+  if (!gray) return fail(c, GZB_ERR_BAD_ARG, "gzb_input_is_gray: null argument");
+  if (!c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_input_is_gray: no input coefficients");
+  unsigned* d_flag = c->d_scalars + 2;
+  CK(cudaMemsetAsync(d_flag, 0, 4, c->stream));
+  for (int k = 1; k < 3; ++k) {
+    const size_t n = comp_blocks(c, k) * 64;
+    KLAUNCH(c, KC_MISC, k_any_nonzero<<<static_cast<unsigned>((n / 8 + 256) / 256), 256, 0, c->stream>>>(c->d_orig + k * c->cs, n, d_flag));
+  }
+  unsigned* h = reinterpret_cast<unsigned*>(c->h_pinned) + 1000;   // bytes 4000.. of the pinned page
+  CK(cudaMemcpyAsync(h, d_flag, 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 4;
+  sync_check(c);
+  *gray = h[0] ? 0 : 1;
+  GZB_END(c)
+}
+
+int gzb_be_stats(const gzb_ctx* c, unsigned long long* selects, unsigned long long* levels) {
+  if (!c) return GZB_ERR_BAD_ARG;
+  if (selects) *selects = c->be.selects;
+  if (levels) *levels = c->be.levels;
+  return GZB_OK;
+}
+
+// Test hook: makes `entries` the order of the context (no candidate lists behind it).
+int gzb_be_test_load_order(gzb_ctx* c, const gzb_order_entry* entries, size_t n) {
+  GZB_TRY(c)
+  if (!entries || n == 0 || n >= (size_t(1) << 31)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_test_load_order: bad argument");
+  gzb_ctx::Backend& B = c->be;
+  be_reserve(c, c->nblocks, n);
+  B.active = true;
+  B.num_blocks = c->nblocks;
+  B.total = 0;
+  B.n = n;
+  CK(cudaMemsetAsync(B.st, 0, sizeof(BeState), c->stream));
+  CK(cudaMemcpyAsync(B.order, entries, n * 8, cudaMemcpyHostToDevice, c->stream));
+  const unsigned nn = static_cast<unsigned>(n);
+  CK(cudaMemcpyAsync(&B.st->n, &nn, 4, cudaMemcpyHostToDevice, c->stream));
+  KLAUNCH(c, KC_MISC, k_be_sort_begin<<<1, 1, 0, c->stream>>>(B.st));
+  sync_check(c);
+  GZB_END(c)
 }
 
 // ---- YUV 4:2:0 ---------------------------------------------------------------------------------

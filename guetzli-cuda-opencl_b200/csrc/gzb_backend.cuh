@@ -1,0 +1,523 @@
+// gzb_backend.cuh -- SelectFrequencyBackEnd (guetzli/processor.cc:723-919) on the device.
+//
+// Per adjustment iteration the reference builds `global_order` -- one (block, value) pair for every
+// remaining zeroing candidate of every block with a non-zero weight, up to 10^7 pairs at 12 MPix --
+// std::sort()s it and walks it from the front until the estimated file size has moved far enough.
+// The walk cannot stop (nor be observed) before `min_coeffs_to_change` entries, so all but its last
+// few hundred to few thousand steps are a SET of entries: the first p of the sorted order, in any
+// order. Here everything up to that point stays in HBM:
+//
+//   k_be_count / k_scan_counts / k_be_fill : the order, in the reference's block-major arrangement
+//       (processor.cc:786-813), values (err - max_err) / weight in IEEE float like the host code;
+//   k_be_select : ONE persistent cooperative kernel that evaluates libstdc++'s introsort
+//       (std::sort = __introsort_loop + __final_insertion_sort) lazily: it runs the library's
+//       median-of-three + unguarded Hoare partition steps -- the same element swaps, so that ties
+//       between blocks end up exactly where std::sort puts them -- only on the ranges that straddle
+//       p, postponing every right-hand range on a device-side stack, until the straddling range is
+//       short enough for the host to finish it with the library's own code. A partition of a long
+//       range is data parallel although the library's loop is sequential: the loop swaps the k-th
+//       element from the left that is not less than the pivot with the k-th from the right that is
+//       not greater, while the former lies left of the latter; both lists can be read off the
+//       array before any swap, so ranks come from prefix sums and the swaps commute;
+//   k_be_prefix_count / k_be_apply_prefix : each block takes as many of its next candidates as it
+//       has entries among the first p (processor.cc:854-876 for a whole prefix at once);
+//   k_be_gather : the state of the few blocks the sequential walk will touch (quantised indices,
+//       last_index), for the host;
+//   k_be_apply_walk / k_be_update_max_err : the walked flips and processor.cc:893-895.
+//
+// The array never leaves the device; the host sees the short range around p (a few KB).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "gzb_device_math.cuh"
+
+namespace gzb {
+
+// std::pair<int, float> of the reference's global_order, as raw 64 bits: low word = block index,
+// high word = the float's bits (little endian: .first at the lower address).
+typedef unsigned long long BeEntry;
+__host__ __device__ __forceinline__ BeEntry be_make(int block, float val) {
+#ifdef __CUDA_ARCH__
+  return static_cast<unsigned long long>(static_cast<unsigned>(block)) | (static_cast<unsigned long long>(__float_as_uint(val)) << 32);
+#else
+  unsigned u;
+  memcpy(&u, &val, 4);
+  return static_cast<unsigned long long>(static_cast<unsigned>(block)) | (static_cast<unsigned long long>(u) << 32);
+#endif
+}
+__device__ __forceinline__ float be_val(BeEntry e) { return __uint_as_float(static_cast<unsigned>(e >> 32)); }
+__device__ __forceinline__ int be_block(BeEntry e) { return static_cast<int>(static_cast<unsigned>(e)); }
+
+struct BeRange { unsigned first, last; int depth, pad; };
+constexpr int kBeStack = 128;      // >= 2 * log2(n) + 2 pending ranges
+constexpr int kBeTile = 2048;      // entries per partition tile (256 threads x 8)
+constexpr int kBeThreads = 256;
+constexpr int kBeSmallMax = 4096;  // longest range handed to the host (capacity of BeState::small)
+constexpr unsigned kBeLocalMax = 16384;   // ranges up to this length are partitioned by one CTA (no grid barriers)
+
+enum { BE_RUNNING = 0, BE_SMALL = 1, BE_HEAP = 2, BE_EMPTY = 3 };
+
+// Device-resident state of one back-end pass; the head (up to `stack`) is what the host reads back.
+struct BeState {
+  // ---- results of the order build ----
+  unsigned n;                 // entries in the order
+  unsigned blocks_to_change;  // blocks that contributed at least one entry
+  unsigned below;             // entries with value < limit (partition_point of the first "up" iteration)
+  unsigned changed_blocks;    // blocks flipped by the prefix of this iteration
+  // ---- lazy sort ----
+  int status;                 // BE_*
+  int top;                    // pending ranges on the stack; stack[top - 1] is the leftmost
+  unsigned p_set;             // ranges that end at or before p_set are consumed as a set (dropped unsorted)
+  unsigned small_max;         // a range of at most this many entries goes to the host
+  unsigned levels, levels_total;
+  // the partition in flight
+  unsigned first, last;       // range being partitioned; the pivot sits at `first`
+  int depth;
+  float pv;
+  unsigned ntiles, NL, NR, K;
+  unsigned barrier;           // grid barrier ticket counter
+  unsigned pad0;
+  BeRange stack[kBeStack];
+};
+
+__device__ __forceinline__ BeEntry be_ld(const BeEntry* p) { return __ldcg(p); }
+__device__ __forceinline__ void be_st(BeEntry* p, BeEntry v) { __stcg(p, v); }
+
+// Grid-wide barrier for a cooperative launch (all CTAs resident): a monotone ticket counter, each
+// barrier adds gridDim.x tickets; __threadfence on both sides orders the data of the phases.
+__device__ __forceinline__ void be_grid_sync(unsigned* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned ticket = atomicAdd(bar, 1u);
+    const unsigned target = (ticket / gridDim.x + 1u) * gridDim.x;
+    while (*reinterpret_cast<volatile unsigned*>(bar) < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// std::__move_median_to_first(first, first + 1, mid, last - 1) with comp(a, b) = a.second < b.second.
+__device__ inline void be_median_to_first(BeEntry* a, unsigned first, unsigned last) {
+  const unsigned ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
+  const BeEntry ea = be_ld(a + ia), eb = be_ld(a + ib), ec = be_ld(a + ic);
+  const float va = be_val(ea), vb = be_val(eb), vc = be_val(ec);
+  unsigned pick;
+  if (va < vb) {
+    if (vb < vc) pick = ib;
+    else if (va < vc) pick = ic;
+    else pick = ia;
+  } else if (va < vc) pick = ia;
+  else if (vb < vc) pick = ic;
+  else pick = ib;
+  const BeEntry ef = be_ld(a + first);
+  const BeEntry ep = pick == ia ? ea : pick == ib ? eb : ec;
+  be_st(a + first, ep);
+  be_st(a + pick, ef);
+}
+
+// The control step between two partitions (one thread): drops consumed ranges, stops at a short range
+// or an exhausted depth budget, else pops the leftmost range and moves its pivot into place.
+__device__ inline void be_next_range(BeState* st, BeEntry* a) {
+  for (;;) {
+    if (st->top == 0) { st->status = BE_EMPTY; return; }
+    const BeRange r = st->stack[st->top - 1];
+    if (r.last <= st->p_set) { --st->top; continue; }
+    if (r.last - r.first <= st->small_max) { st->status = BE_SMALL; return; }
+    if (r.depth == 0) { st->status = BE_HEAP; return; }
+    --st->top;
+    st->first = r.first;
+    st->last = r.last;
+    st->depth = r.depth - 1;
+    be_median_to_first(a, r.first, r.last);
+    st->pv = be_val(be_ld(a + r.first));
+    st->ntiles = (r.last - r.first - 1 + kBeTile - 1) / kBeTile;
+    st->K = 0;
+    st->status = BE_RUNNING;
+    ++st->levels;
+    return;
+  }
+}
+
+// Barrier between the phases of a partition: the whole grid, or -- for a range short enough for one
+// CTA -- only the block (the other CTAs wait at the grid barrier of the main loop meanwhile).
+template <bool LOCAL>
+__device__ __forceinline__ void be_phase_sync(BeState* st) {
+  if (LOCAL) { __threadfence_block(); __syncthreads(); }
+  else be_grid_sync(&st->barrier);
+}
+
+// One std::__unguarded_partition_pivot of the range in *st (pivot already at `first`), then the control
+// step that chooses the next range. LOCAL: executed by CTA 0 alone.
+template <bool LOCAL>
+__device__ __forceinline__ void be_partition_level(BeEntry* a, unsigned* lpos, unsigned* rpos, unsigned* tcl, unsigned* tcr,
+                                                   BeState* st, unsigned (*s_cell_l)[8], unsigned (*s_cell_r)[8],
+                                                   unsigned* s_scan, unsigned* s_tile_r) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  volatile BeState* vst = st;
+  const unsigned first = vst->first, last = vst->last;
+  const float pv = vst->pv;
+  const unsigned ntiles = vst->ntiles;
+  BeEntry* A = a + first + 1;
+  const unsigned m = last - first - 1;
+  const unsigned tile0 = LOCAL ? 0u : blockIdx.x, tile_step = LOCAL ? 1u : gridDim.x;
+  // ---- phase 1: per-tile stopper counts ----
+  for (unsigned t = tile0; t < ntiles; t += tile_step) {
+    unsigned nl = 0, nr = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const unsigned i = t * kBeTile + j * kBeThreads + tid;
+      bool fl = false, fr = false;
+      if (i < m) {
+        const float v = be_val(be_ld(A + i));
+        fl = !(v < pv);
+        fr = !(pv < v);
+      }
+      nl += __popc(__ballot_sync(0xffffffffu, fl));
+      nr += __popc(__ballot_sync(0xffffffffu, fr));
+    }
+    if (lane == 0) { s_cell_l[0][warp] = nl; s_cell_r[0][warp] = nr; }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned sl = 0, sr = 0;
+      for (int w = 0; w < 8; ++w) { sl += s_cell_l[0][w]; sr += s_cell_r[0][w]; }
+      __stcg(tcl + t, sl);
+      __stcg(tcr + t, sr);
+    }
+    __syncthreads();
+  }
+  be_phase_sync<LOCAL>(st);
+  // ---- phase 2 (CTA 0): tile offsets. tcl[t] <- stoppers left of tile t; tcr[t] <- right stoppers right of tile t ----
+  if (blockIdx.x == 0) {
+    const unsigned per = (ntiles + kBeThreads - 1) / kBeThreads;
+    const unsigned t0 = min(ntiles, tid * per), t1 = min(ntiles, t0 + per);
+    unsigned sl = 0, sr = 0;
+    for (unsigned t = t0; t < t1; ++t) { sl += __ldcg(tcl + t); sr += __ldcg(tcr + t); }
+    // inclusive scans of the per-thread sums (left counts forward, right counts backward)
+    s_scan[tid] = sl;
+    __syncthreads();
+    for (int off = 1; off < kBeThreads; off <<= 1) {
+      const unsigned v = tid >= off ? s_scan[tid - off] : 0;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    unsigned runl = s_scan[tid] - sl;
+    const unsigned NL = s_scan[kBeThreads - 1];
+    __syncthreads();
+    s_scan[tid] = sr;
+    __syncthreads();
+    for (int off = 1; off < kBeThreads; off <<= 1) {
+      const unsigned v = tid + off < kBeThreads ? s_scan[tid + off] : 0;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    const unsigned NR = s_scan[0];
+    unsigned runr = s_scan[tid];   // right stoppers in this thread's tiles and everything to their right
+    for (unsigned t = t0; t < t1; ++t) {
+      const unsigned cl = __ldcg(tcl + t), cr = __ldcg(tcr + t);
+      __stcg(tcl + t, runl);
+      runl += cl;
+      runr -= cr;
+      __stcg(tcr + t, runr);
+    }
+    if (tid == 0) { vst->NL = NL; vst->NR = NR; }
+    __syncthreads();
+  }
+  be_phase_sync<LOCAL>(st);
+  // ---- phase 3: the two stopper lists ----
+  for (unsigned t = tile0; t < ntiles; t += tile_step) {
+    unsigned bl[8], br[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const unsigned i = t * kBeTile + j * kBeThreads + tid;
+      bool fl = false, fr = false;
+      if (i < m) {
+        const float v = be_val(be_ld(A + i));
+        fl = !(v < pv);
+        fr = !(pv < v);
+      }
+      bl[j] = __ballot_sync(0xffffffffu, fl);
+      br[j] = __ballot_sync(0xffffffffu, fr);
+      if (lane == 0) { s_cell_l[j][warp] = __popc(bl[j]); s_cell_r[j][warp] = __popc(br[j]); }
+    }
+    __syncthreads();
+    // exclusive scan of the 64 cells in index order (iteration-major, then warp): two cells per lane of warp 0
+    if (warp == 0) {
+      unsigned* cl = &s_cell_l[0][0];
+      unsigned* cr = &s_cell_r[0][0];
+      const unsigned l0 = cl[2 * lane], l1 = cl[2 * lane + 1], r0 = cr[2 * lane], r1 = cr[2 * lane + 1];
+      unsigned sl = l0 + l1, sr = r0 + r1;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned vl = __shfl_up_sync(0xffffffffu, sl, off), vr = __shfl_up_sync(0xffffffffu, sr, off);
+        if (lane >= off) { sl += vl; sr += vr; }
+      }
+      cl[2 * lane] = sl - l0 - l1; cl[2 * lane + 1] = sl - l1;
+      cr[2 * lane] = sr - r0 - r1; cr[2 * lane + 1] = sr - r1;
+      if (lane == 31) *s_tile_r = sr;   // right stoppers in the tile
+    }
+    __syncthreads();
+    const unsigned base_l = __ldcg(tcl + t);
+    // right stoppers of this tile take ranks [tcr[t], tcr[t] + tile_r) counted from the right
+    const unsigned base_r = __ldcg(tcr + t), tile_r = *s_tile_r;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const unsigned i = t * kBeTile + j * kBeThreads + tid;
+      if (bl[j] >> lane & 1u) __stcg(lpos + base_l + s_cell_l[j][warp] + __popc(bl[j] & lt), i);
+      if (br[j] >> lane & 1u) {
+        const unsigned asc = s_cell_r[j][warp] + __popc(br[j] & lt);   // rank from the left inside the tile
+        __stcg(rpos + base_r + (tile_r - 1u - asc), i);
+      }
+    }
+    __syncthreads();
+  }
+  be_phase_sync<LOCAL>(st);
+  // ---- phase 4: the swaps. Pair k is swapped iff lpos[k] < rpos[k] (monotone in k); K = their number ----
+  {
+    const unsigned NL = vst->NL, NR = vst->NR;
+    const unsigned lim = min(NL, NR);
+    unsigned cnt = 0;
+    const unsigned k0 = LOCAL ? tid : blockIdx.x * kBeThreads + tid, kstep = LOCAL ? kBeThreads : gridDim.x * kBeThreads;
+    for (unsigned k = k0; k < lim; k += kstep) {
+      const unsigned l = __ldcg(lpos + k), r = __ldcg(rpos + k);
+      if (!(l < r)) break;
+      const BeEntry el = be_ld(A + l), er = be_ld(A + r);
+      be_st(A + l, er);
+      be_st(A + r, el);
+      ++cnt;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    if (lane == 0 && cnt) atomicAdd(&st->K, cnt);
+  }
+  be_phase_sync<LOCAL>(st);
+  // ---- phase 5 (one thread): the cut, the two new ranges, the next pivot ----
+  if (blockIdx.x == 0 && tid == 0) {
+    const unsigned K = vst->K, NL = vst->NL;
+    unsigned cut = m;   // the scans are guarded by the median-of-three: a stopper exists
+    if (K < NL) cut = min(cut, __ldcg(lpos + K));
+    if (K > 0) cut = min(cut, __ldcg(rpos + K - 1));
+    const unsigned gcut = first + 1 + cut;
+    const int depth = vst->depth;
+    st->stack[st->top++] = BeRange{gcut, last, depth, 0};
+    st->stack[st->top++] = BeRange{first, gcut, depth, 0};
+    be_next_range(st, a);
+    __threadfence();
+  }
+}
+
+// Lazy introsort: see the file header. Cooperative launch, gridDim.x CTAs of kBeThreads threads.
+//   a     : the order (n entries)
+//   lpos  : scratch, n words: positions (relative to first + 1) of the entries that stop the left scan
+//   rpos  : scratch, n words: ... that stop the right scan, rpos[k] = k-th from the right
+//   tcl / tcr : scratch, per-tile counts, then tile offsets (ceil(n / kBeTile) + 1 words each)
+//   small : receives the entries of the short range the kernel stops at (status BE_SMALL)
+__global__ void __launch_bounds__(kBeThreads)
+k_be_select(BeEntry* a, unsigned* lpos, unsigned* rpos, unsigned* tcl, unsigned* tcr, BeState* st, BeEntry* small) {
+  __shared__ unsigned s_cell_l[8][8], s_cell_r[8][8];   // [iteration][warp] stopper counts of a tile
+  __shared__ unsigned s_scan[kBeThreads];
+  __shared__ unsigned s_tile_r;
+  const int tid = threadIdx.x;
+  volatile BeState* vst = st;
+  if (blockIdx.x == 0 && tid == 0) { st->levels = 0; be_next_range(st, a); __threadfence(); }
+  for (;;) {
+    be_grid_sync(&st->barrier);
+    if (vst->status != BE_RUNNING) break;
+    if (vst->last - vst->first <= kBeLocalMax) {
+      // short ranges: CTA 0 partitions on its own for as long as they stay short, the rest of the grid waits above
+      if (blockIdx.x == 0) {
+        do {
+          be_partition_level<true>(a, lpos, rpos, tcl, tcr, st, s_cell_l, s_cell_r, s_scan, &s_tile_r);
+          __syncthreads();
+        } while (vst->status == BE_RUNNING && vst->last - vst->first <= kBeLocalMax);
+      }
+      continue;
+    }
+    be_partition_level<false>(a, lpos, rpos, tcl, tcr, st, s_cell_l, s_cell_r, s_scan, &s_tile_r);
+  }
+  // the short range the host finishes
+  if (blockIdx.x == 0 && vst->status == BE_SMALL) {
+    const BeRange r = st->stack[st->top - 1];
+    for (unsigned i = tid; i < r.last - r.first; i += kBeThreads) small[i] = be_ld(a + r.first + i);
+  }
+  if (blockIdx.x == 0 && tid == 0) st->levels_total += st->levels;
+}
+
+// ---- the order ---------------------------------------------------------------------------------
+// Candidate list addressing with the reference's clamp (processor.cc:789-791, 859): a block whose
+// offset equals the total reads the last entry of the arrays.
+struct BeCands {
+  const int* off;          // [num_blocks + 1]
+  const uint8_t* idx;      // [total]
+  const float* err;        // [total]
+  int total;
+};
+__device__ __forceinline__ int be_cand_offset(const BeCands& c, int b) { return max(0, min(c.off[b], c.total - 1)); }
+
+// entries block b contributes (processor.cc:794-811)
+__global__ void k_be_count(BeCands c, const float* __restrict__ weight, const int* __restrict__ last_index, int num_blocks,
+                           int direction, int* __restrict__ counts, BeState* st) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  int cnt = 0;
+  if (b < num_blocks && weight[b] != 0.f) {
+    const int offset = be_cand_offset(c, b);
+    const int num = c.off[b + 1] - offset;
+    const int li = last_index[b];
+    cnt = direction > 0 ? max(0, num - li) : max(0, li);
+  }
+  if (b < num_blocks) counts[b] = cnt;
+  const unsigned any = __popc(__ballot_sync(0xffffffffu, cnt > 0));
+  if ((threadIdx.x & 31) == 0 && any) atomicAdd(&st->blocks_to_change, any);
+}
+
+// warp per block: its entries in the reference's order, at the block's offset of the scan
+__global__ void k_be_fill(BeCands c, const float* __restrict__ weight, const int* __restrict__ last_index,
+                          const float* __restrict__ max_err, const int* __restrict__ counts, const int* __restrict__ offsets,
+                          int num_blocks, int direction, float limit, BeEntry* __restrict__ order, BeState* st) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= num_blocks) return;
+  const int cnt = counts[b];
+  if (cnt == 0) return;
+  const int offset = be_cand_offset(c, b);
+  const int li = last_index[b];
+  const float me = max_err[b], w = weight[b];
+  const float* errs = c.err + offset;
+  BeEntry* o = order + offsets[b];
+  unsigned below = 0;
+  for (int j = lane; j < cnt; j += 32) {
+    const float e = errs[direction > 0 ? li + j : li - 1 - j];
+    const float val = direction > 0 ? (e - me) / w : (me - e) / w;
+    o[j] = be_make(b, val);
+    below += val < limit ? 1u : 0u;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) below += __shfl_xor_sync(0xffffffffu, below, off);
+  if (lane == 0 && below) atomicAdd(&st->below, below);
+}
+
+__global__ void k_be_set_n(const int* __restrict__ offsets, int num_blocks, BeState* st) {
+  st->n = static_cast<unsigned>(offsets[num_blocks]);
+}
+
+// (re)starts the lazy sort over the n entries: one pending range with introsort's depth budget
+__global__ void k_be_sort_begin(BeState* st) {
+  const unsigned n = st->n;
+  st->top = 0;
+  st->levels_total = 0;
+  if (n >= 1) {   // (a single entry is a short range: the host takes it as it is)
+    st->stack[0] = BeRange{0u, n, 2 * (31 - __clz(n)), 0};   // 2 * std::__lg(n)
+    st->top = 1;
+  }
+}
+
+__global__ void k_be_select_args(BeState* st, unsigned p_set, unsigned small_max) {
+  st->p_set = p_set;
+  st->small_max = small_max;
+  st->barrier = 0;
+}
+
+// ---- the prefix, consumed as a set ---------------------------------------------------------------
+__global__ void k_be_prefix_count(const BeEntry* __restrict__ order, unsigned p, unsigned* __restrict__ pcount) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p) atomicAdd(&pcount[be_block(order[i])], 1u);
+}
+
+// Geometry of the pass: unit b of the search owns coefficient block (b / pass_bw) * coef_bw + b % pass_bw
+// of the searched planes (the 4:2:0 luma plane is MCU-padded).
+struct BeGeom { int num_blocks, pass_bw, coef_bw; size_t cs; };
+__device__ __forceinline__ size_t be_cblock(const BeGeom& g, int b) {
+  return static_cast<size_t>(b / g.pass_bw) * g.coef_bw + b % g.pass_bw;
+}
+
+// thread per block: the next pcount[b] candidates of the block are flipped (processor.cc:858-875)
+__global__ void k_be_apply_prefix(BeCands c, BeGeom g, const unsigned* __restrict__ pcount, int direction,
+                                  const int16_t* __restrict__ orig, const int* __restrict__ q192,
+                                  int16_t* __restrict__ coef, int* __restrict__ last_index, BeState* st) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned times = 0;
+  if (b < g.num_blocks) times = pcount[b];
+  const unsigned any = __popc(__ballot_sync(0xffffffffu, times > 0));
+  if ((threadIdx.x & 31) == 0 && any) atomicAdd(&st->changed_blocks, any);
+  if (!times) return;
+  const uint8_t* cands = c.idx + be_cand_offset(c, b);
+  const size_t cb = be_cblock(g, b);
+  int li = last_index[b];
+  for (unsigned rep = 0; rep < times; ++rep) {
+    const int cidx = cands[li + min(direction, 0)];
+    const int comp = cidx >> 6, k = cidx & 63;
+    const size_t at = comp * g.cs + cb * 64 + k;
+    coef[at] = direction > 0 ? static_cast<int16_t>(0) : static_cast<int16_t>(quantize_coeff(orig[at], q192[cidx]));
+    li += direction;
+  }
+  last_index[b] = li;
+}
+
+// ---- the walk's blocks ---------------------------------------------------------------------------
+// One record per requested block: what the sequential walk on the host needs to flip the block's next
+// candidates and to price the symbols that change.
+struct BeBlockState {
+  int last_index;
+  unsigned prefix_count;      // entries of the block in this iteration's prefix (> 0: already counted as changed)
+  int16_t idx[3][64];         // quantised indices (coefficient / q) of the three components
+  int16_t requant[3][64];     // Quantize(original, q): the value a "down" step restores
+};
+__global__ void k_be_gather(BeGeom g, const int* __restrict__ blocks, int nreq, const int16_t* __restrict__ coef,
+                            const int16_t* __restrict__ orig, const int* __restrict__ q192, const int* __restrict__ last_index,
+                            const unsigned* __restrict__ pcount, int comp_mask, int want_requant, BeBlockState* __restrict__ out) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= nreq) return;
+  const int b = blocks[r];
+  const size_t cb = be_cblock(g, b);
+  BeBlockState* o = out + r;
+  if (lane == 0) { o->last_index = last_index[b]; o->prefix_count = pcount[b]; }
+  for (int i = lane; i < 192; i += 32) {
+    const int comp = i >> 6, k = i & 63;
+    int16_t vi = 0, vr = 0;
+    if (comp_mask >> comp & 1) {
+      const size_t at = comp * g.cs + cb * 64 + k;
+      const int q = q192[i];
+      vi = static_cast<int16_t>(coef[at] / q);
+      if (want_requant) vr = static_cast<int16_t>(quantize_coeff(orig[at], q));
+    }
+    o->idx[comp][k] = vi;
+    o->requant[comp][k] = vr;
+  }
+}
+
+// the flips of the sequential walk that stay applied
+__global__ void k_be_apply_walk(BeGeom g, const int* __restrict__ blocks, const uint8_t* __restrict__ cidx,
+                                const int16_t* __restrict__ val, int n, int direction, int16_t* __restrict__ coef,
+                                int* __restrict__ last_index) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = blocks[i], ci = cidx[i];
+  coef[(ci >> 6) * g.cs + be_cblock(g, b) * 64 + (ci & 63)] = val[i];
+  atomicAdd(&last_index[b], direction);
+}
+
+// processor.cc:893-895
+__global__ void k_be_update_max_err(const float* __restrict__ weight, float val_threshold, int direction, int num_blocks,
+                                    float* __restrict__ max_err) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= num_blocks) return;
+  const float d = (weight[b] * val_threshold) * static_cast<float>(direction);
+  max_err[b] = max_err[b] + d;
+}
+
+// IsGrayscale (processor.cc:921-929): any non-zero coefficient in the chroma planes of the q=1 input?
+__global__ void k_any_nonzero(const int16_t* __restrict__ p, size_t n, unsigned* flag) {
+  size_t i = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) * 8;
+  bool nz = false;
+  if (i + 8 <= n) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p + i);
+    nz = (v.x | v.y | v.z | v.w) != 0;
+  } else {
+    for (; i < n; ++i) nz = nz || p[i] != 0;
+  }
+  if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
+}  // namespace gzb

@@ -199,6 +199,69 @@ int gzb_compute_block_error_adjustment_weights_f(gzb_ctx* ctx, int direction, in
                                                  double target_mul, int factor, const float* distmap,
                                                  float* block_weight);
 
+/* ---- SelectFrequencyBackEnd on the device (guetzli/processor.cc:723-919) ---------------------
+ * The adjustment loop's state -- candidate lists, last_indexes, max_block_error, block_weight and the
+ * sorted `global_order` of up to 10^7 (block, value) pairs -- lives in HBM. The host keeps only what is
+ * sequential by definition: the stopping test on the estimated size over the LAST few hundred steps of
+ * the walk. The order is sorted lazily with exactly the element movements of libstdc++'s std::sort (the
+ * reference sorts with it and cross-block ties are the norm), see csrc/gzb_backend.cuh. */
+typedef struct { int block; float value; } gzb_order_entry;   /* std::pair<int, float> of global_order */
+/* What the host walk needs to know about one block (gzb_be_gather). */
+typedef struct {
+  int last_index;            /* last_indexes[block] */
+  unsigned prefix_count;     /* flips of this block in the prefix of the current iteration */
+  int16_t idx[3][64];        /* quantised indices (coefficient / q), natural order; components outside comp_mask: 0 */
+  int16_t requant[3][64];    /* Quantize(input coefficient, q) (quantize.h:24-29): what a "down" step writes; 0 if not asked */
+} gzb_be_block_state;
+/* Starts a pass over the units of comp_mask (8x8 blocks; 16x16 macro-blocks for the chroma pass of a
+ * 4:2:0 image): last_indexes and max_block_error are zeroed (processor.cc:757-758). The candidate lists
+ * (processor.cc:694-716) are taken from the host arrays, or -- offsets == NULL -- from the lists the last
+ * gzb_compute_block_zeroing_candidates call over all blocks of comp_mask left on the device (`total`
+ * = its *n_out). */
+int gzb_be_begin(gzb_ctx* ctx, int comp_mask, const int* offsets, const uint8_t* cand_idx,
+                 const float* cand_err, size_t total);
+/* processor.cc:775-828 without the sort: ComputeBlockErrorAdjustmentWeights for rblock = 1, 2, .. until
+ * the order is non-empty, then global_order in the reference's arrangement, on the device.
+ * *n = global_order.size(), *below = entries with value < below_limit (the partition_point of the
+ * first "up" iteration, processor.cc:840-848), *rblock = the radius used (4 if the order stayed empty). */
+int gzb_be_build_order(gzb_ctx* ctx, int direction, double target_mul, float below_limit, uint64_t* n,
+                       int* blocks_to_change, uint64_t* below, int* rblock);
+/* One step of the lazy std::sort. Pending ranges that end at or before p_set are dropped unsorted (their
+ * entries are consumed as a set); the leftmost remaining range is partitioned, the library's way, until
+ * it holds at most small_max (<= 4096) entries. status 1: entries_out receives that range
+ * [*first, *last) -- still to be sorted by the caller with depth budget *depth (std::__introsort_loop's
+ * third argument) -- and the range stays pending; 2: the range [*first, *last) has used up its depth
+ * budget (std::sort heap-sorts it: fetch, std::partial_sort, store); 3: nothing is pending. */
+int gzb_be_select(gzb_ctx* ctx, uint64_t p_set, int small_max, int* status, uint64_t* first,
+                  uint64_t* last, int* depth, gzb_order_entry* entries_out);
+int gzb_be_fetch_order(gzb_ctx* ctx, uint64_t first, gzb_order_entry* out, size_t n);
+int gzb_be_store_order(gzb_ctx* ctx, uint64_t first, const gzb_order_entry* in, size_t n);
+/* Consumes order[0, p) as a set (processor.cc:854-876 for each entry; the order of the entries does not
+ * matter before the first observable step): every block takes as many of its next candidates as it has
+ * entries there. ac_hist768 (optional) receives the AC symbol counts of the candidate afterwards, counted
+ * as a file of hist_ncomp components; *changed_blocks the number of blocks flipped. blocks / nreq /
+ * states_out (optional): a gzb_be_gather in the same round trip. */
+int gzb_be_apply_prefix(gzb_ctx* ctx, uint64_t p, int direction, int hist_ncomp, uint32_t* ac_hist768,
+                        int* changed_blocks, const int* blocks, int nreq, gzb_be_block_state* states_out);
+/* State of nreq (<= 4096) blocks for the sequential part of the walk. */
+int gzb_be_gather(gzb_ctx* ctx, const int* blocks, int nreq, int direction, gzb_be_block_state* states_out);
+/* End of an iteration: the flips of the sequential walk (unit index, coefficient index 64*c + k, value;
+ * each advances last_indexes by direction), max_block_error += block_weight * val_threshold * direction
+ * (processor.cc:893-895), and the candidate's samples are re-rendered for the next Compare. */
+int gzb_be_finish_iteration(gzb_ctx* ctx, const int32_t* blocks, const uint8_t* cidx, const int16_t* val,
+                            size_t n, int direction, float val_threshold);
+/* IsGrayscale(jpg) of the input (processor.cc:921-929): *gray = 1 if both chroma planes are all zero. */
+int gzb_input_is_gray(gzb_ctx* ctx, int* gray);
+/* Counters: selects = gzb_be_select calls, levels = partitions run on the device, host_ranges = short
+ * ranges finished by the caller. */
+int gzb_be_stats(const gzb_ctx* ctx, unsigned long long* selects, unsigned long long* levels);
+/* Test hook: sorts n entries through the same device path (partitions on the device down to small_max,
+ * short ranges finished with the host's restatement of introsort) and checks nothing else. The result
+ * must equal std::sort's permutation. prefix > 0: additionally treats [0, prefix) as a set first. */
+int gzb_test_device_sort(gzb_ctx* ctx, gzb_order_entry* entries, size_t n, size_t prefix, int small_max);
+/* Test hook: makes `entries` the context's order (no candidate lists behind it) and restarts the lazy sort. */
+int gzb_be_test_load_order(gzb_ctx* ctx, const gzb_order_entry* entries, size_t n);
+
 /* ---- YUV 4:2:0 (Params::try_420 / force_420; guetzli/processor.cc:986-1016) ------------------
  * Processor::DownsampleImage + OutputImage::SaveToJpegData on the q=1 input (guetzli/processor.cc:
  * 109-116, 994-997; guetzli/output_image.cc:496-640; guetzli/preprocess_downsample.cc:157-281, default
@@ -268,7 +331,11 @@ typedef struct {
   double device_write_ms;                /* candidate files coded on the device (histograms, codes, scan, fetch) */
   double search_wall_ms, trial_host_ms, trial_device_ms;  /* SelectQuantMatrix phase; host/device legs of its trials */
   int search_rounds, search_trials;      /* SelectQuantMatrix: exchange rounds / trials evaluated by the group */
-  double downsample_ms;                  /* YUV420 passes: DownsampleImage + SaveToJpegData on the device, coefficients fetched */
+  double downsample_ms;                  /* YUV420 passes: DownsampleImage + SaveToJpegData on the device */
+  unsigned long long be_selects, be_levels;  /* back end: lazy-sort kernel launches / partitions run on the device */
+  unsigned long long be_host_ranges;     /* back end: short ranges of the order finished on the host */
+  double be_select_ms, be_gather_ms, be_pool_ms;  /* inside be_walk_ms: lazy-sort round trips, block-state round trips
+                                                     (the first one consumes the prefix), parallel entropy-code rebuilds */
 } gzb_encode_stats;
 int gzb_encode_rgb(int device, const uint8_t* rgb, int width, int height, float butteraugli_target,
                    int host_threads, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,

@@ -130,12 +130,24 @@ bool B200ButteraugliComparator::ComputeBlockZeroingOrder(const JPEGData& jpg, co
   const int last_c = (comp_mask & 4) ? 2 : (comp_mask & 2) ? 1 : 0;   // processor.cc:565-572
   const size_t nblocks = static_cast<size_t>(img.component(last_c).width_in_blocks()) * img.component(last_c).height_in_blocks();
   output_order->assign(nblocks * 192, gzb_coeff_data{0, 0.0f});
+  // SaveToJpegData drops all-zero chroma planes (guetzli/output_image.cc:588): a grey jpg has ONE component.
+  // Its chroma coefficients are zeros of the layout the context expects.
+  if (jpg.components.empty() || (comp_mask >> jpg.components.size()) != 0) return false;   // processor.cc:735
+  const std::vector<coeff_t>* planes[3];
+  std::vector<coeff_t> zeros;
+  for (int c = 0; c < 3; ++c) {
+    if (static_cast<size_t>(c) < jpg.components.size()) {
+      planes[c] = &jpg.components[c].coeffs;
+    } else {
+      const size_t want = static_cast<size_t>(img.component(c).width_in_blocks()) * img.component(c).height_in_blocks() * 64;
+      if (zeros.size() < want) zeros.assign(want, 0);
+      planes[c] = &zeros;
+    }
+  }
   if (Is444(img)) {
-    if (gzb_set_jpeg_coeffs(ctx_, jpg.components[0].coeffs.data(), jpg.components[1].coeffs.data(),
-                            jpg.components[2].coeffs.data()) != GZB_OK) return false;
+    if (gzb_set_jpeg_coeffs(ctx_, planes[0]->data(), planes[1]->data(), planes[2]->data()) != GZB_OK) return false;
   } else {
-    if (gzb_set_jpeg_coeffs_420(ctx_, jpg.components[0].coeffs.data(), jpg.components[1].coeffs.data(),
-                                jpg.components[2].coeffs.data()) != GZB_OK) return false;
+    if (gzb_set_jpeg_coeffs_420(ctx_, planes[0]->data(), planes[1]->data(), planes[2]->data()) != GZB_OK) return false;
   }
   PushImage(img);
   return gzb_compute_block_zeroing_order(ctx_, comp_mask, output_order->data()) == GZB_OK;

@@ -54,6 +54,22 @@ def have_ref():
         os.path.exists("/root/reference/guetzli/processor.cc")
 
 
+_dropin = None
+
+
+def ref_dropin():
+    """oracle/_ref/libgzref_dropin.so: the unmodified reference Processor over the product's comparator
+    (the only checker library that links libgzb200.so; GPU tests only)."""
+    global _dropin
+    if _dropin is None:
+        ref()
+        path = os.path.join(ORACLE_DIR, "_ref", "libgzref_dropin.so")
+        if not os.path.exists(path):
+            _build("dropin")
+        _dropin = C.CDLL(path)
+    return _dropin
+
+
 def ref():
     global _ref
     if _ref is None:

@@ -200,7 +200,7 @@ def test_unmodified_reference_processor_420_through_b200_comparator(gz, name):
     factor 2), must emit the reference's bytes."""
     import ctypes as C
     import _libs
-    L = _libs.ref()
+    L = _libs.ref_dropin()
     L.ref_process_rgb_b200_params.restype = C.c_long
     gold = _gold_420()[name]
     kind, size, q, mode = name.split("_")

@@ -88,7 +88,7 @@ def test_unmodified_reference_processor_drives_b200_comparator(gz):
     import _libs
     if not _libs.have_ref():
         pytest.skip("oracle/_ref not present")
-    L = _libs.ref()
+    L = _libs.ref_dropin()
     L.ref_process_rgb_b200.restype = C.c_long
     gold_all = json.load(open(os.path.join(GOLD, "synth_encodes.json")))
     for key in ["97x61_q84_s1254", "128x96_q90_s1234"]:

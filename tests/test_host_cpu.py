@@ -110,30 +110,36 @@ def test_jpeg_writer_grayscale_and_sparse(gz):
     s.close()
 
 
-def test_lazy_sort_equals_std_sort(gz):
+def _sort_cases(rng, n):
+    yield rng.random(n).astype(np.float32)
+    yield rng.integers(0, 7, n).astype(np.float32)                      # heavy ties
+    yield np.sort(rng.random(n).astype(np.float32))                      # sorted input
+    yield (rng.integers(0, max(1, n // 3), n) / 8.0).astype(np.float32)
+    yield (np.arange(n) // 7).astype(np.float32)[::-1].copy()            # descending runs of equal keys
+
+
+def test_restated_introsort_equals_std_sort(gz):
+    """exact_sort (gzb_encoder.cc) restates libstdc++'s std::sort; the whole sort, and the sort evaluated
+    the way the device does it (one partition at a time, right-hand ranges pending, short ranges finished
+    separately with their depth budget), must both give std::sort's permutation, ties included."""
     L = gz.lib()
-    L.gzb_test_lazy_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    L.gzb_test_exact_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.gzb_test_exact_sort_split.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
     L.gzb_test_std_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    assert L.gzb_test_sort_emulation_ok() == 1
     rng = np.random.default_rng(4)
-    for n in [0, 1, 2, 15, 16, 17, 33, 100, 1000, 5000, 70000, 600000, 1500000]:   # >= 2^18: parallel partition
-        for kind in range(4):
-            if kind == 0:
-                v = rng.random(n).astype(np.float32)
-            elif kind == 1:
-                v = rng.integers(0, 7, n).astype(np.float32)          # heavy ties
-            elif kind == 2:
-                v = np.sort(rng.random(n).astype(np.float32))           # sorted input
-            else:
-                v = (rng.integers(0, max(1, n // 3), n) / 8.0).astype(np.float32)
+    for n in [0, 1, 2, 15, 16, 17, 33, 100, 1000, 5000, 70000, 600000]:
+        for v in _sort_cases(rng, n):
             ids = np.arange(n, dtype=np.int32)
             a_id, a_v = ids.copy(), v.copy()
             L.gzb_test_std_sort(p(a_id), p(a_v), n)
-            for prefix in sorted({0, 1, n // 100, n // 7, n // 2, n}):
+            b_id, b_v = ids.copy(), v.copy()
+            L.gzb_test_exact_sort(p(b_id), p(b_v), n)
+            assert np.array_equal(b_id, a_id) and np.array_equal(b_v, a_v), n
+            for small in (16, 100, 1024, 4096):
                 b_id, b_v = ids.copy(), v.copy()
-                L.gzb_test_lazy_sort(p(b_id), p(b_v), n, prefix)
-                assert np.array_equal(b_id[:prefix], a_id[:prefix]), (n, kind, prefix)
-                assert np.array_equal(b_v[:prefix], a_v[:prefix])
-                assert np.array_equal(np.sort(b_id), np.arange(n, dtype=np.int32))
+                L.gzb_test_exact_sort_split(p(b_id), p(b_v), n, small)
+                assert np.array_equal(b_id, a_id) and np.array_equal(b_v, a_v), (n, small)
 
 
 def test_worker_pool_runs_every_task_exactly_once(gz):
@@ -152,40 +158,6 @@ def test_worker_pool_runs_every_task_exactly_once(gz):
     for t in th:
         t.join(300)
     assert res == [0, 0, 0, 0]
-
-
-def test_multiply_quantiser_is_exact(gz):
-    L = gz.lib()
-    L.gzb_test_quantize_magic.restype = C.c_long
-    assert L.gzb_test_quantize_magic(700) == 0
-
-
-def test_lazy_sort_set_prefix_is_std_sorts_prefix_as_a_set(gz):
-    """LazySort::ensure_set(p): positions [0,p) hold std::sort's first p entries (any order, ties
-    included) and the walk can continue with exact positions from p on (the back end's silent prefix)."""
-    L = gz.lib()
-    L.gzb_test_lazy_sort_set.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
-    L.gzb_test_std_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
-    rng = np.random.default_rng(9)
-    for n in [40, 1000, 70000, 600000, 1200000]:
-        for kind in range(3):
-            if kind == 0:
-                v = rng.random(n).astype(np.float32)
-            elif kind == 1:
-                v = rng.integers(0, 5, n).astype(np.float32)           # heavy ties: the set is not key-determined
-            else:
-                v = (rng.integers(0, max(1, n // 3), n) / 8.0).astype(np.float32)
-            ids = np.arange(n, dtype=np.int32)
-            a_id, a_v = ids.copy(), v.copy()
-            L.gzb_test_std_sort(p(a_id), p(a_v), n)
-            for pfx in sorted({0, 1, n // 50, n // 3, n - 10, n}):
-                upto = min(n - 1, pfx + max(30, n // 20))
-                b_id, b_v = ids.copy(), v.copy()
-                L.gzb_test_lazy_sort_set(p(b_id), p(b_v), n, pfx, upto)
-                assert np.array_equal(np.sort(b_id[:pfx]), np.sort(a_id[:pfx])), (n, kind, pfx)
-                assert np.array_equal(b_id[pfx:upto + 1], a_id[pfx:upto + 1]), (n, kind, pfx)
-                assert np.array_equal(b_v[pfx:upto + 1], a_v[pfx:upto + 1])
-                assert np.array_equal(np.sort(b_id), ids)
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
@@ -216,3 +188,15 @@ def test_huffman_depths_equal_reference(gz):
         L.gzb_test_huffman_depths(p(counts), p(got2), p(warm))
         assert np.array_equal(got, want), trial
         assert np.array_equal(got2, want), trial
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_reference_checker_does_not_link_the_product():
+    """oracle/_ref/libgzref.so is the unmodified reference plus a forwarding shim; only the separate
+    drop-in library (libgzref_dropin.so) may depend on libgzb200.so."""
+    import subprocess
+    ref()
+    path = os.path.join(ROOT, "oracle", "_ref", "libgzref.so")
+    needed = subprocess.run(["readelf", "-d", path], capture_output=True, text=True).stdout
+    assert "NEEDED" in needed
+    assert "gzb200" not in needed, needed
