@@ -4,20 +4,27 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size WxH] [--quality Q]
 
 A "step" is one full guetzli::Process of one synthetic image per GPU (RGB -> q=1 coefficients ->
-SelectQuantMatrix -> block-zeroing search -> back-end iterations -> best JPEG). Defaults: N=1,
-1024x1024 at quality 90 (BASELINE.json configs[1]). With N>1 (launched by torchrun, one rank per
-GPU) every rank encodes its own image of the batch: weak scaling, no data-path collective.
+SelectQuantMatrix -> block-zeroing search -> back-end iterations -> best JPEG). Default workload: the
+configuration the metric and the >=100x target are quoted on, 4000x3000 at quality 95 (BASELINE.json
+configs[2]'s image on ONE B200). With N>1 (torchrun, one rank per GPU) every rank encodes its own image
+of that size per step: weak scaling, no data-path collective (images are independent units).
 
   value  : MPix/s of gzb_encoder_run with the image, its XYB and its q=1 coefficients already
            resident in HBM (gzb_encoder_create is outside the timed region)
-  e2e    : MPix/s of gzb_encode_rgb from a host RGB buffer to host JPEG bytes (context creation,
+  e2e    : MPix/s of gzb_encode_rgb from a pinned host RGB buffer to host JPEG bytes (context creation,
            H2D of the image, every per-iteration copy and the D2H results inside the timed region)
   roofline : dominant kernel (k_zeroing_order), algorithmic bytes U2 = 3084 B per 8x8 block
-            / its CUDA-event duration on the launching stream, vs MEASURED_PEAKS.json
-  cpu_baseline : the unmodified reference (oracle/_ref) on one host core on a bounded sample
+           (SURVEY.md 8d) / its CUDA-event duration on the launching stream, vs MEASURED_PEAKS.json;
+           the FP64 rate of the same kernel against a non-FMA FP64 peak measured in this run
+  cpu_baseline : the unmodified reference (oracle/_ref) on one host core on a bounded crop of the same
+           image, plus the stored single-core time of the WHOLE workload image (tests/golden/full_encodes.json)
+  batch64 : BASELINE configs[3], 64 images of 1920x1080 at q95 split over the ranks, several encodes in
+           flight per GPU (gzb_encode_rgb_batch) -- extra key, separately timed
+  group  : BASELINE configs[2] at N>1, the 12 MPix image encoded ONCE by all ranks together
+           (SelectQuantMatrix candidates + zeroing blocks sharded, NCCL all-gather) -- extra key
 
---impl reference runs the reference's own CPU encoder on all host cores (one image per core, the
-reference's own batching method, tests/golden_test.sh:25) and prints the same JSON shape.
+--impl reference runs the reference's own CPU encoder on all host cores at the same quality on crops
+of the same workload image (one crop per core per step) and prints the same JSON shape.
 """
 import argparse
 import json
@@ -40,16 +47,15 @@ FALLBACK_HBM_GBS = 6650.0
 
 
 def ncu_evidence(kernel, w, h):
-    """dram bytes per launch / FP64-pipe utilisation of `kernel` from the committed ncu --set full
-    capture (profiles/r1_ncu_traffic.json, taken at 1024x1024). Only returned for that size."""
+    """Per-launch ncu counters of `kernel` from the committed `ncu --set full` capture of THIS workload
+    (profiles/r2_ncu_traffic.json holds one entry per image size): dram bytes, FP64-pipe utilisation and
+    the double-precision instruction counts the FP64 rate is computed from."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-        k = d["kernels"][kernel]
-        if (w, h) != (1024, 1024):
-            return None, None, d["source"]
-        return k["dram_bytes_per_launch"], k["fp64_pipe_pct"], d["source"]
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+        k = d["sizes"]["%dx%d" % (w, h)]["kernels"][kernel]
+        return k, d["sizes"]["%dx%d" % (w, h)].get("source")
     except Exception:
-        return None, None, None
+        return None, None
 
 
 def peaks():
@@ -141,18 +147,54 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------------
+# the workload image and bounded samples of it
+# ------------------------------------------------------------------------------------------------
+CROP = 384   # side of the crops the CPU reference is timed on (a whole 12 MPix encode takes half an hour per core)
+
+
+def workload_image(w, h, seed):
+    import _libs
+    return _libs.synth_image(w, h, seed)
+
+
+def crop_origins(w, h, count, first=0):
+    """`count` crop origins spread over the image on a grid (deterministic), starting at index `first`."""
+    nx, ny = max(1, w // CROP), max(1, h // CROP)
+    out = []
+    for i in range(first, first + count):
+        j = (i * 7919) % (nx * ny)
+        out.append(((j % nx) * CROP, (j // nx) * CROP))
+    return out
+
+
+def stored_full_reference(w, h, quality, seed):
+    """Single-core time of the unmodified reference on the WHOLE workload image, measured once in the build
+    container and committed with the golden bytes (tests/golden/full_encodes.json, make_full_golden.py)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "tests", "golden", "full_encodes.json")))
+        g = d["%dx%d_q%d_s%d" % (w, h, int(quality), seed)]
+        return g
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
 # reference arm: the unmodified reference CPU encoder on all host cores
 # ------------------------------------------------------------------------------------------------
+_REF_IMG = None
+
+
 def _ref_worker(args):
-    w, h, seed, target = args
+    x0, y0, target = args
     import _libs
-    img = _libs.synth_image(w, h, seed)
+    crop = np.ascontiguousarray(_REF_IMG[y0:y0 + CROP, x0:x0 + CROP])
     t0 = time.perf_counter()
-    jpg, iters, _ = _libs.ref_process(img, target)
+    jpg, iters, _ = _libs.ref_process(crop, target)
     return time.perf_counter() - t0, len(jpg), iters
 
 
 def run_reference(a, rank, world):
+    global _REF_IMG
     if rank != 0:
         return
     import multiprocessing as mp
@@ -161,30 +203,38 @@ def run_reference(a, rank, world):
         emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgzref.so not built"}))
         return
     cores = os.cpu_count() or 1
-    # bounded sample of the workload: one 256x256 crop-sized synthetic image per core per step
-    sw, sh = 256, 256
+    w, h = a.size
+    # bounded sample of the workload: crops of the SAME image at the SAME quality, one per host core per
+    # step (the reference has no threading; its own test runs one process per core, tests/golden_test.sh:25)
+    _REF_IMG = workload_image(w, h, 1234)
     target = float(np.float32(_libs.ref().ref_butteraugli_score_for_quality(float(a.quality))))
     ctx = mp.get_context("fork")
     times = []
     with ctx.Pool(cores) as pool:
         for step in range(a.warmup + a.steps):
-            jobs = [(sw, sh, 1234 + 10 * (step * cores + k), target) for k in range(cores)]
+            jobs = [(x0, y0, target) for (x0, y0) in crop_origins(w, h, cores, step * cores)]
             t0 = time.perf_counter()
             pool.map(_ref_worker, jobs)
             dt = time.perf_counter() - t0
             if step >= a.warmup:
                 times.append(dt)
-    mpix_step = cores * sw * sh / 1e6
+    mpix_step = cores * CROP * CROP / 1e6
     total = sum(times)
     value = mpix_step * len(times) / total
+    full = stored_full_reference(w, h, a.quality, 1234)
+    sample = ("%d crops of %dx%d of the synthetic %dx%d workload image per step, one per host core, quality %g"
+              % (cores, CROP, CROP, w, h, a.quality))
     line = {
         "impl": "reference", "metric": "end-to-end encode MPix/s", "value": value, "unit": "MPix/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "reference CPU guetzli::Process, quality %g, %d images of %dx%d per step (one per host core)"
-                               % (a.quality, cores, sw, sh)},
-        "cpu_baseline": {"value": value, "unit": "MPix/s", "cores": cores, "kind": "reference",
-                         "sample": "%d synthetic %dx%d images per step, one per core, quality %g" % (cores, sw, sh, a.quality)},
+        "config": {"workload": "synthetic %dx%d sRGB (SURVEY 8d generator, seed 1234), quality %g, guetzli::Process of the "
+                               "reference on the host CPU; bounded sample: %s" % (w, h, a.quality, sample)},
+        "cpu_baseline": {"value": value, "unit": "MPix/s", "cores": cores, "kind": "reference", "sample": sample,
+                         "full_workload_one_core": None if not full else {
+                             "seconds": full["reference_seconds_one_core"], "value": w * h / 1e6 / full["reference_seconds_one_core"],
+                             "unit": "MPix/s", "note": "the whole workload image on one core, measured in the build container "
+                                                       "(tests/golden/full_encodes.json): per-pixel cost grows with image size"}},
         "e2e": {"value": value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -194,23 +244,35 @@ def run_reference(a, rank, world):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline_single_core(quality):
-    """The unmodified reference on ONE core on a bounded sample (384x384, same generator)."""
+def cpu_baseline_single_core(img, w, h, quality):
+    """The unmodified reference on ONE core on a bounded sample: one CROP x CROP crop of the workload image."""
     import _libs
     if not _libs.have_ref():
         return None
-    sw, sh = 384, 384
-    img = _libs.synth_image(sw, sh, 1234)
+    x0, y0 = crop_origins(w, h, 1)[0]
+    crop = np.ascontiguousarray(img[y0:y0 + CROP, x0:x0 + CROP])
     target = float(np.float32(_libs.ref().ref_butteraugli_score_for_quality(float(quality))))
     t0 = time.perf_counter()
-    jpg, iters, _ = _libs.ref_process(img, target)
+    jpg, iters, _ = _libs.ref_process(crop, target)
     dt = time.perf_counter() - t0
-    return {"value": sw * sh / 1e6 / dt, "unit": "MPix/s", "cores": 1, "kind": "reference",
-            "sample": "one synthetic %dx%d image, quality %g, guetzli::Process single-threaded: %.1f s, %d iterations"
-                      % (sw, sh, quality, dt, iters)}
+    full = stored_full_reference(w, h, quality, 1234)
+    return {"value": crop.shape[0] * crop.shape[1] / 1e6 / dt, "unit": "MPix/s", "cores": 1, "kind": "reference",
+            "sample": "one %dx%d crop of the workload image, quality %g, guetzli::Process single-threaded: %.1f s, %d iterations"
+                      % (crop.shape[1], crop.shape[0], quality, dt, iters),
+            "full_workload_one_core": None if not full else {
+                "seconds": full["reference_seconds_one_core"], "value": w * h / 1e6 / full["reference_seconds_one_core"], "unit": "MPix/s",
+                "note": "the whole workload image (same generator and seed) on one core of the build container, stored with "
+                        "the golden bytes in tests/golden/full_encodes.json"}}
+
+
+def pinned_copy(torch, img):
+    """The image in page-locked host memory (the e2e arm copies its input from there)."""
+    t = torch.from_numpy(np.ascontiguousarray(img)).pin_memory()
+    return t, t.numpy()
 
 
 def run_ours(a, rank, world, local):
+    import hashlib
     import torch
     import __graft_entry__ as ge
     import _libs
@@ -230,134 +292,12 @@ def run_ours(a, rank, world, local):
     target = np.float32(gz.ButteraugliScoreForQuality(a.quality))
     cores = os.cpu_count() or 1
     host_threads = min(16, max(1, cores // max(1, world)))
-    if a.mode == "group" and world > 1:
-        # one image: the sequential back end runs on rank 0 alone, the other ranks only drive their GPU
-        host_threads = min(16, max(1, cores - 2 * (world - 1))) if rank == 0 else 2
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
-
-    group = a.mode == "group"
-
-    def one_image(step):
-        # batch mode: every rank its own image; group mode: all ranks share the step's image
-        return _libs.synth_image(w, h, 1234 + 10 * (step if group else step * world + rank))
-
-    allgather = None
-    if group and world > 1:
-        allgather = gz.torch_allgather(dist, torch.device("cuda", local))   # NCCL over NVLink
-
-    K = max(1, a.inflight) if not group else 1
-    if K > 1:
-        host_threads = max(1, host_threads // K)
-    images = [one_image(s) for s in range((a.warmup + a.steps) * K)]
-    sampler = ClockSampler(local)
-    run_ms, e2e_ms, launches, h2d, d2h = [], [], 0, 0, 0
-    z_ms_sum = cmp_ms_sum = 0.0
-    rounds, trials = [], []
-    kt = {}
-    n_cmp = 0
-    for step in range(a.warmup + a.steps):
-        timed = step >= a.warmup
-        if step == 0:
-            sampler.start()
-        if timed and step == a.warmup:
-            sampler.mark()
-        img = images[step * K]
-        # ---- device-resident arm: create outside, run inside the timed region
-        encs = [gz.Encoder(images[step * K + k], target, device=local, host_threads=host_threads, profile=False) for k in range(K)]
-        enc = encs[0]
-        if allgather is not None:
-            enc.set_group(rank, world, allgather)
-        flush.fill_(step & 0xff)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        t0 = time.perf_counter()
-        if K == 1:
-            jpg, st, _ = enc.run()
-        else:
-            # the encodes of the batch run concurrently: one's host phases overlap the others' kernels
-            res = [None] * K
-            th = [threading.Thread(target=lambda k=k: res.__setitem__(k, encs[k].run())) for k in range(K)]
-            for t in th:
-                t.start()
-            for t in th:
-                t.join()
-            jpg, st, _ = res[0]
-            for k in range(1, K):
-                st = dict(st, launches=st["launches"] + res[k][1]["launches"], num_compares=st["num_compares"] + res[k][1]["num_compares"])
-        e1.record()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) * 1e3
-        if timed:
-            run_ms.append(max(dt, e0.elapsed_time(e1)))
-            launches += st["launches"]
-            n_cmp += st["num_compares"]
-            # the dominant kernel and the Compare pipeline are bracketed by CUDA events on their own
-            # stream inside the library on every step (no per-launch profiling in the timed region)
-            z_ms_sum += st["device_zeroing_ms"]
-            cmp_ms_sum += st["device_compare_ms"]
-        for en in encs:
-            en.close()
-        # ---- end-to-end arm: host RGB buffer -> host JPEG bytes
-        flush.fill_((step + 1) & 0xff)
-        barrier()
-        t0 = time.perf_counter()
-        if allgather is not None:
-            jpg2, st2, _ = gz.ProcessGroup(img, target, dist, device=local, host_threads=host_threads)
-        elif K == 1:
-            jpg2, st2, _ = gz.Process(img, target, device=local, host_threads=host_threads)
-        else:
-            res2 = [None] * K
-            th = [threading.Thread(target=lambda k=k: res2.__setitem__(k, gz.Process(images[step * K + k], target, device=local,
-                                                                                     host_threads=host_threads))) for k in range(K)]
-            for t in th:
-                t.start()
-            for t in th:
-                t.join()
-            jpg2, st2, _ = res2[0]
-            for k in range(1, K):
-                st2 = dict(st2, h2d_bytes=st2["h2d_bytes"] + res2[k][1]["h2d_bytes"], d2h_bytes=st2["d2h_bytes"] + res2[k][1]["d2h_bytes"])
-        dt2 = (time.perf_counter() - t0) * 1e3
-        assert jpg2 == jpg
-        if timed:
-            rounds.append(st["search_rounds"]); trials.append(st["search_trials"])
-        if timed:
-            e2e_ms.append(dt2)
-            h2d += st2["h2d_bytes"]; d2h += st2["d2h_bytes"] + len(jpg2) * 0
-    clocks = sampler.stop()
-    # Throughput with several encodes in flight on the one GPU (their host phases overlap each other's
-    # kernels): an extra, separately timed measurement next to the single-image headline.
-    concurrent = None
-    if world == 1 and K == 1 and not group and not a.no_concurrent:
-        KC, NB = 3, 6
-        ht = max(1, host_threads // KC)
-        cimgs = [_libs.synth_image(w, h, 5000 + 10 * i) for i in range(NB * 2)]
-        ctimes = []
-        for step in range(1 + a.steps):
-            flush.fill_(step & 0xff)
-            torch.cuda.synchronize()
-            batch = [cimgs[(step * NB + k) % len(cimgs)] for k in range(NB)]
-            t0 = time.perf_counter()
-            gz.ProcessBatch(batch, target, device=local, inflight=KC, host_threads_per_encode=ht)
-            if step >= 1:
-                ctimes.append((time.perf_counter() - t0) * 1e3)
-        concurrent = {"inflight_per_gpu": KC, "host_threads_per_encode": ht, "images_per_batch": NB, "e2e_value": NB * w * h / 1e6 * len(ctimes) / (sum(ctimes) / 1e3),
-                      "unit": "MPix/s", "ms_per_batch": sum(ctimes) / len(ctimes),
-                      "note": "gzb_encode_rgb_batch: %d images per call from host buffers, %d encodes in flight on %d host threads "
-                              "each; the headline value / e2e above are one image at a time" % (NB, KC, ht)}
-    # per-kernel breakdown: ONE extra, untimed step with an event pair around every launch
-    if rank == 0:
-        enc = gz.Encoder(images[-1], target, device=local, host_threads=host_threads, profile=True)
-        if allgather is None:
-            enc.run()
-            for k, (ms, n) in enc.kernel_times().items():
-                kt[k] = (ms, n)
-        enc.close()
 
     def reduce_max(x):
         if dist is None:
@@ -373,13 +313,101 @@ def run_ours(a, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # One image per rank (seed 1234 + 10 * rank, the SURVEY 8d generator), the same at every step: nothing is
+    # carried from one encode to the next except the allocator's cached slab, and L2 is flushed in between.
+    seed = 1234 + 10 * rank
+    pin_t, img = pinned_copy(torch, workload_image(w, h, seed))
+    sampler = ClockSampler(local)
+    run_ms, e2e_ms, launches, h2d, d2h = [], [], 0, 0, 0
+    z_ms_sum = cmp_ms_sum = 0.0
+    n_cmp = 0
+    last_st = None
+    jpg = b""
+    for step in range(a.warmup + a.steps):
+        timed = step >= a.warmup
+        if step == 0:
+            sampler.start()
+        if timed and step == a.warmup:
+            sampler.mark()
+        # ---- device-resident arm: create outside, run inside the timed region
+        enc = gz.Encoder(img, target, device=local, host_threads=host_threads, profile=False)
+        flush.fill_(step & 0xff)
+        barrier()
+        t0 = time.perf_counter()
+        jpg, st, _ = enc.run()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        if timed:
+            run_ms.append(dt)
+            launches += st["launches"]
+            n_cmp += st["num_compares"]
+            # the dominant kernel and the Compare pipeline are bracketed by CUDA events on their own
+            # stream inside the library on every step (no per-launch profiling in the timed region)
+            z_ms_sum += st["device_zeroing_ms"]
+            cmp_ms_sum += st["device_compare_ms"]
+            last_st = st
+        enc.close()
+        # ---- end-to-end arm: pinned host RGB buffer -> host JPEG bytes
+        flush.fill_((step + 1) & 0xff)
+        barrier()
+        t0 = time.perf_counter()
+        jpg2, st2, _ = gz.Process(img, target, device=local, host_threads=host_threads)
+        dt2 = (time.perf_counter() - t0) * 1e3
+        assert jpg2 == jpg
+        if timed:
+            e2e_ms.append(dt2)
+            h2d += st2["h2d_bytes"]; d2h += st2["d2h_bytes"]
+    clocks = sampler.stop()
     total_run = reduce_max(sum(run_ms))
     total_e2e = reduce_max(sum(e2e_ms))
     launches_all = int(reduce_sum(launches))
     mpix = w * h / 1e6
-    images_per_step = 1 if group else world * K
-    value = images_per_step * mpix * a.steps / (total_run / 1e3)
-    e2e_value = images_per_step * mpix * a.steps / (total_e2e / 1e3)
+    value = world * mpix * a.steps / (total_run / 1e3)
+    e2e_value = world * mpix * a.steps / (total_e2e / 1e3)
+
+    # ---- extra: BASELINE configs[3], a fixed batch of 64 images of 1920x1080 at q95 split over the ranks,
+    # three encodes in flight per GPU (one encode's host phases overlap the others' kernels)
+    batch64 = None
+    if not a.no_extras:
+        bw_, bh_, NIMG, KC = 1920, 1080, 64, 3
+        bt = np.float32(gz.ButteraugliScoreForQuality(95))
+        distinct = [workload_image(bw_, bh_, 1234 + 10 * k) for k in range(8)]   # image i of the batch = distinct[i % 8]
+        mine = [distinct[i % 8] for i in range(NIMG) if i % world == rank]
+        ht = max(1, host_threads // KC)
+        gz.ProcessBatch(mine[:KC], bt, device=local, inflight=KC, host_threads_per_encode=ht)   # warm-up: slabs, pools
+        flush.fill_(7)
+        barrier()
+        t0 = time.perf_counter()
+        res = gz.ProcessBatch(mine, bt, device=local, inflight=KC, host_threads_per_encode=ht)
+        torch.cuda.synchronize()
+        bdt = reduce_max(time.perf_counter() - t0)
+        batch64 = {"workload": "BASELINE configs[3]: 64 synthetic 1920x1080 images (8 distinct, seeds 1234+10k, cycled), quality 95, "
+                               "split round-robin over %d GPU(s), gzb_encode_rgb_batch from host buffers" % world,
+                   "value": NIMG * bw_ * bh_ / 1e6 / bdt, "unit": "MPix/s", "seconds": bdt, "inflight_per_gpu": KC,
+                   "host_threads_per_encode": ht, "images_per_gpu": len(mine), "scaling": "strong",
+                   "bytes_first_image": len(res[0][0])}
+
+    # ---- extra (N > 1): BASELINE configs[2], ONE image encoded by all ranks together
+    group = None
+    if world > 1 and not a.no_extras:
+        gimg = workload_image(w, h, 1234) if rank != 0 else img
+        ght = min(16, max(1, cores - 2 * (world - 1))) if rank == 0 else 2   # the sequential back end runs on rank 0
+        gtimes = []
+        gj = b""
+        for it in range(3):
+            flush.fill_(it)
+            barrier()
+            t0 = time.perf_counter()
+            gj, gst, _ = gz.ProcessGroup(gimg, target, dist, device=local, host_threads=ght)
+            torch.cuda.synchronize()
+            gdt = reduce_max(time.perf_counter() - t0)
+            if it >= 1:
+                gtimes.append(gdt)
+        group = {"workload": "BASELINE configs[2]: the %dx%d q%g image encoded ONCE by %d GPUs (SelectQuantMatrix candidates and "
+                             "zeroing blocks sharded, NCCL all-gather per round; back end on rank 0)" % (w, h, a.quality, world),
+                 "value": mpix / (sum(gtimes) / len(gtimes)), "unit": "MPix/s", "seconds": sum(gtimes) / len(gtimes), "scaling": "strong",
+                 "bytes_equal_single_gpu": (gj == jpg) if rank == 0 else None}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -387,36 +415,52 @@ def run_ours(a, rank, world, local):
     peak, peak_src = peaks()
     nblocks = ((w + 7) // 8) * ((h + 7) // 8)
     z_ms, z_n = z_ms_sum, a.steps          # one zeroing launch per encode
-    gpu_ms_total = sum(v[0] for v in kt.values())
-    kz_ms = kt.get("k_zeroing_order", (0.0, 0))[0]
+    step_ms = total_run / a.steps
     roof = None
     if z_n:
         achieved = ALGO_BYTES_PER_BLOCK * nblocks / (z_ms / z_n / 1e3) / 1e9
-        traffic, fp64_pct, ncu_src = ncu_evidence("k_zeroing_order", w, h)
+        ev, ncu_src = ncu_evidence("k_zeroing_order", w, h)
+        fp64 = None
+        try:
+            pk = gz.MeasureFp64Peak(local)
+            fp64 = {"peak_gflops_non_fma": pk, "peak_source": "measured in this run: dependent-free DADD/DMUL streams, all SMs "
+                                                              "(gzb_measure_fp64_peak)"}
+            if ev and ev.get("fp64_flop_per_launch"):
+                fp64["achieved_gflops"] = ev["fp64_flop_per_launch"] / (z_ms / z_n / 1e3) / 1e9
+                fp64["frac"] = fp64["achieved_gflops"] / pk
+        except Exception as ex:   # noqa
+            fp64 = {"error": str(ex)}
         roof = {"bound": "hbm", "kernel": "k_zeroing_order", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ev.get("dram_bytes_per_launch") if ev else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_BLOCK * nblocks,
-                "avg_launch_ms": z_ms / z_n, "share_of_gpu_time": kz_ms / gpu_ms_total if gpu_ms_total else None,
-                "fp64_pipe_pct_of_peak": fp64_pct, "ncu_source": ncu_src,
+                "avg_launch_ms": z_ms / z_n, "share_of_step": (z_ms / z_n) / step_ms,
+                "fp64_pipe_pct_of_peak": ev.get("fp64_pipe_pct") if ev else None, "fp64": fp64, "ncu_source": ncu_src,
                 "note": "FP64-pipe/latency-bound search kernel (SURVEY 8d): ~126 CompareBlock trials per 8x8 block in "
                         "double precision; its U2 bytes are touched once, so the HBM fraction is small by construction "
-                        "and the FP64-pipe utilisation from ncu is the meaningful ceiling"}
+                        "and the FP64 rate against the measured non-FMA peak is the meaningful ceiling"}
     cmp_ms = cmp_ms_sum
-    kernels = {k: {"ms_per_step": ms, "launches_per_step": n} for k, (ms, n) in sorted(kt.items(), key=lambda kv: -kv[1][0])}
+    st = last_st
+    phases = {k: st[k] for k in ("search_wall_ms", "zeroing_wall_ms", "backend_wall_ms", "compare_wall_ms", "device_compare_ms",
+                                 "device_zeroing_ms", "be_order_ms", "be_walk_ms", "be_select_ms", "be_gather_ms", "be_codes_ms",
+                                 "be_pool_ms", "be_update_ms", "device_write_ms", "run_ms")}
+    phases["note"] = ("wall-clock partition of the last timed step inside gzb_encoder_run: run = search + zeroing + backend (+ small "
+                      "rest); backend = compare_wall + be_order + be_walk + be_update + coding waits; be_walk contains be_select, "
+                      "be_gather and be_codes (which contains be_pool); device_* are CUDA-event times on the launching stream")
+    gold = stored_full_reference(w, h, a.quality, 1234)
+    parity = {"sha256": hashlib.sha256(jpg).hexdigest(), "bytes": len(jpg)}
+    if gold:
+        parity["equals_reference_bytes"] = parity["sha256"] == gold["sha256"]
+        parity["reference"] = "tests/golden/full_encodes.json (unmodified reference, single thread, same image)"
     line = {
         "metric": "end-to-end encode MPix/s", "value": value, "unit": "MPix/s", "n_gpus": world, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": total_run / a.steps, "higher_is_better": True, "scaling": "strong" if group else "weak",
+        "warmup": a.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic %dx%d sRGB (SURVEY 8d generator, seed 1234+10k), quality %g, %s, "
-                               "guetzli::Process" % (w, h, a.quality,
-                                                     "ONE image per step shared by all GPUs: SelectQuantMatrix candidates and "
-                                                     "zeroing blocks sharded, NCCL all-gather per round" if group
-                                                     else ("one image per GPU per step" if K == 1 else
-                                                           "%d images per GPU per step, encoded concurrently" % K)),
-                   "mode": a.mode, "search_rounds_per_step": sum(rounds) / max(1, len(rounds)),
-                   "search_trials_per_step": sum(trials) / max(1, len(trials)),
-                   "l2": "256 MiB buffer written between timed steps (L2 flush)", "host_threads_per_encode": host_threads, "inflight_per_gpu": K,
-                   "compares_per_step": n_cmp / a.steps},
+        "config": {"workload": "synthetic %dx%d sRGB (SURVEY 8d generator, seed 1234+10*rank), quality %g, one image per GPU per "
+                               "step, guetzli::Process" % (w, h, a.quality),
+                   "l2": "256 MiB buffer written between timed steps (L2 flush); the same image at every step",
+                   "host_threads_per_encode": host_threads, "compares_per_step": n_cmp / a.steps,
+                   "iterations_per_step": st["num_iterations"], "be_steps_per_step": st["be_steps"],
+                   "be_prefix_steps_per_step": st["be_prefix_steps"]},
         "e2e": {"value": e2e_value, "unit": "MPix/s", "ms_per_step": total_e2e / a.steps,
                 "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps},
         "gpu_launches": launches_all,
@@ -424,10 +468,11 @@ def run_ours(a, rank, world, local):
         "roofline": roof,
         "butteraugli": {"compare_device_ms_per_call": cmp_ms / max(1, n_cmp), "mpix_per_s": mpix / (cmp_ms / max(1, n_cmp) / 1e3) if cmp_ms else None,
                         "hbm_frac_U1": (ALGO_BYTES_COMPARE_PER_PX * w * h / (cmp_ms / max(1, n_cmp) / 1e3) / 1e9 / peak) if cmp_ms else None},
-        "concurrent": concurrent,
-        "kernels": kernels,
-        "kernels_note": "one extra untimed step with a CUDA-event pair around every launch; the timed steps carry no per-launch profiling",
-        "cpu_baseline": cpu_baseline_single_core(a.quality) if world == 1 and not a.no_cpu_baseline else None,
+        "phases_ms": phases,
+        "parity": parity,
+        "batch64": batch64,
+        "group": group,
+        "cpu_baseline": cpu_baseline_single_core(img, w, h, a.quality) if world == 1 and not a.no_cpu_baseline else None,
     }
     emit(json.dumps(line))
     if dist is not None:
@@ -496,17 +541,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", default="1024x1024", type=lambda s: tuple(int(v) for v in s.lower().split("x")))
-    ap.add_argument("--quality", type=float, default=90.0)
+    ap.add_argument("--size", default="4000x3000", type=lambda s: tuple(int(v) for v in s.lower().split("x")))
+    ap.add_argument("--quality", type=float, default=95.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-concurrent", action="store_true", help="skip the extra 3-images-in-flight throughput measurement")
-    ap.add_argument("--inflight", type=int, default=1,
-                    help="batch mode: images encoded concurrently per GPU (one host thread group + one device context "
-                         "each); a step is then a batch of that many images per GPU. Default 1 = one image per step")
-    ap.add_argument("--mode", default="batch", choices=["batch", "group", "butteraugli"],
-                    help="batch: one image per GPU (BASELINE configs[1]/[3]); group: one image shared by all GPUs "
-                         "(configs[2]); butteraugli: standalone Compare sweep + quality sweep (configs[4])")
+    ap.add_argument("--no-extras", action="store_true", help="skip the batch64 (configs[3]) and group (configs[2]) measurements")
+    ap.add_argument("--mode", default="batch", choices=["batch", "butteraugli"],
+                    help="batch: one image per GPU per step (the headline); butteraugli: standalone Compare sweep + "
+                         "quality sweep (configs[4])")
     a = ap.parse_args()
+    if os.environ.get("GZB_BENCH_WATCHDOG"):   # debugging aid: dump the Python stacks if the run takes this many seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["GZB_BENCH_WATCHDOG"]), repeat=False, file=sys.stderr)
     guard_stdout()
     rank, world, local = dist_env()
     if a.impl == "reference":

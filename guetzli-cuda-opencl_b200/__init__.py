@@ -341,6 +341,20 @@ def DiffmapOpsinDynamicsImage(xyb0, xyb1, device=0):
     return out
 
 
+def Mask(xyb0, xyb1, device=0):
+    """cuMask (butteraugli::Mask): two [3,H,W] XYB images -> (mask [3,H,W], mask_dc [3,H,W])."""
+    a = np.ascontiguousarray(xyb0, np.float32)
+    b = np.ascontiguousarray(xyb1, np.float32)
+    _, h, w = a.shape
+    m = np.zeros((3, h, w), np.float32)
+    d = np.zeros((3, h, w), np.float32)
+    L = lib()
+    L.gzb_mask.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_size_t, C.c_size_t] + [C.c_void_p] * 6
+    _check(L.gzb_mask(device, _p(m[0]), _p(m[1]), _p(m[2]), _p(d[0]), _p(d[1]), _p(d[2]), w, h,
+                      _p(a[0]), _p(a[1]), _p(a[2]), _p(b[0]), _p(b[1]), _p(b[2])))
+    return m, d
+
+
 def Blur(plane, sigma, border_ratio=0.0, device=0):
     a = np.ascontiguousarray(plane, np.float32).copy()
     h, w = a.shape
@@ -387,6 +401,15 @@ def ButteraugliScoreForQuality(quality):
     L.gzb_butteraugli_score_for_quality.restype = C.c_double
     L.gzb_butteraugli_score_for_quality.argtypes = [C.c_double]
     return L.gzb_butteraugli_score_for_quality(float(quality))
+
+
+def MeasureFp64Peak(device=0):
+    """Non-FMA FP64 peak of the device in Gflop/s (gzb_measure_fp64_peak)."""
+    g = C.c_double()
+    L = lib()
+    L.gzb_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    _check(L.gzb_measure_fp64_peak(device, C.byref(g)))
+    return float(g.value)
 
 
 def Process(rgb, butteraugli_target, device=0, host_threads=0, want_trace=False, try_420=False, force_420=False):

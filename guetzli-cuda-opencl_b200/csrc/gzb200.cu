@@ -418,6 +418,8 @@ struct gzb_ctx {
     unsigned int* hist = nullptr;      // [48 + 768]
     unsigned* flag = nullptr;
     int select_grid = 0;
+    BeRange h_stack[kBeStack];         // host copy of the pending ranges after the last select
+    int h_top = 0;
     unsigned long long n = 0;          // entries of the current order
     unsigned long long selects = 0, levels = 0, host_ranges = 0;
   } be;
@@ -1695,10 +1697,8 @@ void be_reserve(gzb_ctx* c, int num_blocks, size_t total) {
   B.lpos = reinterpret_cast<unsigned*>(base + o_lp);
   B.rpos = reinterpret_cast<unsigned*>(base + o_rp);
   if (B.select_grid == 0) {
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_be_select, kBeThreads, 0));
     static const int want = getenv("GZB_BE_CTAS_PER_SM") ? atoi(getenv("GZB_BE_CTAS_PER_SM")) : 2;
-    B.select_grid = c->sm_count * std::max(1, std::min(per_sm, want));
+    B.select_grid = c->sm_count * std::max(1, std::min(8, want));
   }
 }
 char* be_pinned(gzb_ctx* c) { return static_cast<char*>(c->slab.be_pinned); }
@@ -1777,6 +1777,7 @@ int gzb_be_build_order(gzb_ctx* c, int direction, double target_mul, float below
     if (hs[0] > 0) break;
   }
   B.n = hs[0];
+  B.h_top = 0;   // one pending range [0, n): gzb_be_select falls back to n
   *n = hs[0];
   *blocks_to_change = static_cast<int>(hs[1]);
   *below = hs[2];
@@ -1791,19 +1792,42 @@ int gzb_be_select(gzb_ctx* c, uint64_t p_set, int small_max, int* status, uint64
   gzb_ctx::Backend& B = c->be;
   if (!B.active) return fail(c, GZB_ERR_STATE, "gzb_be_select: gzb_be_begin not called");
   if (!status || !first || !last || !depth || small_max < 16 || small_max > kBeSmallMax) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_select: bad argument");
-  KLAUNCH(c, KC_MISC, k_be_select_args<<<1, 1, 0, c->stream>>>(B.st, static_cast<unsigned>(std::min<uint64_t>(p_set, B.n)), static_cast<unsigned>(small_max)));
-  {
-    BeEntry* a = B.order; unsigned* lp = B.lpos; unsigned* rp = B.rpos; unsigned* tl = B.tcl; unsigned* tr = B.tcr;
-    BeState* st = B.st; BeEntry* sm = B.small;
-    void* args[] = {&a, &lp, &rp, &tl, &tr, &st, &sm};
-    KLAUNCH(c, KC_MISC, CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k_be_select), dim3(B.select_grid), dim3(kBeThreads), args, 0, c->stream)));
-  }
+  const unsigned pset = static_cast<unsigned>(std::min<uint64_t>(p_set, B.n));
+  KLAUNCH(c, KC_MISC, k_be_select_begin<<<1, 1, 0, c->stream>>>(B.order, B.st, pset, static_cast<unsigned>(small_max)));
   const size_t bytes = sizeof(BeState) + sizeof(BeEntry) * static_cast<size_t>(small_max);
   BeState* hst = reinterpret_cast<BeState*>(be_pinned(c) + kBePinState);
-  CK(cudaMemcpyAsync(hst, B.st, bytes, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += bytes;
-  sync_check(c);
+  // Length of the range the sort will work on first, from the host's copy of the pending ranges: a long range
+  // needs about log2(length / kBeLocalMax) grid-level partitions before one CTA can take over. The kernels of a
+  // level return at once when no long range is in flight, so a wrong guess only costs empty launches or one
+  // more round trip.
+  size_t len = B.n;
+  for (int i = B.h_top - 1; i >= 0; --i) {
+    if (B.h_stack[i].last <= pset) continue;
+    len = B.h_stack[i].last - B.h_stack[i].first;
+    break;
+  }
+  const int G = B.select_grid;
+  for (;;) {
+    int levels = 0;
+    for (size_t l = len; l > kBeLocalMax; l >>= 1) ++levels;
+    if (levels > 0) levels += 2;
+    for (int l = 0; l < levels; ++l) {
+      KLAUNCH(c, KC_MISC, k_be_tiles_count<<<G, kBeThreads, 0, c->stream>>>(B.order, B.tcl, B.tcr, B.st));
+      KLAUNCH(c, KC_MISC, k_be_tiles_scan<<<1, kBeThreads, 0, c->stream>>>(B.order, B.tcl, B.tcr, B.st));
+      KLAUNCH(c, KC_MISC, k_be_tiles_lists<<<G, kBeThreads, 0, c->stream>>>(B.order, B.lpos, B.rpos, B.tcl, B.tcr, B.st));
+      KLAUNCH(c, KC_MISC, k_be_swap<<<G, kBeThreads, 0, c->stream>>>(B.order, B.lpos, B.rpos, B.st));
+      KLAUNCH(c, KC_MISC, k_be_finalize<<<1, 1, 0, c->stream>>>(B.order, B.lpos, B.rpos, B.st));
+    }
+    KLAUNCH(c, KC_MISC, k_be_local<<<1, kBeThreads, 0, c->stream>>>(B.order, B.lpos, B.rpos, B.tcl, B.tcr, B.st, B.small));
+    CK(cudaMemcpyAsync(hst, B.st, bytes, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += bytes;
+    sync_check(c);
+    if (hst->status != BE_RUNNING) break;
+    len = std::max<size_t>(static_cast<size_t>(hst->last - hst->first), 4 * static_cast<size_t>(kBeLocalMax));   // a long range is still in flight
+  }
   ++B.selects;
   B.levels += hst->levels;
+  B.h_top = std::max(0, std::min(hst->top, kBeStack));
+  memcpy(B.h_stack, hst->stack, sizeof(BeRange) * B.h_top);
   *status = hst->status;
   if (hst->status == BE_EMPTY || hst->top <= 0) {
     *status = BE_EMPTY;
@@ -1979,6 +2003,7 @@ int gzb_be_test_load_order(gzb_ctx* c, const gzb_order_entry* entries, size_t n)
   B.num_blocks = c->nblocks;
   B.total = 0;
   B.n = n;
+  B.h_top = 0;
   CK(cudaMemsetAsync(B.st, 0, sizeof(BeState), c->stream));
   CK(cudaMemcpyAsync(B.order, entries, n * 8, cudaMemcpyHostToDevice, c->stream));
   const unsigned nn = static_cast<unsigned>(n);
@@ -1986,6 +2011,40 @@ int gzb_be_test_load_order(gzb_ctx* c, const gzb_order_entry* entries, size_t n)
   KLAUNCH(c, KC_MISC, k_be_sort_begin<<<1, 1, 0, c->stream>>>(B.st));
   sync_check(c);
   GZB_END(c)
+}
+
+// Non-FMA FP64 peak of the device in Gflop/s (DADD + DMUL issued back to back on all SMs): the
+// denominator for the FP64 rate of the search kernels, which are built with -fmad=false.
+int gzb_measure_fp64_peak(int device, double* gflops) {
+  if (!gflops) return fail(nullptr, GZB_ERR_BAD_ARG, "gzb_measure_fp64_peak: null argument");
+  try {
+    CK(cudaSetDevice(device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int ctas = sms * 8, iters = 8192;
+    double* d = nullptr;
+    dmalloc(&d, static_cast<size_t>(ctas) * 256);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {   // first repetition warms up (clocks, instruction cache)
+      CK(cudaEventRecord(e0, nullptr));
+      k_fp64_peak<<<ctas, 256>>>(d, iters, 1.0000001, 1e-9);
+      CK(cudaEventRecord(e1, nullptr));
+      CK(cudaEventSynchronize(e1));
+      CK(cudaGetLastError());
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double flops = static_cast<double>(ctas) * 256 * iters * 16.0;
+      if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *gflops = best;
+  } catch (const std::string& e) { return fail(nullptr, GZB_ERR_CUDA, e); }
+  return GZB_OK;
 }
 
 // ---- YUV 4:2:0 ---------------------------------------------------------------------------------
@@ -2233,6 +2292,58 @@ int gzb_diffmap_opsin_dynamics_image(int device, float* result, const float* r, 
     CK(cudaMemcpy2DAsync(result, c->W * sizeof(float), c->d_diffmap, c->P * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (static_cast<unsigned long long>(c->W * sizeof(float)) * (c->H));
     sync_check(c);
   } catch (const std::string& e) { rc = fail(nullptr, GZB_ERR_CUDA, e); }
+  free_ctx(c);
+  return rc;
+}
+
+// butteraugli::Mask (butteraugli.cc:1505-1566) as a standalone stage: the cuMask hook of the reference
+// (clguetzli/cuguetzli.h:42-47, dispatched from clbutter_comparator.cpp:1651-1666). Host planes in and out.
+int gzb_mask(int device, float* mask_r, float* mask_g, float* mask_b, float* maskdc_r, float* maskdc_g, float* maskdc_b,
+             size_t xsize, size_t ysize, const float* r, const float* g, const float* b, const float* r2, const float* g2,
+             const float* b2) {
+  if (!mask_r || !mask_g || !mask_b || !maskdc_r || !maskdc_g || !maskdc_b || !r || !g || !b || !r2 || !g2 || !b2)
+    return fail(nullptr, GZB_ERR_BAD_ARG, "gzb_mask: null plane");
+  if (xsize < 32 || ysize < 32) return fail(nullptr, GZB_ERR_TOO_SMALL, "gzb_mask: image smaller than 32x32");
+  if (xsize >= (1u << 16) || ysize >= (1u << 16)) return fail(nullptr, GZB_ERR_BAD_ARG, "gzb_mask: image too large");
+  gzb_ctx* c = alloc_ctx(device, static_cast<int>(xsize), static_cast<int>(ysize), 1.0f);
+  if (!c) return GZB_ERR_CUDA;
+  int rc = GZB_OK;
+  BlurPlan pl[3];
+  float* lat[3] = {nullptr, nullptr, nullptr};
+  try {
+    const int W = c->W, H = c->H, P = c->P;
+    const float* s0[3] = {r, g, b};
+    const float* s1[3] = {r2, g2, b2};
+    for (int k = 0; k < 3; ++k) {
+      CK(cudaMemcpy2DAsync(c->d_xyb0 + k * c->ps, P * sizeof(float), s0[k], W * sizeof(float), W * sizeof(float), H, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpy2DAsync(c->d_xyb1 + k * c->ps, P * sizeof(float), s1[k], W * sizeof(float), W * sizeof(float), H, cudaMemcpyHostToDevice, c->stream));
+      c->h2d_bytes += 2ull * W * sizeof(float) * H;
+    }
+    // DiffPrecompute + Average5x5 + MinSquareVal -> d_bl[0..2]; then the three blurs on their full decimated lattices
+    dim3 blk(32, 8), grd((W + 31) / 32, (H + 31) / 32, 3);
+    KLAUNCH(c, KC_MASK_FRONT, k_mask_front<<<grd, blk, 0, c->stream>>>(c->d_xyb0, c->d_xyb1, c->ps, W, H, P, c->d_bl, kAllDirty));
+    const int kinds[3] = {kB9657, kB14264, kB4533};
+    MaskSample ms;
+    for (int k = 0; k < 3; ++k) {
+      pl[k].build_decimated(g_hk[kinds[k]], kinds[k], W, H, P, 0.0, 1);
+      pl[k].upload_own();
+      dmalloc(&lat[k], pl[k].out_floats());
+      run_blur(c, pl[k], c->d_bl + k * c->ps, 0, 1, lat[k], 0, pl[k].g.tmp_pitch);
+      ms.m[k] = lat[k];
+      ms.pitch[k] = pl[k].g.tmp_pitch;
+      ms.x0[k] = pl[k].g.x0; ms.sx[k] = pl[k].g.sx; ms.y0[k] = pl[k].g.y0; ms.sy[k] = pl[k].g.sy;
+    }
+    // the six output planes reuse the MaskHighIntensityChange planes
+    dim3 gpx((W + 31) / 32, (H + 7) / 8);
+    KLAUNCH(c, KC_COMBINE, k_mask_full<<<gpx, blk, 0, c->stream>>>(ms, W, H, P, c->d_mh, c->d_mh + 3 * c->ps, c->ps));
+    float* outs[6] = {mask_r, mask_g, mask_b, maskdc_r, maskdc_g, maskdc_b};
+    for (int k = 0; k < 6; ++k) {
+      CK(cudaMemcpy2DAsync(outs[k], W * sizeof(float), c->d_mh + k * c->ps, P * sizeof(float), W * sizeof(float), H, cudaMemcpyDeviceToHost, c->stream));
+      c->d2h_bytes += static_cast<unsigned long long>(W) * sizeof(float) * H;
+    }
+    sync_check(c);
+  } catch (const std::string& e) { rc = fail(nullptr, GZB_ERR_CUDA, e); }
+  for (int k = 0; k < 3; ++k) { if (lat[k]) cudaFree(lat[k]); pl[k].release(); }
   free_ctx(c);
   return rc;
 }

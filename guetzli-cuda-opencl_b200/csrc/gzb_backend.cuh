@@ -9,8 +9,8 @@
 //
 //   k_be_count / k_scan_counts / k_be_fill : the order, in the reference's block-major arrangement
 //       (processor.cc:786-813), values (err - max_err) / weight in IEEE float like the host code;
-//   k_be_select : ONE persistent cooperative kernel that evaluates libstdc++'s introsort
-//       (std::sort = __introsort_loop + __final_insertion_sort) lazily: it runs the library's
+//   k_be_tiles_* / k_be_swap / k_be_finalize / k_be_local : libstdc++'s introsort
+//       (std::sort = __introsort_loop + __final_insertion_sort) evaluated lazily: they run the library's
 //       median-of-three + unguarded Hoare partition steps -- the same element swaps, so that ties
 //       between blocks end up exactly where std::sort puts them -- only on the ranges that straddle
 //       p, postponing every right-hand range on a device-side stack, until the straddling range is
@@ -75,27 +75,12 @@ struct BeState {
   int depth;
   float pv;
   unsigned ntiles, NL, NR, K;
-  unsigned barrier;           // grid barrier ticket counter
-  unsigned pad0;
+  unsigned pad0, pad1;
   BeRange stack[kBeStack];
 };
 
 __device__ __forceinline__ BeEntry be_ld(const BeEntry* p) { return __ldcg(p); }
 __device__ __forceinline__ void be_st(BeEntry* p, BeEntry v) { __stcg(p, v); }
-
-// Grid-wide barrier for a cooperative launch (all CTAs resident): a monotone ticket counter, each
-// barrier adds gridDim.x tickets; __threadfence on both sides orders the data of the phases.
-__device__ __forceinline__ void be_grid_sync(unsigned* bar) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned ticket = atomicAdd(bar, 1u);
-    const unsigned target = (ticket / gridDim.x + 1u) * gridDim.x;
-    while (*reinterpret_cast<volatile unsigned*>(bar) < target) { }
-    __threadfence();
-  }
-  __syncthreads();
-}
 
 // std::__move_median_to_first(first, first + 1, mid, last - 1) with comp(a, b) = a.second < b.second.
 __device__ inline void be_median_to_first(BeEntry* a, unsigned first, unsigned last) {
@@ -139,114 +124,129 @@ __device__ inline void be_next_range(BeState* st, BeEntry* a) {
   }
 }
 
-// Barrier between the phases of a partition: the whole grid, or -- for a range short enough for one
-// CTA -- only the block (the other CTAs wait at the grid barrier of the main loop meanwhile).
-template <bool LOCAL>
-__device__ __forceinline__ void be_phase_sync(BeState* st) {
-  if (LOCAL) { __threadfence_block(); __syncthreads(); }
-  else be_grid_sync(&st->barrier);
+// ---- one std::__unguarded_partition_pivot of the range in *st (pivot already at `first`) -----------
+// Five phases with a grid-wide dependency between them. A long range runs them as five launches on a
+// grid of CTAs (k_be_tiles_count .. k_be_finalize); a range of at most kBeLocalMax entries runs all of
+// them inside ONE CTA (k_be_local), which keeps going level after level while the ranges stay short.
+// No kernel ever waits for another CTA, so any number of contexts can sort concurrently.
+struct BeLevel {
+  unsigned first, last, m, ntiles;
+  float pv;
+  BeEntry* A;   // a + first + 1: the entries the two scans walk
+};
+__device__ __forceinline__ BeLevel be_level(BeEntry* a, const BeState* st) {
+  const volatile BeState* v = st;
+  BeLevel L;
+  L.first = v->first; L.last = v->last; L.pv = v->pv; L.ntiles = v->ntiles;
+  L.m = L.last - L.first - 1;
+  L.A = a + L.first + 1;
+  return L;
+}
+// a grid-level partition is in flight (the range is long)?
+__device__ __forceinline__ bool be_grid_level(const BeState* st) {
+  const volatile BeState* v = st;
+  return v->status == BE_RUNNING && v->last - v->first > kBeLocalMax;
 }
 
-// One std::__unguarded_partition_pivot of the range in *st (pivot already at `first`), then the control
-// step that chooses the next range. LOCAL: executed by CTA 0 alone.
-template <bool LOCAL>
-__device__ __forceinline__ void be_partition_level(BeEntry* a, unsigned* lpos, unsigned* rpos, unsigned* tcl, unsigned* tcr,
-                                                   BeState* st, unsigned (*s_cell_l)[8], unsigned (*s_cell_r)[8],
-                                                   unsigned* s_scan, unsigned* s_tile_r) {
+struct BeSmem {
+  unsigned cell_l[8][8], cell_r[8][8];   // [iteration][warp] stopper counts of a tile
+  unsigned scan[kBeThreads];
+  unsigned tile_r;
+};
+
+// phase 1: per-tile stopper counts
+__device__ __forceinline__ void be_phase_count(const BeLevel& L, unsigned tile0, unsigned tile_step, unsigned* tcl, unsigned* tcr, BeSmem& sm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  volatile BeState* vst = st;
-  const unsigned first = vst->first, last = vst->last;
-  const float pv = vst->pv;
-  const unsigned ntiles = vst->ntiles;
-  BeEntry* A = a + first + 1;
-  const unsigned m = last - first - 1;
-  const unsigned tile0 = LOCAL ? 0u : blockIdx.x, tile_step = LOCAL ? 1u : gridDim.x;
-  // ---- phase 1: per-tile stopper counts ----
-  for (unsigned t = tile0; t < ntiles; t += tile_step) {
+  for (unsigned t = tile0; t < L.ntiles; t += tile_step) {
     unsigned nl = 0, nr = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const unsigned i = t * kBeTile + j * kBeThreads + tid;
       bool fl = false, fr = false;
-      if (i < m) {
-        const float v = be_val(be_ld(A + i));
-        fl = !(v < pv);
-        fr = !(pv < v);
+      if (i < L.m) {
+        const float v = be_val(be_ld(L.A + i));
+        fl = !(v < L.pv);
+        fr = !(L.pv < v);
       }
       nl += __popc(__ballot_sync(0xffffffffu, fl));
       nr += __popc(__ballot_sync(0xffffffffu, fr));
     }
-    if (lane == 0) { s_cell_l[0][warp] = nl; s_cell_r[0][warp] = nr; }
+    if (lane == 0) { sm.cell_l[0][warp] = nl; sm.cell_r[0][warp] = nr; }
     __syncthreads();
     if (tid == 0) {
       unsigned sl = 0, sr = 0;
-      for (int w = 0; w < 8; ++w) { sl += s_cell_l[0][w]; sr += s_cell_r[0][w]; }
+      for (int w = 0; w < 8; ++w) { sl += sm.cell_l[0][w]; sr += sm.cell_r[0][w]; }
       __stcg(tcl + t, sl);
       __stcg(tcr + t, sr);
     }
     __syncthreads();
   }
-  be_phase_sync<LOCAL>(st);
-  // ---- phase 2 (CTA 0): tile offsets. tcl[t] <- stoppers left of tile t; tcr[t] <- right stoppers right of tile t ----
-  if (blockIdx.x == 0) {
-    const unsigned per = (ntiles + kBeThreads - 1) / kBeThreads;
-    const unsigned t0 = min(ntiles, tid * per), t1 = min(ntiles, t0 + per);
-    unsigned sl = 0, sr = 0;
-    for (unsigned t = t0; t < t1; ++t) { sl += __ldcg(tcl + t); sr += __ldcg(tcr + t); }
-    // inclusive scans of the per-thread sums (left counts forward, right counts backward)
-    s_scan[tid] = sl;
+}
+
+// phase 2 (one CTA): tile offsets. tcl[t] <- stoppers left of tile t; tcr[t] <- right stoppers right of tile t
+__device__ __forceinline__ void be_phase_scan(const BeLevel& L, unsigned* tcl, unsigned* tcr, BeState* st, BeSmem& sm) {
+  const int tid = threadIdx.x;
+  const unsigned per = (L.ntiles + kBeThreads - 1) / kBeThreads;
+  const unsigned t0 = min(L.ntiles, tid * per), t1 = min(L.ntiles, t0 + per);
+  unsigned sl = 0, sr = 0;
+  for (unsigned t = t0; t < t1; ++t) { sl += __ldcg(tcl + t); sr += __ldcg(tcr + t); }
+  // inclusive scans of the per-thread sums (left counts forward, right counts backward)
+  sm.scan[tid] = sl;
+  __syncthreads();
+  for (int off = 1; off < kBeThreads; off <<= 1) {
+    const unsigned v = tid >= off ? sm.scan[tid - off] : 0;
     __syncthreads();
-    for (int off = 1; off < kBeThreads; off <<= 1) {
-      const unsigned v = tid >= off ? s_scan[tid - off] : 0;
-      __syncthreads();
-      s_scan[tid] += v;
-      __syncthreads();
-    }
-    unsigned runl = s_scan[tid] - sl;
-    const unsigned NL = s_scan[kBeThreads - 1];
-    __syncthreads();
-    s_scan[tid] = sr;
-    __syncthreads();
-    for (int off = 1; off < kBeThreads; off <<= 1) {
-      const unsigned v = tid + off < kBeThreads ? s_scan[tid + off] : 0;
-      __syncthreads();
-      s_scan[tid] += v;
-      __syncthreads();
-    }
-    const unsigned NR = s_scan[0];
-    unsigned runr = s_scan[tid];   // right stoppers in this thread's tiles and everything to their right
-    for (unsigned t = t0; t < t1; ++t) {
-      const unsigned cl = __ldcg(tcl + t), cr = __ldcg(tcr + t);
-      __stcg(tcl + t, runl);
-      runl += cl;
-      runr -= cr;
-      __stcg(tcr + t, runr);
-    }
-    if (tid == 0) { vst->NL = NL; vst->NR = NR; }
+    sm.scan[tid] += v;
     __syncthreads();
   }
-  be_phase_sync<LOCAL>(st);
-  // ---- phase 3: the two stopper lists ----
-  for (unsigned t = tile0; t < ntiles; t += tile_step) {
+  unsigned runl = sm.scan[tid] - sl;
+  const unsigned NL = sm.scan[kBeThreads - 1];
+  __syncthreads();
+  sm.scan[tid] = sr;
+  __syncthreads();
+  for (int off = 1; off < kBeThreads; off <<= 1) {
+    const unsigned v = tid + off < kBeThreads ? sm.scan[tid + off] : 0;
+    __syncthreads();
+    sm.scan[tid] += v;
+    __syncthreads();
+  }
+  const unsigned NR = sm.scan[0];
+  unsigned runr = sm.scan[tid];   // right stoppers in this thread's tiles and everything to their right
+  for (unsigned t = t0; t < t1; ++t) {
+    const unsigned cl = __ldcg(tcl + t), cr = __ldcg(tcr + t);
+    __stcg(tcl + t, runl);
+    runl += cl;
+    runr -= cr;
+    __stcg(tcr + t, runr);
+  }
+  if (tid == 0) { st->NL = NL; st->NR = NR; }
+  __syncthreads();
+}
+
+// phase 3: the two stopper lists
+__device__ __forceinline__ void be_phase_lists(const BeLevel& L, unsigned tile0, unsigned tile_step, const unsigned* tcl, const unsigned* tcr,
+                                               unsigned* lpos, unsigned* rpos, BeSmem& sm) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (unsigned t = tile0; t < L.ntiles; t += tile_step) {
     unsigned bl[8], br[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const unsigned i = t * kBeTile + j * kBeThreads + tid;
       bool fl = false, fr = false;
-      if (i < m) {
-        const float v = be_val(be_ld(A + i));
-        fl = !(v < pv);
-        fr = !(pv < v);
+      if (i < L.m) {
+        const float v = be_val(be_ld(L.A + i));
+        fl = !(v < L.pv);
+        fr = !(L.pv < v);
       }
       bl[j] = __ballot_sync(0xffffffffu, fl);
       br[j] = __ballot_sync(0xffffffffu, fr);
-      if (lane == 0) { s_cell_l[j][warp] = __popc(bl[j]); s_cell_r[j][warp] = __popc(br[j]); }
+      if (lane == 0) { sm.cell_l[j][warp] = __popc(bl[j]); sm.cell_r[j][warp] = __popc(br[j]); }
     }
     __syncthreads();
     // exclusive scan of the 64 cells in index order (iteration-major, then warp): two cells per lane of warp 0
     if (warp == 0) {
-      unsigned* cl = &s_cell_l[0][0];
-      unsigned* cr = &s_cell_r[0][0];
+      unsigned* cl = &sm.cell_l[0][0];
+      unsigned* cr = &sm.cell_r[0][0];
       const unsigned l0 = cl[2 * lane], l1 = cl[2 * lane + 1], r0 = cr[2 * lane], r1 = cr[2 * lane + 1];
       unsigned sl = l0 + l1, sr = r0 + r1;
 #pragma unroll
@@ -256,94 +256,111 @@ __device__ __forceinline__ void be_partition_level(BeEntry* a, unsigned* lpos, u
       }
       cl[2 * lane] = sl - l0 - l1; cl[2 * lane + 1] = sl - l1;
       cr[2 * lane] = sr - r0 - r1; cr[2 * lane + 1] = sr - r1;
-      if (lane == 31) *s_tile_r = sr;   // right stoppers in the tile
+      if (lane == 31) sm.tile_r = sr;   // right stoppers in the tile
     }
     __syncthreads();
     const unsigned base_l = __ldcg(tcl + t);
     // right stoppers of this tile take ranks [tcr[t], tcr[t] + tile_r) counted from the right
-    const unsigned base_r = __ldcg(tcr + t), tile_r = *s_tile_r;
+    const unsigned base_r = __ldcg(tcr + t), tile_r = sm.tile_r;
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const unsigned i = t * kBeTile + j * kBeThreads + tid;
-      if (bl[j] >> lane & 1u) __stcg(lpos + base_l + s_cell_l[j][warp] + __popc(bl[j] & lt), i);
+      if (bl[j] >> lane & 1u) __stcg(lpos + base_l + sm.cell_l[j][warp] + __popc(bl[j] & lt), i);
       if (br[j] >> lane & 1u) {
-        const unsigned asc = s_cell_r[j][warp] + __popc(br[j] & lt);   // rank from the left inside the tile
+        const unsigned asc = sm.cell_r[j][warp] + __popc(br[j] & lt);   // rank from the left inside the tile
         __stcg(rpos + base_r + (tile_r - 1u - asc), i);
       }
     }
     __syncthreads();
   }
-  be_phase_sync<LOCAL>(st);
-  // ---- phase 4: the swaps. Pair k is swapped iff lpos[k] < rpos[k] (monotone in k); K = their number ----
-  {
-    const unsigned NL = vst->NL, NR = vst->NR;
-    const unsigned lim = min(NL, NR);
-    unsigned cnt = 0;
-    const unsigned k0 = LOCAL ? tid : blockIdx.x * kBeThreads + tid, kstep = LOCAL ? kBeThreads : gridDim.x * kBeThreads;
-    for (unsigned k = k0; k < lim; k += kstep) {
-      const unsigned l = __ldcg(lpos + k), r = __ldcg(rpos + k);
-      if (!(l < r)) break;
-      const BeEntry el = be_ld(A + l), er = be_ld(A + r);
-      be_st(A + l, er);
-      be_st(A + r, el);
-      ++cnt;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-    if (lane == 0 && cnt) atomicAdd(&st->K, cnt);
-  }
-  be_phase_sync<LOCAL>(st);
-  // ---- phase 5 (one thread): the cut, the two new ranges, the next pivot ----
-  if (blockIdx.x == 0 && tid == 0) {
-    const unsigned K = vst->K, NL = vst->NL;
-    unsigned cut = m;   // the scans are guarded by the median-of-three: a stopper exists
-    if (K < NL) cut = min(cut, __ldcg(lpos + K));
-    if (K > 0) cut = min(cut, __ldcg(rpos + K - 1));
-    const unsigned gcut = first + 1 + cut;
-    const int depth = vst->depth;
-    st->stack[st->top++] = BeRange{gcut, last, depth, 0};
-    st->stack[st->top++] = BeRange{first, gcut, depth, 0};
-    be_next_range(st, a);
-    __threadfence();
-  }
 }
 
-// Lazy introsort: see the file header. Cooperative launch, gridDim.x CTAs of kBeThreads threads.
-//   a     : the order (n entries)
-//   lpos  : scratch, n words: positions (relative to first + 1) of the entries that stop the left scan
-//   rpos  : scratch, n words: ... that stop the right scan, rpos[k] = k-th from the right
-//   tcl / tcr : scratch, per-tile counts, then tile offsets (ceil(n / kBeTile) + 1 words each)
-//   small : receives the entries of the short range the kernel stops at (status BE_SMALL)
+// phase 4: the swaps. Pair k is swapped iff lpos[k] < rpos[k] (monotone in k); K = their number
+__device__ __forceinline__ void be_phase_swap(const BeLevel& L, unsigned k0, unsigned kstep, const unsigned* lpos, const unsigned* rpos, BeState* st) {
+  const volatile BeState* v = st;
+  const unsigned lim = min(v->NL, v->NR);
+  unsigned cnt = 0;
+  for (unsigned k = k0; k < lim; k += kstep) {
+    const unsigned l = __ldcg(lpos + k), r = __ldcg(rpos + k);
+    if (!(l < r)) break;
+    const BeEntry el = be_ld(L.A + l), er = be_ld(L.A + r);
+    be_st(L.A + l, er);
+    be_st(L.A + r, el);
+    ++cnt;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&st->K, cnt);
+}
+
+// phase 5 (one thread): the cut, the two new ranges, the next pivot
+__device__ __forceinline__ void be_phase_finalize(const BeLevel& L, BeEntry* a, const unsigned* lpos, const unsigned* rpos, BeState* st) {
+  const volatile BeState* v = st;
+  const unsigned K = v->K, NL = v->NL;
+  unsigned cut = L.m;   // the scans are guarded by the median-of-three: a stopper exists
+  if (K < NL) cut = min(cut, __ldcg(lpos + K));
+  if (K > 0) cut = min(cut, __ldcg(rpos + K - 1));
+  const unsigned gcut = L.first + 1 + cut;
+  const int depth = v->depth;
+  st->stack[st->top++] = BeRange{gcut, L.last, depth, 0};
+  st->stack[st->top++] = BeRange{L.first, gcut, depth, 0};
+  be_next_range(st, a);
+}
+
 __global__ void __launch_bounds__(kBeThreads)
-k_be_select(BeEntry* a, unsigned* lpos, unsigned* rpos, unsigned* tcl, unsigned* tcr, BeState* st, BeEntry* small) {
-  __shared__ unsigned s_cell_l[8][8], s_cell_r[8][8];   // [iteration][warp] stopper counts of a tile
-  __shared__ unsigned s_scan[kBeThreads];
-  __shared__ unsigned s_tile_r;
+k_be_tiles_count(BeEntry* a, unsigned* tcl, unsigned* tcr, BeState* st) {
+  __shared__ BeSmem sm;
+  if (!be_grid_level(st)) return;
+  be_phase_count(be_level(a, st), blockIdx.x, gridDim.x, tcl, tcr, sm);
+}
+__global__ void __launch_bounds__(kBeThreads)
+k_be_tiles_scan(BeEntry* a, unsigned* tcl, unsigned* tcr, BeState* st) {
+  __shared__ BeSmem sm;
+  if (!be_grid_level(st)) return;
+  be_phase_scan(be_level(a, st), tcl, tcr, st, sm);
+}
+__global__ void __launch_bounds__(kBeThreads)
+k_be_tiles_lists(BeEntry* a, unsigned* lpos, unsigned* rpos, const unsigned* tcl, const unsigned* tcr, BeState* st) {
+  __shared__ BeSmem sm;
+  if (!be_grid_level(st)) return;
+  be_phase_lists(be_level(a, st), blockIdx.x, gridDim.x, tcl, tcr, lpos, rpos, sm);
+}
+__global__ void __launch_bounds__(kBeThreads)
+k_be_swap(BeEntry* a, const unsigned* lpos, const unsigned* rpos, BeState* st) {
+  if (!be_grid_level(st)) return;
+  be_phase_swap(be_level(a, st), blockIdx.x * kBeThreads + threadIdx.x, gridDim.x * kBeThreads, lpos, rpos, st);
+}
+__global__ void k_be_finalize(BeEntry* a, const unsigned* lpos, const unsigned* rpos, BeState* st) {
+  if (!be_grid_level(st)) return;
+  be_phase_finalize(be_level(a, st), a, lpos, rpos, st);
+}
+
+// Short ranges: one CTA partitions level after level for as long as the ranges stay short, then -- if the
+// sort has stopped at a range for the host -- copies that range out.
+//   small : receives the entries of the short range the sort stops at (status BE_SMALL)
+__global__ void __launch_bounds__(kBeThreads)
+k_be_local(BeEntry* a, unsigned* lpos, unsigned* rpos, unsigned* tcl, unsigned* tcr, BeState* st, BeEntry* small) {
+  __shared__ BeSmem sm;
   const int tid = threadIdx.x;
   volatile BeState* vst = st;
-  if (blockIdx.x == 0 && tid == 0) { st->levels = 0; be_next_range(st, a); __threadfence(); }
-  for (;;) {
-    be_grid_sync(&st->barrier);
-    if (vst->status != BE_RUNNING) break;
-    if (vst->last - vst->first <= kBeLocalMax) {
-      // short ranges: CTA 0 partitions on its own for as long as they stay short, the rest of the grid waits above
-      if (blockIdx.x == 0) {
-        do {
-          be_partition_level<true>(a, lpos, rpos, tcl, tcr, st, s_cell_l, s_cell_r, s_scan, &s_tile_r);
-          __syncthreads();
-        } while (vst->status == BE_RUNNING && vst->last - vst->first <= kBeLocalMax);
-      }
-      continue;
-    }
-    be_partition_level<false>(a, lpos, rpos, tcl, tcr, st, s_cell_l, s_cell_r, s_scan, &s_tile_r);
+  while (vst->status == BE_RUNNING && vst->last - vst->first <= kBeLocalMax) {
+    const BeLevel L = be_level(a, st);
+    be_phase_count(L, 0, 1, tcl, tcr, sm);
+    __threadfence_block(); __syncthreads();
+    be_phase_scan(L, tcl, tcr, st, sm);
+    __threadfence_block(); __syncthreads();
+    be_phase_lists(L, 0, 1, tcl, tcr, lpos, rpos, sm);
+    __threadfence_block(); __syncthreads();
+    be_phase_swap(L, tid, kBeThreads, lpos, rpos, st);
+    __threadfence_block(); __syncthreads();
+    if (tid == 0) { be_phase_finalize(L, a, lpos, rpos, st); __threadfence_block(); }
+    __syncthreads();
   }
-  // the short range the host finishes
-  if (blockIdx.x == 0 && vst->status == BE_SMALL) {
+  if (vst->status == BE_SMALL) {
     const BeRange r = st->stack[st->top - 1];
     for (unsigned i = tid; i < r.last - r.first; i += kBeThreads) small[i] = be_ld(a + r.first + i);
   }
-  if (blockIdx.x == 0 && tid == 0) st->levels_total += st->levels;
 }
 
 // ---- the order ---------------------------------------------------------------------------------
@@ -413,10 +430,12 @@ __global__ void k_be_sort_begin(BeState* st) {
   }
 }
 
-__global__ void k_be_select_args(BeState* st, unsigned p_set, unsigned small_max) {
+// starts a gzb_be_select: the parameters, then the first control step
+__global__ void k_be_select_begin(BeEntry* a, BeState* st, unsigned p_set, unsigned small_max) {
   st->p_set = p_set;
   st->small_max = small_max;
-  st->barrier = 0;
+  st->levels = 0;
+  be_next_range(st, a);
 }
 
 // ---- the prefix, consumed as a set ---------------------------------------------------------------

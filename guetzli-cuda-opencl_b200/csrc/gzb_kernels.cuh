@@ -1042,6 +1042,23 @@ __global__ void k_block_mask_scale(MaskSample ms, int bw, int bh, float* __restr
   for (int c = 0; c < 3; ++c) out[3 * b + c] = static_cast<float>(mask[c]);
 }
 
+// The full-resolution mask / mask_dc planes of butteraugli::Mask (butteraugli.cc:1505-1566), for the
+// standalone gzb_mask entry point only: the Compare pipeline never materialises them (k_combine looks
+// the tables up at the one pixel per res cell it needs).
+__global__ void __launch_bounds__(256)
+k_mask_full(MaskSample ms, int W, int H, int P, float* __restrict__ mask, float* __restrict__ mask_dc, size_t stride) {
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  double m[3], d[3];
+  mask_at(ms, x, y, m, d, true);
+  const size_t o = static_cast<size_t>(y) * P + x;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    mask[c * stride + o] = static_cast<float>(m[c]);
+    mask_dc[c * stride + o] = static_cast<float>(d[c]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K10: tail of CalculateDiffmap (butteraugli.cc:1009-1043) + score (1233-1240):
 //   diffmap = (up + 24.82f * blur(up_crop)) * 1/25.82, max-reduced into *dist_bits.
@@ -1230,6 +1247,23 @@ __global__ void k_pack_candidates(const CoeffRec* __restrict__ order, int nblock
     }
     base += __popc(m);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Measurement aid: the non-FMA double-precision rate of the device. The search kernels are compiled
+// with -fmad=false (the reference's CPU arithmetic has no contraction), so their ceiling is one DADD or
+// DMUL per FP64 lane and clock, not the FMA rate of the data sheet. Eight independent mul/add chains per
+// thread keep the pipe full; `iters` x 16 flops per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_fp64_peak(double* __restrict__ out, int iters, double m, double c) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = a0 * m; a1 = a1 * m; a2 = a2 * m; a3 = a3 * m; a4 = a4 * m; a5 = a5 * m; a6 = a6 * m; a7 = a7 * m;
+    a0 = a0 + c; a1 = a1 + c; a2 = a2 + c; a3 = a3 + c; a4 = a4 + c; a5 = a5 + c; a6 = a6 + c; a7 = a7 + c;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
 }  // namespace gzb

@@ -297,6 +297,12 @@ int gzb_diffmap_opsin_dynamics_image(int device, float* result, const float* r, 
 /* butteraugli::Blur (butteraugli.cc:100-148) / cuBlurEx (clguetzli/cuguetzli.h:73-75). */
 int gzb_blur(int device, float* plane, size_t xsize, size_t ysize, double sigma,
              double border_ratio);
+/* butteraugli::Mask (third_party/butteraugli/butteraugli/butteraugli.cc:1505-1566): replaces cuMask
+ * (clguetzli/cuguetzli.h:42-47; dispatcher clguetzli/clbutter_comparator.cpp:1651-1666). Six XYB planes in
+ * (xsize*ysize floats each), mask and mask_dc planes out. */
+int gzb_mask(int device, float* mask_r, float* mask_g, float* mask_b, float* maskdc_r, float* maskdc_g,
+             float* maskdc_b, size_t xsize, size_t ysize, const float* r, const float* g, const float* b,
+             const float* r2, const float* g2, const float* b2);
 /* Standalone butteraugli of two sRGB8 images (interleaved): distance and optional diffmap. */
 int gzb_butteraugli_srgb(int device, const uint8_t* rgb0, const uint8_t* rgb1, int width,
                          int height, float* distance, float* diffmap_out);
@@ -414,6 +420,10 @@ const char* gzb_profile_name(int i);
 int gzb_profile_get(gzb_ctx* ctx, int i, double* ms, unsigned long long* launches);
 int gzb_profile_reset(gzb_ctx* ctx);
 /* Host->device and device->host bytes moved by this context since creation. */
+/* Measurement aid: the device's double-precision rate WITHOUT fused multiply-add (DADD + DMUL streams on all
+ * SMs), in Gflop/s. The search kernels are built with -fmad=false to match the reference's arithmetic, so this
+ * -- not the data-sheet FMA rate -- is their arithmetic ceiling. */
+int gzb_measure_fp64_peak(int device, double* gflops);
 int gzb_get_transfer_bytes(const gzb_ctx* ctx, unsigned long long* h2d, unsigned long long* d2h);
 
 /* ---- timing of the last call on this context (CUDA events on the context's stream) -------- */

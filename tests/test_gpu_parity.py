@@ -72,6 +72,21 @@ def test_diffmap_opsin_dynamics_image(gz, w, h):
     assert d == want.max()
 
 
+@pytest.mark.parametrize("w,h", [(32, 32), (97, 61), (200, 133), (444, 258)])
+def test_mask(gz, w, h):
+    """gzb_mask == butteraugli::Mask (the cuMask hook): full-resolution mask and mask_dc planes, bit-exact."""
+    img = synth_image(w, h, 11)
+    rng = np.random.default_rng(11)
+    img2 = np.clip(img.astype(np.int32) + rng.integers(-9, 10, img.shape), 0, 255).astype(np.uint8)
+    a = np.zeros((3, h, w), np.float32); b = a.copy()
+    oracle().gzo_srgb_to_xyb(p(img), w, h, p(a)); oracle().gzo_srgb_to_xyb(p(img2), w, h, p(b))
+    want_m = np.zeros((3, h, w), np.float32); want_d = want_m.copy()
+    oracle().gzo_mask(p(a), p(b), w, h, p(want_m), p(want_d))
+    m, d = gz.Mask(a, b)
+    report("mask", m, want_m)
+    report("mask_dc", d, want_d)
+
+
 @pytest.mark.parametrize("w,h,q", [(64, 48, 3), (97, 61, 5), (200, 133, 2), (70, 45, 4)])
 def test_compare_stages(gz, w, h, q):
     img = synth_image(w, h)
