@@ -627,9 +627,10 @@ def QuantSearchSimulate(rank, world, allgather, target, eval_fn, batch=1, mode=0
     EVAL = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_uint64))
 
     def ev(user, original, q, dist_out, size_out):
-        d, sz = eval_fn(bool(original), [q[i] for i in range(192)])
-        dist_out[0] = d
-        size_out[0] = sz
+        r = eval_fn(bool(original), [q[i] for i in range(192)])
+        if r is None:      # the stand-in for a failed GPU trial
+            return 1
+        dist_out[0], size_out[0] = r
         return 0
     ev_c = EVAL(ev)
     cb = make_allgather_callback(allgather, world) if world > 1 else ALLGATHER_FN(0)

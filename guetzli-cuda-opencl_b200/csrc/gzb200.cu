@@ -344,6 +344,7 @@ struct gzb_ctx {
   float target = 0.f;
   float distance = 0.f;
   float last_ms = 0.f;
+  unsigned zeroing_tie_blocks = 0;   // blocks of the last zeroing search whose candidate keys tied (sorted the library's way)
   unsigned long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   Slab slab;
   struct Req { void** pp; size_t bytes; };
@@ -1282,6 +1283,7 @@ static int run_zeroing(gzb_ctx* c, int comp_mask, int mode, int b0 = 0, int b1 =
   const int units = zeroing_units(c, comp_mask);
   if (b1 < 0) b1 = units;
   CK(cudaMemsetAsync(c->d_scalars + 1, 0, sizeof(unsigned int), c->stream));
+  CK(cudaMemsetAsync(c->d_scalars + 3, 0, sizeof(unsigned int), c->stream));   // blocks whose sort keys tie
   if (mode == 0)
     CK(cudaMemsetAsync(c->d_order + 192 * static_cast<size_t>(b0), 0,
                        sizeof(gzb_coeff_data) * 192 * static_cast<size_t>(b1 - b0), c->stream));
@@ -1305,14 +1307,14 @@ static int run_zeroing(gzb_ctx* c, int comp_mask, int mode, int b0 = 0, int b1 =
     const int ctas = std::max(1, std::min(b1 - b0, c->sm_count * 5));
     KLAUNCH(c, KC_ZEROING, k_zeroing_order_mb<<<ctas, 128, 0, c->stream>>>(
         c->d_orig, c->d_coef, cs, c->d_rgb0, c->d_ycc, c->ps, c->P, c->W, c->H, c->bw, c->mcw, b1, c->d_mask_scale,
-        c->target, 3, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_scalars + 1, lpt));
+        c->target, 3, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_scalars + 1, lpt, c->d_scalars + 3));
   } else {
     static const int per_sm = getenv("GZB_ZERO_CTAS_PER_SM") ? atoi(getenv("GZB_ZERO_CTAS_PER_SM")) : 6;   // tuning probe (7 fit; the pipes saturate at 5-6)
     const int ctas = std::max(1, std::min((b1 - b0 + kZeroWarps - 1) / kZeroWarps, c->sm_count * std::max(1, per_sm)));
     KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<ctas, 32 * kZeroWarps, 0, c->stream>>>(
         c->d_orig, c->d_coef, cs, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, b1, c->d_mask_scale, comp_mask,
         c->target, 3, mode, 0, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1, lpt,
-        coef_bw, c->mode420 ? c->d_cup : nullptr));
+        coef_bw, c->mode420 ? c->d_cup : nullptr, c->d_scalars + 3));
   }
   CK(cudaEventRecord(c->ev1, c->stream));
   return 0;
@@ -1356,7 +1358,7 @@ int gzb_compare_block(gzb_ctx* c, int block_x, int block_y, const int16_t* candi
   CK(cudaMemsetAsync(c->d_scalars + 1, 0, sizeof(unsigned int), c->stream));
   KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<1, 32 * kZeroWarps, 0, c->stream>>>(
       d_cand, d_cand, 64, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, 1, c->d_mask_scale, 7, c->target, 3, 2,
-      block_y * c->bw + block_x, 0, nullptr, c->d_block_err, nullptr, c->d_scalars + 1, nullptr, c->bw, nullptr));
+      block_y * c->bw + block_x, 0, nullptr, c->d_block_err, nullptr, c->d_scalars + 1, nullptr, c->bw, nullptr, nullptr));
   CK(cudaMemcpyAsync(c->h_pinned, c->d_block_err, sizeof(float), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 4;
   sync_check(c);
   *err = static_cast<double>(c->h_pinned[0]);
@@ -1410,7 +1412,10 @@ int gzb_compute_block_zeroing_order(gzb_ctx* c, int comp_mask, gzb_coeff_data* o
   run_zeroing(c, comp_mask, 0);
   const size_t nrec = static_cast<size_t>(192) * zeroing_units(c, comp_mask);
   CK(cudaMemcpyAsync(out, c->d_order, sizeof(gzb_coeff_data) * nrec, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += sizeof(gzb_coeff_data) * nrec;
+  unsigned* h_tie = reinterpret_cast<unsigned*>(c->h_pinned) + 1001;   // bytes 4004.. of the pinned page
+  CK(cudaMemcpyAsync(h_tie, c->d_scalars + 3, 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 4;
   sync_check(c);
+  c->zeroing_tie_blocks = *h_tie;
   CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   GZB_END(c)
 }
@@ -1441,7 +1446,10 @@ int gzb_compute_block_zeroing_candidates_range(gzb_ctx* c, int comp_mask, int bl
     c->packed_b1 = block_end;
   }
   CK(cudaMemcpyAsync(offsets, d_offsets, (static_cast<size_t>(nloc) + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (static_cast<size_t>(nloc) + 1) * sizeof(int);
+  unsigned* h_tie = reinterpret_cast<unsigned*>(c->h_pinned) + 1001;   // bytes 4004.. of the pinned page
+  CK(cudaMemcpyAsync(h_tie, c->d_scalars + 3, 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 4;
   sync_check(c);
+  c->zeroing_tie_blocks = *h_tie;
   CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   const size_t n = static_cast<size_t>(offsets[nloc]);
   *n_out = n;
@@ -2201,6 +2209,7 @@ int gzb_get_transfer_bytes(const gzb_ctx* c, unsigned long long* h2d, unsigned l
   if (d2h) *d2h = c->d2h_bytes;
   return GZB_OK;
 }
+unsigned gzb_last_zeroing_tie_blocks(const gzb_ctx* c) { return c ? c->zeroing_tie_blocks : 0; }
 float gzb_last_device_ms(const gzb_ctx* c) { return c ? c->last_ms : 0.f; }
 unsigned long long gzb_launch_count(const gzb_ctx* c) { return c ? c->launches : 0; }
 unsigned long long gzb_incremental_compare_count(const gzb_ctx* c) { return c ? c->incremental_compares : 0; }

@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "../../include/gzb200.h"
+#include "gzb_exact_sort.h"
 #include "gzb_jpeg.h"
 #include "gzb_quant_search.h"
 
@@ -157,75 +158,11 @@ struct OrderLess {
 
 namespace exact_sort {
 
-inline bool less(const OrderEntry& a, const OrderEntry& b) { return a.second < b.second; }
-
-// std::__move_median_to_first(result, a, b, c)
-inline void median_to_first(OrderEntry* result, OrderEntry* a, OrderEntry* b, OrderEntry* c) {
-  if (less(*a, *b)) {
-    if (less(*b, *c)) std::swap(*result, *b);
-    else if (less(*a, *c)) std::swap(*result, *c);
-    else std::swap(*result, *a);
-  } else if (less(*a, *c)) std::swap(*result, *a);
-  else if (less(*b, *c)) std::swap(*result, *c);
-  else std::swap(*result, *b);
-}
-
-// std::__unguarded_partition_pivot(first, last)
-inline OrderEntry* partition_pivot(OrderEntry* first, OrderEntry* last) {
-  OrderEntry* mid = first + (last - first) / 2;
-  median_to_first(first, first + 1, mid, last - 1);
-  const OrderEntry* pivot = first;
-  OrderEntry* lo = first + 1;
-  OrderEntry* hi = last;
-  for (;;) {
-    while (less(*lo, *pivot)) ++lo;
-    --hi;
-    while (less(*pivot, *hi)) --hi;
-    if (!(lo < hi)) return lo;
-    std::swap(*lo, *hi);
-    ++lo;
-  }
-}
-
-// std::__insertion_sort: each element moves left past the strictly greater ones
-inline void insertion_sort(OrderEntry* first, OrderEntry* last) {
-  for (OrderEntry* i = first; i < last; ++i) {
-    const OrderEntry v = *i;
-    OrderEntry* j = i;
-    while (j > first && less(v, *(j - 1))) { *j = *(j - 1); --j; }
-    *j = v;
-  }
-}
-
-// std::__partial_sort(first, last, last): make_heap + sort_heap
-inline void heap_sort(OrderEntry* first, OrderEntry* last) {
-  std::make_heap(first, last, OrderLess());
-  std::sort_heap(first, last, OrderLess());
-}
-
-// std::__introsort_loop(first, last, depth): leaves ranges of at most 16 entries unsorted
-void introsort_loop(OrderEntry* first, OrderEntry* last, int depth) {
-  while (last - first > 16) {
-    if (depth == 0) { heap_sort(first, last); return; }
-    --depth;
-    OrderEntry* cut = partition_pivot(first, last);
-    introsort_loop(cut, last, depth);
-    last = cut;
-  }
-}
-
-// Final arrangement of a range std::sort's partitioning has isolated with `depth` budget left. The
-// library's closing insertion sort never moves an entry across a partition boundary (everything on the
-// left is <= the pivot <= everything on the right, and entries only pass strictly greater ones), so it
-// can be run range by range.
-void finish_range(OrderEntry* first, OrderEntry* last, int depth) {
-  if (last - first > 1) {
-    introsort_loop(first, last, depth);
-    insertion_sort(first, last);
-  }
-}
-
-int depth_budget(size_t n) { int lg = 0; while ((n >> (lg + 1)) != 0) ++lg; return 2 * lg; }
+// the algorithm itself: gzb_exact_sort.h (shared with the device code of the block-zeroing search)
+inline OrderEntry* partition_pivot(OrderEntry* first, OrderEntry* last) { return gzb::xsort::partition_pivot(first, last, OrderLess()); }
+inline void heap_sort(OrderEntry* first, OrderEntry* last) { gzb::xsort::heap_sort(first, last, OrderLess()); }
+inline void finish_range(OrderEntry* first, OrderEntry* last, int depth) { gzb::xsort::finish_range<72>(first, last, depth, OrderLess()); }
+inline int depth_budget(size_t n) { return gzb::xsort::depth_budget(n); }
 
 // One-time check of the restatement against the std::sort of this build on tie-heavy inputs.
 bool emulation_ok() {
@@ -242,6 +179,13 @@ bool emulation_ok() {
       std::sort(b.begin(), b.end(), OrderLess());
       finish_range(a.data(), a.data() + n, depth_budget(n));
       if (a != b) return false;
+      // the heap-sort fallback (depth budget exhausted) against std::partial_sort, which is the same library path
+      std::vector<OrderEntry> c2 = b, d2;
+      for (size_t i = 0; i + 1 < n; i += 2) std::swap(c2[i], c2[n - 1 - i / 2]);
+      d2 = c2;
+      std::partial_sort(d2.begin(), d2.end(), d2.end(), OrderLess());
+      heap_sort(c2.data(), c2.data() + n);
+      if (c2 != d2) return false;
     }
     return true;
   }();
@@ -720,6 +664,14 @@ void gzb_test_exact_sort_split(int* first, float* second, size_t n, size_t small
     pending.push_back({cut, r.last, r.depth});
     pending.push_back({r.first, cut, r.depth});
   }
+  for (size_t i = 0; i < n; ++i) { first[i] = v[i].first; second[i] = v[i].second; }
+}
+// heap path alone, and std::partial_sort(first, last, last) for the checker
+void gzb_test_exact_heap_sort(int* first, float* second, size_t n, int use_std) {
+  std::vector<OrderEntry> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(first[i], second[i]);
+  if (use_std) std::partial_sort(v.begin(), v.end(), v.end(), OrderLess());
+  else exact_sort::heap_sort(v.data(), v.data() + n);
   for (size_t i = 0; i < n; ++i) { first[i] = v[i].first; second[i] = v[i].second; }
 }
 int gzb_test_sort_emulation_ok(void) { return exact_sort::emulation_ok() ? 1 : 0; }

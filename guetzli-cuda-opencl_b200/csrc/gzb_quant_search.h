@@ -271,9 +271,15 @@ class QuantSearch {
     }
     std::vector<TrialOutcome> local(my_trials.size());
     if (!my_trials.empty()) {
-      if (!evaluate(my_trials, &local)) return false;
-      evaluated_here_ += static_cast<int>(my_trials.size());
-      for (size_t j = 0; j < my_trials.size(); ++j) mine[j] = Rec{1, local[j].distance, local[j].jpg_size};
+      // A rank whose evaluation fails still takes part in the exchange below with valid = 0 for its trials:
+      // every rank then sees the missing outcome and leaves together, instead of the others waiting for
+      // this rank inside the collective.
+      if (evaluate(my_trials, &local)) {
+        evaluated_here_ += static_cast<int>(my_trials.size());
+        for (size_t j = 0; j < my_trials.size(); ++j) mine[j] = Rec{1, local[j].distance, local[j].jpg_size};
+      } else if (g_.world == 1) {
+        return false;
+      }
     }
     std::vector<Rec> all(static_cast<size_t>(g_.world) * batch_);
     if (g_.world > 1) {

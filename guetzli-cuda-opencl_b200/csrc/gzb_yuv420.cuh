@@ -379,7 +379,7 @@ k_zeroing_order_mb(const int16_t* __restrict__ orig, const int16_t* __restrict__
                    const uint8_t* __restrict__ rgb_planes, const uint8_t* __restrict__ ycc, size_t plane_stride,
                    int P, int W, int H, int bw, int mcw, int nmb, const float* __restrict__ mask_scale, float limit,
                    int lookahead, int mb_begin, CoeffDataDev* __restrict__ out, unsigned int* __restrict__ counter,
-                   const int* __restrict__ lpt_order) {
+                   const int* __restrict__ lpt_order, unsigned int* __restrict__ tie_counter) {
   __shared__ ZeroMbSmem m;
   __shared__ int s_basis[64];
   const float* s_lut = g_tab.srgb_lin;
@@ -457,16 +457,8 @@ k_zeroing_order_mb(const int16_t* __restrict__ orig, const int16_t* __restrict__
       n += __popc(mk);
     }
     __syncwarp();
-    for (int e = lane; e < n; e += 32) {
-      const float ke = s.key[e];
-      int rank = 0;
-      for (int j = 0; j < n; ++j) {
-        const float kj = s.key[j];
-        rank += (kj < ke || (kj == ke && j < e)) ? 1 : 0;
-      }
-      s.order[rank] = s.ent[e];
-    }
-    __syncwarp();
+    // (every warp of the macro-block orders its private copy; only the first one reports a tie)
+    warp_input_order(s.key, s.ent, n, s.order, reinterpret_cast<ZeroSortPair*>(s.bufA), (threadIdx.x >> 5) == 0 ? tie_counter : nullptr, lane);
     CoeffDataDev* o = out + static_cast<size_t>(mb) * 192;
     int win[3];
     int nwin = min(lookahead, n), next = nwin, nout = 0;

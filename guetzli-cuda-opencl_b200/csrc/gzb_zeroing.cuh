@@ -12,6 +12,7 @@
 #pragma once
 #include "gzb_device_math.cuh"
 #include "gzb_zeroing_model.h"
+#include "gzb_exact_sort.h"
 #include <cstddef>
 
 namespace gzb {
@@ -233,6 +234,48 @@ __device__ __forceinline__ void warp_full_idct(ZeroWarpSmem& s, const int* s_bas
 
 constexpr int kZeroWarps = 4;
 
+// Input order of a block's candidates: ascending key, as std::sort leaves them (processor.cc:410-412).
+// Without equal keys any sort gives that order, and up to 16 entries std::sort is a plain (stable)
+// insertion sort, so the ranks computed by the whole warp are exact. A block with more than 16 candidates
+// AND two equal keys (possible: |57| * csf[84] == |116| * csf[70] in float, see
+// tests/test_host_cpu.py::test_zeroing_key_ties_are_possible) gets the library's own arrangement: one
+// lane runs the restated introsort (gzb_exact_sort.h) over the (key, index) pairs in the order the
+// reference builds them. `pairs` is scratch for 192 pairs (bufA + bufB, dead at this point).
+struct ZeroSortPair { float key; int ent; };
+struct ZeroSortLess {
+  __host__ __device__ bool operator()(const ZeroSortPair& a, const ZeroSortPair& b) const { return a.key < b.key; }
+};
+// (kept out of line: the rare path must not cost the search loop registers)
+__device__ __noinline__ void zero_exact_sort(ZeroSortPair* pairs, int n, unsigned char* order) {
+  xsort::sort<16>(pairs, pairs + n, ZeroSortLess());
+  for (int i = 0; i < n; ++i) order[i] = static_cast<unsigned char>(pairs[i].ent);
+}
+__device__ __forceinline__ void warp_input_order(const float* key, const unsigned char* ent, int n, unsigned char* order,
+                                                 ZeroSortPair* pairs, unsigned int* tie_counter, int lane) {
+  int ties = 0;
+  for (int e = lane; e < n; e += 32) {
+    const float ke = key[e];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float kj = key[j];
+      rank += (kj < ke || (kj == ke && j < e)) ? 1 : 0;
+      ties += (kj == ke && j != e) ? 1 : 0;
+    }
+    order[rank] = ent[e];
+  }
+  const bool tied = __any_sync(0xffffffffu, ties != 0);
+  __syncwarp();
+  if (tied && n > 16) {
+    for (int e = lane; e < n; e += 32) pairs[e] = ZeroSortPair{key[e], ent[e]};
+    __syncwarp();
+    if (lane == 0) {
+      zero_exact_sort(pairs, n, order);
+      if (tie_counter) atomicAdd(tie_counter, 1u);
+    }
+    __syncwarp();
+  }
+}
+
 // Longest-processing-time-first order of the blocks [b0, b1): a block's search costs about three
 // CompareBlock trials per non-zero AC coefficient, and at ~1 MPix a warp only gets five or six blocks,
 // so handing out the expensive blocks first shortens the tail of the launch. Counting sort by the
@@ -285,7 +328,8 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
                 int comp_mask, float limit, int lookahead, int mode, int single_block, int block_begin,
                 CoeffDataDev* __restrict__ out, float* __restrict__ err_out,
                 float* __restrict__ pregamma_out, unsigned int* __restrict__ counter,
-                const int* __restrict__ lpt_order, int coef_bw, const uint8_t* __restrict__ fixed_chroma) {
+                const int* __restrict__ lpt_order, int coef_bw, const uint8_t* __restrict__ fixed_chroma,
+                unsigned int* __restrict__ tie_counter) {
   __shared__ ZeroWarpSmem sm[kZeroWarps];
   __shared__ int s_basis[64];
   const float* s_lut = g_tab.srgb_lin;   // 1 KB, L1-resident; shared memory is the occupancy limiter
@@ -360,16 +404,7 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
       n += __popc(m);
     }
     __syncwarp();
-    for (int e = lane; e < n; e += 32) {
-      const float ke = s.key[e];
-      int rank = 0;
-      for (int j = 0; j < n; ++j) {
-        const float kj = s.key[j];
-        rank += (kj < ke || (kj == ke && j < e)) ? 1 : 0;
-      }
-      s.order[rank] = s.ent[e];
-    }
-    __syncwarp();
+    warp_input_order(s.key, s.ent, n, s.order, reinterpret_cast<ZeroSortPair*>(s.bufA), tie_counter, lane);
     // ---- greedy loop ----
     CoeffDataDev* o = out + static_cast<size_t>(b) * 192;
     int win[3];

@@ -429,6 +429,9 @@ int gzb_get_transfer_bytes(const gzb_ctx* ctx, unsigned long long* h2d, unsigned
 /* ---- timing of the last call on this context (CUDA events on the context's stream) -------- */
 /* Device milliseconds spent by the kernels of the last gzb_compare / zeroing call. */
 float gzb_last_device_ms(const gzb_ctx* ctx);
+/* Blocks of the last zeroing search with more than 16 candidates and two equal ordering keys: their input order
+ * (guetzli/processor.cc:410-412) is std::sort's own arrangement, reproduced by the restated introsort. */
+unsigned gzb_last_zeroing_tie_blocks(const gzb_ctx* ctx);
 /* Number of kernels launched by this context since creation (bench `gpu_launches`). */
 unsigned long long gzb_launch_count(const gzb_ctx* ctx);
 /* Number of Compares of this context that were incremental: between two Compares separated only by

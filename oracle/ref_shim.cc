@@ -349,6 +349,14 @@ double ref_session_compare_block(void* p, int bx, int by, const int16_t* candida
 // The MODE_CPU branch of SelectFrequencyMasking (processor.cc:638-672) for
 // 4:4:4: out has nblocks*192 {int idx; float err} records, zero-filled.
 // Requires start_block_comparisons. block_begin/block_end select a range.
+// Overwrites the session's q=1 input coefficients (jpg.components[c].coeffs) -- for tests that need
+// specific coefficient values (e.g. two equal zeroing-order keys in one block).
+void ref_session_set_jpg_coeffs(void* p, const coeff_t* c0, const coeff_t* c1, const coeff_t* c2) {
+  Session* s = static_cast<Session*>(p);
+  const coeff_t* src[3] = {c0, c1, c2};
+  for (int c = 0; c < 3; ++c)
+    memcpy(s->jpg.components[c].coeffs.data(), src[c], s->jpg.components[c].coeffs.size() * sizeof(coeff_t));
+}
 void ref_session_zeroing_order(void* p, int comp_mask, int block_begin, int block_end,
                                guetzli::CoeffData* out) {
   Session* s = static_cast<Session*>(p);

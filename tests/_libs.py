@@ -143,6 +143,11 @@ class RefSession:
     def reset(self):
         self.L.ref_session_reset(self.s)
 
+    def set_jpg_coeffs(self, coeffs):
+        """Overwrites the q=1 input coefficients of the session (jpg.components[c].coeffs)."""
+        coeffs = np.ascontiguousarray(coeffs, np.int16)
+        self.L.ref_session_set_jpg_coeffs(self.s, p(coeffs[0]), p(coeffs[1]), p(coeffs[2]))
+
     def apply_quant(self, q):
         q = np.ascontiguousarray(q, np.int32).reshape(192)
         self.L.ref_session_apply_quant(self.s, p(q))

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Golden results of the UNMODIFIED reference (oracle/_ref) on the FULL bench workloads of
-BASELINE.json: synthetic 1024x1024 at q90 (configs[1]) and 4000x3000 at q95 (configs[2]), same
-generator and seed as bench.py. Single-threaded CPU Guetzli: about a minute and about a quarter of an
-hour. Writes tests/golden/full_encodes.json (sha256, size, iterations, seconds, trace)."""
+BASELINE.json: synthetic 1024x1024 at q90 (configs[1]), 4000x3000 at q95 (configs[2]) and two images of the
+64-image batch of configs[3] (1920x1080 at q95, seeds 1234 and 1244), same generator and seeds as bench.py.
+Single-threaded CPU Guetzli: about two minutes, half an hour and five minutes each. Writes tests/golden/full_encodes.json (sha256, size, iterations, seconds, trace)."""
 import hashlib, json, os, sys, time
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
@@ -13,7 +13,7 @@ def main():
     L = ref()
     path = os.path.join(HERE, "full_encodes.json")
     out = json.load(open(path)) if os.path.exists(path) else {}
-    for (w, h, q, seed) in [(1024, 1024, 90, 1234), (4000, 3000, 95, 1234)]:
+    for (w, h, q, seed) in [(1024, 1024, 90, 1234), (4000, 3000, 95, 1234), (1920, 1080, 95, 1234), (1920, 1080, 95, 1244)]:
         key = "%dx%d_q%d_s%d" % (w, h, q, seed)
         if key in out:
             continue

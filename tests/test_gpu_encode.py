@@ -241,9 +241,10 @@ def test_group_encode_edge_cases(gz, name, world):
     assert got == trace_records(gold["trace"])
 
 
-@pytest.mark.parametrize("key", ["1024x1024_q90_s1234", "4000x3000_q95_s1234"])
+@pytest.mark.parametrize("key", ["1024x1024_q90_s1234", "4000x3000_q95_s1234", "1920x1080_q95_s1234", "1920x1080_q95_s1244"])
 def test_full_bench_workloads_equal_reference(gz, key):
-    """The FULL workloads of BASELINE.json (bench.py's 1 MPix q90 image, the 12 MPix q95 image):
+    """The FULL workloads of BASELINE.json (the 1 MPix q90 image of configs[1], bench.py's 12 MPix q95 image,
+    two images of the 64-image batch of configs[3]):
     bytes and iteration trace of the single-threaded CPU reference (tests/golden/full_encodes.json,
     two minutes and a quarter of an hour of CPU Guetzli, made by tests/golden/make_full_golden.py)."""
     path = os.path.join(GOLD, "full_encodes.json")

@@ -214,6 +214,68 @@ def test_compare_against_compiled_reference_bees(gz):
     cmp_.close(); s.close()
 
 
+@pytest.mark.parametrize("w,h", [(2048, 2048), (4000, 3000)])
+def test_compare_at_bench_sizes_equals_oracle(gz, w, h):
+    """Compare at the sizes of the bench workloads (4 and 12 MPix; TMA tile loads, decimated lattices and the
+    persistent grids all at full scale) against the plain-C oracle: diffmap and distance bit-exact. The
+    candidate is the image after ApplyGlobalQuantization with the all-3 matrix (SURVEY 8d's M2 input)."""
+    img = synth_image(w, h, 1234)
+    orig = jpeg_coeffs(img)
+    cmp_ = gz.ButteraugliComparator(w, h, img, 0.971769)
+    cmp_.SetJpegCoeffs(orig)
+    cmp_.CopyFromJpegData()
+    cmp_.ApplyGlobalQuantization(np.full(192, 3, np.int32))
+    cur = cmp_.GetCoeffs()
+    d = cmp_.Compare()
+    dm = cmp_.distmap()
+    cmp_.close()
+    want = np.zeros((h, w), np.float32)
+    d_o = oracle().gzo_compare(p(img), p(cur[0]), p(cur[1]), p(cur[2]), w, h, p(want))
+    report("diffmap %dx%d" % (w, h), dm, want)
+    assert d == d_o == want.max()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_zeroing_order_with_equal_keys_is_std_sorts(gz):
+    """Two candidates of one block can have the same ordering key (|orig| * csf, guetzli/processor.cc:401) --
+    e.g. |116| * csf[70] == |57| * csf[84] in float. std::sort places such ties its own (unstable) way once a
+    block has more than 16 candidates; the device detects the tie and runs the restated introsort. Checker:
+    the compiled reference, whose std::sort is the real one. Bit-exact idx and err."""
+    w, h = 64, 48
+    img = synth_image(w, h, 21)
+    s = RefSession(img, 0.971769)
+    co = s.jpg_coeffs().copy()
+    # (component, k, amplitude) pairs with equal float keys, found by tests/test_host_cpu.py's probe
+    pairs = [((1, 6, 116), (1, 20, 57)), ((1, 40, 13), (2, 59, 174)), ((1, 6, 232), (1, 20, 114)),
+             ((1, 27, 208), (2, 36, 109)), ((0, 46, 164), (0, 54, 193))]
+    nb = co.shape[1]
+    for b in range(nb):
+        (c0, k0, a0), (c1, k1, a1) = pairs[b % len(pairs)]
+        sg = -1 if (b // len(pairs)) % 2 else 1
+        co[c0, b, k0] = sg * a0
+        co[c1, b, k1] = -sg * a1
+        if b % 3 == 0:          # a second tie in the same block
+            (d0, l0, e0), (d1, l1, e1) = pairs[(b + 2) % len(pairs)]
+            co[d0, b, l0] = e0
+            co[d1, b, l1] = e1
+    s.set_jpg_coeffs(co)
+    s.reset()
+    s.start_block_comparisons()
+    zo_ref = s.zeroing_order(7)
+    cmp_ = gz.ButteraugliComparator(w, h, img, 0.971769)
+    cmp_.SetJpegCoeffs(co)
+    cmp_.CopyFromJpegData()
+    report("coeffs", cmp_.GetCoeffs(), s.coeffs())
+    cmp_.StartBlockComparisons()
+    zo = cmp_.ComputeBlockZeroingOrder(7)
+    L = gz.lib()
+    L.gzb_last_zeroing_tie_blocks.restype = C.c_uint
+    assert L.gzb_last_zeroing_tie_blocks(cmp_._ctx) == nb      # every block was crafted to tie
+    report("tied zeroing idx", zo["idx"], zo_ref["idx"])
+    report("tied zeroing err", zo["err"], zo_ref["err"])
+    cmp_.close(); s.close()
+
+
 def test_dct_double(gz):
     """ComputeBlockDCTDouble / IDCTDouble (guetzli/dct_double.cc:47-85), bit-exact."""
     rng = np.random.default_rng(8)

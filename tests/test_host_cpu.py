@@ -142,6 +142,46 @@ def test_restated_introsort_equals_std_sort(gz):
                 assert np.array_equal(b_id, a_id) and np.array_equal(b_v, a_v), (n, small)
 
 
+def test_restated_heap_sort_equals_std_partial_sort(gz):
+    """The fallback of introsort when the depth budget runs out: std::__partial_sort(first, last, last)."""
+    L = gz.lib()
+    L.gzb_test_exact_heap_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    rng = np.random.default_rng(6)
+    for n in [0, 1, 2, 3, 17, 100, 189, 1000, 4097, 50000]:
+        for v in _sort_cases(rng, n):
+            ids = np.arange(n, dtype=np.int32)
+            a_id, a_v, b_id, b_v = ids.copy(), v.copy(), ids.copy(), v.copy()
+            L.gzb_test_exact_heap_sort(p(a_id), p(a_v), n, 1)
+            L.gzb_test_exact_heap_sort(p(b_id), p(b_v), n, 0)
+            assert np.array_equal(a_id, b_id) and np.array_equal(a_v, b_v), n
+
+
+def test_zeroing_key_ties_are_possible():
+    """Probe of the zeroing-order model (guetzli/order.inc: key = |orig| * csf[idx] + bias[idx] in float):
+    two DIFFERENT coefficients of a block can have equal keys, so the per-block std::sort's tie placement
+    matters and the device kernel must reproduce it (gzb_zeroing.cuh: warp_input_order). None below |64|."""
+    txt = open(os.path.join(ROOT, "guetzli-cuda-opencl_b200", "csrc", "gzb_zeroing_model.h")).read()
+    vals = re.findall(r"\{\s*([-0-9.e+]+)f?,\s*([-0-9.e+]+)f?\}", txt[txt.index("kGzbZeroModel[192] = {"):])
+    assert len(vals) == 192
+    csf = np.array([float(a) for a, _ in vals], np.float32)
+    bias = np.array([float(b) for _, b in vals], np.float32)
+    idxs = np.array([i for i in range(192) if i % 64 != 0])
+
+    def ties(amax):
+        amp = np.arange(1, amax + 1, dtype=np.float32)
+        keys = (amp[None, :] * csf[idxs][:, None]).astype(np.float32) + bias[idxs][:, None]
+        ids = np.repeat(idxs, amax)
+        k = keys.reshape(-1)
+        o = np.argsort(k, kind="stable")
+        ks, is_ = k[o], ids[o]
+        return int(np.count_nonzero((ks[1:] == ks[:-1]) & (is_[1:] != is_[:-1])))
+    assert ties(63) == 0
+    assert ties(255) > 0
+    k70 = np.float32(116) * csf[70] + bias[70]
+    k84 = np.float32(57) * csf[84] + bias[84]
+    assert k70 == k84      # the pair used by tests/test_gpu_parity.py::test_zeroing_order_with_equal_keys_is_std_sorts
+
+
 def test_worker_pool_runs_every_task_exactly_once(gz):
     """The spin-then-sleep pool under many short back-to-back jobs, also with several pools alive at
     once (one per encoder thread in the group tests) and more threads than cores."""

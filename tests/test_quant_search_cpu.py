@@ -247,3 +247,33 @@ def test_downsampled_search_replays_the_reference_sequence(gz, kind, world):
         for g, w in zip(got, want_visited):
             assert g[0] == w[0] and abs(g[1] - w[1]) < 1e-9 and g[2] == w[2] and g[3] == w[3]
         assert r["best_q"] == want_best[0] and r["best_ok"] == want_best[1]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_a_failing_rank_fails_the_whole_group_without_a_hang(gz, world):
+    """A rank whose trial fails (CUDA error, out of memory) must still enter the exchange: every rank then
+    returns an error in the same round instead of the others blocking inside the all-gather."""
+    target = 0.971769
+    ok_ev = make_eval("typical")
+    calls = [0] * world
+    ag = BarrierAllGather(world)
+    res = [None] * world
+
+    def work(r):
+        def ev(original, q):
+            calls[r] += 1
+            if r == world - 1 and calls[r] >= 2:
+                return None          # second trial of the last rank fails
+            return ok_ev(original, q)
+        try:
+            gz.QuantSearchSimulate(r, world, ag.for_rank(r), target, ev)
+            res[r] = "ok"
+        except Exception as ex:   # noqa
+            res[r] = "error"
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(60)
+    assert not any(t.is_alive() for t in th), "a rank is stuck in the exchange"
+    assert res == ["error"] * world
