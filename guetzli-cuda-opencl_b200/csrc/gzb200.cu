@@ -381,7 +381,9 @@ struct gzb_ctx {
   float* d_bmax = nullptr, *d_weight = nullptr, *d_mask_scale = nullptr, *d_block_err = nullptr;
   float* d_pregamma = nullptr;
   unsigned char* d_flags = nullptr;
-  unsigned int* d_scalars = nullptr;  // [0] distance bits, [1] work counter
+  unsigned int* d_scalars = nullptr;  // [0] distance bits, [1] work counter, [2] grey flag, [3] tie counter, [4] block-change record valid
+  uint8_t* d_blk_changed = nullptr;   // one byte per 8x8 block: samples changed since the last Compare (BlockChanges)
+  bool blk_tracking = false;          // every change since the last Compare is recorded in d_blk_changed
   int* d_q = nullptr;          // 192 ints
   uint8_t* d_upd = nullptr;    // sparse-update staging: [cap] int32 | [cap] int16 | [cap] u8
   size_t upd_cap = 0;
@@ -402,7 +404,7 @@ struct gzb_ctx {
   bool inter_valid = false;          // the buffers of the last Compare describe the candidate before `changed`
   bool changed_overflow = false;     // too many changes since the last Compare to track
   std::vector<int4> changed;         // pixel rectangles (x0, y0, x1, y1) whose samples changed since the last Compare
-  unsigned long long incremental_compares = 0;
+  unsigned long long incremental_compares = 0, fine_bdm_compares = 0;
 
   // ---- SelectFrequencyBackEnd on the device (gzb_backend.cuh); pointers into slab.be ----
   struct Backend {
@@ -413,7 +415,7 @@ struct gzb_ctx {
     BeEntry* small = nullptr;          // directly behind *st: one copy brings both to the host
     int* cand_off = nullptr; uint8_t* cand_idx = nullptr; float* cand_err = nullptr;
     int* last_index = nullptr; float* max_err = nullptr;
-    int* counts = nullptr; int* offsets = nullptr; unsigned* pcount = nullptr;
+    int* counts = nullptr; int* offsets = nullptr; unsigned* pcount = nullptr; int* chunk_sums = nullptr;
     BeEntry* order = nullptr; unsigned* lpos = nullptr; unsigned* rpos = nullptr; unsigned* tcl = nullptr; unsigned* tcr = nullptr;
     int* req_blocks = nullptr; BeBlockState* req_out = nullptr;
     unsigned int* hist = nullptr;      // [48 + 768]
@@ -604,8 +606,9 @@ void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
     CK(cudaStreamWaitEvent(sl, c->ev_fork, 0));
   }
   // (block_diff_ac cells outside the kernel's domain were zeroed once, at context creation)
-  KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac, dmask(c, DS_BDM)));
-  KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_dc<<<(cells + 127) / 128, 128, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, dmask(c, DS_BDM)));
+  const BlockChanges bc{c->d_blk_changed, c->d_scalars + 4, c->bw, c->bh};
+  KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac, dmask(c, DS_BDM), bc));
+  KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_dc<<<(cells + 127) / 128, 128, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, dmask(c, DS_BDM), bc));
   if (c->concurrent) CK(cudaEventRecord(c->ev_bdm, sb));
   // EdgeDetectorLowFreq (its blur scratch is the first part of d_tmp, the main stream's the rest)
   run_blur(c, c->p_lf, c->d_mh, c->ps, 6, c->d_lf, c->lf_stride, c->p_lf.g.tmp_pitch, sl, c->d_tmp, dmask(c, DS_LFH), dmask(c, DS_LFV));
@@ -616,6 +619,8 @@ void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
   // Mask + combine
   run_mask(c, m0, m1, false);
   if (c->concurrent) CK(cudaStreamWaitEvent(c->stream, c->ev_lf, 0));   // ev_lf follows ev_bdm
+  // the BlockDiffMap kernels have read the record of changed blocks: start a new one
+  CK(cudaMemsetAsync(c->d_blk_changed, 0, c->nblocks, c->stream));
   KLAUNCH(c, KC_COMBINE, k_combine<<<gres, blk, 0, c->stream>>>(mask_sample(c, false), c->d_dc, c->d_ac, c->d_lft, c->d_edm, W, H, c->rxs, c->rys, c->sqp, c->d_sq,
                                                                dmask(c, DS_COMB)));
   // CalculateDiffmap
@@ -725,7 +730,8 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     need(c, &c->d_block_err, c->nblocks);
     need(c, &c->d_pregamma, static_cast<size_t>(192) * c->nblocks);
     need(c, &c->d_flags, c->nblocks);
-    need(c, &c->d_scalars, 4);
+    need(c, &c->d_scalars, 8);
+    need(c, &c->d_blk_changed, c->nblocks);
     need(c, &c->d_q, 192);
     need(c, &c->d_order, static_cast<size_t>(192) * c->nblocks);
     need(c, &c->d_upd, static_cast<size_t>(c->nblocks) * 8 * 8);
@@ -734,6 +740,7 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
                          &c->p_mk[2], &c->p_mkb2, &c->p_dm};
     for (BlurPlan* pl : plans) { need(c, &pl->d_sx, pl->hx.size()); need(c, &pl->d_sy, pl->hy.size()); }
     commit_slab(c);
+    CK(cudaMemsetAsync(c->d_scalars, 0, 8 * sizeof(unsigned int), c->stream));   // (the block-change record starts invalid)
     for (BlurPlan* pl : plans) pl->upload(c->stream);
     // TMA descriptors for the H passes whose input planes are fixed: the sigma-14 blur of the six
     // MaskHighIntensityChange planes and the three mask blurs (+ the block-comparison lattice)
@@ -1103,7 +1110,8 @@ int gzb_update_coeffs(gzb_ctx* c, const int32_t* block_ix, const uint8_t* idx, c
     const size_t cs = c->cs;
     KLAUNCH(c, KC_MISC, k_scatter_coeffs<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(
         reinterpret_cast<const int*>(stage), reinterpret_cast<const int16_t*>(stage + cap * 4),
-        stage + cap * 6, n, cs, c->d_coef));
+        stage + cap * 6, n, cs, c->d_coef, c->mode420 ? nullptr : c->d_blk_changed));
+    if (c->mode420) c->blk_tracking = false;   // (component block != image block: not recorded)
     if (dbg) { sync_check(c); fprintf(stderr, "update n=%zu validate %.3f ms, h2d+scatter %.3f ms\n", n, d1 - d0, dbg_now_ms() - d1); }
   }
   const double d2 = dbg_now_ms();
@@ -1142,6 +1150,12 @@ int gzb_compare_begin(gzb_ctx* c) {
   GZB_TRY(c)
   if (!c->have_coeffs) return fail(c, GZB_ERR_STATE, "gzb_compare: no candidate coefficients");
   CK(cudaEventRecord(c->ev0, c->stream));
+  // BlockDiffMap cells are recomputed only around the blocks flipped since the last Compare when that record is
+  // complete and the buffers of the last Compare still describe the candidate before those flips.
+  static const bool no_fine = getenv("GZB_NO_FINE_BDM") != nullptr;
+  const bool fine_bdm = !no_fine && c->inter_valid && c->blk_tracking;
+  CK(cudaMemsetAsync(c->d_scalars + 4, fine_bdm ? 1 : 0, sizeof(unsigned int), c->stream));
+  if (fine_bdm) ++c->fine_bdm_compares;
   // Full or incremental: the per-stage dirty masks decide which tiles the kernels below recompute.
   prepare_dirty_masks(c);
   // Every Compare of a context runs the same ~25 launches on the same buffers (three streams, fork
@@ -1185,6 +1199,7 @@ int gzb_compare_begin(gzb_ctx* c) {
     }
   }
   // from here on the context's buffers describe this candidate
+  c->blk_tracking = true;   // (the Compare has cleared the record)
   c->inter_valid = true;
   c->changed.clear();
   c->changed_overflow = false;
@@ -1664,7 +1679,7 @@ void be_reserve(gzb_ctx* c, int num_blocks, size_t total) {
   const size_t o_state = take(sizeof(BeState) + sizeof(BeEntry) * kBeSmallMax);
   const size_t o_hist = take((48 + 768 + 8) * 4);
   const size_t o_off = take((nb + 1) * 4), o_li = take(nb * 4), o_me = take(nb * 4), o_cnt = take(nb * 4);
-  const size_t o_offs = take((nb + 1) * 4), o_pc = take(nb * 4);
+  const size_t o_offs = take((nb + 1) * 4), o_pc = take(nb * 4), o_cs = take(1024 * 4);
   const size_t o_req = take(kBeSmallMax * 4), o_out = take(sizeof(BeBlockState) * kBeSmallMax);
   const size_t o_tcl = take(ntiles * 4), o_tcr = take(ntiles * 4);
   const size_t o_idx = take(T), o_err = take(T * 4), o_order = take(T * 8), o_lp = take(T * 4), o_rp = take(T * 4);
@@ -1695,6 +1710,7 @@ void be_reserve(gzb_ctx* c, int num_blocks, size_t total) {
   B.counts = reinterpret_cast<int*>(base + o_cnt);
   B.offsets = reinterpret_cast<int*>(base + o_offs);
   B.pcount = reinterpret_cast<unsigned*>(base + o_pc);
+  B.chunk_sums = reinterpret_cast<int*>(base + o_cs);
   B.req_blocks = reinterpret_cast<int*>(base + o_req);
   B.req_out = reinterpret_cast<BeBlockState*>(base + o_out);
   B.tcl = reinterpret_cast<unsigned*>(base + o_tcl);
@@ -1734,6 +1750,10 @@ int gzb_be_begin(gzb_ctx* c, int comp_mask, const int* offsets, const uint8_t* c
   B.geom.pass_bw = (c->W + bs - 1) / bs;
   B.geom.coef_bw = comp_bw(c, (comp_mask & 1) ? 0 : 1);
   B.geom.cs = c->cs;
+  B.geom.factor = B.factor;
+  B.geom.bw = c->bw;
+  B.geom.bh = c->bh;
+  B.geom.blk_changed = c->d_blk_changed;
   if (resident) {
     int* d_counts; int* d_offsets; float* d_err; uint8_t* d_idx;
     packed_ptrs(c, &d_counts, &d_offsets, &d_err, &d_idx);
@@ -1775,7 +1795,16 @@ int gzb_be_build_order(gzb_ctx* c, int direction, double target_mul, float below
     launch_block_weights(c, c->d_diffmap, direction, rblock, target_mul, B.factor);
     CK(cudaMemsetAsync(B.st, 0, 16, c->stream));   // n, blocks_to_change, below, changed_blocks
     KLAUNCH(c, KC_MISC, k_be_count<<<(nb + 255) / 256, 256, 0, c->stream>>>(cands, c->d_weight, B.last_index, nb, direction, B.counts, B.st));
-    KLAUNCH(c, KC_MISC, k_scan_counts<<<1, 1024, 0, c->stream>>>(B.counts, nb, B.offsets));
+    {
+      const int nchunks = (nb + kScanChunk - 1) / kScanChunk;
+      if (nchunks <= 1024) {
+        KLAUNCH(c, KC_MISC, k_scan_chunk_sums<<<nchunks, 256, 0, c->stream>>>(B.counts, nb, B.chunk_sums));
+        KLAUNCH(c, KC_MISC, k_scan_chunk_offsets<<<1, 1024, 0, c->stream>>>(B.chunk_sums, nchunks, B.offsets, nb));
+        KLAUNCH(c, KC_MISC, k_scan_chunk_apply<<<nchunks, 256, 0, c->stream>>>(B.counts, nb, B.chunk_sums, B.offsets));
+      } else {
+        KLAUNCH(c, KC_MISC, k_scan_counts<<<1, 1024, 0, c->stream>>>(B.counts, nb, B.offsets));
+      }
+    }
     KLAUNCH(c, KC_MISC, k_be_set_n<<<1, 1, 0, c->stream>>>(B.offsets, nb, B.st));
     KLAUNCH(c, KC_MISC, k_be_fill<<<(nb * 32 + 255) / 256, 256, 0, c->stream>>>(cands, c->d_weight, B.last_index, B.max_err, B.counts, B.offsets, nb,
                                                                                 direction, below_limit, B.order, B.st));
@@ -1821,10 +1850,8 @@ int gzb_be_select(gzb_ctx* c, uint64_t p_set, int small_max, int* status, uint64
     if (levels > 0) levels += 2;
     for (int l = 0; l < levels; ++l) {
       KLAUNCH(c, KC_MISC, k_be_tiles_count<<<G, kBeThreads, 0, c->stream>>>(B.order, B.tcl, B.tcr, B.st));
-      KLAUNCH(c, KC_MISC, k_be_tiles_scan<<<1, kBeThreads, 0, c->stream>>>(B.order, B.tcl, B.tcr, B.st));
       KLAUNCH(c, KC_MISC, k_be_tiles_lists<<<G, kBeThreads, 0, c->stream>>>(B.order, B.lpos, B.rpos, B.tcl, B.tcr, B.st));
       KLAUNCH(c, KC_MISC, k_be_swap<<<G, kBeThreads, 0, c->stream>>>(B.order, B.lpos, B.rpos, B.st));
-      KLAUNCH(c, KC_MISC, k_be_finalize<<<1, 1, 0, c->stream>>>(B.order, B.lpos, B.rpos, B.st));
     }
     KLAUNCH(c, KC_MISC, k_be_local<<<1, kBeThreads, 0, c->stream>>>(B.order, B.lpos, B.rpos, B.tcl, B.tcr, B.st, B.small));
     CK(cudaMemcpyAsync(hst, B.st, bytes, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += bytes;
@@ -1861,8 +1888,8 @@ int gzb_be_fetch_order(gzb_ctx* c, uint64_t first, gzb_order_entry* out, size_t 
 int gzb_be_store_order(gzb_ctx* c, uint64_t first, const gzb_order_entry* in, size_t n) {
   GZB_TRY(c)
   if (!c->be.active || !in || first + n > c->be.n) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_store_order: bad argument");
+  // (pageable source: the copy is staged before the call returns; the rest is ordered by the stream)
   CK(cudaMemcpyAsync(c->be.order + first, in, n * 8, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += n * 8;
-  sync_check(c);
   GZB_END(c)
 }
 
@@ -1872,8 +1899,17 @@ void be_launch_gather(gzb_ctx* c, const int* blocks, int nreq, int direction) {
   CK(cudaMemcpyAsync(B.req_blocks, blocks, static_cast<size_t>(nreq) * 4, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += static_cast<size_t>(nreq) * 4;
   KLAUNCH(c, KC_MISC, k_be_gather<<<(nreq * 32 + 255) / 256, 256, 0, c->stream>>>(B.geom, B.req_blocks, nreq, c->d_coef, c->d_orig, c->d_q, B.last_index,
                                                                                 B.pcount, B.comp_mask, direction < 0 ? 1 : 0, B.req_out));
-  CK(cudaMemcpyAsync(be_pinned(c) + kBePinGather, B.req_out, sizeof(BeBlockState) * static_cast<size_t>(nreq), cudaMemcpyDeviceToHost, c->stream));
-  c->d2h_bytes += sizeof(BeBlockState) * static_cast<size_t>(nreq);
+  // an "up" step never reads the requantised values: the tail of every record stays on the device
+  const size_t width = direction < 0 ? sizeof(BeBlockState) : offsetof(BeBlockState, requant);
+  CK(cudaMemcpy2DAsync(be_pinned(c) + kBePinGather, sizeof(BeBlockState), B.req_out, sizeof(BeBlockState), width, static_cast<size_t>(nreq),
+                       cudaMemcpyDeviceToHost, c->stream));
+  c->d2h_bytes += width * static_cast<size_t>(nreq);
+}
+void be_copy_states(gzb_ctx* c, gzb_be_block_state* out, int nreq, int direction) {
+  const char* src = be_pinned(c) + kBePinGather;
+  if (direction < 0) { memcpy(out, src, sizeof(BeBlockState) * static_cast<size_t>(nreq)); return; }
+  const size_t width = offsetof(BeBlockState, requant);
+  for (int i = 0; i < nreq; ++i) memcpy(reinterpret_cast<char*>(out + i), src + sizeof(BeBlockState) * static_cast<size_t>(i), width);
 }
 }  // namespace
 
@@ -1910,7 +1946,7 @@ int gzb_be_apply_prefix(gzb_ctx* c, uint64_t p, int direction, int hist_ncomp, u
   sync_check(c);
   if (ac_hist768) memcpy(ac_hist768, hh + 48, 768 * 4);
   if (changed_blocks) *changed_blocks = static_cast<int>(hh[48 + 768]);
-  if (nreq > 0) memcpy(states_out, be_pinned(c) + kBePinGather, sizeof(BeBlockState) * static_cast<size_t>(nreq));
+  if (nreq > 0) be_copy_states(c, states_out, nreq, direction);
   GZB_END(c)
 }
 
@@ -1923,7 +1959,7 @@ int gzb_be_gather(gzb_ctx* c, const int* blocks, int nreq, int direction, gzb_be
   if (nreq == 0) return GZB_OK;
   be_launch_gather(c, blocks, nreq, direction);
   sync_check(c);
-  memcpy(states_out, be_pinned(c) + kBePinGather, sizeof(BeBlockState) * static_cast<size_t>(nreq));
+  be_copy_states(c, states_out, nreq, direction);
   GZB_END(c)
 }
 
@@ -2213,6 +2249,7 @@ unsigned gzb_last_zeroing_tie_blocks(const gzb_ctx* c) { return c ? c->zeroing_t
 float gzb_last_device_ms(const gzb_ctx* c) { return c ? c->last_ms : 0.f; }
 unsigned long long gzb_launch_count(const gzb_ctx* c) { return c ? c->launches : 0; }
 unsigned long long gzb_incremental_compare_count(const gzb_ctx* c) { return c ? c->incremental_compares : 0; }
+unsigned long long gzb_fine_bdm_compare_count(const gzb_ctx* c) { return c ? c->fine_bdm_compares : 0; }
 
 // ---- stage entry points ----------------------------------------------------------------------
 int gzb_blur(int device, float* plane, size_t xsize, size_t ysize, double sigma, double border_ratio) {

@@ -75,7 +75,7 @@ struct BeState {
   int depth;
   float pv;
   unsigned ntiles, NL, NR, K;
-  unsigned pad0, pad1;
+  unsigned done_count, done_swap;   // CTAs that have finished the count / swap phase of the level in flight
   BeRange stack[kBeStack];
 };
 
@@ -118,6 +118,8 @@ __device__ inline void be_next_range(BeState* st, BeEntry* a) {
     st->pv = be_val(be_ld(a + r.first));
     st->ntiles = (r.last - r.first - 1 + kBeTile - 1) / kBeTile;
     st->K = 0;
+    st->done_count = 0;
+    st->done_swap = 0;
     st->status = BE_RUNNING;
     ++st->levels;
     return;
@@ -308,17 +310,24 @@ __device__ __forceinline__ void be_phase_finalize(const BeLevel& L, BeEntry* a, 
   be_next_range(st, a);
 }
 
+// Three launches per long level: the last CTA to finish the count phase scans the tile counts, and the
+// last one to finish the swaps takes the control step (ticket counters; nobody waits for anybody).
+__device__ __forceinline__ bool be_last_cta(unsigned* counter) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
 __global__ void __launch_bounds__(kBeThreads)
 k_be_tiles_count(BeEntry* a, unsigned* tcl, unsigned* tcr, BeState* st) {
   __shared__ BeSmem sm;
   if (!be_grid_level(st)) return;
-  be_phase_count(be_level(a, st), blockIdx.x, gridDim.x, tcl, tcr, sm);
-}
-__global__ void __launch_bounds__(kBeThreads)
-k_be_tiles_scan(BeEntry* a, unsigned* tcl, unsigned* tcr, BeState* st) {
-  __shared__ BeSmem sm;
-  if (!be_grid_level(st)) return;
-  be_phase_scan(be_level(a, st), tcl, tcr, st, sm);
+  const BeLevel L = be_level(a, st);
+  be_phase_count(L, blockIdx.x, gridDim.x, tcl, tcr, sm);
+  if (be_last_cta(&st->done_count)) be_phase_scan(L, tcl, tcr, st, sm);
 }
 __global__ void __launch_bounds__(kBeThreads)
 k_be_tiles_lists(BeEntry* a, unsigned* lpos, unsigned* rpos, const unsigned* tcl, const unsigned* tcr, BeState* st) {
@@ -329,11 +338,9 @@ k_be_tiles_lists(BeEntry* a, unsigned* lpos, unsigned* rpos, const unsigned* tcl
 __global__ void __launch_bounds__(kBeThreads)
 k_be_swap(BeEntry* a, const unsigned* lpos, const unsigned* rpos, BeState* st) {
   if (!be_grid_level(st)) return;
-  be_phase_swap(be_level(a, st), blockIdx.x * kBeThreads + threadIdx.x, gridDim.x * kBeThreads, lpos, rpos, st);
-}
-__global__ void k_be_finalize(BeEntry* a, const unsigned* lpos, const unsigned* rpos, BeState* st) {
-  if (!be_grid_level(st)) return;
-  be_phase_finalize(be_level(a, st), a, lpos, rpos, st);
+  const BeLevel L = be_level(a, st);
+  be_phase_swap(L, blockIdx.x * kBeThreads + threadIdx.x, gridDim.x * kBeThreads, lpos, rpos, st);
+  if (be_last_cta(&st->done_swap) && threadIdx.x == 0) be_phase_finalize(L, a, lpos, rpos, st);
 }
 
 // Short ranges: one CTA partitions level after level for as long as the ranges stay short, then -- if the
@@ -446,7 +453,21 @@ __global__ void k_be_prefix_count(const BeEntry* __restrict__ order, unsigned p,
 
 // Geometry of the pass: unit b of the search owns coefficient block (b / pass_bw) * coef_bw + b % pass_bw
 // of the searched planes (the 4:2:0 luma plane is MCU-padded).
-struct BeGeom { int num_blocks, pass_bw, coef_bw; size_t cs; };
+struct BeGeom {
+  int num_blocks, pass_bw, coef_bw; size_t cs;
+  int factor, bw, bh;        // sampling factor of the searched planes; 8x8 blocks of the image
+  uint8_t* blk_changed;      // one byte per 8x8 image block: its samples changed since the last Compare
+};
+// Marks the image blocks whose samples a flip in unit b changes: the unit's own block, or -- for a
+// sub-sampled chroma block -- the 2x2 luma blocks of its macro-block plus one block all around (the fancy
+// upsampling reaches one sample past the macro-block).
+__device__ __forceinline__ void be_mark_changed(const BeGeom& g, int b) {
+  if (!g.blk_changed) return;
+  if (g.factor == 1) { g.blk_changed[b] = 1; return; }
+  const int mx = b % g.pass_bw, my = b / g.pass_bw;
+  for (int by = max(2 * my - 1, 0); by <= min(2 * my + 2, g.bh - 1); ++by)
+    for (int bx = max(2 * mx - 1, 0); bx <= min(2 * mx + 2, g.bw - 1); ++bx) g.blk_changed[by * g.bw + bx] = 1;
+}
 __device__ __forceinline__ size_t be_cblock(const BeGeom& g, int b) {
   return static_cast<size_t>(b / g.pass_bw) * g.coef_bw + b % g.pass_bw;
 }
@@ -461,6 +482,7 @@ __global__ void k_be_apply_prefix(BeCands c, BeGeom g, const unsigned* __restric
   const unsigned any = __popc(__ballot_sync(0xffffffffu, times > 0));
   if ((threadIdx.x & 31) == 0 && any) atomicAdd(&st->changed_blocks, any);
   if (!times) return;
+  be_mark_changed(g, b);
   const uint8_t* cands = c.idx + be_cand_offset(c, b);
   const size_t cb = be_cblock(g, b);
   int li = last_index[b];
@@ -480,9 +502,13 @@ __global__ void k_be_apply_prefix(BeCands c, BeGeom g, const unsigned* __restric
 struct BeBlockState {
   int last_index;
   unsigned prefix_count;      // entries of the block in this iteration's prefix (> 0: already counted as changed)
+  unsigned long long zmask[3];   // bit z set: the coefficient at zig-zag position z of the component is non-zero
   int16_t idx[3][64];         // quantised indices (coefficient / q) of the three components
   int16_t requant[3][64];     // Quantize(original, q): the value a "down" step restores
 };
+__constant__ uint8_t c_be_zigzag[64] = {   // natural index -> zig-zag position
+    0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30, 41, 43, 9,  11, 18, 24, 31, 40, 44, 53,
+    10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
 __global__ void k_be_gather(BeGeom g, const int* __restrict__ blocks, int nreq, const int16_t* __restrict__ coef,
                             const int16_t* __restrict__ orig, const int* __restrict__ q192, const int* __restrict__ last_index,
                             const unsigned* __restrict__ pcount, int comp_mask, int want_requant, BeBlockState* __restrict__ out) {
@@ -492,8 +518,9 @@ __global__ void k_be_gather(BeGeom g, const int* __restrict__ blocks, int nreq, 
   const size_t cb = be_cblock(g, b);
   BeBlockState* o = out + r;
   if (lane == 0) { o->last_index = last_index[b]; o->prefix_count = pcount[b]; }
-  for (int i = lane; i < 192; i += 32) {
-    const int comp = i >> 6, k = i & 63;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int i = lane + 32 * j, comp = i >> 6, k = i & 63;   // a warp covers half a component per step
     int16_t vi = 0, vr = 0;
     if (comp_mask >> comp & 1) {
       const size_t at = comp * g.cs + cb * 64 + k;
@@ -502,7 +529,14 @@ __global__ void k_be_gather(BeGeom g, const int* __restrict__ blocks, int nreq, 
       if (want_requant) vr = static_cast<int16_t>(quantize_coeff(orig[at], q));
     }
     o->idx[comp][k] = vi;
-    o->requant[comp][k] = vr;
+    if (want_requant) o->requant[comp][k] = vr;
+    // non-zero mask in zig-zag positions: OR over the warp (two steps per component)
+    unsigned long long m = vi != 0 ? 1ull << c_be_zigzag[k] : 0ull;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, off);
+    if (lane == 0) {
+      if (j & 1) o->zmask[comp] |= m; else o->zmask[comp] = m;
+    }
   }
 }
 
@@ -515,6 +549,7 @@ __global__ void k_be_apply_walk(BeGeom g, const int* __restrict__ blocks, const 
   const int b = blocks[i], ci = cidx[i];
   coef[(ci >> 6) * g.cs + be_cblock(g, b) * 64 + (ci & 63)] = val[i];
   atomicAdd(&last_index[b], direction);
+  be_mark_changed(g, b);
 }
 
 // processor.cc:893-895

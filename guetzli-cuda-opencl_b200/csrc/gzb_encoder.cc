@@ -193,6 +193,57 @@ bool emulation_ok() {
   return ok && !forced_off;
 }
 
+
+// Lazy std::sort of one short range of the order on the host: the same partition tree as
+// xsort::introsort_loop, but a right-hand part is only finished when the walk reaches it.
+struct HostLazy {
+  std::vector<OrderEntry> buf;
+  size_t done = 0;       // buf[0, done) is final
+  size_t appended = 0;   // ... and this much of it has been handed to the walk
+  struct R { size_t first, last; int depth; };
+  std::vector<R> pending;   // back() = leftmost
+  void reset(size_t n, int depth) {
+    done = appended = 0;
+    pending.clear();
+    if (n > 0) pending.push_back({0, n, depth});
+  }
+  void clear() { buf.clear(); reset(0, 0); }
+  // buf[0, p) becomes the SET std::sort would leave there (in no particular order); whatever the split
+  // finalises beyond p is reflected in `done`.
+  void split_set(size_t p) {
+    while (!pending.empty() && pending.back().first < p) {
+      R r = pending.back();
+      pending.pop_back();
+      if (r.last <= p) continue;   // wholly inside the set
+      if (r.last - r.first <= 16 || r.depth == 0) {
+        finish_range(buf.data() + r.first, buf.data() + r.last, r.depth);
+        done = r.last;
+        break;   // ranges are disjoint and ordered: nothing else starts before p
+      }
+      --r.depth;
+      const size_t cut = static_cast<size_t>(partition_pivot(buf.data() + r.first, buf.data() + r.last) - buf.data());
+      pending.push_back({cut, r.last, r.depth});
+      pending.push_back({r.first, cut, r.depth});
+    }
+    done = std::max(done, p);
+  }
+  // finalises the leftmost pending range (at most 16 entries, or a heap-sorted one); false: nothing pending
+  bool advance() {
+    if (pending.empty()) return false;
+    R r = pending.back();
+    pending.pop_back();
+    while (r.last - r.first > 16 && r.depth > 0) {
+      --r.depth;
+      const size_t cut = static_cast<size_t>(partition_pivot(buf.data() + r.first, buf.data() + r.last) - buf.data());
+      pending.push_back({cut, r.last, r.depth});
+      r.last = cut;
+    }
+    finish_range(buf.data() + r.first, buf.data() + r.last, r.depth);
+    done = r.last;
+    return true;
+  }
+};
+
 }  // namespace exact_sort
 
 // ---- the candidate as a JPEG, coded on the device ------------------------------------------------
@@ -674,6 +725,16 @@ void gzb_test_exact_heap_sort(int* first, float* second, size_t n, int use_std) 
   else exact_sort::heap_sort(v.data(), v.data() + n);
   for (size_t i = 0; i < n; ++i) { first[i] = v[i].first; second[i] = v[i].second; }
 }
+// HostLazy: split_set(p), then advance() to the end; [p, n) must be std::sort's arrangement, [0, p) its set.
+void gzb_test_host_lazy(int* first, float* second, size_t n, size_t p) {
+  exact_sort::HostLazy lz;
+  lz.buf.resize(n);
+  for (size_t i = 0; i < n; ++i) lz.buf[i] = std::make_pair(first[i], second[i]);
+  lz.reset(n, exact_sort::depth_budget(n));
+  if (p > 0) lz.split_set(p);
+  while (lz.advance()) {}
+  for (size_t i = 0; i < n; ++i) { first[i] = lz.buf[i].first; second[i] = lz.buf[i].second; }
+}
 int gzb_test_sort_emulation_ok(void) { return exact_sort::emulation_ok() ? 1 : 0; }
 // Test hook (GPU): sorts `entries` through the back end's device path -- long ranges partitioned by
 // k_be_select, short ones finished by exact_sort -- optionally consuming [0, prefix) as a set first (those
@@ -1076,9 +1137,13 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       size_t wbase = 0;
       bool order_done = false;         // every entry of the order has been fetched
       std::vector<OrderEntry> range_buf(4096);
+      exact_sort::HostLazy lazy;
       std::vector<int> req_blocks;
       std::vector<gzb_be_block_state> req_states;
-      static const int small_max = getenv("GZB_BE_SMALL_MAX") ? std::max(16, std::min(4096, atoi(getenv("GZB_BE_SMALL_MAX")))) : 1024;
+      // longest range the device hands over: about what the walk of the previous iteration consumed beyond its
+      // prefix (the state of every block named in the range is fetched with it), within [512, 4096]
+      static const int small_max_env = getenv("GZB_BE_SMALL_MAX") ? std::max(16, std::min(4096, atoi(getenv("GZB_BE_SMALL_MAX")))) : 0;
+      int small_max = small_max_env ? small_max_env : 2048;
       // the coefficient flips of the sequential walk
       struct Flips {
         std::vector<int32_t> block; std::vector<uint8_t> cidx; std::vector<int16_t> val;
@@ -1150,112 +1215,115 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           wblocks.clear();
           wslot.clear();
           went.clear();
+          lazy.clear();
           wbase = prefix;
           order_done = false;
           int walk_changed_blocks = 0, prefix_changed_blocks = 0;
           bool prefix_applied = false;
-          // Fetches the next exactly sorted stretch of the order (at least one entry unless the order is
-          // exhausted) and the state of its blocks. The first call of an iteration also consumes the prefix.
-          auto fetch_more = [&]() -> bool {
-            const double ts = now_ms();
-            const size_t have_end = wbase + went.size();
-            size_t rf = 0, rl = 0;
-            if (!exact_sort::emulation_ok()) {
-              // a standard library whose std::sort this file does not restate: sort the whole order with it
-              if (have_end == prefix) {
-                std::vector<OrderEntry> all(order_size);
-                if (gzb_be_fetch_order(e.ctx, 0, reinterpret_cast<gzb_order_entry*>(all.data()), order_size) != GZB_OK) return false;
-                std::sort(all.begin(), all.end(), OrderLess());
-                if (prefix > 0 && gzb_be_store_order(e.ctx, 0, reinterpret_cast<const gzb_order_entry*>(all.data()), prefix) != GZB_OK) return false;
-                went.assign(all.begin() + prefix, all.end());
+          // Blocks named by entries [from, to) of `src` that the walk has not seen yet -> their state from the
+          // device. The first call of an iteration also consumes the prefix (the head of the straddling range
+          // must be in place on the device by then).
+          auto gather_blocks = [&](const OrderEntry* src, size_t count) -> bool {
+            const double tg = now_ms();
+            size_t at = 0;
+            do {
+              req_blocks.clear();
+              while (at < count && req_blocks.size() < 4096) {
+                const int b = src[at++].first;
+                if (wslot.emplace(b, static_cast<int>(wblocks.size() + req_blocks.size())).second) req_blocks.push_back(b);
               }
-              order_done = true;
-              rf = prefix; rl = order_size;
-            } else {
-              int status = 0, depth = 0;
-              uint64_t f64 = 0, l64 = 0;
-              const double tsel = now_ms();
-              if (gzb_be_select(e.ctx, have_end, small_max, &status, &f64, &l64, &depth, reinterpret_cast<gzb_order_entry*>(range_buf.data())) != GZB_OK)
-                return false;
-              e.st.be_select_ms += now_ms() - tsel;
-              rf = static_cast<size_t>(f64); rl = static_cast<size_t>(l64);
-              if (status == 3) {
-                order_done = true;
-              } else {
-                OrderEntry* r0 = range_buf.data();
-                std::vector<OrderEntry> big;
-                if (status == 2) {   // depth budget exhausted: std::sort heap-sorts this range
-                  big.resize(rl - rf);
-                  if (gzb_be_fetch_order(e.ctx, rf, reinterpret_cast<gzb_order_entry*>(big.data()), rl - rf) != GZB_OK) return false;
-                  exact_sort::heap_sort(big.data(), big.data() + big.size());
-                  r0 = big.data();
-                } else {
-                  exact_sort::finish_range(r0, r0 + (rl - rf), depth);
+              const size_t slot0 = wblocks.size();
+              req_states.resize(req_blocks.size());
+              const int nreq = static_cast<int>(req_blocks.size());
+              if (!prefix_applied) {
+                uint32_t ac[768];
+                if (gzb_be_apply_prefix(e.ctx, prefix, direction, back_ncomp, prefix > 0 ? ac : nullptr, &prefix_changed_blocks,
+                                        req_blocks.data(), nreq, req_states.data()) != GZB_OK) return false;
+                if (prefix > 0) {
+                  for (int c = 0; c < back_ncomp; ++c) histogram_from_counts(ac + 256 * c, 256, &ac_hist[c]);
+                  recount_bits();  // raw bit sums for the current codes and the new histograms
+                  changed_coeffs = static_cast<int>(prefix);
+                  e.st.be_steps += prefix;
+                  e.st.be_prefix_steps += prefix;
                 }
-                ++e.st.be_host_ranges;
-                if (rf < have_end) {
-                  // the range straddles the end of the prefix: its head belongs to the set
-                  if (gzb_be_store_order(e.ctx, rf, reinterpret_cast<const gzb_order_entry*>(r0), have_end - rf) != GZB_OK) return false;
-                }
-                went.insert(went.end(), r0 + (std::max(rf, have_end) - rf), r0 + (rl - rf));
+                prefix_applied = true;
+              } else if (nreq > 0) {
+                if (gzb_be_gather(e.ctx, req_blocks.data(), nreq, direction, req_states.data()) != GZB_OK) return false;
               }
-            }
-            e.st.be_sort_ms += now_ms() - ts;
+              wblocks.resize(slot0 + req_blocks.size());
+              for (size_t i = 0; i < req_blocks.size(); ++i) {
+                WalkBlock& wb = wblocks[slot0 + i];
+                wb.block = req_blocks[i];
+                wb.st = req_states[i];
+                wb.last_index = wb.st.last_index;
+                wb.in_prefix = wb.st.prefix_count > 0;
+                wb.touched = false;
+                for (int c = 0; c < 3; ++c) wb.zmask[c] = wb.st.zmask[c];
+              }
+            } while (at < count);
+            e.st.be_gather_ms += now_ms() - tg;
             return true;
           };
-          // The state of the blocks of the next stretch of fetched entries. The first call of an iteration
-          // also consumes the prefix (after fetch_more has put the head of the straddling range in place).
-          size_t gathered = 0;   // entries of `went` whose blocks are known
-          auto gather_next = [&]() -> bool {
-            const double tg = now_ms();
-            const size_t g1 = std::min(went.size(), gathered + 2048);
-            req_blocks.clear();
-            for (size_t i = gathered; i < g1; ++i) {
-              const int b = went[i].first;
-              if (wslot.emplace(b, static_cast<int>(wblocks.size() + req_blocks.size())).second) req_blocks.push_back(b);
+          // Makes at least one more entry of the order final (appended to `went`), or sets order_done. A range
+          // comes from the device partitioned down to at most `small_max` entries (gzb_be_select); this thread
+          // finishes it lazily, std::sort's way, only as far as the walk gets. The first range of an iteration
+          // straddles the end of the prefix: its head is split off as a set and goes back to the device.
+          auto fetch_more = [&]() -> bool {
+            const double ts = now_ms();
+            struct Timer { double t0; double& acc; ~Timer() { acc += now_ms() - t0; } } timer{ts, e.st.be_sort_ms};
+            if (lazy.advance()) {
+              went.insert(went.end(), lazy.buf.begin() + lazy.appended, lazy.buf.begin() + lazy.done);
+              lazy.appended = lazy.done;
+              e.st.be_lazy_ms += now_ms() - ts;
+              return true;
             }
-            const size_t slot0 = wblocks.size();
-            req_states.resize(req_blocks.size());
-            const int nreq = static_cast<int>(req_blocks.size());
-            if (!prefix_applied) {
-              uint32_t ac[768];
-              if (gzb_be_apply_prefix(e.ctx, prefix, direction, back_ncomp, prefix > 0 ? ac : nullptr, &prefix_changed_blocks,
-                                      req_blocks.data(), nreq, req_states.data()) != GZB_OK) return false;
-              if (prefix > 0) {
-                for (int c = 0; c < back_ncomp; ++c) histogram_from_counts(ac + 256 * c, 256, &ac_hist[c]);
-                recount_bits();  // raw bit sums for the current codes and the new histograms
-                changed_coeffs = static_cast<int>(prefix);
-                e.st.be_steps += prefix;
-                e.st.be_prefix_steps += prefix;
-              }
-              prefix_applied = true;
-            } else if (nreq > 0) {
-              if (gzb_be_gather(e.ctx, req_blocks.data(), nreq, direction, req_states.data()) != GZB_OK) return false;
+            const size_t have_end = wbase + went.size();
+            if (!exact_sort::emulation_ok()) {
+              // a standard library whose std::sort this file does not restate: sort the whole order with it
+              std::vector<OrderEntry> all(order_size);
+              if (gzb_be_fetch_order(e.ctx, 0, reinterpret_cast<gzb_order_entry*>(all.data()), order_size) != GZB_OK) return false;
+              std::sort(all.begin(), all.end(), OrderLess());
+              if (prefix > 0 && gzb_be_store_order(e.ctx, 0, reinterpret_cast<const gzb_order_entry*>(all.data()), prefix) != GZB_OK) return false;
+              went.assign(all.begin() + prefix, all.end());
+              order_done = true;
+              return gather_blocks(went.data(), went.size());
             }
-            wblocks.resize(slot0 + req_blocks.size());
-            for (size_t i = 0; i < req_blocks.size(); ++i) {
-              WalkBlock& wb = wblocks[slot0 + i];
-              wb.block = req_blocks[i];
-              wb.st = req_states[i];
-              wb.last_index = wb.st.last_index;
-              wb.in_prefix = wb.st.prefix_count > 0;
-              wb.touched = false;
-              for (int c = 0; c < 3; ++c) wb.zmask[c] = gzb::jpeg::zigzag_nonzero_mask(wb.st.idx[c]);
+            int status = 0, depth = 0;
+            uint64_t f64 = 0, l64 = 0;
+            const double tsel = now_ms();
+            if (gzb_be_select(e.ctx, have_end, small_max, &status, &f64, &l64, &depth, reinterpret_cast<gzb_order_entry*>(range_buf.data())) != GZB_OK)
+              return false;
+            e.st.be_select_ms += now_ms() - tsel;
+            const size_t rf = static_cast<size_t>(f64), rl = static_cast<size_t>(l64);
+            if (status == 3) { order_done = true; return true; }
+            if (status == 2) {   // depth budget exhausted on a long range: std::sort heap-sorts it
+              lazy.buf.resize(rl - rf);
+              if (gzb_be_fetch_order(e.ctx, rf, reinterpret_cast<gzb_order_entry*>(lazy.buf.data()), rl - rf) != GZB_OK) return false;
+              lazy.reset(rl - rf, 0);
+            } else {
+              lazy.buf.assign(range_buf.begin(), range_buf.begin() + (rl - rf));
+              lazy.reset(rl - rf, depth);
             }
-            gathered = g1;
-            e.st.be_gather_ms += now_ms() - tg;
+            ++e.st.be_host_ranges;
+            const size_t head = have_end > rf ? have_end - rf : 0;   // entries of the range that belong to the prefix
+            if (head > 0) {
+              const double tl = now_ms();
+              lazy.split_set(head);
+              e.st.be_lazy_ms += now_ms() - tl;
+              if (gzb_be_store_order(e.ctx, rf, reinterpret_cast<const gzb_order_entry*>(lazy.buf.data()), head) != GZB_OK) return false;
+            }
+            lazy.appended = head;
+            if (!gather_blocks(lazy.buf.data() + head, lazy.buf.size() - head)) return false;
+            if (lazy.done <= head) lazy.advance();
+            went.insert(went.end(), lazy.buf.begin() + lazy.appended, lazy.buf.begin() + lazy.done);
+            lazy.appended = lazy.done;
             return true;
           };
           bool fetch_failed = false;
           auto have_entry = [&](size_t i) -> bool {
-            const size_t at = i - wbase;
-            while (at >= gathered) {
-              if (at >= went.size()) {
-                if (order_done) return false;
-                if (!fetch_more()) { fetch_failed = true; return false; }
-                continue;
-              }
-              if (!gather_next()) { fetch_failed = true; return false; }
+            while (i - wbase >= went.size()) {
+              if (order_done) return false;
+              if (!fetch_more()) { fetch_failed = true; return false; }
             }
             return true;
           };
@@ -1447,6 +1515,10 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           }
           if (fetch_failed) return fail(GZB_ERR_CUDA);
           if (changed_coeffs > 0) val_threshold = went[last_step - wbase].second;
+          if (!small_max_env) {
+            const size_t walked = last_step + 1 - prefix;
+            small_max = static_cast<int>(std::min<size_t>(4096, std::max<size_t>(1024, (2 * walked + 255) / 256 * 256)));
+          }
           const size_t changed_blocks = static_cast<size_t>(prefix_changed_blocks + walk_changed_blocks);
           { const double t1 = now_ms(); e.st.be_walk_ms += t1 - tt; tt = t1; }
           ++e.st.num_iterations;

@@ -210,8 +210,10 @@ typedef struct { int block; float value; } gzb_order_entry;   /* std::pair<int, 
 typedef struct {
   int last_index;            /* last_indexes[block] */
   unsigned prefix_count;     /* flips of this block in the prefix of the current iteration */
+  unsigned long long zmask[3]; /* per component: bit z set = the coefficient at zig-zag position z is non-zero */
   int16_t idx[3][64];        /* quantised indices (coefficient / q), natural order; components outside comp_mask: 0 */
-  int16_t requant[3][64];    /* Quantize(input coefficient, q) (quantize.h:24-29): what a "down" step writes; 0 if not asked */
+  int16_t requant[3][64];    /* Quantize(input coefficient, q) (quantize.h:24-29): what a "down" step writes; only filled
+                                for direction -1 */
 } gzb_be_block_state;
 /* Starts a pass over the units of comp_mask (8x8 blocks; 16x16 macro-blocks for the chroma pass of a
  * 4:2:0 image): last_indexes and max_block_error are zeroed (processor.cc:757-758). The candidate lists
@@ -340,6 +342,7 @@ typedef struct {
   double downsample_ms;                  /* YUV420 passes: DownsampleImage + SaveToJpegData on the device */
   unsigned long long be_selects, be_levels;  /* back end: lazy-sort kernel launches / partitions run on the device */
   unsigned long long be_host_ranges;     /* back end: short ranges of the order finished on the host */
+  double be_lazy_ms;                     /* inside be_sort_ms: host finishing of the short ranges */
   double be_select_ms, be_gather_ms, be_pool_ms;  /* inside be_walk_ms: lazy-sort round trips, block-state round trips
                                                      (the first one consumes the prefix), parallel entropy-code rebuilds */
 } gzb_encode_stats;
@@ -440,6 +443,9 @@ unsigned long long gzb_launch_count(const gzb_ctx* ctx);
  * block transforms); all other values are still in the context's buffers. The results are bit-identical
  * to a full Compare. GZB_NO_INCREMENTAL=1 in the environment disables it. */
 unsigned long long gzb_incremental_compare_count(const gzb_ctx* ctx);
+/* Compares whose BlockDiffMap cells were recomputed only around the blocks flipped since the previous Compare
+ * (every other stage ran in full): the back end's "down" iterations flip 1-5 % of the blocks. */
+unsigned long long gzb_fine_bdm_compare_count(const gzb_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ for rep in range(reps + 1):
     if rep and (best is None or dt < best[0]): best = (dt, st)
 dt, st = best
 keys = ["search_wall_ms", "zeroing_wall_ms", "device_zeroing_ms", "backend_wall_ms", "compare_wall_ms", "device_compare_ms", "device_write_ms",
-        "be_order_ms", "be_walk_ms", "be_sort_ms", "be_select_ms", "be_gather_ms", "be_codes_ms", "be_pool_ms", "be_update_ms", "be_selects",
+        "be_order_ms", "be_walk_ms", "be_sort_ms", "be_select_ms", "be_lazy_ms", "be_gather_ms", "be_codes_ms", "be_pool_ms", "be_update_ms", "be_selects",
         "be_levels", "be_host_ranges", "num_iterations", "num_entropy_code_builds", "be_steps", "be_prefix_steps", "d2h_bytes", "h2d_bytes", "launches"]
 print("%dx%d q%g best of %d: %.1f ms  %.2f MPix/s  %d bytes  env=%s" % (w, h, q, reps, dt * 1e3, w * h / 1e6 / dt, len(jpg),
       {k: v for k, v in os.environ.items() if k.startswith("GZB_")}))

@@ -349,6 +349,47 @@ def test_incremental_compare_equals_full(gz, w, h, yuv420, maxchg):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("w,h,yuv420,frac", [(200, 133, False, 0.05), (1000, 700, False, 0.03), (2048, 1536, False, 0.01),
+                                             (1000, 700, False, 0.4), (257, 131, True, 0.05), (1200, 800, True, 0.02)])
+def test_compare_after_many_scattered_updates_equals_full(gz, w, h, yuv420, frac):
+    """The back end's iterations flip coefficients in hundreds to thousands of scattered blocks: too many for
+    the tile masks, but BlockDiffMap -- a third of a Compare -- only recomputes the cells whose window a flipped
+    block can reach (k_block_diff_map / k_block_dc with BlockChanges). Must equal a full Compare bit for bit.
+    (4:2:0 updates through gzb_update_coeffs are not recorded per block: those Compares are simply full.)"""
+    img = synth_image(w, h, 23)
+    a = gz.ButteraugliComparator(w, h, img, 0.97)
+    b = gz.ButteraugliComparator(w, h, img, 0.97)
+    co = gz.RgbToJpegCoeffs(img)
+    for c in (a, b):
+        c.SetJpegCoeffs(co)
+        if yuv420:
+            c.Downsample420()
+        c.CopyFromJpegData()
+        c.ApplyGlobalQuantization(np.full(192, 4, np.int32))
+    a.Compare()
+    rng = np.random.default_rng(29)
+    for step in range(6):
+        cur = a.GetCoeffs()
+        blocks, idxs, vals = [], [], []
+        for comp in range(3):
+            nb = cur[comp].shape[0]
+            n = max(1, int(frac * nb))
+            pick = rng.choice(nb, n, replace=False)
+            if step % 2 == 0:      # also the corners and the last block row / column
+                pick = np.unique(np.concatenate([pick, [0, nb - 1]]))
+            for blk in pick:
+                blocks.append(int(blk)); idxs.append(64 * comp + int(rng.integers(0, 64))); vals.append(int(rng.integers(-8, 9)) * 4)
+        a.UpdateCoeffs(blocks, idxs, vals)
+        d = a.Compare()
+        b.SetCoeffs(a.GetCoeffs())
+        d_full = b.Compare()
+        report("diffmap after scattered updates, step %d" % step, a.distmap(), b.distmap())
+        assert float(d) == float(d_full)
+    assert a.fine_bdm_compare_count() == (0 if yuv420 else 6)
+    assert b.fine_bdm_compare_count() == 0
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("w,h", [(32, 32), (33, 47), (97, 61), (200, 133), (444, 258), (1024, 768)])
 def test_rgb_front_end_on_device(gz, w, h):
     """EncodeRGBToJpeg with q = 1 (RGB -> YCbCr fixed point, integer forward DCT) on the device equals the

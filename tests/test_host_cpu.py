@@ -142,6 +142,25 @@ def test_restated_introsort_equals_std_sort(gz):
                 assert np.array_equal(b_id, a_id) and np.array_equal(b_v, a_v), (n, small)
 
 
+def test_host_lazy_sort_of_a_short_range(gz):
+    """HostLazy (gzb_encoder.cc): the short ranges the device hands over are finished lazily -- the head that
+    belongs to the prefix as a set, the rest in std::sort's arrangement, piece by piece."""
+    L = gz.lib()
+    L.gzb_test_host_lazy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    L.gzb_test_std_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(17)
+    for n in [1, 2, 16, 17, 40, 500, 4096]:
+        for v in _sort_cases(rng, n):
+            ids = np.arange(n, dtype=np.int32)
+            a_id, a_v = ids.copy(), v.copy()
+            L.gzb_test_std_sort(p(a_id), p(a_v), n)
+            for pfx in sorted({0, 1, n // 3, n - 1}):
+                b_id, b_v = ids.copy(), v.copy()
+                L.gzb_test_host_lazy(p(b_id), p(b_v), n, pfx)
+                assert np.array_equal(b_id[pfx:], a_id[pfx:]) and np.array_equal(b_v[pfx:], a_v[pfx:]), (n, pfx)
+                assert np.array_equal(np.sort(b_id[:pfx]), np.sort(a_id[:pfx])), (n, pfx)
+
+
 def test_restated_heap_sort_equals_std_partial_sort(gz):
     """The fallback of introsort when the depth budget runs out: std::__partial_sort(first, last, last)."""
     L = gz.lib()
