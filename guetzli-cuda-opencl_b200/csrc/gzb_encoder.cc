@@ -383,7 +383,9 @@ struct Encoder {
   bool want_trace = false, ran = false;
   float distance = 0.f;
   gzb::Group group;                 // multi-GPU candidate sharding (gzb_encoder_set_group)
-  bool best_remote = false;         // the best file so far was written on another rank
+  size_t best_size = 0;             // size of the best file so far (MaybeOutput, processor.cc:151-160)
+  bool defer_trial_bytes = false;   // a SelectQuantMatrix trial that becomes the best is rebuilt at the end instead of fetched
+  bool best_remote = false;         // the best file so far is not in best_jpeg: rebuild it from best_trial at the end
   gzb::Trial best_trial{};          // ... and this is the trial that produced it
   int search_rounds = 0, search_trials = 0;
   unsigned long long code_gen = 0;  // counts device codings: tells whether a trial's scan is still resident
@@ -443,7 +445,15 @@ void Encoder::maybe_output_trial(const gzb::Trial& t, const gzb::TrialOutcome& o
   log(" Score[%.4f]", score);
   if (score < best_score || best_score < 0) {
     best_score = score;
-    if (o.owner == group.rank && (o.resident_gen == 0 || o.resident_gen == code_gen)) {
+    best_size = static_cast<size_t>(o.jpg_size);
+    if (defer_trial_bytes) {
+      // Only the best file of the WHOLE search is ever read. A trial of SelectQuantMatrix is rarely that file
+      // (the back end almost always improves on it), and its bytes -- tens of megabytes for the first ones --
+      // can be produced again from its matrix at the end, so they are not fetched now.
+      best_jpeg.clear();
+      best_remote = true;
+      best_trial = t;
+    } else if (o.owner == group.rank && (o.resident_gen == 0 || o.resident_gen == code_gen)) {
       if (o.resident_gen != 0) {   // still on the device: fetch it now
         DeviceJpeg dj;
         dj.header = o.jpeg;
@@ -1171,7 +1181,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       for (int direction : directions) {
         for (;;) {
           // down-adjusting only makes the output larger (processor.cc:766-774)
-          if (stop_early && direction == -1 && prev_size > 1.01 * e.best_jpeg.size()) break;
+          if (stop_early && direction == -1 && prev_size > 1.01 * e.best_size) break;
           double tt = now_ms();
           // distmap is all zeros until the first iteration has compared (processor.cc:777-780)
           if (first_up_iter && gzb_clear_distmap(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
@@ -1549,6 +1559,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           e.log(" Score[%.4f]", score);
           if (score < e.best_score || e.best_score < 0) {
             if (!device_fetch_jpeg(e.ctx, dj, &e.best_jpeg)) return fail(GZB_ERR_CUDA);
+            e.best_size = jpg_size;
             e.best_score = score;
             e.best_remote = false;
             e.log(" (*)");
@@ -1567,6 +1578,9 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   if (gzb_input_is_gray(e.ctx, &gray_i) != GZB_OK) return fail(GZB_ERR_CUDA);
   const bool gray = gray_i != 0;
   const int try_420 = (e.force_420 || (e.try_420 && !gray)) ? 1 : 0;
+  // (a YUV420 pass replaces the input coefficients on the device: a 4:4:4 trial could not be rendered again after it)
+  static const bool no_defer = getenv("GZB_NO_DEFER_BYTES") != nullptr;
+  e.defer_trial_bytes = !try_420 && !no_defer;
   const int force_420 = e.force_420 ? 1 : 0;
   if (try_420 && e.group.world > 1) {
     g_encode_err = "gzb_encoder_run: the YUV420 passes are not sharded over a group";
