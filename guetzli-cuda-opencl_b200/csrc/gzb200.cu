@@ -2057,6 +2057,22 @@ int gzb_be_test_load_order(gzb_ctx* c, const gzb_order_entry* entries, size_t n)
   GZB_END(c)
 }
 
+// Test hook (host arithmetic): the fused-multiply-add quotient of gamma_rational (gzb_device_math.cuh) against
+// IEEE division for EVERY float argument in [0, 1024]; returns the number of mismatches.
+unsigned long long gzb_test_gamma_division(void) {
+  unsigned long long bad = 0;
+  for (uint32_t bits = 0; bits <= 0x44800000u; ++bits) {
+    float xf;
+    memcpy(&xf, &bits, 4);
+    const double x = static_cast<double>(xf) - 0.770000000000000;
+    volatile double c = kGammaRange;
+    const double want = x / c;
+    const double got = div_by_gamma_range(x);
+    bad += memcmp(&want, &got, 8) != 0 ? 1 : 0;
+  }
+  return bad;
+}
+
 // Non-FMA FP64 peak of the device in Gflop/s (DADD + DMUL issued back to back on all SMs): the
 // denominator for the FP64 rate of the search kernels, which are built with -fmad=false.
 int gzb_measure_fp64_peak(int device, double* gflops) {

@@ -61,11 +61,22 @@ __device__ __forceinline__ void opsin_absorbance(double r, double g, double b, d
   out[2] = 0.0882062883536 * r + 0.158581714673 * g + 0.712857943858 * b + 10.6524069248;
 }
 
+constexpr double kGammaRange = 274.579999999999984 - 0.770000000000000;
+constexpr double kGammaRangeInv = 1.0 / kGammaRange;
+__host__ __device__ __forceinline__ double div_by_gamma_range(double x) {
+  const double q0 = x * kGammaRangeInv;
+  const double r = fma(-kGammaRange, q0, x);
+  return fma(r, kGammaRangeInv, q0);
+}
+
 // Degree-5/5 Chebyshev rational via Clenshaw; argument and result pass through float.
 __device__ __forceinline__ double gamma_rational(double v) {
   const float xf = static_cast<float>(v);
-  const double x01 = (static_cast<double>(xf) - 0.770000000000000) /
-                     (274.579999999999984 - 0.770000000000000);
+  // (xf - 0.77) / (274.58 - 0.77), correctly rounded, without the division routine: with y = RN(1 / c),
+  // q0 = RN(x * y) is within an ulp of x / c, r = x - c * q0 is exact in one fused operation, and
+  // RN(q0 + r * y) is the correctly rounded quotient (Markstein's theorem for division through a correctly
+  // rounded reciprocal). gzb_test_gamma_division checks all floats in [0, 1024] against IEEE division on the host.
+  const double x01 = div_by_gamma_range(static_cast<double>(xf) - 0.770000000000000);
   const double x = 2.0 * x01 - 1.0;
   double p1 = 0.0, p2 = 0.0, q1 = 0.0, q2 = 0.0, t, xb;
 #define GZB_CLENSHAW(P, Q)                  \

@@ -1139,17 +1139,17 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         int block, last_index;
         bool in_prefix, touched;
         uint64_t zmask[3];
-        gzb_be_block_state st;
       };
       std::vector<WalkBlock> wblocks;
-      std::unordered_map<int, int> wslot;
+      std::vector<gzb_be_block_state> wstates;   // wstates[slot]: the block's coefficients as the device reported them, edited by the walk
+      wstates.reserve(8192);
+      std::vector<int> wslot(num_blocks, -1);   // unit -> index into wblocks / wstates, -1: not fetched in this iteration
       std::vector<OrderEntry> went;
       size_t wbase = 0;
       bool order_done = false;         // every entry of the order has been fetched
       std::vector<OrderEntry> range_buf(4096);
       exact_sort::HostLazy lazy;
       std::vector<int> req_blocks;
-      std::vector<gzb_be_block_state> req_states;
       // longest range the device hands over: about what the walk of the previous iteration consumed beyond its
       // prefix (the state of every block named in the range is fetched with it), within [512, 4096]
       static const int small_max_env = getenv("GZB_BE_SMALL_MAX") ? std::max(16, std::min(4096, atoi(getenv("GZB_BE_SMALL_MAX")))) : 0;
@@ -1222,8 +1222,9 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           size_t prefix = 0;
           if (min_coeffs_to_change > 9 && order_size > 10)
             prefix = std::min(static_cast<size_t>(min_coeffs_to_change - 9), order_size - 10);
+          for (const WalkBlock& wb : wblocks) wslot[wb.block] = -1;
           wblocks.clear();
-          wslot.clear();
+          wstates.clear();
           went.clear();
           lazy.clear();
           wbase = prefix;
@@ -1240,15 +1241,16 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
               req_blocks.clear();
               while (at < count && req_blocks.size() < 4096) {
                 const int b = src[at++].first;
-                if (wslot.emplace(b, static_cast<int>(wblocks.size() + req_blocks.size())).second) req_blocks.push_back(b);
+                if (wslot[b] < 0) { wslot[b] = static_cast<int>(wblocks.size() + req_blocks.size()); req_blocks.push_back(b); }
               }
               const size_t slot0 = wblocks.size();
-              req_states.resize(req_blocks.size());
+              wstates.resize(slot0 + req_blocks.size());
+              gzb_be_block_state* req_states = wstates.data() + slot0;   // filled in place
               const int nreq = static_cast<int>(req_blocks.size());
               if (!prefix_applied) {
                 uint32_t ac[768];
                 if (gzb_be_apply_prefix(e.ctx, prefix, direction, back_ncomp, prefix > 0 ? ac : nullptr, &prefix_changed_blocks,
-                                        req_blocks.data(), nreq, req_states.data()) != GZB_OK) return false;
+                                        req_blocks.data(), nreq, req_states) != GZB_OK) return false;
                 if (prefix > 0) {
                   for (int c = 0; c < back_ncomp; ++c) histogram_from_counts(ac + 256 * c, 256, &ac_hist[c]);
                   recount_bits();  // raw bit sums for the current codes and the new histograms
@@ -1258,17 +1260,16 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
                 }
                 prefix_applied = true;
               } else if (nreq > 0) {
-                if (gzb_be_gather(e.ctx, req_blocks.data(), nreq, direction, req_states.data()) != GZB_OK) return false;
+                if (gzb_be_gather(e.ctx, req_blocks.data(), nreq, direction, req_states) != GZB_OK) return false;
               }
               wblocks.resize(slot0 + req_blocks.size());
               for (size_t i = 0; i < req_blocks.size(); ++i) {
                 WalkBlock& wb = wblocks[slot0 + i];
                 wb.block = req_blocks[i];
-                wb.st = req_states[i];
-                wb.last_index = wb.st.last_index;
-                wb.in_prefix = wb.st.prefix_count > 0;
+                wb.last_index = req_states[i].last_index;
+                wb.in_prefix = req_states[i].prefix_count > 0;
                 wb.touched = false;
-                for (int c = 0; c < 3; ++c) wb.zmask[c] = wb.st.zmask[c];
+                for (int c = 0; c < 3; ++c) wb.zmask[c] = req_states[i].zmask[c];
               }
             } while (at < count);
             e.st.be_gather_ms += now_ms() - tg;
@@ -1351,8 +1352,8 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
             const int cidx = candidates[last_idx + std::min(direction, 0)];
             const int c = cidx / 64, k = cidx % 64, z = gzb::jpeg::kZigZag[k];
             const int* qc = e.quant[c];
-            int16_t* blk_idx = wb.st.idx[c];
-            const int16_t newval = direction > 0 ? 0 : wb.st.requant[c][k];   // Quantize(jpg coefficient, q)
+            int16_t* blk_idx = wstates[slot].idx[c];
+            const int16_t newval = direction > 0 ? 0 : wstates[slot].requant[c][k];   // Quantize(jpg coefficient, q)
             const int16_t new_idx = static_cast<int16_t>(newval / qc[k]);
             const int16_t old_idx = blk_idx[k];
             // UpdateACHistogram(-1, old block); UpdateACHistogram(+1, new block) (processor.cc:491-515,
@@ -1506,7 +1507,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
                   for (size_t j = ulog.size(); j-- > keep;) {
                     const UndoRec& u = ulog[j];
                     WalkBlock& wb = wblocks[u.slot];
-                    wb.st.idx[u.c][u.k] = u.old_idx;
+                    wstates[u.slot].idx[u.c][u.k] = u.old_idx;
                     wb.zmask[u.c] = u.old_mask;
                     wb.last_index -= direction;
                     if (u.newly_touched) { wb.touched = false; if (!wb.in_prefix) --walk_changed_blocks; }

@@ -427,6 +427,9 @@ int gzb_profile_reset(gzb_ctx* ctx);
  * SMs), in Gflop/s. The search kernels are built with -fmad=false to match the reference's arithmetic, so this
  * -- not the data-sheet FMA rate -- is their arithmetic ceiling. */
 int gzb_measure_fp64_peak(int device, double* gflops);
+/* Test hook (host arithmetic only): the FMA-based quotient used by the opsin gamma against IEEE division for every
+ * float argument in [0, 1024]; returns the number of mismatches (must be 0). */
+unsigned long long gzb_test_gamma_division(void);
 int gzb_get_transfer_bytes(const gzb_ctx* ctx, unsigned long long* h2d, unsigned long long* d2h);
 
 /* ---- timing of the last call on this context (CUDA events on the context's stream) -------- */

@@ -201,6 +201,15 @@ def test_zeroing_key_ties_are_possible():
     assert k70 == k84      # the pair used by tests/test_gpu_parity.py::test_zeroing_order_with_equal_keys_is_std_sorts
 
 
+def test_gamma_range_division_by_fma_is_ieee_division(gz):
+    """gamma_rational divides (x - 0.77) by the constant 273.81 with a multiply and two fused multiply-adds
+    (gzb_device_math.cuh: div_by_gamma_range). Exhaustive over every float x in [0, 1024] (the opsin
+    absorbances lie in [0.77, 260]): the same bits as IEEE division."""
+    L = gz.lib()
+    L.gzb_test_gamma_division.restype = C.c_ulonglong
+    assert L.gzb_test_gamma_division() == 0
+
+
 def test_worker_pool_runs_every_task_exactly_once(gz):
     """The spin-then-sleep pool under many short back-to-back jobs, also with several pools alive at
     once (one per encoder thread in the group tests) and more threads than cores."""
