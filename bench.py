@@ -466,7 +466,9 @@ def run_ours(a, rank, world, local):
         "gpu_launches": launches_all,
         "clocks": clocks,
         "roofline": roof,
-        "butteraugli": {"compare_device_ms_per_call": cmp_ms / max(1, n_cmp), "mpix_per_s": mpix / (cmp_ms / max(1, n_cmp) / 1e3) if cmp_ms else None,
+        "butteraugli": {"note": "averaged over the Compares of an encode: %d of %d recompute BlockDiffMap only around the blocks flipped since "
+                                "the previous Compare; a full Compare is what bench.py --mode butteraugli times" % (st["num_fine_bdm_compares"], st["num_compares"]),
+                        "compare_device_ms_per_call": cmp_ms / max(1, n_cmp), "mpix_per_s": mpix / (cmp_ms / max(1, n_cmp) / 1e3) if cmp_ms else None,
                         "hbm_frac_U1": (ALGO_BYTES_COMPARE_PER_PX * w * h / (cmp_ms / max(1, n_cmp) / 1e3) / 1e9 / peak) if cmp_ms else None},
         "phases_ms": phases,
         "parity": parity,
@@ -502,6 +504,10 @@ def run_butteraugli_sweep(a, local):
         c.ApplyGlobalQuantization(np.full(192, 3, np.int32))
         dev_ms, wall_ms = [], []
         for it in range(a.warmup + a.steps):
+            # a Compare that follows another one of the SAME candidate would only recompute what changed (nothing);
+            # re-rendering the candidate makes the next Compare a full one, as for a new candidate
+            c.CopyFromJpegData()
+            c.ApplyGlobalQuantization(np.full(192, 3, np.int32))
             flush.fill_(it & 0xff)
             torch.cuda.synchronize()
             t0 = time.perf_counter()

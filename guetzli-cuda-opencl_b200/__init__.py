@@ -394,7 +394,7 @@ class EncodeStats(C.Structure):
                 ("be_prefix_steps", C.c_ulonglong), ("device_write_ms", C.c_double), ("search_wall_ms", C.c_double), ("trial_host_ms", C.c_double),
                 ("trial_device_ms", C.c_double), ("search_rounds", C.c_int), ("search_trials", C.c_int),
                 ("downsample_ms", C.c_double), ("be_selects", C.c_ulonglong), ("be_levels", C.c_ulonglong),
-                ("be_host_ranges", C.c_ulonglong), ("be_lazy_ms", C.c_double), ("be_select_ms", C.c_double), ("be_gather_ms", C.c_double),
+                ("be_host_ranges", C.c_ulonglong), ("be_lazy_ms", C.c_double), ("num_fine_bdm_compares", C.c_ulonglong), ("be_select_ms", C.c_double), ("be_gather_ms", C.c_double),
                 ("be_pool_ms", C.c_double)]
 
     def as_dict(self):

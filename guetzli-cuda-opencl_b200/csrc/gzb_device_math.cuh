@@ -28,6 +28,26 @@ __constant__ const double kCsf8x8[37] = {  // ba.cc:157-198
     0.991205724152, 0.5, 0.3831134973, 0.349686450518, 0.627264168628, 0.308982169883,
     0.3831134973, 0.36198671102, 1.05178802919, 0.3831134973, 0.12};
 
+// Scalar constants of the per-pixel arithmetic, in constant memory and deliberately NOT const-qualified: a
+// double-precision literal costs two UMOV instructions every time it is used (the profile of
+// k_zeroing_order showed 10 % of its issue slots going there), a constant-bank operand costs none.
+struct MathConsts {
+  double absorb[3][4];          // OpsinAbsorbance rows: r, g, b weights and bias (ba.cc:741-764)
+  double gamma_lo, gamma_range, gamma_range_inv;
+  double gamma_p[6], gamma_q[6];   // Chebyshev coefficients in Clenshaw order, the constant term last (ba.cc:868-941)
+  double xyb[4];                // RgbToXyb (ba.cc:283-292)
+  double mhic[4];               // MaskHighIntensityChange (ba.cc:798-841)
+};
+__constant__ MathConsts g_mc = {
+    {{0.348036746003, 0.577814843137, 0.0544556093735, 0.774145581713},
+     {0.26922717275, 0.767247733938, 0.0366922708552, 0.920130265014},
+     {0.0882062883536, 0.158581714673, 0.712857943858, 10.6524069248}},
+    0.770000000000000, 274.579999999999984 - 0.770000000000000, 1.0 / (274.579999999999984 - 0.770000000000000),
+    {6.683258861509244, 85.840860336314364, 373.566100223287378, 908.662212739659481, 1496.058452015812463, 881.979476556478289},
+    {0.035662329617191, 0.899112889751053, 4.711532733641639, 12.161463238367844, 20.557285797683576, 12.262350348616792},
+    {1.01611726948, 0.982482243696, 1.43571362627, 0.896039849412},
+    {106.95800948271017, 275.19165240059317, 18599.41286306991, 410.8995306951065}};
+
 // ---------------------------------------------------------------------------------------------
 // Piecewise-linear table lookups (ba.cc:249-281)
 // ---------------------------------------------------------------------------------------------
@@ -56,9 +76,9 @@ __device__ __forceinline__ double interp_clamp512(const double* __restrict__ lut
 // Opsin dynamics (ba.cc:741-764, 868-941, 283-292, 951-973)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void opsin_absorbance(double r, double g, double b, double out[3]) {
-  out[0] = 0.348036746003 * r + 0.577814843137 * g + 0.0544556093735 * b + 0.774145581713;
-  out[1] = 0.26922717275 * r + 0.767247733938 * g + 0.0366922708552 * b + 0.920130265014;
-  out[2] = 0.0882062883536 * r + 0.158581714673 * g + 0.712857943858 * b + 10.6524069248;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    out[c] = g_mc.absorb[c][0] * r + g_mc.absorb[c][1] * g + g_mc.absorb[c][2] * b + g_mc.absorb[c][3];
 }
 
 constexpr double kGammaRange = 274.579999999999984 - 0.770000000000000;
@@ -76,20 +96,18 @@ __device__ __forceinline__ double gamma_rational(double v) {
   // q0 = RN(x * y) is within an ulp of x / c, r = x - c * q0 is exact in one fused operation, and
   // RN(q0 + r * y) is the correctly rounded quotient (Markstein's theorem for division through a correctly
   // rounded reciprocal). gzb_test_gamma_division checks all floats in [0, 1024] against IEEE division on the host.
-  const double x01 = div_by_gamma_range(static_cast<double>(xf) - 0.770000000000000);
+  const double xd = static_cast<double>(xf) - g_mc.gamma_lo;
+  const double q0 = xd * g_mc.gamma_range_inv;
+  const double x01 = fma(fma(-g_mc.gamma_range, q0, xd), g_mc.gamma_range_inv, q0);
   const double x = 2.0 * x01 - 1.0;
   double p1 = 0.0, p2 = 0.0, q1 = 0.0, q2 = 0.0, t, xb;
-#define GZB_CLENSHAW(P, Q)                  \
-  xb = x * p1; t = (xb + xb) - p2 + (P); p2 = p1; p1 = t; \
-  xb = x * q1; t = (xb + xb) - q2 + (Q); q2 = q1; q1 = t;
-  GZB_CLENSHAW(6.683258861509244, 0.035662329617191)
-  GZB_CLENSHAW(85.840860336314364, 0.899112889751053)
-  GZB_CLENSHAW(373.566100223287378, 4.711532733641639)
-  GZB_CLENSHAW(908.662212739659481, 12.161463238367844)
-  GZB_CLENSHAW(1496.058452015812463, 20.557285797683576)
-#undef GZB_CLENSHAW
-  const double yp = x * p1 - p2 + 881.979476556478289;
-  const double yq = x * q1 - q2 + 12.262350348616792;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    xb = x * p1; t = (xb + xb) - p2 + g_mc.gamma_p[k]; p2 = p1; p1 = t;
+    xb = x * q1; t = (xb + xb) - q2 + g_mc.gamma_q[k]; q2 = q1; q1 = t;
+  }
+  const double yp = x * p1 - p2 + g_mc.gamma_p[5];
+  const double yq = x * q1 - q2 + g_mc.gamma_q[5];
   if (yq == 0.0) return 0.0;
   return static_cast<double>(static_cast<float>(yp / yq));
 }
@@ -105,8 +123,8 @@ __device__ __forceinline__ void opsin_pixel(float br, float bg, float bb, float 
     const double sens = gamma_rational(pm[c]) / pm[c];
     cm[c] *= sens;
   }
-  X = static_cast<float>(1.01611726948 * cm[0] - 0.982482243696 * cm[1]);
-  Y = static_cast<float>(1.43571362627 * cm[0] + 0.896039849412 * cm[1]);
+  X = static_cast<float>(g_mc.xyb[0] * cm[0] - g_mc.xyb[1] * cm[1]);
+  Y = static_cast<float>(g_mc.xyb[2] * cm[0] + g_mc.xyb[3] * cm[1]);
   B = static_cast<float>(cm[2]);
 }
 
@@ -117,11 +135,11 @@ __device__ __forceinline__ void opsin_pixel(float br, float bg, float bb, float 
 __device__ __forceinline__ void mhic_pixel(const float c0[3], const float c1[3], double worst,
                                            float o0[3], float o1[3]) {
   const double ave1 = (c0[1] + c1[1]) * 0.5;  // float sum, widened by the double multiply
-  const double chroma = 106.95800948271017 / (ave1 + 106.95800948271017);
+  const double chroma = g_mc.mhic[0] / (ave1 + g_mc.mhic[0]);
   double mix[3];
-  mix[0] = chroma * 275.19165240059317 / (worst + 275.19165240059317);
-  mix[1] = 18599.41286306991 / (worst + 18599.41286306991);
-  mix[2] = chroma * 410.8995306951065 / (worst + 410.8995306951065);
+  mix[0] = chroma * g_mc.mhic[1] / (worst + g_mc.mhic[1]);
+  mix[1] = g_mc.mhic[2] / (worst + g_mc.mhic[2]);
+  mix[2] = chroma * g_mc.mhic[3] / (worst + g_mc.mhic[3]);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const double ave = (c0[c] + c1[c]) * 0.5;

@@ -1648,6 +1648,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
     e.best_remote = false;
   }
   gzb_be_stats(e.ctx, &e.st.be_selects, &e.st.be_levels);
+  e.st.num_fine_bdm_compares = gzb_fine_bdm_compare_count(e.ctx);
   e.st.search_rounds = e.search_rounds;
   e.st.search_trials = e.search_trials;
   e.st.launches = gzb_launch_count(e.ctx);

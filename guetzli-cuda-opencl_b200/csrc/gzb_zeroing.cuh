@@ -321,7 +321,10 @@ k_zero_lpt_scatter(const unsigned char* __restrict__ cost, unsigned int* __restr
 // mode 2: CompareBlock of ONE block `single_block` whose candidate coefficients are the 192 values
 //         at `cur` (comp_stride 64, nblocks 1) -> err_out[0] (Comparator::CompareBlock adaptor)
 // Blocks [block_begin, nblocks) are processed (a group of GPUs splits the image by block range).
-__global__ void __launch_bounds__(32 * kZeroWarps, 7)
+#ifndef GZB_ZERO_MIN_CTAS
+#define GZB_ZERO_MIN_CTAS 7
+#endif
+__global__ void __launch_bounds__(32 * kZeroWarps, GZB_ZERO_MIN_CTAS)
 k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cur,
                 size_t comp_stride, const uint8_t* __restrict__ rgb_planes, size_t plane_stride,
                 int P, int W, int H, int bw, int nblocks, const float* __restrict__ mask_scale,

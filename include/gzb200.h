@@ -343,6 +343,7 @@ typedef struct {
   unsigned long long be_selects, be_levels;  /* back end: lazy-sort kernel launches / partitions run on the device */
   unsigned long long be_host_ranges;     /* back end: short ranges of the order finished on the host */
   double be_lazy_ms;                     /* inside be_sort_ms: host finishing of the short ranges */
+  unsigned long long num_fine_bdm_compares;  /* of num_compares: BlockDiffMap recomputed only around the flipped blocks */
   double be_select_ms, be_gather_ms, be_pool_ms;  /* inside be_walk_ms: lazy-sort round trips, block-state round trips
                                                      (the first one consumes the prefix), parallel entropy-code rebuilds */
 } gzb_encode_stats;

@@ -120,14 +120,37 @@ def traffic(path, note):
         e["time_us"] += num(d, "gpu__time_duration.sum", "us") or 0
         e["fp64_pipe_pct"] = num(d, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")
         e["xu_pipe_pct"] = num(d, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active")
+        e["issue_active_pct"] = num(d, "sm__issue_active.avg.pct_of_peak_sustained_elapsed")
+        # double-precision flops of the launch: one per DADD / DMUL, two per DFMA (thread-level, predicated-on)
+        dadd = num(d, "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum")
+        dmul = num(d, "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum")
+        dfma = num(d, "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum")
+        if dadd is not None and dmul is not None and dfma is not None:
+            e["fp64_flop"] = e.get("fp64_flop", 0.0) + dadd + dmul + 2 * dfma
     for e in kernels.values():
         e["dram_bytes_per_launch"] = e["dram_bytes"] / e["launches"]
-    print(json.dumps({"source": note, "kernels": kernels}, indent=1))
+        if "fp64_flop" in e:
+            e["fp64_flop_per_launch"] = e["fp64_flop"] / e["launches"]
+    return {"source": note, "kernels": kernels}
+
+
+def traffic_sizes(args):
+    """traffic2 <out.json> <WxH> <file.ncu-rep> <note> [<WxH> <file.ncu-rep> <note> ...]: one entry per image size
+    (bench.py looks its workload's size up)."""
+    import json
+    out = {"sizes": {}}
+    for i in range(1, len(args), 3):
+        out["sizes"][args[i]] = traffic(args[i + 1], args[i + 2])
+    with open(args[0], "w") as f:
+        json.dump(out, f, indent=1)
 
 
 if __name__ == "__main__":
     if sys.argv[1] == "traffic":
-        traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
+        import json
+        print(json.dumps(traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else ""), indent=1))
+    elif sys.argv[1] == "traffic2":
+        traffic_sizes(sys.argv[2:])
     elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
     else:
