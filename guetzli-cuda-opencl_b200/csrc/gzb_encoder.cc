@@ -950,8 +950,12 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   // ---- SelectFrequencyMasking(jpg, img, comp_mask, target_mul, stop_early) (processor.cc:559-919) ----
   // Returns 1 when this rank of a group has nothing left to do (the back end runs on rank 0).
   // jpg_ncomp: jpg.components.size() of the pass (1 only for a grey image after a forced "downsampling").
+  // shard: the zeroing search is split over the ranks of the group (all ranks hold the same candidate). The
+  // chroma pass of a YUV420 image starts from the candidate rank 0's luma back end has left, which the other
+  // ranks do not have: rank 0 then searches alone (shard = false) and the others return at once.
   auto select_frequency_masking = [&](const int comp_mask, const double target_mul, const bool stop_early,
-                                      const int jpg_ncomp) -> int {
+                                      const int jpg_ncomp, const bool shard = true) -> int {
+    if (!shard && e.group.rank != 0) return 1;
     // units of the pass: 8x8 blocks, or the 16x16 macro-blocks of the sub-sampled chroma planes
     const int factor = (e.yuv420 && (comp_mask & 6)) ? 2 : 1;
     const int pass_bw = (width + 8 * factor - 1) / (8 * factor), pass_bh = (height + 8 * factor - 1) / (8 * factor);
@@ -959,7 +963,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
     std::vector<int> cand_offsets(num_blocks + 1);
     std::vector<uint8_t> cand_coeffs;
     std::vector<float> cand_errors;   // only a group needs them on the host (for the exchange)
-    const int world = e.group.world, rank = e.group.rank;
+    const int world = shard ? e.group.world : 1, rank = shard ? e.group.rank : 0;
     {
       // In a group a failing rank still takes part in the exchanges and reports its status there, so
       // that all ranks leave together instead of waiting for it inside a collective.
@@ -1583,23 +1587,35 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
   static const bool no_defer = getenv("GZB_NO_DEFER_BYTES") != nullptr;
   e.defer_trial_bytes = !try_420 && !no_defer;
   const int force_420 = e.force_420 ? 1 : 0;
-  if (try_420 && e.group.world > 1) {
-    g_encode_err = "gzb_encoder_run: the YUV420 passes are not sharded over a group";
-    return GZB_ERR_UNSUPPORTED;
-  }
   // force_420 on a grey image: OutputImage::Downsample returns early (output_image.cc:536-539), the
   // image stays 4:4:4 and SaveToJpegData leaves ONE component in jpg, so the pass is the luma-only one
   // with target_mul 1 (processor.cc:1011-1014; the chroma pass returns at processor.cc:735).
   const bool gray_force = force_420 && gray;
-  bool idle_rank = false;
+  // The best file so far is a SelectQuantMatrix trial whose bytes are not here (evaluated on another rank, or
+  // not fetched): render and code it again. ("Original": the q=1 input with three index-0 tables,
+  // processor.cc:967-985.)
+  auto rebuild_best_trial = [&]() -> bool {
+    const gzb::Trial& t = e.best_trial;
+    if ((t.original ? gzb_copy_from_jpeg(e.ctx, &ones[0][0]) : gzb_quantize_from_jpeg(e.ctx, &t.q[0][0])) != GZB_OK) return false;
+    DeviceJpeg dj;
+    if (!device_code_candidate(e.ctx, width, height, e.nb, t.q, t.original != 0, nullptr, nullptr, &dj, e.yuv420) ||
+        !device_fetch_jpeg(e.ctx, dj, &e.best_jpeg)) return false;
+    e.st.num_jpeg_writes++;
+    e.best_remote = false;
+    return true;
+  };
+  bool idle_rank = false;   // a rank other than 0 of a group: it takes part in the searches, rank 0 returns the file
   if (force_420) {   // the original is compared and output before any pass (processor.cc:967-985)
     const int rc = select_quant(1, nullptr);
     if (rc != GZB_OK) return rc;
   }
-  for (int downsample = force_420; downsample <= try_420 && !idle_rank; ++downsample) {
+  for (int downsample = force_420; downsample <= try_420; ++downsample) {
     int best_q[3][64];
     if (downsample && !gray_force) {
-      // DownsampleImage + SaveToJpegData on the q=1 input, on the device
+      // The downsampling replaces the input coefficients: a 4:4:4 trial that is the best so far and whose bytes
+      // are elsewhere has to be rebuilt now.
+      if (e.best_remote && !idle_rank && !rebuild_best_trial()) return fail(GZB_ERR_CUDA);
+      // DownsampleImage + SaveToJpegData on the q=1 input, on the device (every rank of a group on its own copy)
       const double t0 = now_ms();
       if (gzb_downsample_420(e.ctx) != GZB_OK) return fail(GZB_ERR_CUDA);
       e.set_geometry(true);
@@ -1614,7 +1630,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       rc = select_frequency_masking(1, 1.0, false, 1);
     } else {
       rc = select_frequency_masking(1, static_cast<double>(0.97f), false, 3);   // ymul (processor.cc:1011)
-      if (rc == GZB_OK) rc = select_frequency_masking(6, 1.0, true, 3);
+      if (rc >= 0) rc = select_frequency_masking(6, 1.0, true, 3, /*shard=*/false);
     }
     if (rc < 0) return rc;
     idle_rank = rc == 1;
@@ -1636,17 +1652,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
     return GZB_OK;
   }
 
-  if (e.best_remote) {
-    // the winning file is a SelectQuantMatrix trial that another rank wrote: render and code it again here
-    // ("Original": the q=1 input with three index-0 tables, processor.cc:967-985)
-    const gzb::Trial& t = e.best_trial;
-    if ((t.original ? gzb_copy_from_jpeg(e.ctx, &ones[0][0]) : gzb_quantize_from_jpeg(e.ctx, &t.q[0][0])) != GZB_OK) return fail(GZB_ERR_CUDA);
-    DeviceJpeg dj;
-    if (!device_code_candidate(e.ctx, width, height, e.nb, t.q, t.original != 0, nullptr, nullptr, &dj, e.yuv420) ||
-        !device_fetch_jpeg(e.ctx, dj, &e.best_jpeg)) return fail(GZB_ERR_CUDA);
-    e.st.num_jpeg_writes++;
-    e.best_remote = false;
-  }
+  if (e.best_remote && !rebuild_best_trial()) return fail(GZB_ERR_CUDA);
   gzb_be_stats(e.ctx, &e.st.be_selects, &e.st.be_levels);
   e.st.num_fine_bdm_compares = gzb_fine_bdm_compare_count(e.ctx);
   e.st.search_rounds = e.search_rounds;

@@ -388,6 +388,12 @@ int gzb_encoder_set_params(gzb_encoder* enc, int try_420, int force_420);
  *     lists are all-gathered.
  *   * The back end (processor.cc:723-919) is one sequential walk: rank 0 runs it and returns the
  *     JPEG; the other ranks return from gzb_encoder_run with *jpeg_size == 0.
+ *   * With try_420 / force_420 (processor.cc:986-1016) every rank downsamples its own copy; the quant
+ *     searches of both passes and the zeroing searches of the 4:4:4 pass and of the luma pass are
+ *     shared as above. The chroma pass starts from the candidate rank 0's luma back end leaves
+ *     behind, which the other ranks do not have: rank 0 runs its zeroing search alone.
+ * A rank whose work fails still enters every exchange and reports the failure there, so all ranks
+ * return an error together instead of the others waiting inside the collective.
  * `allgather` must gather `nbytes` from every rank into recv[world*nbytes] in rank order (e.g.
  * ncclAllGather / torch.distributed.all_gather over NCCL) and return 0; it is called the same
  * number of times with the same sizes on every rank. Call before gzb_encoder_run. */

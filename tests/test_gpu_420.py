@@ -212,3 +212,25 @@ def test_unmodified_reference_processor_420_through_b200_comparator(gz, name):
                                       0, p(out), C.c_long(out.size), C.byref(iters))
     assert n == gold["size"] and iters.value == gold["iterations"]
     assert hashlib.sha256(out[:n].tobytes()).hexdigest() == gold["sha256"]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("name", [n for n in ("bees_444x258_q90_force", "bees_444x258_q95_try", "synth_33x47_q84_force", "synth_96x80_q95_try",
+                                               "gray_80x64_q90_force", "gray_80x64_q90_try", "red_129x66_q92_try") if n in _gold_420()])
+def test_group_encode_420_equals_reference(gz, name, world):
+    """One image on several GPUs with Params::try_420 / force_420: the quant searches of both passes and the
+    zeroing searches of the 4:4:4 and the luma pass are sharded over the group (the chroma pass, which starts
+    from rank 0's luma result, runs on rank 0); rank 0 must return the reference's bytes and trace."""
+    from test_gpu_encode import run_thread_group
+    gold = _gold_420()[name]
+    kind, size, q, mode = name.split("_")
+    w, h = (int(v) for v in size.split("x"))
+    img = image_420(kind, w, h)
+    res = run_thread_group(gz, img, np.float32(gold["target"]), world, try_420=mode == "try", force_420=mode == "force")
+    jpg, st, trace = res[0]
+    got = trace_records([l for l in trace.splitlines() if "Out[" in l])
+    assert got == trace_records(gold["trace"])
+    assert hashlib.sha256(jpg).hexdigest() == gold["sha256"]
+    assert st["num_iterations"] == gold["iterations"]
+    for r in range(1, world):
+        assert res[r][0] == b""

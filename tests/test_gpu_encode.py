@@ -123,7 +123,7 @@ def test_compare_block_single_equals_batched(gz):
     c.close()
 
 
-def run_thread_group(gz, img, target, world):
+def run_thread_group(gz, img, target, world, **params):
     """`world` encoders of the same image as the ranks of a group, one host thread each, on the one
     GPU of the test box (the exchange is a thread barrier; across GPUs it is NCCL, bench.py)."""
     import threading
@@ -133,7 +133,7 @@ def run_thread_group(gz, img, target, world):
 
     def work(r):
         try:
-            enc = gz.Encoder(img, target, host_threads=2)
+            enc = gz.Encoder(img, target, host_threads=2, **params)
             enc.set_group(r, world, ag.for_rank(r))
             res[r] = enc.run(want_trace=True)
             enc.close()
