@@ -1326,10 +1326,22 @@ static int run_zeroing(gzb_ctx* c, int comp_mask, int mode, int b0 = 0, int b1 =
   } else {
     static const int per_sm = getenv("GZB_ZERO_CTAS_PER_SM") ? atoi(getenv("GZB_ZERO_CTAS_PER_SM")) : 6;   // tuning probe (7 fit; the pipes saturate at 5-6)
     const int ctas = std::max(1, std::min((b1 - b0 + kZeroWarps - 1) / kZeroWarps, c->sm_count * std::max(1, per_sm)));
-    KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<ctas, 32 * kZeroWarps, 0, c->stream>>>(
-        c->d_orig, c->d_coef, cs, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, b1, c->d_mask_scale, comp_mask,
-        c->target, 3, mode, 0, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1, lpt,
-        coef_bw, c->mode420 ? c->d_cup : nullptr, c->d_scalars + 3));
+    // Too few blocks to fill the GPU with one warp each (4 warps x 7 CTAs per SM): three warps per block, one per
+    // look-ahead trial (8 teams per SM are resident). GZB_ZERO_TEAM=0/1 forces the choice.
+    static const int team_env = getenv("GZB_ZERO_TEAM") ? atoi(getenv("GZB_ZERO_TEAM")) : -1;
+    const bool team = mode == 0 && (team_env >= 0 ? team_env != 0 : (b1 - b0) <= 2 * c->sm_count * 8);
+    if (team) {
+      const int tctas = std::max(1, std::min((b1 - b0 + 1) / 2, c->sm_count * 4));
+      KLAUNCH(c, KC_ZEROING, k_zeroing_order<3><<<tctas, 32 * kZeroTeamWarps, 0, c->stream>>>(
+          c->d_orig, c->d_coef, cs, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, b1, c->d_mask_scale, comp_mask,
+          c->target, 3, mode, 0, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1, lpt,
+          coef_bw, c->mode420 ? c->d_cup : nullptr, c->d_scalars + 3));
+    } else {
+      KLAUNCH(c, KC_ZEROING, k_zeroing_order<1><<<ctas, 32 * kZeroWarps, 0, c->stream>>>(
+          c->d_orig, c->d_coef, cs, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, b1, c->d_mask_scale, comp_mask,
+          c->target, 3, mode, 0, b0, reinterpret_cast<CoeffDataDev*>(c->d_order), c->d_block_err, c->d_pregamma, c->d_scalars + 1, lpt,
+          coef_bw, c->mode420 ? c->d_cup : nullptr, c->d_scalars + 3));
+    }
   }
   CK(cudaEventRecord(c->ev1, c->stream));
   return 0;
@@ -1371,7 +1383,7 @@ int gzb_compare_block(gzb_ctx* c, int block_x, int block_y, const int16_t* candi
   int16_t* d_cand = reinterpret_cast<int16_t*>(c->d_upd);  // 384 bytes of the update staging area
   CK(cudaMemcpyAsync(d_cand, candidate192, 192 * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += 384;
   CK(cudaMemsetAsync(c->d_scalars + 1, 0, sizeof(unsigned int), c->stream));
-  KLAUNCH(c, KC_ZEROING, k_zeroing_order<<<1, 32 * kZeroWarps, 0, c->stream>>>(
+  KLAUNCH(c, KC_ZEROING, k_zeroing_order<1><<<1, 32 * kZeroWarps, 0, c->stream>>>(
       d_cand, d_cand, 64, c->d_rgb0, c->ps, c->P, c->W, c->H, c->bw, 1, c->d_mask_scale, 7, c->target, 3, 2,
       block_y * c->bw + block_x, 0, nullptr, c->d_block_err, nullptr, c->d_scalars + 1, nullptr, c->bw, nullptr, nullptr));
   CK(cudaMemcpyAsync(c->h_pinned, c->d_block_err, sizeof(float), cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 4;

@@ -324,7 +324,17 @@ k_zero_lpt_scatter(const unsigned char* __restrict__ cost, unsigned int* __restr
 #ifndef GZB_ZERO_MIN_CTAS
 #define GZB_ZERO_MIN_CTAS 7
 #endif
-__global__ void __launch_bounds__(32 * kZeroWarps, GZB_ZERO_MIN_CTAS)
+// TEAM = 1: one warp per block, the <= 3 look-ahead trials of a round one after the other (large images: the
+// GPU is full of blocks anyway). TEAM = 3: three warps per block, each with its own private copy of the block
+// state, one trial of the round each; they exchange the three errors through shared memory and all commit the
+// same winner (the redundant set-up and commits cost ~6 % more instructions, which is why this variant is only
+// launched when there are too few blocks to fill the GPU with one warp each: tests/bees.png has 1848).
+constexpr int kZeroTeamWarps = 6;   // two teams of three per CTA: 6 x 7888 bytes of state stay under 48 KB of static smem
+__device__ __forceinline__ void zero_team_bar(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(96) : "memory");
+}
+template <int TEAM>
+__global__ void __launch_bounds__(TEAM == 1 ? 32 * kZeroWarps : 32 * kZeroTeamWarps, TEAM == 1 ? GZB_ZERO_MIN_CTAS : 4)
 k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cur,
                 size_t comp_stride, const uint8_t* __restrict__ rgb_planes, size_t plane_stride,
                 int P, int W, int H, int bw, int nblocks, const float* __restrict__ mask_scale,
@@ -333,18 +343,28 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
                 float* __restrict__ pregamma_out, unsigned int* __restrict__ counter,
                 const int* __restrict__ lpt_order, int coef_bw, const uint8_t* __restrict__ fixed_chroma,
                 unsigned int* __restrict__ tie_counter) {
-  __shared__ ZeroWarpSmem sm[kZeroWarps];
+  constexpr int kWarps = TEAM == 1 ? kZeroWarps : kZeroTeamWarps;
+  __shared__ ZeroWarpSmem sm[kWarps];
   __shared__ int s_basis[64];
+  __shared__ unsigned int s_team_blk[2];
+  __shared__ float s_team_err[2][2][3];   // [team][round parity][member]
   const float* s_lut = g_tab.srgb_lin;   // 1 KB, L1-resident; shared memory is the occupancy limiter
   if (threadIdx.x < 64) s_basis[threadIdx.x] = kIdctBasis[threadIdx.x];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int team = warp / TEAM, member = warp - team * TEAM;
   ZeroWarpSmem& s = sm[warp];
   const double csf_a = kCsf8x8[4 + lane], csf_b = kCsf8x8[36];
   for (;;) {
     unsigned int b = 0;
-    if (lane == 0) b = atomicAdd(counter, 1u);
-    b = __shfl_sync(0xffffffffu, b, 0) + static_cast<unsigned int>(block_begin);
+    if (TEAM == 1) {
+      if (lane == 0) b = atomicAdd(counter, 1u);
+      b = __shfl_sync(0xffffffffu, b, 0) + static_cast<unsigned int>(block_begin);
+    } else {
+      if (member == 0 && lane == 0) s_team_blk[team] = atomicAdd(counter, 1u);
+      zero_team_bar(team);
+      b = s_team_blk[team] + static_cast<unsigned int>(block_begin);
+    }
     if (b >= static_cast<unsigned int>(nblocks)) break;
     if (lpt_order) b = static_cast<unsigned int>(lpt_order[b - block_begin]);
     const int blk = mode == 2 ? single_block : static_cast<int>(b);  // image block (b indexes coefficients)
@@ -369,7 +389,7 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
     }
     __syncwarp();
     warp_block_opsin(s.bufA, s.bufB, s.pg0, lane);
-    if (pregamma_out) {
+    if (pregamma_out && member == 0) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) pregamma_out[static_cast<size_t>(b) * 192 + lane + 32 * k] = s.pg0[lane + 32 * k];
     }
@@ -407,23 +427,38 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
       n += __popc(m);
     }
     __syncwarp();
-    warp_input_order(s.key, s.ent, n, s.order, reinterpret_cast<ZeroSortPair*>(s.bufA), tie_counter, lane);
+    warp_input_order(s.key, s.ent, n, s.order, reinterpret_cast<ZeroSortPair*>(s.bufA), member == 0 ? tie_counter : nullptr, lane);
     // ---- greedy loop ----
     CoeffDataDev* o = out + static_cast<size_t>(b) * 192;
     int win[3];
     int nwin = min(lookahead, n), next = nwin, nout = 0;
     for (int i = 0; i < 3; ++i) win[i] = i < nwin ? s.order[i] : 0;
+    int round = 0;
     while (nwin > 0) {
       float best_err = 1e17f;
       int best_i = 0;
-      for (int i = 0; i < nwin; ++i) {
-        const float err = warp_compare_block(s, s_basis, s_lut, win[i], vx, vy, scale, csf_a, csf_b, lane);
-        const float max_err = fmaxf(0.0f, err);
-        if (max_err < best_err) { best_err = max_err; best_i = i; }
+      if (TEAM == 1) {
+        for (int i = 0; i < nwin; ++i) {
+          const float err = warp_compare_block(s, s_basis, s_lut, win[i], vx, vy, scale, csf_a, csf_b, lane);
+          const float max_err = fmaxf(0.0f, err);
+          if (max_err < best_err) { best_err = max_err; best_i = i; }
+        }
+      } else {
+        // one trial of the round per member; the errors meet in shared memory (slots alternate by round, so one
+        // barrier per round orders the writes of round r + 2 after the reads of round r)
+        float mine = 0.0f;
+        if (member < nwin) mine = fmaxf(0.0f, warp_compare_block(s, s_basis, s_lut, win[member], vx, vy, scale, csf_a, csf_b, lane));
+        if (lane == 0) s_team_err[team][round & 1][member] = mine;
+        zero_team_bar(team);
+        for (int i = 0; i < nwin; ++i) {
+          const float max_err = s_team_err[team][round & 1][i];
+          if (max_err < best_err) { best_err = max_err; best_i = i; }
+        }
+        ++round;
       }
       const int idx = win[best_i];
       warp_commit_zero(s, s_basis, idx, lane);
-      if (lane == 0) { o[nout].idx = idx; o[nout].block_err = best_err; }
+      if (lane == 0 && member == 0) { o[nout].idx = idx; o[nout].block_err = best_err; }
       ++nout;
       for (int i = best_i; i + 1 < nwin; ++i) win[i] = win[i + 1];
       if (next < n) win[nwin - 1] = s.order[next++];
@@ -431,7 +466,7 @@ k_zeroing_order(const int16_t* __restrict__ orig, const int16_t* __restrict__ cu
     }
     __syncwarp();
     // ---- monotone from the tail, cut at the limit (processor.cc:467-479) ----
-    if (lane == 0) {
+    if (lane == 0 && member == 0) {
       float min_err = 1e10f;
       for (int i = nout - 1; i >= 0; --i) {
         min_err = fminf(min_err, o[i].block_err);
