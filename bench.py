@@ -242,6 +242,58 @@ def run_reference(a, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+# speed-only comparator: the reference's OWN CUDA path (guetzli --cuda) on the same GPU
+# ------------------------------------------------------------------------------------------------
+def run_reference_cuda(a, rank, world):
+    """`--impl reference-cuda`: the reference built with -D__USE_CUDA__ (oracle/Makefile: refcuda), its kernels JIT-ed
+    from PTX for compute_100, g_mathMode = MODE_CUDA -- Compare and the zeroing search on the GPU, everything
+    else on one host thread, float-only arithmetic (its bytes differ from the CPU encoder's: never a parity
+    reference). One 1024x1024 crop of the workload image per step: a whole 12 MPix encode takes it minutes."""
+    if rank != 0:
+        return
+    import ctypes as C
+    import _libs
+    base = os.path.join(ROOT, "oracle", "_ref", "cuda")
+    so = os.path.join(base, "libgzref_cuda.so")
+    if not os.path.exists(so) or not os.path.exists(os.path.join(base, "clguetzli", "clguetzli.cu.ptx64")):
+        emit(json.dumps({"impl": "reference-cuda", "unavailable": "oracle/_ref/cuda not built (make -C oracle refcuda)"}))
+        return
+    w, h = a.size
+    side = min(1024, w, h)
+    img = workload_image(w, h, 1234)
+    crop = np.ascontiguousarray(img[:side, :side])
+    os.chdir(base)   # ocu.cpp:44 reads clguetzli/clguetzli.cu.ptx64 relative to the working directory
+    L = C.CDLL(so)
+    L.ref_butteraugli_score_for_quality.restype = C.c_double
+    L.ref_butteraugli_score_for_quality.argtypes = [C.c_double]
+    L.ref_process_rgb.restype = C.c_long
+    target = float(np.float32(L.ref_butteraugli_score_for_quality(float(a.quality))))
+    L.ref_set_math_mode(3)   # MODE_CUDA (clguetzli/clguetzli.h:17-25)
+    out = np.zeros(side * side * 3 + (1 << 16), np.uint8)
+    iters = C.c_int()
+    times, sizes = [], []
+    for step in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        n = L.ref_process_rgb(_libs.p(crop), side, side, C.c_float(target), _libs.p(out), C.c_long(out.size), None,
+                              C.c_long(0), C.byref(iters))
+        dt = time.perf_counter() - t0
+        if n <= 0:
+            emit(json.dumps({"impl": "reference-cuda", "unavailable": "guetzli::Process failed in MODE_CUDA (%d)" % n}))
+            return
+        if step >= a.warmup:
+            times.append(dt); sizes.append(int(n))
+    value = side * side / 1e6 * len(times) / sum(times)
+    emit(json.dumps({
+        "impl": "reference-cuda", "metric": "end-to-end encode MPix/s", "value": value, "unit": "MPix/s", "n_gpus": 1,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "the reference's own --cuda path (kernels of clguetzli/clguetzli.cu JIT-ed for compute_100, host search on "
+                               "one thread) on a %dx%d crop of the synthetic %dx%d workload image, quality %g; float-only arithmetic, "
+                               "output differs from the CPU encoder's (speed comparison only)" % (side, side, w, h, a.quality),
+                   "iterations": iters.value, "bytes": sizes[-1]}}))
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def cpu_baseline_single_core(img, w, h, quality):
@@ -546,7 +598,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--size", default="4000x3000", type=lambda s: tuple(int(v) for v in s.lower().split("x")))
     ap.add_argument("--quality", type=float, default=95.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -562,6 +614,8 @@ def main():
     rank, world, local = dist_env()
     if a.impl == "reference":
         run_reference(a, rank, world)
+    elif a.impl == "reference-cuda":
+        run_reference_cuda(a, rank, world)
     elif a.mode == "butteraugli":
         if rank == 0:
             run_butteraugli_sweep(a, local)

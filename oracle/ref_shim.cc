@@ -85,6 +85,11 @@ struct Session {
 
 extern "C" {
 
+// g_mathMode of the reference (clguetzli/clguetzli.h): 0 = MODE_CPU. Only the speed-only CUDA comparator
+// build (oracle/Makefile: refcuda) ever sets another mode.
+void ref_set_math_mode(int mode) { g_mathMode = static_cast<MATH_MODE>(mode); }
+int ref_get_math_mode(void) { return static_cast<int>(g_mathMode); }
+
 // ---------------------------------------------------------------- scalars
 void ref_srgb8_to_linear_table(double* out256) {
   memcpy(out256, guetzli::Srgb8ToLinearTable(), 256 * sizeof(double));
