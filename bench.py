@@ -149,7 +149,7 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # the workload image and bounded samples of it
 # ------------------------------------------------------------------------------------------------
-CROP = 384   # side of the crops the CPU reference is timed on (a whole 12 MPix encode takes half an hour per core)
+CROP = 320   # side of the crops the CPU reference is timed on (a whole 12 MPix encode takes half an hour per core)
 
 
 def workload_image(w, h, seed):

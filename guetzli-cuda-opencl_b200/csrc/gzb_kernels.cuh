@@ -686,11 +686,20 @@ struct SmallBlur3 {
   const double* sy[3];
 };
 constexpr int kSbT = 32, kSbR = 3;
+// The only reader of these six planes is k_edge_detector_map below. For the res cell at (3rx, 3ry) it reads the
+// columns 3rx - 3, 3rx, 3rx + 3 and 3rx + 4, 3rx + 7, 3rx + 10 (x = px or px + 7, and x -+ 3), i.e. only columns
+// with x mod 3 in {0, 1} -- except for the cells clamped to the right border (px = W - 8), which read columns
+// >= W - 11. The same holds for rows. So only the outputs with (x mod 3 != 2 or x >= W - 12) and (y mod 3 != 2
+// or y >= H - 12) are computed: 4/9 of the V pass and 2/3 of the H pass. The needed columns / rows of the tile are
+// listed once per CTA and the work items are spread over the 256 threads in compact form.
+__device__ __forceinline__ bool sb_needed(int g, int size) { return g % 3 != 2 || g >= size - 12; }
 __global__ void __launch_bounds__(256)
 k_blur_small_hv(const float* __restrict__ in, float* __restrict__ out, size_t plane_stride, int W, int H, int P,
                 SmallBlur3 sb, DirtyMask dm) {
   __shared__ float s_in[kSbT + 2 * kSbR][kSbT + 2 * kSbR + 1];
   __shared__ float s_h[kSbT + 2 * kSbR][kSbT + 1];
+  __shared__ unsigned char s_cols[kSbT], s_rows[kSbT];
+  __shared__ int s_nc, s_nr;
   if (!dirty_at(dm, blockIdx.x * kSbT, blockIdx.y * kSbT)) return;   // the CTA's tile is the mask's tile
   const int ch = blockIdx.z % 3;
   const int r = sb.r[ch];
@@ -702,37 +711,63 @@ k_blur_small_hv(const float* __restrict__ in, float* __restrict__ out, size_t pl
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int x0 = blockIdx.x * kSbT, y0 = blockIdx.y * kSbT;
   const int span = kSbT + 2 * r;
-  for (int i = tid; i < span * span; i += 256) {
-    const int ly = i / span, lx = i - ly * span;
-    const int gx = x0 + lx - r, gy = y0 + ly - r;
-    float v = 0.0f;
-    if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = in[static_cast<size_t>(gy) * P + gx];
-    s_in[ly][lx] = v;
+  if (tid < 32) {   // the needed columns of the tile, compacted (warp 0)
+    const bool need = x0 + tid < W && sb_needed(x0 + tid, W);
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (need) s_cols[__popc(m & ((1u << tid) - 1))] = static_cast<unsigned char>(tid);
+    if (tid == 0) s_nc = __popc(m);
+  } else if (tid < 64) {   // ... and rows (warp 1)
+    const int l = tid - 32;
+    const bool need = y0 + l < H && sb_needed(y0 + l, H);
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (need) s_rows[__popc(m & ((1u << l) - 1))] = static_cast<unsigned char>(l);
+    if (l == 0) s_nr = __popc(m);
   }
-  __syncthreads();
-  const int nt = 2 * r + 1;
-  for (int i = tid; i < span * kSbT; i += 256) {
-    const int ly = i >> 5, lx = i & 31;
-    const int gx = x0 + lx, gy = y0 + ly - r;
-    float v = 0.0f;
-    if (gx < W && gy >= 0 && gy < H) {
-      const float* p = &s_in[ly][lx];
-      double acc = 0.0;
-      for (int k = 0; k < nt; ++k) acc += static_cast<double>(p[k] * taps[k]);
-      v = static_cast<float>(acc * scale_x[gx]);
+  // (work items are walked as (row, column) pairs with a carried remainder: one division per thread and loop)
+  {
+    const int dq = 256 / span, dr = 256 - dq * span;
+    int ly = tid / span, lx = tid - ly * span;
+    for (; ly < span; ly += dq, lx += dr) {
+      if (lx >= span) { lx -= span; ++ly; if (ly >= span) break; }
+      const int gx = x0 + lx - r, gy = y0 + ly - r;
+      float v = 0.0f;
+      if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = in[static_cast<size_t>(gy) * P + gx];
+      s_in[ly][lx] = v;
     }
-    s_h[ly][lx] = v;
   }
   __syncthreads();
-  const int gx = x0 + threadIdx.x;
-  if (gx >= W) return;
-#pragma unroll
-  for (int rr = 0; rr < kSbT; rr += 8) {
-    const int ly = threadIdx.y + rr, gy = y0 + ly;
-    if (gy >= H) break;
-    double acc = 0.0;
-    for (int k = 0; k < nt; ++k) acc += static_cast<double>(s_h[ly + k][threadIdx.x] * taps[k]);
-    out[static_cast<size_t>(gy) * P + gx] = static_cast<float>(acc * scale_y[gy]);
+  const int nt = 2 * r + 1, nc = s_nc, nr = s_nr;
+  if (nc == 0) return;
+  const int dq = 256 / nc, dr = 256 - dq * nc;
+  // H pass: every tile row (the V pass needs r rows above and below each needed row), needed columns only
+  {
+    int ly = tid / nc, ci = tid - ly * nc;
+    for (; ly < span; ly += dq, ci += dr) {
+      if (ci >= nc) { ci -= nc; ++ly; if (ly >= span) break; }
+      const int lx = s_cols[ci];
+      const int gx = x0 + lx, gy = y0 + ly - r;
+      float v = 0.0f;
+      if (gy >= 0 && gy < H) {
+        const float* p = &s_in[ly][lx];
+        double acc = 0.0;
+        for (int k = 0; k < nt; ++k) acc += static_cast<double>(p[k] * taps[k]);
+        v = static_cast<float>(acc * scale_x[gx]);
+      }
+      s_h[ly][lx] = v;
+    }
+  }
+  __syncthreads();
+  // V pass: needed rows x needed columns
+  {
+    int ri = tid / nc, ci = tid - ri * nc;
+    for (; ri < nr; ri += dq, ci += dr) {
+      if (ci >= nc) { ci -= nc; ++ri; if (ri >= nr) break; }
+      const int ly = s_rows[ri], lx = s_cols[ci];
+      const int gx = x0 + lx, gy = y0 + ly;
+      double acc = 0.0;
+      for (int k = 0; k < nt; ++k) acc += static_cast<double>(s_h[ly + k][lx] * taps[k]);
+      out[static_cast<size_t>(gy) * P + gx] = static_cast<float>(acc * scale_y[gy]);
+    }
   }
 }
 

@@ -269,3 +269,21 @@ def test_batch_with_encodes_in_flight_equals_single_encodes(gz):
         assert [g[0] for g in got] == single
     got = gz.ProcessBatch(imgs[:3], t, inflight=2, try_420=True)
     assert [g[0] for g in got] == [gz.Process(im, t, try_420=True)[0] for im in imgs[:3]]
+
+
+def test_std_sort_fallback_gives_the_same_bytes():
+    """If the restated introsort ever disagreed with the std::sort of the build (another standard library), the
+    back end fetches the order and sorts it with std::sort itself. GZB_NO_SORT_EMULATION=1 forces that path (the
+    switch is read once per process, hence the subprocess): same golden bytes on bees.png."""
+    import subprocess, sys
+    gold = json.load(open(os.path.join(GOLD, "bees_q95.json")))
+    code = ("import sys, hashlib, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r); "
+            "import __graft_entry__ as ge; from _libs import bees; gz = ge.load_package(); "
+            "jpg, st, _ = gz.Process(bees(), np.float32(%r)); print(hashlib.sha256(jpg).hexdigest(), st['be_selects'])"
+            % (ROOT, os.path.join(ROOT, "tests"), gold["target"]))
+    env = dict(os.environ, GZB_NO_SORT_EMULATION="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    sha, selects = out.stdout.split()[-2:]
+    assert sha == gold["sha256"]
+    assert int(selects) == 0      # the device's lazy sort was not used
