@@ -365,9 +365,13 @@ def run_ours(a, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # One image per rank (seed 1234 + 10 * rank, the SURVEY 8d generator), the same at every step: nothing is
-    # carried from one encode to the next except the allocator's cached slab, and L2 is flushed in between.
-    seed = 1234 + 10 * rank
+    # One image per rank, the same at every step: nothing is carried from one encode to the next except the
+    # allocator's cached slab, and L2 is flushed in between. Weak scaling needs the SAME work on every GPU, so all
+    # ranks encode the seed-1234 image of the SURVEY 8d generator (whose bytes are pinned to the reference's).
+    # --distinct-images gives rank r the image of seed 1234 + 10 r instead: the time of an encode then depends on
+    # the image (the observable tail of the back-end walk is 135 000 to 800 000 steps on these eight), and the
+    # line's max-over-ranks is the slowest image's; its `per_rank` shows them. `batch64` always uses distinct images.
+    seed = 1234 + (10 * rank if a.distinct_images else 0)
     pin_t, img = pinned_copy(torch, workload_image(w, h, seed))
     sampler = ClockSampler(local)
     run_ms, e2e_ms, launches, h2d, d2h = [], [], 0, 0, 0
@@ -412,6 +416,13 @@ def run_ours(a, rank, world, local):
     clocks = sampler.stop()
     total_run = reduce_max(sum(run_ms))
     total_e2e = reduce_max(sum(e2e_ms))
+    per_rank = None
+    if dist is not None:   # every rank's own mean step time and iteration count (images differ by rank)
+        mine = torch.tensor([sum(run_ms) / len(run_ms), float(last_st["num_iterations"]), float(last_st["be_steps"] - last_st["be_prefix_steps"])],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": r, "ms_per_step": float(t[0]), "iterations": int(t[1]), "walked_steps": int(t[2])} for r, t in enumerate(allr)]
     launches_all = int(reduce_sum(launches))
     mpix = w * h / 1e6
     value = world * mpix * a.steps / (total_run / 1e3)
@@ -498,7 +509,7 @@ def run_ours(a, rank, world, local):
     phases["note"] = ("wall-clock partition of the last timed step inside gzb_encoder_run: run = search + zeroing + backend (+ small "
                       "rest); backend = compare_wall + be_order + be_walk + be_update + coding waits; be_walk contains be_select, "
                       "be_gather and be_codes (which contains be_pool); device_* are CUDA-event times on the launching stream")
-    gold = stored_full_reference(w, h, a.quality, 1234)
+    gold = stored_full_reference(w, h, a.quality, seed)
     parity = {"sha256": hashlib.sha256(jpg).hexdigest(), "bytes": len(jpg)}
     if gold:
         parity["equals_reference_bytes"] = parity["sha256"] == gold["sha256"]
@@ -507,8 +518,8 @@ def run_ours(a, rank, world, local):
         "metric": "end-to-end encode MPix/s", "value": value, "unit": "MPix/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic %dx%d sRGB (SURVEY 8d generator, seed 1234+10*rank), quality %g, one image per GPU per "
-                               "step, guetzli::Process" % (w, h, a.quality),
+        "config": {"workload": "synthetic %dx%d sRGB (SURVEY 8d generator, seed %s), quality %g, one image per GPU per "
+                               "step, guetzli::Process" % (w, h, "1234+10*rank" if a.distinct_images else "1234 on every rank", a.quality),
                    "l2": "256 MiB buffer written between timed steps (L2 flush); the same image at every step",
                    "host_threads_per_encode": host_threads, "compares_per_step": n_cmp / a.steps,
                    "iterations_per_step": st["num_iterations"], "be_steps_per_step": st["be_steps"],
@@ -523,6 +534,7 @@ def run_ours(a, rank, world, local):
                         "compare_device_ms_per_call": cmp_ms / max(1, n_cmp), "mpix_per_s": mpix / (cmp_ms / max(1, n_cmp) / 1e3) if cmp_ms else None,
                         "hbm_frac_U1": (ALGO_BYTES_COMPARE_PER_PX * w * h / (cmp_ms / max(1, n_cmp) / 1e3) / 1e9 / peak) if cmp_ms else None},
         "phases_ms": phases,
+        "per_rank": per_rank,
         "parity": parity,
         "batch64": batch64,
         "group": group,
@@ -602,6 +614,7 @@ def main():
     ap.add_argument("--size", default="4000x3000", type=lambda s: tuple(int(v) for v in s.lower().split("x")))
     ap.add_argument("--quality", type=float, default=95.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--distinct-images", action="store_true", help="N > 1: a different image per rank (seed 1234 + 10 * rank)")
     ap.add_argument("--no-extras", action="store_true", help="skip the batch64 (configs[3]) and group (configs[2]) measurements")
     ap.add_argument("--mode", default="batch", choices=["batch", "butteraugli"],
                     help="batch: one image per GPU per step (the headline); butteraugli: standalone Compare sweep + "

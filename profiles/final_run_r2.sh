@@ -1,0 +1,20 @@
+#!/bin/bash
+# final measurement set of round 2 (one B200)
+mkdir -p gpurun_out
+O=gpurun_out
+(timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4) > $O/r2_gpu_tests_final.log 2>&1
+cat $O/r2_gpu_tests_final.log
+(timeout 120 python __graft_entry__.py smoke 2>&1 | tail -2) > $O/r2_smoke.log; cat $O/r2_smoke.log
+timeout 600 python bench.py > $O/r2_bench_12mpix_q95.json 2> $O/bench.err; echo bench rc=$?; tail -2 $O/bench.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/r2_bench_reference_arm.json 2>> $O/bench.err; echo ref rc=$?
+timeout 300 python bench.py --impl reference-cuda --steps 2 --warmup 1 > $O/r2_bench_reference_cuda.json 2>> $O/bench.err; echo refcuda rc=$?
+timeout 600 python bench.py --mode butteraugli --steps 5 --warmup 3 > $O/r2_bench_butteraugli_sweep.json 2>> $O/bench.err; echo ba rc=$?
+timeout 300 python bench.py --size 1024x1024 --quality 90 --no-extras > $O/r2_bench_1mpix_q90.json 2>> $O/bench.err; echo 1mpix rc=$?
+timeout 300 python bench.py --size 1920x1080 --quality 95 --no-extras --no-cpu-baseline > $O/r2_bench_2mpix_q95.json 2>> $O/bench.err; echo 2mpix rc=$?
+python - <<'PY'
+import json
+for f in ["r2_bench_12mpix_q95","r2_bench_reference_arm","r2_bench_reference_cuda","r2_bench_1mpix_q90","r2_bench_2mpix_q95"]:
+    try:
+        d=json.load(open("gpurun_out/%s.json"%f)); print(f, d.get("value"), d.get("e2e",{}).get("value"), d.get("ms_per_step"))
+    except Exception as e: print(f, "ERR", e)
+PY
