@@ -1820,7 +1820,7 @@ int gzb_be_build_order(gzb_ctx* c, int direction, double target_mul, float below
     KLAUNCH(c, KC_MISC, k_be_set_n<<<1, 1, 0, c->stream>>>(B.offsets, nb, B.st));
     KLAUNCH(c, KC_MISC, k_be_fill<<<(nb * 32 + 255) / 256, 256, 0, c->stream>>>(cands, c->d_weight, B.last_index, B.max_err, B.counts, B.offsets, nb,
                                                                                 direction, below_limit, B.order, B.st));
-    KLAUNCH(c, KC_MISC, k_be_sort_begin<<<1, 1, 0, c->stream>>>(B.st));
+    KLAUNCH(c, KC_MISC, k_be_sort_begin<<<1, 1, 0, c->stream>>>(B.st, -1));
     CK(cudaMemcpyAsync(hs, B.st, 16, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += 16;
     sync_check(c);
     if (hs[0] > 0) break;
@@ -2050,7 +2050,12 @@ int gzb_be_stats(const gzb_ctx* c, unsigned long long* selects, unsigned long lo
 }
 
 // Test hook: makes `entries` the order of the context (no candidate lists behind it).
+int gzb_be_test_load_order_depth(gzb_ctx* c, const gzb_order_entry* entries, size_t n, int depth);
 int gzb_be_test_load_order(gzb_ctx* c, const gzb_order_entry* entries, size_t n) {
+  return gzb_be_test_load_order_depth(c, entries, n, -1);
+}
+// depth >= 0: the sort starts with this depth budget instead of 2 * log2(n) (reaches the heap-sort fallback)
+int gzb_be_test_load_order_depth(gzb_ctx* c, const gzb_order_entry* entries, size_t n, int depth) {
   GZB_TRY(c)
   if (!entries || n == 0 || n >= (size_t(1) << 31)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_test_load_order: bad argument");
   gzb_ctx::Backend& B = c->be;
@@ -2064,7 +2069,7 @@ int gzb_be_test_load_order(gzb_ctx* c, const gzb_order_entry* entries, size_t n)
   CK(cudaMemcpyAsync(B.order, entries, n * 8, cudaMemcpyHostToDevice, c->stream));
   const unsigned nn = static_cast<unsigned>(n);
   CK(cudaMemcpyAsync(&B.st->n, &nn, 4, cudaMemcpyHostToDevice, c->stream));
-  KLAUNCH(c, KC_MISC, k_be_sort_begin<<<1, 1, 0, c->stream>>>(B.st));
+  KLAUNCH(c, KC_MISC, k_be_sort_begin<<<1, 1, 0, c->stream>>>(B.st, depth));
   sync_check(c);
   GZB_END(c)
 }

@@ -427,12 +427,13 @@ __global__ void k_be_set_n(const int* __restrict__ offsets, int num_blocks, BeSt
 }
 
 // (re)starts the lazy sort over the n entries: one pending range with introsort's depth budget
-__global__ void k_be_sort_begin(BeState* st) {
+__global__ void k_be_sort_begin(BeState* st, int depth_override = -1) {
   const unsigned n = st->n;
   st->top = 0;
   st->levels_total = 0;
   if (n >= 1) {   // (a single entry is a short range: the host takes it as it is)
-    st->stack[0] = BeRange{0u, n, 2 * (31 - __clz(n)), 0};   // 2 * std::__lg(n)
+    // 2 * std::__lg(n); a test may start with a smaller budget to reach the heap-sort fallback
+    st->stack[0] = BeRange{0u, n, depth_override >= 0 ? depth_override : 2 * (31 - __clz(n)), 0};
     st->top = 1;
   }
 }

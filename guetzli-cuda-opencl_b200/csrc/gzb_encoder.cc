@@ -749,9 +749,19 @@ int gzb_test_sort_emulation_ok(void) { return exact_sort::emulation_ok() ? 1 : 0
 // Test hook (GPU): sorts `entries` through the back end's device path -- long ranges partitioned by
 // k_be_select, short ones finished by exact_sort -- optionally consuming [0, prefix) as a set first (those
 // entries come back in unspecified order). Everything from `prefix` on must equal std::sort's arrangement.
+int gzb_test_device_sort_depth(gzb_ctx* ctx, gzb_order_entry* entries, size_t n, size_t prefix, int small_max, int depth);
 int gzb_test_device_sort(gzb_ctx* ctx, gzb_order_entry* entries, size_t n, size_t prefix, int small_max) {
+  return gzb_test_device_sort_depth(ctx, entries, n, prefix, small_max, -1);
+}
+void gzb_test_exact_sort_depth(int* first, float* second, size_t n, int depth) {
+  std::vector<OrderEntry> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(first[i], second[i]);
+  exact_sort::finish_range(v.data(), v.data() + n, depth);
+  for (size_t i = 0; i < n; ++i) { first[i] = v[i].first; second[i] = v[i].second; }
+}
+int gzb_test_device_sort_depth(gzb_ctx* ctx, gzb_order_entry* entries, size_t n, size_t prefix, int small_max, int depth) {
   if (!ctx || !entries || n == 0 || prefix > n) return GZB_ERR_BAD_ARG;
-  int rc = gzb_be_test_load_order(ctx, entries, n);
+  int rc = gzb_be_test_load_order_depth(ctx, entries, n, depth);
   if (rc != GZB_OK) return rc;
   std::vector<OrderEntry> buf(4096), big;
   size_t have_end = prefix;

@@ -263,6 +263,11 @@ int gzb_be_stats(const gzb_ctx* ctx, unsigned long long* selects, unsigned long 
 int gzb_test_device_sort(gzb_ctx* ctx, gzb_order_entry* entries, size_t n, size_t prefix, int small_max);
 /* Test hook: makes `entries` the context's order (no candidate lists behind it) and restarts the lazy sort. */
 int gzb_be_test_load_order(gzb_ctx* ctx, const gzb_order_entry* entries, size_t n);
+/* The same with a depth budget other than 2 * log2(n): a small one drives the sort into introsort's heap-sort fallback. */
+int gzb_be_test_load_order_depth(gzb_ctx* ctx, const gzb_order_entry* entries, size_t n, int depth);
+int gzb_test_device_sort_depth(gzb_ctx* ctx, gzb_order_entry* entries, size_t n, size_t prefix, int small_max, int depth);
+/* Host checker for it: the restated introsort over the whole array with the given depth budget. */
+void gzb_test_exact_sort_depth(int* first, float* second, size_t n, int depth);
 
 /* ---- YUV 4:2:0 (Params::try_420 / force_420; guetzli/processor.cc:986-1016) ------------------
  * Processor::DownsampleImage + OutputImage::SaveToJpegData on the q=1 input (guetzli/processor.cc:

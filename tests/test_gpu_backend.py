@@ -62,6 +62,30 @@ def test_device_lazy_sort_equals_std_sort(gz, ctx, n):
                 assert np.array_equal(np.sort(e["block"][:pfx]), np.sort(a_id[:pfx])), (name, n, pfx, small)
 
 
+@pytest.mark.parametrize("n,depth", [(5000, 0), (5000, 2), (70000, 3), (70000, 6), (600000, 4)])
+def test_device_lazy_sort_with_exhausted_depth_budget(gz, ctx, n, depth):
+    """introsort heap-sorts a range whose depth budget is used up. The real budget (2 log2 n) is almost never
+    exhausted, so the sort is started with a tiny one: the device must stop partitioning such a range (status 2),
+    the host heap-sorts it, and the result must equal the restated introsort run whole with the same budget
+    (whose heap path is checked against std::partial_sort in tests/test_host_cpu.py)."""
+    L = gz.lib()
+    L.gzb_test_device_sort_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int]
+    L.gzb_test_exact_sort_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    rng = np.random.default_rng(7 + n + depth)
+    entry = np.dtype([("block", np.int32), ("value", np.float32)])
+    for name, v in _cases(rng, n):
+        ids = np.arange(n, dtype=np.int32)
+        a_id, a_v = ids.copy(), v.copy()
+        L.gzb_test_exact_sort_depth(p(a_id), p(a_v), n, depth)
+        for pfx in (0, n // 3):
+            e = np.zeros(n, entry)
+            e["block"], e["value"] = ids, v
+            assert L.gzb_test_device_sort_depth(ctx._ctx, p(e), n, pfx, 1024, depth) == 0
+            assert np.array_equal(e["block"][pfx:], a_id[pfx:]), (name, n, depth, pfx)
+            assert np.array_equal(e["value"][pfx:], a_v[pfx:]), (name, n, depth, pfx)
+            assert np.array_equal(np.sort(e["block"][:pfx]), np.sort(a_id[:pfx])), (name, n, depth, pfx)
+
+
 def test_input_is_gray(gz):
     L = gz.lib()
     img = synth_image(96, 64)
