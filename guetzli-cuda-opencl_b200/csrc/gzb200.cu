@@ -1835,15 +1835,17 @@ int gzb_be_build_order(gzb_ctx* c, int direction, double target_mul, float below
   GZB_END(c)
 }
 
-int gzb_be_select(gzb_ctx* c, uint64_t p_set, int small_max, int* status, uint64_t* first, uint64_t* last, int* depth,
-                  gzb_order_entry* entries_out) {
+int gzb_be_select_ranges(gzb_ctx* c, uint64_t p_set, int small_max, uint64_t want_end, int* status, int* nranges,
+                         gzb_be_range* ranges, gzb_order_entry* entries_out) {
   GZB_TRY(c)
   gzb_ctx::Backend& B = c->be;
   if (!B.active) return fail(c, GZB_ERR_STATE, "gzb_be_select: gzb_be_begin not called");
-  if (!status || !first || !last || !depth || small_max < 16 || small_max > kBeSmallMax) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_select: bad argument");
+  if (!status || !nranges || !ranges || small_max < 16 || small_max > kBeSmallMax) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_select: bad argument");
   const unsigned pset = static_cast<unsigned>(std::min<uint64_t>(p_set, B.n));
-  KLAUNCH(c, KC_MISC, k_be_select_begin<<<1, 1, 0, c->stream>>>(B.order, B.st, pset, static_cast<unsigned>(small_max)));
-  const size_t bytes = sizeof(BeState) + sizeof(BeEntry) * static_cast<size_t>(small_max);
+  KLAUNCH(c, KC_MISC, k_be_select_begin<<<1, 1, 0, c->stream>>>(B.order, B.st, pset, static_cast<unsigned>(small_max),
+                                                                static_cast<unsigned>(std::min<uint64_t>(want_end, B.n))));
+  // (one range is all a caller without want_end gets: the copy stays short)
+  const size_t bytes = sizeof(BeState) + sizeof(BeEntry) * static_cast<size_t>(want_end > p_set ? kBeSmallMax : small_max);
   BeState* hst = reinterpret_cast<BeState*>(be_pinned(c) + kBePinState);
   // Length of the range the sort will work on first, from the host's copy of the pending ranges: a long range
   // needs about log2(length / kBeLocalMax) grid-level partitions before one CTA can take over. The kernels of a
@@ -1868,7 +1870,7 @@ int gzb_be_select(gzb_ctx* c, uint64_t p_set, int small_max, int* status, uint64
     KLAUNCH(c, KC_MISC, k_be_local<<<1, kBeThreads, 0, c->stream>>>(B.order, B.lpos, B.rpos, B.tcl, B.tcr, B.st, B.small));
     CK(cudaMemcpyAsync(hst, B.st, bytes, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += bytes;
     sync_check(c);
-    if (hst->status != BE_RUNNING) break;
+    if (hst->status != BE_RUNNING || hst->nret > 0) break;
     len = std::max<size_t>(static_cast<size_t>(hst->last - hst->first), 4 * static_cast<size_t>(kBeLocalMax));   // a long range is still in flight
   }
   ++B.selects;
@@ -1876,17 +1878,36 @@ int gzb_be_select(gzb_ctx* c, uint64_t p_set, int small_max, int* status, uint64
   B.h_top = std::max(0, std::min(hst->top, kBeStack));
   memcpy(B.h_stack, hst->stack, sizeof(BeRange) * B.h_top);
   *status = hst->status;
-  if (hst->status == BE_EMPTY || hst->top <= 0) {
+  *nranges = 0;
+  const int nret = static_cast<int>(std::min<unsigned>(hst->nret, kBeMaxRet));
+  if (nret > 0) {
+    // short ranges, consecutive, their entries back to back behind the state (a range the sort stopped at
+    // afterwards for another reason is reported by the next call)
+    *status = BE_SMALL;
+    *nranges = nret;
+    for (int i = 0; i < nret; ++i) ranges[i] = gzb_be_range{hst->ret[i].first, hst->ret[i].last, hst->ret[i].depth, 0};
+    if (entries_out) memcpy(entries_out, reinterpret_cast<const char*>(hst) + sizeof(BeState), sizeof(BeEntry) * hst->ret_total);
+  } else if (hst->status == BE_EMPTY || hst->top <= 0) {
     *status = BE_EMPTY;
-    *first = *last = B.n;
-    *depth = 0;
-  } else {
+  } else {   // BE_HEAP: the caller fetches the range itself
     const BeRange r = hst->stack[hst->top - 1];
-    *first = r.first; *last = r.last; *depth = r.depth;
-    if (hst->status == BE_SMALL && entries_out)
-      memcpy(entries_out, reinterpret_cast<const char*>(hst) + sizeof(BeState), sizeof(BeEntry) * (r.last - r.first));
+    *nranges = 1;
+    ranges[0] = gzb_be_range{r.first, r.last, r.depth, 0};
   }
   GZB_END(c)
+}
+
+int gzb_be_select(gzb_ctx* c, uint64_t p_set, int small_max, int* status, uint64_t* first, uint64_t* last, int* depth,
+                  gzb_order_entry* entries_out) {
+  if (!c) return GZB_ERR_BAD_ARG;
+  if (!first || !last || !depth) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_select: bad argument");
+  int nranges = 0;
+  gzb_be_range r[8];
+  const int rc = gzb_be_select_ranges(c, p_set, small_max, 0, status, &nranges, r, entries_out);
+  if (rc != GZB_OK) return rc;
+  if (nranges > 0) { *first = r[0].first; *last = r[0].last; *depth = r[0].depth; }
+  else { *first = *last = c->be.n; *depth = 0; }
+  return GZB_OK;
 }
 
 int gzb_be_fetch_order(gzb_ctx* c, uint64_t first, gzb_order_entry* out, size_t n) {

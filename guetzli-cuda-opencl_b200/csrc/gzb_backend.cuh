@@ -54,6 +54,7 @@ constexpr int kBeTile = 2048;      // entries per partition tile (256 threads x 
 constexpr int kBeThreads = 256;
 constexpr int kBeSmallMax = 4096;  // longest range handed to the host (capacity of BeState::small)
 constexpr unsigned kBeLocalMax = 16384;   // ranges up to this length are partitioned by one CTA (no grid barriers)
+constexpr int kBeMaxRet = 8;       // short ranges one gzb_be_select_ranges can hand over
 
 enum { BE_RUNNING = 0, BE_SMALL = 1, BE_HEAP = 2, BE_EMPTY = 3 };
 
@@ -76,8 +77,13 @@ struct BeState {
   float pv;
   unsigned ntiles, NL, NR, K;
   unsigned done_count, done_swap;   // CTAs that have finished the count / swap phase of the level in flight
+  // short ranges handed to the host by this select (consecutive, leftmost first; entries back to back in `small`)
+  unsigned want_end;          // keep handing over ranges while they end before this position (and fit)
+  unsigned nret, ret_total, pad_;
+  BeRange ret[kBeMaxRet];
   BeRange stack[kBeStack];
 };
+static_assert(sizeof(BeState) % 8 == 0, "the 8-byte entries of the handed-over ranges follow the state");
 
 __device__ __forceinline__ BeEntry be_ld(const BeEntry* p) { return __ldcg(p); }
 __device__ __forceinline__ void be_st(BeEntry* p, BeEntry v) { __stcg(p, v); }
@@ -344,29 +350,54 @@ k_be_swap(BeEntry* a, const unsigned* lpos, const unsigned* rpos, BeState* st) {
 }
 
 // Short ranges: one CTA partitions level after level for as long as the ranges stay short, then -- if the
-// sort has stopped at a range for the host -- copies that range out.
-//   small : receives the entries of the short range the sort stops at (status BE_SMALL)
+// sort has stopped at a range for the host -- copies that range out. If the caller wants more than that
+// (want_end) and the next pending range is again one this CTA can partition, it carries on with it in the
+// same launch: every range handed over saves the host a round trip.
+//   small : receives the entries of the ranges handed over (BeState::ret), back to back
 __global__ void __launch_bounds__(kBeThreads)
 k_be_local(BeEntry* a, unsigned* lpos, unsigned* rpos, unsigned* tcl, unsigned* tcr, BeState* st, BeEntry* small) {
   __shared__ BeSmem sm;
+  __shared__ int s_more;
   const int tid = threadIdx.x;
   volatile BeState* vst = st;
-  while (vst->status == BE_RUNNING && vst->last - vst->first <= kBeLocalMax) {
-    const BeLevel L = be_level(a, st);
-    be_phase_count(L, 0, 1, tcl, tcr, sm);
-    __threadfence_block(); __syncthreads();
-    be_phase_scan(L, tcl, tcr, st, sm);
-    __threadfence_block(); __syncthreads();
-    be_phase_lists(L, 0, 1, tcl, tcr, lpos, rpos, sm);
-    __threadfence_block(); __syncthreads();
-    be_phase_swap(L, tid, kBeThreads, lpos, rpos, st);
-    __threadfence_block(); __syncthreads();
-    if (tid == 0) { be_phase_finalize(L, a, lpos, rpos, st); __threadfence_block(); }
-    __syncthreads();
-  }
-  if (vst->status == BE_SMALL) {
+  for (;;) {
+    while (vst->status == BE_RUNNING && vst->last - vst->first <= kBeLocalMax) {
+      const BeLevel L = be_level(a, st);
+      be_phase_count(L, 0, 1, tcl, tcr, sm);
+      __threadfence_block(); __syncthreads();
+      be_phase_scan(L, tcl, tcr, st, sm);
+      __threadfence_block(); __syncthreads();
+      be_phase_lists(L, 0, 1, tcl, tcr, lpos, rpos, sm);
+      __threadfence_block(); __syncthreads();
+      be_phase_swap(L, tid, kBeThreads, lpos, rpos, st);
+      __threadfence_block(); __syncthreads();
+      if (tid == 0) { be_phase_finalize(L, a, lpos, rpos, st); __threadfence_block(); }
+      __syncthreads();
+    }
+    if (vst->status != BE_SMALL) break;
     const BeRange r = st->stack[st->top - 1];
-    for (unsigned i = tid; i < r.last - r.first; i += kBeThreads) small[i] = be_ld(a + r.first + i);
+    const unsigned base = vst->ret_total;
+    for (unsigned i = tid; i < r.last - r.first; i += kBeThreads) small[base + i] = be_ld(a + r.first + i);
+    __syncthreads();
+    if (tid == 0) {
+      st->ret[st->nret++] = r;
+      st->ret_total = base + (r.last - r.first);
+      int more = 0;
+      if (st->nret < kBeMaxRet && r.last < st->want_end && st->top >= 2) {
+        const BeRange nx = st->stack[st->top - 2];
+        const unsigned nlen = nx.last - nx.first;
+        if (nlen <= kBeLocalMax && (nlen <= st->small_max || nx.depth > 0) &&
+            st->ret_total + min(nlen, st->small_max) <= static_cast<unsigned>(kBeSmallMax)) {
+          st->p_set = r.last;   // the range just handed over is the host's now
+          be_next_range(st, a);
+          more = 1;
+        }
+      }
+      s_more = more;
+      __threadfence_block();
+    }
+    __syncthreads();
+    if (!s_more) break;
   }
 }
 
@@ -439,9 +470,12 @@ __global__ void k_be_sort_begin(BeState* st, int depth_override = -1) {
 }
 
 // starts a gzb_be_select: the parameters, then the first control step
-__global__ void k_be_select_begin(BeEntry* a, BeState* st, unsigned p_set, unsigned small_max) {
+__global__ void k_be_select_begin(BeEntry* a, BeState* st, unsigned p_set, unsigned small_max, unsigned want_end) {
   st->p_set = p_set;
   st->small_max = small_max;
+  st->want_end = want_end;
+  st->nret = 0;
+  st->ret_total = 0;
   st->levels = 0;
   be_next_range(st, a);
 }

@@ -207,6 +207,12 @@ struct HostLazy {
     pending.clear();
     if (n > 0) pending.push_back({0, n, depth});
   }
+  // several consecutive ranges of buf (leftmost first), each isolated by the sort with its own depth budget
+  void reset_ranges(const R* r, int count) {
+    done = appended = 0;
+    pending.clear();
+    for (int i = count - 1; i >= 0; --i) if (r[i].last > r[i].first) pending.push_back(r[i]);
+  }
   void clear() { buf.clear(); reset(0, 0); }
   // buf[0, p) becomes the SET std::sort would leave there (in no particular order); whatever the split
   // finalises beyond p is reflected in `done`.
@@ -765,13 +771,17 @@ int gzb_test_device_sort_depth(gzb_ctx* ctx, gzb_order_entry* entries, size_t n,
   if (rc != GZB_OK) return rc;
   std::vector<OrderEntry> buf(4096), big;
   size_t have_end = prefix;
+  // small_max < 0: several ranges per round trip (gzb_be_select_ranges), as many as fit
+  const size_t want = small_max < 0 ? 4096 : 0;
+  if (small_max < 0) small_max = -small_max;
   for (;;) {
-    int status = 0, depth = 0;
-    uint64_t f64 = 0, l64 = 0;
-    rc = gzb_be_select(ctx, have_end, small_max, &status, &f64, &l64, &depth, reinterpret_cast<gzb_order_entry*>(buf.data()));
+    int status = 0, nranges = 0;
+    gzb_be_range rr[8];
+    rc = gzb_be_select_ranges(ctx, have_end, small_max, have_end + want, &status, &nranges, rr, reinterpret_cast<gzb_order_entry*>(buf.data()));
     if (rc != GZB_OK) return rc;
     if (status == 3) break;
-    const size_t rf = static_cast<size_t>(f64), rl = static_cast<size_t>(l64);
+    if (nranges < 1 || (want == 0 && nranges != 1)) return GZB_ERR_STATE;
+    const size_t rf = static_cast<size_t>(rr[0].first), rl = static_cast<size_t>(rr[nranges - 1].last);
     OrderEntry* r0 = buf.data();
     if (status == 2) {
       big.resize(rl - rf);
@@ -780,7 +790,10 @@ int gzb_test_device_sort_depth(gzb_ctx* ctx, gzb_order_entry* entries, size_t n,
       exact_sort::heap_sort(big.data(), big.data() + big.size());
       r0 = big.data();
     } else {
-      exact_sort::finish_range(r0, r0 + (rl - rf), depth);
+      for (int i = 0; i < nranges; ++i) {
+        if (i > 0 && rr[i].first != rr[i - 1].last) return GZB_ERR_STATE;   // consecutive
+        exact_sort::finish_range(r0 + (rr[i].first - rf), r0 + (rr[i].last - rf), rr[i].depth);
+      }
     }
     rc = gzb_be_store_order(ctx, rf, reinterpret_cast<const gzb_order_entry*>(r0), rl - rf);
     if (rc != GZB_OK) return rc;
@@ -1164,10 +1177,13 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       std::vector<OrderEntry> range_buf(4096);
       exact_sort::HostLazy lazy;
       std::vector<int> req_blocks;
-      // longest range the device hands over: about what the walk of the previous iteration consumed beyond its
-      // prefix (the state of every block named in the range is fetched with it), within [512, 4096]
+      // The device partitions down to ranges of at most small_max entries and hands over, in one round trip, as
+      // many consecutive ones as cover want_more entries past the prefix: about what the walk of the previous
+      // iteration asked for (the state of every block named in them is fetched too, so more is not free).
       static const int small_max_env = getenv("GZB_BE_SMALL_MAX") ? std::max(16, std::min(4096, atoi(getenv("GZB_BE_SMALL_MAX")))) : 0;
-      int small_max = small_max_env ? small_max_env : 2048;
+      static const int want_env = getenv("GZB_BE_WANT") ? std::max(0, atoi(getenv("GZB_BE_WANT"))) : -1;
+      const int small_max = small_max_env ? small_max_env : 1024;
+      size_t want_more = want_env >= 0 ? want_env : 1024;
       // the coefficient flips of the sequential walk
       struct Flips {
         std::vector<int32_t> block; std::vector<uint8_t> cidx; std::vector<int16_t> val;
@@ -1313,21 +1329,27 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
               order_done = true;
               return gather_blocks(went.data(), went.size());
             }
-            int status = 0, depth = 0;
-            uint64_t f64 = 0, l64 = 0;
+            int status = 0, nranges = 0;
+            gzb_be_range rr[8];
             const double tsel = now_ms();
-            if (gzb_be_select(e.ctx, have_end, small_max, &status, &f64, &l64, &depth, reinterpret_cast<gzb_order_entry*>(range_buf.data())) != GZB_OK)
+            // (the walk of the previous iteration is the best guess of how far this one will get)
+            if (gzb_be_select_ranges(e.ctx, have_end, small_max, have_end + want_more, &status, &nranges, rr,
+                                     reinterpret_cast<gzb_order_entry*>(range_buf.data())) != GZB_OK)
               return false;
             e.st.be_select_ms += now_ms() - tsel;
-            const size_t rf = static_cast<size_t>(f64), rl = static_cast<size_t>(l64);
-            if (status == 3) { order_done = true; return true; }
+            if (status == 3 || nranges <= 0) { order_done = true; return true; }
+            const size_t rf = static_cast<size_t>(rr[0].first), rl = static_cast<size_t>(rr[nranges - 1].last);
             if (status == 2) {   // depth budget exhausted on a long range: std::sort heap-sorts it
               lazy.buf.resize(rl - rf);
               if (gzb_be_fetch_order(e.ctx, rf, reinterpret_cast<gzb_order_entry*>(lazy.buf.data()), rl - rf) != GZB_OK) return false;
               lazy.reset(rl - rf, 0);
             } else {
               lazy.buf.assign(range_buf.begin(), range_buf.begin() + (rl - rf));
-              lazy.reset(rl - rf, depth);
+              exact_sort::HostLazy::R lr[8];
+              for (int i = 0; i < nranges; ++i)
+                lr[i] = {static_cast<size_t>(rr[i].first) - rf, static_cast<size_t>(rr[i].last) - rf, rr[i].depth};
+              lazy.reset_ranges(lr, nranges);
+              e.st.be_host_ranges += nranges - 1;
             }
             ++e.st.be_host_ranges;
             const size_t head = have_end > rf ? have_end - rf : 0;   // entries of the range that belong to the prefix
@@ -1540,10 +1562,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           }
           if (fetch_failed) return fail(GZB_ERR_CUDA);
           if (changed_coeffs > 0) val_threshold = went[last_step - wbase].second;
-          if (!small_max_env) {
-            const size_t walked = last_step + 1 - prefix;
-            small_max = static_cast<int>(std::min<size_t>(4096, std::max<size_t>(1024, (2 * walked + 255) / 256 * 256)));
-          }
+          if (want_env < 0) want_more = std::min<size_t>(3072, std::max<size_t>(256, went.size() + went.size() / 8 + 64));
           const size_t changed_blocks = static_cast<size_t>(prefix_changed_blocks + walk_changed_blocks);
           { const double t1 = now_ms(); e.st.be_walk_ms += t1 - tt; tt = t1; }
           ++e.st.num_iterations;

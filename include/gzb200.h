@@ -236,6 +236,13 @@ int gzb_be_build_order(gzb_ctx* ctx, int direction, double target_mul, float bel
  * budget (std::sort heap-sorts it: fetch, std::partial_sort, store); 3: nothing is pending. */
 int gzb_be_select(gzb_ctx* ctx, uint64_t p_set, int small_max, int* status, uint64_t* first,
                   uint64_t* last, int* depth, gzb_order_entry* entries_out);
+/* The same for a caller that expects to need the order up to position want_end: up to 8 consecutive short
+ * ranges (leftmost first, at most 4096 entries together, entries back to back in entries_out) in one
+ * round trip -- the device goes on to the next pending range as long as one thread block can partition
+ * it. status 1: *nranges ranges; 2: ranges[0] needs the heap sort; 3: nothing is pending. */
+typedef struct { uint64_t first, last; int depth; int reserved; } gzb_be_range;
+int gzb_be_select_ranges(gzb_ctx* ctx, uint64_t p_set, int small_max, uint64_t want_end, int* status,
+                         int* nranges, gzb_be_range* ranges, gzb_order_entry* entries_out);
 int gzb_be_fetch_order(gzb_ctx* ctx, uint64_t first, gzb_order_entry* out, size_t n);
 int gzb_be_store_order(gzb_ctx* ctx, uint64_t first, const gzb_order_entry* in, size_t n);
 /* Consumes order[0, p) as a set (processor.cc:854-876 for each entry; the order of the entries does not

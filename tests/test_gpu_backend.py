@@ -50,7 +50,8 @@ def test_device_lazy_sort_equals_std_sort(gz, ctx, n):
         a_id, a_v = ids.copy(), v.copy()
         L.gzb_test_std_sort(p(a_id), p(a_v), n)
         prefixes = sorted({0, n // 50, n // 3, max(0, n - 10)})
-        smalls = (16, 1024, 4096) if n <= 70000 else (1024,)
+        # (a negative length asks for several short ranges per round trip: gzb_be_select_ranges)
+        smalls = (16, 1024, 4096, -64, -1024) if n <= 70000 else (1024, -512)
         for small in smalls:
             for pfx in prefixes:
                 e = np.zeros(n, entry)
@@ -77,10 +78,10 @@ def test_device_lazy_sort_with_exhausted_depth_budget(gz, ctx, n, depth):
         ids = np.arange(n, dtype=np.int32)
         a_id, a_v = ids.copy(), v.copy()
         L.gzb_test_exact_sort_depth(p(a_id), p(a_v), n, depth)
-        for pfx in (0, n // 3):
+        for pfx, small in ((0, 1024), (n // 3, 1024), (n // 3, -256)):
             e = np.zeros(n, entry)
             e["block"], e["value"] = ids, v
-            assert L.gzb_test_device_sort_depth(ctx._ctx, p(e), n, pfx, 1024, depth) == 0
+            assert L.gzb_test_device_sort_depth(ctx._ctx, p(e), n, pfx, small, depth) == 0
             assert np.array_equal(e["block"][pfx:], a_id[pfx:]), (name, n, depth, pfx)
             assert np.array_equal(e["value"][pfx:], a_v[pfx:]), (name, n, depth, pfx)
             assert np.array_equal(np.sort(e["block"][:pfx]), np.sort(a_id[:pfx])), (name, n, depth, pfx)
