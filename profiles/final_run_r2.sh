@@ -18,3 +18,11 @@ for f in ["r2_bench_12mpix_q95","r2_bench_reference_arm","r2_bench_reference_cud
         d=json.load(open("gpurun_out/%s.json"%f)); print(f, d.get("value"), d.get("e2e",{}).get("value"), d.get("ms_per_step"))
     except Exception as e: print(f, "ERR", e)
 PY
+# launch list of one whole encode of the bench workload (after the plain runs above exited 0)
+TMP=/tmp/ncu_r2; mkdir -p $TMP
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file $TMP/r2_launches_12mpix.csv python profiles/encode_probe.py 4000 3000 95 > $O/r2_launches.log 2>&1
+python profiles/summarize.py launches $TMP/r2_launches_12mpix.csv \
+    "ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none python profiles/encode_probe.py 4000 3000 95" > $O/r2_launches_12mpix.md
+gzip -c $TMP/r2_launches_12mpix.csv > $O/r2_launches_12mpix.csv.gz
+head -20 $O/r2_launches_12mpix.md
