@@ -1711,6 +1711,8 @@ void be_reserve(gzb_ctx* c, int num_blocks, size_t total) {
     CK(cudaMallocHost(&c->slab.be_pinned, kBePinBytes));
     c->slab.be_pinned_cap = kBePinBytes;
   }
+  // (per device; the call is cheap)
+  CK(cudaFuncSetAttribute(k_be_local, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBeLocalSmemBytes)));
   char* base = static_cast<char*>(c->slab.be);
   B.st = reinterpret_cast<BeState*>(base + o_state);
   B.small = reinterpret_cast<BeEntry*>(base + o_state + sizeof(BeState));
@@ -1867,7 +1869,7 @@ int gzb_be_select_ranges(gzb_ctx* c, uint64_t p_set, int small_max, uint64_t wan
       KLAUNCH(c, KC_MISC, k_be_tiles_lists<<<G, kBeThreads, 0, c->stream>>>(B.order, B.lpos, B.rpos, B.tcl, B.tcr, B.st));
       KLAUNCH(c, KC_MISC, k_be_swap<<<G, kBeThreads, 0, c->stream>>>(B.order, B.lpos, B.rpos, B.st));
     }
-    KLAUNCH(c, KC_MISC, k_be_local<<<1, kBeThreads, 0, c->stream>>>(B.order, B.lpos, B.rpos, B.tcl, B.tcr, B.st, B.small));
+    KLAUNCH(c, KC_MISC, k_be_local<<<1, kBeLocalThreads, kBeLocalSmemBytes, c->stream>>>(B.order, B.st, B.small));
     CK(cudaMemcpyAsync(hst, B.st, bytes, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += bytes;
     sync_check(c);
     if (hst->status != BE_RUNNING || hst->nret > 0) break;

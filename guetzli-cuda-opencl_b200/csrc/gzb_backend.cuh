@@ -9,7 +9,7 @@
 //
 //   k_be_count / k_scan_counts / k_be_fill : the order, in the reference's block-major arrangement
 //       (processor.cc:786-813), values (err - max_err) / weight in IEEE float like the host code;
-//   k_be_tiles_* / k_be_swap / k_be_finalize / k_be_local : libstdc++'s introsort
+//   k_be_tiles_* / k_be_swap / k_be_local : libstdc++'s introsort
 //       (std::sort = __introsort_loop + __final_insertion_sort) evaluated lazily: they run the library's
 //       median-of-three + unguarded Hoare partition steps -- the same element swaps, so that ties
 //       between blocks end up exactly where std::sort puts them -- only on the ranges that straddle
@@ -133,9 +133,9 @@ __device__ inline void be_next_range(BeState* st, BeEntry* a) {
 }
 
 // ---- one std::__unguarded_partition_pivot of the range in *st (pivot already at `first`) -----------
-// Five phases with a grid-wide dependency between them. A long range runs them as five launches on a
-// grid of CTAs (k_be_tiles_count .. k_be_finalize); a range of at most kBeLocalMax entries runs all of
-// them inside ONE CTA (k_be_local), which keeps going level after level while the ranges stay short.
+// Five phases with a grid-wide dependency between them. A long range runs them as three launches on a
+// grid of CTAs (k_be_tiles_count, k_be_tiles_lists, k_be_swap); a range of at most kBeLocalMax entries is
+// partitioned by ONE CTA in shared memory (k_be_local), level after level while the ranges stay short.
 // No kernel ever waits for another CTA, so any number of contexts can sort concurrently.
 struct BeLevel {
   unsigned first, last, m, ntiles;
@@ -349,55 +349,285 @@ k_be_swap(BeEntry* a, const unsigned* lpos, const unsigned* rpos, BeState* st) {
   if (be_last_cta(&st->done_swap) && threadIdx.x == 0) be_phase_finalize(L, a, lpos, rpos, st);
 }
 
-// Short ranges: one CTA partitions level after level for as long as the ranges stay short, then -- if the
-// sort has stopped at a range for the host -- copies that range out. If the caller wants more than that
-// (want_end) and the next pending range is again one this CTA can partition, it carries on with it in the
-// same launch: every range handed over saves the host a round trip.
+// ---- short ranges: one CTA, the range in shared memory ------------------------------------------------
+// A range of at most kBeLocalMax entries is loaded into shared memory once and partitioned there level after
+// level (the library's partition restated with ballots: the k-th stopper from either side is found by a
+// binary search over per-chunk counts instead of from stored lists), then written back. When the sort has
+// stopped at a range for the host, the kernel copies it out; if the caller wants more than that (want_end)
+// and the next pending range is again one this CTA can partition, it carries on with it in the same launch:
+// every range handed over saves the host a round trip.
 //   small : receives the entries of the ranges handed over (BeState::ret), back to back
-__global__ void __launch_bounds__(kBeThreads)
-k_be_local(BeEntry* a, unsigned* lpos, unsigned* rpos, unsigned* tcl, unsigned* tcr, BeState* st, BeEntry* small) {
-  __shared__ BeSmem sm;
-  __shared__ int s_more;
-  const int tid = threadIdx.x;
-  volatile BeState* vst = st;
-  for (;;) {
-    while (vst->status == BE_RUNNING && vst->last - vst->first <= kBeLocalMax) {
-      const BeLevel L = be_level(a, st);
-      be_phase_count(L, 0, 1, tcl, tcr, sm);
-      __threadfence_block(); __syncthreads();
-      be_phase_scan(L, tcl, tcr, st, sm);
-      __threadfence_block(); __syncthreads();
-      be_phase_lists(L, 0, 1, tcl, tcr, lpos, rpos, sm);
-      __threadfence_block(); __syncthreads();
-      be_phase_swap(L, tid, kBeThreads, lpos, rpos, st);
-      __threadfence_block(); __syncthreads();
-      if (tid == 0) { be_phase_finalize(L, a, lpos, rpos, st); __threadfence_block(); }
-      __syncthreads();
+constexpr int kBeLocalThreads = 1024;
+constexpr int kBeLocalChunks = kBeLocalMax / 32;   // ballot words of a level
+struct BeLocalSmem {
+  BeState st;                                          // working copy of the state
+  unsigned bl[kBeLocalChunks], br[kBeLocalChunks];     // stopper ballots: bit = entry is not less / not greater than the pivot
+  unsigned exl[kBeLocalChunks];                        // left stoppers before chunk c
+  unsigned inr[kBeLocalChunks + 1];                    // right stoppers in chunks >= c
+  unsigned wsum[2][32];
+  unsigned NL, NR, K;
+  unsigned wlo, whi;                                   // entries [wlo, whi) of the order are held in shared memory (none: whi == wlo)
+  int action;
+};
+constexpr size_t kBeLocalSmemBytes = sizeof(BeEntry) * kBeLocalMax + sizeof(BeLocalSmem);
+enum { BE_ACT_LEVEL = 0, BE_ACT_LOAD = 1, BE_ACT_LOAD_PIVOT = 2, BE_ACT_BIG = 3, BE_ACT_STOP = 4, BE_ACT_EXIT = 5 };
+
+// position of the n-th (0-based, from bit 0) set bit of m
+__device__ __forceinline__ unsigned be_nth_set_bit(unsigned m, unsigned n) {
+  unsigned pos = 0;
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const unsigned c = __popc((m >> pos) & ((1u << w) - 1u));
+    if (n >= c) { n -= c; pos += w; }
+  }
+  return pos;
+}
+// position (relative to A) of the right stopper of rank k from the right / the left stopper of rank k from the left
+__device__ __forceinline__ unsigned be_local_select_right(const BeLocalSmem& s, unsigned nchunks, unsigned k) {
+  unsigned lo = 0, hi = nchunks;   // inr[lo] > k >= inr[hi]
+  while (hi - lo > 1) {
+    const unsigned mid = (lo + hi) >> 1;
+    if (s.inr[mid] > k) lo = mid; else hi = mid;
+  }
+  const unsigned m = s.br[lo], j = k - s.inr[lo + 1];   // rank j counted from the top bit
+  return 32u * lo + be_nth_set_bit(m, __popc(m) - 1u - j);
+}
+__device__ __forceinline__ unsigned be_local_select_left(const BeLocalSmem& s, unsigned nchunks, unsigned k) {
+  unsigned lo = 0, hi = nchunks;   // exl[lo] <= k < exl[hi]
+  while (hi - lo > 1) {
+    const unsigned mid = (lo + hi) >> 1;
+    if (s.exl[mid] <= k) lo = mid; else hi = mid;
+  }
+  return 32u * lo + be_nth_set_bit(s.bl[lo], k - s.exl[lo]);
+}
+
+// std::__move_median_to_first on the window (indices relative to it)
+__device__ inline void be_local_median(BeEntry* e, unsigned first, unsigned last) {
+  const unsigned ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
+  const BeEntry ea = e[ia], eb = e[ib], ec = e[ic];
+  const float va = be_val(ea), vb = be_val(eb), vc = be_val(ec);
+  unsigned pick;
+  if (va < vb) {
+    if (vb < vc) pick = ib;
+    else if (va < vc) pick = ic;
+    else pick = ia;
+  } else if (va < vc) pick = ia;
+  else if (vb < vc) pick = ic;
+  else pick = ib;
+  const BeEntry ef = e[first];
+  e[first] = pick == ia ? ea : pick == ib ? eb : ec;
+  e[pick] = ef;
+}
+
+// one std::__unguarded_partition_pivot of [st.first, st.last) inside the window (pivot at its first entry),
+// then (thread 0) the two new ranges
+__device__ __forceinline__ void be_local_level(BeEntry* e, BeLocalSmem& s) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned f = s.st.first - s.wlo, m = s.st.last - s.st.first - 1;
+  BeEntry* A = e + f + 1;
+  const float pv = s.st.pv;
+  const unsigned nchunks = (m + 31) >> 5;
+  for (unsigned c = warp; c < nchunks; c += kBeLocalThreads / 32) {
+    const unsigned i = 32 * c + lane;
+    bool fl = false, fr = false;
+    if (i < m) {
+      const float v = be_val(A[i]);
+      fl = !(v < pv);
+      fr = !(pv < v);
     }
-    if (vst->status != BE_SMALL) break;
-    const BeRange r = st->stack[st->top - 1];
-    const unsigned base = vst->ret_total;
-    for (unsigned i = tid; i < r.last - r.first; i += kBeThreads) small[base + i] = be_ld(a + r.first + i);
-    __syncthreads();
-    if (tid == 0) {
-      st->ret[st->nret++] = r;
-      st->ret_total = base + (r.last - r.first);
-      int more = 0;
-      if (st->nret < kBeMaxRet && r.last < st->want_end && st->top >= 2) {
-        const BeRange nx = st->stack[st->top - 2];
-        const unsigned nlen = nx.last - nx.first;
-        if (nlen <= kBeLocalMax && (nlen <= st->small_max || nx.depth > 0) &&
-            st->ret_total + min(nlen, st->small_max) <= static_cast<unsigned>(kBeSmallMax)) {
-          st->p_set = r.last;   // the range just handed over is the host's now
-          be_next_range(st, a);
-          more = 1;
+    const unsigned b1 = __ballot_sync(0xffffffffu, fl), b2 = __ballot_sync(0xffffffffu, fr);
+    if (lane == 0) { s.bl[c] = b1; s.br[c] = b2; }
+  }
+  __syncthreads();
+  // chunk t belongs to thread t: left counts scanned forward, right counts backward
+  unsigned cl = 0, cr = 0;
+  if (tid < kBeLocalChunks && static_cast<unsigned>(tid) < nchunks) { cl = __popc(s.bl[tid]); cr = __popc(s.br[tid]); }
+  unsigned il = cl, ir = cr;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned vl = __shfl_up_sync(0xffffffffu, il, off), vr = __shfl_down_sync(0xffffffffu, ir, off);
+    if (lane >= off) il += vl;
+    if (lane + off < 32) ir += vr;
+  }
+  if (warp < kBeLocalChunks / 32) {
+    if (lane == 31) s.wsum[0][warp] = il;
+    if (lane == 0) s.wsum[1][warp] = ir;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const bool in = lane < kBeLocalChunks / 32;
+    const unsigned wl = in ? s.wsum[0][lane] : 0u, wr = in ? s.wsum[1][lane] : 0u;
+    unsigned sl = wl, sr = wr;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned vl = __shfl_up_sync(0xffffffffu, sl, off), vr = __shfl_down_sync(0xffffffffu, sr, off);
+      if (lane >= off) sl += vl;
+      if (lane + off < 32) sr += vr;
+    }
+    s.wsum[0][lane] = sl - wl;   // left stoppers in the warps before this one
+    s.wsum[1][lane] = sr - wr;   // right stoppers in the warps after this one
+    if (lane == 31) s.NL = sl;
+    if (lane == 0) { s.NR = sr; s.K = 0; s.inr[kBeLocalChunks] = 0; }
+  }
+  __syncthreads();
+  if (tid < kBeLocalChunks) {
+    s.exl[tid] = s.wsum[0][warp] + il - cl;
+    s.inr[tid] = s.wsum[1][warp] + ir;
+  }
+  __syncthreads();
+  // the swaps: pair k is swapped iff its left stopper lies left of its right stopper (monotone in k)
+  const unsigned NL = s.NL, NR = s.NR, lim = min(NL, NR);
+  unsigned cnt = 0;
+  for (unsigned c = warp; c < nchunks; c += kBeLocalThreads / 32) {
+    const unsigned b1 = s.bl[c];
+    if (b1 >> lane & 1u) {
+      const unsigned k = s.exl[c] + __popc(b1 & ((1u << lane) - 1u));
+      if (k < lim) {
+        const unsigned i = 32 * c + lane, r = be_local_select_right(s, nchunks, k);
+        if (i < r) {
+          const BeEntry x = A[i], y = A[r];
+          A[i] = y;
+          A[r] = x;
+          ++cnt;
         }
       }
-      s_more = more;
-      __threadfence_block();
     }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  if (lane == 0 && cnt) atomicAdd(&s.K, cnt);
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned K = s.K;
+    unsigned cut = m;   // the scans are guarded by the median-of-three: a stopper exists
+    if (K < NL) cut = min(cut, be_local_select_left(s, nchunks, K));
+    if (K > 0) cut = min(cut, be_local_select_right(s, nchunks, K - 1));
+    const unsigned gcut = s.st.first + 1 + cut;
+    const int depth = s.st.depth;
+    s.st.stack[s.st.top++] = BeRange{gcut, s.st.last, depth, 0};
+    s.st.stack[s.st.top++] = BeRange{s.st.first, gcut, depth, 0};
+  }
+}
+
+// be_next_range on the working copy (thread 0): the action the CTA takes next
+__device__ inline int be_local_next(BeLocalSmem& s, BeEntry* e) {
+  BeState& st = s.st;
+  for (;;) {
+    if (st.top == 0) { st.status = BE_EMPTY; return BE_ACT_STOP; }
+    const BeRange r = st.stack[st.top - 1];
+    if (r.last <= st.p_set) { --st.top; continue; }
+    const unsigned len = r.last - r.first;
+    if (len <= st.small_max) { st.status = BE_SMALL; return BE_ACT_STOP; }
+    if (r.depth == 0) { st.status = BE_HEAP; return BE_ACT_STOP; }
+    if (len > kBeLocalMax) return BE_ACT_BIG;   // a long range: the grid kernels' turn
+    --st.top;
+    st.first = r.first;
+    st.last = r.last;
+    st.depth = r.depth - 1;
+    st.status = BE_RUNNING;
+    ++st.levels;
+    if (s.whi > s.wlo && r.first >= s.wlo && r.last <= s.whi) {
+      be_local_median(e, r.first - s.wlo, r.last - s.wlo);
+      st.pv = be_val(e[r.first - s.wlo]);
+      return BE_ACT_LEVEL;
+    }
+    return BE_ACT_LOAD_PIVOT;
+  }
+}
+
+__global__ void __launch_bounds__(kBeLocalThreads)
+k_be_local(BeEntry* a, BeState* st, BeEntry* small) {
+  extern __shared__ unsigned long long be_local_dyn[];
+  BeEntry* e = be_local_dyn;
+  BeLocalSmem& s = *reinterpret_cast<BeLocalSmem*>(be_local_dyn + kBeLocalMax);
+  const int tid = threadIdx.x;
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(st);
+    unsigned* dst = reinterpret_cast<unsigned*>(&s.st);
+    for (unsigned i = tid; i < sizeof(BeState) / 4; i += kBeLocalThreads) dst[i] = __ldcg(src + i);
+  }
+  if (tid == 0) { s.wlo = 0; s.whi = 0; }
+  __syncthreads();
+  if (tid == 0) {
+    // (a range in flight has its pivot in place already: the control step that started it ran on the array in HBM)
+    if (s.st.status == BE_RUNNING) s.action = s.st.last - s.st.first <= kBeLocalMax ? BE_ACT_LOAD : BE_ACT_EXIT;
+    else s.action = BE_ACT_STOP;
+  }
+  __syncthreads();
+  auto flush = [&]() {
+    const unsigned wlo = s.wlo, n = s.whi - s.wlo;
+    for (unsigned i = tid; i < n; i += kBeLocalThreads) be_st(a + wlo + i, e[i]);
+  };
+  for (;;) {
+    int act = s.action;
+    if (act == BE_ACT_LOAD || act == BE_ACT_LOAD_PIVOT) {
+      flush();
+      __syncthreads();
+      const unsigned first = s.st.first, n = s.st.last - s.st.first;
+      for (unsigned i = tid; i < n; i += kBeLocalThreads) e[i] = be_ld(a + first + i);
+      __syncthreads();
+      if (tid == 0) {
+        s.wlo = first;
+        s.whi = first + n;
+        if (act == BE_ACT_LOAD_PIVOT) {
+          be_local_median(e, 0, n);
+          s.st.pv = be_val(e[0]);
+        }
+      }
+      __syncthreads();
+      act = BE_ACT_LEVEL;
+    }
+    if (act == BE_ACT_LEVEL) {
+      be_local_level(e, s);
+      if (tid == 0) s.action = be_local_next(s, e);
+      __syncthreads();
+      continue;
+    }
+    if (act == BE_ACT_STOP && s.st.status == BE_SMALL) {
+      // hand the range over; maybe go on with the next one
+      const BeRange r = s.st.stack[s.st.top - 1];
+      const unsigned base = s.st.ret_total, n = r.last - r.first;
+      if (s.whi > s.wlo && r.first >= s.wlo && r.last <= s.whi) {
+        for (unsigned i = tid; i < n; i += kBeLocalThreads) small[base + i] = e[r.first - s.wlo + i];
+      } else {
+        for (unsigned i = tid; i < n; i += kBeLocalThreads) small[base + i] = be_ld(a + r.first + i);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        BeState& w = s.st;
+        w.ret[w.nret++] = r;
+        w.ret_total = base + n;
+        int next = BE_ACT_EXIT;
+        if (w.nret < static_cast<unsigned>(kBeMaxRet) && r.last < w.want_end && w.top >= 2) {
+          const BeRange nx = w.stack[w.top - 2];
+          const unsigned nlen = nx.last - nx.first;
+          if (nlen <= kBeLocalMax && (nlen <= w.small_max || nx.depth > 0) &&
+              w.ret_total + min(nlen, w.small_max) <= static_cast<unsigned>(kBeSmallMax)) {
+            w.p_set = r.last;   // the range just handed over is the host's now
+            next = be_local_next(s, e);
+          }
+        }
+        s.action = next;
+      }
+      __syncthreads();
+      if (s.action == BE_ACT_EXIT) break;
+      continue;
+    }
+    break;   // BE_ACT_BIG, BE_ACT_EXIT, or stopped at an exhausted depth budget / an empty stack
+  }
+  const int last_act = s.action;
+  __syncthreads();
+  flush();
+  {
+    unsigned* dst = reinterpret_cast<unsigned*>(st);
+    const unsigned* src = reinterpret_cast<const unsigned*>(&s.st);
+    for (unsigned i = tid; i < sizeof(BeState) / 4; i += kBeLocalThreads) __stcg(dst + i, src[i]);
+  }
+  if (last_act == BE_ACT_BIG) {
+    // the next range is a long one: its control step (median of three, level set-up) runs on the array in HBM
+    __threadfence();
     __syncthreads();
-    if (!s_more) break;
+    if (tid == 0) be_next_range(st, a);
   }
 }
 

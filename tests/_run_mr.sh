@@ -2,6 +2,4 @@
 timeout 600 python -m pytest tests/test_gpu_backend.py tests/test_gpu_encode.py -m gpu -x -q 2>&1 | tail -5
 for cfg in "1024 1024 90" "1920 1080 95" "4000 3000 95"; do
   timeout 200 python tests/perf_quick.py $cfg 3 2>&1 | tail -2
-  GZB_BE_WANT=0 timeout 200 python tests/perf_quick.py $cfg 3 2>&1 | tail -2
-  GZB_BE_WANT=0 GZB_BE_SMALL_MAX=2048 timeout 200 python tests/perf_quick.py $cfg 3 2>&1 | tail -2
 done
