@@ -607,7 +607,17 @@ void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
   }
   // (block_diff_ac cells outside the kernel's domain were zeroed once, at context creation)
   const BlockChanges bc{c->d_blk_changed, c->d_scalars + 4, c->bw, c->bh};
-  KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac, dmask(c, DS_BDM), bc));
+  static const int strip_env = getenv("GZB_BDM_STRIP") ? atoi(getenv("GZB_BDM_STRIP")) : 1;
+  if (strip_env) {
+    const int strips = ncx * ((ncy + kBsCells - 1) / kBsCells);
+    // (128 threads, 7 CTAs per SM: the best of 128x7/8, 160x5/6, 192x5, 256x4 on a B200 -- profiles/r2_bdm_strip.md)
+    const int sctas = std::min(strips, c->sm_count * kBsMinCtas * 4);
+    CK(cudaFuncSetAttribute(k_block_diff_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BsSmem))));
+    CK(cudaFuncSetAttribute(k_block_diff_strip, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_diff_strip<<<sctas, kBsThreads, sizeof(BsSmem), sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_ac, dmask(c, DS_BDM), bc));
+  } else {
+    KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac, dmask(c, DS_BDM), bc));
+  }
   KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_dc<<<(cells + 127) / 128, 128, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, dmask(c, DS_BDM), bc));
   if (c->concurrent) CK(cudaEventRecord(c->ev_bdm, sb));
   // EdgeDetectorLowFreq (its blur scratch is the first part of d_tmp, the main stream's the rest)

@@ -869,6 +869,180 @@ k_block_diff_map(const float* __restrict__ a, const float* __restrict__ b, size_
   }
 }
 
+// K6': the same AC term, a CTA per vertical strip of kBsCells cells. Cells are 3 px apart and their
+// windows 8 px high, so a row of a window is shared by 8/3 cells: the strip computes the average /
+// half-difference planes and the row transforms ONCE per image row (29 rows instead of 8 x 8), and every stage
+// is a flat loop of independent tasks over the CTA's threads -- the warp-per-cell kernel above leaves 12 of 32
+// lanes idle in the column transforms, runs the 33 per-frequency terms as two passes of 32 lanes and the three
+// ordered sums on 3 lanes. Per-element arithmetic (and so every bit of the result) is that of warp_block_diff.
+constexpr int kBsCells = 8, kBsThreads = 128, kBsMinCtas = 7;
+constexpr int kBsRows = 3 * (kBsCells - 1) + 8;      // 29 image rows under a strip
+constexpr int kBsPlane = kBsRows * 9;                // a plane: rows of 8 doubles padded to 9
+// Strides (in doubles) chosen so that the 16 lanes of a half-warp hit 16 different bank pairs where it matters:
+constexpr int kBsSpecRow = 40;                       // a (plane, bin) column of the row spectra; = 8 mod 16: the column
+                                                     // transforms run cell-fastest, 8 cells (3 rows apart) x 2 columns
+constexpr int kBsPow = 41;                           // power spectrum of one (cell, plane): 40 used bins; odd
+constexpr int kBsPowCell = 178;                      // ... of one cell (4 planes); = 2 mod 16
+struct BsSmem {
+  // Two regions, each reused once its first tenant is dead: the samples and the planes (read by stages 1 and
+  // 3) make room for the power spectra (written by stage 4), the row spectra (read by stage 4) for the
+  // per-frequency terms (written by stage 5).
+  union {
+    struct {
+      float in[2][3][kBsRows][9];                    // the two images' samples under the strip (rows padded: stage 1 runs row-fastest)
+      double pl[4][kBsPlane];                        // y_avg, x/y/z half-differences
+    } a;
+    double pw[kBsCells][kBsPowCell];                 // power spectra: bin 8u + v of plane p at kBsPow * p + 8u + (v ^ u)
+  } u1;
+  union {
+    struct { double sre[4 * 5][kBsSpecRow], sim[4 * 5][kBsSpecRow]; } b;   // row spectra: [plane * 5 + bin][row]
+    double term[kBsCells][3][33];
+  } u2;
+  double csf[37];                                    // kCsf8x8 (indexed per lane: not from the constant bank)
+  int oy[kBsCells];                                  // window origin of each cell (clamped at the bottom border)
+  int list[kBsCells], nlist;
+  unsigned char row_need[kBsRows + 3];
+};
+__global__ void __launch_bounds__(kBsThreads, kBsMinCtas)
+k_block_diff_strip(const float* __restrict__ a, const float* __restrict__ b, size_t stride, int W, int H, int P, int rxs,
+                   int ncx, int ncy, float* __restrict__ ac_out, DirtyMask dm, BlockChanges bc) {
+  extern __shared__ unsigned long long bs_dyn[];
+  BsSmem& s = *reinterpret_cast<BsSmem*>(bs_dyn);
+  const int tid = threadIdx.x;
+  const int nsy = (ncy + kBsCells - 1) / kBsCells, total = ncx * nsy;
+  const bool fine = bc.chg != nullptr && *bc.enable != 0;
+  const bool all = dm.m == nullptr && !fine;   // a full Compare: every cell
+  if (tid < 37) s.csf[tid] = kCsf8x8[tid];
+  for (int strip = blockIdx.x; strip < total; strip += gridDim.x) {
+    const int sy = strip / ncx, rx = strip - sy * ncx;
+    const int ry0 = sy * kBsCells, ncell = min(kBsCells, ncy - ry0);
+    const int ox = min(3 * rx, W - 8), y_lo = min(3 * ry0, H - 8);
+    __syncthreads();   // the previous strip's terms have been summed
+    if (tid < 32) {    // warp 0: which cells, in a compact list
+      bool need = false;
+      int oy = y_lo;
+      if (tid < ncell) {
+        const int ry = ry0 + tid;
+        oy = min(3 * ry, H - 8);
+        need = all || (dirty_at(dm, 3 * rx, 3 * ry) && (!fine || cell_window_changed(bc, ox, oy)));
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, need);
+      if (tid < kBsCells) s.oy[tid] = oy;
+      if (need) s.list[__popc(m & ((1u << tid) - 1u))] = tid;
+      if (tid == 0) s.nlist = __popc(m);
+      // rows some needed cell covers
+      bool rn = false;
+#pragma unroll
+      for (int k = 0; k < kBsCells; ++k) {
+        const int r0 = __shfl_sync(0xffffffffu, oy, k) - y_lo;
+        rn = rn || ((m >> k & 1u) && tid >= r0 && tid < r0 + 8);
+      }
+      if (tid < kBsRows) s.row_need[tid] = rn ? 1 : 0;
+    }
+    __syncthreads();
+    const int nlist = s.nlist;
+    if (nlist == 0) continue;   // (uniform)
+    const int nrows = s.oy[ncell - 1] + 8 - y_lo;
+    // samples: 2 images x 3 channels x nrows x 8 (all loads of a thread in flight before the first store)
+    {
+      constexpr int kPer = (6 * kBsRows * 8 + kBsThreads - 1) / kBsThreads;
+      float v[kPer];
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const int i = tid + j * kBsThreads;
+        const int x = i & 7, r = (i >> 3) % kBsRows, pc = i / (8 * kBsRows);   // pc = image * 3 + channel
+        v[j] = 0.0f;
+        if (i < 6 * kBsRows * 8 && r < nrows && s.row_need[r]) {
+          const int ch = pc >= 3 ? pc - 3 : pc;
+          v[j] = __ldg((pc >= 3 ? b : a) + ch * stride + static_cast<size_t>(y_lo + r) * P + ox + x);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const int i = tid + j * kBsThreads;
+        if (i < 6 * kBsRows * 8) (&s.u1.a.in[0][0][0][0])[(i >> 3) * 9 + (i & 7)] = v[j];
+      }
+    }
+    __syncthreads();
+    // (1) planes (row-fastest: the strides of 9 floats / 9 doubles keep the lanes on different banks)
+    for (int i = tid; i < kBsRows * 8; i += kBsThreads) {
+      const int x = i / kBsRows, r = i - x * kBsRows;
+      if (r < nrows && s.row_need[r]) {
+        const double a0 = s.u1.a.in[0][0][r][x], a1 = s.u1.a.in[0][1][r][x], a2 = s.u1.a.in[0][2][r][x];
+        const double b0 = s.u1.a.in[1][0][r][x], b1 = s.u1.a.in[1][1][r][x], b2 = s.u1.a.in[1][2][r][x];
+        const int o = r * 9 + x;
+        s.u1.a.pl[0][o] = (a1 + b1) / 2;
+        s.u1.a.pl[1][o] = (a0 - b0) / 2;
+        s.u1.a.pl[2][o] = (a1 - b1) / 2;
+        s.u1.a.pl[3][o] = (a2 - b2) / 2;
+      }
+    }
+    __syncthreads();
+    // (3) row transforms, once per (plane, image row)
+    for (int t = tid; t < 4 * kBsRows; t += kBsThreads) {
+      const int plane = t / kBsRows, r = t - plane * kBsRows;
+      if (r < nrows && s.row_need[r]) {
+        double x[8], re[5], im[5];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = s.u1.a.pl[plane][9 * r + k];
+        rfft8_half(x, re, im);
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          s.u2.b.sre[plane * 5 + u][r] = re[u];
+          s.u2.b.sim[plane * 5 + u][r] = im[u];
+        }
+      }
+    }
+    __syncthreads();
+    // (4) column transforms: task = (needed cell, plane, bin u). The power spectra overwrite the samples and
+    // planes, which nobody reads any more.
+    for (int t = tid; t < 20 * nlist; t += kBsThreads) {
+      const int pu = t / nlist, li = t - pu * nlist, cell = s.list[li], plane = pu / 5, u = pu - 5 * plane;   // cell-fastest
+      const int r0 = s.oy[cell] - y_lo;
+      double re[8], im[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { re[k] = s.u2.b.sre[pu][r0 + k]; im[k] = s.u2.b.sim[pu][r0 + k]; }
+      cfft8(re, im);
+      double* dst = &s.u1.pw[cell][kBsPow * plane + 8 * u];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) dst[v ^ u] = (re[v] * re[v] + im[v] * im[v]) * 0.000064;
+    }
+    __syncthreads();
+    // (5) per-frequency terms i = 4..36 of every needed cell (over the row spectra)
+    for (int t = tid; t < 33 * nlist; t += kBsThreads) {
+      const int li = t / 33, k = t - 33 * li, i = 4 + k, cell = s.list[li];
+      const double d = s.csf[i];
+      const int pi = i ^ (i >> 3);
+      const double* pw = s.u1.pw[cell];
+      const double tx = d * 64.8 * pw[kBsPow + pi];
+      const double tz = d * 2.4 * pw[3 * kBsPow + pi];
+      const double ya = sqrt(pw[pi]), yh = sqrt(pw[2 * kBsPow + pi]);
+      const double y0 = remove_range_around_zero(ya - yh, 0.04);
+      const double y1 = remove_range_around_zero(ya + yh, 0.04);
+      double ty = 0.0;
+      if (y0 != y1) {
+        const double v0 = interp_signed21(g_tab.lut21[1], y0 * 1.51983458269);
+        const double v1 = interp_signed21(g_tab.lut21[1], y1 * 1.51983458269);
+        const double vy = 1.753123908348329 * (v0 - v1);
+        ty = d * vy * vy;
+      }
+      s.u2.term[cell][0][k] = tx;
+      s.u2.term[cell][1][k] = ty;
+      s.u2.term[cell][2][k] = tz;
+    }
+    __syncthreads();
+    // the ordered sums: one lane per (cell, channel)
+    if (tid < 3 * nlist) {
+      const int li = tid / 3, c = tid - 3 * li, cell = s.list[li];
+      const double* t = s.u2.term[cell][c];
+      double sum = 0.0;
+#pragma unroll
+      for (int i = 0; i < 33; ++i) sum += t[i];
+      ac_out[3 * (static_cast<size_t>(ry0 + cell) * rxs + rx) + c] = static_cast<float>(sum);
+    }
+  }
+}
+
 // K6b: the DC term of BlockDiffMap (butteraugli.cc:602-617, 1098-1106), one res cell per thread: the
 // mean of the 64 per-pixel half-differences in the reference's order, then the low-frequency
 // colour metric. (The warp-per-cell kernel would spend 64 dependent additions on three lanes.)
