@@ -1939,22 +1939,23 @@ int gzb_be_store_order(gzb_ctx* c, uint64_t first, const gzb_order_entry* in, si
 }
 
 namespace {
+// an "up" step never reads the requantised values: its records are only the head of a BeBlockState
+size_t be_state_stride(int direction) { return direction < 0 ? sizeof(BeBlockState) : offsetof(BeBlockState, requant); }
 void be_launch_gather(gzb_ctx* c, const int* blocks, int nreq, int direction) {
   gzb_ctx::Backend& B = c->be;
+  const size_t stride = be_state_stride(direction);
   CK(cudaMemcpyAsync(B.req_blocks, blocks, static_cast<size_t>(nreq) * 4, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += static_cast<size_t>(nreq) * 4;
   KLAUNCH(c, KC_MISC, k_be_gather<<<(nreq * 32 + 255) / 256, 256, 0, c->stream>>>(B.geom, B.req_blocks, nreq, c->d_coef, c->d_orig, c->d_q, B.last_index,
-                                                                                B.pcount, B.comp_mask, direction < 0 ? 1 : 0, B.req_out));
-  // an "up" step never reads the requantised values: the tail of every record stays on the device
-  const size_t width = direction < 0 ? sizeof(BeBlockState) : offsetof(BeBlockState, requant);
-  CK(cudaMemcpy2DAsync(be_pinned(c) + kBePinGather, sizeof(BeBlockState), B.req_out, sizeof(BeBlockState), width, static_cast<size_t>(nreq),
-                       cudaMemcpyDeviceToHost, c->stream));
-  c->d2h_bytes += width * static_cast<size_t>(nreq);
+                                                                                B.pcount, B.comp_mask, direction < 0 ? 1 : 0,
+                                                                                reinterpret_cast<char*>(B.req_out), stride));
+  CK(cudaMemcpyAsync(be_pinned(c) + kBePinGather, B.req_out, stride * static_cast<size_t>(nreq), cudaMemcpyDeviceToHost, c->stream));
+  c->d2h_bytes += stride * static_cast<size_t>(nreq);
 }
 void be_copy_states(gzb_ctx* c, gzb_be_block_state* out, int nreq, int direction) {
   const char* src = be_pinned(c) + kBePinGather;
   if (direction < 0) { memcpy(out, src, sizeof(BeBlockState) * static_cast<size_t>(nreq)); return; }
-  const size_t width = offsetof(BeBlockState, requant);
-  for (int i = 0; i < nreq; ++i) memcpy(reinterpret_cast<char*>(out + i), src + sizeof(BeBlockState) * static_cast<size_t>(i), width);
+  const size_t stride = be_state_stride(direction);
+  for (int i = 0; i < nreq; ++i) memcpy(reinterpret_cast<char*>(out + i), src + stride * static_cast<size_t>(i), stride);
 }
 }  // namespace
 

@@ -776,12 +776,14 @@ __constant__ uint8_t c_be_zigzag[64] = {   // natural index -> zig-zag position
     10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
 __global__ void k_be_gather(BeGeom g, const int* __restrict__ blocks, int nreq, const int16_t* __restrict__ coef,
                             const int16_t* __restrict__ orig, const int* __restrict__ q192, const int* __restrict__ last_index,
-                            const unsigned* __restrict__ pcount, int comp_mask, int want_requant, BeBlockState* __restrict__ out) {
+                            const unsigned* __restrict__ pcount, int comp_mask, int want_requant, char* __restrict__ out, size_t out_stride) {
+  // (records out_stride bytes apart: without the requantised values only the head of each record exists, so that
+  // what goes to the host is one contiguous copy)
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= nreq) return;
   const int b = blocks[r];
   const size_t cb = be_cblock(g, b);
-  BeBlockState* o = out + r;
+  BeBlockState* o = reinterpret_cast<BeBlockState*>(out + static_cast<size_t>(r) * out_stride);
   if (lane == 0) { o->last_index = last_index[b]; o->prefix_count = pcount[b]; }
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
