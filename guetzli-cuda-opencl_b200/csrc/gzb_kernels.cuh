@@ -693,6 +693,50 @@ constexpr int kSbT = 32, kSbR = 3;
 // or y >= H - 12) are computed: 4/9 of the V pass and 2/3 of the H pass. The needed columns / rows of the tile are
 // listed once per CTA and the work items are spread over the 256 threads in compact form.
 __device__ __forceinline__ bool sb_needed(int g, int size) { return g % 3 != 2 || g >= size - 12; }
+// (the two passes with the tap count known at compile time: the loops unroll)
+template <int R>
+__device__ __forceinline__ void sb_passes(float (*s_in)[kSbT + 2 * kSbR + 1], float (*s_h)[kSbT + 1], const unsigned char* s_cols,
+                                          const unsigned char* s_rows, int nc, int nr, const float* __restrict__ taps,
+                                          const double* __restrict__ scale_x, const double* __restrict__ scale_y, float* __restrict__ out,
+                                          int x0, int y0, int H, int P, int tid) {
+  constexpr int nt = 2 * R + 1, span = kSbT + 2 * R;
+  float tp[nt];
+#pragma unroll
+  for (int k = 0; k < nt; ++k) tp[k] = taps[k];
+  const int dq = 256 / nc, dr = 256 - dq * nc;
+  // H pass: every tile row (the V pass needs R rows above and below each needed row), needed columns only
+  {
+    int ly = tid / nc, ci = tid - ly * nc;
+    for (; ly < span; ly += dq, ci += dr) {
+      if (ci >= nc) { ci -= nc; ++ly; if (ly >= span) break; }
+      const int lx = s_cols[ci];
+      const int gx = x0 + lx, gy = y0 + ly - R;
+      float v = 0.0f;
+      if (gy >= 0 && gy < H) {
+        const float* p = &s_in[ly][lx];
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < nt; ++k) acc += static_cast<double>(p[k] * tp[k]);
+        v = static_cast<float>(acc * scale_x[gx]);
+      }
+      s_h[ly][lx] = v;
+    }
+  }
+  __syncthreads();
+  // V pass: needed rows x needed columns
+  {
+    int ri = tid / nc, ci = tid - ri * nc;
+    for (; ri < nr; ri += dq, ci += dr) {
+      if (ci >= nc) { ci -= nc; ++ri; if (ri >= nr) break; }
+      const int ly = s_rows[ri], lx = s_cols[ci];
+      const int gx = x0 + lx, gy = y0 + ly;
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < nt; ++k) acc += static_cast<double>(s_h[ly + k][lx] * tp[k]);
+      out[static_cast<size_t>(gy) * P + gx] = static_cast<float>(acc * scale_y[gy]);
+    }
+  }
+}
 __global__ void __launch_bounds__(256)
 k_blur_small_hv(const float* __restrict__ in, float* __restrict__ out, size_t plane_stride, int W, int H, int P,
                 SmallBlur3 sb, DirtyMask dm) {
@@ -736,39 +780,11 @@ k_blur_small_hv(const float* __restrict__ in, float* __restrict__ out, size_t pl
     }
   }
   __syncthreads();
-  const int nt = 2 * r + 1, nc = s_nc, nr = s_nr;
+  const int nc = s_nc, nr = s_nr;
   if (nc == 0) return;
-  const int dq = 256 / nc, dr = 256 - dq * nc;
-  // H pass: every tile row (the V pass needs r rows above and below each needed row), needed columns only
-  {
-    int ly = tid / nc, ci = tid - ly * nc;
-    for (; ly < span; ly += dq, ci += dr) {
-      if (ci >= nc) { ci -= nc; ++ly; if (ly >= span) break; }
-      const int lx = s_cols[ci];
-      const int gx = x0 + lx, gy = y0 + ly - r;
-      float v = 0.0f;
-      if (gy >= 0 && gy < H) {
-        const float* p = &s_in[ly][lx];
-        double acc = 0.0;
-        for (int k = 0; k < nt; ++k) acc += static_cast<double>(p[k] * taps[k]);
-        v = static_cast<float>(acc * scale_x[gx]);
-      }
-      s_h[ly][lx] = v;
-    }
-  }
-  __syncthreads();
-  // V pass: needed rows x needed columns
-  {
-    int ri = tid / nc, ci = tid - ri * nc;
-    for (; ri < nr; ri += dq, ci += dr) {
-      if (ci >= nc) { ci -= nc; ++ri; if (ri >= nr) break; }
-      const int ly = s_rows[ri], lx = s_cols[ci];
-      const int gx = x0 + lx, gy = y0 + ly;
-      double acc = 0.0;
-      for (int k = 0; k < nt; ++k) acc += static_cast<double>(s_h[ly + k][lx] * taps[k]);
-      out[static_cast<size_t>(gy) * P + gx] = static_cast<float>(acc * scale_y[gy]);
-    }
-  }
+  if (r == 3) sb_passes<3>(s_in, s_h, s_cols, s_rows, nc, nr, taps, scale_x, scale_y, out, x0, y0, H, P, tid);
+  else if (r == 2) sb_passes<2>(s_in, s_h, s_cols, s_rows, nc, nr, taps, scale_x, scale_y, out, x0, y0, H, P, tid);
+  else sb_passes<1>(s_in, s_h, s_cols, s_rows, nc, nr, taps, scale_x, scale_y, out, x0, y0, H, P, tid);
 }
 
 // ---------------------------------------------------------------------------------------------
