@@ -612,8 +612,6 @@ void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
     const int strips = ncx * ((ncy + kBsCells - 1) / kBsCells);
     // (128 threads, 7 CTAs per SM: the best of 128x7/8, 160x5/6, 192x5, 256x4 on a B200 -- profiles/r2_bdm_strip.md)
     const int sctas = std::min(strips, c->sm_count * kBsMinCtas * 4);
-    CK(cudaFuncSetAttribute(k_block_diff_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BsSmem))));
-    CK(cudaFuncSetAttribute(k_block_diff_strip, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_diff_strip<<<sctas, kBsThreads, sizeof(BsSmem), sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_ac, dmask(c, DS_BDM), bc));
   } else {
     KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac, dmask(c, DS_BDM), bc));
@@ -751,6 +749,9 @@ gzb_ctx* alloc_ctx(int device, int W, int H, float target) {
     for (BlurPlan* pl : plans) { need(c, &pl->d_sx, pl->hx.size()); need(c, &pl->d_sy, pl->hy.size()); }
     commit_slab(c);
     CK(cudaMemsetAsync(c->d_scalars, 0, 8 * sizeof(unsigned int), c->stream));   // (the block-change record starts invalid)
+    // (function attributes are per device; the calls are cheap)
+    CK(cudaFuncSetAttribute(k_block_diff_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BsSmem))));
+    CK(cudaFuncSetAttribute(k_block_diff_strip, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     for (BlurPlan* pl : plans) pl->upload(c->stream);
     // TMA descriptors for the H passes whose input planes are fixed: the sigma-14 blur of the six
     // MaskHighIntensityChange planes and the three mask blurs (+ the block-comparison lattice)
@@ -1687,9 +1688,11 @@ int gzb_compute_block_error_adjustment_weights(gzb_ctx* c, int direction, int ma
 // ---- SelectFrequencyBackEnd on the device (gzb_backend.cuh) --------------------------------------
 namespace {
 const size_t kBePinState = 0;                      // BeState + small entries
-const size_t kBePinHist = 64 << 10;                // 816 counters + scalars
-const size_t kBePinGather = 72 << 10;              // gathered block states
+const size_t kBePinHist = 96 << 10;                // 816 counters + scalars
+const size_t kBePinGather = 104 << 10;             // gathered block states
 const size_t kBePinBytes = kBePinGather + sizeof(BeBlockState) * kBeSmallMax;
+static_assert(sizeof(BeState) + sizeof(BeEntry) * kBeSmallMax <= kBePinHist, "pinned layout");
+static_assert(kBeSmallMax == GZB_BE_MAX_ENTRIES && kBeMaxRet == GZB_BE_MAX_RANGES, "include/gzb200.h");
 
 // (Re)allocates the back-end arrays for num_blocks units and `total` candidates / order entries.
 void be_reserve(gzb_ctx* c, int num_blocks, size_t total) {
@@ -1914,7 +1917,7 @@ int gzb_be_select(gzb_ctx* c, uint64_t p_set, int small_max, int* status, uint64
   if (!c) return GZB_ERR_BAD_ARG;
   if (!first || !last || !depth) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_select: bad argument");
   int nranges = 0;
-  gzb_be_range r[8];
+  gzb_be_range r[GZB_BE_MAX_RANGES];
   const int rc = gzb_be_select_ranges(c, p_set, small_max, 0, status, &nranges, r, entries_out);
   if (rc != GZB_OK) return rc;
   if (nranges > 0) { *first = r[0].first; *last = r[0].last; *depth = r[0].depth; }

@@ -52,9 +52,9 @@ struct BeRange { unsigned first, last; int depth, pad; };
 constexpr int kBeStack = 128;      // >= 2 * log2(n) + 2 pending ranges
 constexpr int kBeTile = 2048;      // entries per partition tile (256 threads x 8)
 constexpr int kBeThreads = 256;
-constexpr int kBeSmallMax = 4096;  // longest range handed to the host (capacity of BeState::small)
+constexpr int kBeSmallMax = 8192;  // entries one select can hand to the host (capacity of BeState::small), blocks one gather returns
 constexpr unsigned kBeLocalMax = 16384;   // ranges up to this length are partitioned by one CTA (no grid barriers)
-constexpr int kBeMaxRet = 8;       // short ranges one gzb_be_select_ranges can hand over
+constexpr int kBeMaxRet = 16;      // short ranges one gzb_be_select_ranges can hand over
 
 enum { BE_RUNNING = 0, BE_SMALL = 1, BE_HEAP = 2, BE_EMPTY = 3 };
 

@@ -769,14 +769,14 @@ int gzb_test_device_sort_depth(gzb_ctx* ctx, gzb_order_entry* entries, size_t n,
   if (!ctx || !entries || n == 0 || prefix > n) return GZB_ERR_BAD_ARG;
   int rc = gzb_be_test_load_order_depth(ctx, entries, n, depth);
   if (rc != GZB_OK) return rc;
-  std::vector<OrderEntry> buf(4096), big;
+  std::vector<OrderEntry> buf(GZB_BE_MAX_ENTRIES), big;
   size_t have_end = prefix;
   // small_max < 0: several ranges per round trip (gzb_be_select_ranges), as many as fit
-  const size_t want = small_max < 0 ? 4096 : 0;
+  const size_t want = small_max < 0 ? GZB_BE_MAX_ENTRIES : 0;
   if (small_max < 0) small_max = -small_max;
   for (;;) {
     int status = 0, nranges = 0;
-    gzb_be_range rr[8];
+    gzb_be_range rr[GZB_BE_MAX_RANGES];
     rc = gzb_be_select_ranges(ctx, have_end, small_max, have_end + want, &status, &nranges, rr, reinterpret_cast<gzb_order_entry*>(buf.data()));
     if (rc != GZB_OK) return rc;
     if (status == 3) break;
@@ -1168,13 +1168,33 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         uint64_t zmask[3];
       };
       std::vector<WalkBlock> wblocks;
-      std::vector<gzb_be_block_state> wstates;   // wstates[slot]: the block's coefficients as the device reported them, edited by the walk
-      wstates.reserve(8192);
+      // wstates[slot]: the block's coefficients as the device reported them, edited by the walk. A plain buffer:
+      // the records are filled by gzb_be_gather, and value-initialising 800 bytes per block first costs as much
+      // as copying them.
+      struct StateBuf {
+        gzb_be_block_state* p = nullptr;
+        size_t n = 0, cap = 0;
+        ~StateBuf() { free(p); }
+        void clear() { n = 0; }
+        bool resize(size_t want) {
+          if (want > cap) {
+            const size_t nc = std::max(want, std::max<size_t>(8192, cap * 2));
+            void* q = realloc(p, nc * sizeof(gzb_be_block_state));
+            if (!q) return false;
+            p = static_cast<gzb_be_block_state*>(q);
+            cap = nc;
+          }
+          n = want;
+          return true;
+        }
+        gzb_be_block_state* data() { return p; }
+        gzb_be_block_state& operator[](size_t i) { return p[i]; }
+      } wstates;
       std::vector<int> wslot(num_blocks, -1);   // unit -> index into wblocks / wstates, -1: not fetched in this iteration
       std::vector<OrderEntry> went;
       size_t wbase = 0;
       bool order_done = false;         // every entry of the order has been fetched
-      std::vector<OrderEntry> range_buf(4096);
+      std::vector<OrderEntry> range_buf(GZB_BE_MAX_ENTRIES);
       exact_sort::HostLazy lazy;
       std::vector<int> req_blocks;
       // The device partitions down to ranges of at most small_max entries and hands over, in one round trip, as
@@ -1183,6 +1203,10 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       static const int small_max_env = getenv("GZB_BE_SMALL_MAX") ? std::max(16, std::min(4096, atoi(getenv("GZB_BE_SMALL_MAX")))) : 0;
       static const int want_env = getenv("GZB_BE_WANT") ? std::max(0, atoi(getenv("GZB_BE_WANT"))) : -1;
       const int small_max = small_max_env ? small_max_env : 1024;
+      // (one estimate per direction: "up" and "down" walks differ by an order of magnitude on some images; within
+      // an iteration every further round trip asks for twice as much)
+      const size_t want_cap = GZB_BE_MAX_ENTRIES - 1024;
+      size_t want_dir[2] = {1024, 1024};
       size_t want_more = want_env >= 0 ? want_env : 1024;
       // the coefficient flips of the sequential walk
       struct Flips {
@@ -1258,6 +1282,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           went.clear();
           lazy.clear();
           wbase = prefix;
+          if (want_env < 0) want_more = want_dir[direction > 0 ? 1 : 0];
           order_done = false;
           int walk_changed_blocks = 0, prefix_changed_blocks = 0;
           bool prefix_applied = false;
@@ -1269,12 +1294,12 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
             size_t at = 0;
             do {
               req_blocks.clear();
-              while (at < count && req_blocks.size() < 4096) {
+              while (at < count && req_blocks.size() < GZB_BE_MAX_ENTRIES) {
                 const int b = src[at++].first;
                 if (wslot[b] < 0) { wslot[b] = static_cast<int>(wblocks.size() + req_blocks.size()); req_blocks.push_back(b); }
               }
               const size_t slot0 = wblocks.size();
-              wstates.resize(slot0 + req_blocks.size());
+              if (!wstates.resize(slot0 + req_blocks.size())) return false;
               gzb_be_block_state* req_states = wstates.data() + slot0;   // filled in place
               const int nreq = static_cast<int>(req_blocks.size());
               if (!prefix_applied) {
@@ -1330,12 +1355,13 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
               return gather_blocks(went.data(), went.size());
             }
             int status = 0, nranges = 0;
-            gzb_be_range rr[8];
+            gzb_be_range rr[GZB_BE_MAX_RANGES];
             const double tsel = now_ms();
             // (the walk of the previous iteration is the best guess of how far this one will get)
             if (gzb_be_select_ranges(e.ctx, have_end, small_max, have_end + want_more, &status, &nranges, rr,
                                      reinterpret_cast<gzb_order_entry*>(range_buf.data())) != GZB_OK)
               return false;
+            if (want_env < 0) want_more = std::min(want_cap, 2 * want_more);
             e.st.be_select_ms += now_ms() - tsel;
             if (status == 3 || nranges <= 0) { order_done = true; return true; }
             const size_t rf = static_cast<size_t>(rr[0].first), rl = static_cast<size_t>(rr[nranges - 1].last);
@@ -1345,7 +1371,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
               lazy.reset(rl - rf, 0);
             } else {
               lazy.buf.assign(range_buf.begin(), range_buf.begin() + (rl - rf));
-              exact_sort::HostLazy::R lr[8];
+              exact_sort::HostLazy::R lr[GZB_BE_MAX_RANGES];
               for (int i = 0; i < nranges; ++i)
                 lr[i] = {static_cast<size_t>(rr[i].first) - rf, static_cast<size_t>(rr[i].last) - rf, rr[i].depth};
               lazy.reset_ranges(lr, nranges);
@@ -1467,6 +1493,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           // window that stops are undone. Decisions are those of the one-step-at-a-time loop.
           if (windowed && !stopped && i < order_size) {
             const int NB = 2 * e.pool->size();
+            Histogram base_hist[3];
             if (static_cast<int>(windows.size()) < NB) windows.resize(NB);
             while (!stopped && i < order_size) {
               const double tb = now_ms();
@@ -1474,6 +1501,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
               ulog.clear();
               const size_t i0 = i;
               int nw = 0;
+              for (int c = 0; c < 3; ++c) base_hist[c] = ac_hist[c];
               while (nw < NB && i < order_size) {
                 CodeWindow& W = windows[nw++];
                 W.first = i;
@@ -1483,10 +1511,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
                   W.delta_begin[st] = static_cast<uint32_t>(dlog.size());
                   if (!have_entry(i)) return fail(GZB_ERR_CUDA);
                   flip(i, &dlog, &ulog);
-                  if (st == 0) {
-                    for (int c = 0; c < 3; ++c) W.hist[c] = ac_hist[c];
-                    W.changed_first = changed_coeffs;
-                  }
+                  if (st == 0) W.changed_first = changed_coeffs;   // (its histograms: base + the deltas so far, rebuilt by the pool)
                   ++W.nsteps;
                 }
                 W.delta_begin[W.nsteps] = static_cast<uint32_t>(dlog.size());
@@ -1494,6 +1519,9 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
               const double tpool = now_ms();
               e.pool->run(nw, [&](int w) {
                 CodeWindow& W = windows[w];
+                // the histograms after the window's first step: the batch's base plus every delta up to there
+                for (int c = 0; c < 3; ++c) W.hist[c] = base_hist[c];
+                for (uint32_t j = 0; j < W.delta_begin[1]; ++j) W.hist[dlog[j].c].add(dlog[j].sym, dlog[j].w);
                 Histogram clustered[3] = {W.hist[0], W.hist[1], W.hist[2]};
                 size_t num = ncomp;
                 int indexes[4];
@@ -1562,7 +1590,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           }
           if (fetch_failed) return fail(GZB_ERR_CUDA);
           if (changed_coeffs > 0) val_threshold = went[last_step - wbase].second;
-          if (want_env < 0) want_more = std::min<size_t>(3072, std::max<size_t>(256, went.size() + went.size() / 8 + 64));
+          if (want_env < 0) want_dir[direction > 0 ? 1 : 0] = std::min(want_cap, std::max<size_t>(256, went.size() + went.size() / 8 + 64));
           const size_t changed_blocks = static_cast<size_t>(prefix_changed_blocks + walk_changed_blocks);
           { const double t1 = now_ms(); e.st.be_walk_ms += t1 - tt; tt = t1; }
           ++e.st.num_iterations;

@@ -230,14 +230,16 @@ int gzb_be_build_order(gzb_ctx* ctx, int direction, double target_mul, float bel
                        int* blocks_to_change, uint64_t* below, int* rblock);
 /* One step of the lazy std::sort. Pending ranges that end at or before p_set are dropped unsorted (their
  * entries are consumed as a set); the leftmost remaining range is partitioned, the library's way, until
- * it holds at most small_max (<= 4096) entries. status 1: entries_out receives that range
+ * it holds at most small_max (<= GZB_BE_MAX_ENTRIES) entries. status 1: entries_out receives that range
  * [*first, *last) -- still to be sorted by the caller with depth budget *depth (std::__introsort_loop's
  * third argument) -- and the range stays pending; 2: the range [*first, *last) has used up its depth
  * budget (std::sort heap-sorts it: fetch, std::partial_sort, store); 3: nothing is pending. */
 int gzb_be_select(gzb_ctx* ctx, uint64_t p_set, int small_max, int* status, uint64_t* first,
                   uint64_t* last, int* depth, gzb_order_entry* entries_out);
-/* The same for a caller that expects to need the order up to position want_end: up to 8 consecutive short
- * ranges (leftmost first, at most 4096 entries together, entries back to back in entries_out) in one
+#define GZB_BE_MAX_ENTRIES 8192   /* entries one select hands over; blocks one gather returns */
+#define GZB_BE_MAX_RANGES 16
+/* The same for a caller that expects to need the order up to position want_end: up to GZB_BE_MAX_RANGES consecutive
+ * short ranges (leftmost first, at most GZB_BE_MAX_ENTRIES entries together, entries back to back in entries_out) in one
  * round trip -- the device goes on to the next pending range as long as one thread block can partition
  * it. status 1: *nranges ranges; 2: ranges[0] needs the heap sort; 3: nothing is pending. */
 typedef struct { uint64_t first, last; int depth; int reserved; } gzb_be_range;
@@ -252,7 +254,7 @@ int gzb_be_store_order(gzb_ctx* ctx, uint64_t first, const gzb_order_entry* in, 
  * states_out (optional): a gzb_be_gather in the same round trip. */
 int gzb_be_apply_prefix(gzb_ctx* ctx, uint64_t p, int direction, int hist_ncomp, uint32_t* ac_hist768,
                         int* changed_blocks, const int* blocks, int nreq, gzb_be_block_state* states_out);
-/* State of nreq (<= 4096) blocks for the sequential part of the walk. */
+/* State of nreq (<= GZB_BE_MAX_ENTRIES) blocks for the sequential part of the walk. */
 int gzb_be_gather(gzb_ctx* ctx, const int* blocks, int nreq, int direction, gzb_be_block_state* states_out);
 /* End of an iteration: the flips of the sequential walk (unit index, coefficient index 64*c + k, value;
  * each advances last_indexes by direction), max_block_error += block_weight * val_threshold * direction

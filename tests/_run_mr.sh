@@ -1,5 +1,5 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
-timeout 300 python bench.py --mode butteraugli --steps 5 --warmup 3 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print([(x['size'], round(x['compare_device_ms'],3)) for x in d['sweep']])"
+timeout 600 python -m pytest tests/test_gpu_backend.py tests/test_gpu_encode.py tests/test_gpu_420.py -m gpu -x -q 2>&1 | tail -2
+PQ_SEED=1284 timeout 300 python tests/perf_quick.py 4000 3000 95 2 2>&1 | tail -2 | cut -c1-700
+timeout 300 python tests/perf_quick.py 4000 3000 95 3 2>&1 | tail -2 | cut -c1-700
+timeout 300 python tests/perf_quick.py 1024 1024 90 3 2>&1 | tail -2 | cut -c1-300

@@ -8,7 +8,7 @@ import __graft_entry__ as ge
 gz = ge.load_package()
 w, h, q = int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3])
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-img = synth_image(w, h)
+img = synth_image(w, h, int(os.environ.get("PQ_SEED", "1234")))
 t = np.float32(gz.ButteraugliScoreForQuality(q))
 best = None
 for rep in range(reps + 1):
