@@ -694,7 +694,18 @@ long gzb_test_pool_stress(int threads, int jobs) {
     const int n = 1 + (j * 7919) % 67;
     std::atomic<long> sum(0);
     std::vector<int> hits(n, 0);
-    pool.run(n, [&](int i) { sum.fetch_add(i + 1); ++hits[i]; if ((j & 255) == 0 && i == 0) std::this_thread::yield(); });
+    const std::function<void(int)> fn = [&](int i) { sum.fetch_add(i + 1); ++hits[i]; if ((j & 255) == 0 && i == 0) std::this_thread::yield(); };
+    if (j % 3 == 2) {
+      // the two-part form: the caller does something else (here: a nested run(), which must then stay on this
+      // thread) between handing the items out and joining
+      pool.begin(n, fn);
+      std::atomic<int> inner(0);
+      pool.run(3, [&](int) { inner.fetch_add(1); });
+      pool.finish();
+      if (inner.load() != 3) ++bad;
+    } else {
+      pool.run(n, fn);
+    }
     long want = static_cast<long>(n) * (n + 1) / 2;
     bool once = true;
     for (int h : hits) once = once && h == 1;
@@ -1226,9 +1237,17 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
         int est[10];
         gzb::jpeg::HuffCache caches[5];
       };
-      std::vector<CodeWindow> windows;
-      std::vector<SymDelta> dlog;
-      std::vector<UndoRec> ulog;
+      // A batch of windows: walked by this thread (symbol deltas and undo records logged), then evaluated by the
+      // pool. Two of them: the next batch is walked while the pool evaluates the current one.
+      struct Batch {
+        std::vector<SymDelta> dlog;
+        std::vector<UndoRec> ulog;
+        std::vector<CodeWindow> windows;
+        Histogram base[3];   // the AC histograms before the batch's first step
+        size_t i0 = 0;
+        int nw = 0;
+      };
+      Batch batches[2];
       bool first_up_iter = true;
       const int directions[2] = {1, -1};
       const int n_ccoef = static_cast<int>(cand_coeffs.size());
@@ -1493,100 +1512,122 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           // window that stops are undone. Decisions are those of the one-step-at-a-time loop.
           if (windowed && !stopped && i < order_size) {
             const int NB = 2 * e.pool->size();
-            Histogram base_hist[3];
-            if (static_cast<int>(windows.size()) < NB) windows.resize(NB);
-            while (!stopped && i < order_size) {
-              const double tb = now_ms();
-              dlog.clear();
-              ulog.clear();
-              const size_t i0 = i;
-              int nw = 0;
-              for (int c = 0; c < 3; ++c) base_hist[c] = ac_hist[c];
-              while (nw < NB && i < order_size) {
-                CodeWindow& W = windows[nw++];
+            // walks up to NB windows from step i on; false: the order could not be fetched
+            auto walk_batch = [&](Batch& B) -> bool {
+              B.dlog.clear();
+              B.ulog.clear();
+              B.i0 = i;
+              B.nw = 0;
+              for (int c = 0; c < 3; ++c) B.base[c] = ac_hist[c];
+              if (static_cast<int>(B.windows.size()) < NB) B.windows.resize(NB);
+              while (B.nw < NB && i < order_size) {
+                CodeWindow& W = B.windows[B.nw++];
                 W.first = i;
                 W.nsteps = 0;
                 W.break_step = -1;
                 for (int st = 0; st < 10 && i < order_size; ++st, ++i) {
-                  W.delta_begin[st] = static_cast<uint32_t>(dlog.size());
-                  if (!have_entry(i)) return fail(GZB_ERR_CUDA);
-                  flip(i, &dlog, &ulog);
+                  W.delta_begin[st] = static_cast<uint32_t>(B.dlog.size());
+                  if (!have_entry(i)) return false;
+                  flip(i, &B.dlog, &B.ulog);
                   if (st == 0) W.changed_first = changed_coeffs;   // (its histograms: base + the deltas so far, rebuilt by the pool)
                   ++W.nsteps;
                 }
-                W.delta_begin[W.nsteps] = static_cast<uint32_t>(dlog.size());
+                W.delta_begin[W.nsteps] = static_cast<uint32_t>(B.dlog.size());
               }
-              const double tpool = now_ms();
-              e.pool->run(nw, [&](int w) {
-                CodeWindow& W = windows[w];
-                // the histograms after the window's first step: the batch's base plus every delta up to there
-                for (int c = 0; c < 3; ++c) W.hist[c] = base_hist[c];
-                for (uint32_t j = 0; j < W.delta_begin[1]; ++j) W.hist[dlog[j].c].add(dlog[j].sym, dlog[j].w);
-                Histogram clustered[3] = {W.hist[0], W.hist[1], W.hist[2]};
-                size_t num = ncomp;
-                int indexes[4];
-                uint8_t cd[3 * Histogram::kSize];
-                gzb::jpeg::cluster_histograms(clustered, &num, indexes, cd, W.caches);
-                for (int c = 0; c < ncomp; ++c)
-                  memcpy(&W.depths[c * Histogram::kSize], &cd[indexes[c] * Histogram::kSize], Histogram::kSize);
-                size_t hs = 0;
-                for (size_t k = 0; k < num; ++k) hs += gzb::jpeg::header_cost_bits(clustered[k]) / 8;
-                W.ac_histogram_size = static_cast<int>(hs);
-                uint64_t raw[3] = {0, 0, 0};
-                for (int c = 0; c < ncomp; ++c) {
-                  const uint8_t* d = &W.depths[c * Histogram::kSize];
-                  uint64_t bits = 0;
-                  for (int k = 0; k + 1 < Histogram::kSize; ++k) bits += static_cast<uint64_t>(W.hist[c].counts[k] / 2) * (d[k] + (k & 0xf));
-                  raw[c] = bits;
-                }
-                for (int st = 0; st < W.nsteps; ++st) {
-                  if (st > 0)
-                    for (uint32_t j = W.delta_begin[st]; j < W.delta_begin[st + 1]; ++j) {
-                      const SymDelta& dl = dlog[j];
-                      raw[dl.c] += static_cast<int64_t>(dl.w) * (W.depths[dl.c * Histogram::kSize + dl.sym] + (dl.sym & 0xf));
-                    }
-                  for (int c = 0; c < 3; ++c) W.raw[st][c] = raw[c];
-                  const int changed = W.changed_first + st;
-                  W.est[st] = -1;
-                  if (changed > min_coeffs_to_change || W.first + st + 1 == order_size) {
-                    size_t numbits = 0;
-                    for (int c = 0; c < ncomp; ++c) numbits += raw[c] + ((raw[c] * 3 + 512) >> 10);
-                    const int est = header_size + dc_size + W.ac_histogram_size + static_cast<int>((numbits + 7) / 8);
-                    W.est[st] = est;
-                    if (changed > min_coeffs_to_change && std::abs(est - prev_size) > min_size_delta) { W.break_step = st; break; }
+              return true;
+            };
+            // one window on a pool thread: its entropy codes, then the size estimate step by step
+            auto eval_window = [&](Batch& B, int w) {
+              CodeWindow& W = B.windows[w];
+              const std::vector<SymDelta>& dlog = B.dlog;
+              // the histograms after the window's first step: the batch's base plus every delta up to there
+              for (int c = 0; c < 3; ++c) W.hist[c] = B.base[c];
+              for (uint32_t j = 0; j < W.delta_begin[1]; ++j) W.hist[dlog[j].c].add(dlog[j].sym, dlog[j].w);
+              Histogram clustered[3] = {W.hist[0], W.hist[1], W.hist[2]};
+              size_t num = ncomp;
+              int indexes[4];
+              uint8_t cd[3 * Histogram::kSize];
+              gzb::jpeg::cluster_histograms(clustered, &num, indexes, cd, W.caches);
+              for (int c = 0; c < ncomp; ++c)
+                memcpy(&W.depths[c * Histogram::kSize], &cd[indexes[c] * Histogram::kSize], Histogram::kSize);
+              size_t hs = 0;
+              for (size_t k = 0; k < num; ++k) hs += gzb::jpeg::header_cost_bits(clustered[k]) / 8;
+              W.ac_histogram_size = static_cast<int>(hs);
+              uint64_t raw[3] = {0, 0, 0};
+              for (int c = 0; c < ncomp; ++c) {
+                const uint8_t* d = &W.depths[c * Histogram::kSize];
+                uint64_t bits = 0;
+                for (int k = 0; k + 1 < Histogram::kSize; ++k) bits += static_cast<uint64_t>(W.hist[c].counts[k] / 2) * (d[k] + (k & 0xf));
+                raw[c] = bits;
+              }
+              for (int st = 0; st < W.nsteps; ++st) {
+                if (st > 0)
+                  for (uint32_t j = W.delta_begin[st]; j < W.delta_begin[st + 1]; ++j) {
+                    const SymDelta& dl = dlog[j];
+                    raw[dl.c] += static_cast<int64_t>(dl.w) * (W.depths[dl.c * Histogram::kSize + dl.sym] + (dl.sym & 0xf));
                   }
+                for (int c = 0; c < 3; ++c) W.raw[st][c] = raw[c];
+                const int changed = W.changed_first + st;
+                W.est[st] = -1;
+                if (changed > min_coeffs_to_change || W.first + st + 1 == order_size) {
+                  size_t numbits = 0;
+                  for (int c = 0; c < ncomp; ++c) numbits += raw[c] + ((raw[c] * 3 + 512) >> 10);
+                  const int est = header_size + dc_size + W.ac_histogram_size + static_cast<int>((numbits + 7) / 8);
+                  W.est[st] = est;
+                  if (changed > min_coeffs_to_change && std::abs(est - prev_size) > min_size_delta) { W.break_step = st; break; }
                 }
-              });
+              }
+            };
+            // takes back the steps of a batch from its keep-th on (the latest batch first)
+            auto undo_from = [&](Batch& B, size_t keep) {
+              if (keep >= B.ulog.size()) return;
+              for (size_t j = B.dlog.size(); j-- > B.ulog[keep].delta_begin;) ac_hist[B.dlog[j].c].add(B.dlog[j].sym, -B.dlog[j].w);
+              for (size_t j = B.ulog.size(); j-- > keep;) {
+                const UndoRec& u = B.ulog[j];
+                WalkBlock& wb = wblocks[u.slot];
+                wstates[u.slot].idx[u.c][u.k] = u.old_idx;
+                wb.zmask[u.c] = u.old_mask;
+                wb.last_index -= direction;
+                if (u.newly_touched) { wb.touched = false; if (!wb.in_prefix) --walk_changed_blocks; }
+                job->block.pop_back(); job->cidx.pop_back(); job->val.pop_back();
+                --changed_coeffs;
+                --e.st.be_steps;
+              }
+            };
+            const std::function<void(int)> evals[2] = {[&](int w) { eval_window(batches[0], w); }, [&](int w) { eval_window(batches[1], w); }};
+            const double tb = now_ms();
+            int cur = 0;
+            if (!walk_batch(batches[0])) return fail(GZB_ERR_CUDA);
+            for (;;) {
+              Batch& B = batches[cur];
+              Batch& N = batches[1 - cur];
+              // The pool evaluates this batch while this thread walks the next one ahead of the decision: if the
+              // loop stops inside this batch, the next one is taken back whole.
+              e.pool->begin(B.nw, evals[cur]);
+              bool have_next = false, ok = true;
+              if (i < order_size) { ok = walk_batch(N); have_next = ok; }
+              const double tpool = now_ms();
+              e.pool->finish();
               e.st.be_pool_ms += now_ms() - tpool;
-              int final_w = nw - 1, final_st = windows[nw - 1].nsteps - 1;
-              for (int w = 0; w < nw; ++w)
-                if (windows[w].break_step >= 0) { final_w = w; final_st = windows[w].break_step; stopped = true; break; }
-              const CodeWindow& F = windows[final_w];
+              if (!ok) return fail(GZB_ERR_CUDA);
+              int final_w = B.nw - 1, final_st = B.windows[B.nw - 1].nsteps - 1;
+              for (int w = 0; w < B.nw; ++w)
+                if (B.windows[w].break_step >= 0) { final_w = w; final_st = B.windows[w].break_step; stopped = true; break; }
+              const CodeWindow& F = B.windows[final_w];
               e.st.num_entropy_code_builds += final_w + 1;
               last_step = F.first + final_st;
               if (stopped) {  // undo the steps walked past the stop
-                const size_t keep = last_step + 1 - i0;
-                if (keep < ulog.size()) {
-                  for (size_t j = dlog.size(); j-- > ulog[keep].delta_begin;) ac_hist[dlog[j].c].add(dlog[j].sym, -dlog[j].w);
-                  for (size_t j = ulog.size(); j-- > keep;) {
-                    const UndoRec& u = ulog[j];
-                    WalkBlock& wb = wblocks[u.slot];
-                    wstates[u.slot].idx[u.c][u.k] = u.old_idx;
-                    wb.zmask[u.c] = u.old_mask;
-                    wb.last_index -= direction;
-                    if (u.newly_touched) { wb.touched = false; if (!wb.in_prefix) --walk_changed_blocks; }
-                    job->block.pop_back(); job->cidx.pop_back(); job->val.pop_back();
-                    --changed_coeffs;
-                    --e.st.be_steps;
-                  }
-                }
+                if (have_next) undo_from(N, 0);
+                undo_from(B, last_step + 1 - B.i0);
               }
               memcpy(ac_depths.data(), F.depths, 3 * Histogram::kSize);
               ac_histogram_size = F.ac_histogram_size;
               for (int c = 0; c < 3; ++c) raw_bits[c] = F.raw[final_st][c];
               if (F.est[final_st] >= 0) est_jpg_size = F.est[final_st];
-              e.st.be_codes_ms += now_ms() - tb;
+              if (stopped || !have_next) break;
+              cur = 1 - cur;
             }
+            e.st.be_codes_ms += now_ms() - tb;
           }
           if (fetch_failed) return fail(GZB_ERR_CUDA);
           if (changed_coeffs > 0) val_threshold = went[last_step - wbase].second;

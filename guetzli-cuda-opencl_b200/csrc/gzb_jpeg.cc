@@ -678,27 +678,41 @@ void WorkerPool::worker() {
 
 void WorkerPool::run(int n, const std::function<void(int)>& fn) {
   if (n <= 0) return;
-  if (nthreads_ == 1 || n == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
-  Job job;
+  if (nthreads_ == 1 || n == 1 || async_open_) { for (int i = 0; i < n; ++i) fn(i); return; }
+  begin(n, fn);
+  finish();
+}
+
+void WorkerPool::begin(int n, const std::function<void(int)>& fn) {
+  Job& job = async_job_;
   job.fn = &fn;
-  job.n = n;
-  job.pending.store(n);
+  job.n = std::max(0, n);
+  job.next.store(0);
+  job.pending.store(job.n);
+  async_open_ = true;
+  if (job.n == 0 || nthreads_ == 1) return;   // (finish() does the items)
   job_.store(&job);
   epoch_.fetch_add(1, std::memory_order_release);
   if (sleepers_.load() > 0) {
     std::lock_guard<std::mutex> l(mu_);   // a sleeper checks the epoch under this mutex
     cv_start_.notify_all();
   }
+}
+
+void WorkerPool::finish() {
+  if (!async_open_) return;
+  Job& job = async_job_;
   for (;;) {  // the caller works too
     const int i = job.next.fetch_add(1);
-    if (i >= n) break;
-    fn(i);
+    if (i >= job.n) break;
+    (*job.fn)(i);
     job.pending.fetch_sub(1);
   }
   int spins = 0;
   while (job.pending.load(std::memory_order_acquire) != 0) { if (++spins < 64) cpu_relax(); else std::this_thread::yield(); }
   job_.store(nullptr);
   while (active_.load() != 0) cpu_relax();
+  async_open_ = false;
 }
 
 }  // namespace gzb

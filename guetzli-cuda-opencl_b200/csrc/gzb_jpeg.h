@@ -31,6 +31,11 @@ class WorkerPool {
   ~WorkerPool();
   int size() const { return nthreads_; }
   void run(int n, const std::function<void(int)>& fn);
+  // The same in two halves: begin() hands the items to the workers and returns; finish() makes the caller work
+  // on what is left and returns when all items are done. fn must stay alive in between, and run() must not be
+  // called in between (it would then do its items on the calling thread).
+  void begin(int n, const std::function<void(int)>& fn);
+  void finish();
 
  private:
   struct Job {
@@ -47,6 +52,8 @@ class WorkerPool {
   std::atomic<unsigned long long> epoch_{0};
   std::atomic<int> active_{0}, sleepers_{0};
   std::atomic<bool> stop_{false};
+  Job async_job_;
+  bool async_open_ = false;
 };
 
 namespace jpeg {
