@@ -469,7 +469,9 @@ def run_ours(a, rank, world, local):
         group = {"workload": "BASELINE configs[2]: the %dx%d q%g image encoded ONCE by %d GPUs (SelectQuantMatrix candidates and "
                              "zeroing blocks sharded, NCCL all-gather per round; back end on rank 0)" % (w, h, a.quality, world),
                  "value": mpix / (sum(gtimes) / len(gtimes)), "unit": "MPix/s", "seconds": sum(gtimes) / len(gtimes), "scaling": "strong",
-                 "bytes_equal_single_gpu": (gj == jpg) if rank == 0 else None}
+                 "bytes_equal_single_gpu": (gj == jpg) if rank == 0 else None,
+                 "rank0_phases_ms": {k: round(float(gst[k]), 2) for k in ("search_wall_ms", "zeroing_wall_ms", "device_zeroing_ms", "backend_wall_ms",
+                                                                         "compare_wall_ms", "be_walk_ms", "be_order_ms", "create_ms", "prepare_ms", "run_ms", "total_wall_ms") if k in gst}}
 
     if rank != 0:
         if dist is not None:

@@ -550,16 +550,32 @@ class Encoder:
             L.gzb_free(tr)
         return data, st.as_dict(), trace
 
-    def set_group(self, rank, world, allgather):
+    def set_group(self, rank, world, allgather, allgather_device=None):
         """gzb_encoder_set_group: this encoder becomes rank `rank` of `world` encoders of the SAME
         image (one per GPU). `allgather(send: bytes-like) -> bytes` must return the concatenation of
-        every rank's buffer in rank order (see torch_allgather)."""
+        every rank's buffer in rank order (see torch_allgather). `allgather_device(d_send, nbytes, d_recv)`
+        (optional, gzb_encoder_set_group_device) all-gathers DEVICE memory given as integer pointers (see
+        torch_allgather_device): the zeroing candidates then go from GPU to GPU."""
         self._cb = make_allgather_callback(allgather, world)   # keep the thunk alive
         L = lib()
         L.gzb_encoder_set_group.argtypes = [C.c_void_p, C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p]
         rc = L.gzb_encoder_set_group(self._enc, rank, world, self._cb, None)
         if rc != 0:
             raise GzbError("gzb_encoder_set_group failed (%d): %s" % (rc, L.gzb_encode_last_error().decode(errors="replace")))
+        if allgather_device is not None:
+            def thunk(user, d_send, nbytes, d_recv):
+                try:
+                    allgather_device(int(d_send or 0), int(nbytes), int(d_recv or 0))
+                    return 0
+                except Exception:  # never let an exception cross the C boundary
+                    import traceback
+                    traceback.print_exc()
+                    return -2
+            self._cb_dev = ALLGATHER_FN(thunk)
+            L.gzb_encoder_set_group_device.argtypes = [C.c_void_p, ALLGATHER_FN]
+            rc = L.gzb_encoder_set_group_device(self._enc, self._cb_dev)
+            if rc != 0:
+                raise GzbError("gzb_encoder_set_group_device failed (%d): %s" % (rc, L.gzb_encode_last_error().decode(errors="replace")))
 
     def kernel_times(self):
         return profile_get(self._ctx)
@@ -583,6 +599,12 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void
 def make_allgather_callback(allgather, world):
     def thunk(user, send, nbytes, recv):
         try:
+            into = getattr(allgather, "into", None)
+            if into is not None:   # no intermediate copies: numpy views of the two C buffers
+                s = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), shape=(nbytes,))
+                r = np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_uint8)), shape=(world * nbytes,))
+                into(s, r)
+                return 0
             out = allgather(C.string_at(send, nbytes))
             if len(out) != world * nbytes:
                 return -1
@@ -597,7 +619,8 @@ def make_allgather_callback(allgather, world):
 
 def torch_allgather(dist, device):
     """An allgather(bytes)->bytes over torch.distributed: NCCL over NVLink/NVSwitch when `device` is
-    a CUDA device (the exchange buffers are staged through HBM), gloo for the CPU tests."""
+    a CUDA device (the exchange buffers are staged through HBM), gloo for the CPU tests. Its `into(send, recv)`
+    form works on numpy views of the caller's buffers (one copy in, one copy out)."""
     import torch
     world = dist.get_world_size()
 
@@ -606,7 +629,34 @@ def torch_allgather(dist, device):
         outs = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(outs, t)
         return b"".join(o.cpu().numpy().tobytes() for o in outs)
+
+    def into(send, recv):
+        t = torch.from_numpy(send).to(device)
+        out = torch.empty((world, t.numel()), dtype=torch.uint8, device=device)
+        dist.all_gather(list(out.unbind(0)), t)
+        torch.from_numpy(recv).copy_(out.view(-1))
+    allgather.into = into
     return allgather
+
+
+def torch_allgather_device(dist, device):
+    """gzb_allgather_device_fn over torch.distributed (NCCL): the two device pointers are wrapped as uint8
+    tensors without a copy and all-gathered over NVLink / NVSwitch."""
+    import torch
+    world = dist.get_world_size()
+    dev = torch.device("cuda", device) if isinstance(device, int) else device
+
+    class _Ptr(object):   # a raw device pointer as a 1-D uint8 CUDA array
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    def fn(d_send, nbytes, d_recv):
+        with torch.cuda.device(dev):
+            s = torch.as_tensor(_Ptr(d_send, nbytes), device=dev)
+            r = torch.as_tensor(_Ptr(d_recv, nbytes * world), device=dev)
+            dist.all_gather_into_tensor(r, s)
+            torch.cuda.current_stream(dev).synchronize()
+    return fn
 
 
 def ProcessGroup(rgb, butteraugli_target, dist, device=0, host_threads=0, want_trace=False):
@@ -617,7 +667,8 @@ def ProcessGroup(rgb, butteraugli_target, dist, device=0, host_threads=0, want_t
     dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
     enc = Encoder(rgb, butteraugli_target, device=device, host_threads=host_threads)
     try:
-        enc.set_group(dist.get_rank(), dist.get_world_size(), torch_allgather(dist, dev))
+        enc.set_group(dist.get_rank(), dist.get_world_size(), torch_allgather(dist, dev),
+                      torch_allgather_device(dist, dev) if dev.type == "cuda" else None)
         return enc.run(want_trace)
     finally:
         enc.close()

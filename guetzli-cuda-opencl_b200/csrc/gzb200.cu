@@ -1756,17 +1756,10 @@ char* be_pinned(gzb_ctx* c) { return static_cast<char*>(c->slab.be_pinned); }
 BeCands be_cands(const gzb_ctx* c) { return BeCands{c->be.cand_off, c->be.cand_idx, c->be.cand_err, c->be.total}; }
 }  // namespace
 
-int gzb_be_begin(gzb_ctx* c, int comp_mask, const int* offsets, const uint8_t* cand_idx, const float* cand_err, size_t total) {
-  GZB_TRY(c)
-  if (!c->have_coeffs || !c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_be_begin: coefficients missing");
-  if (comp_mask < 1 || comp_mask > 7 || (c->mode420 && comp_mask != 1 && comp_mask != 6)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_begin: bad comp_mask");
-  if (total >= (size_t(1) << 31)) return fail(c, GZB_ERR_UNSUPPORTED, "gzb_be_begin: too many candidates");
+namespace {
+// the part of gzb_be_begin before / after the candidate lists are in place
+void be_begin_setup(gzb_ctx* c, int comp_mask, int units, size_t total) {
   gzb_ctx::Backend& B = c->be;
-  const int units = zeroing_units(c, comp_mask);
-  const bool resident = offsets == nullptr;
-  if (resident && !(c->packed_valid && c->packed_mask == comp_mask && c->packed_b0 == 0 && c->packed_b1 == units))
-    return fail(c, GZB_ERR_STATE, "gzb_be_begin: no resident candidate lists for this comp_mask");
-  if (!resident && total > 0 && (!cand_idx || !cand_err)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_begin: null candidate arrays");
   be_reserve(c, units, total);
   B.comp_mask = comp_mask;
   B.factor = (c->mode420 && (comp_mask & 6)) ? 2 : 1;
@@ -1781,6 +1774,32 @@ int gzb_be_begin(gzb_ctx* c, int comp_mask, const int* offsets, const uint8_t* c
   B.geom.bw = c->bw;
   B.geom.bh = c->bh;
   B.geom.blk_changed = c->d_blk_changed;
+}
+void be_begin_finish(gzb_ctx* c, int units) {
+  gzb_ctx::Backend& B = c->be;
+  CK(cudaMemsetAsync(B.st, 0, sizeof(BeState), c->stream));
+  CK(cudaMemsetAsync(B.last_index, 0, static_cast<size_t>(units) * 4, c->stream));
+  CK(cudaMemsetAsync(B.max_err, 0, static_cast<size_t>(units) * 4, c->stream));
+  CK(cudaMemsetAsync(B.pcount, 0, static_cast<size_t>(units) * 4, c->stream));
+  sync_check(c);   // the host arrays may be released by the caller
+  B.active = true;
+  B.n = 0;
+}
+}  // namespace
+
+int gzb_be_begin(gzb_ctx* c, int comp_mask, const int* offsets, const uint8_t* cand_idx, const float* cand_err, size_t total) {
+  GZB_TRY(c)
+  if (!c->have_coeffs || !c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_be_begin: coefficients missing");
+  if (comp_mask < 1 || comp_mask > 7 || (c->mode420 && comp_mask != 1 && comp_mask != 6)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_begin: bad comp_mask");
+  if (total >= (size_t(1) << 31)) return fail(c, GZB_ERR_UNSUPPORTED, "gzb_be_begin: too many candidates");
+  gzb_ctx::Backend& B = c->be;
+  const int units = zeroing_units(c, comp_mask);
+  const bool resident = offsets == nullptr;
+  if (resident && !(c->packed_valid && c->packed_mask == comp_mask && c->packed_b0 == 0 && c->packed_b1 == units))
+    return fail(c, GZB_ERR_STATE, "gzb_be_begin: no resident candidate lists for this comp_mask");
+  if (!resident && total > 0 && (!cand_idx || !cand_err)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_begin: null candidate arrays");
+  if (!resident && offsets[units] != static_cast<int>(total)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_begin: offsets[num_blocks] != total");
+  be_begin_setup(c, comp_mask, units, total);
   if (resident) {
     int* d_counts; int* d_offsets; float* d_err; uint8_t* d_idx;
     packed_ptrs(c, &d_counts, &d_offsets, &d_err, &d_idx);
@@ -1790,21 +1809,73 @@ int gzb_be_begin(gzb_ctx* c, int comp_mask, const int* offsets, const uint8_t* c
       CK(cudaMemcpyAsync(B.cand_err, d_err, total * 4, cudaMemcpyDeviceToDevice, c->stream));
     }
   } else {
-    if (offsets[units] != static_cast<int>(total)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_begin: offsets[num_blocks] != total");
     CK(cudaMemcpyAsync(B.cand_off, offsets, (static_cast<size_t>(units) + 1) * 4, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (static_cast<size_t>(units) + 1) * 4;
     if (total) {
       CK(cudaMemcpyAsync(B.cand_idx, cand_idx, total, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += total;
       CK(cudaMemcpyAsync(B.cand_err, cand_err, total * 4, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += total * 4;
     }
   }
-  CK(cudaMemsetAsync(B.st, 0, sizeof(BeState), c->stream));
-  CK(cudaMemsetAsync(B.last_index, 0, static_cast<size_t>(units) * 4, c->stream));
-  CK(cudaMemsetAsync(B.max_err, 0, static_cast<size_t>(units) * 4, c->stream));
-  CK(cudaMemsetAsync(B.pcount, 0, static_cast<size_t>(units) * 4, c->stream));
-  sync_check(c);   // the host arrays may be released by the caller
-  B.active = true;
-  B.n = 0;
+  be_begin_finish(c, units);
   GZB_END(c)
+}
+
+int gzb_be_begin_gathered(gzb_ctx* c, int comp_mask, int world, int rank, const int* global_offsets, const uint64_t* counts,
+                          int (*allgather_device)(void*, const void*, size_t, void*), void* user, int begin, uint8_t* cand_idx_out) {
+  GZB_TRY(c)
+  if (!c->have_coeffs || !c->have_orig_coeffs) return fail(c, GZB_ERR_STATE, "gzb_be_begin_gathered: coefficients missing");
+  if (comp_mask < 1 || comp_mask > 7 || (c->mode420 && comp_mask != 1 && comp_mask != 6)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_begin_gathered: bad comp_mask");
+  if (world < 1 || rank < 0 || rank >= world || !counts || !allgather_device || (begin && !global_offsets))
+    return fail(c, GZB_ERR_BAD_ARG, "gzb_be_begin_gathered: bad argument");
+  const int units = zeroing_units(c, comp_mask);
+  const int b0 = static_cast<int>(static_cast<int64_t>(units) * rank / world), b1 = static_cast<int>(static_cast<int64_t>(units) * (rank + 1) / world);
+  if (!(c->packed_valid && c->packed_mask == comp_mask && c->packed_b0 == b0 && c->packed_b1 == b1))
+    return fail(c, GZB_ERR_STATE, "gzb_be_begin_gathered: no resident candidate lists for this rank's block range");
+  size_t total = 0, maxn = 0;
+  std::vector<size_t> base(static_cast<size_t>(world) + 1, 0);
+  for (int r = 0; r < world; ++r) {
+    maxn = std::max<size_t>(maxn, counts[r]);
+    base[r + 1] = base[r] + counts[r];
+  }
+  total = base[world];
+  if (total >= (size_t(1) << 31)) return fail(c, GZB_ERR_UNSUPPORTED, "gzb_be_begin_gathered: too many candidates");
+  if (begin && global_offsets[units] != static_cast<int>(total)) return fail(c, GZB_ERR_BAD_ARG, "gzb_be_begin_gathered: offsets[num_blocks] != total");
+  // one record per rank: [errors (4 * maxn) | coefficient indices (maxn)], padded to the longest list
+  const size_t rec = (5 * maxn + 255) & ~size_t(255);
+  char* tmp = nullptr;
+  if (rec) CK(cudaMalloc(&tmp, rec * (static_cast<size_t>(world) + 1)));
+  struct Free { char* p; ~Free() { if (p) cudaFree(p); } } guard{tmp};
+  char* d_send = tmp;
+  char* d_recv = tmp ? tmp + rec : nullptr;
+  const size_t n = counts[rank];
+  if (rec) {
+    int* d_counts; int* d_offsets; float* d_err; uint8_t* d_idx;
+    packed_ptrs(c, &d_counts, &d_offsets, &d_err, &d_idx);
+    if (n) {
+      CK(cudaMemcpyAsync(d_send, d_err, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+      CK(cudaMemcpyAsync(d_send + 4 * maxn, d_idx, n, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    sync_check(c);
+    if (allgather_device(user, d_send, rec, d_recv) != 0) return fail(c, GZB_ERR_CUDA, "gzb_be_begin_gathered: the device all-gather failed");
+  }
+  if (begin) {
+    gzb_ctx::Backend& B = c->be;
+    be_begin_setup(c, comp_mask, units, total);
+    CK(cudaMemcpyAsync(B.cand_off, global_offsets, (static_cast<size_t>(units) + 1) * 4, cudaMemcpyHostToDevice, c->stream)); c->h2d_bytes += (static_cast<size_t>(units) + 1) * 4;
+    for (int r = 0; r < world; ++r) {
+      const size_t nr = counts[r];
+      if (!nr) continue;
+      const char* src = d_recv + static_cast<size_t>(r) * rec;
+      CK(cudaMemcpyAsync(B.cand_err + base[r], src, nr * 4, cudaMemcpyDeviceToDevice, c->stream));
+      CK(cudaMemcpyAsync(B.cand_idx + base[r], src + 4 * maxn, nr, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (cand_idx_out && total) { CK(cudaMemcpyAsync(cand_idx_out, B.cand_idx, total, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += total; }
+    be_begin_finish(c, units);
+  }
+  GZB_END(c)
+}
+
+int gzb_test_memcpy_d2d(void* dst, const void* src, size_t nbytes) {
+  return cudaMemcpy(dst, src, nbytes, cudaMemcpyDeviceToDevice) == cudaSuccess ? GZB_OK : GZB_ERR_CUDA;
 }
 
 int gzb_be_build_order(gzb_ctx* c, int direction, double target_mul, float below_limit, uint64_t* n, int* blocks_to_change,

@@ -897,6 +897,13 @@ int gzb_encoder_set_group(gzb_encoder* enc, int rank, int world, gzb_allgather_f
   return GZB_OK;
 }
 
+int gzb_encoder_set_group_device(gzb_encoder* enc, gzb_allgather_device_fn allgather_device) {
+  if (!enc) { g_encode_err = "gzb_encoder_set_group_device: null encoder"; return GZB_ERR_BAD_ARG; }
+  if (enc->e.ran) { g_encode_err = "gzb_encoder_set_group_device: the encoder has already run"; return GZB_ERR_STATE; }
+  enc->e.group.allgather_device = allgather_device;
+  return GZB_OK;
+}
+
 int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb_encode_stats* stats,
                     char** trace_out) {
   if (!enc || !jpeg_out || !jpeg_size) { g_encode_err = "gzb_encoder_run: null argument"; return GZB_ERR_BAD_ARG; }
@@ -998,6 +1005,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
     std::vector<uint8_t> cand_coeffs;
     std::vector<float> cand_errors;   // only a group needs them on the host (for the exchange)
     const int world = shard ? e.group.world : 1, rank = shard ? e.group.rank : 0;
+    bool be_begun = false;   // the device-side exchange leaves the lists in the back end's state
     {
       // In a group a failing rank still takes part in the exchanges and reports its status there, so
       // that all ranks leave together instead of waiting for it inside a collective.
@@ -1012,22 +1020,24 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
       std::vector<int> loc_off(nloc + 1, 0);
       size_t ncand = 0;
       cand_coeffs.resize(static_cast<size_t>(nloc) * 48 + 16);
-      if (world > 1) cand_errors.resize(cand_coeffs.size());
-      // alone, the errors stay on the device (gzb_be_begin picks the packed lists up where they are)
-      float* errs = world > 1 ? cand_errors.data() : nullptr;
+      // alone, or with a device-side exchange, the errors stay on the device (gzb_be_begin / gzb_be_begin_gathered
+      // pick the packed lists up where they are)
+      const bool host_exchange = world > 1 && e.group.allgather_device == nullptr;
+      if (host_exchange) cand_errors.resize(cand_coeffs.size());
+      float* errs = host_exchange ? cand_errors.data() : nullptr;
       if (zrc == GZB_OK && gzb_compute_block_zeroing_candidates_range(e.ctx, comp_mask, b0, b1, loc_off.data(), cand_coeffs.data(), errs,
                                                                       cand_coeffs.size(), &ncand) != GZB_OK) zrc = GZB_ERR_CUDA;
       if (zrc == GZB_OK && ncand > cand_coeffs.size()) {  // more than 48 candidates per block on average: fetch again (no recompute)
         cand_coeffs.resize(ncand);
-        if (world > 1) cand_errors.resize(ncand);
-        errs = world > 1 ? cand_errors.data() : nullptr;
+        if (host_exchange) cand_errors.resize(ncand);
+        errs = host_exchange ? cand_errors.data() : nullptr;
         if (gzb_compute_block_zeroing_candidates_range(e.ctx, comp_mask, b0, b1, loc_off.data(), cand_coeffs.data(), errs, ncand,
                                                        &ncand) != GZB_OK) zrc = GZB_ERR_CUDA;
       }
       if (zrc != GZB_OK) { ncand = 0; std::fill(loc_off.begin(), loc_off.end(), 0); g_encode_err = gzb_last_error(e.ctx); }
       if (zrc != GZB_OK && world == 1) return zrc;
       cand_coeffs.resize(ncand);
-      if (world > 1) cand_errors.resize(ncand);
+      if (host_exchange) cand_errors.resize(ncand);
       e.st.device_zeroing_ms += gzb_last_device_ms(e.ctx);
       if (world == 1) {
         cand_offsets = loc_off;
@@ -1066,6 +1076,18 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           for (int b = rb0; b < rb1; ++b) cand_offsets[b] = static_cast<int>(base[r]) + ro[b - rb0];
         }
         cand_offsets[num_blocks] = static_cast<int>(total);
+        if (!host_exchange) {
+          // all-gather 2 on the devices: the lists go from GPU to GPU and become the back end's on rank 0, whose
+          // host only needs the coefficient indices
+          std::vector<uint64_t> counts(world);
+          for (int r = 0; r < world; ++r) counts[r] = base[r + 1] - base[r];
+          if (rank == 0) cand_coeffs.resize(total);
+          int grc = gzb_be_begin_gathered(e.ctx, comp_mask, world, rank, cand_offsets.data(), counts.data(), e.group.allgather_device,
+                                          e.group.user, rank == 0 ? 1 : 0, rank == 0 ? cand_coeffs.data() : nullptr);
+          // (a rank that fails here has already taken part in the collective or made it fail for everybody)
+          if (grc != GZB_OK) return fail(GZB_ERR_CUDA);
+          be_begun = true;
+        } else {
         // all-gather 2: the packed candidates, [errors | coefficient indices], padded to the longest
         const size_t rec = maxn * 5;
         std::vector<uint8_t> send(rec + 1, 0), all(static_cast<size_t>(world) * (rec + 1));
@@ -1083,6 +1105,7 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
           memcpy(cand_errors.data() + base[r], src, n * sizeof(float));
           memcpy(cand_coeffs.data() + base[r], src + maxn * 4, n);
         }
+        }
       }
       e.st.zeroing_wall_ms += now_ms() - t0;
       gzb_finish_block_comparisons(e.ctx);
@@ -1090,7 +1113,8 @@ int gzb_encoder_run(gzb_encoder* enc, uint8_t** jpeg_out, size_t* jpeg_size, gzb
 
     // The back end is one sequential walk: rank 0 of a group finishes the image alone.
     if (rank != 0) return 1;
-    if (world > 1 && gzb_be_begin(e.ctx, comp_mask, cand_offsets.data(), cand_coeffs.data(), cand_errors.data(), cand_coeffs.size()) != GZB_OK)
+    if (world > 1 && !be_begun &&
+        gzb_be_begin(e.ctx, comp_mask, cand_offsets.data(), cand_coeffs.data(), cand_errors.data(), cand_coeffs.size()) != GZB_OK)
       return fail(GZB_ERR_CUDA);
     std::vector<float>().swap(cand_errors);
 

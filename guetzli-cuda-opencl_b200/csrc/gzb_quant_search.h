@@ -112,6 +112,8 @@ struct Group {
   int rank = 0, world = 1;
   AllGatherFn allgather = nullptr;
   void* user = nullptr;
+  // optional: all-gather of device memory, for the bulky exchange of the zeroing candidates (gzb_allgather_device_fn)
+  int (*allgather_device)(void* user, const void* d_send, size_t nbytes, void* d_recv) = nullptr;
 };
 
 // One TryQuantMatrix-like trial: the q=1 "original" written with the input's tables

@@ -226,6 +226,16 @@ int gzb_be_begin(gzb_ctx* ctx, int comp_mask, const int* offsets, const uint8_t*
  * the order is non-empty, then global_order in the reference's arrangement, on the device.
  * *n = global_order.size(), *below = entries with value < below_limit (the partition_point of the
  * first "up" iteration, processor.cc:840-848), *rblock = the radius used (4 if the order stayed empty). */
+/* gzb_be_begin for rank `rank` of a group of `world` contexts that each hold the resident candidate lists of
+ * their own block range [units * r / world, units * (r + 1) / world) (gzb_compute_block_zeroing_candidates_range):
+ * the lists are all-gathered on the devices through `allgather_device` (counts[r] = candidates of rank r,
+ * global_offsets[units + 1] = the offsets of the concatenation) and, on the ranks with begin != 0, become the
+ * back end's lists; cand_idx_out (optional, sum(counts) bytes) receives the coefficient indices for the host. */
+int gzb_be_begin_gathered(gzb_ctx* ctx, int comp_mask, int world, int rank, const int* global_offsets,
+                          const uint64_t* counts, int (*allgather_device)(void*, const void*, size_t, void*),
+                          void* user, int begin, uint8_t* cand_idx_out);
+/* Test hook: cudaMemcpy device to device (a thread-group stand-in for the device all-gather). */
+int gzb_test_memcpy_d2d(void* dst, const void* src, size_t nbytes);
 int gzb_be_build_order(gzb_ctx* ctx, int direction, double target_mul, float below_limit, uint64_t* n,
                        int* blocks_to_change, uint64_t* below, int* rblock);
 /* One step of the lazy std::sort. Pending ranges that end at or before p_set are dropped unsorted (their
@@ -413,6 +423,15 @@ int gzb_encoder_set_params(gzb_encoder* enc, int try_420, int force_420);
  * number of times with the same sizes on every rank. Call before gzb_encoder_run. */
 typedef int (*gzb_allgather_fn)(void* user, const void* send, size_t nbytes, void* recv);
 int gzb_encoder_set_group(gzb_encoder* enc, int rank, int world, gzb_allgather_fn allgather, void* user);
+/* Optional second exchange function for the group, for the one bulky exchange (the zeroing candidates: 5 bytes
+ * per candidate, tens of MB at 12 MPix): an all-gather of DEVICE memory -- nbytes at d_send on this rank's GPU
+ * into d_recv (world * nbytes, rank order) -- e.g. ncclAllGather on the caller's communicator or
+ * torch.distributed.all_gather_into_tensor on tensors that alias the pointers. The library has synchronised
+ * its own stream before the call; the function returns when d_recv is complete. With it the candidate lists go
+ * from GPU to GPU over NVLink and never visit the host; without it they are staged through `allgather`. `user`
+ * is the pointer given to gzb_encoder_set_group. Call after gzb_encoder_set_group. */
+typedef int (*gzb_allgather_device_fn)(void* user, const void* d_send, size_t nbytes, void* d_recv);
+int gzb_encoder_set_group_device(gzb_encoder* enc, gzb_allgather_device_fn allgather_device);
 void gzb_encoder_destroy(gzb_encoder* enc);
 const char* gzb_encode_last_error(void);
 void gzb_free(void* p);

@@ -8,6 +8,7 @@ import json
 import os
 import re
 
+import ctypes as C
 import numpy as np
 import pytest
 
@@ -123,7 +124,27 @@ def test_compare_block_single_equals_batched(gz):
     c.close()
 
 
-def run_thread_group(gz, img, target, world, **params):
+class BarrierDeviceAllGather:
+    """gzb_allgather_device_fn for ranks that are threads on ONE GPU: every rank publishes its send pointer, then
+    copies all of them into its own receive buffer (device to device)."""
+    def __init__(self, world, lib):
+        import threading
+        self.world, self.slots, self.bar, self.lib, self.calls = world, [None] * world, threading.Barrier(world), lib, 0
+        lib.gzb_test_memcpy_d2d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+
+    def for_rank(self, r):
+        def fn(d_send, nbytes, d_recv):
+            self.slots[r] = d_send
+            self.bar.wait()
+            for k in range(self.world):
+                assert self.lib.gzb_test_memcpy_d2d(d_recv + k * nbytes, self.slots[k], nbytes) == 0
+            if r == 0:
+                self.calls += 1
+            self.bar.wait()
+        return fn
+
+
+def run_thread_group(gz, img, target, world, device_exchange=None, **params):
     """`world` encoders of the same image as the ranks of a group, one host thread each, on the one
     GPU of the test box (the exchange is a thread barrier; across GPUs it is NCCL, bench.py)."""
     import threading
@@ -134,7 +155,7 @@ def run_thread_group(gz, img, target, world, **params):
     def work(r):
         try:
             enc = gz.Encoder(img, target, host_threads=2, **params)
-            enc.set_group(r, world, ag.for_rank(r))
+            enc.set_group(r, world, ag.for_rank(r), device_exchange.for_rank(r) if device_exchange else None)
             res[r] = enc.run(want_trace=True)
             enc.close()
         except Exception as e:  # a dead rank would leave the others at the barrier
@@ -167,6 +188,25 @@ def test_group_encode_equals_single_gpu_encode(gz, world):
     quant_trials = sum(1 for l in gold["trace"] if "GQ[" in l) + 1
     assert st["search_rounds"] < quant_trials        # fewer serial rounds than trials
     assert sum(r[1]["num_compares"] for r in res[1:]) > 0   # the other ranks did evaluate trials
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_group_encode_with_device_side_candidate_exchange(gz, world):
+    """gzb_encoder_set_group_device: the zeroing candidates are all-gathered on the device(s) and become the back
+    end's lists without visiting the host. Same bytes; also for the YUV420 branch (luma pass sharded)."""
+    gold = json.load(open(os.path.join(GOLD, "synth_encodes.json")))["160x120_q95_s1244"]
+    img = synth_image(160, 120, 1244)
+    dx = BarrierDeviceAllGather(world, gz.lib())
+    res = run_thread_group(gz, img, np.float32(gold["target"]), world, device_exchange=dx)
+    assert hashlib.sha256(res[0][0]).hexdigest() == gold["sha256"]
+    assert dx.calls == 1
+    for r in range(1, world):
+        assert res[r][0] == b""
+    single = gz.Process(img, np.float32(gold["target"]), try_420=True)[0]
+    dx = BarrierDeviceAllGather(world, gz.lib())
+    res = run_thread_group(gz, img, np.float32(gold["target"]), world, device_exchange=dx, try_420=True)
+    assert res[0][0] == single
+    assert dx.calls == 2   # the 4:4:4 pass and the luma pass of the 4:2:0 branch
 
 
 def test_group_encode_bees_golden(gz):
