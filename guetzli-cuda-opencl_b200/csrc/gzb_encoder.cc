@@ -762,6 +762,43 @@ void gzb_test_host_lazy(int* first, float* second, size_t n, size_t p) {
   while (lz.advance()) {}
   for (size_t i = 0; i < n; ++i) { first[i] = lz.buf[i].first; second[i] = lz.buf[i].second; }
 }
+// The multi-range hand-over on the host side: the restated partition plays the device (leftmost first, right-hand
+// ranges pending, down to small_max), and the short ranges are given to HostLazy `group` consecutive ones at a time
+// (HostLazy::reset_ranges), the first group with the prefix p split off as a set.
+void gzb_test_host_lazy_ranges(int* first, float* second, size_t n, size_t p, size_t small_max, int group) {
+  std::vector<OrderEntry> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = std::make_pair(first[i], second[i]);
+  typedef exact_sort::HostLazy::R R;
+  std::vector<R> pending, small;
+  if (n > 0) pending.push_back({0, n, exact_sort::depth_budget(n)});
+  while (!pending.empty()) {
+    R r = pending.back();
+    pending.pop_back();
+    if (r.last <= p) continue;   // consumed as a set
+    if (r.last - r.first <= std::max<size_t>(small_max, 16) || r.depth == 0) { small.push_back(r); continue; }
+    --r.depth;
+    const size_t cut = static_cast<size_t>(exact_sort::partition_pivot(v.data() + r.first, v.data() + r.last) - v.data());
+    pending.push_back({cut, r.last, r.depth});
+    pending.push_back({r.first, cut, r.depth});
+  }
+  size_t have_end = p;
+  for (size_t g = 0; g < small.size();) {
+    size_t ge = g + 1;
+    while (ge < small.size() && static_cast<int>(ge - g) < group && small[ge].first == small[ge - 1].last) ++ge;
+    const size_t rf = small[g].first, rl = small[ge - 1].last;
+    exact_sort::HostLazy lz;
+    lz.buf.assign(v.begin() + rf, v.begin() + rl);
+    std::vector<R> rel;
+    for (size_t k = g; k < ge; ++k) rel.push_back({small[k].first - rf, small[k].last - rf, small[k].depth});
+    lz.reset_ranges(rel.data(), static_cast<int>(rel.size()));
+    if (have_end > rf) lz.split_set(have_end - rf);
+    while (lz.advance()) {}
+    std::copy(lz.buf.begin(), lz.buf.end(), v.begin() + rf);
+    have_end = rl;
+    g = ge;
+  }
+  for (size_t i = 0; i < n; ++i) { first[i] = v[i].first; second[i] = v[i].second; }
+}
 int gzb_test_sort_emulation_ok(void) { return exact_sort::emulation_ok() ? 1 : 0; }
 // Test hook (GPU): sorts `entries` through the back end's device path -- long ranges partitioned by
 // k_be_select, short ones finished by exact_sort -- optionally consuming [0, prefix) as a set first (those

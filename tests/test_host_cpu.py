@@ -161,6 +161,26 @@ def test_host_lazy_sort_of_a_short_range(gz):
                 assert np.array_equal(np.sort(b_id[:pfx]), np.sort(a_id[:pfx])), (n, pfx)
 
 
+def test_host_lazy_sort_of_several_ranges_per_round_trip(gz):
+    """gzb_be_select_ranges hands over up to 16 consecutive short ranges at once (HostLazy::reset_ranges): the
+    restated partition plays the device here. Everything from the prefix on must be std::sort's arrangement."""
+    L = gz.lib()
+    L.gzb_test_host_lazy_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
+    L.gzb_test_std_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(23)
+    for n in [1, 17, 500, 5000, 40000]:
+        for v in _sort_cases(rng, n):
+            ids = np.arange(n, dtype=np.int32)
+            a_id, a_v = ids.copy(), v.copy()
+            L.gzb_test_std_sort(p(a_id), p(a_v), n)
+            for pfx in sorted({0, n // 3, max(0, n - 10)}):
+                for small, group in ((16, 16), (100, 3), (1024, 16), (1024, 1)):
+                    b_id, b_v = ids.copy(), v.copy()
+                    L.gzb_test_host_lazy_ranges(p(b_id), p(b_v), n, pfx, small, group)
+                    assert np.array_equal(b_id[pfx:], a_id[pfx:]) and np.array_equal(b_v[pfx:], a_v[pfx:]), (n, pfx, small, group)
+                    assert np.array_equal(np.sort(b_id[:pfx]), np.sort(a_id[:pfx])), (n, pfx, small, group)
+
+
 def test_restated_heap_sort_equals_std_partial_sort(gz):
     """The fallback of introsort when the depth budget runs out: std::__partial_sort(first, last, last)."""
     L = gz.lib()
