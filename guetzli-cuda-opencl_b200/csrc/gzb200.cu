@@ -616,7 +616,12 @@ void run_diffmap(gzb_ctx* c, const float* xyb0, const float* xyb1) {
   } else {
     KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_diff_map<<<ctas, 32 * kBdmWarps, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, c->d_ac, dmask(c, DS_BDM), bc));
   }
-  KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_dc<<<(cells + 127) / 128, 128, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, dmask(c, DS_BDM), bc));
+  static const int dc_rows_env = getenv("GZB_BDC_ROWS") ? atoi(getenv("GZB_BDC_ROWS")) : 1;
+  if (dc_rows_env) {
+    KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_dc_rows<<<dim3((ncx + kBdcCells - 1) / kBdcCells, ncy), kBdcThreads, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, dmask(c, DS_BDM), bc));
+  } else {
+    KLAUNCH_S(c, sb, KC_BLOCK_DIFF, k_block_dc<<<(cells + 127) / 128, 128, 0, sb>>>(m0, m1, c->ps, W, H, P, c->rxs, ncx, ncy, c->d_dc, dmask(c, DS_BDM), bc));
+  }
   if (c->concurrent) CK(cudaEventRecord(c->ev_bdm, sb));
   // EdgeDetectorLowFreq (its blur scratch is the first part of d_tmp, the main stream's the rest)
   run_blur(c, c->p_lf, c->d_mh, c->ps, 6, c->d_lf, c->lf_stride, c->p_lf.g.tmp_pitch, sl, c->d_tmp, dmask(c, DS_LFH), dmask(c, DS_LFV));

@@ -1093,6 +1093,73 @@ k_block_dc(const float* __restrict__ a, const float* __restrict__ b, size_t stri
   for (int c = 0; c < 3; ++c) o[c] = static_cast<float>(sq[c]);
 }
 
+// K6b': the same DC term, a CTA per 64 horizontally adjacent cells. Cells are 3 px apart and their windows 8 px
+// wide, so a sample is read by 8/3 cells of a row: the CTA loads the 8 image rows under its cells once (coalesced),
+// keeps the half-differences (a - b) / 2 of the three channels as doubles in shared memory -- two conversions
+// per SAMPLE instead of per term -- and one thread per (cell, channel) adds its 64 in the reference's order.
+constexpr int kBdcCells = 64, kBdcThreads = 224;   // >= the 197 samples of a row and >= 3 x 64 sums
+constexpr int kBdcWidth = 3 * (kBdcCells - 1) + 8;   // 197 samples under 64 cells
+constexpr int kBdcPitch = kBdcWidth + 1;             // (cells are 3 doubles apart: any pitch keeps 16 lanes on 16 bank pairs)
+__global__ void __launch_bounds__(kBdcThreads)
+k_block_dc_rows(const float* __restrict__ a, const float* __restrict__ b, size_t stride, int W, int H, int P,
+                int rxs, int ncx, int ncy, float* __restrict__ dc_out, DirtyMask dm, BlockChanges bc) {
+  __shared__ double s_hd[3][8][kBdcPitch];
+  __shared__ double s_m[3][kBdcCells];
+  __shared__ unsigned char s_need[kBdcCells];
+  const int tid = threadIdx.x;
+  const int ry = blockIdx.y, rx0 = blockIdx.x * kBdcCells;
+  const int ncell = min(kBdcCells, ncx - rx0);
+  const int oy = min(3 * ry, H - 8), x_lo = min(3 * rx0, W - 8);
+  const bool fine = bc.chg != nullptr && *bc.enable != 0;
+  bool need = false;
+  if (tid < kBdcCells) {
+    if (tid < ncell) {
+      const int rx = rx0 + tid, ox = min(3 * rx, W - 8);
+      need = dirty_at(dm, 3 * rx, 3 * ry) && (!fine || cell_window_changed(bc, ox, oy));
+    }
+    s_need[tid] = need ? 1 : 0;
+  }
+  if (!__syncthreads_or(need ? 1 : 0)) return;
+  const int wid = min(3 * (rx0 + ncell - 1), W - 8) + 8 - x_lo;   // samples under the CTA's cells
+  // half-differences of the three channels: 24 rows of wid samples, a thread per sample of a row
+  if (tid < wid) {
+    const float* pa = a + static_cast<size_t>(oy) * P + x_lo + tid;
+    const float* pb = b + static_cast<size_t>(oy) * P + x_lo + tid;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int y = 0; y < 8; ++y) {
+        const size_t g = c * stride + static_cast<size_t>(y) * P;
+        s_hd[c][y][tid] = (static_cast<double>(__ldg(pa + g)) - static_cast<double>(__ldg(pb + g))) / 2;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int cell = tid % kBdcCells, c = tid / kBdcCells;
+    if (c < 3 && cell < ncell && s_need[cell]) {
+      const int x0 = min(3 * (rx0 + cell), W - 8) - x_lo;
+      double acc = 0.0;
+#pragma unroll 1
+      for (int y = 0; y < 8; ++y) {
+        const double* r = &s_hd[c][y][x0];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) acc += r[x];
+      }
+      s_m[c][cell] = acc / 32;
+    }
+  }
+  __syncthreads();
+  if (tid < ncell && s_need[tid]) {
+    const double m[3] = {s_m[0][tid], s_m[1][tid], s_m[2][tid]};
+    double sq[3] = {0.0, 0.0, 0.0};
+    lowfreq_sq_acc0(m, kCsf8x8[0], sq);
+    float* o = dc_out + 3 * (static_cast<size_t>(ry) * rxs + rx0 + tid);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = static_cast<float>(sq[c]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K7: EdgeDetectorLowFreq consumer (butteraugli.cc:1164-1204). Reads the decimated sigma-14 maps:
 // blurred[y][x] == small[y/4][x/4]. One lattice point per thread. The reference adds the term into
