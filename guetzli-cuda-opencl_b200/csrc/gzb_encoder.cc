@@ -146,7 +146,7 @@ using gzb::quant_data_better;
 // libstdc++ build, whose std::sort is introsort: median-of-three + unguarded Hoare partitioning down to
 // ranges of 16 with a depth budget of 2 * floor(log2(n)), heap sort when the budget runs out, one final
 // insertion sort. The long ranges are partitioned on the device with the same element movements
-// (gzb_backend.cuh: k_be_select); the short ranges it hands back are finished here. This is a
+// (gzb_backend.cuh: k_be_tiles_* / k_be_swap / k_be_local); the short ranges it hands back are finished here. This is a
 // restatement of the algorithm, not a call into the library's private functions; sort_emulation_ok()
 // checks it once per process against the std::sort this library was built with and the driver falls back
 // to sorting the whole order with std::sort itself when they disagree (a different standard library).
@@ -801,7 +801,7 @@ void gzb_test_host_lazy_ranges(int* first, float* second, size_t n, size_t p, si
 }
 int gzb_test_sort_emulation_ok(void) { return exact_sort::emulation_ok() ? 1 : 0; }
 // Test hook (GPU): sorts `entries` through the back end's device path -- long ranges partitioned by
-// k_be_select, short ones finished by exact_sort -- optionally consuming [0, prefix) as a set first (those
+// the k_be_* kernels, short ones finished by exact_sort -- optionally consuming [0, prefix) as a set first (those
 // entries come back in unspecified order). Everything from `prefix` on must equal std::sort's arrangement.
 int gzb_test_device_sort_depth(gzb_ctx* ctx, gzb_order_entry* entries, size_t n, size_t prefix, int small_max, int depth);
 int gzb_test_device_sort(gzb_ctx* ctx, gzb_order_entry* entries, size_t n, size_t prefix, int small_max) {

@@ -1,6 +1,6 @@
 """The device side of SelectFrequencyBackEnd (csrc/gzb_backend.cuh) on its own.
 
-k_be_select must move the entries of the order exactly like libstdc++'s std::sort does (median-of-three,
+The partition kernels (k_be_tiles_*, k_be_swap, k_be_local) must move the entries of the order exactly like libstdc++'s std::sort does (median-of-three,
 unguarded Hoare partition): the reference sorts `global_order` with it (guetzli/processor.cc:825-828) and
 ties between different blocks are common, so which of the tied entries ends up inside the consumed part
 decides the output bytes. Checker: std::sort itself (gzb_test_std_sort), bit-exact."""
